@@ -1,0 +1,2 @@
+"""syncvsr_b200: B200-native (sm_100a) implementation of the SyncVSR dense forward/backward hot path."""
+__version__ = "0.1.0"

@@ -1,0 +1,316 @@
+// tcgen05 implicit-GEMM kernel (see igemm.cuh). Warp roles (192 threads):
+//   warp 0    : TMA producer  (one elected lane)
+//   warp 1    : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2-5 : epilogue, one TMEM lane-quarter each (warp_id % 4 selects the quarter tcgen05.ld may touch)
+#include "igemm.cuh"
+#include "tmap.h"
+
+namespace svsr {
+
+struct IgemmKParams {
+  int tiles_h, tiles_w;
+  int bn, bh, bw;
+  int o_N, OH, OW;
+  int stride;
+  int ntaps, cblocks;
+  int a_coff;
+  int a_box_bytes;
+  int tap_dh[IGEMM_MAX_TAPS];
+  int tap_dw[IGEMM_MAX_TAPS];
+  int tap_kbase[IGEMM_MAX_TAPS];
+  void* out;
+  const float* bias;
+  const void* resid;
+  int out_fp32, resid_fp32;
+  int ldc, c_off;
+  int o_H, o_W, o_sh, o_sw, o_oh, o_ow;
+  int n_cols;
+  float alpha;
+};
+
+template <int BN, int STAGES>
+struct IgemmSmem {
+  static constexpr int A_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16 (one 128B swizzle row each)
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmKParams p) {
+  using L = IgemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile -> (image block, row block, col block) of the logical output grid
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int tw = mt % p.tiles_w;
+  const int th = (mt / p.tiles_w) % p.tiles_h;
+  const int tn = mt / (p.tiles_w * p.tiles_h);
+  const int n0 = tn * p.bn, oh0 = th * p.bh, ow0 = tw * p.bw;
+  const int num_kb = p.ntaps * p.cblocks;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int tap = kb / p.cblocks;
+        const int cc = kb - tap * p.cblocks;
+        uint8_t* sA = smem + stage * L::STAGE_BYTES;
+        uint8_t* sB = sA + L::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + L::B_BYTES));
+        tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
+                    oh0 * p.stride + p.tap_dh[tap], n0);
+        tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+        const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t b_desc = umma_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // accumulator row == pixel slot in the box
+    const int hw = p.bh * p.bw;
+    const int dn = r / hw;
+    const int rem = r - dn * hw;
+    const int dh = rem / p.bw;
+    const int dw = rem - dh * p.bw;
+    const int n = n0 + dn, oh = oh0 + dh, ow = ow0 + dw;
+    const bool row_valid = (r < p.bn * hw) && (n < p.o_N) && (oh < p.OH) && (ow < p.OW);
+    const long long pix =
+        ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
+    const long long row_off = pix * p.ldc + p.c_off;
+
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+      tmem_ld_wait();
+      const int col0 = nt * BN + ch * 32;
+      if (!row_valid || col0 >= p.n_cols) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.n_cols) f[j] += __ldg(p.bias + col0 + j);
+      }
+      const bool full_chunk = (col0 + 32 <= p.n_cols);
+      if (p.resid) {
+        if (p.resid_fp32) {
+          const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = reinterpret_cast<const float4*>(rp)[j];
+              f[4 * j] += t.x, f[4 * j + 1] += t.y, f[4 * j + 2] += t.z, f[4 * j + 3] += t.w;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += rp[j];
+          }
+        } else {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + row_off + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 t = reinterpret_cast<const uint4*>(rp)[j];
+              float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+              f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += b.x, f[8 * j + 3] += b.y;
+              f[8 * j + 4] += c.x, f[8 * j + 5] += c.y, f[8 * j + 6] += d.x, f[8 * j + 7] += d.y;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += __bfloat162float(rp[j]);
+          }
+        }
+      }
+      if (p.out_fp32) {
+        float* op = reinterpret_cast<float*>(p.out) + row_off + col0;
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = f[j];
+        }
+      } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 t;
+            t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            reinterpret_cast<uint4*>(op)[j] = t;
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = __float2bfloat16(f[j]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+void igemm_choose_box(int o_N, int OH, int OW, int* pbn, int* pbh, int* pbw) {
+  long long best_tiles = -1;
+  int best[3] = {1, 1, 1};
+  for (int bw = 1; bw <= OW && bw <= 128; ++bw) {
+    for (int bh = 1; bh <= OH && bh * bw <= 128; ++bh) {
+      int bn = 1;
+      if (bh == OH && bw == OW) bn = 128 / (OH * OW);
+      if (bn > o_N) bn = o_N;
+      if (bn > 128) bn = 128;
+      if (bn < 1) bn = 1;
+      long long tiles = (long long)((o_N + bn - 1) / bn) * ((OH + bh - 1) / bh) * ((OW + bw - 1) / bw);
+      if (best_tiles < 0 || tiles < best_tiles) {
+        best_tiles = tiles;
+        best[0] = bn, best[1] = bh, best[2] = bw;
+      }
+    }
+  }
+  *pbn = best[0], *pbh = best[1], *pbw = best[2];
+}
+
+template <int BN, int STAGES>
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmKParams& kp, dim3 grid,
+                    cudaStream_t stream) {
+  using L = IgemmSmem<BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL));
+    attr_done = true;
+  }
+  igemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, kp);
+  SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+
+int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
+  SVSR_REQUIRE(p.a && p.b && p.out, "igemm: null operand");
+  SVSR_REQUIRE(p.cin > 0 && p.cin % 64 == 0, "igemm: cin=%d must be a positive multiple of 64", p.cin);
+  SVSR_REQUIRE(p.a_C % 8 == 0 && p.a_coff % 8 == 0, "igemm: A channel pitch/offset must be multiples of 8");
+  SVSR_REQUIRE(p.b_cols % 8 == 0, "igemm: B pitch %d must be a multiple of 8", p.b_cols);
+  SVSR_REQUIRE(p.ntaps >= 1 && p.ntaps <= IGEMM_MAX_TAPS, "igemm: ntaps=%d out of range", p.ntaps);
+  SVSR_REQUIRE(p.ldc % 8 == 0 && p.c_off % 8 == 0, "igemm: output pitch/offset must be multiples of 8");
+  SVSR_REQUIRE(p.stride == 1 || p.stride == 2, "igemm: stride must be 1 or 2");
+
+  IgemmKParams kp{};
+  igemm_choose_box(p.o_N, p.OH, p.OW, &kp.bn, &kp.bh, &kp.bw);
+  kp.tiles_h = (p.OH + kp.bh - 1) / kp.bh;
+  kp.tiles_w = (p.OW + kp.bw - 1) / kp.bw;
+  const int tiles_n = (p.o_N + kp.bn - 1) / kp.bn;
+  kp.o_N = p.o_N, kp.OH = p.OH, kp.OW = p.OW;
+  kp.stride = p.stride;
+  kp.ntaps = p.ntaps;
+  kp.cblocks = p.cin / 64;
+  kp.a_coff = p.a_coff;
+  kp.a_box_bytes = kp.bn * kp.bh * kp.bw * 128;
+  for (int t = 0; t < p.ntaps; ++t) {
+    kp.tap_dh[t] = p.tap_dh[t];
+    kp.tap_dw[t] = p.tap_dw[t];
+    kp.tap_kbase[t] = p.tap_kbase[t];
+  }
+  kp.out = p.out, kp.bias = p.bias, kp.resid = p.resid;
+  kp.out_fp32 = p.out_fp32, kp.resid_fp32 = p.resid_fp32;
+  kp.ldc = p.ldc, kp.c_off = p.c_off;
+  kp.o_H = p.o_H, kp.o_W = p.o_W, kp.o_sh = p.o_sh, kp.o_sw = p.o_sw, kp.o_oh = p.o_oh, kp.o_ow = p.o_ow;
+  kp.n_cols = p.b_rows;
+  kp.alpha = p.alpha;
+
+  // A: [a_N, a_H, a_W, a_C] NHWC, box = (64 ch, bw, bh, bn) pixels, traversal stride for strided convs.
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p.a_C, (uint64_t)p.a_W, (uint64_t)p.a_H, (uint64_t)p.a_N};
+    uint64_t strides[3] = {(uint64_t)p.a_C * 2, (uint64_t)p.a_W * p.a_C * 2, (uint64_t)p.a_H * p.a_W * p.a_C * 2};
+    uint32_t box[4] = {64, (uint32_t)((kp.bw - 1) * p.stride + 1), (uint32_t)((kp.bh - 1) * p.stride + 1),
+                       (uint32_t)kp.bn};
+    uint32_t es[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
+    int rc = make_tmap_bf16(&tmA, p.a, 4, dims, strides, box, es, true);
+    if (rc) return rc;
+  }
+  int BN = p.b_rows <= 64 ? 64 : (p.b_rows <= 128 ? 128 : 256);
+  {
+    uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
+    uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tmB, p.b, 2, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)(tiles_n * kp.tiles_h * kp.tiles_w), (unsigned)((p.b_rows + BN - 1) / BN));
+  switch (BN) {
+    case 64: return launch_t<64, 4>(tmA, tmB, kp, grid, stream);
+    case 128: return launch_t<128, 3>(tmA, tmB, kp, grid, stream);
+    default: return launch_t<256, 4>(tmA, tmB, kp, grid, stream);
+  }
+}
+
+}  // namespace svsr

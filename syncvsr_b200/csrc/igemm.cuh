@@ -1,0 +1,52 @@
+// Implicit-GEMM on tcgen05 tensor cores (sm_100a): D[pixels, N] = sum_taps A_shift(tap)[pixels, Cin] * B[N, tap*Cin]^T
+//   * A = NHWC bf16 activation tensor, fetched tap by tap with 4-D tiled TMA (out-of-bounds = zero padding,
+//     element strides give strided convolutions) -- no im2col buffer ever exists.
+//   * B = bf16 weight matrix [N_total, K_total], K contiguous, fetched with 2-D TMA.
+//   * accumulators live in TMEM; a 4-warp epilogue applies bias / residual and stores NHWC bf16 or fp32.
+// A dense GEMM is the degenerate case of one tap on a [M,1,1,K] "image".
+#pragma once
+#include "common.cuh"
+
+namespace svsr {
+
+constexpr int IGEMM_MAX_TAPS = 16;
+
+// Host-side problem description. All channel counts are in elements (bf16).
+struct IgemmProblem {
+  // ---- A operand (activations), NHWC ----
+  const void* a = nullptr;
+  int a_N = 0, a_H = 1, a_W = 1;  // images, rows, cols of the tensor A lives in
+  int a_C = 0;                    // channels per pixel as laid out in memory (pixel pitch)
+  int a_coff = 0;                 // first contracted channel
+  int cin = 0;                    // contracted channels per tap (multiple of 64)
+  int stride = 1;                 // input coordinate = output coordinate * stride + tap offset
+  // ---- taps ----
+  int ntaps = 1;
+  int tap_dh[IGEMM_MAX_TAPS] = {0};
+  int tap_dw[IGEMM_MAX_TAPS] = {0};
+  int tap_kbase[IGEMM_MAX_TAPS] = {0};  // column of B where this tap's cin block starts
+  // ---- logical output grid that the M dimension enumerates ----
+  int o_N = 0, OH = 1, OW = 1;
+  // ---- B operand ----
+  const void* b = nullptr;
+  int b_rows = 0;  // N_total (valid output columns)
+  int b_cols = 0;  // K_total (row pitch of B, multiple of 8)
+  // ---- output tensor: pixel (n, oh*o_sh+o_oh, ow*o_sw+o_ow) of a [o_N, o_H, o_W, ldc] tensor ----
+  void* out = nullptr;
+  int out_fp32 = 0;
+  int ldc = 0;    // elements per output pixel (pitch)
+  int c_off = 0;  // first output channel
+  int o_H = 1, o_W = 1, o_sh = 1, o_sw = 1, o_oh = 0, o_ow = 0;
+  // ---- epilogue ----
+  const float* bias = nullptr;  // [b_rows] fp32 or null
+  const void* resid = nullptr;  // same geometry as out (pitch ldc, offset c_off), or null
+  int resid_fp32 = 0;
+  float alpha = 1.0f;  // out = alpha*acc (+bias) (+resid)
+};
+
+int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
+
+// Chooses the pixel box (bn, bh, bw) with bn*bh*bw <= 128 that wastes the fewest MMA rows.
+void igemm_choose_box(int o_N, int OH, int OW, int* bn, int* bh, int* bw);
+
+}  // namespace svsr
