@@ -43,6 +43,27 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
 int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
 
+/* dx[N,H,W,Cin] = conv2d input-gradient of dy[N,OH,OW,Cout]; wd is the weight packed for dgrad as
+ * [Cin, R*S*Cout] bf16 (column (r*S+s)*Cout+co holds W[co][ci][r][s]). If resid != NULL it is added (it may alias
+ * dx: gradient accumulation of the residual branch). For stride 2 the four output-parity classes are issued as
+ * four launches; pixels no tap reaches (1x1 stride-2) are left untouched, so dx must be pre-zeroed in that case.
+ * Replaces autograd's conv backward-data for resnet.layer1-4 (lightning.py:114-117). */
+int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                      int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
+
+/* dw[R*S*Cin, Cout] (fp32, += accumulate) = weight gradient of conv2d: row (r*S+s)*Cin+ci, column co.
+ * x[N,H,W,Cin], dy[N,OH,OW,Cout] bf16. Replaces autograd's conv backward-weight. */
+int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                      int stride, int pad, void* stream);
+
+/* dw[N,K] (fp32, pitch ldw, += accumulate) = dy[M,N]^T . x[M,K]; dy, x bf16 with pitches ldy, ldx.
+ * Replaces autograd's Linear backward-weight. N % 64 == 0. */
+int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,
+                    void* stream);
+
+/* Developer hardware probe (see csrc/debug_probe.cu); not part of the product path. */
+int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,11 @@
 #include "../../include/svsr.h"
 #include "common.cuh"
 #include "igemm.cuh"
+#include "wgrad.cuh"
+
+namespace svsr {
+int debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, cudaStream_t stream);
+}
 
 using namespace svsr;
 
@@ -42,6 +47,69 @@ int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, 
   p.o_H = OH, p.o_W = OW;
   p.resid = resid;
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                      int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream) {
+  SVSR_REQUIRE(R * S <= IGEMM_MAX_TAPS, "dgrad: %dx%d filter has too many taps", R, S);
+  SVSR_REQUIRE(stride == 1 || stride == 2, "dgrad: stride must be 1 or 2");
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+  for (int a = 0; a < stride; ++a)
+    for (int b = 0; b < stride; ++b) {
+      IgemmProblem p;
+      p.a = dy, p.a_N = N, p.a_H = OH, p.a_W = OW, p.a_C = Cout, p.a_coff = 0, p.cin = Cout, p.stride = 1;
+      p.ntaps = 0;
+      for (int r = 0; r < R; ++r) {
+        if ((a + pad - r) % stride != 0) continue;
+        for (int s = 0; s < S; ++s) {
+          if ((b + pad - s) % stride != 0) continue;
+          const int t = p.ntaps++;
+          // dx[h,w] += dy[(h+pad-r)/stride, (w+pad-s)/stride] . W[:, :, r, s]  with h = stride*i + a
+          p.tap_dh[t] = (a + pad - r) / stride, p.tap_dw[t] = (b + pad - s) / stride;
+          p.tap_kbase[t] = (r * S + s) * Cout;
+        }
+      }
+      if (p.ntaps == 0) continue;
+      p.o_N = N, p.OH = (H - a + stride - 1) / stride, p.OW = (W - b + stride - 1) / stride;
+      if (p.OH <= 0 || p.OW <= 0) continue;
+      p.b = wd, p.b_rows = Cin, p.b_cols = R * S * Cout;
+      p.out = dx, p.out_fp32 = out_fp32, p.ldc = Cin, p.c_off = 0;
+      p.o_H = H, p.o_W = W, p.o_sh = stride, p.o_sw = stride, p.o_oh = a, p.o_ow = b;
+      p.resid = resid, p.resid_fp32 = out_fp32;
+      int rc = igemm_launch(p, static_cast<cudaStream_t>(stream));
+      if (rc) return rc;
+    }
+  return SVSR_OK;
+}
+
+int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                      int stride, int pad, void* stream) {
+  SVSR_REQUIRE(R * S <= WGRAD_MAX_TAPS, "wgrad: %dx%d filter has too many taps", R, S);
+  WgradProblem p;
+  p.a = x, p.a_N = N, p.a_H = H, p.a_W = W, p.a_C = Cin, p.a_coff = 0, p.a_cin = Cin, p.a_stride = stride;
+  p.ntaps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) p.tap_dh[r * S + s] = r - pad, p.tap_dw[r * S + s] = s - pad;
+  p.b = dy, p.b_C = Cout, p.b_coff = 0, p.n_cols = Cout;
+  p.k_N = N, p.k_H = (H + 2 * pad - R) / stride + 1, p.k_W = (W + 2 * pad - S) / stride + 1;
+  p.out = dw, p.ldo = Cout;
+  return wgrad_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,
+                    void* stream) {
+  SVSR_REQUIRE(N % 64 == 0, "gemm_wgrad: N=%d must be a multiple of 64", N);
+  WgradProblem p;
+  p.a = dy, p.a_N = M, p.a_H = 1, p.a_W = 1, p.a_C = ldy, p.a_coff = 0, p.a_cin = N, p.a_stride = 1;
+  p.ntaps = 1;
+  p.b = x, p.b_C = ldx, p.b_coff = 0, p.n_cols = K;
+  p.k_N = M, p.k_H = 1, p.k_W = 1;
+  p.out = dw, p.ldo = ldw;
+  return wgrad_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream) {
+  return debug_rowshift(a, b, out, shift, mode, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,242 @@
+// tcgen05 weight-gradient kernel (see wgrad.cuh). Same warp roles as igemm.cu.
+// smem stage = A: two 64-channel blocks [128 pixel rows x 128 B] + B: BN/64 such blocks, all SWIZZLE_128B, MN-major.
+#include "wgrad.cuh"
+#include "igemm.cuh"  // igemm_choose_box
+#include "tmap.h"
+
+namespace svsr {
+
+struct WgradKParams {
+  int tiles_h, tiles_w, ktiles;
+  int bn, bh, bw, box_rows;
+  int a_stride, a_coff, a_cblocks;  // a_cblocks = a_cin / 64
+  int ngroups;                      // ntaps * a_cblocks: number of 64-row groups of D
+  int mb_per_cta;
+  int tap_dh[WGRAD_MAX_TAPS];
+  int tap_dw[WGRAD_MAX_TAPS];
+  int b_coff, n_cols;
+  float* out;
+  int ldo;
+};
+
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int BLK = 128 * 128;  // one 64-channel block: 128 pixel rows x 128 B
+  static constexpr int A_BYTES = 2 * BLK;
+  static constexpr int B_BYTES = (BN / 64) * BLK;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradKParams p) {
+  using L = WgradSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mb0 = blockIdx.x * p.mb_per_cta;  // first 128-row block of D handled here
+  const int nb = blockIdx.y;
+  const int split = blockIdx.z, nsplit = gridDim.z;
+  const int num_mblocks = (p.ngroups + 1) / 2;
+  const int mb_cnt = min(p.mb_per_cta, num_mblocks - mb0);
+  const int my_ktiles = (p.ktiles - split + nsplit - 1) / nsplit;  // kt = split, split+nsplit, ...
+  constexpr uint32_t TMEM_COLS = 512;
+
+  // Rows >= box_rows of every block are never written by TMA: zero them once so they contribute 0 to the sums.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < L::BAR_OFFSET / 16; i += blockDim.x) z[i] = zero;
+  }
+  fence_proxy_async_smem();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_ktiles; ++i) {
+        const int kt = split + i * nsplit;
+        const int tw = kt % p.tiles_w;
+        const int th = (kt / p.tiles_w) % p.tiles_h;
+        const int tn = kt / (p.tiles_w * p.tiles_h);
+        const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+        for (int mbi = 0; mbi < mb_cnt; ++mbi) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + L::A_BYTES;
+          const int g0 = 2 * (mb0 + mbi);
+          const int nsub = (g0 + 1 < p.ngroups) ? 2 : 1;
+          mbar_expect_tx(&full_bar[stage], box_bytes * (uint32_t)(nsub + BN / 64));
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int g = g0 + sub;
+            const int tap = g / p.a_cblocks;
+            const int cb = g - tap * p.a_cblocks;
+            tma_load_4d(sA + sub * L::BLK, &tmA, &full_bar[stage], p.a_coff + cb * 64,
+                        w0 * p.a_stride + p.tap_dw[tap], h0 * p.a_stride + p.tap_dh[tap], n0);
+          }
+#pragma unroll
+          for (int blk = 0; blk < BN / 64; ++blk)
+            tma_load_4d(sB + blk * L::BLK, &tmB, &full_bar[stage], p.b_coff + nb * BN + blk * 64, w0, h0, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+      const int ksteps = (p.box_rows + 15) / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_ktiles; ++i) {
+        for (int mbi = 0; mbi < mb_cnt; ++mbi) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // one MMA consumes 16 pixel rows = two 8-row swizzle atoms (SBO = 1024 B apart);
+            // 64-channel blocks are LBO = 16 KB apart.
+            const uint64_t a_desc = umma_smem_desc_sw128(a_addr + ks * 2048, L::BLK, 1024);
+            const uint64_t b_desc = umma_smem_desc_sw128(b_addr + ks * 2048, L::BLK, 1024);
+            umma_bf16(tmem_base + (uint32_t)(mbi * BN), a_desc, b_desc, idesc, (i | ks) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    for (int mbi = 0; mbi < mb_cnt; ++mbi) {
+      const int g = 2 * (mb0 + mbi) + (r >> 6);
+      const bool row_valid = (g < p.ngroups) && (my_ktiles > 0);
+      float* orow = p.out + (long long)(g * 64 + (r & 63)) * p.ldo;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mbi * BN + ch * 32), v);
+        tmem_ld_wait();
+        const int col0 = nb * BN + ch * 32;
+        if (!row_valid) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.n_cols) atomicAdd(orow + col0 + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradKParams& kp, dim3 grid,
+                    cudaStream_t stream) {
+  using L = WgradSmem<BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL));
+    attr_done = true;
+  }
+  wgrad_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, kp);
+  SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+
+int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
+  SVSR_REQUIRE(p.a && p.b && p.out, "wgrad: null operand");
+  SVSR_REQUIRE(p.a_cin > 0 && p.a_cin % 64 == 0, "wgrad: a_cin=%d must be a positive multiple of 64", p.a_cin);
+  SVSR_REQUIRE(p.a_C % 8 == 0 && p.a_coff % 8 == 0 && p.b_C % 8 == 0 && p.b_coff % 8 == 0,
+               "wgrad: channel pitches/offsets must be multiples of 8");
+  SVSR_REQUIRE(p.ntaps >= 1 && p.ntaps <= WGRAD_MAX_TAPS, "wgrad: ntaps=%d out of range", p.ntaps);
+  SVSR_REQUIRE(p.a_stride == 1 || p.a_stride == 2, "wgrad: stride must be 1 or 2");
+  SVSR_REQUIRE(p.n_cols > 0 && p.ldo >= p.n_cols, "wgrad: bad output geometry");
+
+  WgradKParams kp{};
+  igemm_choose_box(p.k_N, p.k_H, p.k_W, &kp.bn, &kp.bh, &kp.bw);
+  kp.tiles_h = (p.k_H + kp.bh - 1) / kp.bh;
+  kp.tiles_w = (p.k_W + kp.bw - 1) / kp.bw;
+  const int tiles_n = (p.k_N + kp.bn - 1) / kp.bn;
+  kp.ktiles = tiles_n * kp.tiles_h * kp.tiles_w;
+  kp.box_rows = kp.bn * kp.bh * kp.bw;
+  kp.a_stride = p.a_stride, kp.a_coff = p.a_coff, kp.a_cblocks = p.a_cin / 64;
+  kp.ngroups = p.ntaps * kp.a_cblocks;
+  for (int t = 0; t < p.ntaps; ++t) kp.tap_dh[t] = p.tap_dh[t], kp.tap_dw[t] = p.tap_dw[t];
+  kp.b_coff = p.b_coff, kp.n_cols = p.n_cols;
+  kp.out = p.out, kp.ldo = p.ldo;
+
+  const int BN = p.n_cols <= 64 ? 64 : (p.n_cols <= 128 ? 128 : 256);
+  const int num_mblocks = (kp.ngroups + 1) / 2;
+  kp.mb_per_cta = 512 / BN;
+  if (kp.mb_per_cta > num_mblocks) kp.mb_per_cta = num_mblocks;
+  const int gx = (num_mblocks + kp.mb_per_cta - 1) / kp.mb_per_cta;
+  const int gy = (p.n_cols + BN - 1) / BN;
+  int nsplit = (2 * 148 + gx * gy - 1) / (gx * gy);
+  if (nsplit > kp.ktiles) nsplit = kp.ktiles;
+  if (nsplit < 1) nsplit = 1;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p.a_C, (uint64_t)p.a_W, (uint64_t)p.a_H, (uint64_t)p.a_N};
+    uint64_t strides[3] = {(uint64_t)p.a_C * 2, (uint64_t)p.a_W * p.a_C * 2, (uint64_t)p.a_H * p.a_W * p.a_C * 2};
+    uint32_t box[4] = {64, (uint32_t)((kp.bw - 1) * p.a_stride + 1), (uint32_t)((kp.bh - 1) * p.a_stride + 1),
+                       (uint32_t)kp.bn};
+    uint32_t es[4] = {1, (uint32_t)p.a_stride, (uint32_t)p.a_stride, 1};
+    int rc = make_tmap_bf16(&tmA, p.a, 4, dims, strides, box, es, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p.b_C, (uint64_t)p.k_W, (uint64_t)p.k_H, (uint64_t)p.k_N};
+    uint64_t strides[3] = {(uint64_t)p.b_C * 2, (uint64_t)p.k_W * p.b_C * 2, (uint64_t)p.k_H * p.k_W * p.b_C * 2};
+    uint32_t box[4] = {64, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    int rc = make_tmap_bf16(&tmB, p.b, 4, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
+  switch (BN) {
+    case 64: return launch_t<64, 3>(tmA, tmB, kp, grid, stream);
+    case 128: return launch_t<128, 3>(tmA, tmB, kp, grid, stream);
+    default: return launch_t<256, 2>(tmA, tmB, kp, grid, stream);
+  }
+}
+
+}  // namespace svsr

@@ -82,7 +82,122 @@ def case_conv(N, H, W, Cin, Cout, R, stride, pad):
           f"{ms*1e3:.1f}us {tf:.1f}TF/s {'OK' if rel < 1e-2 else 'FAIL'}")
 
 
+def case_dgrad(N, H, W, Cin, Cout, R, stride, pad, resid=False):
+    import torch
+    import torch.nn.functional as F
+    from syncvsr_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    OH = (H + 2 * pad - R) // stride + 1
+    dy = torch.randn(N, OH, OH, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, R, R, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    rs = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16) if resid else None
+    wd = ops.pack_conv_weight_dgrad(w)
+    dx = ops.conv2d_dgrad(dy, wd, H, W, R, R, stride, pad, resid=rs)
+    torch.cuda.synchronize()
+    x = torch.zeros(N, Cin, H, W, device="cuda", requires_grad=True)
+    y = F.conv2d(x, w.float(), stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(y, x, dy.float().permute(0, 3, 1, 2))
+    ref = ref.permute(0, 2, 3, 1)
+    if resid:
+        ref = ref + rs.float()
+    rel, mx = _rel_err(dx, ref)
+    ms = _time(lambda: ops.conv2d_dgrad(dy, wd, H, W, R, R, stride, pad, resid=rs))
+    tf = 2.0 * N * OH * OH * Cout * Cin * R * R / ms / 1e9
+    print(f"dgrad N={N} {H}x{W} Cin={Cin} Cout={Cout} k={R} s={stride} p={pad} resid={resid}: rel={rel:.3e} "
+          f"max={mx:.3e} {ms*1e3:.1f}us {tf:.1f}TF/s {'OK' if rel < 1e-2 else 'FAIL'}")
+
+
+def case_wgrad(N, H, W, Cin, Cout, R, stride, pad):
+    import torch
+    import torch.nn.functional as F
+    from syncvsr_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    OH = (H + 2 * pad - R) // stride + 1
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    dy = (torch.randn(N, OH, OH, Cout, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    dw = ops.unpack_conv_wgrad(ops.conv2d_wgrad(x, dy, R, R, stride, pad), Cin, R, R)
+    torch.cuda.synchronize()
+    w = torch.zeros(Cout, Cin, R, R, device="cuda", requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(y, w, dy.float().permute(0, 3, 1, 2))
+    rel, mx = _rel_err(dw, ref)
+    out = torch.zeros(R * R * Cin, Cout, device="cuda")
+    ms = _time(lambda: ops.conv2d_wgrad(x, dy, R, R, stride, pad, out=out))
+    tf = 2.0 * N * OH * OH * Cout * Cin * R * R / ms / 1e9
+    print(f"wgrad N={N} {H}x{W} Cin={Cin} Cout={Cout} k={R} s={stride} p={pad}: rel={rel:.3e} max={mx:.3e} "
+          f"{ms*1e3:.1f}us {tf:.1f}TF/s {'OK' if rel < 1e-3 else 'FAIL'}")
+
+
+def case_gemm_wgrad(M, N, K):
+    import torch
+    from syncvsr_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    dw = ops.gemm_wgrad(dy, x)
+    torch.cuda.synchronize()
+    ref = dy.float().T @ x.float()
+    rel, mx = _rel_err(dw, ref)
+    out = torch.zeros(N, K, device="cuda")
+    ms = _time(lambda: ops.gemm_wgrad(dy, x, out=out))
+    tf = 2.0 * M * N * K / ms / 1e9
+    print(f"gemm_wgrad M={M} N={N} K={K}: rel={rel:.3e} max={mx:.3e} {ms*1e3:.1f}us {tf:.1f}TF/s "
+          f"{'OK' if rel < 1e-3 else 'FAIL'}")
+
+
+def case_rowshift():
+    import ctypes as C
+    import torch
+    from syncvsr_b200._lib import check, lib, ptr, stream_ptr
+
+    g = torch.Generator(device="cuda").manual_seed(6)
+    res = []
+    for mode in (0, 2, 1, 3):
+        mn = mode & 1
+        a = torch.randn(256, 128 if mn else 64, device="cuda", generator=g).to(torch.bfloat16)
+        b = torch.randn(256 if mn else 64, 64, device="cuda", generator=g).to(torch.bfloat16)
+        for shift in (0, 8, 1, 3, 13, 50):
+            out = torch.zeros(128, 64, device="cuda")
+            check(lib().svsr_debug_rowshift(ptr(a), ptr(b), ptr(out), C.c_int(shift), C.c_int(mode), stream_ptr()),
+                  "rowshift")
+            torch.cuda.synchronize()
+            if mn:
+                ref = a[shift:shift + 128].float().T @ b[shift:shift + 128].float()
+            else:
+                ref = a[shift:shift + 128].float() @ b.float().T
+            rel, _ = _rel_err(out, ref)
+            res.append(f"m{mode}s{shift}:{rel:.1e}")
+    print("rowshift " + " ".join(res))
+
+
 CASES = {
+    "rowshift": case_rowshift,
+    "dgrad_l1": lambda: case_dgrad(58, 22, 22, 64, 64, 3, 1, 1),
+    "dgrad_l1r": lambda: case_dgrad(58, 22, 22, 64, 64, 3, 1, 1, resid=True),
+    "dgrad_l2s2": lambda: case_dgrad(58, 22, 22, 64, 128, 3, 2, 1),
+    "dgrad_l3s2": lambda: case_dgrad(58, 11, 11, 128, 256, 3, 2, 1),
+    "dgrad_ds": lambda: case_dgrad(58, 22, 22, 64, 128, 1, 2, 0),
+    "dgrad_ds3": lambda: case_dgrad(58, 11, 11, 128, 256, 1, 2, 0),
+    "wgrad_l1": lambda: case_wgrad(58, 22, 22, 64, 64, 3, 1, 1),
+    "wgrad_l2": lambda: case_wgrad(58, 11, 11, 128, 128, 3, 1, 1),
+    "wgrad_l3": lambda: case_wgrad(58, 6, 6, 256, 256, 3, 1, 1),
+    "wgrad_l4": lambda: case_wgrad(58, 3, 3, 512, 512, 3, 1, 1),
+    "wgrad_l2s2": lambda: case_wgrad(58, 22, 22, 64, 128, 3, 2, 1),
+    "wgrad_l3s2": lambda: case_wgrad(58, 11, 11, 128, 256, 3, 2, 1),
+    "wgrad_ds": lambda: case_wgrad(58, 22, 22, 64, 128, 1, 2, 0),
+    "gemm_wgrad1": lambda: case_gemm_wgrad(1920, 512, 512),
+    "gemm_wgrad2": lambda: case_gemm_wgrad(1920, 4096, 512),
+    "gemm_wgrad3": lambda: case_gemm_wgrad(1856, 2560, 512),
+    "gemm_wgrad4": lambda: case_gemm_wgrad(1920, 512, 2048),
+    "wgrad_l1_big": lambda: case_wgrad(1856, 22, 22, 64, 64, 3, 1, 1),
+    "wgrad_l2_big": lambda: case_wgrad(1856, 11, 11, 128, 128, 3, 1, 1),
+    "wgrad_l3_big": lambda: case_wgrad(1856, 6, 6, 256, 256, 3, 1, 1),
+    "wgrad_l4_big": lambda: case_wgrad(1856, 3, 3, 512, 512, 3, 1, 1),
+    "dgrad_l1_big": lambda: case_dgrad(1856, 22, 22, 64, 64, 3, 1, 1),
+    "dgrad_l2s2_big": lambda: case_dgrad(1856, 22, 22, 64, 128, 3, 2, 1),
     "gemm_small": lambda: case_gemm(128, 64, 64),
     "gemm_k512": lambda: case_gemm(256, 128, 512),
     "gemm_n256": lambda: case_gemm(1920, 512, 512, bias=True),
@@ -105,14 +220,17 @@ CASES = {
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] != "--all":
+    if len(sys.argv) > 1 and not sys.argv[1].startswith("--"):
         for name in sys.argv[1:]:
             CASES[name]()
         return
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
     lines = []
-    for name in CASES:
+    names = list(CASES)
+    if sys.argv[1:2] == ["--prefix"]:
+        names = [n for n in names if any(n.startswith(p) for p in sys.argv[2:])]
+    for name in names:
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=180)
