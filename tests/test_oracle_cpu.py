@@ -52,10 +52,10 @@ def test_oracle_matches_reference_golden(name, golden_dir):
         # fp32 summation order alone moves them by ~2e-3 between two CPU runs of the same math.
         assert rel(P["stem3d.0.weight"].grad, fx["grad_stem_w"]) < 1e-2
         assert rel(P["resnet.layer1.0.conv1.weight"].grad[:4], fx["grad_l1_conv1_slice"]) < 1e-2
-        assert rel(P["cls_token"].grad, fx["grad_cls_token"]) < 1e-4
-        assert rel(P["audio_projection.bias"].grad, fx["grad_audio_bias"]) < 1e-4
-        assert rel(P["resnet.layer4.1.bn2.weight"].grad, fx["grad_l4_bn2_w"]) < 1e-4
-        assert rel(P["encoder.layers.0.0.g"].grad, fx["grad_enc0_g"]) < 1e-4
+        assert rel(P["cls_token"].grad, fx["grad_cls_token"]) < 2e-3
+        assert rel(P["audio_projection.bias"].grad, fx["grad_audio_bias"]) < 2e-3
+        assert rel(P["resnet.layer4.1.bn2.weight"].grad, fx["grad_l4_bn2_w"]) < 2e-3
+        assert rel(P["encoder.layers.0.0.g"].grad, fx["grad_enc0_g"]) < 2e-3
         for k, n in fx["grad_norms"].items():
             assert P[k].grad.double().norm().item() == pytest.approx(n, rel=2e-3), k
         assert sorted(k for k, v in P.items() if v.requires_grad and v.grad is None) == []
