@@ -61,6 +61,52 @@ int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
 int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * LRW word-level model step executor: the whole of TransformerLightningModule.forward (lightning.py:133-191) and
+ * its backward as two calls. Parameters, gradients and BatchNorm buffers live in three flat fp32 arenas owned by
+ * the caller (torch tensors); the engine defines the layout (svsr_lrw_param_info) using the reference's
+ * state-dict names, so nn.Parameter views into the arena round-trip the reference's checkpoints. The gradient
+ * arena is what the data-parallel step all-reduces with one NCCL call.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct svsr_lrw_config {
+  int B, T, H, W;                 /* clips per step on this GPU, frames, crop height/width */
+  int dim, depth, heads;          /* model.bert.{dim,depth,heads} (yaml:19-21) */
+  int audio_alignment, vq_groups, audio_vocab; /* lightning.py:58-67 (there derived from the codec path) */
+  int num_labels;                 /* model.bert.num_labels */
+  int rotary_v;                   /* x-transformers 1.9.x rotates v as well (SURVEY Appendix A switch 1) */
+  float lambda_audio;             /* optim.lambda_audio */
+  float label_smoothing;          /* train.label_smoothing */
+  float bn_eps, bn_momentum;      /* torch.nn.BatchNorm defaults 1e-5 / 0.1 */
+} svsr_lrw_config;
+
+int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle);
+int svsr_lrw_destroy(void* handle);
+int64_t svsr_lrw_param_count(void* handle);     /* elements of the parameter (= gradient) arena */
+int64_t svsr_lrw_buffer_count(void* handle);    /* elements of the BatchNorm running-stat arena */
+int64_t svsr_lrw_workspace_bytes(void* handle); /* activation + packed-operand workspace */
+int svsr_lrw_num_params(void* handle);
+int svsr_lrw_num_buffers(void* handle);
+/* i-th tensor of the arena: reference state-dict name, shape[5], element offset, AdamW-decay flag (ndim >= 2) */
+int svsr_lrw_param_info(void* handle, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset, int* decay);
+int svsr_lrw_buffer_info(void* handle, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset);
+int svsr_lrw_bind(void* handle, float* params, float* grads, float* buffers, void* workspace, int64_t workspace_bytes);
+/* fp32 master weights -> bf16 tensor-core operand layouts; call after every optimizer step */
+int svsr_lrw_pack_weights(void* handle, void* stream);
+/* videos fp32 [B,1,T,H,W]; tokens int64 [B, >=T*A, G] with batch stride tok_stride_b (elements); labels int64 [B]
+ * or soft_labels fp32 [B,num_labels] (CutMix). train: batch-stat BN + buffer update. skip_mask bit i drops encoder
+ * sublayer i (layer_dropout decided on the host like the reference). metrics (device fp32[5]) = loss_total,
+ * loss_category, loss_audio, accuracy_top1, accuracy_top5. */
+int svsr_lrw_forward(void* handle, const float* videos, const int64_t* tokens, int64_t tok_stride_b,
+                     const int64_t* labels, const float* soft_labels, int train, uint32_t skip_mask, float* metrics,
+                     void* stream);
+/* forward_videos (lightning.py:112-119) only: fills the "inputs_embeds" tensor ([B,T+1,dim] fp32, row 0 = CLS) */
+int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* stream);
+/* (*grad_scale) * d loss_total / d params accumulated (+=) into the gradient arena; grad_scale is a DEVICE fp32
+ * scalar (the upstream gradient autograd hands to loss_total) or NULL for 1. One backward per forward. */
+int svsr_lrw_backward(void* handle, const float* grad_scale, void* stream);
+/* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */
+int svsr_lrw_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
+
 /* Developer hardware probe (see csrc/debug_probe.cu); not part of the product path. */
 int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream);
 

@@ -60,9 +60,11 @@ def batchnorm(x: Tensor, prefix: str, P: Dict[str, Tensor], train: bool, new_sta
 # stem3d: Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3),bias=False) -> BatchNorm3d -> GELU(erf) -> MaxPool3d((1,3,3),(1,2,2),(0,1,1))
 # (lightning.py:49-54)
 # ----------------------------------------------------------------------------------------------------------------
-def stem3d(videos: Tensor, P, train: bool, new_stats, q: QFn = None) -> Tensor:
+def stem3d(videos: Tensor, P, train: bool, new_stats, q: QFn = None, cap: Optional[dict] = None) -> Tensor:
     x = F.conv3d(_q(q, videos), _q(q, P["stem3d.0.weight"]), None, (1, 2, 2), (2, 3, 3))
     x = _q(q, x)
+    if cap is not None:
+        cap["stem_conv"] = x.detach()
     x = batchnorm(x, "stem3d.1", P, train, new_stats)
     x = F.gelu(x)
     x = F.max_pool3d(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
@@ -89,13 +91,19 @@ def basic_block(x: Tensor, prefix: str, P, stride: int, train: bool, new_stats, 
     return _q(q, F.relu(out + sc))
 
 
-def forward_videos(videos: Tensor, P, train: bool, new_stats, q: QFn = None) -> Tensor:
+def forward_videos(videos: Tensor, P, train: bool, new_stats, q: QFn = None, cap: Optional[dict] = None) -> Tensor:
     """lightning.py:112-119: stem -> transpose(1,2).flatten(0,1) -> layer1..4 -> mean((2,3)) -> unflatten."""
     B = videos.shape[0]
-    h = stem3d(videos, P, train, new_stats, q).transpose(1, 2).flatten(0, 1)
+    h = stem3d(videos, P, train, new_stats, q, cap).transpose(1, 2).flatten(0, 1)
+    if cap is not None:
+        cap["stem_out"] = h.detach()
+    bi = 0
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
-        h = basic_block(h, f"resnet.layer{li}.0", P, stride, train, new_stats, q)
-        h = basic_block(h, f"resnet.layer{li}.1", P, 1, train, new_stats, q)
+        for b, st in ((0, stride), (1, 1)):
+            h = basic_block(h, f"resnet.layer{li}.{b}", P, st, train, new_stats, q)
+            if cap is not None:
+                cap[f"block{bi}.out"] = h.detach()
+            bi += 1
     return h.mean((2, 3)).unflatten(0, (B, -1))
 
 
@@ -162,10 +170,11 @@ def audio_targets(audio_tokens: Tensor, T: int, A: int) -> Tensor:
 def lrw_forward(P: Dict[str, Tensor], videos: Tensor, audio_tokens: Tensor, labels: Tensor, word_mask: Tensor, *,
                 depth: int = 12, heads: int = 8, audio_alignment: int = 4, vq_groups: int = 2,
                 audio_vocab_size: int = 320, lambda_audio: float = 10.0, label_smoothing: float = 0.0,
-                use_wb: bool = False, train: bool = True, q: QFn = None, skip: Optional[set] = None):
+                use_wb: bool = False, train: bool = True, q: QFn = None, skip: Optional[set] = None,
+                cap: Optional[dict] = None):
     """lightning.py:133-191. Returns the reference's metric dict plus last_hidden_state / logits and new BN buffers."""
     new_stats: Dict[str, Tensor] = {}
-    emb = forward_videos(videos, P, train, new_stats, q)
+    emb = forward_videos(videos, P, train, new_stats, q, cap)
     if use_wb:
         emb = torch.cat((emb, word_mask.unsqueeze(-1)), dim=-1)
     B, T, D = emb.shape

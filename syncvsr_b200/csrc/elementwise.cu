@@ -1,0 +1,605 @@
+#include "elementwise.cuh"
+
+namespace svsr {
+
+namespace {
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x, r.v[1] = a.y, r.v[2] = b.x, r.v[3] = b.y, r.v[4] = c.x, r.v[5] = c.y, r.v[6] = d.x, r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]), u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]), u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ F8 ldf8(const float* p) {
+  F8 r;
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+inline unsigned grid_for(long long work_items, int per_block, int max_blocks = 148 * 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (unsigned)b;
+}
+
+// Reduce 16 per-thread partials (8 channels x 2 quantities) across the row slots of a 256-thread block and add
+// them to the fp64 accumulators stats[q*C + channel].
+__device__ __forceinline__ void block_channel_reduce(const float (&acc)[16], int cg, int C, double* stats) {
+  __shared__ float sred[256 * 16];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sred[i * 256 + tid] = acc[i];
+  __syncthreads();
+  const int slots = 256 / cg;
+  // thread (g = tid % cg) sums quantity i over slots; spread the 16 quantities over the slot threads
+  for (int i = tid / cg; i < 16; i += slots) {
+    const int g = tid % cg;
+    float s = 0.f;
+    for (int sl = 0; sl < slots; ++sl) s += sred[i * 256 + sl * cg + g];
+    const int q = i >> 3, ch = g * 8 + (i & 7);
+    atomicAdd(&stats[q * C + ch], (double)s);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void stem_patch_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, int B, int T, int H,
+                                  int W, int OH, int OW) {
+  const long long total = (long long)B * T * OH * OW * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kh = (int)(i & 7);
+    long long pix = i >> 3;
+    const int ow = (int)(pix % OW);
+    long long t1 = pix / OW;
+    const int oh = (int)(t1 % OH);
+    const long long bt = t1 / OH;
+    F8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = 0.f;
+    const int ih = 2 * oh + kh - 3;
+    if (kh < 7 && ih >= 0 && ih < H) {
+      const float* row = x + (bt * H + ih) * (long long)W;
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        const int iw = 2 * ow + kw - 3;
+        if (iw >= 0 && iw < W) r.v[kw] = __ldg(row + iw);
+      }
+    }
+    st8(P + pix * 64 + kh * 8, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                       double* stats) {
+  const int cg = C >> 3;
+  const int g = threadIdx.x % cg, slot = threadIdx.x / cg, rpb = 256 / cg;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (long long r = (long long)blockIdx.x * rpb + slot; r < rows; r += (long long)gridDim.x * rpb) {
+    F8 v = ld8(x + r * C + g * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v.v[k], acc[8 + k] += v.v[k] * v.v[k];
+  }
+  block_channel_reduce(acc, cg, C, stats);
+}
+
+// coef layout: [0] mean, [1] invstd, [2] scale = gamma*invstd, [3] shift = beta - mean*scale  (each [C])
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long rows, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* coef,
+                                   int update_running) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = (double)rows;
+  double mean, var;
+  if (update_running < 0) {  // eval mode: normalise with the running statistics
+    mean = running_mean[c], var = running_var[c];
+  } else {
+    mean = stats[c] / n;
+    var = stats[C + c] / n - mean * mean;
+    if (var < 0) var = 0;
+  }
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  coef[c] = (float)mean;
+  coef[C + c] = invstd;
+  coef[2 * C + c] = sc;
+  coef[3 * C + c] = beta[c] - (float)mean * sc;
+  if (update_running > 0) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
+                const __nv_bfloat16* __restrict__ res, const float* __restrict__ rcoef, int relu,
+                __nv_bfloat16* __restrict__ out, long long rows, int C) {
+  const int cg = C >> 3;
+  const long long total = rows * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long off = (i / cg) * C + g * 8;
+    F8 v = ld8(x + off);
+    const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = v.v[k] * sc.v[k] + sh.v[k];
+    if (res) {
+      F8 rv = ld8(res + off);
+      if (rcoef) {
+        const F8 rs = ldf8(rcoef + 2 * C + g * 8), rh = ldf8(rcoef + 3 * C + g * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] += rv.v[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+    }
+    st8(out + off, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
+                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef, long long rows, int C,
+                     double* stats) {
+  const int cg = C >> 3;
+  const int g = threadIdx.x % cg, slot = threadIdx.x / cg, rpb = 256 / cg;
+  const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (long long r = (long long)blockIdx.x * rpb + slot; r < rows; r += (long long)gridDim.x * rpb) {
+    const long long off = r * C + g * 8;
+    F8 gv = ld8(dout + off);
+    if (relu_ref) {
+      const F8 o = ld8(relu_ref + off);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
+    }
+    const F8 cv = ld8(c + off);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] += gv.v[k];
+      acc[8 + k] += gv.v[k] * (cv.v[k] - mean.v[k]) * invstd.v[k];
+    }
+  }
+  block_channel_reduce(acc, cg, C, stats);
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, long long rows, int C, float* dgamma,
+                                       float* dbeta, float* kcoef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sg = stats[c], sgx = stats[C + c];
+  dbeta[c] += (float)sg;
+  dgamma[c] += (float)sgx;
+  kcoef[c] = (float)(sg / (double)rows);
+  kcoef[C + c] = (float)(sgx / (double)rows);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
+                    const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
+                    const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
+                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C) {
+  const int cg = C >> 3;
+  const long long total = rows * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long off = (i / cg) * C + g * 8;
+    F8 gv = ld8(dout + off);
+    if (relu_ref) {
+      const F8 o = ld8(relu_ref + off);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
+    }
+    if (gmask_out) st8(gmask_out + off, gv);
+    const F8 cv = ld8(c + off);
+    const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8), sc = ldf8(coef + 2 * C + g * 8);
+    const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (cv.v[k] - mean.v[k]) * invstd.v[k];
+      o.v[k] = sc.v[k] * (gv.v[k] - k1.v[k] - xh * k2.v[k]);
+    }
+    st8(dc + off, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef,
+                         __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ argmax, int N, int IH, int IW, int OH,
+                         int OW) {
+  constexpr int C = 64, cg = 8;
+  const long long total = (long long)N * OH * OW * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int ow = (int)(pix % OW);
+    long long t1 = pix / OW;
+    const int oh = (int)(t1 % OH);
+    const long long n = t1 / OH;
+    const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) best[k] = -INFINITY, bi[k] = 0;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh + kh - 1;
+      if (ih < 0 || ih >= IH) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = 2 * ow + kw - 1;
+        if (iw < 0 || iw >= IW) continue;
+        const F8 v = ld8(y0 + ((n * IH + ih) * IW + iw) * C + g * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float a = gelu_f(v.v[k] * sc.v[k] + sh.v[k]);
+          if (a > best[k]) best[k] = a, bi[k] = kh * 3 + kw;  // first maximum wins (torch max_pool semantics)
+        }
+      }
+    }
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = best[k];
+    st8(out + pix * C + g * 8, o);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(argmax + pix * C + g * 8) = packed;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+stem_pool_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
+                          const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef,
+                          __nv_bfloat16* __restrict__ dz, int N, int IH, int IW, int OH, int OW) {
+  constexpr int C = 64, cg = 8;
+  const long long total = (long long)N * IH * IW * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int iw = (int)(pix % IW);
+    long long t1 = pix / IW;
+    const int ih = (int)(t1 % IH);
+    const long long n = t1 / IH;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // windows (oh, ow) that contain (ih, iw): 2*oh-1 <= ih <= 2*oh+1
+    const int oh_lo = ih >> 1, oh_hi = (ih + 1) >> 1;
+    const int ow_lo = iw >> 1, ow_hi = (iw + 1) >> 1;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      if (oh >= OH) continue;
+      const int kh = ih - (2 * oh - 1);
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        if (ow >= OW) continue;
+        const int pos = kh * 3 + (iw - (2 * ow - 1));
+        const long long o = ((n * OH + oh) * OW + ow) * C + g * 8;
+        const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
+        const F8 d = ld8(dout + o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a = ((k < 4 ? am.x : am.y) >> (8 * (k & 3))) & 0xff;
+          if ((int)a == pos) acc[k] += d.v[k];
+        }
+      }
+    }
+    const F8 v = ld8(y0 + pix * C + g * 8);
+    const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k] == 0.f ? 0.f : acc[k] * gelu_grad_f(v.v[k] * sc.v[k] + sh.v[k]);
+    st8(dz + pix * C + g * 8, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void meanpool_cls_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ cls,
+                                    float* __restrict__ xs, int B, int T, int HW, int C) {
+  const int cg = C >> 3;
+  const long long total = (long long)B * (T + 1) * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long row = i / cg;  // b*(T+1) + tt
+    const int tt = (int)(row % (T + 1));
+    const long long b = row / (T + 1);
+    float* dst = xs + row * C + g * 8;
+    if (tt == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = cls[g * 8 + k];
+      continue;
+    }
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const __nv_bfloat16* src = a + ((b * T + (tt - 1)) * HW) * (long long)C + g * 8;
+    for (int p = 0; p < HW; ++p) {
+      const F8 v = ld8(src + (long long)p * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+    }
+    const float inv = 1.0f / (float)HW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = acc[k] * inv;
+  }
+}
+
+__global__ void meanpool_cls_bwd_kernel(const float* __restrict__ dx, __nv_bfloat16* __restrict__ dout,
+                                        float* __restrict__ dcls, int B, int T, int HW, int C) {
+  const int cg = C >> 3;
+  const long long total = (long long)B * (T + 1) * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long row = i / cg;
+    const int tt = (int)(row % (T + 1));
+    const long long b = row / (T + 1);
+    const F8 d = ldf8(dx + row * C + g * 8);
+    if (tt == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(dcls + g * 8 + k, d.v[k]);
+      continue;
+    }
+    F8 o;
+    const float inv = 1.0f / (float)HW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = d.v[k] * inv;
+    __nv_bfloat16* dst = dout + ((b * T + (tt - 1)) * HW) * (long long)C + g * 8;
+    for (int p = 0; p < HW; ++p) st8(dst + (long long)p * C, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                        __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int RS) {
+  const long long total = (long long)Cout * Cin * RS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int rs = (int)(i % RS);
+    const int ci = (int)((i / RS) % Cin);
+    const int co = (int)(i / ((long long)RS * Cin));
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    wf[(long long)co * RS * Cin + (long long)rs * Cin + ci] = v;
+    if (wd) wd[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
+  }
+}
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ d, float* __restrict__ grad, int Cout, int Cin,
+                                         int RS) {
+  const long long total = (long long)Cout * Cin * RS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int rs = (int)(i % RS);
+    const int ci = (int)((i / RS) % Cin);
+    const int co = (int)(i / ((long long)RS * Cin));
+    grad[i] += d[((long long)rs * Cin + ci) * Cout + co];
+  }
+}
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 64 * 320
+  if (i >= 64 * 320) return;
+  const int co = i / 320, k = i % 320;
+  const int kt = k / 64, kh = (k % 64) / 8, kw = k % 8;
+  float v = 0.f;
+  if (kh < 7 && kw < 7) v = w[((co * 5 + kt) * 7 + kh) * 7 + kw];
+  wp[i] = __float2bfloat16(v);
+}
+__global__ void unpack_stem_wgrad_kernel(const float* __restrict__ d, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 64*245
+  if (i >= 64 * 245) return;
+  const int co = i / 245, r = i % 245;
+  const int kt = r / 49, kh = (r % 49) / 7, kw = r % 7;
+  grad[i] += d[(kt * 64 + kh * 8 + kw) * 64 + co];
+}
+__global__ void pack_linear_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
+                                          __nv_bfloat16* __restrict__ wt, int N, int K, int ldb, int ldt) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int n = n0 + j, k = k0 + threadIdx.x;
+    float v = (n < N && k < K) ? w[(long long)n * K + k] : 0.f;
+    tile[j][threadIdx.x] = v;
+    if (n < N && k < K) wb[(long long)n * ldb + k] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  if (wt) {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int k = k0 + j, n = n0 + threadIdx.x;
+      if (n < N && k < K) wt[(long long)k * ldt + n] = __float2bfloat16(tile[threadIdx.x][j]);
+    }
+  }
+}
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db, int M,
+                                   int N) {
+  // block handles 64 columns x a slab of rows; threads: 64 columns x 4 row lanes
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane_r = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (col < N)
+    for (int r = blockIdx.y * 4 + lane_r; r < M; r += gridDim.y * 4) acc += __bfloat162float(dy[(long long)r * ld + col]);
+  __shared__ float s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  if (lane_r == 0 && col < N) atomicAdd(db + col, s[threadIdx.x] + s[threadIdx.x + 64] + s[threadIdx.x + 128] + s[threadIdx.x + 192]);
+}
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+__global__ void split_cast_last_kernel(const float* __restrict__ last, __nv_bfloat16* __restrict__ cls,
+                                       __nv_bfloat16* __restrict__ frames, int B, int T, int D) {
+  const long long total = (long long)B * (T + 1) * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long row = i / D;
+    const int tt = (int)(row % (T + 1));
+    const long long b = row / (T + 1);
+    const __nv_bfloat16 v = __float2bfloat16(last[i]);
+    if (tt == 0)
+      cls[b * D + d] = v;
+    else
+      frames[(b * T + tt - 1) * D + d] = v;
+  }
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK() SVSR_CHECK_CUDA(cudaGetLastError())
+
+int stem_patch(const float* videos, __nv_bfloat16* patches, int B, int T, int H, int W, cudaStream_t s) {
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)B * T * OH * OW * 8;
+  stem_patch_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(videos, patches, B, T, H, W, OH, OW);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_stats(const __nv_bfloat16* x, long long rows, int C, double* stats, cudaStream_t s) {
+  SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_stats: unsupported channel count %d", C);
+  const int rpb = 256 / (C / 8);
+  bn_stats_kernel<<<grid_for(rows, rpb * 8, 148 * 4), 256, 0, s>>>(x, rows, C, stats);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_finalize(const double* stats, long long rows, int C, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* coef, int update_running,
+                cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, rows, C, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, coef, update_running);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res, const float* rcoef, int relu,
+             __nv_bfloat16* out, long long rows, int C, cudaStream_t s) {
+  bn_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(x, coef, res, rcoef, relu, out, rows, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
+                  long long rows, int C, double* stats, cudaStream_t s) {
+  SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
+  const int rpb = 256 / (C / 8);
+  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, float* dbeta, float* kcoef,
+                    cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, rows, C, dgamma, dbeta, kcoef);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
+                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C,
+                 cudaStream_t s) {
+  bn_bwd_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out,
+                                                                       rows, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16* out, uint8_t* argmax, int N, int IH,
+                      int IW, cudaStream_t s) {
+  const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
+  stem_bn_gelu_pool_kernel<<<grid_for((long long)N * OH * OW * 8, 256 * 2), 256, 0, s>>>(y0, coef, out, argmax, N, IH,
+                                                                                      IW, OH, OW);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
+                       __nv_bfloat16* dz, int N, int IH, int IW, cudaStream_t s) {
+  const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
+  stem_pool_gelu_bwd_kernel<<<grid_for((long long)N * IH * IW * 8, 256 * 2), 256, 0, s>>>(dout, argmax, y0, coef, dz,
+                                                                                       N, IH, IW, OH, OW);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,
+                 cudaStream_t s) {
+  meanpool_cls_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(a, cls, x_stream, B, T, HW, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s) {
+  meanpool_cls_bwd_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(dx, dout, dcls, B, T, HW, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int pack_conv_weight(const float* w, __nv_bfloat16* w_fprop, __nv_bfloat16* w_dgrad, int Cout, int Cin, int R, int S,
+                     cudaStream_t s) {
+  pack_conv_weight_kernel<<<grid_for((long long)Cout * Cin * R * S, 256), 256, 0, s>>>(w, w_fprop, w_dgrad, Cout, Cin,
+                                                                                    R * S);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int unpack_conv_wgrad(const float* d, float* grad, int Cout, int Cin, int R, int S, cudaStream_t s) {
+  unpack_conv_wgrad_kernel<<<grid_for((long long)Cout * Cin * R * S, 256), 256, 0, s>>>(d, grad, Cout, Cin, R * S);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int pack_stem_weight(const float* w, __nv_bfloat16* wp, cudaStream_t s) {
+  pack_stem_weight_kernel<<<(64 * 320 + 255) / 256, 256, 0, s>>>(w, wp);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int unpack_stem_wgrad(const float* d, float* grad, cudaStream_t s) {
+  unpack_stem_wgrad_kernel<<<(64 * 245 + 255) / 256, 256, 0, s>>>(d, grad);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int N, int K, int ldb, int ldt,
+                       cudaStream_t s) {
+  dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
+  pack_linear_weight_kernel<<<grid, block, 0, s>>>(w, wb, wt, N, K, ldb, ldt);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (unsigned)((M + 255) / 256 < 1 ? 1 : (M + 255) / 256));
+  colsum_bf16_kernel<<<grid, 256, 0, s>>>(dy, ld, db, M, N);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s) {
+  cast_f32_to_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+
+int split_cast_last(const float* last, __nv_bfloat16* cls, __nv_bfloat16* frames, int B, int T, int D, cudaStream_t s) {
+  split_cast_last_kernel<<<grid_for((long long)B * (T + 1) * D, 256 * 4), 256, 0, s>>>(last, cls, frames, B, T, D);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+
+}  // namespace svsr

@@ -1,0 +1,60 @@
+// HBM-bound kernels of the LRW hot path: BatchNorm statistics / apply / backward, the stem's patch gather and
+// BN+GELU+max-pool, spatial mean pooling, weight packing. NHWC bf16 activations, 8 channels (16 B) per thread,
+// fp32 math, fp64 cross-block accumulation for the batch statistics.
+#pragma once
+#include "common.cuh"
+
+namespace svsr {
+
+// stem: videos fp32 [B,1,T,H,W] -> patches bf16 [B,T,OH*OW,64]; slot kh*8+kw = x[2oh+kh-3, 2ow+kw-3] (7x7, zero padded)
+int stem_patch(const float* videos, __nv_bfloat16* patches, int B, int T, int H, int W, cudaStream_t s);
+
+// per-channel sum / sum of squares of x[rows, C] accumulated (+=) into fp64 stats[0..C) and stats[C..2C)
+int bn_stats(const __nv_bfloat16* x, long long rows, int C, double* stats, cudaStream_t s);
+// finalize: mean/invstd/scale/shift (fp32 [4][C] in `coef`) + running stats update (momentum, unbiased variance)
+// update_running: 1 = train (batch stats, update buffers), 0 = batch stats only, -1 = eval (use running stats)
+int bn_finalize(const double* stats, long long rows, int C, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* coef, int update_running,
+                cudaStream_t s);
+// out = act(x*scale+shift (+ res*rscale+rshift | + res)); coef/rcoef are the [4][C] blocks of bn_finalize
+int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res, const float* rcoef, int relu,
+             __nv_bfloat16* out, long long rows, int C, cudaStream_t s);
+// backward reductions: g = dout * (ref > 0 if ref) ; stats[0..C) += sum g ; stats[C..2C) += sum g * xhat
+int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
+                  long long rows, int C, double* stats, cudaStream_t s);
+// dgamma += sum g*xhat ; dbeta += sum g ; kcoef[0..C) = sum g / rows ; kcoef[C..2C) = sum g*xhat / rows
+int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, float* dbeta, float* kcoef,
+                    cudaStream_t s);
+// dc = scale * (g - k1 - xhat*k2); optionally also writes g (the relu-masked upstream gradient) to gmask_out
+int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
+                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C,
+                 cudaStream_t s);
+
+// stem epilogue: y0 [N,IH,IW,64] -> max_pool3x3s2p1(gelu(bn(y0))) [N,OH,OW,64] + argmax slot (uint8)
+int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16* out, uint8_t* argmax, int N, int IH,
+                      int IW, cudaStream_t s);
+// dz[N,IH,IW,64] = (scatter of dout through argmax) * gelu'(bn(y0))
+int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
+                       __nv_bfloat16* dz, int N, int IH, int IW, cudaStream_t s);
+
+// x_stream[b, t+1, :] = mean over HW of a[b*T+t, :, :]; x_stream[b, 0, :] = cls  (fp32 [B,T+1,C])
+int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,
+                 cudaStream_t s);
+// dout[b*T+t, hw, :] = dx[b, t+1, :] / HW (bf16); dcls += sum_b dx[b,0,:]
+int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s);
+
+// ---- weight packing (fp32 master -> bf16 operand layouts) and gradient unpacking ----
+int pack_conv_weight(const float* w, __nv_bfloat16* w_fprop, __nv_bfloat16* w_dgrad, int Cout, int Cin, int R, int S,
+                     cudaStream_t s);
+int unpack_conv_wgrad(const float* d, float* grad, int Cout, int Cin, int R, int S, cudaStream_t s);
+int pack_stem_weight(const float* w, __nv_bfloat16* wp, cudaStream_t s);  // [64,1,5,7,7] -> [64, 5*64]
+int unpack_stem_wgrad(const float* d, float* grad, cudaStream_t s);        // [5*64, 64] -> [64,1,5,7,7] (+=)
+int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int N, int K, int ldb, int ldt,
+                       cudaStream_t s);
+// db[N] += column sums of dy[M, N] (bf16, pitch ld)
+int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s);
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
+// last [B, T+1, D] fp32 -> cls rows [B, D] and frame rows [B*T, D], both bf16
+int split_cast_last(const float* last, __nv_bfloat16* cls, __nv_bfloat16* frames, int B, int T, int D, cudaStream_t s);
+
+}  // namespace svsr

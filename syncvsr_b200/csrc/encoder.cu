@@ -1,0 +1,358 @@
+#include "encoder.cuh"
+
+namespace svsr {
+
+namespace {
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm: one warp per row, D <= 1024 (D % 32 == 0); lanes own strided elements j = lane + 32*i
+// ------------------------------------------------------------------------------------------------
+template <int MAXI>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ y,
+                   float* __restrict__ inv_out, int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ni = D >> 5;
+  const float rs = rsqrtf((float)D);
+  for (int row = warp; row < M; row += nwarps) {
+    const float* xr = x + (long long)row * D;
+    float v[MAXI];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i)
+      if (i < ni) {
+        v[i] = xr[lane + 32 * i];
+        ss += v[i] * v[i];
+      }
+    ss = warp_sum(ss);
+    const float norm = sqrtf(ss) * rs;
+    const float inv = 1.0f / fmaxf(norm, eps);
+    if (lane == 0) inv_out[row] = inv;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i)
+      if (i < ni) y[(long long)row * D + lane + 32 * i] = __float2bfloat16(v[i] * inv * g[lane + 32 * i]);
+  }
+}
+
+template <int MAXI>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
+                   const float* __restrict__ inv_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb,
+                   float* __restrict__ dg, int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ni = D >> 5;
+  float dgacc[MAXI];
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) dgacc[i] = 0.f;
+  for (int row = warp; row < M; row += nwarps) {
+    const long long base = (long long)row * D;
+    const float inv = inv_in[row];
+    const bool clamped = inv >= 1.0f / eps;  // norm <= eps: the scale is a constant there
+    float xv[MAXI], dv[MAXI];
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i)
+      if (i < ni) {
+        const int j = lane + 32 * i;
+        xv[i] = x[base + j];
+        dv[i] = __bfloat162float(dy[base + j]);
+        t += dv[i] * g[j] * xv[i];
+        dgacc[i] += dv[i] * xv[i] * inv;
+      }
+    t = warp_sum(t);
+    const float coef = clamped ? 0.f : inv * inv * inv / (float)D * t;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i)
+      if (i < ni) {
+        const int j = lane + 32 * i;
+        const float nv = dx[base + j] + g[j] * inv * dv[i] - coef * xv[i];
+        dx[base + j] = nv;
+        dxb[base + j] = __float2bfloat16(nv);
+      }
+  }
+  // reduce dg over the block's warps, then one atomic per element per block
+  __shared__ float sdg[8][32 * MAXI];
+  const int w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) sdg[w][lane + 32 * i] = dgacc[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += sdg[ww][j];
+    atomicAdd(dg + j, s);
+  }
+}
+
+__global__ void rotary_table_kernel(float* tab, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 16) return;
+  const int pos = i / 16, f = i % 16;
+  const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * f) / 32.0f);
+  const float ang = (float)pos * inv_freq;
+  tab[pos * 32 + f] = cosf(ang);
+  tab[pos * 32 + 16 + f] = sinf(ang);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention core, one CTA per (batch, head); n <= 64 tokens, head dim 64. Everything lives in smem as fp32.
+// ------------------------------------------------------------------------------------------------
+constexpr int AT_MAXN = 64;
+constexpr int AT_D = 64;
+constexpr int AT_LD = 65;  // padded row pitch (floats) against bank conflicts
+
+__device__ __forceinline__ void load_rot(const __nv_bfloat16* __restrict__ src, int ld, const float* __restrict__ rot,
+                                         float* dst, int n, bool rotate) {
+  // src points at token 0 of this (b, head, q|k|v) slice; rows are `ld` elements apart
+  for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
+    const int pos = i >> 5, d2 = (i & 31) * 2;
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + (long long)pos * ld + d2);
+    dst[pos * AT_LD + d2] = __low2float(v);
+    dst[pos * AT_LD + d2 + 1] = __high2float(v);
+  }
+  __syncthreads();
+  if (rotate) {
+    for (int i = threadIdx.x; i < n * 16; i += blockDim.x) {
+      const int pos = i >> 4, f = i & 15;
+      const float c = rot[pos * 32 + f], s = rot[pos * 32 + 16 + f];
+      const float a = dst[pos * AT_LD + f], b = dst[pos * AT_LD + 16 + f];
+      dst[pos * AT_LD + f] = a * c - b * s;
+      dst[pos * AT_LD + 16 + f] = b * c + a * s;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void scores_softmax(const float* sq, const float* sk, float* sp, int n, float scale) {
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+    const int r = i / n, c = i - r * n;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < AT_D; ++d) acc += sq[r * AT_LD + d] * sk[c * AT_LD + d];
+    sp[r * AT_LD + c] = acc * scale;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < n; r += nw) {
+    const float a = lane < n ? sp[r * AT_LD + lane] : -INFINITY;
+    const float b = lane + 32 < n ? sp[r * AT_LD + lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(a, b));
+    const float ea = lane < n ? expf(a - m) : 0.f, eb = lane + 32 < n ? expf(b - m) : 0.f;
+    const float inv = 1.0f / warp_sum(ea + eb);
+    if (lane < n) sp[r * AT_LD + lane] = ea * inv;
+    if (lane + 32 < n) sp[r * AT_LD + lane + 32] = eb * inv;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128)
+attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
+                     __nv_bfloat16* __restrict__ o, int n, int heads, int rotary_v) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sk = sq + AT_MAXN * AT_LD;
+  float* sv = sk + AT_MAXN * AT_LD;
+  float* sp = sv + AT_MAXN * AT_LD;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int inner = heads * AT_D, ld = 3 * inner;
+  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
+  load_rot(base, ld, rot, sq, n, true);
+  load_rot(base + inner, ld, rot, sk, n, true);
+  load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
+  scores_softmax(sq, sk, sp, n, 0.125f);
+  for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
+    const int r = i >> 5, d2 = (i & 31) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float p = sp[r * AT_LD + j];
+      a0 += p * sv[j * AT_LD + d2];
+      a1 += p * sv[j * AT_LD + d2 + 1];
+    }
+    *reinterpret_cast<__nv_bfloat162*>(o + ((long long)b * n + r) * inner + h * AT_D + d2) =
+        __floats2bfloat162_rn(a0, a1);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
+                     const __nv_bfloat16* __restrict__ d_o, __nv_bfloat16* __restrict__ dqkv, int n, int heads,
+                     int rotary_v) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sk = sq + AT_MAXN * AT_LD;
+  float* sv = sk + AT_MAXN * AT_LD;
+  float* sp = sv + AT_MAXN * AT_LD;
+  float* sdo = sp + AT_MAXN * AT_LD;
+  float* sds = sdo + AT_MAXN * AT_LD;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int inner = heads * AT_D, ld = 3 * inner;
+  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
+  load_rot(base, ld, rot, sq, n, true);
+  load_rot(base + inner, ld, rot, sk, n, true);
+  load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
+  load_rot(d_o + (long long)b * n * inner + h * AT_D, inner, rot, sdo, n, false);
+  scores_softmax(sq, sk, sp, n, 0.125f);
+  // dP = dO V^T ; dS = P o (dP - rowsum(dP o P))
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+    const int r = i / n, c = i - r * n;
+    float acc = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < AT_D; ++d) acc += sdo[r * AT_LD + d] * sv[c * AT_LD + d];
+    sds[r * AT_LD + c] = acc;
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < n; r += nw) {
+      const float pa = lane < n ? sp[r * AT_LD + lane] : 0.f, pb = lane + 32 < n ? sp[r * AT_LD + lane + 32] : 0.f;
+      const float da = lane < n ? sds[r * AT_LD + lane] : 0.f, db = lane + 32 < n ? sds[r * AT_LD + lane + 32] : 0.f;
+      const float dot = warp_sum(pa * da + pb * db);
+      if (lane < n) sds[r * AT_LD + lane] = pa * (da - dot);
+      if (lane + 32 < n) sds[r * AT_LD + lane + 32] = pb * (db - dot);
+    }
+  }
+  __syncthreads();
+  // gradients in the rotated frame, then rotate back (transpose of the rotation) and store
+  __nv_bfloat16* obase = dqkv + (long long)b * n * ld + h * AT_D;
+  for (int i = threadIdx.x; i < n * 16 * 3; i += blockDim.x) {
+    const int which = i / (n * 16);  // 0 = q, 1 = k, 2 = v
+    const int rem = i - which * n * 16;
+    const int r = rem >> 4, f = rem & 15;
+    // this thread produces dims {f, f+16, f+32, f+48} of row r
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n; ++j) {
+      float w;
+      const float* src;
+      if (which == 0) {
+        w = sds[r * AT_LD + j] * 0.125f, src = sk + j * AT_LD;  // dQ' = scale * dS K'
+      } else if (which == 1) {
+        w = sds[j * AT_LD + r] * 0.125f, src = sq + j * AT_LD;  // dK' = scale * dS^T Q'
+      } else {
+        w = sp[j * AT_LD + r], src = sdo + j * AT_LD;  // dV' = P^T dO
+      }
+      acc[0] += w * src[f], acc[1] += w * src[f + 16], acc[2] += w * src[f + 32], acc[3] += w * src[f + 48];
+    }
+    if (which < 2 || rotary_v) {
+      const float c = rot[r * 32 + f], s = rot[r * 32 + 16 + f];
+      const float a = acc[0], bb = acc[1];
+      acc[0] = a * c + bb * s;
+      acc[1] = -a * s + bb * c;
+    }
+    __nv_bfloat16* dst = obase + which * inner + (long long)r * ld;
+    dst[f] = __float2bfloat16(acc[0]);
+    dst[f + 16] = __float2bfloat16(acc[1]);
+    dst[f + 32] = __float2bfloat16(acc[2]);
+    dst[f + 48] = __float2bfloat16(acc[3]);
+  }
+}
+
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M,
+                                 int F) {
+  const long long total = M * (F / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (F / 2);
+    const int c = (int)(i % (F / 2)) * 2;
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + c);
+    const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
+    *reinterpret_cast<__nv_bfloat162*>(u + r * F + c) =
+        __floats2bfloat162_rn(__low2float(v) * gelu_f(__low2float(gt)), __high2float(v) * gelu_f(__high2float(gt)));
+  }
+}
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ du,
+                                 __nv_bfloat16* __restrict__ dh, long long M, int F) {
+  const long long total = M * (F / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (F / 2);
+    const int c = (int)(i % (F / 2)) * 2;
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + c);
+    const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
+    const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(du + r * F + c);
+    const float v0 = __low2float(v), v1 = __high2float(v), g0 = __low2float(gt), g1 = __high2float(gt);
+    const float d0 = __low2float(d), d1 = __high2float(d);
+    *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + c) = __floats2bfloat162_rn(d0 * gelu_f(g0), d1 * gelu_f(g1));
+    *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + F + c) =
+        __floats2bfloat162_rn(d0 * v0 * gelu_grad_f(g0), d1 * v1 * gelu_grad_f(g1));
+  }
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK() SVSR_CHECK_CUDA(cudaGetLastError())
+
+int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s) {
+  SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
+  const int blocks = (M + 7) / 8 < 148 * 4 ? (M + 7) / 8 : 148 * 4;
+  if (D <= 512)
+    rmsnorm_fwd_kernel<16><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps);
+  else
+    rmsnorm_fwd_kernel<32><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
+                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s) {
+  SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
+  const int blocks = (M + 7) / 8 < 148 ? (M + 7) / 8 : 148;
+  if (D <= 512)
+    rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps);
+  else
+    rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int rotary_table(float* tab, int n, cudaStream_t s) {
+  rotary_table_kernel<<<(n * 16 + 127) / 128, 128, 0, s>>>(tab, n);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
+                  int rotary_v, cudaStream_t s) {
+  SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
+  const int smem = 4 * AT_MAXN * AT_LD * sizeof(float);
+  static bool done = false;
+  if (!done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
+                  int n, int heads, int rotary_v, cudaStream_t s) {
+  SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
+  const int smem = 6 * AT_MAXN * AT_LD * sizeof(float);
+  static bool done = false;
+  if (!done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  attention_bwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, cudaStream_t s) {
+  const long long total = (long long)M * (F / 2);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, cudaStream_t s) {
+  const long long total = (long long)M * (F / 2);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+
+}  // namespace svsr

@@ -1,0 +1,28 @@
+// Non-GEMM pieces of the x-transformers encoder sublayers (lightning.py:95-105,158):
+// RMSNorm, rotary + softmax attention core for short sequences (n <= 64, dim_head = 64), GEGLU.
+// The projections around them run on the tcgen05 GEMM (igemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace svsr {
+
+// y[M,D] (bf16) = x / clamp(||x||_2 * D^-1/2, eps) * g ; inv[M] = 1 / clamp(...)
+int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s);
+// dx[M,D] (fp32) += d rmsnorm ; dx_bf16 = bf16(dx) ; dg[D] += ...   (dy is the gradient wrt y, bf16)
+int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
+                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s);
+
+// rotary cos/sin table for positions 0..n-1, 16 frequencies (rotary dim 32): tab[pos*32 + i] = cos, [pos*32+16+i] = sin
+int rotary_table(float* tab, int n, cudaStream_t s);
+
+// qkv [B*n, 3*heads*64] bf16 (q | k | v) -> o [B*n, heads*64] bf16; rotary on the first 32 dims of q, k and v
+int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
+                  int rotary_v, cudaStream_t s);
+int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
+                  int n, int heads, int rotary_v, cudaStream_t s);
+
+// u[M,F] = h[:, :F] * gelu(h[:, F:]) ; dh from du
+int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, cudaStream_t s);
+int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, cudaStream_t s);
+
+}  // namespace svsr

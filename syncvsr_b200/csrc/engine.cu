@@ -1,0 +1,747 @@
+// Native step executor for the LRW word-level model (reference: LRW/video/src/lightning.py:36-191).
+// Owns the layout of the flat parameter / gradient / buffer arenas, the activation workspace and the bf16 operand
+// copies of the weights, and sequences every kernel of forward and backward on one stream (no autograd, no
+// per-op Python): stem3d -> resnet.layer1-4 -> mean pool + CLS -> x-transformers encoder -> the two loss heads.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/svsr.h"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "encoder.cuh"
+#include "heads.cuh"
+#include "igemm.cuh"
+#include "wgrad.cuh"
+
+namespace svsr {
+
+#define RC(expr)              \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc) return _rc;      \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+struct ParamInfo {
+  std::string name;
+  int ndim;
+  long long shape[5];
+  long long offset;  // elements into the fp32 arena
+  long long numel;
+  int decay;  // AdamW weight decay applies (ndim >= 2; lightning.py:217-219)
+};
+
+struct BnRef {
+  long long gamma, beta;  // param arena offsets
+  long long rmean, rvar;  // buffer arena offsets
+  int C;
+  size_t coef, kcoef, stats_f, stats_b;  // workspace offsets
+};
+
+struct ConvRef {
+  long long w;  // param arena offset
+  int cin, cout, R, stride, pad;
+  size_t wf, wd;  // packed bf16 operands (fprop / dgrad)
+};
+
+struct BlockRef {
+  int cin, cout, stride, Hin, Hout;
+  bool ds;
+  ConvRef conv1, conv2, convds;
+  BnRef bn1, bn2, bnds;
+  size_t c1, a1, c2, out, cds;  // saved activations (bf16)
+};
+
+struct LinRef {
+  long long w, b;  // param arena offsets (b < 0: no bias)
+  int N, K;
+  size_t wb, wt;  // bf16 [N, K] and transposed [K, ldt]
+  int ldt;
+};
+
+struct EncLayerRef {
+  long long g_a, g_f;
+  LinRef qkv, out, ff1, ff2;
+  size_t xn_a, inv_a, qkvbuf, obuf, xn_f, inv_f, hbuf, ubuf;
+};
+
+struct LrwEngine {
+  svsr_lrw_config cfg;
+  int N;   // frames = B*T
+  int M;   // tokens = B*(T+1)
+  int H0;  // stem conv output size
+  int H1;  // pooled size (layer1 input)
+  std::vector<ParamInfo> params;
+  std::vector<ParamInfo> buffers;
+  long long param_count = 0, buffer_count = 0;
+  size_t ws_bytes = 0;
+
+  // bound storage
+  float* P = nullptr;
+  float* G = nullptr;
+  float* BUF = nullptr;
+  uint8_t* WS = nullptr;
+
+  // model structure
+  ConvRef stem_conv;
+  BnRef stem_bn;
+  BlockRef blocks[8];
+  long long cls_off;
+  std::vector<EncLayerRef> enc;
+  LinRef cat, aud;
+  int cat_ld;  // padded pitch of category logits
+
+  // workspace offsets
+  size_t patches, y0, x1, argmax, xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a,
+      logits_c, dlogits_c, acc, bad_token, rot, stats_arena, stats_arena_bytes;
+  size_t dx, dxb, t_du, t_dh, t_dyn, t_do, t_dqkv, gbuf[5], stem_dz, wgrad_tmp;
+  // forward inputs remembered for backward
+  uint32_t last_skip = 0;
+  bool fwd_done = false;
+
+  template <class T>
+  T* ws(size_t off) const {
+    return reinterpret_cast<T*>(WS + off);
+  }
+  float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * cfg.dim; }
+};
+
+namespace {
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+};
+
+long long add_param(std::vector<ParamInfo>& v, long long& count, const std::string& name,
+                    std::initializer_list<long long> shape) {
+  ParamInfo p;
+  p.name = name;
+  p.ndim = (int)shape.size();
+  p.numel = 1;
+  int i = 0;
+  for (long long s : shape) p.shape[i++] = s, p.numel *= s;
+  for (; i < 5; ++i) p.shape[i] = 1;
+  p.offset = count;
+  p.decay = p.ndim >= 2;
+  count += (p.numel + 3) & ~3LL;  // keep every tensor 16-byte aligned inside the arena
+  v.push_back(p);
+  return p.offset;
+}
+
+void add_bn(LrwEngine& e, BnRef& bn, const std::string& prefix, int C, Bump& b) {
+  bn.C = C;
+  bn.gamma = add_param(e.params, e.param_count, prefix + ".weight", {C});
+  bn.beta = add_param(e.params, e.param_count, prefix + ".bias", {C});
+  bn.rmean = add_param(e.buffers, e.buffer_count, prefix + ".running_mean", {C});
+  bn.rvar = add_param(e.buffers, e.buffer_count, prefix + ".running_var", {C});
+  bn.coef = b.take(4 * C * sizeof(float));
+  bn.kcoef = b.take(2 * C * sizeof(float));
+}
+
+void add_conv(LrwEngine& e, ConvRef& c, const std::string& name, int cin, int cout, int R, int stride, int pad,
+              Bump& b) {
+  c.cin = cin, c.cout = cout, c.R = R, c.stride = stride, c.pad = pad;
+  c.w = add_param(e.params, e.param_count, name, {cout, cin, R, R});
+  c.wf = b.take((size_t)cout * R * R * cin * 2);
+  c.wd = b.take((size_t)cin * R * R * cout * 2);
+}
+
+void add_linear(LrwEngine& e, LinRef& l, const std::string& wname, const std::string& bname, int N, int K, Bump& b) {
+  l.N = N, l.K = K;
+  l.w = add_param(e.params, e.param_count, wname, {N, K});
+  l.b = bname.empty() ? -1 : add_param(e.params, e.param_count, bname, {N});
+  l.ldt = (N + 63) / 64 * 64;
+  l.wb = b.take((size_t)N * K * 2);
+  l.wt = b.take((size_t)K * l.ldt * 2);
+}
+
+int conv_out(int h, int k, int s, int p) { return (h + 2 * p - k) / s + 1; }
+
+}  // namespace
+
+static int engine_build(LrwEngine& e) {
+  const svsr_lrw_config& c = e.cfg;
+  SVSR_REQUIRE(c.B > 0 && c.T > 0 && c.H > 0 && c.W == c.H, "lrw: bad clip geometry B=%d T=%d H=%d W=%d", c.B, c.T,
+               c.H, c.W);
+  SVSR_REQUIRE(c.dim == 512 && c.heads * 64 == 512, "lrw: encoder dim must be 512 with 8 heads of 64 (got %d/%d)",
+               c.dim, c.heads);
+  SVSR_REQUIRE(c.depth >= 1 && c.depth <= 16, "lrw: depth %d out of range", c.depth);
+  SVSR_REQUIRE(c.T + 1 <= 64, "lrw: sequence length %d too long for the attention core", c.T + 1);
+  SVSR_REQUIRE((c.audio_alignment * c.vq_groups * c.audio_vocab) % 64 == 0,
+               "lrw: audio logits per frame (%d) must be a multiple of 64",
+               c.audio_alignment * c.vq_groups * c.audio_vocab);
+  e.N = c.B * c.T;
+  e.M = c.B * (c.T + 1);
+  e.H0 = conv_out(c.H, 7, 2, 3);
+  e.H1 = conv_out(e.H0, 3, 2, 1);
+  Bump b;
+
+  // ---- parameters (reference state-dict names) + packed operand storage ----
+  e.stem_conv.cin = 1, e.stem_conv.cout = 64;
+  e.stem_conv.w = add_param(e.params, e.param_count, "stem3d.0.weight", {64, 1, 5, 7, 7});
+  e.stem_conv.wf = b.take(64 * 320 * 2);
+  add_bn(e, e.stem_bn, "stem3d.1", 64, b);
+  int cin = 64, h = e.H1;
+  const int widths[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    for (int bi = 0; bi < 2; ++bi) {
+      BlockRef& blk = e.blocks[li * 2 + bi];
+      const std::string pre = "resnet.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      blk.cin = bi == 0 ? cin : widths[li];
+      blk.cout = widths[li];
+      blk.stride = (bi == 0 && li > 0) ? 2 : 1;
+      blk.Hin = h;
+      blk.Hout = conv_out(h, 3, blk.stride, 1);
+      blk.ds = (bi == 0 && li > 0);
+      add_conv(e, blk.conv1, pre + ".conv1.weight", blk.cin, blk.cout, 3, blk.stride, 1, b);
+      add_bn(e, blk.bn1, pre + ".bn1", blk.cout, b);
+      add_conv(e, blk.conv2, pre + ".conv2.weight", blk.cout, blk.cout, 3, 1, 1, b);
+      add_bn(e, blk.bn2, pre + ".bn2", blk.cout, b);
+      if (blk.ds) {
+        add_conv(e, blk.convds, pre + ".downsample.0.weight", blk.cin, blk.cout, 1, blk.stride, 0, b);
+        add_bn(e, blk.bnds, pre + ".downsample.1", blk.cout, b);
+      }
+      h = blk.Hout;
+      const size_t act = (size_t)e.N * blk.Hout * blk.Hout * blk.cout * 2;
+      blk.c1 = b.take(act), blk.a1 = b.take(act), blk.c2 = b.take(act), blk.out = b.take(act);
+      blk.cds = blk.ds ? b.take(act) : 0;
+    }
+    cin = widths[li];
+  }
+  e.cls_off = add_param(e.params, e.param_count, "cls_token", {1, 1, c.dim});
+  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  e.enc.resize(c.depth);
+  for (int i = 0; i < c.depth; ++i) {
+    EncLayerRef& L = e.enc[i];
+    const std::string a = "encoder.layers." + std::to_string(2 * i), f = "encoder.layers." + std::to_string(2 * i + 1);
+    L.g_a = add_param(e.params, e.param_count, a + ".0.g", {D});
+    // to_q / to_k / to_v are adjacent in the arena so that they form one [3*inner, D] operand and gradient
+    L.qkv.N = 3 * inner, L.qkv.K = D, L.qkv.b = -1;
+    L.qkv.w = add_param(e.params, e.param_count, a + ".1.to_q.weight", {inner, D});
+    add_param(e.params, e.param_count, a + ".1.to_k.weight", {inner, D});
+    add_param(e.params, e.param_count, a + ".1.to_v.weight", {inner, D});
+    L.qkv.ldt = 3 * inner;
+    L.qkv.wb = b.take((size_t)3 * inner * D * 2);
+    L.qkv.wt = b.take((size_t)D * 3 * inner * 2);
+    add_linear(e, L.out, a + ".1.to_out.weight", "", D, inner, b);
+    L.g_f = add_param(e.params, e.param_count, f + ".0.g", {D});
+    add_linear(e, L.ff1, f + ".1.ff.0.proj.weight", f + ".1.ff.0.proj.bias", 2 * F, D, b);
+    add_linear(e, L.ff2, f + ".1.ff.3.weight", f + ".1.ff.3.bias", D, F, b);
+    L.xn_a = b.take((size_t)e.M * D * 2), L.inv_a = b.take((size_t)e.M * 4);
+    L.qkvbuf = b.take((size_t)e.M * 3 * inner * 2), L.obuf = b.take((size_t)e.M * inner * 2);
+    L.xn_f = b.take((size_t)e.M * D * 2), L.inv_f = b.take((size_t)e.M * 4);
+    L.hbuf = b.take((size_t)e.M * 2 * F * 2), L.ubuf = b.take((size_t)e.M * F * 2);
+  }
+  add_linear(e, e.cat, "category_classifier.weight", "category_classifier.bias", c.num_labels, D, b);
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  add_linear(e, e.aud, "audio_projection.weight", "audio_projection.bias", AGV, D, b);
+  e.cat_ld = (c.num_labels + 63) / 64 * 64;
+
+  // ---- activations ----
+  const size_t n0 = (size_t)e.N * e.H0 * e.H0 * 64;
+  e.patches = b.take(n0 * 2);
+  e.y0 = b.take(n0 * 2);
+  const size_t n1 = (size_t)e.N * e.H1 * e.H1 * 64;
+  e.x1 = b.take(n1 * 2);
+  e.argmax = b.take(n1);
+  e.xs = b.take((size_t)(2 * c.depth + 1) * e.M * D * 4);
+  e.lastb_cls = b.take((size_t)c.B * D * 2);
+  e.lastb_frames = b.take((size_t)e.N * D * 2);
+  e.logits_a = b.take((size_t)e.N * AGV * 4);
+  e.dlogits_a = b.take((size_t)e.N * AGV * 2);
+  e.logits_c = b.take((size_t)c.B * e.cat_ld * 4);
+  e.dlogits_c = b.take((size_t)c.B * e.cat_ld * 2);
+  e.acc = b.take(8 * sizeof(double));
+  e.bad_token = b.take(sizeof(int));
+  e.rot = b.take((size_t)(c.T + 1) * 32 * 4);
+  // BN statistic accumulators (fp64): forward and backward slot per BN, zeroed once per step
+  {
+    Bump sb;
+    auto slot = [&](BnRef& bn) {
+      bn.stats_f = sb.take(2 * bn.C * sizeof(double));
+      bn.stats_b = sb.take(2 * bn.C * sizeof(double));
+    };
+    slot(e.stem_bn);
+    for (auto& blk : e.blocks) {
+      slot(blk.bn1), slot(blk.bn2);
+      if (blk.ds) slot(blk.bnds);
+    }
+    e.stats_arena_bytes = sb.off;
+    e.stats_arena = b.take(sb.off);
+    auto fix = [&](BnRef& bn) { bn.stats_f += e.stats_arena, bn.stats_b += e.stats_arena; };
+    fix(e.stem_bn);
+    for (auto& blk : e.blocks) {
+      fix(blk.bn1), fix(blk.bn2);
+      if (blk.ds) fix(blk.bnds);
+    }
+  }
+  // ---- backward scratch ----
+  e.dx = b.take((size_t)e.M * D * 4);
+  e.dxb = b.take((size_t)e.M * D * 2);
+  e.t_du = b.take((size_t)e.M * F * 2);
+  e.t_dh = b.take((size_t)e.M * 2 * F * 2);
+  e.t_dyn = b.take((size_t)e.M * D * 2);
+  e.t_do = b.take((size_t)e.M * inner * 2);
+  e.t_dqkv = b.take((size_t)e.M * 3 * inner * 2);
+  for (int i = 0; i < 5; ++i) e.gbuf[i] = b.take(n1 * 2);
+  e.stem_dz = b.take(n0 * 2);
+  e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
+  e.ws_bytes = b.off;
+  return SVSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small launch helpers
+// ------------------------------------------------------------------------------------------------
+static int linear_fwd(const LrwEngine& e, const bf16* x, int M, const LinRef& l, void* out, int ldc, int out_fp32,
+                      const void* resid, int resid_fp32, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = x, p.a_N = M, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wb), p.b_rows = l.N, p.b_cols = l.K;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
+  p.bias = l.b >= 0 ? e.P + l.b : nullptr;
+  p.resid = resid, p.resid_fp32 = resid_fp32;
+  return igemm_launch(p, s);
+}
+// dx[M, K] = dy[M, N(ld = ldy)] . W   (uses the transposed operand copy)
+static int linear_dgrad(const LrwEngine& e, const bf16* dy, int ldy, int M, const LinRef& l, void* out, int ldc,
+                        int out_fp32, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = dy, p.a_N = M, p.a_C = ldy, p.cin = l.ldt, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wt), p.b_rows = l.K, p.b_cols = l.ldt;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
+  return igemm_launch(p, s);
+}
+static int linear_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, int M, const LinRef& l,
+                        cudaStream_t s) {
+  WgradProblem p;
+  p.a = dy, p.a_N = M, p.a_C = ldy, p.a_cin = l.ldt, p.ntaps = 1;
+  p.b = x, p.b_C = l.K, p.n_cols = l.K;
+  p.k_N = M;
+  p.out = e.G + l.w, p.ldo = l.K, p.m_valid = l.N;
+  RC(wgrad_launch(p, s));
+  if (l.b >= 0) RC(colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s));
+  return SVSR_OK;
+}
+
+static int conv_fwd(const LrwEngine& e, const bf16* x, int Hin, const ConvRef& c, bf16* y, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = x, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = c.cin, p.cin = c.cin, p.stride = c.stride;
+  p.ntaps = c.R * c.R;
+  for (int r = 0; r < c.R; ++r)
+    for (int q = 0; q < c.R; ++q) {
+      const int t = r * c.R + q;
+      p.tap_dh[t] = r - c.pad, p.tap_dw[t] = q - c.pad, p.tap_kbase[t] = t * c.cin;
+    }
+  const int Ho = conv_out(Hin, c.R, c.stride, c.pad);
+  p.o_N = e.N, p.OH = Ho, p.OW = Ho;
+  p.b = e.ws<bf16>(c.wf), p.b_rows = c.cout, p.b_cols = c.R * c.R * c.cin;
+  p.out = y, p.ldc = c.cout, p.o_H = Ho, p.o_W = Ho;
+  return igemm_launch(p, s);
+}
+extern "C" int svsr_conv2d_dgrad(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int,
+                                 int, int, void*);
+static int conv_dgrad(const LrwEngine& e, const bf16* dy, int Hin, const ConvRef& c, bf16* dx, const bf16* resid,
+                      cudaStream_t s) {
+  return svsr_conv2d_dgrad(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride, c.pad, 0,
+                           s);
+}
+static int conv_wgrad(const LrwEngine& e, const bf16* x, int Hin, const bf16* dy, const ConvRef& c, cudaStream_t s) {
+  float* tmp = e.ws<float>(e.wgrad_tmp);
+  const size_t n = (size_t)c.R * c.R * c.cin * c.cout;
+  SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, n * 4, s));
+  WgradProblem p;
+  p.a = x, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = c.cin, p.a_cin = c.cin, p.a_stride = c.stride;
+  p.ntaps = c.R * c.R;
+  for (int r = 0; r < c.R; ++r)
+    for (int q = 0; q < c.R; ++q) p.tap_dh[r * c.R + q] = r - c.pad, p.tap_dw[r * c.R + q] = q - c.pad;
+  const int Ho = conv_out(Hin, c.R, c.stride, c.pad);
+  p.b = dy, p.b_C = c.cout, p.n_cols = c.cout;
+  p.k_N = e.N, p.k_H = Ho, p.k_W = Ho;
+  p.out = tmp, p.ldo = c.cout;
+  RC(wgrad_launch(p, s));
+  return unpack_conv_wgrad(tmp, e.G + c.w, c.cout, c.cin, c.R, c.R, s);
+}
+
+static int bn_fwd(const LrwEngine& e, const bf16* x, long long rows, const BnRef& bn, int train, cudaStream_t s) {
+  if (train) RC(bn_stats(x, rows, bn.C, e.ws<double>(bn.stats_f), s));
+  return bn_finalize(e.ws<double>(bn.stats_f), rows, bn.C, e.P + bn.gamma, e.P + bn.beta, e.cfg.bn_eps,
+                     e.cfg.bn_momentum, e.BUF + bn.rmean, e.BUF + bn.rvar, e.ws<float>(bn.coef), train ? 1 : -1, s);
+}
+// full BN backward: returns dc (may alias nothing); optionally emits the relu-masked upstream gradient
+static int bn_bwd(const LrwEngine& e, const bf16* dout, const bf16* relu_ref, const bf16* c, long long rows,
+                  const BnRef& bn, bf16* dc, bf16* gmask_out, cudaStream_t s) {
+  RC(bn_bwd_reduce(dout, relu_ref, c, e.ws<float>(bn.coef), rows, bn.C, e.ws<double>(bn.stats_b), s));
+  RC(bn_bwd_finalize(e.ws<double>(bn.stats_b), rows, bn.C, e.G + bn.gamma, e.G + bn.beta, e.ws<float>(bn.kcoef), s));
+  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, gmask_out, rows, bn.C, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int engine_pack(LrwEngine& e, cudaStream_t s) {
+  RC(pack_stem_weight(e.P + e.stem_conv.w, e.ws<bf16>(e.stem_conv.wf), s));
+  for (auto& blk : e.blocks) {
+    RC(pack_conv_weight(e.P + blk.conv1.w, e.ws<bf16>(blk.conv1.wf), e.ws<bf16>(blk.conv1.wd), blk.conv1.cout,
+                        blk.conv1.cin, 3, 3, s));
+    RC(pack_conv_weight(e.P + blk.conv2.w, e.ws<bf16>(blk.conv2.wf), e.ws<bf16>(blk.conv2.wd), blk.conv2.cout,
+                        blk.conv2.cin, 3, 3, s));
+    if (blk.ds)
+      RC(pack_conv_weight(e.P + blk.convds.w, e.ws<bf16>(blk.convds.wf), e.ws<bf16>(blk.convds.wd), blk.convds.cout,
+                          blk.convds.cin, 1, 1, s));
+  }
+  auto pack_lin = [&](const LinRef& l) -> int {
+    if (l.ldt != l.N) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<bf16>(l.wt), 0, (size_t)l.K * l.ldt * 2, s));
+    return pack_linear_weight(e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), l.N, l.K, l.K, l.ldt, s);
+  };
+  for (auto& L : e.enc) {
+    RC(pack_lin(L.qkv));
+    RC(pack_lin(L.out));
+    RC(pack_lin(L.ff1));
+    RC(pack_lin(L.ff2));
+  }
+  RC(pack_lin(e.cat));
+  RC(pack_lin(e.aud));
+  RC(rotary_table(e.ws<float>(e.rot), e.cfg.T + 1, s));
+  return SVSR_OK;
+}
+
+static int engine_forward(LrwEngine& e, const float* videos, const long long* tokens, long long tok_stride_b,
+                          const long long* labels, const float* soft_labels, int train, uint32_t skip_mask,
+                          float* metrics, int videos_only, cudaStream_t s) {
+  const svsr_lrw_config& c = e.cfg;
+  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.stats_arena), 0, e.stats_arena_bytes, s));
+  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));  // acc + bad_token
+
+  // ---- stem3d (lightning.py:49-54): 7x7/s2 patch gather, 5-tap temporal implicit GEMM, BN3d+GELU+maxpool ----
+  RC(stem_patch(videos, e.ws<bf16>(e.patches), c.B, c.T, c.H, c.W, s));
+  {
+    IgemmProblem p;
+    p.a = e.ws<bf16>(e.patches), p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 64, p.cin = 64;
+    p.ntaps = 5;
+    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0, p.tap_kbase[kt] = kt * 64;
+    p.o_N = c.B, p.OH = c.T, p.OW = e.H0 * e.H0;
+    p.b = e.ws<bf16>(e.stem_conv.wf), p.b_rows = 64, p.b_cols = 320;
+    p.out = e.ws<bf16>(e.y0), p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
+    RC(igemm_launch(p, s));
+  }
+  RC(bn_fwd(e, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
+  RC(stem_bn_gelu_pool(e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), e.ws<bf16>(e.x1), e.ws<uint8_t>(e.argmax), e.N,
+                       e.H0, e.H0, s));
+
+  // ---- resnet.layer1-4 (lightning.py:114-117) ----
+  const bf16* x = e.ws<bf16>(e.x1);
+  for (auto& blk : e.blocks) {
+    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
+    RC(conv_fwd(e, x, blk.Hin, blk.conv1, e.ws<bf16>(blk.c1), s));
+    RC(bn_fwd(e, e.ws<bf16>(blk.c1), rows, blk.bn1, train, s));
+    RC(bn_apply(e.ws<bf16>(blk.c1), e.ws<float>(blk.bn1.coef), nullptr, nullptr, 1, e.ws<bf16>(blk.a1), rows, blk.cout,
+                s));
+    RC(conv_fwd(e, e.ws<bf16>(blk.a1), blk.Hout, blk.conv2, e.ws<bf16>(blk.c2), s));
+    RC(bn_fwd(e, e.ws<bf16>(blk.c2), rows, blk.bn2, train, s));
+    if (blk.ds) {
+      RC(conv_fwd(e, x, blk.Hin, blk.convds, e.ws<bf16>(blk.cds), s));
+      RC(bn_fwd(e, e.ws<bf16>(blk.cds), rows, blk.bnds, train, s));
+      RC(bn_apply(e.ws<bf16>(blk.c2), e.ws<float>(blk.bn2.coef), e.ws<bf16>(blk.cds), e.ws<float>(blk.bnds.coef), 1,
+                  e.ws<bf16>(blk.out), rows, blk.cout, s));
+    } else {
+      RC(bn_apply(e.ws<bf16>(blk.c2), e.ws<float>(blk.bn2.coef), x, nullptr, 1, e.ws<bf16>(blk.out), rows, blk.cout,
+                  s));
+    }
+    x = e.ws<bf16>(blk.out);
+  }
+  // ---- mean((2,3)) + CLS concat (lightning.py:118,148-150) ----
+  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  RC(meanpool_cls(x, e.P + e.cls_off, e.xs_buf(0), c.B, c.T, HW4, D, s));
+  if (videos_only) return SVSR_OK;
+
+  // ---- encoder (lightning.py:158) ----
+  for (int i = 0; i < c.depth; ++i) {
+    EncLayerRef& L = e.enc[i];
+    float* xa = e.xs_buf(2 * i);
+    float* xf = e.xs_buf(2 * i + 1);
+    float* xo = e.xs_buf(2 * i + 2);
+    if (skip_mask & (1u << (2 * i))) {
+      SVSR_CHECK_CUDA(cudaMemcpyAsync(xf, xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      RC(rmsnorm_fwd(xa, e.P + L.g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, D, 1e-8f, s));
+      RC(linear_fwd(e, e.ws<bf16>(L.xn_a), e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, 0, s));
+      RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
+                       s));
+      RC(linear_fwd(e, e.ws<bf16>(L.obuf), e.M, L.out, xf, D, 1, xa, 1, s));
+    }
+    if (skip_mask & (1u << (2 * i + 1))) {
+      SVSR_CHECK_CUDA(cudaMemcpyAsync(xo, xf, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      RC(rmsnorm_fwd(xf, e.P + L.g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, D, 1e-8f, s));
+      RC(linear_fwd(e, e.ws<bf16>(L.xn_f), e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * F, 0, nullptr, 0, s));
+      RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, F, s));
+      RC(linear_fwd(e, e.ws<bf16>(L.ubuf), e.M, L.ff2, xo, D, 1, xf, 1, s));
+    }
+  }
+  const float* last = e.xs_buf(2 * c.depth);
+  RC(split_cast_last(last, e.ws<bf16>(e.lastb_cls), e.ws<bf16>(e.lastb_frames), c.B, c.T, D, s));
+
+  // ---- heads + losses (lightning.py:161-174) ----
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  RC(linear_fwd(e, e.ws<bf16>(e.lastb_cls), c.B, e.cat, e.ws<float>(e.logits_c), e.cat_ld, 1, nullptr, 0, s));
+  RC(linear_fwd(e, e.ws<bf16>(e.lastb_frames), e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, 0, s));
+  const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
+  RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing,
+                 e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<double>(e.acc), 1.0f / (float)c.B, s));
+  RC(audio_ce(e.ws<float>(e.logits_a), AGV, tokens, tok_stride_b, c.B, c.T, c.audio_alignment, c.vq_groups,
+              c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc), e.ws<int>(e.bad_token),
+              c.lambda_audio / (float)audio_rows, s));
+  RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s));
+  e.last_skip = skip_mask;
+  e.fwd_done = true;
+  return SVSR_OK;
+}
+
+static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s) {
+  SVSR_REQUIRE(e.fwd_done, "lrw backward called before (or twice after) forward");
+  e.fwd_done = false;
+  const svsr_lrw_config& c = e.cfg;
+  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  float* dx = e.ws<float>(e.dx);
+  bf16* dxb = e.ws<bf16>(e.dxb);
+
+  if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients
+    RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
+    RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)c.B * e.cat_ld, grad_scale, s));
+  }
+  // ---- heads: d last_hidden_state (fp32 stream gradient), weight/bias gradients ----
+  {
+    IgemmProblem p;  // CLS rows: dx[b, 0, :] = dlogits_c[b] . Wc
+    p.a = e.ws<bf16>(e.dlogits_c), p.a_N = c.B, p.a_C = e.cat_ld, p.cin = e.cat.ldt, p.ntaps = 1;
+    p.o_N = c.B, p.OH = 1, p.OW = 1;
+    p.b = e.ws<bf16>(e.cat.wt), p.b_rows = D, p.b_cols = e.cat.ldt;
+    p.out = dx, p.out_fp32 = 1, p.ldc = D, p.o_H = 1, p.o_W = c.T + 1, p.o_ow = 0;
+    RC(igemm_launch(p, s));
+    IgemmProblem q;  // frame rows: dx[b, 1+t, :] = dlogits_a[b, t] . Wa
+    q.a = e.ws<bf16>(e.dlogits_a), q.a_N = c.B, q.a_H = 1, q.a_W = c.T, q.a_C = AGV, q.cin = AGV, q.ntaps = 1;
+    q.o_N = c.B, q.OH = 1, q.OW = c.T;
+    q.b = e.ws<bf16>(e.aud.wt), q.b_rows = D, q.b_cols = e.aud.ldt;
+    q.out = dx, q.out_fp32 = 1, q.ldc = D, q.o_H = 1, q.o_W = c.T + 1, q.o_ow = 1;
+    RC(igemm_launch(q, s));
+  }
+  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<bf16>(e.lastb_cls), c.B, e.cat, s));
+  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), AGV, e.ws<bf16>(e.lastb_frames), e.N, e.aud, s));
+  RC(cast_f32_to_bf16(dx, dxb, (long long)e.M * D, s));
+
+  // ---- encoder, reversed ----
+  for (int i = c.depth - 1; i >= 0; --i) {
+    EncLayerRef& L = e.enc[i];
+    if (!(e.last_skip & (1u << (2 * i + 1)))) {
+      bf16* du = e.ws<bf16>(e.t_du);
+      bf16* dh = e.ws<bf16>(e.t_dh);
+      bf16* dyn = e.ws<bf16>(e.t_dyn);
+      RC(linear_dgrad(e, dxb, D, e.M, L.ff2, du, F, 0, s));
+      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.ubuf), e.M, L.ff2, s));
+      RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, F, s));
+      RC(linear_dgrad(e, dh, 2 * F, e.M, L.ff1, dyn, D, 0, s));
+      RC(linear_wgrad(e, dh, 2 * F, e.ws<bf16>(L.xn_f), e.M, L.ff1, s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), e.P + L.g_f, e.ws<float>(L.inv_f), dx, dxb, e.G + L.g_f, e.M, D, 1e-8f,
+                     s));
+    }
+    if (!(e.last_skip & (1u << (2 * i)))) {
+      bf16* d_o = e.ws<bf16>(e.t_do);
+      bf16* dqkv = e.ws<bf16>(e.t_dqkv);
+      bf16* dyn = e.ws<bf16>(e.t_dyn);
+      RC(linear_dgrad(e, dxb, D, e.M, L.out, d_o, inner, 0, s));
+      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.obuf), e.M, L.out, s));
+      RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s));
+      RC(linear_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, D, 0, s));
+      RC(linear_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), e.M, L.qkv, s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), e.P + L.g_a, e.ws<float>(L.inv_a), dx, dxb, e.G + L.g_a, e.M, D, 1e-8f, s));
+    }
+  }
+
+  // ---- mean pool / CLS ----
+  bf16* T0 = e.ws<bf16>(e.gbuf[0]);  // dOut of the current block, later da1
+  bf16* T1 = e.ws<bf16>(e.gbuf[1]);  // dc2, later dc1
+  bf16* T2 = e.ws<bf16>(e.gbuf[2]);  // relu-masked upstream gradient (identity shortcut branch)
+  bf16* T3 = e.ws<bf16>(e.gbuf[3]);  // dcds
+  bf16* T4 = e.ws<bf16>(e.gbuf[4]);  // dX of the current block
+  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, D, s));
+
+  // ---- resnet trunk, reversed ----
+  for (int bi = 7; bi >= 0; --bi) {
+    BlockRef& blk = e.blocks[bi];
+    const bf16* xin = bi == 0 ? e.ws<bf16>(e.x1) : e.ws<bf16>(e.blocks[bi - 1].out);
+    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
+    const bf16* out = e.ws<bf16>(blk.out);
+    RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, T1, blk.ds ? nullptr : T2, s));
+    if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, T3, nullptr, s));
+    RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, T1, blk.conv2, s));
+    RC(conv_dgrad(e, T1, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
+    RC(bn_bwd(e, T0, e.ws<bf16>(blk.a1), e.ws<bf16>(blk.c1), rows, blk.bn1, T1, nullptr, s));  // T1 := dc1
+    RC(conv_wgrad(e, xin, blk.Hin, T1, blk.conv1, s));
+    if (blk.ds) {
+      RC(conv_wgrad(e, xin, blk.Hin, T3, blk.convds, s));
+      SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
+      RC(conv_dgrad(e, T3, blk.Hin, blk.convds, T4, nullptr, s));
+      RC(conv_dgrad(e, T1, blk.Hin, blk.conv1, T4, T4, s));
+    } else {
+      RC(conv_dgrad(e, T1, blk.Hin, blk.conv1, T4, T2, s));
+    }
+    bf16* t = T0;
+    T0 = T4, T4 = t;
+  }
+
+  // ---- stem ----
+  bf16* dz = e.ws<bf16>(e.stem_dz);
+  RC(stem_pool_gelu_bwd(T0, e.ws<uint8_t>(e.argmax), e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), dz, e.N, e.H0,
+                        e.H0, s));
+  RC(bn_bwd(e, dz, nullptr, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, dz, nullptr, s));
+  {
+    float* tmp = e.ws<float>(e.wgrad_tmp);
+    SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, 320 * 64 * 4, s));
+    WgradProblem p;
+    p.a = e.ws<bf16>(e.patches), p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 64, p.a_cin = 64;
+    p.ntaps = 5;
+    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0;
+    p.b = dz, p.b_C = 64, p.n_cols = 64;
+    p.k_N = c.B, p.k_H = c.T, p.k_W = e.H0 * e.H0;
+    p.out = tmp, p.ldo = 64;
+    RC(wgrad_launch(p, s));
+    RC(unpack_stem_wgrad(tmp, e.G + e.stem_conv.w, s));
+  }
+  return SVSR_OK;
+}
+
+}  // namespace svsr
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace svsr;
+
+extern "C" {
+
+int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle) {
+  SVSR_REQUIRE(cfg && handle, "lrw_create: null argument");
+  LrwEngine* e = new LrwEngine();
+  e->cfg = *cfg;
+  int rc = engine_build(*e);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *handle = e;
+  return SVSR_OK;
+}
+int svsr_lrw_destroy(void* h) {
+  delete static_cast<LrwEngine*>(h);
+  return SVSR_OK;
+}
+int64_t svsr_lrw_param_count(void* h) { return static_cast<LrwEngine*>(h)->param_count; }
+int64_t svsr_lrw_buffer_count(void* h) { return static_cast<LrwEngine*>(h)->buffer_count; }
+int64_t svsr_lrw_workspace_bytes(void* h) { return (int64_t)static_cast<LrwEngine*>(h)->ws_bytes; }
+int svsr_lrw_num_params(void* h) { return (int)static_cast<LrwEngine*>(h)->params.size(); }
+int svsr_lrw_num_buffers(void* h) { return (int)static_cast<LrwEngine*>(h)->buffers.size(); }
+
+static int info(const std::vector<ParamInfo>& v, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset,
+                int* decay) {
+  SVSR_REQUIRE(i >= 0 && i < (int)v.size(), "lrw: tensor index %d out of range", i);
+  *name = v[i].name.c_str();
+  *ndim = v[i].ndim;
+  for (int k = 0; k < 5; ++k) shape[k] = v[i].shape[k];
+  *offset = v[i].offset;
+  if (decay) *decay = v[i].decay;
+  return SVSR_OK;
+}
+int svsr_lrw_param_info(void* h, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset, int* decay) {
+  return info(static_cast<LrwEngine*>(h)->params, i, name, ndim, shape, offset, decay);
+}
+int svsr_lrw_buffer_info(void* h, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset) {
+  return info(static_cast<LrwEngine*>(h)->buffers, i, name, ndim, shape, offset, nullptr);
+}
+int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* workspace, int64_t workspace_bytes) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(params && grads && buffers && workspace, "lrw_bind: null pointer");
+  SVSR_REQUIRE((size_t)workspace_bytes >= e->ws_bytes, "lrw_bind: workspace too small (%lld < %zu)",
+               (long long)workspace_bytes, e->ws_bytes);
+  SVSR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0,
+               "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
+  e->P = params, e->G = grads, e->BUF = buffers, e->WS = static_cast<uint8_t*>(workspace);
+  return SVSR_OK;
+}
+int svsr_lrw_pack_weights(void* h, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  return engine_pack(*e, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
+                     const float* soft_labels, int train, uint32_t skip_mask, float* metrics, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  SVSR_REQUIRE(videos && tokens && metrics, "lrw_forward: null input");
+  SVSR_REQUIRE(tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
+               "lrw_forward: audio_tokens has fewer than T*alignment rows per clip");
+  return engine_forward(*e, videos, reinterpret_cast<const long long*>(tokens), tok_stride_b,
+                        reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask, metrics, 0,
+                        static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_forward_videos(void* h, const float* videos, int train, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  SVSR_REQUIRE(videos, "lrw_forward_videos: null input");
+  return engine_forward(*e, videos, nullptr, 0, nullptr, nullptr, train, 0, nullptr, 1,
+                        static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_backward(void* h, const float* grad_scale, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  return engine_backward(*e, grad_scale, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* dtype) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  const svsr_lrw_config& c = e->cfg;
+  const std::string n(name);
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  auto set = [&](size_t off, int64_t ne, int dt) {
+    *ptr = e->WS + off, *numel = ne, *dtype = dt;
+    return SVSR_OK;
+  };
+  if (n == "last_hidden_state") {
+    *ptr = e->xs_buf(2 * c.depth), *numel = (int64_t)e->M * c.dim, *dtype = 0;
+    return SVSR_OK;
+  }
+  if (n == "inputs_embeds") {
+    *ptr = e->xs_buf(0), *numel = (int64_t)e->M * c.dim, *dtype = 0;
+    return SVSR_OK;
+  }
+  if (n == "logits_audio") return set(e->logits_a, (int64_t)e->N * AGV, 0);
+  if (n == "logits_category") return set(e->logits_c, (int64_t)c.B * e->cat_ld, 0);
+  if (n == "stem_conv") return set(e->y0, (int64_t)e->N * e->H0 * e->H0 * 64, 1);
+  if (n == "stem_out") return set(e->x1, (int64_t)e->N * e->H1 * e->H1 * 64, 1);
+  if (n == "bad_token") return set(e->bad_token, 1, 3);
+  if (n.rfind("block", 0) == 0 && n.size() >= 6) {  // "block<i>.out|c1|a1|c2"
+    const int bi = n[5] - '0';
+    SVSR_REQUIRE(bi >= 0 && bi < 8 && n.size() > 7, "lrw_tensor: bad block tensor %s", name);
+    const BlockRef& blk = e->blocks[bi];
+    const int64_t ne = (int64_t)e->N * blk.Hout * blk.Hout * blk.cout;
+    const std::string f = n.substr(7);
+    if (f == "out") return set(blk.out, ne, 1);
+    if (f == "c1") return set(blk.c1, ne, 1);
+    if (f == "a1") return set(blk.a1, ne, 1);
+    if (f == "c2") return set(blk.c2, ne, 1);
+  }
+  set_last_error("lrw_tensor: unknown tensor '%s'", name);
+  return SVSR_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -17,6 +17,7 @@ struct WgradKParams {
   int b_coff, n_cols;
   float* out;
   int ldo;
+  int m_valid;
 };
 
 template <int BN, int STAGES>
@@ -146,7 +147,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tcgen05_fence_after();
     for (int mbi = 0; mbi < mb_cnt; ++mbi) {
       const int g = 2 * (mb0 + mbi) + (r >> 6);
-      const bool row_valid = (g < p.ngroups) && (my_ktiles > 0);
+      const bool row_valid = (g < p.ngroups) && (my_ktiles > 0) && (g * 64 + (r & 63) < p.m_valid);
       float* orow = p.out + (long long)(g * 64 + (r & 63)) * p.ldo;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
@@ -203,6 +204,7 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
   for (int t = 0; t < p.ntaps; ++t) kp.tap_dh[t] = p.tap_dh[t], kp.tap_dw[t] = p.tap_dw[t];
   kp.b_coff = p.b_coff, kp.n_cols = p.n_cols;
   kp.out = p.out, kp.ldo = p.ldo;
+  kp.m_valid = p.m_valid > 0 ? p.m_valid : p.ntaps * p.a_cin;
 
   const int BN = p.n_cols <= 64 ? 64 : (p.n_cols <= 128 ? 128 : 256);
   const int num_mblocks = (kp.ngroups + 1) / 2;

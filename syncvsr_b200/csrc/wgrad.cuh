@@ -25,6 +25,7 @@ struct WgradProblem {
   // D: fp32 [ntaps * a_cin, n_cols] with pitch ldo, row index = tap * a_cin + channel. Accumulated into (+=).
   float* out = nullptr;
   int ldo = 0;
+  int m_valid = 0;  // rows of D actually written (0 = all ntaps * a_cin)
 };
 
 int wgrad_launch(const WgradProblem& p, cudaStream_t stream);

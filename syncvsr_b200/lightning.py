@@ -1,0 +1,396 @@
+"""Host-side mirror of the reference's LRW module (/root/reference/LRW/video/src/lightning.py:36-223).
+
+`TransformerLightningModule(config)` keeps the reference's constructor argument, attribute names
+(`stem3d`, `resnet.layer1..4`, `encoder`, `audio_projection`, `category_classifier`, `cls_token`, `lambda_audio`,
+`audio_alignment`, `vq_groups`, `audio_vocab_size`, `codec`), `forward_videos`, `forward(videos, audio_tokens,
+labels, word_mask) -> dict`, `training_step/validation_step/test_step`, `configure_optimizers` and state-dict keys,
+so the reference's training loop can construct it and load the reference's checkpoints. All arithmetic runs in the
+sm_100a kernels of libsvsr.so through the native step executor (csrc/engine.cu); PyTorch only owns the memory
+(three flat fp32 arenas + one workspace) and the autograd hook that makes `loss_total.backward()` work.
+There is no CPU / eager fallback: without the shared library or a CUDA device construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from ._lib import SvsrError, check, lib
+
+
+class LrwConfig(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("dim", C.c_int), ("depth", C.c_int), ("heads", C.c_int),
+        ("audio_alignment", C.c_int), ("vq_groups", C.c_int), ("audio_vocab", C.c_int),
+        ("num_labels", C.c_int), ("rotary_v", C.c_int),
+        ("lambda_audio", C.c_float), ("label_smoothing", C.c_float),
+        ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+    ]
+
+
+def _cfg_get(cfg: Any, path: str, default: Any = None) -> Any:
+    cur = cfg
+    for key in path.split("."):
+        if cur is None:
+            return default
+        if isinstance(cur, dict):
+            cur = cur.get(key, None)
+        else:
+            cur = getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's module tree (and therefore its state-dict keys)."""
+
+
+class _StepFunction(torch.autograd.Function):
+    """Makes `metrics['loss_total'].backward()` run the native backward. Gradients are accumulated straight into the
+    flat gradient arena that every parameter's `.grad` is a view of, so nothing is returned through autograd."""
+
+    @staticmethod
+    def forward(ctx, anchor: torch.Tensor, module: "TransformerLightningModule", metrics: torch.Tensor):
+        ctx.module = module
+        return metrics.clone()
+
+    @staticmethod
+    def backward(ctx, grad_metrics: torch.Tensor):
+        ctx.module._native_backward(grad_metrics)
+        return torch.zeros((), device=grad_metrics.device), None, None
+
+
+class TransformerLightningModule(nn.Module):
+    def __init__(self, config: Any, device: Optional[torch.device | str] = None):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise SvsrError("syncvsr_b200 needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
+        lib()  # fail loudly now if libsvsr.so is missing
+        self.config = config
+        self.device_ = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.is_train = False
+        self.word_labels = int(_cfg_get(config, "model.bert.num_labels", 500))
+        self.lambda_audio = float(_cfg_get(config, "optim.lambda_audio", 10.0))
+        self.label_smoothing = float(_cfg_get(config, "train.label_smoothing", 0.0))
+        self.use_wb = bool(_cfg_get(config, "data.use_word_boundary", False))
+        if self.use_wb:
+            raise SvsrError("data.use_word_boundary=True (hidden dim 513) is not built yet in the sm_100a path")
+        if _cfg_get(config, "model.bert.type", "x-transformers") != "x-transformers":
+            raise SvsrError("only model.bert.type == 'x-transformers' is implemented natively")
+
+        # codec constants: explicit keys win, else derived from the codec path exactly like lightning.py:58-67
+        path = str(_cfg_get(config, "model.wav2vec.path", "vq"))
+        if "vq" in path:
+            self.codec, a, g, v = "vq", 4, 2, 320
+        elif "wav2vec2" in path:
+            self.codec, a, g, v = "wav2vec2", 2, 2, 640
+        else:
+            raise SvsrError(f"cannot derive the audio codec from model.wav2vec.path={path!r}")
+        self.audio_alignment = int(_cfg_get(config, "model.audio_alignment", a))
+        self.vq_groups = int(_cfg_get(config, "model.vq_groups", g))
+        self.audio_vocab_size = int(_cfg_get(config, "model.audio_vocab_size", v))
+        self.dim = int(_cfg_get(config, "model.bert.dim", 512))
+        self.depth = int(_cfg_get(config, "model.bert.depth", 12))
+        self.heads = int(_cfg_get(config, "model.bert.heads", 8))
+        self.layer_dropout = float(_cfg_get(config, "model.bert.layer_dropout", 0.0))
+        for key in ("emb_dropout", "attn_dropout", "ff_dropout"):
+            if float(_cfg_get(config, f"model.bert.{key}", 0.0)) != 0.0:
+                # element-wise dropouts are not wired into the native kernels yet; refuse silently-different maths
+                raise SvsrError(f"model.bert.{key} > 0 is not supported by the native path yet (set it to 0)")
+        self.rotary_v = bool(_cfg_get(config, "model.bert.rotary_v", True))
+
+        self._h = C.c_void_p()
+        self._shape_key = None
+        self._flat_p = self._flat_g = self._flat_b = self._ws = None
+        self._metrics = torch.zeros(8, device=self.device_, dtype=torch.float32)
+        self._anchor = torch.zeros((), device=self.device_, requires_grad=True)
+        self._weights_dirty = True
+        self._param_views: Dict[str, nn.Parameter] = {}
+        self._offsets: Dict[str, tuple] = {}
+        # geometry-independent part: parameter arenas. Built with a nominal clip geometry (the parameter layout
+        # does not depend on B/H/W); the workspace is (re)built lazily for the geometry actually fed to forward().
+        self._build_engine(B=1, T=29, H=88, W=88, first=True)
+
+        # parameters the reference's state dict carries but never uses on this path (lightning.py:55 creates the full
+        # timm resnet18; only .layer1-4 run): kept for checkpoint compatibility, never receive gradients.
+        rn = self.resnet
+        rn.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        rn.bn1 = nn.BatchNorm2d(64)
+        rn.fc = nn.Linear(512, 1000)
+        for m in (rn.conv1, rn.bn1, rn.fc):
+            m.to(self.device_)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # engine / arena management
+    # ------------------------------------------------------------------------------------------------------------
+    def _engine_cfg(self, B, T, H, W) -> LrwConfig:
+        return LrwConfig(B, T, H, W, self.dim, self.depth, self.heads, self.audio_alignment, self.vq_groups,
+                         self.audio_vocab_size, self.word_labels, int(self.rotary_v), self.lambda_audio,
+                         self.label_smoothing, 1e-5, 0.1)
+
+    def _build_engine(self, B, T, H, W, first=False):
+        L = lib()
+        L.svsr_lrw_param_count.restype = C.c_int64
+        L.svsr_lrw_buffer_count.restype = C.c_int64
+        L.svsr_lrw_workspace_bytes.restype = C.c_int64
+        if self._h:
+            L.svsr_lrw_destroy(self._h)
+            self._h = C.c_void_p()
+        cfg = self._engine_cfg(B, T, H, W)
+        check(L.svsr_lrw_create(C.byref(cfg), C.byref(self._h)), "svsr_lrw_create")
+        if first:
+            self._create_arenas()
+        ws_bytes = L.svsr_lrw_workspace_bytes(self._h)
+        self._ws = None
+        torch.cuda.empty_cache()
+        self._ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=self.device_)
+        ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
+        check(L.svsr_lrw_bind(self._h, C.c_void_p(self._flat_p.data_ptr()), C.c_void_p(self._flat_g.data_ptr()),
+                              C.c_void_p(self._flat_b.data_ptr()), C.c_void_p(ws_ptr), C.c_int64(ws_bytes)),
+              "svsr_lrw_bind")
+        self._shape_key = (B, T, H, W)
+        self._weights_dirty = True
+
+    def _create_arenas(self):
+        L = lib()
+        h = self._h
+        n_p, n_b = L.svsr_lrw_param_count(h), L.svsr_lrw_buffer_count(h)
+        self._flat_p = torch.zeros(n_p, device=self.device_)
+        self._flat_g = torch.zeros(n_p, device=self.device_)
+        self._flat_b = torch.zeros(n_b, device=self.device_)
+        name, ndim, off, decay = C.c_char_p(), C.c_int(), C.c_int64(), C.c_int()
+        shape = (C.c_int64 * 5)()
+        gen = torch.Generator(device="cpu").manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        self._decay_mask_segments = []
+        for i in range(L.svsr_lrw_num_params(h)):
+            check(L.svsr_lrw_param_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off), C.byref(decay)), "info")
+            key, shp = name.value.decode(), tuple(shape[k] for k in range(ndim.value))
+            n = 1
+            for s in shp:
+                n *= s
+            view = self._flat_p[off.value: off.value + n].view(shp)
+            self._init_param(key, view, gen)
+            p = nn.Parameter(view)
+            self._register(key, p, is_buffer=False)
+            self._param_views[key] = p
+            self._offsets[key] = (off.value, n, shp, bool(decay.value))
+        for i in range(L.svsr_lrw_num_buffers(h)):
+            check(L.svsr_lrw_buffer_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off)), "info")
+            key, shp = name.value.decode(), tuple(shape[k] for k in range(ndim.value))
+            view = self._flat_b[off.value: off.value + shp[0]].view(shp)
+            if key.endswith("running_var"):
+                view.fill_(1.0)
+            self._register(key, view, is_buffer=True)
+        # reference BN modules also carry num_batches_tracked: 0-dim views of one counter vector (one add per step)
+        bn_keys = [k for k in dict(self.named_buffers()) if k.endswith("running_var")]
+        self._nbt = torch.zeros(len(bn_keys), dtype=torch.long, device=self.device_)
+        for i, key in enumerate(bn_keys):
+            self._register(key.replace("running_var", "num_batches_tracked"), self._nbt[i], is_buffer=True)
+        self._attach_grads()
+
+    @staticmethod
+    def _init_param(key: str, view: torch.Tensor, gen: torch.Generator) -> None:
+        """Reference-equivalent default initialisation (torchvision/timm kaiming-normal fan_out convs, BN 1/0,
+        PyTorch-default Linear, randn CLS, RMSNorm g = 1)."""
+        import math
+
+        shp = view.shape
+        is_bn = ".bn" in key or "stem3d.1" in key or "downsample.1" in key
+        if key.endswith(".g") or (is_bn and key.endswith("weight")):
+            view.fill_(1.0)
+        elif is_bn and key.endswith("bias"):
+            view.zero_()
+        elif key == "cls_token":
+            view.copy_(torch.randn(shp, generator=gen))
+        elif view.dim() >= 4:  # conv: kaiming normal, mode=fan_out, relu
+            fan_out = shp[0]
+            for s in shp[2:]:
+                fan_out *= s
+            view.copy_(torch.randn(shp, generator=gen) * math.sqrt(2.0 / fan_out))
+        elif view.dim() == 2:  # nn.Linear default: U(-1/sqrt(in), 1/sqrt(in))
+            bound = 1.0 / math.sqrt(shp[1])
+            view.copy_((torch.rand(shp, generator=gen) * 2 - 1) * bound)
+        elif view.dim() == 1:  # Linear bias
+            fan_in = 2048 if "ff.3" in key else 512
+            bound = 1.0 / math.sqrt(fan_in)
+            view.copy_((torch.rand(shp, generator=gen) * 2 - 1) * bound)
+
+    def _register(self, key: str, value, is_buffer: bool) -> None:
+        parts = key.split(".")
+        node: nn.Module = self
+        for part in parts[:-1]:
+            if part not in node._modules:
+                node.add_module(part, _Node())
+            node = node._modules[part]
+        if is_buffer:
+            node.register_buffer(parts[-1], value)
+        else:
+            node.register_parameter(parts[-1], value)
+
+    def _attach_grads(self) -> None:
+        for key, p in self._param_views.items():
+            off, n, shp, _ = self._offsets[key]
+            p.grad = self._flat_g[off: off + n].view(shp)
+
+    # flat views used by the data-parallel step and the fused optimizer
+    @property
+    def flat_params(self) -> torch.Tensor:
+        return self._flat_p
+
+    @property
+    def flat_grads(self) -> torch.Tensor:
+        return self._flat_g
+
+    def mark_weights_updated(self) -> None:
+        """Call after parameters changed (optimizer step, load_state_dict): bf16 operand copies are repacked lazily."""
+        self._weights_dirty = True
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._weights_dirty = True
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------------------------
+    def _ensure(self, videos: torch.Tensor) -> None:
+        if videos.dim() != 5 or videos.shape[1] != 1:
+            raise ValueError(f"videos must be [B,1,T,H,W], got {tuple(videos.shape)}")
+        B, _, T, H, W = videos.shape
+        if self._shape_key != (B, T, H, W):
+            self._build_engine(B, T, H, W)
+        if self._weights_dirty:
+            check(lib().svsr_lrw_pack_weights(self._h, self._stream()), "svsr_lrw_pack_weights")
+            self._weights_dirty = False
+
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _named_tensor(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        ptr, numel, dt = C.c_void_p(), C.c_int64(), C.c_int()
+        check(lib().svsr_lrw_tensor(self._h, name.encode(), C.byref(ptr), C.byref(numel), C.byref(dt)), "svsr_lrw_tensor")
+        tdt = {0: torch.float32, 1: torch.bfloat16, 2: torch.uint8, 3: torch.int32}[dt.value]
+        esz = {0: 4, 1: 2, 2: 1, 3: 4}[dt.value]
+        off = ptr.value - self._ws.data_ptr()
+        flat = self._ws[off: off + numel.value * esz].view(tdt)
+        return flat.view(shape) if shape is not None else flat
+
+    def forward_videos(self, videos: torch.Tensor) -> torch.Tensor:
+        """lightning.py:112-119 -> [B, T, 512] (fp32 copy of the pooled trunk features)."""
+        videos = videos.to(self.device_, torch.float32).contiguous()
+        self._ensure(videos)
+        B, _, T, _, _ = videos.shape
+        check(lib().svsr_lrw_forward_videos(self._h, C.c_void_p(videos.data_ptr()), C.c_int(int(self.training)),
+                                            self._stream()), "svsr_lrw_forward_videos")
+        return self._named_tensor("inputs_embeds", (B, T + 1, self.dim))[:, 1:, :].clone()
+
+    def forward(self, videos: torch.Tensor, audio_tokens: torch.Tensor, labels: torch.Tensor,
+                word_mask: torch.Tensor) -> Dict[str, torch.Tensor]:
+        videos = videos.to(self.device_, torch.float32).contiguous()
+        audio_tokens = audio_tokens.to(self.device_, torch.long).contiguous()
+        labels = labels.to(self.device_)
+        self._ensure(videos)
+        B, _, T, _, _ = videos.shape
+        if audio_tokens.dim() != 3 or audio_tokens.shape[2] != self.vq_groups:
+            raise ValueError(f"audio_tokens must be [B, >=T*{self.audio_alignment}, {self.vq_groups}]")
+        if audio_tokens.shape[1] < T * self.audio_alignment:
+            raise ValueError("audio_tokens has fewer than seq_len * audio_alignment rows")
+        hard = soft = None
+        if labels.dtype in (torch.long, torch.int32, torch.int64):
+            hard = labels.long().contiguous()
+        else:  # CutMix soft labels [B, num_labels] (augment.py; lightning.py:163-165,177-179)
+            soft = labels.float().contiguous()
+        skip = 0
+        if self.training and self.layer_dropout > 0.0:  # host RNG per sublayer, like x-transformers' layer_dropout
+            for i in range(2 * self.depth):
+                if random.random() < self.layer_dropout:
+                    skip |= 1 << i
+        check(lib().svsr_lrw_forward(
+            self._h, C.c_void_p(videos.data_ptr()), C.c_void_p(audio_tokens.data_ptr()),
+            C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
+            C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_int(int(self.training)), C.c_uint32(skip),
+            C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
+        if self.training:
+            self._nbt += 1
+        m = self._metrics
+        if torch.is_grad_enabled():
+            m = _StepFunction.apply(self._anchor, self, self._metrics)
+        return {"loss_total": m[0], "loss_category": m[1], "loss_audio": m[2], "accuracy_top1": m[3],
+                "accuracy_top5": m[4]}
+
+    def _native_backward(self, grad_metrics: torch.Tensor) -> None:
+        """d(loss_total) only: the other returned entries are metrics (the reference logs them, never differentiates
+        them separately). Accumulates into the flat gradient arena."""
+        g = grad_metrics.contiguous()  # element 0 = d(loss_total), read on the device (no host sync)
+        need_attach = any(p.grad is None for p in self._param_views.values())
+        if need_attach:  # zero_grad(set_to_none=True) dropped the views: start from a clean arena
+            self._flat_g.zero_()
+        check(lib().svsr_lrw_backward(self._h, C.c_void_p(g.data_ptr()), self._stream()), "svsr_lrw_backward")
+        if need_attach:
+            self._attach_grads()
+
+    # named intermediate tensors (parity tests)
+    def last_hidden_state(self) -> torch.Tensor:
+        B, T, _, _ = self._shape_key
+        return self._named_tensor("last_hidden_state", (B, T + 1, self.dim)).clone()
+
+    def logits_audio(self) -> torch.Tensor:
+        B, T, _, _ = self._shape_key
+        return self._named_tensor("logits_audio", (B, T, self.audio_alignment * self.vq_groups,
+                                                   self.audio_vocab_size)).clone()
+
+    def logits_category(self) -> torch.Tensor:
+        B = self._shape_key[0]
+        return self._named_tensor("logits_category", (B, -1))[:, : self.word_labels].clone()
+
+    # ---- the reference's Lightning hooks (lightning.py:194-223) ----
+    def log_dict(self, *a, **k):
+        pass
+
+    def training_step(self, batch, idx: int) -> torch.Tensor:
+        self.is_train = True
+        metrics = self(*batch)
+        self.log_dict({f"train/{k}": v for k, v in metrics.items()})
+        return metrics["loss_total"]
+
+    def validation_step(self, batch, idx: int):
+        self.is_train = False
+        metrics = self(*batch)
+        self.log_dict({f"val/{k}": v for k, v in metrics.items()}, sync_dist=True)
+
+    def test_step(self, batch, idx: int):
+        self.is_train = False
+        metrics = self(*batch)
+        self.log_dict({f"test/{k}": v for k, v in metrics.items()}, sync_dist=True)
+
+    def configure_optimizers(self):
+        """AdamW with decay on ndim >= 2 parameters only (lightning.py:216-223); the cosine schedule comes from
+        transformers.get_scheduler exactly as in the reference when that package is importable."""
+        do_decay = [p for p in self.parameters() if p.requires_grad and p.ndim >= 2]
+        no_decay = [p for p in self.parameters() if p.requires_grad and p.ndim < 2]
+        groups = [{"params": do_decay}, {"params": no_decay, "weight_decay": 0.0}]
+        okw = dict(_cfg_get(self.config, "optim.optimizer", {}) or {})
+        optimizer = torch.optim.AdamW(groups, **okw)
+        skw = dict(_cfg_get(self.config, "optim.scheduler", {}) or {})
+        try:
+            from transformers import get_scheduler
+
+            scheduler = get_scheduler(optimizer=optimizer, **skw)
+            return [optimizer], [{"scheduler": scheduler, "interval": "step"}]
+        except Exception:
+            return [optimizer], []
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().svsr_lrw_destroy(self._h)
+        except Exception:
+            pass
+
+
+# README pseudo-API name (README.md:26-56)
+Model = TransformerLightningModule
