@@ -43,6 +43,12 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
 int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
 
+/* Same-size correlation with an explicit tap list: y[n,h,w,:] = sum_t x[n, h+dh[t], w+dw[t], :] . w[:, t*Cin:(t+1)*Cin]^T
+ * (zero outside the image). The temporal half of the stem's Conv3d runs through this with taps (kt-2, 0) over the
+ * [T, OH*OW] patch image (lightning.py:50). */
+int svsr_conv_taps_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int ntaps,
+                         const int* tap_dh, const int* tap_dw, int out_fp32, void* stream);
+
 /* dx[N,H,W,Cin] = conv2d input-gradient of dy[N,OH,OW,Cout]; wd is the weight packed for dgrad as
  * [Cin, R*S*Cout] bf16 (column (r*S+s)*Cout+co holds W[co][ci][r][s]). If resid != NULL it is added (it may alias
  * dx: gradient accumulation of the residual branch). For stride 2 the four output-parity classes are issued as
@@ -60,6 +66,51 @@ int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
  * Replaces autograd's Linear backward-weight. N % 64 == 0. */
 int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,
                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Non-GEMM operators. bf16 NHWC activations ([rows, C] with rows = N*H*W), fp32 parameters/statistics.
+ * --------------------------------------------------------------------------------------------------------- */
+/* videos fp32 [B,1,T,H,W] -> 7x7/stride-2/pad-3 patches bf16 [B,T,OH*OW,64] (slot kh*8+kw); the 5-tap temporal
+ * part of Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (lightning.py:50) then runs as an implicit GEMM over these. */
+int svsr_stem_patch(const float* videos, void* patches, int B, int T, int H, int W, void* stream);
+/* nn.BatchNorm{2,3}d forward (+ optional residual with its own BN coefficients, + ReLU): lightning.py:51 and the
+ * bn1/bn2/downsample.1 of every BasicBlock. coef (fp32 [4][C]) receives mean, invstd, scale, shift for backward.
+ * train=1: batch statistics + running-stat update; train=0: running statistics. stats_scratch: fp64 [2*C]. */
+int svsr_batchnorm_fwd(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float eps, float momentum, int train, const void* res, const float* res_coef,
+                       int relu, void* out, float* coef, double* stats_scratch, void* stream);
+/* BatchNorm backward: g = dout * (relu_ref > 0 if relu_ref); dgamma += sum g*xhat; dbeta += sum g;
+ * dc = scale*(g - mean g - xhat*mean(g*xhat)); gmask_out (optional) = g. kcoef_scratch: fp32 [2*C]. */
+int svsr_batchnorm_bwd(const void* dout, const void* relu_ref, const void* c, int64_t rows, int C, const float* coef,
+                       float* dgamma, float* dbeta, void* dc, void* gmask_out, double* stats_scratch,
+                       float* kcoef_scratch, void* stream);
+/* BatchNorm3d-apply + GELU(erf) + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (lightning.py:51-53) and its backward */
+int svsr_stem_bn_gelu_pool_fwd(const void* y0, const float* coef, void* out, uint8_t* argmax, int N, int IH, int IW,
+                               void* stream);
+int svsr_stem_pool_gelu_bwd(const void* dout, const uint8_t* argmax, const void* y0, const float* coef, void* dz, int N,
+                            int IH, int IW, void* stream);
+/* hidden.mean((2,3)) + CLS concat (lightning.py:118,148-150): x_stream fp32 [B, T+1, C] */
+int svsr_meanpool_cls_fwd(const void* a, const float* cls, float* x_stream, int B, int T, int HW, int C, void* stream);
+int svsr_meanpool_cls_bwd(const float* dx, void* dout, float* dcls, int B, int T, int HW, int C, void* stream);
+/* x-transformers RMSNorm / rotary attention core / GEGLU */
+int svsr_rmsnorm_fwd(const float* x, const float* g, void* y, float* inv, int M, int D, float eps, void* stream);
+int svsr_rmsnorm_bwd(const void* dy, const float* x, const float* g, const float* inv, float* dx, void* dx_bf16,
+                     float* dg, int M, int D, float eps, void* stream);
+int svsr_rotary_table(float* tab, int n, void* stream);
+int svsr_attention_fwd(const void* qkv, const float* rot, void* o, int B, int n, int heads, int rotary_v, void* stream);
+int svsr_attention_bwd(const void* qkv, const float* rot, const void* d_o, void* dqkv, int B, int n, int heads,
+                       int rotary_v, void* stream);
+int svsr_geglu_fwd(const void* h, void* u, int M, int F, void* stream);
+int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, void* stream);
+/* F.cross_entropy over quantised audio tokens (lightning.py:168-171): logits fp32 [B*T, A*G*V]; row (b,t), group
+ * c=a*G+g is scored against tokens[b*tok_stride_b + (t*A+a)*G + g]. acc[0] += sum nll (fp64);
+ * dlogits (bf16, optional) = (softmax - onehot) * dscale; *bad_token = 1 if a token is outside [0,V). */
+int svsr_audio_ce(const float* logits, int ld, const int64_t* tokens, int64_t tok_stride_b, int B, int T, int A, int G,
+                  int V, void* dlogits, double* acc, int* bad_token, float dscale, void* stream);
+/* F.cross_entropy(logits_category, labels, label_smoothing) with int64 or soft fp32 labels (lightning.py:161-165);
+ * acc[1] += sum loss, acc[2] += #top1, acc[3] += #top5 (lightning.py:177-183). */
+int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const float* soft_labels, int B, int C,
+                     float eps, void* dlogits, int ldd, double* acc, float dscale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * LRW word-level model step executor: the whole of TransformerLightningModule.forward (lightning.py:133-191) and
@@ -82,6 +133,7 @@ typedef struct svsr_lrw_config {
 int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle);
 int svsr_lrw_destroy(void* handle);
 int64_t svsr_lrw_param_count(void* handle);     /* elements of the parameter (= gradient) arena */
+int64_t svsr_lrw_decay_count(void* handle);     /* leading elements of the arena that AdamW decays (ndim >= 2) */
 int64_t svsr_lrw_buffer_count(void* handle);    /* elements of the BatchNorm running-stat arena */
 int64_t svsr_lrw_workspace_bytes(void* handle); /* activation + packed-operand workspace */
 int svsr_lrw_num_params(void* handle);
@@ -106,6 +158,20 @@ int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* 
 int svsr_lrw_backward(void* handle, const float* grad_scale, void* stream);
 /* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */
 int svsr_lrw_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
+
+/* Fused global-norm clip + AdamW over the flat arenas (lightning.py:216-221; Trainer gradient_clip_val). The arena
+ * is [decayed | non-decayed]: the first n_decay elements get weight decay. grad_div divides gradients first (world
+ * size after a SUM all-reduce). scratch: >= 32 bytes device memory; afterwards {fp64 sumsq, fp32 clip coef, fp32 norm}. */
+int svsr_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_decay,
+                    int64_t n_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    float max_norm, float grad_div, void* scratch, void* stream);
+
+/* Kernels launched by this library so far in this process (bench.py reports the per-region difference). */
+long long svsr_launch_count(void);
+/* Per-launch CUDA-event timing of the tensor-core kernels: enable (resets), run, synchronise, read.
+ * kind 0 = igemm_kernel (conv fprop/dgrad, linear fwd/dgrad), 1 = wgrad_kernel. flops are algorithmic (2*MAC). */
+int svsr_prof_enable(int on);
+int svsr_prof_read(int kind, double* total_ms, double* total_flops, int* launches);
 
 /* Developer hardware probe (see csrc/debug_probe.cu); not part of the product path. */
 int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream);

@@ -17,6 +17,14 @@ namespace svsr {
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
 
+// launch accounting (bench.py's "gpu_launches") and optional per-launch CUDA-event timing of the GEMM kernels
+void note_launch();
+long long launch_count();
+enum ProfKind : int { PROF_IGEMM = 0, PROF_WGRAD = 1, PROF_KINDS = 2 };
+bool prof_enabled();
+void prof_begin(int kind, double flops, cudaStream_t s);  // records the start event (no-op when disabled)
+void prof_end(cudaStream_t s);                            // records the stop event
+
 #define SVSR_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

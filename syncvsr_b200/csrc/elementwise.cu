@@ -476,7 +476,9 @@ __global__ void split_cast_last_kernel(const float* __restrict__ last, __nv_bflo
 
 }  // namespace
 
-#define LAUNCH_CHECK() SVSR_CHECK_CUDA(cudaGetLastError())
+#define LAUNCH_CHECK() \
+  note_launch();       \
+  SVSR_CHECK_CUDA(cudaGetLastError())
 
 int stem_patch(const float* videos, __nv_bfloat16* patches, int B, int T, int H, int W, cudaStream_t s) {
   const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;

@@ -286,7 +286,9 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv
 
 }  // namespace
 
-#define LAUNCH_CHECK() SVSR_CHECK_CUDA(cudaGetLastError())
+#define LAUNCH_CHECK() \
+  note_launch();       \
+  SVSR_CHECK_CUDA(cudaGetLastError())
 
 int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s) {
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);

@@ -68,6 +68,12 @@ struct EncLayerRef {
   size_t xn_a, inv_a, qkvbuf, obuf, xn_f, inv_f, hbuf, ubuf;
 };
 
+// The parameter arena is [decayed (ndim >= 2) | non-decayed]; `nodecay_base` is where the second region starts
+// (found by a first sizing pass of engine_build). Buffers use one region.
+struct ArenaCount {
+  long long decay = 0, nodecay = 0, nodecay_base = 0;
+};
+
 struct LrwEngine {
   svsr_lrw_config cfg;
   int N;   // frames = B*T
@@ -76,7 +82,8 @@ struct LrwEngine {
   int H1;  // pooled size (layer1 input)
   std::vector<ParamInfo> params;
   std::vector<ParamInfo> buffers;
-  long long param_count = 0, buffer_count = 0;
+  long long param_count = 0, buffer_count = 0, decay_count = 0;
+  ArenaCount pc, bc;
   size_t ws_bytes = 0;
 
   // bound storage
@@ -120,7 +127,7 @@ struct Bump {
   }
 };
 
-long long add_param(std::vector<ParamInfo>& v, long long& count, const std::string& name,
+long long add_param(std::vector<ParamInfo>& v, ArenaCount& count, const std::string& name,
                     std::initializer_list<long long> shape) {
   ParamInfo p;
   p.name = name;
@@ -129,19 +136,25 @@ long long add_param(std::vector<ParamInfo>& v, long long& count, const std::stri
   int i = 0;
   for (long long s : shape) p.shape[i++] = s, p.numel *= s;
   for (; i < 5; ++i) p.shape[i] = 1;
-  p.offset = count;
   p.decay = p.ndim >= 2;
-  count += (p.numel + 3) & ~3LL;  // keep every tensor 16-byte aligned inside the arena
+  const long long padded = (p.numel + 3) & ~3LL;  // keep every tensor 16-byte aligned inside the arena
+  if (p.decay) {
+    p.offset = count.decay;
+    count.decay += padded;
+  } else {
+    p.offset = count.nodecay_base + count.nodecay;
+    count.nodecay += padded;
+  }
   v.push_back(p);
   return p.offset;
 }
 
 void add_bn(LrwEngine& e, BnRef& bn, const std::string& prefix, int C, Bump& b) {
   bn.C = C;
-  bn.gamma = add_param(e.params, e.param_count, prefix + ".weight", {C});
-  bn.beta = add_param(e.params, e.param_count, prefix + ".bias", {C});
-  bn.rmean = add_param(e.buffers, e.buffer_count, prefix + ".running_mean", {C});
-  bn.rvar = add_param(e.buffers, e.buffer_count, prefix + ".running_var", {C});
+  bn.gamma = add_param(e.params, e.pc, prefix + ".weight", {C});
+  bn.beta = add_param(e.params, e.pc, prefix + ".bias", {C});
+  bn.rmean = add_param(e.buffers, e.bc, prefix + ".running_mean", {C});
+  bn.rvar = add_param(e.buffers, e.bc, prefix + ".running_var", {C});
   bn.coef = b.take(4 * C * sizeof(float));
   bn.kcoef = b.take(2 * C * sizeof(float));
 }
@@ -149,15 +162,15 @@ void add_bn(LrwEngine& e, BnRef& bn, const std::string& prefix, int C, Bump& b) 
 void add_conv(LrwEngine& e, ConvRef& c, const std::string& name, int cin, int cout, int R, int stride, int pad,
               Bump& b) {
   c.cin = cin, c.cout = cout, c.R = R, c.stride = stride, c.pad = pad;
-  c.w = add_param(e.params, e.param_count, name, {cout, cin, R, R});
+  c.w = add_param(e.params, e.pc, name, {cout, cin, R, R});
   c.wf = b.take((size_t)cout * R * R * cin * 2);
   c.wd = b.take((size_t)cin * R * R * cout * 2);
 }
 
 void add_linear(LrwEngine& e, LinRef& l, const std::string& wname, const std::string& bname, int N, int K, Bump& b) {
   l.N = N, l.K = K;
-  l.w = add_param(e.params, e.param_count, wname, {N, K});
-  l.b = bname.empty() ? -1 : add_param(e.params, e.param_count, bname, {N});
+  l.w = add_param(e.params, e.pc, wname, {N, K});
+  l.b = bname.empty() ? -1 : add_param(e.params, e.pc, bname, {N});
   l.ldt = (N + 63) / 64 * 64;
   l.wb = b.take((size_t)N * K * 2);
   l.wt = b.take((size_t)K * l.ldt * 2);
@@ -167,7 +180,10 @@ int conv_out(int h, int k, int s, int p) { return (h + 2 * p - k) / s + 1; }
 
 }  // namespace
 
-static int engine_build(LrwEngine& e) {
+static int engine_build(LrwEngine& e, long long nodecay_base) {
+  e.params.clear(), e.buffers.clear();
+  e.pc = ArenaCount(), e.bc = ArenaCount();
+  e.pc.nodecay_base = nodecay_base;
   const svsr_lrw_config& c = e.cfg;
   SVSR_REQUIRE(c.B > 0 && c.T > 0 && c.H > 0 && c.W == c.H, "lrw: bad clip geometry B=%d T=%d H=%d W=%d", c.B, c.T,
                c.H, c.W);
@@ -186,7 +202,7 @@ static int engine_build(LrwEngine& e) {
 
   // ---- parameters (reference state-dict names) + packed operand storage ----
   e.stem_conv.cin = 1, e.stem_conv.cout = 64;
-  e.stem_conv.w = add_param(e.params, e.param_count, "stem3d.0.weight", {64, 1, 5, 7, 7});
+  e.stem_conv.w = add_param(e.params, e.pc, "stem3d.0.weight", {64, 1, 5, 7, 7});
   e.stem_conv.wf = b.take(64 * 320 * 2);
   add_bn(e, e.stem_bn, "stem3d.1", 64, b);
   int cin = 64, h = e.H1;
@@ -216,23 +232,23 @@ static int engine_build(LrwEngine& e) {
     }
     cin = widths[li];
   }
-  e.cls_off = add_param(e.params, e.param_count, "cls_token", {1, 1, c.dim});
+  e.cls_off = add_param(e.params, e.pc, "cls_token", {1, 1, c.dim});
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   e.enc.resize(c.depth);
   for (int i = 0; i < c.depth; ++i) {
     EncLayerRef& L = e.enc[i];
     const std::string a = "encoder.layers." + std::to_string(2 * i), f = "encoder.layers." + std::to_string(2 * i + 1);
-    L.g_a = add_param(e.params, e.param_count, a + ".0.g", {D});
+    L.g_a = add_param(e.params, e.pc, a + ".0.g", {D});
     // to_q / to_k / to_v are adjacent in the arena so that they form one [3*inner, D] operand and gradient
     L.qkv.N = 3 * inner, L.qkv.K = D, L.qkv.b = -1;
-    L.qkv.w = add_param(e.params, e.param_count, a + ".1.to_q.weight", {inner, D});
-    add_param(e.params, e.param_count, a + ".1.to_k.weight", {inner, D});
-    add_param(e.params, e.param_count, a + ".1.to_v.weight", {inner, D});
+    L.qkv.w = add_param(e.params, e.pc, a + ".1.to_q.weight", {inner, D});
+    add_param(e.params, e.pc, a + ".1.to_k.weight", {inner, D});
+    add_param(e.params, e.pc, a + ".1.to_v.weight", {inner, D});
     L.qkv.ldt = 3 * inner;
     L.qkv.wb = b.take((size_t)3 * inner * D * 2);
     L.qkv.wt = b.take((size_t)D * 3 * inner * 2);
     add_linear(e, L.out, a + ".1.to_out.weight", "", D, inner, b);
-    L.g_f = add_param(e.params, e.param_count, f + ".0.g", {D});
+    L.g_f = add_param(e.params, e.pc, f + ".0.g", {D});
     add_linear(e, L.ff1, f + ".1.ff.0.proj.weight", f + ".1.ff.0.proj.bias", 2 * F, D, b);
     add_linear(e, L.ff2, f + ".1.ff.3.weight", f + ".1.ff.3.bias", D, F, b);
     L.xn_a = b.take((size_t)e.M * D * 2), L.inv_a = b.take((size_t)e.M * 4);
@@ -295,6 +311,9 @@ static int engine_build(LrwEngine& e) {
   e.stem_dz = b.take(n0 * 2);
   e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
   e.ws_bytes = b.off;
+  e.decay_count = e.pc.decay;
+  e.param_count = e.pc.nodecay_base + e.pc.nodecay;
+  e.buffer_count = e.bc.nodecay;
   return SVSR_OK;
 }
 
@@ -432,6 +451,7 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     p.o_N = c.B, p.OH = c.T, p.OW = e.H0 * e.H0;
     p.b = e.ws<bf16>(e.stem_conv.wf), p.b_rows = 64, p.b_cols = 320;
     p.out = e.ws<bf16>(e.y0), p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
+    p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
     RC(igemm_launch(p, s));
   }
   RC(bn_fwd(e, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
@@ -615,6 +635,7 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
     p.b = dz, p.b_C = 64, p.n_cols = 64;
     p.k_N = c.B, p.k_H = c.T, p.k_W = e.H0 * e.H0;
     p.out = tmp, p.ldo = 64;
+    p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
     RC(wgrad_launch(p, s));
     RC(unpack_stem_wgrad(tmp, e.G + e.stem_conv.w, s));
   }
@@ -634,7 +655,8 @@ int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle) {
   SVSR_REQUIRE(cfg && handle, "lrw_create: null argument");
   LrwEngine* e = new LrwEngine();
   e->cfg = *cfg;
-  int rc = engine_build(*e);
+  int rc = engine_build(*e, 0);  // sizing pass: how large is the decayed region?
+  if (!rc) rc = engine_build(*e, e->decay_count);
   if (rc) {
     delete e;
     return rc;
@@ -647,6 +669,7 @@ int svsr_lrw_destroy(void* h) {
   return SVSR_OK;
 }
 int64_t svsr_lrw_param_count(void* h) { return static_cast<LrwEngine*>(h)->param_count; }
+int64_t svsr_lrw_decay_count(void* h) { return static_cast<LrwEngine*>(h)->decay_count; }
 int64_t svsr_lrw_buffer_count(void* h) { return static_cast<LrwEngine*>(h)->buffer_count; }
 int64_t svsr_lrw_workspace_bytes(void* h) { return (int64_t)static_cast<LrwEngine*>(h)->ws_bytes; }
 int svsr_lrw_num_params(void* h) { return (int)static_cast<LrwEngine*>(h)->params.size(); }

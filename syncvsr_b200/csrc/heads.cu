@@ -131,6 +131,7 @@ int scale_bf16_by_device_scalar(__nv_bfloat16* x, long long n, const float* scal
   long long blocks = (n + 1023) / 1024;
   if (blocks > 148 * 8) blocks = 148 * 8;
   scale_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, scale);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
@@ -142,6 +143,7 @@ int audio_ce(const float* logits, int ld, const long long* tokens, long long tok
   if (blocks > 148 * 8) blocks = 148 * 8;
   audio_ce_kernel<<<(unsigned)blocks, 256, 0, s>>>(logits, ld, tokens, tok_stride_b, T, A, G, V, nrows, dlogits, acc,
                                                    bad_token, dscale);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
@@ -150,11 +152,13 @@ int category_ce(const float* logits, int ld, const long long* labels, const floa
   SVSR_REQUIRE((labels != nullptr) != (soft_labels != nullptr), "category_ce: exactly one of labels/soft_labels");
   const int blocks = (B + 7) / 8;
   category_ce_kernel<<<blocks, 256, 0, s>>>(logits, ld, labels, soft_labels, B, C, eps, dlogits, ldd, acc, dscale);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
 int finalize_metrics(const double* acc, float* out, float lambda_audio, int B, long long audio_rows, cudaStream_t s) {
   finalize_metrics_kernel<<<1, 1, 0, s>>>(acc, out, lambda_audio, B, audio_rows);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }

@@ -250,6 +250,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmK
     attr_done = true;
   }
   igemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, kp);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
@@ -306,11 +307,17 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   dim3 grid((unsigned)(tiles_n * kp.tiles_h * kp.tiles_w), (unsigned)((p.b_rows + BN - 1) / BN));
+  const double flops = p.algo_flops > 0 ? p.algo_flops
+                                        : 2.0 * p.o_N * p.OH * p.OW * (double)p.b_rows * p.ntaps * p.cin;
+  prof_begin(PROF_IGEMM, flops, stream);
+  int rc;
   switch (BN) {
-    case 64: return launch_t<64, 4>(tmA, tmB, kp, grid, stream);
-    case 128: return launch_t<128, 3>(tmA, tmB, kp, grid, stream);
-    default: return launch_t<256, 4>(tmA, tmB, kp, grid, stream);
+    case 64: rc = launch_t<64, 4>(tmA, tmB, kp, grid, stream); break;
+    case 128: rc = launch_t<128, 3>(tmA, tmB, kp, grid, stream); break;
+    default: rc = launch_t<256, 4>(tmA, tmB, kp, grid, stream); break;
   }
+  prof_end(stream);
+  return rc;
 }
 
 }  // namespace svsr

@@ -42,6 +42,7 @@ struct IgemmProblem {
   const void* resid = nullptr;  // same geometry as out (pitch ldc, offset c_off), or null
   int resid_fp32 = 0;
   float alpha = 1.0f;  // out = alpha*acc (+bias) (+resid)
+  double algo_flops = 0;  // algorithmic FLOPs of this launch for the profiler (0 = 2*pixels*N*taps*cin)
 };
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);

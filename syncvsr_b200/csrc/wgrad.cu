@@ -179,6 +179,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradK
     attr_done = true;
   }
   wgrad_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, kp);
+  note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
@@ -234,11 +235,18 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
+  const double flops = p.algo_flops > 0
+                           ? p.algo_flops
+                           : 2.0 * p.k_N * p.k_H * p.k_W * (double)p.ntaps * p.a_cin * (double)p.n_cols;
+  prof_begin(PROF_WGRAD, flops, stream);
+  int rc;
   switch (BN) {
-    case 64: return launch_t<64, 3>(tmA, tmB, kp, grid, stream);
-    case 128: return launch_t<128, 3>(tmA, tmB, kp, grid, stream);
-    default: return launch_t<256, 2>(tmA, tmB, kp, grid, stream);
+    case 64: rc = launch_t<64, 3>(tmA, tmB, kp, grid, stream); break;
+    case 128: rc = launch_t<128, 3>(tmA, tmB, kp, grid, stream); break;
+    default: rc = launch_t<256, 2>(tmA, tmB, kp, grid, stream); break;
   }
+  prof_end(stream);
+  return rc;
 }
 
 }  // namespace svsr

@@ -1,0 +1,277 @@
+"""Kernel-level parity (through the C ABI) against plain fp32 PyTorch on IDENTICAL inputs.
+
+Tolerances: the kernels compute in fp32 from bf16-stored operands, so outputs stored in bf16 carry one bf16 rounding
+(2^-9 relative, rel-L2 ~2e-3); fp32 outputs (weight gradients, losses, statistics) must agree to ~1e-4.
+Integer work (audio-token indexing) is checked bit-exactly."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 4e-3
+F32_TOL = 2e-4
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from syncvsr_b200 import ops as o
+
+    return o
+
+
+def randn(*shape, seed=0, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+# ---------------------------------------------------------------- GEMM / conv (tcgen05) -------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1920, 512, 512), (1920, 4096, 512), (100, 512, 2048), (64, 504, 512)])
+def test_gemm(ops, M, N, K):
+    a, b = randn(M, K, seed=1), randn(N, K, seed=2, scale=0.05)
+    bias = randn(N, seed=3, dtype=torch.float32)
+    out = ops.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    ref = a.float() @ b.float().T + bias
+    assert rel(out, ref) < F32_TOL
+
+
+def test_gemm_residual_bf16(ops):
+    a, b, r = randn(1920, 2048, seed=1), randn(512, 2048, seed=2, scale=0.05), randn(1920, 512, seed=3)
+    out = ops.gemm(a, b, resid=r)
+    assert rel(out, a.float() @ b.float().T + r.float()) < BF16_TOL
+
+
+CONVS = [(6, 22, 22, 64, 64, 3, 1, 1), (6, 11, 11, 128, 128, 3, 1, 1), (7, 6, 6, 256, 256, 3, 1, 1),
+         (30, 3, 3, 512, 512, 3, 1, 1), (6, 22, 22, 64, 128, 3, 2, 1), (6, 11, 11, 128, 256, 3, 2, 1),
+         (6, 6, 6, 256, 512, 3, 2, 1), (6, 22, 22, 64, 128, 1, 2, 0), (5, 11, 11, 128, 256, 1, 2, 0),
+         (3, 24, 24, 64, 64, 3, 1, 1), (3, 12, 12, 128, 128, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,pad", CONVS)
+def test_conv_fprop_dgrad_wgrad(ops, N, H, W, Cin, Cout, R, stride, pad):
+    x = randn(N, H, W, Cin, seed=4)
+    w = randn(Cout, Cin, R, R, seed=5, scale=0.05)
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wt = w.float().requires_grad_(True)
+    ref = F.conv2d(xt, wt, stride=stride, padding=pad)
+    y = ops.conv2d_fprop(x, ops.pack_conv_weight(w), R, R, stride, pad)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < BF16_TOL
+    dy = randn(*y.shape, seed=6, scale=0.1)
+    gx, gw = torch.autograd.grad(ref, (xt, wt), dy.float().permute(0, 3, 1, 2))
+    dx = ops.conv2d_dgrad(dy, ops.pack_conv_weight_dgrad(w), H, W, R, R, stride, pad)
+    assert rel(dx, gx.permute(0, 2, 3, 1)) < BF16_TOL
+    dw = ops.unpack_conv_wgrad(ops.conv2d_wgrad(x, dy, R, R, stride, pad), Cin, R, R)
+    assert rel(dw, gw) < F32_TOL
+
+
+def test_conv_dgrad_accumulates_residual_in_place(ops):
+    dy, w = randn(4, 11, 11, 128, seed=7), randn(128, 64, 3, 3, seed=8, scale=0.05)
+    base = randn(4, 22, 22, 64, seed=9)
+    ref = ops.conv2d_dgrad(dy, ops.pack_conv_weight_dgrad(w), 22, 22, 3, 3, 2, 1).float() + base.float()
+    out = ops.conv2d_dgrad(dy, ops.pack_conv_weight_dgrad(w), 22, 22, 3, 3, 2, 1, resid=base)
+    assert rel(out, ref) < BF16_TOL
+
+
+def test_gemm_wgrad(ops):
+    dy, x = randn(1920, 512, seed=10, scale=0.1), randn(1920, 2048, seed=11)
+    assert rel(ops.gemm_wgrad(dy, x), dy.float().T @ x.float()) < F32_TOL
+
+
+def test_stem_conv_matches_conv3d(ops):
+    """patch gather + 5-tap temporal implicit GEMM == Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (lightning.py:50)."""
+    import ctypes as C
+    from syncvsr_b200._lib import check, lib, ptr, stream_ptr
+
+    B, T, S = 2, 29, 88
+    v = randn(B, 1, T, S, S, seed=12, dtype=torch.float32)
+    w = randn(64, 1, 5, 7, 7, seed=13, scale=0.05, dtype=torch.float32)
+    ref = F.conv3d(v.bfloat16().float(), w.bfloat16().float(), None, (1, 2, 2), (2, 3, 3))
+    P = ops.stem_patch(v)
+    wp = torch.zeros(64, 5, 8, 8, device="cuda")
+    wp[:, :, :7, :7] = w[:, 0]
+    wp = wp.reshape(64, 320).bfloat16().contiguous()
+    # temporal 5-tap conv == conv2d with a 5x1 filter over an [T, OH*OW] "image" of 64 patch channels
+    y = ops.conv2d_fprop_generic(P.view(B, T, 44 * 44, 64), wp, taps=[(kt - 2, 0) for kt in range(5)])
+    assert rel(y.view(B, T, 44, 44, 64), ref.permute(0, 2, 3, 4, 1)) < BF16_TOL
+
+
+# ---------------------------------------------------------------- BatchNorm --------------------------------------
+@pytest.mark.parametrize("C,rows", [(64, 5000), (128, 1111), (256, 700), (512, 90)])
+def test_batchnorm_fwd_bwd(ops, C, rows):
+    x = randn(rows, C, seed=20) * 2 + 0.5
+    res = randn(rows, C, seed=21)
+    gamma = randn(C, seed=22, dtype=torch.float32).abs() + 0.5
+    beta = randn(C, seed=23, dtype=torch.float32)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    out, coef = ops.batchnorm_fwd(x, gamma, beta, rm, rv, train=True, res=res, relu=True)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    pre = F.batch_norm(xf, rm2, rv2, gf, bf, True, 0.1, 1e-5)
+    ref = F.relu(pre + res.float())
+    assert rel(out, ref) < BF16_TOL
+    assert rel(rm, rm2) < F32_TOL and rel(rv, rv2) < F32_TOL
+    # backward with the kernel's own output as relu reference (identical mask on both sides)
+    dout = randn(rows, C, seed=24, scale=0.1)
+    mask = (out.float() > 0).float()
+    gx, gg, gb = torch.autograd.grad(pre, (xf, gf, bf), dout.float() * mask)
+    dc, dgamma, dbeta, gm = ops.batchnorm_bwd(dout, out, x, coef, want_gmask=True)
+    assert rel(dc, gx) < BF16_TOL
+    assert rel(dgamma, gg) < 1e-3 and rel(dbeta, gb) < 1e-3
+    assert torch.equal(gm.float(), dout.float() * mask)
+
+
+def test_batchnorm_eval_uses_running_stats(ops):
+    C = 64
+    x = randn(300, C, seed=25)
+    gamma, beta = torch.ones(C, device="cuda") * 1.5, torch.ones(C, device="cuda") * 0.1
+    rm, rv = randn(C, seed=26, dtype=torch.float32) * 0.1, torch.rand(C, device="cuda") + 0.5
+    out, _ = ops.batchnorm_fwd(x, gamma, beta, rm.clone(), rv.clone(), train=False)
+    ref = F.batch_norm(x.float(), rm, rv, gamma, beta, False, 0.1, 1e-5)
+    assert rel(out, ref) < BF16_TOL
+
+
+# ---------------------------------------------------------------- stem BN+GELU+pool ------------------------------
+def test_stem_bn_gelu_pool_fwd_bwd(ops):
+    N, IH = 5, 44
+    y0 = randn(N, IH, IH, 64, seed=30)
+    coef = torch.zeros(4, 64, device="cuda")
+    coef[1] = 1.0
+    coef[2] = randn(64, seed=31, dtype=torch.float32).abs() + 0.5  # scale
+    coef[3] = randn(64, seed=32, dtype=torch.float32) * 0.3  # shift
+    out, am = ops.stem_bn_gelu_pool_fwd(y0, coef)
+    z = (y0.float() * coef[2] + coef[3]).permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(F.gelu(z), 3, 2, 1)
+    assert rel(out, ref.permute(0, 2, 3, 1)) < BF16_TOL
+    dout = randn(*out.shape, seed=33)
+    (gz,) = torch.autograd.grad(ref, z, dout.float().permute(0, 3, 1, 2))
+    dz = ops.stem_pool_gelu_bwd(dout, am, y0, coef)
+    assert rel(dz, gz.permute(0, 2, 3, 1)) < BF16_TOL
+
+
+def test_meanpool_cls(ops):
+    B, T, C = 3, 29, 512
+    a = randn(B * T, 3, 3, C, seed=40)
+    cls = randn(C, seed=41, dtype=torch.float32)
+    xs = ops.meanpool_cls_fwd(a, cls, B, T)
+    ref = torch.cat((cls.expand(B, 1, C), a.float().mean((1, 2)).view(B, T, C)), 1)
+    assert rel(xs, ref) < 1e-5
+    dx = randn(B, T + 1, C, seed=42, dtype=torch.float32)
+    dout, dcls = ops.meanpool_cls_bwd(dx, 9)
+    assert rel(dout, (dx[:, 1:] / 9).reshape(B * T, 1, C).expand(B * T, 9, C)) < BF16_TOL
+    assert rel(dcls, dx[:, 0].sum(0)) < 1e-5
+
+
+# ---------------------------------------------------------------- encoder pieces ---------------------------------
+def test_rmsnorm_fwd_bwd(ops):
+    from oracle.lrw_oracle import rmsnorm
+
+    M, D = 300, 512
+    x = randn(M, D, seed=50, dtype=torch.float32) * 3
+    g = randn(D, seed=51, dtype=torch.float32).abs() + 0.5
+    y, inv = ops.rmsnorm_fwd(x, g)
+    xr, gr = x.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    ref = rmsnorm(xr, gr)
+    assert rel(y, ref) < BF16_TOL
+    dy = randn(M, D, seed=52)
+    gx, gg = torch.autograd.grad(ref, (xr, gr), dy.float())
+    dx = randn(M, D, seed=53, dtype=torch.float32)
+    dx0 = dx.clone()
+    dxb, dg = ops.rmsnorm_bwd(dy, x, g, inv, dx)
+    assert rel(dx - dx0, gx) < 1e-4 and rel(dg, gg) < 1e-4
+    assert rel(dxb, dx) < BF16_TOL
+
+
+@pytest.mark.parametrize("rotary_v", [True, False])
+def test_attention_fwd_bwd(ops, rotary_v):
+    from oracle.lrw_oracle import _rotary, rotary_table
+
+    B, n, H = 3, 30, 8
+    qkv = randn(B * n, 3 * H * 64, seed=60)
+    rot = ops.rotary_table(n)
+    o = ops.attention_fwd(qkv, rot, B, n, H, rotary_v)
+    t = qkv.float().requires_grad_(True)
+    q, k, v = (t[:, i * 512:(i + 1) * 512].view(B, n, H, 64).transpose(1, 2) for i in range(3))
+    fr = rotary_table(n).cuda()
+    q, k = _rotary(q, fr), _rotary(k, fr)
+    if rotary_v:
+        v = _rotary(v, fr)
+    attn = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1)
+    ref = (attn @ v).transpose(1, 2).reshape(B * n, H * 64)
+    assert rel(o, ref) < BF16_TOL
+    d_o = randn(B * n, H * 64, seed=61)
+    (gq,) = torch.autograd.grad(ref, t, d_o.float())
+    dqkv = ops.attention_bwd(qkv, rot, d_o, B, n, H, rotary_v)
+    assert rel(dqkv, gq) < BF16_TOL
+
+
+def test_geglu(ops):
+    h = randn(500, 4096, seed=70)
+    hr = h.float().requires_grad_(True)
+    a, g = hr.chunk(2, -1)
+    ref = a * F.gelu(g)
+    assert rel(ops.geglu_fwd(h), ref) < BF16_TOL
+    du = randn(500, 2048, seed=71)
+    (gh,) = torch.autograd.grad(ref, hr, du.float())
+    assert rel(ops.geglu_bwd(h, du), gh) < BF16_TOL
+
+
+# ---------------------------------------------------------------- loss heads -------------------------------------
+@pytest.mark.parametrize("A,G,V,extra", [(4, 2, 320, 0), (2, 2, 320, 5), (2, 2, 640, 1), (4, 8, 1024, 3)])
+def test_audio_ce_matches_reference_indexing(ops, A, G, V, extra):
+    """lightning.py:168-171: F.cross_entropy(logits.reshape(-1,V), audio_tokens[:, :T*A].flatten())."""
+    B, T = 3, 29
+    logits = randn(B * T, A * G * V, seed=80, dtype=torch.float32) * 2
+    g = torch.Generator(device="cuda").manual_seed(81)
+    tokens = torch.randint(0, V, (B, T * A + extra, G), device="cuda", generator=g)
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr.reshape(B, T, A * G, V).reshape(-1, V), tokens[:, : T * A].flatten())
+    loss, dl, bad = ops.audio_ce(logits, tokens, T, A, G, V, dscale=1.0 / (B * T * A * G))
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    (gl,) = torch.autograd.grad(ref, lr)
+    assert rel(dl, gl) < BF16_TOL
+    assert bad.item() == 0
+    # the target of every row is reproduced bit-exactly: gradient is negative exactly at the reference's target class
+    picked = (dl.float().view(-1, V) < 0).float().argmax(-1)
+    assert torch.equal(picked, tokens[:, : T * A].flatten())
+
+
+def test_audio_ce_flags_out_of_range_tokens(ops):
+    logits = randn(29, 2560, seed=82, dtype=torch.float32)
+    tokens = torch.zeros(1, 116, 2, dtype=torch.int64, device="cuda")
+    tokens[0, 5, 1] = 320
+    _, _, bad = ops.audio_ce(logits, tokens, 29, 4, 2, 320)
+    assert bad.item() == 1
+
+
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+@pytest.mark.parametrize("soft", [False, True])
+def test_category_ce(ops, smoothing, soft):
+    B, C, ld = 37, 500, 512
+    logits = torch.zeros(B, ld, device="cuda")
+    logits[:, :C] = randn(B, C, seed=90, dtype=torch.float32) * 3
+    g = torch.Generator(device="cuda").manual_seed(91)
+    hard = torch.randint(0, C, (B,), device="cuda", generator=g)
+    if soft:  # CutMix-style mix of two one-hots (augment.py)
+        other = torch.randint(0, C, (B,), device="cuda", generator=g)
+        lam = torch.rand(B, 1, device="cuda", generator=g) * 0.4 + 0.6
+        labels = F.one_hot(hard, C).float() * lam + F.one_hot(other, C).float() * (1 - lam)
+    else:
+        labels = hard
+    lr = logits[:, :C].clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels, label_smoothing=smoothing)
+    loss, top1, top5, dl = ops.category_ce(logits, labels, C, smoothing, dscale=1.0 / B)
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    (gl,) = torch.autograd.grad(ref, lr)
+    assert rel(dl[:, :C], gl) < BF16_TOL
+    tgt = labels.argmax(-1) if soft else labels
+    corrects = lr.topk(5, dim=1)[1] == tgt.unsqueeze(1)
+    assert abs(top1.item() - corrects[:, 0].float().mean().item()) < 1e-6
+    assert abs(top5.item() - corrects.float().amax(1).mean().item()) < 1e-6

@@ -85,6 +85,9 @@ def main(depth=2, B=2, S=88):
     for r, k, n in worst[:25]:
         print(f"   {r:.3e}  {k}  |g|={n:.3e}")
     print("grad rel median", sorted(w[0] for w in worst)[len(worst) // 2])
+    print("all grads in arena order:")
+    for k, p in m._param_views.items():
+        print(f"   {rel(p.grad, Pq[k].grad):.3e}  {k}  |g|={float(Pq[k].grad.norm()):.3e} |g_native|={float(p.grad.norm()):.3e}")
     sd = m.state_dict()
     print("running_mean stem rel", rel(sd["stem3d.1.running_mean"], o["new_stats"]["stem3d.1.running_mean"]),
           "running_var l4", rel(sd["resnet.layer4.1.bn2.running_var"], o["new_stats"]["resnet.layer4.1.bn2.running_var"]))
