@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the SyncVSR LRW hot path (BASELINE.json: clips/sec fwd+bwd on LRW-shape [B,1,29,88,88]).
+
+    python bench.py --gpus N --steps K --warmup W            # native sm_100a arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port on the host cores)
+
+A step = zero_grad + forward + backward (+ gradient all-reduce for N > 1) + fused clip/AdamW + bf16 weight repack over
+one batch of B=64 clips per GPU (BASELINE.json configs[1]); `value` has the inputs resident in HBM, `e2e` copies them
+from pinned host memory every step and reads the loss back. Prints ONE JSON line on rank 0."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "clips/sec (fwd+bwd) LRW-shape [B,1,29,88,88]"
+FLOPS_PER_CLIP = 62.61e9  # fwd 21.46 GF, fwd+bwd 62.61 GF (2*MAC, A*G*V = 2560)
+B_PER_GPU = 64
+T, S = 29, 88
+
+
+def lrw_config(depth=12):
+    from oracle.ref_loader import AttrDict  # plain attr-dict helper only (no oracle arithmetic)
+
+    return AttrDict.wrap({
+        "data": {"use_word_boundary": False, "input_size": S},
+        "model": {"resnet": "resnet18", "wav2vec": {"path": "./vq-wav2vec_kmeans.pt"},
+                  "bert": {"type": "x-transformers", "num_tokens": 1, "dim": 512, "depth": depth, "heads": 8,
+                           "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": 0.0, "ff_dropout": 0.0,
+                           "use_rmsnorm": True, "ff_glu": True, "rotary_pos_emb": True, "num_labels": 500}},
+        "optim": {"optimizer": {"lr": 1e-4, "betas": [0.9, 0.999], "eps": 1e-6, "weight_decay": 0.01},
+                  "scheduler": {"name": "cosine", "num_warmup_steps": 15000, "num_training_steps": 270000},
+                  "lambda_audio": 10.0},
+        "train": {"label_smoothing": 0.0, "use_cutmix": False, "precision": "bf16", "gradient_clip_val": 1.0},
+    })
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1364.0), d.get("hbm_gbs", 6556.5), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# reference / CPU-baseline arm: the oracle port of the reference forward+backward on the host cores
+# -------------------------------------------------------------------------------------------------------------------
+def cpu_reference_clips_per_s(steps: int, warmup: int, batch: int = 2):
+    import torch
+
+    from oracle import lrw_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: v.clone().requires_grad_("running" not in k) for k, v in O.make_params(0).items()}
+    videos, tokens, labels, wm = O.make_inputs(1234, batch)
+
+    def one():
+        for v in P.values():
+            v.grad = None
+        out = O.lrw_forward(P, videos, tokens, labels, wm)
+        out["loss_total"].backward()
+        return float(out["loss_total"])
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
+    cps, ms, cores, threads = cpu_reference_clips_per_s(steps, warmup)
+    sample = (f"oracle port of lightning.py:133-191 fwd+bwd, fp32, B=2 x {steps} steps (+{warmup} warm-up), "
+              f"{threads} torch threads on {cores} host cores")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LRW word-level ResNet18+Transformer-12L, fwd+bwd, [2,1,29,88,88] per step (CPU sample)"},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# native arm
+# -------------------------------------------------------------------------------------------------------------------
+def run_native_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from syncvsr_b200._lib import check, lib
+    from syncvsr_b200.lightning import TransformerLightningModule
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = lib()
+    L.svsr_launch_count.restype = C.c_longlong
+
+    torch.manual_seed(1234 + rank)
+    model = TransformerLightningModule(lrw_config()).train()
+    opt = FusedAdamW.from_config(model)
+    step = DataParallelStep(model, opt)
+
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    B = B_PER_GPU
+    n_batches = 2
+    dev_batches = [(torch.randn(B, 1, T, S, S, device="cuda", generator=g),
+                    torch.randint(0, 320, (B, T * 4, 2), device="cuda", generator=g),
+                    torch.randint(0, 500, (B,), device="cuda", generator=g),
+                    torch.zeros(B, 1, device="cuda")) for _ in range(n_batches)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        step(*dev_batches[i % n_batches])
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events on the launching stream ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    check(L.svsr_prof_enable(1), "prof_enable")
+    launches0 = L.svsr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        metrics = step(*dev_batches[i % n_batches])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.svsr_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    prof = {}
+    for kind, name in ((0, "igemm_kernel"), (1, "wgrad_kernel")):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int()
+        check(L.svsr_prof_read(kind, C.byref(ms), C.byref(fl), C.byref(n)), "prof_read")
+        prof[name] = {"ms": ms.value, "flops": fl.value, "launches": n.value}
+    check(L.svsr_prof_enable(0), "prof_enable")
+    loss = float(metrics["loss_total"])
+    ms_per_step = ms_total / args.steps
+    value = world * B * 1e3 / ms_per_step
+
+    # ---- timed region 2: end to end through the public API with pinned HOST inputs ----
+    host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        hb = host_batches[i % n_batches]
+        db = tuple(t.to("cuda", non_blocking=True) for t in hb)
+        m = step(*db)
+        loss_host.copy_(m["loss_total"].reshape(1), non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * B * 1e3 / e2e_ms
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved_tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    share = {k: round(v["ms"] / ms_total, 4) for k, v in prof.items()}
+    roofline = {
+        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+        "launches_per_step": d["launches"] / args.steps, "avg_launch_us": d["ms"] * 1e3 / max(1, d["launches"]),
+        "share_of_step": share,
+        "whole_step_frac": value / world * FLOPS_PER_CLIP / (peak_tf * 1e12),
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "LRW word-level ResNet18+Transformer-12L (x-transformers), fwd+bwd+allreduce+AdamW, "
+                               f"[{B},1,29,88,88] per GPU (BASELINE configs[1])",
+                   "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2": "per-step working set 4.5 GB >> 126 MB L2; two alternating input batches",
+                   "loss_total": loss},
+        "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cps, cms, cores, threads = cpu_reference_clips_per_s(steps=4, warmup=1)
+        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port fwd+bwd fp32, B=2 x 4 steps (+1 warm-up), {cms:.0f} ms/step, "
+                                          f"{threads} threads on {cores} cores"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

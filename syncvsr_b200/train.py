@@ -1,0 +1,96 @@
+"""Data-parallel training step for the native LRW module: one process per GPU (torchrun), per-rank local BatchNorm
+statistics (the reference never wires sync_batchnorm, LRS/video/main.py:33-49), ONE NCCL all-reduce of the flat
+gradient arena per step (replaces DDP's bucketed reducer of Trainer(strategy="ddp"), LRW/video/src/train.py:28),
+then the fused clip + AdamW kernel on every rank (lightning.py:216-223; gradient_clip_val train.py:32)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib
+from .lightning import TransformerLightningModule, _cfg_get
+
+
+def cosine_with_warmup(step: int, base_lr: float, warmup: int, total: int) -> float:
+    """transformers.get_scheduler("cosine") as used by the reference (lightning.py:222): linear warm-up then
+    0.5*(1+cos(pi*progress))."""
+    if step < warmup:
+        return base_lr * step / max(1, warmup)
+    progress = (step - warmup) / max(1, total - warmup)
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, progress))))
+
+
+class FusedAdamW:
+    """AdamW over the module's flat arenas (decayed region first), with global-norm clipping fused in."""
+
+    def __init__(self, module: TransformerLightningModule, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01,
+                 max_grad_norm: float = 1.0):
+        self.module = module
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        p = module.flat_params
+        self.exp_avg = torch.zeros_like(p)
+        self.exp_avg_sq = torch.zeros_like(p)
+        self.scratch = torch.zeros(8, dtype=torch.float64, device=p.device)
+        L = lib()
+        L.svsr_lrw_decay_count.restype = C.c_int64
+        self.n_decay = int(L.svsr_lrw_decay_count(module._h))
+        self.n_total = p.numel()
+        self.t = 0
+
+    @classmethod
+    def from_config(cls, module: TransformerLightningModule) -> "FusedAdamW":
+        o = dict(_cfg_get(module.config, "optim.optimizer", {}) or {})
+        return cls(module, lr=float(o.get("lr", 1e-4)), betas=tuple(o.get("betas", (0.9, 0.999))),
+                   eps=float(o.get("eps", 1e-6)), weight_decay=float(o.get("weight_decay", 0.01)),
+                   max_grad_norm=float(_cfg_get(module.config, "train.gradient_clip_val", 1.0)))
+
+    def zero_grad(self) -> None:
+        self.module.flat_grads.zero_()
+
+    def step(self, lr: Optional[float] = None, grad_div: float = 1.0) -> None:
+        self.t += 1
+        m = self.module
+        check(lib().svsr_adamw_step(
+            C.c_void_p(m.flat_params.data_ptr()), C.c_void_p(m.flat_grads.data_ptr()),
+            C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_int64(self.n_decay),
+            C.c_int64(self.n_total), C.c_float(self.lr if lr is None else lr), C.c_float(self.betas[0]),
+            C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.weight_decay), C.c_int(self.t),
+            C.c_float(self.max_grad_norm), C.c_float(grad_div), C.c_void_p(self.scratch.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "svsr_adamw_step")
+        m.mark_weights_updated()
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm seen by the last step (device scalar, no sync)."""
+        return self.scratch.view(torch.float32)[3]
+
+
+class DataParallelStep:
+    """zero_grad -> forward -> backward -> all-reduce(SUM) of the flat gradient arena -> fused clip+AdamW.
+
+    The native forward/backward are called directly (no autograd graph); the reference-facing
+    `module(...)`/`loss.backward()` API is equivalent and is what the parity tests use."""
+
+    def __init__(self, module: TransformerLightningModule, optimizer: FusedAdamW, group=None):
+        self.module, self.opt, self.group = module, optimizer, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        sch = dict(_cfg_get(module.config, "optim.scheduler", {}) or {})
+        self.warmup = int(sch.get("num_warmup_steps", 0))
+        self.total = int(sch.get("num_training_steps", 1))
+        self.global_step = 0
+
+    def __call__(self, videos, audio_tokens, labels, word_mask=None) -> Dict[str, torch.Tensor]:
+        m = self.module
+        self.opt.zero_grad()
+        with torch.no_grad():
+            metrics = m(videos, audio_tokens, labels, word_mask)
+        check(lib().svsr_lrw_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrw_backward")
+        if self.world > 1:
+            dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        self.global_step += 1
+        lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
+        self.opt.step(lr=lr, grad_div=float(self.world))
+        return metrics

@@ -87,7 +87,8 @@ def test_forward_matches_reference_golden(Module, name, golden_dir):
     assert rel(la[:, 3, :], fx["logits_audio_t3"]) < 5e-2
     assert rel(m.logits_category().cpu(), fx["logits_category"]) < 5e-2
     sd = m.state_dict()
-    assert rel(sd["stem3d.1.running_mean"], fx["running_mean_stem"]) < 2e-3
+    # running_mean of the stem is ~1e-4 in magnitude (zero-mean conv output): absolute tolerance
+    assert (sd["stem3d.1.running_mean"].cpu() - fx["running_mean_stem"]).abs().max().item() < 2e-5
     assert rel(sd["resnet.layer4.1.bn2.running_var"], fx["running_var_l4"]) < 2e-2
     assert int(sd["stem3d.1.num_batches_tracked"]) == 1
     # the reference leaves exactly these parameters without gradient; the native module keeps them out of the arena
