@@ -587,7 +587,7 @@ int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int
   return SVSR_OK;
 }
 int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s) {
-  dim3 grid((N + 63) / 64, (unsigned)((M + 255) / 256 < 1 ? 1 : (M + 255) / 256));
+  dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64 < 1 ? 1 : (M + 63) / 64));
   colsum_bf16_kernel<<<grid, 256, 0, s>>>(dy, ld, db, M, N);
   LAUNCH_CHECK();
   return SVSR_OK;

@@ -157,9 +157,9 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
                      __nv_bfloat16* __restrict__ o, int n, int heads, int rotary_v) {
   extern __shared__ float sm[];
   float* sq = sm;
-  float* sk = sq + AT_MAXN * AT_LD;
-  float* sv = sk + AT_MAXN * AT_LD;
-  float* sp = sv + AT_MAXN * AT_LD;
+  float* sk = sq + n * AT_LD;
+  float* sv = sk + n * AT_LD;
+  float* sp = sv + n * AT_LD;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int inner = heads * AT_D, ld = 3 * inner;
   const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
@@ -186,11 +186,11 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
                      int rotary_v) {
   extern __shared__ float sm[];
   float* sq = sm;
-  float* sk = sq + AT_MAXN * AT_LD;
-  float* sv = sk + AT_MAXN * AT_LD;
-  float* sp = sv + AT_MAXN * AT_LD;
-  float* sdo = sp + AT_MAXN * AT_LD;
-  float* sds = sdo + AT_MAXN * AT_LD;
+  float* sk = sq + n * AT_LD;
+  float* sv = sk + n * AT_LD;
+  float* sp = sv + n * AT_LD;
+  float* sdo = sp + n * AT_LD;
+  float* sds = sdo + n * AT_LD;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int inner = heads * AT_D, ld = 3 * inner;
   const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
@@ -303,7 +303,7 @@ int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, in
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
                 __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s) {
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
-  const int blocks = (M + 7) / 8 < 148 ? (M + 7) / 8 : 148;
+  const int blocks = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
   if (D <= 512)
     rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps);
   else
@@ -319,10 +319,11 @@ int rotary_table(float* tab, int n, cudaStream_t s) {
 int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
                   int rotary_v, cudaStream_t s) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
-  const int smem = 4 * AT_MAXN * AT_LD * sizeof(float);
+  const int smem = 4 * n * AT_LD * sizeof(float);
+  const int smem_max = 4 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;
   if (!done) {
-    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
   attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v);
@@ -332,10 +333,11 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
                   int n, int heads, int rotary_v, cudaStream_t s) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
-  const int smem = 6 * AT_MAXN * AT_LD * sizeof(float);
+  const int smem = 6 * n * AT_LD * sizeof(float);
+  const int smem_max = 6 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;
   if (!done) {
-    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
   attention_bwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v);

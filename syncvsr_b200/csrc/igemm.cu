@@ -9,6 +9,7 @@ namespace svsr {
 
 struct IgemmKParams {
   int tiles_h, tiles_w;
+  int m_tiles, n_tiles;
   int bn, bh, bw;
   int o_N, OH, OW;
   int stride;
@@ -35,31 +36,29 @@ struct IgemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block too small");
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmKParams p) {
+  // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
+  // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
   using L = IgemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile -> (image block, row block, col block) of the logical output grid
-  const int mt = blockIdx.x;
-  const int nt = blockIdx.y;
-  const int tw = mt % p.tiles_w;
-  const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int tn = mt / (p.tiles_w * p.tiles_h);
-  const int n0 = tn * p.bn, oh0 = th * p.bh, ow0 = tw * p.bw;
   const int num_kb = p.ntaps * p.cblocks;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  const int m_tiles = p.m_tiles;
+  const int total_tiles = m_tiles * p.n_tiles;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -68,7 +67,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -81,19 +83,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int tap = kb / p.cblocks;
-        const int cc = kb - tap * p.cblocks;
-        uint8_t* sA = smem + stage * L::STAGE_BYTES;
-        uint8_t* sB = sA + L::A_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + L::B_BYTES));
-        tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
-                    oh0 * p.stride + p.tap_dh[tap], n0);
-        tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int n0 = tn * p.bn, oh0 = th * p.bh, ow0 = tw * p.bw;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int tap = kb / p.cblocks;
+          const int cc = kb - tap * p.cblocks;
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + L::B_BYTES));
+          tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
+                      oh0 * p.stride + p.tap_dh[tap], n0);
+          tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -103,25 +112,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int j = 0;  // local tile counter
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const int acc = j & 1;
+        const uint32_t use = (uint32_t)(j >> 1);
+        mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
-        const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t b_desc = umma_smem_desc_sw128(b_addr, 16, 1024);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
     __syncwarp();
   } else {
@@ -133,83 +150,95 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int rem = r - dn * hw;
     const int dh = rem / p.bw;
     const int dw = rem - dh * p.bw;
-    const int n = n0 + dn, oh = oh0 + dh, ow = ow0 + dw;
-    const bool row_valid = (r < p.bn * hw) && (n < p.o_N) && (oh < p.OH) && (ow < p.OW);
-    const long long pix =
-        ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
-    const long long row_off = pix * p.ldc + p.c_off;
-
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
+    int j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const int n = tn * p.bn + dn, oh = th * p.bh + dh, ow = tw * p.bw + dw;
+      const bool row_valid = (r < p.bn * hw) && (n < p.o_N) && (oh < p.OH) && (ow < p.OW);
+      const long long pix =
+          ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
+      const long long row_off = pix * p.ldc + p.c_off;
+      const int acc = j & 1;
+      mbar_wait(&tmem_full_bar[acc], (uint32_t)((j >> 1) & 1));
+      tcgen05_fence_after();
 
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-      tmem_ld_wait();
-      const int col0 = nt * BN + ch * 32;
-      if (!row_valid || col0 >= p.n_cols) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.n_cols) f[j] += __ldg(p.bias + col0 + j);
-      }
-      const bool full_chunk = (col0 + 32 <= p.n_cols);
-      if (p.resid) {
-        if (p.resid_fp32) {
-          const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t = reinterpret_cast<const float4*>(rp)[j];
-              f[4 * j] += t.x, f[4 * j + 1] += t.y, f[4 * j + 2] += t.z, f[4 * j + 3] += t.w;
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + ch * 32;
+        if (!row_valid || col0 >= p.n_cols) continue;
+        float f[32];
+  #pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias) {
+  #pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.n_cols) f[j] += __ldg(p.bias + col0 + j);
+        }
+        const bool full_chunk = (col0 + 32 <= p.n_cols);
+        if (p.resid) {
+          if (p.resid_fp32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
+            if (full_chunk) {
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 t = reinterpret_cast<const float4*>(rp)[j];
+                f[4 * j] += t.x, f[4 * j + 1] += t.y, f[4 * j + 2] += t.z, f[4 * j + 3] += t.w;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += rp[j];
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += rp[j];
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + row_off + col0;
+            if (full_chunk) {
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 t = reinterpret_cast<const uint4*>(rp)[j];
+                float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+                f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += b.x, f[8 * j + 3] += b.y;
+                f[8 * j + 4] += c.x, f[8 * j + 5] += c.y, f[8 * j + 6] += d.x, f[8 * j + 7] += d.y;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += __bfloat162float(rp[j]);
+            }
+          }
+        }
+        if (p.out_fp32) {
+          float* op = reinterpret_cast<float*>(p.out) + row_off + col0;
+          if (full_chunk) {
+  #pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = f[j];
           }
         } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + row_off + col0;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
           if (full_chunk) {
-#pragma unroll
+  #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 t = reinterpret_cast<const uint4*>(rp)[j];
-              float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-              f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += b.x, f[8 * j + 3] += b.y;
-              f[8 * j + 4] += c.x, f[8 * j + 5] += c.y, f[8 * j + 6] += d.x, f[8 * j + 7] += d.y;
+              uint4 t;
+              t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+              t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              reinterpret_cast<uint4*>(op)[j] = t;
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += __bfloat162float(rp[j]);
+            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = __float2bfloat16(f[j]);
           }
         }
+
       }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + row_off + col0;
-        if (full_chunk) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = f[j];
-        }
-      } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
-        if (full_chunk) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 t;
-            t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-            t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            reinterpret_cast<uint4*>(op)[j] = t;
-          }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = __float2bfloat16(f[j]);
-        }
-      }
+      // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
@@ -298,7 +327,11 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tmA, p.a, 4, dims, strides, box, es, true);
     if (rc) return rc;
   }
+  // N tile: the widest that still gives ~one wave of CTAs (small-M GEMMs of the encoder are latency bound)
+  const long long m_tiles = (long long)tiles_n * kp.tiles_h * kp.tiles_w;
   int BN = p.b_rows <= 64 ? 64 : (p.b_rows <= 128 ? 128 : 256);
+  if (BN == 256 && m_tiles * ((p.b_rows + 255) / 256) < 100) BN = 128;
+  if (BN == 128 && m_tiles * ((p.b_rows + 127) / 128) < 100) BN = 64;
   {
     uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
     uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
@@ -306,14 +339,17 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tmB, p.b, 2, dims, strides, box, nullptr, true);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)(tiles_n * kp.tiles_h * kp.tiles_w), (unsigned)((p.b_rows + BN - 1) / BN));
+  kp.m_tiles = (int)m_tiles;
+  kp.n_tiles = (p.b_rows + BN - 1) / BN;
+  const long long total_tiles = m_tiles * kp.n_tiles;
+  dim3 grid((unsigned)(total_tiles < 148 ? total_tiles : 148));
   const double flops = p.algo_flops > 0 ? p.algo_flops
                                         : 2.0 * p.o_N * p.OH * p.OW * (double)p.b_rows * p.ntaps * p.cin;
   prof_begin(PROF_IGEMM, flops, stream);
   int rc;
   switch (BN) {
-    case 64: rc = launch_t<64, 4>(tmA, tmB, kp, grid, stream); break;
-    case 128: rc = launch_t<128, 3>(tmA, tmB, kp, grid, stream); break;
+    case 64: rc = launch_t<64, 8>(tmA, tmB, kp, grid, stream); break;
+    case 128: rc = launch_t<128, 6>(tmA, tmB, kp, grid, stream); break;
     default: rc = launch_t<256, 4>(tmA, tmB, kp, grid, stream); break;
   }
   prof_end(stream);

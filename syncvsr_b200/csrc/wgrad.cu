@@ -52,7 +52,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr uint32_t TMEM_COLS = 512;
 
   // Rows >= box_rows of every block are never written by TMA: zero them once so they contribute 0 to the sums.
-  {
+  if (p.box_rows < 128) {
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < L::BAR_OFFSET / 16; i += blockDim.x) z[i] = zero;
@@ -213,8 +213,10 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
   if (kp.mb_per_cta > num_mblocks) kp.mb_per_cta = num_mblocks;
   const int gx = (num_mblocks + kp.mb_per_cta - 1) / kp.mb_per_cta;
   const int gy = (p.n_cols + BN - 1) / BN;
+  // split-K: enough CTAs to fill the chip twice, but at least ~4 pixel tiles per CTA so that the fixed cost
+  // (TMEM alloc, pipeline fill, fp32 red.add of the whole tile) is amortised
   int nsplit = (2 * 148 + gx * gy - 1) / (gx * gy);
-  if (nsplit > kp.ktiles) nsplit = kp.ktiles;
+  if (nsplit > (kp.ktiles + 3) / 4) nsplit = (kp.ktiles + 3) / 4;
   if (nsplit < 1) nsplit = 1;
 
   CUtensorMap tmA, tmB;

@@ -1,0 +1,118 @@
+"""CPU tests of the host-side logic: arena layout defined by the native engine (host code, no GPU needed), the LR
+schedule, and the data-parallel gradient reduction on a 2-rank gloo group."""
+import ctypes as C
+import math
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import lrw_oracle as O
+from syncvsr_b200 import _lib
+from syncvsr_b200.lightning import LrwConfig
+
+
+def _engine(B=2, depth=12, A=4, V=320):
+    L = _lib.lib()
+    for f in ("svsr_lrw_param_count", "svsr_lrw_buffer_count", "svsr_lrw_workspace_bytes", "svsr_lrw_decay_count"):
+        getattr(L, f).restype = C.c_int64
+    h = C.c_void_p()
+    cfg = LrwConfig(B, 29, 88, 88, 512, depth, 8, A, 2, V, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    _lib.check(L.svsr_lrw_create(C.byref(cfg), C.byref(h)), "create")
+    return L, h
+
+
+def _table(L, h):
+    name, ndim, off, decay = C.c_char_p(), C.c_int(), C.c_int64(), C.c_int()
+    shape = (C.c_int64 * 5)()
+    rows = []
+    for i in range(L.svsr_lrw_num_params(h)):
+        _lib.check(L.svsr_lrw_param_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off), C.byref(decay)), "info")
+        rows.append((name.value.decode(), tuple(shape[k] for k in range(ndim.value)), off.value, bool(decay.value)))
+    return rows
+
+
+def test_arena_layout_matches_reference_state_dict_and_decay_rule():
+    L, h = _engine()
+    rows = _table(L, h)
+    ref = O.make_params(0)  # reference-named tensors (validated against the reference module in test_oracle_cpu)
+    names = {r[0]: r[1] for r in rows}
+    trainable = {k: tuple(v.shape) for k, v in ref.items() if "running" not in k}
+    assert names == trainable
+    n_decay, n_total = L.svsr_lrw_decay_count(h), L.svsr_lrw_param_count(h)
+    spans = sorted((off, off + math.prod(shape)) for _, shape, off, _ in rows)
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0, "overlapping parameters"
+    assert spans[-1][1] <= n_total
+    for name, shape, off, decay in rows:
+        assert off % 4 == 0
+        assert decay == (len(shape) >= 2)  # lightning.py:217-219
+        assert (off < n_decay) == decay, name
+    # q, k, v of a layer are adjacent (one [1536, 512] operand)
+    offs = {r[0]: r[2] for r in rows}
+    assert offs["encoder.layers.0.1.to_k.weight"] - offs["encoder.layers.0.1.to_q.weight"] == 512 * 512
+    assert offs["encoder.layers.0.1.to_v.weight"] - offs["encoder.layers.0.1.to_k.weight"] == 512 * 512
+    assert sum(math.prod(s) for _, s, _, _ in rows) == 63_152_308  # = reference trainable params minus unused resnet stem/fc
+    L.svsr_lrw_destroy(h)
+
+
+def test_engine_rejects_unsupported_configs():
+    L = _lib.lib()
+    h = C.c_void_p()
+    bad = LrwConfig(2, 29, 88, 88, 513, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    assert L.svsr_lrw_create(C.byref(bad), C.byref(h)) == -1
+    assert b"dim" in L.svsr_last_error()
+    too_long = LrwConfig(2, 80, 88, 88, 512, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    assert L.svsr_lrw_create(C.byref(too_long), C.byref(h)) == -1
+
+
+def test_workspace_scales_with_batch():
+    L, h2 = _engine(B=2)
+    _, h64 = _engine(B=64)
+    w2, w64 = L.svsr_lrw_workspace_bytes(h2), L.svsr_lrw_workspace_bytes(h64)
+    assert w2 < w64 < 8 * 2**30
+    assert L.svsr_lrw_param_count(h2) == L.svsr_lrw_param_count(h64)
+
+
+def test_cosine_schedule_matches_transformers():
+    from transformers import get_scheduler
+
+    from syncvsr_b200.train import cosine_with_warmup
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-4)
+    sch = get_scheduler("cosine", optimizer=opt, num_warmup_steps=10, num_training_steps=100)
+    for step in range(1, 100):
+        opt.step()
+        sch.step()
+        assert sch.get_last_lr()[0] == pytest.approx(cosine_with_warmup(step, 1e-4, 10, 100), rel=1e-6, abs=1e-12)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # each rank holds the gradient arena of its own shard (synthetic): the DP step SUM-reduces the flat arena once
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1000, generator=g)
+    mine = flat.clone()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    ok = torch.allclose(flat, sum(gathered)) and torch.allclose(flat / world, torch.stack(gathered).mean(0), atol=1e-6)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
