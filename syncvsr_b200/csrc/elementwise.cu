@@ -247,10 +247,12 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
     const int oh = (int)(t1 % OH);
     const long long n = t1 / OH;
     const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
-    float best[8];
-    int bi[8];
+    // GELU is unimodal (decreasing below ~-0.75, increasing above), so the window maximum of gelu(z) is attained at
+    // the largest or the smallest z: track both extremes (first occurrence) and evaluate erf twice instead of 9 times.
+    float zmax[8], zmin[8];
+    int imax[8], imin[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) best[k] = -INFINITY, bi[k] = 0;
+    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, zmin[k] = INFINITY, imax[k] = 0, imin[k] = 0;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = 2 * oh + kh - 1;
@@ -262,10 +264,21 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
         const F8 v = ld8(y0 + ((n * IH + ih) * IW + iw) * C + g * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float a = gelu_f(v.v[k] * sc.v[k] + sh.v[k]);
-          if (a > best[k]) best[k] = a, bi[k] = kh * 3 + kw;  // first maximum wins (torch max_pool semantics)
+          const float z = v.v[k] * sc.v[k] + sh.v[k];
+          if (z > zmax[k]) zmax[k] = z, imax[k] = kh * 3 + kw;
+          if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
         }
       }
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = gelu_f(zmax[k]), b = gelu_f(zmin[k]);
+      // first maximum wins (torch max_pool semantics): on a tie the earlier window position
+      const bool take_min = (b > a) || (b == a && imin[k] < imax[k]);
+      best[k] = take_min ? b : a;
+      bi[k] = take_min ? imin[k] : imax[k];
     }
     F8 o;
 #pragma unroll

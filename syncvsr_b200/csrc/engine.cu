@@ -104,7 +104,12 @@ struct LrwEngine {
   // workspace offsets
   size_t patches, y0, x1, argmax, xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a,
       logits_c, dlogits_c, acc, bad_token, rot, stats_arena, stats_arena_bytes;
-  size_t dx, dxb, t_du, t_dh, t_dyn, t_do, t_dqkv, gbuf[5], stem_dz, wgrad_tmp;
+  size_t dx, dxb[3], t_du, t_dh[2], t_dyn, t_do, t_dqkv[2], gbuf[9], stem_dz, wgrad_tmp;
+  // weight-gradient side stream (backward): forked from / joined to the caller's stream with events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  int fork_idx = 0;
   // forward inputs remembered for backward
   uint32_t last_skip = 0;
   bool fwd_done = false;
@@ -301,13 +306,13 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   }
   // ---- backward scratch ----
   e.dx = b.take((size_t)e.M * D * 4);
-  e.dxb = b.take((size_t)e.M * D * 2);
+  for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * D * 2);
   e.t_du = b.take((size_t)e.M * F * 2);
-  e.t_dh = b.take((size_t)e.M * 2 * F * 2);
+  for (int i = 0; i < 2; ++i) e.t_dh[i] = b.take((size_t)e.M * 2 * F * 2);
   e.t_dyn = b.take((size_t)e.M * D * 2);
   e.t_do = b.take((size_t)e.M * inner * 2);
-  e.t_dqkv = b.take((size_t)e.M * 3 * inner * 2);
-  for (int i = 0; i < 5; ++i) e.gbuf[i] = b.take(n1 * 2);
+  for (int i = 0; i < 2; ++i) e.t_dqkv[i] = b.take((size_t)e.M * 3 * inner * 2);
+  for (int i = 0; i < 9; ++i) e.gbuf[i] = b.take(n1 * 2);
   e.stem_dz = b.take(n0 * 2);
   e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
   e.ws_bytes = b.off;
@@ -527,6 +532,39 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   return SVSR_OK;
 }
 
+// Backward runs on two streams: `s` carries the critical chain (dgrad GEMMs, BatchNorm / attention / norm backward),
+// `e.side` carries every weight-gradient GEMM (+ bias column sums, gradient unpack). The side work only reads
+// tensors the chain has finished (fork event) and the chain never overwrites a tensor the side stream may still be
+// reading: the hazard buffers (dc*, dxb, dh, dqkv) are double buffered and the chain waits for the side stream's
+// unit k-2 before starting unit k (bounded lag). HBM-bound BN kernels thereby overlap tensor-bound wgrad kernels.
+struct SideQueue {
+  LrwEngine& e;
+  cudaStream_t s;
+  int unit = 0;
+  int rc = SVSR_OK;
+  SideQueue(LrwEngine& e_, cudaStream_t s_) : e(e_), s(s_) {}
+  // everything enqueued on `s` so far becomes visible to the side stream
+  int fork() {
+    cudaEvent_t ev = e.ev_fork[e.fork_idx++ & 3];
+    SVSR_CHECK_CUDA(cudaEventRecord(ev, s));
+    SVSR_CHECK_CUDA(cudaStreamWaitEvent(e.side, ev, 0));
+    return SVSR_OK;
+  }
+  // close unit `unit` on the side stream and make the chain wait for unit-1 (so unit-2's buffers are reusable next)
+  int end_unit() {
+    SVSR_CHECK_CUDA(cudaEventRecord(e.ev_done[unit & 3], e.side));
+    if (unit >= 1) SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, e.ev_done[(unit - 1) & 3], 0));
+    ++unit;
+    return SVSR_OK;
+  }
+  int join() {
+    cudaEvent_t ev = e.ev_done[unit & 3];
+    SVSR_CHECK_CUDA(cudaEventRecord(ev, e.side));
+    SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, ev, 0));
+    return SVSR_OK;
+  }
+};
+
 static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s) {
   SVSR_REQUIRE(e.fwd_done, "lrw backward called before (or twice after) forward");
   e.fwd_done = false;
@@ -534,13 +572,17 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   float* dx = e.ws<float>(e.dx);
-  bf16* dxb = e.ws<bf16>(e.dxb);
+  SideQueue sq(e, s);
+  cudaStream_t w = e.side;  // weight-gradient stream
 
   if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)c.B * e.cat_ld, grad_scale, s));
   }
   // ---- heads: d last_hidden_state (fp32 stream gradient), weight/bias gradients ----
+  RC(sq.fork());
+  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<bf16>(e.lastb_cls), c.B, e.cat, w));
+  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), AGV, e.ws<bf16>(e.lastb_frames), e.N, e.aud, w));
   {
     IgemmProblem p;  // CLS rows: dx[b, 0, :] = dlogits_c[b] . Wc
     p.a = e.ws<bf16>(e.dlogits_c), p.a_N = c.B, p.a_C = e.cat_ld, p.cin = e.cat.ldt, p.ntaps = 1;
@@ -555,69 +597,86 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
     q.out = dx, q.out_fp32 = 1, q.ldc = D, q.o_H = 1, q.o_W = c.T + 1, q.o_ow = 1;
     RC(igemm_launch(q, s));
   }
-  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<bf16>(e.lastb_cls), c.B, e.cat, s));
-  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), AGV, e.ws<bf16>(e.lastb_frames), e.N, e.aud, s));
-  RC(cast_f32_to_bf16(dx, dxb, (long long)e.M * D, s));
+  int xb = 0;  // which dxb buffer holds the current bf16 copy of the stream gradient
+  RC(cast_f32_to_bf16(dx, e.ws<bf16>(e.dxb[xb]), (long long)e.M * D, s));
+  RC(sq.end_unit());
 
-  // ---- encoder, reversed ----
+  // ---- encoder, reversed: one unit per sublayer ----
   for (int i = c.depth - 1; i >= 0; --i) {
     EncLayerRef& L = e.enc[i];
     if (!(e.last_skip & (1u << (2 * i + 1)))) {
+      bf16* dxb = e.ws<bf16>(e.dxb[xb]);
+      bf16* dxb_next = e.ws<bf16>(e.dxb[(xb + 1) % 3]);  // 3-deep: unit k-1's side work may still read its copy
       bf16* du = e.ws<bf16>(e.t_du);
-      bf16* dh = e.ws<bf16>(e.t_dh);
+      bf16* dh = e.ws<bf16>(e.t_dh[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
+      RC(sq.fork());  // dxb complete
+      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.ubuf), e.M, L.ff2, w));
       RC(linear_dgrad(e, dxb, D, e.M, L.ff2, du, F, 0, s));
-      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.ubuf), e.M, L.ff2, s));
       RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, F, s));
+      RC(sq.fork());  // dh complete
+      RC(linear_wgrad(e, dh, 2 * F, e.ws<bf16>(L.xn_f), e.M, L.ff1, w));
       RC(linear_dgrad(e, dh, 2 * F, e.M, L.ff1, dyn, D, 0, s));
-      RC(linear_wgrad(e, dh, 2 * F, e.ws<bf16>(L.xn_f), e.M, L.ff1, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), e.P + L.g_f, e.ws<float>(L.inv_f), dx, dxb, e.G + L.g_f, e.M, D, 1e-8f,
-                     s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), e.P + L.g_f, e.ws<float>(L.inv_f), dx, dxb_next, e.G + L.g_f, e.M, D,
+                     1e-8f, s));
+      xb = (xb + 1) % 3;
+      RC(sq.end_unit());
     }
     if (!(e.last_skip & (1u << (2 * i)))) {
+      bf16* dxb = e.ws<bf16>(e.dxb[xb]);
+      bf16* dxb_next = e.ws<bf16>(e.dxb[(xb + 1) % 3]);  // 3-deep: unit k-1's side work may still read its copy
       bf16* d_o = e.ws<bf16>(e.t_do);
-      bf16* dqkv = e.ws<bf16>(e.t_dqkv);
+      bf16* dqkv = e.ws<bf16>(e.t_dqkv[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
+      RC(sq.fork());
+      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.obuf), e.M, L.out, w));
       RC(linear_dgrad(e, dxb, D, e.M, L.out, d_o, inner, 0, s));
-      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.obuf), e.M, L.out, s));
       RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s));
+      RC(sq.fork());
+      RC(linear_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), e.M, L.qkv, w));
       RC(linear_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, D, 0, s));
-      RC(linear_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), e.M, L.qkv, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), e.P + L.g_a, e.ws<float>(L.inv_a), dx, dxb, e.G + L.g_a, e.M, D, 1e-8f, s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), e.P + L.g_a, e.ws<float>(L.inv_a), dx, dxb_next, e.G + L.g_a, e.M, D, 1e-8f,
+                     s));
+      xb = (xb + 1) % 3;
+      RC(sq.end_unit());
     }
   }
 
   // ---- mean pool / CLS ----
   bf16* T0 = e.ws<bf16>(e.gbuf[0]);  // dOut of the current block, later da1
-  bf16* T1 = e.ws<bf16>(e.gbuf[1]);  // dc2, later dc1
-  bf16* T2 = e.ws<bf16>(e.gbuf[2]);  // relu-masked upstream gradient (identity shortcut branch)
-  bf16* T3 = e.ws<bf16>(e.gbuf[3]);  // dcds
-  bf16* T4 = e.ws<bf16>(e.gbuf[4]);  // dX of the current block
+  bf16* T2 = e.ws<bf16>(e.gbuf[1]);  // relu-masked upstream gradient (identity shortcut branch)
+  bf16* T4 = e.ws<bf16>(e.gbuf[2]);  // dX of the current block
   const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
   RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, D, s));
 
-  // ---- resnet trunk, reversed ----
+  // ---- resnet trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
   for (int bi = 7; bi >= 0; --bi) {
     BlockRef& blk = e.blocks[bi];
+    bf16* DC2 = e.ws<bf16>(e.gbuf[3 + (bi & 1)]);
+    bf16* DC1 = e.ws<bf16>(e.gbuf[5 + (bi & 1)]);
+    bf16* DCD = e.ws<bf16>(e.gbuf[7 + (bi & 1)]);
     const bf16* xin = bi == 0 ? e.ws<bf16>(e.x1) : e.ws<bf16>(e.blocks[bi - 1].out);
     const long long rows = (long long)e.N * blk.Hout * blk.Hout;
     const bf16* out = e.ws<bf16>(blk.out);
-    RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, T1, blk.ds ? nullptr : T2, s));
-    if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, T3, nullptr, s));
-    RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, T1, blk.conv2, s));
-    RC(conv_dgrad(e, T1, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
-    RC(bn_bwd(e, T0, e.ws<bf16>(blk.a1), e.ws<bf16>(blk.c1), rows, blk.bn1, T1, nullptr, s));  // T1 := dc1
-    RC(conv_wgrad(e, xin, blk.Hin, T1, blk.conv1, s));
+    RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : T2, s));
+    if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
+    RC(sq.fork());  // dc2 (and dcds) complete
+    RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
+    if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
+    RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
+    RC(bn_bwd(e, T0, e.ws<bf16>(blk.a1), e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s));
+    RC(sq.fork());  // dc1 complete
+    RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
     if (blk.ds) {
-      RC(conv_wgrad(e, xin, blk.Hin, T3, blk.convds, s));
       SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
-      RC(conv_dgrad(e, T3, blk.Hin, blk.convds, T4, nullptr, s));
-      RC(conv_dgrad(e, T1, blk.Hin, blk.conv1, T4, T4, s));
+      RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, T4, nullptr, s));
+      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s));
     } else {
-      RC(conv_dgrad(e, T1, blk.Hin, blk.conv1, T4, T2, s));
+      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T2, s));
     }
     bf16* t = T0;
     T0 = T4, T4 = t;
+    RC(sq.end_unit());
   }
 
   // ---- stem ----
@@ -625,9 +684,10 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
   RC(stem_pool_gelu_bwd(T0, e.ws<uint8_t>(e.argmax), e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), dz, e.N, e.H0,
                         e.H0, s));
   RC(bn_bwd(e, dz, nullptr, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, dz, nullptr, s));
+  RC(sq.fork());
   {
     float* tmp = e.ws<float>(e.wgrad_tmp);
-    SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, 320 * 64 * 4, s));
+    SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, 320 * 64 * 4, w));
     WgradProblem p;
     p.a = e.ws<bf16>(e.patches), p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 64, p.a_cin = 64;
     p.ntaps = 5;
@@ -636,9 +696,10 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
     p.k_N = c.B, p.k_H = c.T, p.k_W = e.H0 * e.H0;
     p.out = tmp, p.ldo = 64;
     p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
-    RC(wgrad_launch(p, s));
-    RC(unpack_stem_wgrad(tmp, e.G + e.stem_conv.w, s));
+    RC(wgrad_launch(p, w));
+    RC(unpack_stem_wgrad(tmp, e.G + e.stem_conv.w, w));
   }
+  RC(sq.join());
   return SVSR_OK;
 }
 
@@ -665,7 +726,12 @@ int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle) {
   return SVSR_OK;
 }
 int svsr_lrw_destroy(void* h) {
-  delete static_cast<LrwEngine*>(h);
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  if (e && e->side) {
+    cudaStreamDestroy(e->side);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(e->ev_fork[i]), cudaEventDestroy(e->ev_done[i]);
+  }
+  delete e;
   return SVSR_OK;
 }
 int64_t svsr_lrw_param_count(void* h) { return static_cast<LrwEngine*>(h)->param_count; }
@@ -699,6 +765,13 @@ int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* wo
   SVSR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0,
                "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
   e->P = params, e->G = grads, e->BUF = buffers, e->WS = static_cast<uint8_t*>(workspace);
+  if (!e->side) {  // first bind happens on the GPU box: create the weight-gradient stream and its events
+    SVSR_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+      SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming));
+      SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    }
+  }
   return SVSR_OK;
 }
 int svsr_lrw_pack_weights(void* h, void* stream) {
