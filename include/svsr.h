@@ -156,6 +156,11 @@ int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* 
 /* (*grad_scale) * d loss_total / d params accumulated (+=) into the gradient arena; grad_scale is a DEVICE fp32
  * scalar (the upstream gradient autograd hands to loss_total) or NULL for 1. One backward per forward. */
 int svsr_lrw_backward(void* handle, const float* grad_scale, void* stream);
+/* The same backward in two stages so that the data-parallel step can overlap communication with compute:
+ * stage 0 = loss heads + encoder + mean-pool (completes the gradient arena range returned by
+ * svsr_lrw_early_grad_region: cls_token, encoder and head weights, ~160 MB), stage 1 = ResNet trunk + stem. */
+int svsr_lrw_backward_stage(void* handle, const float* grad_scale, int stage, void* stream);
+int svsr_lrw_early_grad_region(void* handle, int64_t* begin, int64_t* end);
 /* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */
 int svsr_lrw_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
 

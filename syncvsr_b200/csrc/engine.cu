@@ -113,6 +113,7 @@ struct LrwEngine {
   // forward inputs remembered for backward
   uint32_t last_skip = 0;
   bool fwd_done = false;
+  bool bwd_stage0_done = false;
 
   template <class T>
   T* ws(size_t off) const {
@@ -358,7 +359,8 @@ static int linear_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16*
   return SVSR_OK;
 }
 
-static int conv_fwd(const LrwEngine& e, const bf16* x, int Hin, const ConvRef& c, bf16* y, cudaStream_t s) {
+static int conv_fwd(const LrwEngine& e, const bf16* x, int Hin, const ConvRef& c, bf16* y, double* bn_stats,
+                    cudaStream_t s) {
   IgemmProblem p;
   p.a = x, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = c.cin, p.cin = c.cin, p.stride = c.stride;
   p.ntaps = c.R * c.R;
@@ -371,6 +373,7 @@ static int conv_fwd(const LrwEngine& e, const bf16* x, int Hin, const ConvRef& c
   p.o_N = e.N, p.OH = Ho, p.OW = Ho;
   p.b = e.ws<bf16>(c.wf), p.b_rows = c.cout, p.b_cols = c.R * c.R * c.cin;
   p.out = y, p.ldc = c.cout, p.o_H = Ho, p.o_W = Ho;
+  p.bn_stats = bn_stats;
   return igemm_launch(p, s);
 }
 extern "C" int svsr_conv2d_dgrad(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int,
@@ -397,8 +400,9 @@ static int conv_wgrad(const LrwEngine& e, const bf16* x, int Hin, const bf16* dy
   return unpack_conv_wgrad(tmp, e.G + c.w, c.cout, c.cin, c.R, c.R, s);
 }
 
+// batch statistics were accumulated by the producing conv's epilogue (IgemmProblem::bn_stats)
 static int bn_fwd(const LrwEngine& e, const bf16* x, long long rows, const BnRef& bn, int train, cudaStream_t s) {
-  if (train) RC(bn_stats(x, rows, bn.C, e.ws<double>(bn.stats_f), s));
+  (void)x;
   return bn_finalize(e.ws<double>(bn.stats_f), rows, bn.C, e.P + bn.gamma, e.P + bn.beta, e.cfg.bn_eps,
                      e.cfg.bn_momentum, e.BUF + bn.rmean, e.BUF + bn.rvar, e.ws<float>(bn.coef), train ? 1 : -1, s);
 }
@@ -457,6 +461,7 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     p.b = e.ws<bf16>(e.stem_conv.wf), p.b_rows = 64, p.b_cols = 320;
     p.out = e.ws<bf16>(e.y0), p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
     p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
+    p.bn_stats = train ? e.ws<double>(e.stem_bn.stats_f) : nullptr;
     RC(igemm_launch(p, s));
   }
   RC(bn_fwd(e, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
@@ -467,14 +472,16 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   const bf16* x = e.ws<bf16>(e.x1);
   for (auto& blk : e.blocks) {
     const long long rows = (long long)e.N * blk.Hout * blk.Hout;
-    RC(conv_fwd(e, x, blk.Hin, blk.conv1, e.ws<bf16>(blk.c1), s));
+    RC(conv_fwd(e, x, blk.Hin, blk.conv1, e.ws<bf16>(blk.c1), train ? e.ws<double>(blk.bn1.stats_f) : nullptr, s));
     RC(bn_fwd(e, e.ws<bf16>(blk.c1), rows, blk.bn1, train, s));
     RC(bn_apply(e.ws<bf16>(blk.c1), e.ws<float>(blk.bn1.coef), nullptr, nullptr, 1, e.ws<bf16>(blk.a1), rows, blk.cout,
                 s));
-    RC(conv_fwd(e, e.ws<bf16>(blk.a1), blk.Hout, blk.conv2, e.ws<bf16>(blk.c2), s));
+    RC(conv_fwd(e, e.ws<bf16>(blk.a1), blk.Hout, blk.conv2, e.ws<bf16>(blk.c2),
+                train ? e.ws<double>(blk.bn2.stats_f) : nullptr, s));
     RC(bn_fwd(e, e.ws<bf16>(blk.c2), rows, blk.bn2, train, s));
     if (blk.ds) {
-      RC(conv_fwd(e, x, blk.Hin, blk.convds, e.ws<bf16>(blk.cds), s));
+      RC(conv_fwd(e, x, blk.Hin, blk.convds, e.ws<bf16>(blk.cds), train ? e.ws<double>(blk.bnds.stats_f) : nullptr,
+                  s));
       RC(bn_fwd(e, e.ws<bf16>(blk.cds), rows, blk.bnds, train, s));
       RC(bn_apply(e.ws<bf16>(blk.c2), e.ws<float>(blk.bn2.coef), e.ws<bf16>(blk.cds), e.ws<float>(blk.bnds.coef), 1,
                   e.ws<bf16>(blk.out), rows, blk.cout, s));
@@ -565,16 +572,26 @@ struct SideQueue {
   }
 };
 
-static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s) {
-  SVSR_REQUIRE(e.fwd_done, "lrw backward called before (or twice after) forward");
-  e.fwd_done = false;
+// stage 0: loss heads + encoder + mean-pool/CLS (completes the gradients of cls_token, encoder and head weights);
+// stage 1: ResNet trunk + stem. stage < 0: both. Each stage joins the side stream before returning.
+static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cudaStream_t s) {
+  if (stage <= 0) {
+    SVSR_REQUIRE(e.fwd_done, "lrw backward called before (or twice after) forward");
+    e.fwd_done = false;
+    e.bwd_stage0_done = false;
+  } else {
+    SVSR_REQUIRE(e.bwd_stage0_done, "lrw backward stage 1 called before stage 0");
+  }
   const svsr_lrw_config& c = e.cfg;
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   float* dx = e.ws<float>(e.dx);
   SideQueue sq(e, s);
   cudaStream_t w = e.side;  // weight-gradient stream
-
+  bf16* T0 = e.ws<bf16>(e.gbuf[0]);  // dOut of the current block, later da1
+  bf16* T2 = e.ws<bf16>(e.gbuf[1]);  // relu-masked upstream gradient (identity shortcut branch)
+  bf16* T4 = e.ws<bf16>(e.gbuf[2]);  // dX of the current block
+  if (stage <= 0) {
   if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)c.B * e.cat_ld, grad_scale, s));
@@ -643,11 +660,11 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, cudaStream_t s
   }
 
   // ---- mean pool / CLS ----
-  bf16* T0 = e.ws<bf16>(e.gbuf[0]);  // dOut of the current block, later da1
-  bf16* T2 = e.ws<bf16>(e.gbuf[1]);  // relu-masked upstream gradient (identity shortcut branch)
-  bf16* T4 = e.ws<bf16>(e.gbuf[2]);  // dX of the current block
   const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
   RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, D, s));
+  e.bwd_stage0_done = true;
+  if (stage == 0) return sq.join();
+  }  // stage <= 0
 
   // ---- resnet trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
   for (int bi = 7; bi >= 0; --bi) {
@@ -800,7 +817,18 @@ int svsr_lrw_forward_videos(void* h, const float* videos, int train, void* strea
 int svsr_lrw_backward(void* h, const float* grad_scale, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
-  return engine_backward(*e, grad_scale, static_cast<cudaStream_t>(stream));
+  return engine_backward(*e, grad_scale, -1, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_backward_stage(void* h, const float* grad_scale, int stage, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  SVSR_REQUIRE(stage == 0 || stage == 1, "lrw_backward_stage: stage must be 0 or 1");
+  return engine_backward(*e, grad_scale, stage, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrw_early_grad_region(void* h, int64_t* begin, int64_t* end) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  *begin = e->cls_off, *end = e->decay_count;
+  return SVSR_OK;
 }
 int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* dtype) {
   LrwEngine* e = static_cast<LrwEngine*>(h);

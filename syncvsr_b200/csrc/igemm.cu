@@ -27,6 +27,7 @@ struct IgemmKParams {
   int o_H, o_W, o_sh, o_sw, o_oh, o_ow;
   int n_cols;
   float alpha;
+  double* bn_stats;
 };
 
 template <int BN, int STAGES>
@@ -35,9 +36,25 @@ struct IgemmSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int STATS_OFFSET = BAR_OFFSET + 256;  // fp32 [2][512] per-CTA BatchNorm partial sums
+  static constexpr int TOTAL = STATS_OFFSET + 4096 + 1024;  // + alignment slack
   static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block too small");
 };
+
+// Transposed warp reduction: every lane holds 32 values (one accumulator row); afterwards lane l holds in v[0] the
+// sum over the 32 lanes of value l. 31 shuffles (halving exchange) instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
@@ -52,6 +69,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [2][512]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,6 +92,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (p.bn_stats)
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_stats[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -240,6 +260,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const int t = threadIdx.x - 64;
+      for (int cidx = t; cidx < p.n_cols; cidx += 128) {
+        atomicAdd(p.bn_stats + cidx, (double)s_stats[cidx]);
+        atomicAdd(p.bn_stats + p.n_cols + cidx, (double)s_stats[512 + cidx]);
+      }
+    }
   }
 
   tcgen05_fence_before();
@@ -315,6 +343,8 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.o_H = p.o_H, kp.o_W = p.o_W, kp.o_sh = p.o_sh, kp.o_sw = p.o_sw, kp.o_oh = p.o_oh, kp.o_ow = p.o_ow;
   kp.n_cols = p.b_rows;
   kp.alpha = p.alpha;
+  kp.bn_stats = p.bn_stats;
+  SVSR_REQUIRE(!p.bn_stats || p.b_rows <= 512, "igemm: fused BN statistics support at most 512 output channels");
 
   // A: [a_N, a_H, a_W, a_C] NHWC, box = (64 ch, bw, bh, bn) pixels, traversal stride for strided convs.
   CUtensorMap tmA, tmB;

@@ -42,6 +42,9 @@ struct IgemmProblem {
   const void* resid = nullptr;  // same geometry as out (pitch ldc, offset c_off), or null
   int resid_fp32 = 0;
   float alpha = 1.0f;  // out = alpha*acc (+bias) (+resid)
+  // optional fused BatchNorm statistics: fp64 [2][b_rows] accumulators (+=): per-output-channel sum and sum of
+  // squares of the fp32 accumulators over all valid pixels (train-mode BN of the conv output, lightning.py:51)
+  double* bn_stats = nullptr;
   double algo_flops = 0;  // algorithmic FLOPs of this launch for the profiler (0 = 2*pixels*N*taps*cin)
 };
 
