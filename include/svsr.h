@@ -43,6 +43,12 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
 int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
 
+/* svsr_conv2d_fprop that also accumulates (+=) the train-mode BatchNorm statistics of its output in the epilogue:
+ * bn_stats fp64 [2][Cout] = per-channel sum and sum of squares of the fp32 accumulators over all output pixels
+ * (conv -> BatchNorm pairs of lightning.py:50-51 and of every BasicBlock). Cout <= 512. */
+int svsr_conv2d_fprop_bnstats(const void* x, const void* w, void* y, double* bn_stats, int N, int H, int W, int Cin,
+                              int Cout, int R, int S, int stride, int pad, void* stream);
+
 /* Same-size correlation with an explicit tap list: y[n,h,w,:] = sum_t x[n, h+dh[t], w+dw[t], :] . w[:, t*Cin:(t+1)*Cin]^T
  * (zero outside the image). The temporal half of the stem's Conv3d runs through this with taps (kt-2, 0) over the
  * [T, OH*OW] patch image (lightning.py:50). */
@@ -100,8 +106,10 @@ int svsr_rotary_table(float* tab, int n, void* stream);
 int svsr_attention_fwd(const void* qkv, const float* rot, void* o, int B, int n, int heads, int rotary_v, void* stream);
 int svsr_attention_bwd(const void* qkv, const float* rot, const void* d_o, void* dqkv, int B, int n, int heads,
                        int rotary_v, void* stream);
-int svsr_geglu_fwd(const void* h, void* u, int M, int F, void* stream);
-int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, void* stream);
+/* GEGLU + Dropout(ff_dropout): u = dropout(h[:, :F] * gelu(h[:, F:])). The keep-mask is a counter-based function of
+ * (seed, element index), regenerated identically by the backward; p_drop = 0 disables it. */
+int svsr_geglu_fwd(const void* h, void* u, int M, int F, float p_drop, uint64_t seed, void* stream);
+int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, float p_drop, uint64_t seed, void* stream);
 /* F.cross_entropy over quantised audio tokens (lightning.py:168-171): logits fp32 [B*T, A*G*V]; row (b,t), group
  * c=a*G+g is scored against tokens[b*tok_stride_b + (t*A+a)*G + g]. acc[0] += sum nll (fp64);
  * dlogits (bf16, optional) = (softmax - onehot) * dscale; *bad_token = 1 if a token is outside [0,V). */
@@ -128,6 +136,7 @@ typedef struct svsr_lrw_config {
   float lambda_audio;             /* optim.lambda_audio */
   float label_smoothing;          /* train.label_smoothing */
   float bn_eps, bn_momentum;      /* torch.nn.BatchNorm defaults 1e-5 / 0.1 */
+  float ff_dropout;               /* model.bert.ff_dropout (training only; mask seeded per forward call) */
 } svsr_lrw_config;
 
 int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle);
@@ -146,11 +155,12 @@ int svsr_lrw_bind(void* handle, float* params, float* grads, float* buffers, voi
 int svsr_lrw_pack_weights(void* handle, void* stream);
 /* videos fp32 [B,1,T,H,W]; tokens int64 [B, >=T*A, G] with batch stride tok_stride_b (elements); labels int64 [B]
  * or soft_labels fp32 [B,num_labels] (CutMix). train: batch-stat BN + buffer update. skip_mask bit i drops encoder
- * sublayer i (layer_dropout decided on the host like the reference). metrics (device fp32[5]) = loss_total,
+ * sublayer i (layer_dropout decided on the host like the reference); dropout_seed seeds this step's ff_dropout masks.
+ * metrics (device fp32[5]) = loss_total,
  * loss_category, loss_audio, accuracy_top1, accuracy_top5. */
 int svsr_lrw_forward(void* handle, const float* videos, const int64_t* tokens, int64_t tok_stride_b,
-                     const int64_t* labels, const float* soft_labels, int train, uint32_t skip_mask, float* metrics,
-                     void* stream);
+                     const int64_t* labels, const float* soft_labels, int train, uint32_t skip_mask,
+                     uint64_t dropout_seed, float* metrics, void* stream);
 /* forward_videos (lightning.py:112-119) only: fills the "inputs_embeds" tensor ([B,T+1,dim] fp32, row 0 = CLS) */
 int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* stream);
 /* (*grad_scale) * d loss_total / d params accumulated (+=) into the gradient arena; grad_scale is a DEVICE fp32

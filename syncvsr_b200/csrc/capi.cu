@@ -49,6 +49,26 @@ int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, 
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int svsr_conv2d_fprop_bnstats(const void* x, const void* w, void* y, double* bn_stats, int N, int H, int W, int Cin,
+                              int Cout, int R, int S, int stride, int pad, void* stream) {
+  SVSR_REQUIRE(R * S <= IGEMM_MAX_TAPS && bn_stats, "conv_bnstats: bad arguments");
+  IgemmProblem p;
+  p.a = x, p.a_N = N, p.a_H = H, p.a_W = W, p.a_C = Cin, p.a_coff = 0, p.cin = Cin, p.stride = stride;
+  p.ntaps = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int t = r * S + s;
+      p.tap_dh[t] = r - pad, p.tap_dw[t] = s - pad, p.tap_kbase[t] = t * Cin;
+    }
+  const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+  p.o_N = N, p.OH = OH, p.OW = OW;
+  p.b = w, p.b_rows = Cout, p.b_cols = R * S * Cin;
+  p.out = y, p.out_fp32 = 0, p.ldc = Cout, p.c_off = 0;
+  p.o_H = OH, p.o_W = OW;
+  p.bn_stats = bn_stats;
+  return igemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
 int svsr_conv_taps_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int ntaps,
                          const int* tap_dh, const int* tap_dw, int out_fp32, void* stream) {
   SVSR_REQUIRE(ntaps >= 1 && ntaps <= IGEMM_MAX_TAPS && tap_dh && tap_dw, "conv_taps: bad tap list");

@@ -82,11 +82,14 @@ int svsr_attention_bwd(const void* qkv, const float* rot, const void* d_o, void*
   return attention_bwd(static_cast<const bf16*>(qkv), rot, static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), B,
                        n, heads, rotary_v, ST(stream));
 }
-int svsr_geglu_fwd(const void* h, void* u, int M, int F, void* stream) {
-  return geglu_fwd(static_cast<const bf16*>(h), static_cast<bf16*>(u), M, F, ST(stream));
+int svsr_geglu_fwd(const void* h, void* u, int M, int F, float p_drop, uint64_t seed, void* stream) {
+  SVSR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "geglu: dropout p=%f out of [0,1)", p_drop);
+  return geglu_fwd(static_cast<const bf16*>(h), static_cast<bf16*>(u), M, F, p_drop, seed, ST(stream));
 }
-int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, void* stream) {
-  return geglu_bwd(static_cast<const bf16*>(h), static_cast<const bf16*>(du), static_cast<bf16*>(dh), M, F, ST(stream));
+int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, float p_drop, uint64_t seed, void* stream) {
+  SVSR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "geglu: dropout p=%f out of [0,1)", p_drop);
+  return geglu_bwd(static_cast<const bf16*>(h), static_cast<const bf16*>(du), static_cast<bf16*>(dh), M, F, p_drop, seed,
+                   ST(stream));
 }
 
 int svsr_audio_ce(const float* logits, int ld, const int64_t* tokens, int64_t tok_stride_b, int B, int T, int A, int G,

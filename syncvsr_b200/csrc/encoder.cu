@@ -253,22 +253,41 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
+// counter-based dropout mask: keep(idx) is a pure function of (seed, element index), so backward regenerates it
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long x = seed ^ (idx * 0x9E3779B97F4A7C15ULL);
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (float)((unsigned)(x >> 40)) * (1.0f / 16777216.0f) >= p;
+}
+
+// u = dropout_p(value * gelu(gate))   (x-transformers FeedForward: GLU -> Dropout(ff_dropout) -> Linear)
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M,
-                                 int F) {
+                                 int F, float p, unsigned long long seed) {
   const long long total = M * (F / 2);
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (F / 2);
     const int c = (int)(i % (F / 2)) * 2;
     const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + c);
     const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
-    *reinterpret_cast<__nv_bfloat162*>(u + r * F + c) =
-        __floats2bfloat162_rn(__low2float(v) * gelu_f(__low2float(gt)), __high2float(v) * gelu_f(__high2float(gt)));
+    float o0 = __low2float(v) * gelu_f(__low2float(gt)), o1 = __high2float(v) * gelu_f(__high2float(gt));
+    if (p > 0.f) {
+      o0 = dropout_keep(seed, (unsigned long long)(r * F + c), p) ? o0 * keep_scale : 0.f;
+      o1 = dropout_keep(seed, (unsigned long long)(r * F + c + 1), p) ? o1 * keep_scale : 0.f;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(u + r * F + c) = __floats2bfloat162_rn(o0, o1);
   }
 }
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ du,
-                                 __nv_bfloat16* __restrict__ dh, long long M, int F) {
+                                 __nv_bfloat16* __restrict__ dh, long long M, int F, float p,
+                                 unsigned long long seed) {
   const long long total = M * (F / 2);
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (F / 2);
@@ -277,7 +296,11 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv
     const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
     const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(du + r * F + c);
     const float v0 = __low2float(v), v1 = __high2float(v), g0 = __low2float(gt), g1 = __high2float(gt);
-    const float d0 = __low2float(d), d1 = __high2float(d);
+    float d0 = __low2float(d), d1 = __high2float(d);
+    if (p > 0.f) {
+      d0 = dropout_keep(seed, (unsigned long long)(r * F + c), p) ? d0 * keep_scale : 0.f;
+      d1 = dropout_keep(seed, (unsigned long long)(r * F + c + 1), p) ? d1 * keep_scale : 0.f;
+    }
     *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + c) = __floats2bfloat162_rn(d0 * gelu_f(g0), d1 * gelu_f(g1));
     *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + F + c) =
         __floats2bfloat162_rn(d0 * v0 * gelu_grad_f(g0), d1 * v1 * gelu_grad_f(g1));
@@ -344,17 +367,18 @@ int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat1
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, cudaStream_t s) {
+int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s) {
   const long long total = (long long)M * (F / 2);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F);
+  geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F, p, seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, cudaStream_t s) {
+int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, float p,
+              unsigned long long seed, cudaStream_t s) {
   const long long total = (long long)M * (F / 2);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F);
+  geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F, p, seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

@@ -21,8 +21,10 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
                   int n, int heads, int rotary_v, cudaStream_t s);
 
-// u[M,F] = h[:, :F] * gelu(h[:, F:]) ; dh from du
-int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, cudaStream_t s);
-int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, cudaStream_t s);
+// u[M,F] = dropout_p(h[:, :F] * gelu(h[:, F:])) ; dh from du. The dropout mask is a counter-based function of
+// (seed, element index): forward and backward regenerate the same mask, nothing is stored. p = 0 disables it.
+int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s);
+int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, float p,
+              unsigned long long seed, cudaStream_t s);
 
 }  // namespace svsr

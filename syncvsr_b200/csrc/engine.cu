@@ -112,6 +112,8 @@ struct LrwEngine {
   int fork_idx = 0;
   // forward inputs remembered for backward
   uint32_t last_skip = 0;
+  unsigned long long last_seed = 0;
+  int last_train = 0;
   bool fwd_done = false;
   bool bwd_stage0_done = false;
 
@@ -196,6 +198,7 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   SVSR_REQUIRE(c.dim == 512 && c.heads * 64 == 512, "lrw: encoder dim must be 512 with 8 heads of 64 (got %d/%d)",
                c.dim, c.heads);
   SVSR_REQUIRE(c.depth >= 1 && c.depth <= 16, "lrw: depth %d out of range", c.depth);
+  SVSR_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f, "lrw: ff_dropout %f out of [0,1)", c.ff_dropout);
   SVSR_REQUIRE(c.T + 1 <= 64, "lrw: sequence length %d too long for the attention core", c.T + 1);
   SVSR_REQUIRE((c.audio_alignment * c.vq_groups * c.audio_vocab) % 64 == 0,
                "lrw: audio logits per frame (%d) must be a multiple of 64",
@@ -444,7 +447,7 @@ static int engine_pack(LrwEngine& e, cudaStream_t s) {
 
 static int engine_forward(LrwEngine& e, const float* videos, const long long* tokens, long long tok_stride_b,
                           const long long* labels, const float* soft_labels, int train, uint32_t skip_mask,
-                          float* metrics, int videos_only, cudaStream_t s) {
+                          unsigned long long dropout_seed, float* metrics, int videos_only, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.stats_arena), 0, e.stats_arena_bytes, s));
@@ -516,7 +519,8 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     } else {
       RC(rmsnorm_fwd(xf, e.P + L.g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, D, 1e-8f, s));
       RC(linear_fwd(e, e.ws<bf16>(L.xn_f), e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * F, 0, nullptr, 0, s));
-      RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, F, s));
+      RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, F, train ? c.ff_dropout : 0.f,
+                   dropout_seed + 0x1000ULL * (unsigned long long)i, s));
       RC(linear_fwd(e, e.ws<bf16>(L.ubuf), e.M, L.ff2, xo, D, 1, xf, 1, s));
     }
   }
@@ -535,6 +539,8 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
               c.lambda_audio / (float)audio_rows, s));
   RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s));
   e.last_skip = skip_mask;
+  e.last_seed = dropout_seed;
+  e.last_train = train;
   e.fwd_done = true;
   return SVSR_OK;
 }
@@ -630,7 +636,8 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
       RC(sq.fork());  // dxb complete
       RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.ubuf), e.M, L.ff2, w));
       RC(linear_dgrad(e, dxb, D, e.M, L.ff2, du, F, 0, s));
-      RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, F, s));
+      RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, F, e.last_train ? c.ff_dropout : 0.f,
+                   e.last_seed + 0x1000ULL * (unsigned long long)i, s));
       RC(sq.fork());  // dh complete
       RC(linear_wgrad(e, dh, 2 * F, e.ws<bf16>(L.xn_f), e.M, L.ff1, w));
       RC(linear_dgrad(e, dh, 2 * F, e.M, L.ff1, dyn, D, 0, s));
@@ -797,21 +804,22 @@ int svsr_lrw_pack_weights(void* h, void* stream) {
   return engine_pack(*e, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
-                     const float* soft_labels, int train, uint32_t skip_mask, float* metrics, void* stream) {
+                     const float* soft_labels, int train, uint32_t skip_mask, uint64_t dropout_seed, float* metrics,
+                     void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
   SVSR_REQUIRE(videos && tokens && metrics, "lrw_forward: null input");
   SVSR_REQUIRE(tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
                "lrw_forward: audio_tokens has fewer than T*alignment rows per clip");
   return engine_forward(*e, videos, reinterpret_cast<const long long*>(tokens), tok_stride_b,
-                        reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask, metrics, 0,
+                        reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask, dropout_seed, metrics, 0,
                         static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_forward_videos(void* h, const float* videos, int train, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
   SVSR_REQUIRE(videos, "lrw_forward_videos: null input");
-  return engine_forward(*e, videos, nullptr, 0, nullptr, nullptr, train, 0, nullptr, 1,
+  return engine_forward(*e, videos, nullptr, 0, nullptr, nullptr, train, 0, 0, nullptr, 1,
                         static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_backward(void* h, const float* grad_scale, void* stream) {

@@ -191,6 +191,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
         tmem_ld_wait();
         const int col0 = nt * BN + ch * 32;
+        if (p.bn_stats) {  // fused BatchNorm statistics of the fp32 accumulators (whole warp participates)
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            a[j] = row_valid ? __uint_as_float(v[j]) : 0.f;
+            b[j] = a[j] * a[j];
+          }
+          warp_transpose_reduce32(a, lane);
+          warp_transpose_reduce32(b, lane);
+          if (col0 + lane < p.n_cols) {
+            atomicAdd(&s_stats[col0 + lane], a[0]);
+            atomicAdd(&s_stats[512 + col0 + lane], b[0]);
+          }
+        }
         if (!row_valid || col0 >= p.n_cols) continue;
         float f[32];
   #pragma unroll

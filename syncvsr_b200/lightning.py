@@ -28,7 +28,7 @@ class LrwConfig(C.Structure):
         ("audio_alignment", C.c_int), ("vq_groups", C.c_int), ("audio_vocab", C.c_int),
         ("num_labels", C.c_int), ("rotary_v", C.c_int),
         ("lambda_audio", C.c_float), ("label_smoothing", C.c_float),
-        ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("ff_dropout", C.c_float),
     ]
 
 
@@ -96,7 +96,8 @@ class TransformerLightningModule(nn.Module):
         self.depth = int(_cfg_get(config, "model.bert.depth", 12))
         self.heads = int(_cfg_get(config, "model.bert.heads", 8))
         self.layer_dropout = float(_cfg_get(config, "model.bert.layer_dropout", 0.0))
-        for key in ("emb_dropout", "attn_dropout", "ff_dropout"):
+        self.ff_dropout = float(_cfg_get(config, "model.bert.ff_dropout", 0.0))
+        for key in ("emb_dropout", "attn_dropout"):
             if float(_cfg_get(config, f"model.bert.{key}", 0.0)) != 0.0:
                 # element-wise dropouts are not wired into the native kernels yet; refuse silently-different maths
                 raise SvsrError(f"model.bert.{key} > 0 is not supported by the native path yet (set it to 0)")
@@ -129,7 +130,7 @@ class TransformerLightningModule(nn.Module):
     def _engine_cfg(self, B, T, H, W) -> LrwConfig:
         return LrwConfig(B, T, H, W, self.dim, self.depth, self.heads, self.audio_alignment, self.vq_groups,
                          self.audio_vocab_size, self.word_labels, int(self.rotary_v), self.lambda_audio,
-                         self.label_smoothing, 1e-5, 0.1)
+                         self.label_smoothing, 1e-5, 0.1, self.ff_dropout)
 
     def _build_engine(self, B, T, H, W, first=False):
         L = lib()
@@ -313,6 +314,7 @@ class TransformerLightningModule(nn.Module):
             self._h, C.c_void_p(videos.data_ptr()), C.c_void_p(audio_tokens.data_ptr()),
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
             C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_int(int(self.training)), C.c_uint32(skip),
+            C.c_uint64(random.getrandbits(63) if (self.training and self.ff_dropout > 0) else 0),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         if self.training:
             self._nbt += 1

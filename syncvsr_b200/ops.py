@@ -239,17 +239,18 @@ def attention_bwd(qkv, rot, d_o, B, n, heads, rotary_v=True):
     return dqkv
 
 
-def geglu_fwd(h):
+def geglu_fwd(h, p_drop=0.0, seed=0):
     M, F2 = h.shape
     u = torch.empty(M, F2 // 2, device=h.device, dtype=torch.bfloat16)
-    check(lib().svsr_geglu_fwd(ptr(h), ptr(u), _i(M), _i(F2 // 2), stream_ptr()), "svsr_geglu_fwd")
+    check(lib().svsr_geglu_fwd(ptr(h), ptr(u), _i(M), _i(F2 // 2), C.c_float(p_drop), C.c_uint64(seed), stream_ptr()),
+          "svsr_geglu_fwd")
     return u
 
 
-def geglu_bwd(h, du):
+def geglu_bwd(h, du, p_drop=0.0, seed=0):
     dh = torch.empty_like(h)
-    check(lib().svsr_geglu_bwd(ptr(h), ptr(du), ptr(dh), _i(h.shape[0]), _i(h.shape[1] // 2), stream_ptr()),
-          "svsr_geglu_bwd")
+    check(lib().svsr_geglu_bwd(ptr(h), ptr(du), ptr(dh), _i(h.shape[0]), _i(h.shape[1] // 2), C.c_float(p_drop),
+                               C.c_uint64(seed), stream_ptr()), "svsr_geglu_bwd")
     return dh
 
 
@@ -291,3 +292,18 @@ def conv2d_fprop_generic(x: torch.Tensor, w_packed: torch.Tensor, taps, out_dtyp
     check(lib().svsr_conv_taps_fprop(ptr(x), ptr(w_packed), ptr(y), _i(N), _i(H), _i(W), _i(Cin), _i(Cout), _i(n), dh,
                                      dw, _i(out_dtype == torch.float32), stream_ptr()), "svsr_conv_taps_fprop")
     return y
+
+
+def conv2d_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, R: int, S: int, stride: int, pad: int):
+    """conv fprop + fused per-channel (sum, sum of squares) of the output; returns (y bf16, stats fp64 [2, Cout])."""
+    _req(x, torch.bfloat16, "x"), _req(w_packed, torch.bfloat16, "w_packed")
+    N, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    OH = (H + 2 * pad - R) // stride + 1
+    OW = (W + 2 * pad - S) // stride + 1
+    y = torch.empty(N, OH, OW, Cout, device=x.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2, Cout, device=x.device, dtype=torch.float64)
+    check(lib().svsr_conv2d_fprop_bnstats(ptr(x), ptr(w_packed), ptr(y), ptr(stats), _i(N), _i(H), _i(W), _i(Cin),
+                                          _i(Cout), _i(R), _i(S), _i(stride), _i(pad), stream_ptr()),
+          "svsr_conv2d_fprop_bnstats")
+    return y, stats

@@ -19,7 +19,7 @@ def _engine(B=2, depth=12, A=4, V=320):
     for f in ("svsr_lrw_param_count", "svsr_lrw_buffer_count", "svsr_lrw_workspace_bytes", "svsr_lrw_decay_count"):
         getattr(L, f).restype = C.c_int64
     h = C.c_void_p()
-    cfg = LrwConfig(B, 29, 88, 88, 512, depth, 8, A, 2, V, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    cfg = LrwConfig(B, 29, 88, 88, 512, depth, 8, A, 2, V, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)
     _lib.check(L.svsr_lrw_create(C.byref(cfg), C.byref(h)), "create")
     return L, h
 
@@ -61,10 +61,10 @@ def test_arena_layout_matches_reference_state_dict_and_decay_rule():
 def test_engine_rejects_unsupported_configs():
     L = _lib.lib()
     h = C.c_void_p()
-    bad = LrwConfig(2, 29, 88, 88, 513, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    bad = LrwConfig(2, 29, 88, 88, 513, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)
     assert L.svsr_lrw_create(C.byref(bad), C.byref(h)) == -1
     assert b"dim" in L.svsr_last_error()
-    too_long = LrwConfig(2, 80, 88, 88, 512, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1)
+    too_long = LrwConfig(2, 80, 88, 88, 512, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)
     assert L.svsr_lrw_create(C.byref(too_long), C.byref(h)) == -1
 
 

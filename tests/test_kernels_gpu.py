@@ -71,6 +71,19 @@ def test_conv_fprop_dgrad_wgrad(ops, N, H, W, Cin, Cout, R, stride, pad):
     assert rel(dw, gw) < F32_TOL
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,pad", [(40, 22, 22, 64, 64, 3, 1, 1), (33, 11, 11, 128, 128, 3, 1, 1),
+                                                          (35, 22, 22, 64, 128, 3, 2, 1), (50, 6, 6, 256, 512, 1, 2, 0),
+                                                          (700, 3, 3, 512, 512, 3, 1, 1)])
+def test_conv_fused_batchnorm_statistics(ops, N, H, W, Cin, Cout, R, stride, pad):
+    x = randn(N, H, W, Cin, seed=14)
+    w = randn(Cout, Cin, R, R, seed=15, scale=0.05)
+    y, stats = ops.conv2d_fprop_bnstats(x, ops.pack_conv_weight(w), R, R, stride, pad)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=stride, padding=pad)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < BF16_TOL
+    assert rel(stats[0], ref.sum((0, 2, 3)).double()) < 1e-4
+    assert rel(stats[1], (ref.double() ** 2).sum((0, 2, 3))) < 1e-4
+
+
 def test_conv_dgrad_accumulates_residual_in_place(ops):
     dy, w = randn(4, 11, 11, 128, seed=7), randn(128, 64, 3, 3, seed=8, scale=0.05)
     base = randn(4, 22, 22, 64, seed=9)
@@ -221,6 +234,26 @@ def test_geglu(ops):
     du = randn(500, 2048, seed=71)
     (gh,) = torch.autograd.grad(ref, hr, du.float())
     assert rel(ops.geglu_bwd(h, du), gh) < BF16_TOL
+
+
+def test_geglu_dropout_mask_is_consistent_between_forward_and_backward(ops):
+    """Dropout(ff_dropout) after the GLU (x-transformers FeedForward): kept elements are scaled by 1/(1-p), the
+    backward regenerates the identical mask from (seed, index)."""
+    p, seed = 0.3, 1234567
+    h = randn(640, 4096, seed=72)
+    u0 = ops.geglu_fwd(h).float()
+    u = ops.geglu_fwd(h, p, seed).float()
+    keep = u != 0
+    frac = 1.0 - keep.float().mean().item()
+    assert abs(frac - p) < 5e-3
+    assert rel(u[keep], (u0 / (1 - p))[keep]) < BF16_TOL
+    assert not torch.equal(ops.geglu_fwd(h, p, seed + 1).float() != 0, keep)  # another seed, another mask
+    assert torch.equal(ops.geglu_fwd(h, p, seed).float(), u)  # deterministic
+    du = randn(640, 2048, seed=73)
+    dh = ops.geglu_bwd(h, du, p, seed).float()
+    dh_ref = ops.geglu_bwd(h, (du.float() * keep / (1 - p)).bfloat16()).float()
+    assert rel(dh, dh_ref) < BF16_TOL
+    assert torch.equal(dh[:, :2048][~keep], torch.zeros_like(dh[:, :2048][~keep]))
 
 
 # ---------------------------------------------------------------- loss heads -------------------------------------

@@ -25,10 +25,11 @@ def cosine(a, b):
     return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
 
 
-def make_cfg(depth=12, path="./vq-wav2vec_kmeans.pt", label_smoothing=0.0, layer_dropout=0.0, extra_model=None):
+def make_cfg(depth=12, path="./vq-wav2vec_kmeans.pt", label_smoothing=0.0, layer_dropout=0.0, ff_dropout=0.0,
+             extra_model=None):
     model = {"resnet": "resnet18", "wav2vec": {"path": path},
              "bert": {"type": "x-transformers", "num_tokens": 1, "dim": 512, "depth": depth, "heads": 8,
-                      "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": layer_dropout, "ff_dropout": 0.0,
+                      "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": layer_dropout, "ff_dropout": ff_dropout,
                       "use_rmsnorm": True, "ff_glu": True, "rotary_pos_emb": True, "num_labels": 500}}
     model.update(extra_model or {})
     return AttrDict.wrap({
@@ -153,9 +154,30 @@ def test_layer_dropout_mask_matches_oracle_skip_set(Module):
     m._ensure(v)
     check(lib().svsr_lrw_forward(m._h, C.c_void_p(v.data_ptr()), C.c_void_p(t.data_ptr()), C.c_int64(t.stride(0)),
                                  C.c_void_p(l.data_ptr()), C.c_void_p(0), C.c_int(1), C.c_uint32(0b0110),
-                                 C.c_void_p(m._metrics.data_ptr()), m._stream()), "fwd")
+                                 C.c_uint64(0), C.c_void_p(m._metrics.data_ptr()), m._stream()), "fwd")
     o = O.lrw_forward(P, videos, tokens, labels, wm, depth=2, q=O.bf16_ste, skip={1, 2})
     assert float(m._metrics[0]) == pytest.approx(float(o["loss_total"]), rel=1e-3)
+
+
+def test_reference_training_config_dropouts(Module):
+    """The shipped yaml trains with layer_dropout=0.2 and ff_dropout=0.3 (config/bert-12l-512d_...yaml:27-28):
+    stochastic, so checked statistically -- eval mode is unaffected, train-mode loss stays near the no-dropout loss."""
+    meta = dict(B=2, S=88, A=4, G=2, V=320, depth=4, seed_p=9, seed_x=82, extra_tokens=0)
+    m, P, (videos, tokens, labels, wm) = _native(Module, meta, layer_dropout=0.2, ff_dropout=0.3)
+    v, t, l, w = videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda()
+    base = float(O.lrw_forward(P, videos, tokens, labels, wm, depth=4)["loss_total"])
+    losses = []
+    for _ in range(6):
+        out = m(v, t, l, w)
+        out["loss_total"].backward()
+        losses.append(float(out["loss_total"]))
+        assert torch.isfinite(m.flat_grads).all()
+    assert len(set(losses)) > 1  # stochastic
+    assert all(abs(x - base) / base < 0.15 for x in losses)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = float(m(v, t, l, w)["loss_total"]), float(m(v, t, l, w)["loss_total"])
+    assert e1 == e2
 
 
 def test_forward_videos_and_state_dict_roundtrip(Module):
