@@ -130,15 +130,37 @@ __device__ __forceinline__ void load_rot(const __nv_bfloat16* __restrict__ src, 
   }
 }
 
-__device__ __forceinline__ void scores_softmax(const float* sq, const float* sk, float* sp, int n, float scale) {
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-    const int r = i / n, c = i - r * n;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < AT_D; ++d) acc += sq[r * AT_LD + d] * sk[c * AT_LD + d];
-    sp[r * AT_LD + c] = acc * scale;
+// out[r][c] = scale * sum_d A[r][d] * B[c][d]  (both [n x 64] in smem): register tile of 2 rows x 4 columns per thread,
+// 8 FMAs per 6 shared loads, bank-conflict free with the 65-float pitch.
+__device__ __forceinline__ void mm_abt(const float* sa, const float* sb, float* out, int n, float scale) {
+  const int nrp = (n + 1) >> 1, ncq = (n + 3) >> 2;
+  for (int t = threadIdx.x; t < nrp * ncq; t += blockDim.x) {
+    const int rp = t / ncq, cq = t - rp * ncq;
+    const int r0 = 2 * rp, r1 = min(r0 + 1, n - 1);
+    int c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = min(4 * cq + j, n - 1);
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 8
+    for (int d = 0; d < AT_D; ++d) {
+      const float a0 = sa[r0 * AT_LD + d], a1 = sa[r1 * AT_LD + d];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b = sb[c[j] * AT_LD + d];
+        acc[0][j] += a0 * b;
+        acc[1][j] += a1 * b;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * cq + j < n) {
+        out[r0 * AT_LD + 4 * cq + j] = acc[0][j] * scale;
+        if (r0 + 1 < n) out[(r0 + 1) * AT_LD + 4 * cq + j] = acc[1][j] * scale;
+      }
   }
-  __syncthreads();
+}
+
+__device__ __forceinline__ void softmax_rows(float* sp, int n) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int r = warp; r < n; r += nw) {
     const float a = lane < n ? sp[r * AT_LD + lane] : -INFINITY;
@@ -149,7 +171,27 @@ __device__ __forceinline__ void scores_softmax(const float* sq, const float* sk,
     if (lane < n) sp[r * AT_LD + lane] = ea * inv;
     if (lane + 32 < n) sp[r * AT_LD + lane + 32] = eb * inv;
   }
-  __syncthreads();
+}
+
+// acc[i][k] = sum_j L(r_i, j) * R[j][cq + 8k]; L(r, j) = Lm[r][j] or, transposed, Lm[j][r]. 2 rows x 8 strided columns
+// per thread (16 FMAs per 10 shared loads); the column stride of 8 keeps a rotary pair (f, f+16) in one thread.
+template <bool TRANS>
+__device__ __forceinline__ void mm_tile_2x8(const float* Lm, const float* R, int n, int r0, int r1, int cq,
+                                            float (&acc)[2][8]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float p0 = TRANS ? Lm[j * AT_LD + r0] : Lm[r0 * AT_LD + j];
+    const float p1 = TRANS ? Lm[j * AT_LD + r1] : Lm[r1 * AT_LD + j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = R[j * AT_LD + cq + 8 * k];
+      acc[0][k] += p0 * v;
+      acc[1][k] += p1 * v;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(128)
@@ -166,17 +208,23 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   load_rot(base, ld, rot, sq, n, true);
   load_rot(base + inner, ld, rot, sk, n, true);
   load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
-  scores_softmax(sq, sk, sp, n, 0.125f);
-  for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
-    const int r = i >> 5, d2 = (i & 31) * 2;
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < n; ++j) {
-      const float p = sp[r * AT_LD + j];
-      a0 += p * sv[j * AT_LD + d2];
-      a1 += p * sv[j * AT_LD + d2 + 1];
+  mm_abt(sq, sk, sp, n, 0.125f);
+  __syncthreads();
+  softmax_rows(sp, n);
+  __syncthreads();
+  const int nrp = (n + 1) >> 1;
+  for (int t = threadIdx.x; t < nrp * 8; t += blockDim.x) {
+    const int rp = t >> 3, cq = t & 7;
+    const int r0 = 2 * rp, r1 = min(r0 + 1, n - 1);
+    float acc[2][8];
+    mm_tile_2x8<false>(sp, sv, n, r0, r1, cq, acc);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (r0 + i >= n) continue;
+      __nv_bfloat16* dst = o + ((long long)b * n + r0 + i) * inner + h * AT_D + cq;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[8 * k] = __float2bfloat16(acc[i][k]);
     }
-    *reinterpret_cast<__nv_bfloat162*>(o + ((long long)b * n + r) * inner + h * AT_D + d2) =
-        __floats2bfloat162_rn(a0, a1);
   }
 }
 
@@ -198,17 +246,12 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   load_rot(base + inner, ld, rot, sk, n, true);
   load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
   load_rot(d_o + (long long)b * n * inner + h * AT_D, inner, rot, sdo, n, false);
-  scores_softmax(sq, sk, sp, n, 0.125f);
-  // dP = dO V^T ; dS = P o (dP - rowsum(dP o P))
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-    const int r = i / n, c = i - r * n;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < AT_D; ++d) acc += sdo[r * AT_LD + d] * sv[c * AT_LD + d];
-    sds[r * AT_LD + c] = acc;
-  }
+  mm_abt(sq, sk, sp, n, 0.125f);  // S
+  mm_abt(sdo, sv, sds, n, 1.0f);  // dP = dO V'^T
   __syncthreads();
-  {
+  softmax_rows(sp, n);
+  __syncthreads();
+  {  // dS = P o (dP - rowsum(dP o P))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int r = warp; r < n; r += nw) {
       const float pa = lane < n ? sp[r * AT_LD + lane] : 0.f, pb = lane + 32 < n ? sp[r * AT_LD + lane + 32] : 0.f;
@@ -219,37 +262,43 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
     }
   }
   __syncthreads();
-  // gradients in the rotated frame, then rotate back (transpose of the rotation) and store
+  // dQ' = scale dS K', dK' = scale dS^T Q', dV' = P^T dO; rotate back (transpose of the rotation) and store
   __nv_bfloat16* obase = dqkv + (long long)b * n * ld + h * AT_D;
-  for (int i = threadIdx.x; i < n * 16 * 3; i += blockDim.x) {
-    const int which = i / (n * 16);  // 0 = q, 1 = k, 2 = v
-    const int rem = i - which * n * 16;
-    const int r = rem >> 4, f = rem & 15;
-    // this thread produces dims {f, f+16, f+32, f+48} of row r
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < n; ++j) {
-      float w;
-      const float* src;
-      if (which == 0) {
-        w = sds[r * AT_LD + j] * 0.125f, src = sk + j * AT_LD;  // dQ' = scale * dS K'
-      } else if (which == 1) {
-        w = sds[j * AT_LD + r] * 0.125f, src = sq + j * AT_LD;  // dK' = scale * dS^T Q'
-      } else {
-        w = sp[j * AT_LD + r], src = sdo + j * AT_LD;  // dV' = P^T dO
+  const int nrp = (n + 1) >> 1;
+  for (int t = threadIdx.x; t < nrp * 8 * 3; t += blockDim.x) {
+    const int which = t / (nrp * 8);  // 0 = q, 1 = k, 2 = v
+    const int rem = t - which * nrp * 8;
+    const int rp = rem >> 3, cq = rem & 7;
+    const int r0 = 2 * rp, r1 = min(r0 + 1, n - 1);
+    float acc[2][8];
+    if (which == 0)
+      mm_tile_2x8<false>(sds, sk, n, r0, r1, cq, acc);
+    else if (which == 1)
+      mm_tile_2x8<true>(sds, sq, n, r0, r1, cq, acc);
+    else
+      mm_tile_2x8<true>(sp, sdo, n, r0, r1, cq, acc);
+    const float sc = which < 2 ? 0.125f : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + i;
+      if (r >= n) continue;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = acc[i][k] * sc;
+      if (which < 2 || rotary_v) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // columns f = cq + 8k (< 16) pair with f + 16 = cq + 8(k+2)
+          const int f = cq + 8 * k;
+          const float c = rot[r * 32 + f], s_ = rot[r * 32 + 16 + f];
+          const float a = v[k], bb = v[k + 2];
+          v[k] = a * c + bb * s_;
+          v[k + 2] = -a * s_ + bb * c;
+        }
       }
-      acc[0] += w * src[f], acc[1] += w * src[f + 16], acc[2] += w * src[f + 32], acc[3] += w * src[f + 48];
+      __nv_bfloat16* dst = obase + which * inner + (long long)r * ld + cq;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[8 * k] = __float2bfloat16(v[k]);
     }
-    if (which < 2 || rotary_v) {
-      const float c = rot[r * 32 + f], s = rot[r * 32 + 16 + f];
-      const float a = acc[0], bb = acc[1];
-      acc[0] = a * c + bb * s;
-      acc[1] = -a * s + bb * c;
-    }
-    __nv_bfloat16* dst = obase + which * inner + (long long)r * ld;
-    dst[f] = __float2bfloat16(acc[0]);
-    dst[f + 16] = __float2bfloat16(acc[1]);
-    dst[f + 32] = __float2bfloat16(acc[2]);
-    dst[f + 48] = __float2bfloat16(acc[3]);
   }
 }
 

@@ -36,8 +36,8 @@ struct IgemmSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STATS_OFFSET = BAR_OFFSET + 256;  // fp32 [2][512] per-CTA BatchNorm partial sums
-  static constexpr int TOTAL = STATS_OFFSET + 4096 + 1024;  // + alignment slack
+  static constexpr int STATS_OFFSET = BAR_OFFSET + 256;  // fp32 [4 warps][2][512] per-CTA BatchNorm partial sums
+  static constexpr int TOTAL = STATS_OFFSET + 4 * 4096 + 1024;  // + alignment slack
   static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block too small");
 };
 
@@ -69,7 +69,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [2][512]
+  float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [4][2][512], one slice per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,7 +93,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   if (p.bn_stats)
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_stats[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -200,9 +200,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           warp_transpose_reduce32(a, lane);
           warp_transpose_reduce32(b, lane);
-          if (col0 + lane < p.n_cols) {
-            atomicAdd(&s_stats[col0 + lane], a[0]);
-            atomicAdd(&s_stats[512 + col0 + lane], b[0]);
+          if (col0 + lane < p.n_cols) {  // private slice per warp, fixed order: run-to-run deterministic
+            s_stats[q * 1024 + col0 + lane] += a[0];
+            s_stats[q * 1024 + 512 + col0 + lane] += b[0];
           }
         }
         if (!row_valid || col0 >= p.n_cols) continue;
@@ -278,8 +278,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       const int t = threadIdx.x - 64;
       for (int cidx = t; cidx < p.n_cols; cidx += 128) {
-        atomicAdd(p.bn_stats + cidx, (double)s_stats[cidx]);
-        atomicAdd(p.bn_stats + p.n_cols + cidx, (double)s_stats[512 + cidx]);
+        const double su = (double)s_stats[cidx] + (double)s_stats[1024 + cidx] + (double)s_stats[2048 + cidx] +
+                          (double)s_stats[3072 + cidx];
+        const double sq2 = (double)s_stats[512 + cidx] + (double)s_stats[1536 + cidx] + (double)s_stats[2560 + cidx] +
+                           (double)s_stats[3584 + cidx];
+        atomicAdd(p.bn_stats + cidx, su);
+        atomicAdd(p.bn_stats + p.n_cols + cidx, sq2);
       }
     }
   }
