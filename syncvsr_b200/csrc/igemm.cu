@@ -28,6 +28,7 @@ struct IgemmKParams {
   int n_cols;
   float alpha;
   double* bn_stats;
+  int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
 };
 
 template <int BN, int STAGES>
@@ -36,8 +37,11 @@ struct IgemmSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STATS_OFFSET = BAR_OFFSET + 256;  // fp32 [4 warps][2][512] per-CTA BatchNorm partial sums
+  static constexpr int STAGING_OFFSET = BAR_OFFSET;  // 2 x [128 rows x 128 B] epilogue staging tiles (1024-aligned)
+  static constexpr int BAR_OFFSET2 = STAGING_OFFSET + 2 * 16384;
+  static constexpr int STATS_OFFSET = BAR_OFFSET2 + 256;  // fp32 [4 warps][2][512] per-CTA BatchNorm partial sums
   static constexpr int TOTAL = STATS_OFFSET + 4 * 4096 + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
   static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block too small");
 };
 
@@ -58,13 +62,15 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmKParams p) {
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const IgemmKParams p) {
   // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
   // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
   using L = IgemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET2);
+  uint8_t* s_stage = smem + L::STAGING_OFFSET;
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
@@ -81,6 +87,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -171,12 +178,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int dh = rem / p.bw;
     const int dw = rem - dh * p.bw;
     int j = 0;
+    int gcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
-      const int n = tn * p.bn + dn, oh = th * p.bh + dh, ow = tw * p.bw + dw;
+      const int n0 = tn * p.bn, oh0 = th * p.bh, ow0 = tw * p.bw;
+      const int n = n0 + dn, oh = oh0 + dh, ow = ow0 + dw;
       const bool row_valid = (r < p.bn * hw) && (n < p.o_N) && (oh < p.OH) && (ow < p.OW);
       const long long pix =
           ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
@@ -205,7 +214,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             s_stats[q * 1024 + 512 + col0 + lane] += b[0];
           }
         }
-        if (!row_valid || col0 >= p.n_cols) continue;
+        if (!p.tma_store && (!row_valid || col0 >= p.n_cols)) continue;
         float f[32];
   #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
@@ -215,7 +224,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (col0 + j < p.n_cols) f[j] += __ldg(p.bias + col0 + j);
         }
         const bool full_chunk = (col0 + 32 <= p.n_cols);
-        if (p.resid) {
+        if (p.resid && row_valid) {
           if (p.resid_fp32) {
             const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
             if (full_chunk) {
@@ -251,10 +260,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else {
             for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = f[j];
           }
+        } else if (p.tma_store) {
+          // stage 64 output channels (two 32-column chunks) per pixel row in a SWIZZLE_128B tile, then one TMA store
+          const int grp = gcount + (ch >> 1);  // running 64-column group index of this CTA (selects the buffer)
+          uint8_t* stg = s_stage + (grp & 1) * 16384;
+          if ((ch & 1) == 0) {
+            if (threadIdx.x == 64) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 t;
+            t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            const int chunk = ((ch & 1) * 4 + j) ^ (r & 7);  // 16-byte chunk position after the 128B swizzle
+            *reinterpret_cast<uint4*>(stg + r * 128 + chunk * 16) = t;
+          }
+          if ((ch & 1) == 1) {
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+              tma_store_4d(&tmC, stg, p.c_off + nt * BN + (ch >> 1) * 64, ow0 * p.o_sw + p.o_ow, oh0 * p.o_sh + p.o_oh,
+                           n0);
+              tma_store_commit();
+            }
+          }
         } else {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
           if (full_chunk) {
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 t;
               t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
@@ -267,13 +303,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = __float2bfloat16(f[j]);
           }
         }
-
       }
+      gcount += BN / 64;
       // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
     if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       const int t = threadIdx.x - 64;
@@ -315,8 +352,8 @@ void igemm_choose_box(int o_N, int OH, int OW, int* pbn, int* pbh, int* pbw) {
 }
 
 template <int BN, int STAGES>
-static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmKParams& kp, dim3 grid,
-                    cudaStream_t stream) {
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
+                    dim3 grid, cudaStream_t stream) {
   using L = IgemmSmem<BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -324,7 +361,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmK
                                          L::TOTAL));
     attr_done = true;
   }
-  igemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, kp);
+  igemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
@@ -391,14 +428,26 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.n_tiles = (p.b_rows + BN - 1) / BN;
   const long long total_tiles = m_tiles * kp.n_tiles;
   dim3 grid((unsigned)(total_tiles < 148 ? total_tiles : 148));
+  // bf16 outputs whose channel count is a multiple of 64 leave through TMA tensor stores (the map mirrors the output
+  // geometry: pitch ldc, pixel strides o_s*, so hardware clips pixels outside the tensor)
+  CUtensorMap tmC = tmA;
+  kp.tma_store = (!p.out_fp32 && p.b_rows % 64 == 0) ? 1 : 0;
+  if (kp.tma_store) {
+    uint64_t dims[4] = {(uint64_t)p.ldc, (uint64_t)p.o_W, (uint64_t)p.o_H, (uint64_t)p.o_N};
+    uint64_t strides[3] = {(uint64_t)p.ldc * 2, (uint64_t)p.o_W * p.ldc * 2, (uint64_t)p.o_H * p.o_W * p.ldc * 2};
+    uint32_t box[4] = {64, (uint32_t)((kp.bw - 1) * p.o_sw + 1), (uint32_t)((kp.bh - 1) * p.o_sh + 1), (uint32_t)kp.bn};
+    uint32_t es[4] = {1, (uint32_t)p.o_sw, (uint32_t)p.o_sh, 1};
+    int rc2 = make_tmap_bf16(&tmC, p.out, 4, dims, strides, box, es, true);
+    if (rc2) return rc2;
+  }
   const double flops = p.algo_flops > 0 ? p.algo_flops
                                         : 2.0 * p.o_N * p.OH * p.OW * (double)p.b_rows * p.ntaps * p.cin;
   prof_begin(PROF_IGEMM, flops, stream);
   int rc;
   switch (BN) {
-    case 64: rc = launch_t<64, 8>(tmA, tmB, kp, grid, stream); break;
-    case 128: rc = launch_t<128, 6>(tmA, tmB, kp, grid, stream); break;
-    default: rc = launch_t<256, 4>(tmA, tmB, kp, grid, stream); break;
+    case 64: rc = launch_t<64, 7>(tmA, tmB, tmC, kp, grid, stream); break;
+    case 128: rc = launch_t<128, 5>(tmA, tmB, tmC, kp, grid, stream); break;
+    default: rc = launch_t<256, 3>(tmA, tmB, tmC, kp, grid, stream); break;
   }
   prof_end(stream);
   return rc;
