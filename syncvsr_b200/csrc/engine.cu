@@ -13,6 +13,7 @@
 #include "encoder.cuh"
 #include "heads.cuh"
 #include "igemm.cuh"
+#include "precise.cuh"
 #include "wgrad.cuh"
 
 namespace svsr {
@@ -110,6 +111,8 @@ struct LrwEngine {
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int fork_idx = 0;
+  // parity-mode (fp32 activations, split-bf16 operands) scratch layout: offsets into a caller-provided buffer
+  size_t p_patches, p_y0, p_act[6], p_s3, p_w3, p_xs[2], p_xn, p_qkv, p_o, p_h, p_u, p_lc, p_lf, p_bytes = 0;
   // forward inputs remembered for backward
   uint32_t last_skip = 0;
   unsigned long long last_seed = 0;
@@ -320,6 +323,30 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.stem_dz = b.take(n0 * 2);
   e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
   e.ws_bytes = b.off;
+  {  // parity-mode scratch (only allocated by the caller when forward_precise is used)
+    Bump pb;
+    const size_t AGVp = (size_t)AGV;
+    e.p_patches = pb.take(n0 * 4);
+    e.p_y0 = pb.take(n0 * 4);
+    for (int i = 0; i < 6; ++i) e.p_act[i] = pb.take(n1 * 4);
+    size_t s3 = n0 * 3 * 2;                                   // stem patches, 192 channels
+    if ((size_t)e.M * 3 * F * 2 > s3) s3 = (size_t)e.M * 3 * F * 2;
+    if ((size_t)e.N * 3 * D * 2 > s3) s3 = (size_t)e.N * 3 * D * 2;
+    e.p_s3 = pb.take(s3);
+    size_t w3 = (size_t)512 * 9 * 1536 * 2;
+    if ((size_t)2 * F * 3 * D * 2 > w3) w3 = (size_t)2 * F * 3 * D * 2;
+    if (AGVp * 3 * D * 2 > w3) w3 = AGVp * 3 * D * 2;
+    e.p_w3 = pb.take(w3);
+    for (int i = 0; i < 2; ++i) e.p_xs[i] = pb.take((size_t)e.M * D * 4);
+    e.p_xn = pb.take((size_t)e.M * D * 4);
+    e.p_qkv = pb.take((size_t)e.M * 3 * inner * 4);
+    e.p_o = pb.take((size_t)e.M * inner * 4);
+    e.p_h = pb.take((size_t)e.M * 2 * F * 4);
+    e.p_u = pb.take((size_t)e.M * F * 4);
+    e.p_lc = pb.take((size_t)c.B * D * 4);
+    e.p_lf = pb.take((size_t)e.N * D * 4);
+    e.p_bytes = pb.off;
+  }
   e.decay_count = e.pc.decay;
   e.param_count = e.pc.nodecay_base + e.pc.nodecay;
   e.buffer_count = e.bc.nodecay;
@@ -542,6 +569,141 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   e.last_seed = dropout_seed;
   e.last_train = train;
   e.fwd_done = true;
+  return SVSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parity-mode forward (see precise.cuh): fp32 activations, split-bf16 tensor-core operands, forward only.
+// ------------------------------------------------------------------------------------------------
+static int precise_gemm(const LrwEngine& e, uint8_t* PW, const float* x, long long rows, int K, const float* w, int N,
+                        const float* bias, const float* resid, float* out, int ldc, cudaStream_t s) {
+  bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
+  bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
+  RC(split3_f32(x, S3, rows, K, s));
+  RC(pack_linear_weight_split(w, W3, N, K, s));
+  IgemmProblem p;
+  p.a = S3, p.a_N = (int)rows, p.a_C = 3 * K, p.cin = 3 * K, p.ntaps = 1;
+  p.o_N = (int)rows;
+  p.b = W3, p.b_rows = N, p.b_cols = 3 * K;
+  p.out = out, p.out_fp32 = 1, p.ldc = ldc;
+  p.bias = bias, p.resid = resid, p.resid_fp32 = 1;
+  return igemm_launch(p, s);
+}
+static int precise_conv(const LrwEngine& e, uint8_t* PW, const float* x, int Hin, const ConvRef& c, float* y,
+                        double* bn_stats, cudaStream_t s) {
+  bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
+  bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
+  RC(split3_f32(x, S3, (long long)e.N * Hin * Hin, c.cin, s));
+  RC(pack_conv_weight_split(e.P + c.w, W3, c.cout, c.cin, c.R * c.R, s));
+  IgemmProblem p;
+  p.a = S3, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = 3 * c.cin, p.cin = 3 * c.cin, p.stride = c.stride;
+  p.ntaps = c.R * c.R;
+  for (int r = 0; r < c.R; ++r)
+    for (int q = 0; q < c.R; ++q) {
+      const int t = r * c.R + q;
+      p.tap_dh[t] = r - c.pad, p.tap_dw[t] = q - c.pad, p.tap_kbase[t] = t * 3 * c.cin;
+    }
+  const int Ho = conv_out(Hin, c.R, c.stride, c.pad);
+  p.o_N = e.N, p.OH = Ho, p.OW = Ho;
+  p.b = W3, p.b_rows = c.cout, p.b_cols = c.R * c.R * 3 * c.cin;
+  p.out = y, p.out_fp32 = 1, p.ldc = c.cout, p.o_H = Ho, p.o_W = Ho;
+  p.bn_stats = bn_stats;
+  return igemm_launch(p, s);
+}
+static int precise_bn_coef(const LrwEngine& e, long long rows, const BnRef& bn, int train, cudaStream_t s) {
+  // batch statistics were accumulated by the conv epilogue; running buffers are NOT updated in parity mode
+  return bn_finalize(e.ws<double>(bn.stats_f), rows, bn.C, e.P + bn.gamma, e.P + bn.beta, e.cfg.bn_eps,
+                     e.cfg.bn_momentum, e.BUF + bn.rmean, e.BUF + bn.rvar, e.ws<float>(bn.coef), train ? 0 : -1, s);
+}
+
+static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos, const long long* tokens,
+                                  long long tok_stride_b, const long long* labels, const float* soft_labels, int train,
+                                  uint32_t skip_mask, float* metrics, cudaStream_t s) {
+  const svsr_lrw_config& c = e.cfg;
+  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
+  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.stats_arena), 0, e.stats_arena_bytes, s));
+  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));
+  RC(rotary_table(e.ws<float>(e.rot), c.T + 1, s));
+  // ---- stem ----
+  RC(stem_patch_f32(videos, PF(e.p_patches), c.B, c.T, c.H, c.W, s));
+  {
+    bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
+    bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
+    RC(split3_f32(PF(e.p_patches), S3, (long long)e.N * e.H0 * e.H0, 64, s));
+    RC(pack_stem_weight_split(e.P + e.stem_conv.w, W3, s));
+    IgemmProblem p;
+    p.a = S3, p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 192, p.cin = 192;
+    p.ntaps = 5;
+    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0, p.tap_kbase[kt] = kt * 192;
+    p.o_N = c.B, p.OH = c.T, p.OW = e.H0 * e.H0;
+    p.b = W3, p.b_rows = 64, p.b_cols = 960;
+    p.out = PF(e.p_y0), p.out_fp32 = 1, p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
+    p.bn_stats = train ? e.ws<double>(e.stem_bn.stats_f) : nullptr;
+    RC(igemm_launch(p, s));
+  }
+  RC(precise_bn_coef(e, (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
+  float* x = PF(e.p_act[0]);
+  float* nxt = PF(e.p_act[1]);
+  float *C1 = PF(e.p_act[2]), *A1 = PF(e.p_act[3]), *C2 = PF(e.p_act[4]), *CDS = PF(e.p_act[5]);
+  RC(stem_bn_gelu_pool_f32(PF(e.p_y0), e.ws<float>(e.stem_bn.coef), x, e.N, e.H0, e.H0, s));
+  // ---- trunk ----
+  for (auto& blk : e.blocks) {
+    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
+    RC(precise_conv(e, PW, x, blk.Hin, blk.conv1, C1, train ? e.ws<double>(blk.bn1.stats_f) : nullptr, s));
+    RC(precise_bn_coef(e, rows, blk.bn1, train, s));
+    RC(bn_apply_f32(C1, e.ws<float>(blk.bn1.coef), nullptr, nullptr, 1, A1, rows, blk.cout, s));
+    RC(precise_conv(e, PW, A1, blk.Hout, blk.conv2, C2, train ? e.ws<double>(blk.bn2.stats_f) : nullptr, s));
+    RC(precise_bn_coef(e, rows, blk.bn2, train, s));
+    if (blk.ds) {
+      RC(precise_conv(e, PW, x, blk.Hin, blk.convds, CDS, train ? e.ws<double>(blk.bnds.stats_f) : nullptr, s));
+      RC(precise_bn_coef(e, rows, blk.bnds, train, s));
+      RC(bn_apply_f32(C2, e.ws<float>(blk.bn2.coef), CDS, e.ws<float>(blk.bnds.coef), 1, nxt, rows, blk.cout, s));
+    } else {
+      RC(bn_apply_f32(C2, e.ws<float>(blk.bn2.coef), x, nullptr, 1, nxt, rows, blk.cout, s));
+    }
+    float* t = x;
+    x = nxt, nxt = t;
+  }
+  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  float* xa = PF(e.p_xs[0]);
+  float* xb = PF(e.p_xs[1]);
+  RC(meanpool_cls_f32(x, e.P + e.cls_off, xa, c.B, c.T, HW4, D, s));
+  SVSR_CHECK_CUDA(cudaMemcpyAsync(e.xs_buf(0), xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- encoder (sublayer outputs ping-pong between xa and xb) ----
+  for (int i = 0; i < c.depth; ++i) {
+    EncLayerRef& L = e.enc[i];
+    if (!(skip_mask & (1u << (2 * i)))) {
+      RC(rmsnorm_fwd_f32(xa, e.P + L.g_a, PF(e.p_xn), e.M, D, 1e-8f, s));
+      RC(precise_gemm(e, PW, PF(e.p_xn), e.M, D, e.P + L.qkv.w, 3 * inner, nullptr, nullptr, PF(e.p_qkv), 3 * inner, s));
+      RC(attention_fwd_f32(PF(e.p_qkv), e.ws<float>(e.rot), PF(e.p_o), c.B, c.T + 1, c.heads, c.rotary_v, s));
+      RC(precise_gemm(e, PW, PF(e.p_o), e.M, inner, e.P + L.out.w, D, nullptr, xa, xb, D, s));
+      float* t = xa;
+      xa = xb, xb = t;
+    }
+    if (!(skip_mask & (1u << (2 * i + 1)))) {
+      RC(rmsnorm_fwd_f32(xa, e.P + L.g_f, PF(e.p_xn), e.M, D, 1e-8f, s));
+      RC(precise_gemm(e, PW, PF(e.p_xn), e.M, D, e.P + L.ff1.w, 2 * F, e.P + L.ff1.b, nullptr, PF(e.p_h), 2 * F, s));
+      RC(geglu_fwd_f32(PF(e.p_h), PF(e.p_u), e.M, F, s));
+      RC(precise_gemm(e, PW, PF(e.p_u), e.M, F, e.P + L.ff2.w, D, e.P + L.ff2.b, xa, xb, D, s));
+      float* t = xa;
+      xa = xb, xb = t;
+    }
+  }
+  SVSR_CHECK_CUDA(cudaMemcpyAsync(e.xs_buf(2 * c.depth), xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- heads ----
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  RC(split_last_f32(xa, PF(e.p_lc), PF(e.p_lf), c.B, c.T, D, s));
+  RC(precise_gemm(e, PW, PF(e.p_lc), c.B, D, e.P + e.cat.w, c.num_labels, e.P + e.cat.b, nullptr, e.ws<float>(e.logits_c),
+                  e.cat_ld, s));
+  RC(precise_gemm(e, PW, PF(e.p_lf), e.N, D, e.P + e.aud.w, AGV, e.P + e.aud.b, nullptr, e.ws<float>(e.logits_a), AGV, s));
+  const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
+  RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing, nullptr,
+                 e.cat_ld, e.ws<double>(e.acc), 0.f, s));
+  RC(audio_ce(e.ws<float>(e.logits_a), AGV, tokens, tok_stride_b, c.B, c.T, c.audio_alignment, c.vq_groups,
+              c.audio_vocab, nullptr, e.ws<double>(e.acc), e.ws<int>(e.bad_token), 0.f, s));
+  RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s));
+  e.fwd_done = false;  // no backward exists for this mode
   return SVSR_OK;
 }
 
@@ -814,6 +976,21 @@ int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_
   return engine_forward(*e, videos, reinterpret_cast<const long long*>(tokens), tok_stride_b,
                         reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask, dropout_seed, metrics, 0,
                         static_cast<cudaStream_t>(stream));
+}
+int64_t svsr_lrw_precise_workspace_bytes(void* h) { return (int64_t)static_cast<LrwEngine*>(h)->p_bytes; }
+int svsr_lrw_forward_precise(void* h, void* precise_ws, int64_t precise_ws_bytes, const float* videos,
+                             const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
+                             const float* soft_labels, int train, uint32_t skip_mask, float* metrics, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  SVSR_REQUIRE(precise_ws && (size_t)precise_ws_bytes >= e->p_bytes && ((uintptr_t)precise_ws & 1023) == 0,
+               "lrw_forward_precise: scratch missing, too small or not 1024-byte aligned");
+  SVSR_REQUIRE(videos && tokens && metrics, "lrw_forward_precise: null input");
+  SVSR_REQUIRE(tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
+               "lrw_forward_precise: audio_tokens has fewer than T*alignment rows per clip");
+  return engine_forward_precise(*e, static_cast<uint8_t*>(precise_ws), videos, reinterpret_cast<const long long*>(tokens),
+                                tok_stride_b, reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask,
+                                metrics, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_forward_videos(void* h, const float* videos, int train, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);

@@ -1,0 +1,31 @@
+// fp32-class "parity mode" of the forward pass. Activations stay fp32 in HBM; every tensor-core operand is split into
+// two bf16 terms x = hi + lo and the contraction is K-concatenated as [hi | lo | hi] . [hi | hi | lo]^T
+// (= hi*hi + lo*hi + hi*lo, ~16 mantissa bits, fp32 accumulation) so the SAME tcgen05 implicit-GEMM kernel computes it
+// with three times the channels. Element-wise kernels here are the fp32-I/O twins of elementwise.cu / encoder.cu.
+// Forward only: this mode exists to demonstrate north_star's 1e-3 output tolerance, not for throughput.
+#pragma once
+#include "common.cuh"
+
+namespace svsr {
+
+int split3_f32(const float* x, __nv_bfloat16* out, long long rows, int C, cudaStream_t s);  // [rows,3C] = hi|lo|hi
+// conv weight fp32 [Cout,Cin,R,S] -> bf16 [Cout, R*S*3*Cin], per tap [hi(Cin) | hi(Cin) | lo(Cin)]
+int pack_conv_weight_split(const float* w, __nv_bfloat16* out, int Cout, int Cin, int RS, cudaStream_t s);
+// linear weight fp32 [N,K] -> bf16 [N, 3K] = [hi | hi | lo]
+int pack_linear_weight_split(const float* w, __nv_bfloat16* out, int N, int K, cudaStream_t s);
+// stem weight fp32 [64,1,5,7,7] -> bf16 [64, 5*192], per temporal tap [hi(64 slots) | hi | lo], slot = kh*8+kw
+int pack_stem_weight_split(const float* w, __nv_bfloat16* out, cudaStream_t s);
+
+int stem_patch_f32(const float* videos, float* patches, int B, int T, int H, int W, cudaStream_t s);
+int bn_apply_f32(const float* x, const float* coef, const float* res, const float* rcoef, int relu, float* out,
+                 long long rows, int C, cudaStream_t s);
+int stem_bn_gelu_pool_f32(const float* y0, const float* coef, float* out, int N, int IH, int IW, cudaStream_t s);
+int meanpool_cls_f32(const float* a, const float* cls, float* x_stream, int B, int T, int HW, int C, cudaStream_t s);
+int rmsnorm_fwd_f32(const float* x, const float* g, float* y, int M, int D, float eps, cudaStream_t s);
+int attention_fwd_f32(const float* qkv, const float* rot, float* o, int B, int n, int heads, int rotary_v,
+                      cudaStream_t s);
+int geglu_fwd_f32(const float* h, float* u, int M, int F, cudaStream_t s);
+// last [B,T+1,D] -> cls [B,D], frames [B*T,D]
+int split_last_f32(const float* last, float* cls, float* frames, int B, int T, int D, cudaStream_t s);
+
+}  // namespace svsr

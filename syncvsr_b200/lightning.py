@@ -324,6 +324,33 @@ class TransformerLightningModule(nn.Module):
         return {"loss_total": m[0], "loss_category": m[1], "loss_audio": m[2], "accuracy_top1": m[3],
                 "accuracy_top5": m[4]}
 
+    @torch.no_grad()
+    def forward_precise(self, videos: torch.Tensor, audio_tokens: torch.Tensor, labels: torch.Tensor,
+                        word_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Parity-mode forward (fp32 activations, split-bf16 tensor-core operands; csrc/precise.cuh): same outputs as
+        forward() at fp32-class accuracy. Forward only; `last_hidden_state()` / `logits_audio()` read its results."""
+        videos = videos.to(self.device_, torch.float32).contiguous()
+        audio_tokens = audio_tokens.to(self.device_, torch.long).contiguous()
+        labels = labels.to(self.device_)
+        self._ensure(videos)
+        L = lib()
+        L.svsr_lrw_precise_workspace_bytes.restype = C.c_int64
+        need = L.svsr_lrw_precise_workspace_bytes(self._h)
+        if getattr(self, "_pws", None) is None or self._pws.numel() < need + 1024:
+            self._pws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device_)
+        pptr = (self._pws.data_ptr() + 1023) & ~1023
+        hard = labels.long().contiguous() if labels.dtype in (torch.long, torch.int32) else None
+        soft = labels.float().contiguous() if hard is None else None
+        metrics = torch.zeros(8, device=self.device_)
+        check(L.svsr_lrw_forward_precise(
+            self._h, C.c_void_p(pptr), C.c_int64(need), C.c_void_p(videos.data_ptr()),
+            C.c_void_p(audio_tokens.data_ptr()), C.c_int64(audio_tokens.stride(0)),
+            C.c_void_p(hard.data_ptr() if hard is not None else 0), C.c_void_p(soft.data_ptr() if soft is not None else 0),
+            C.c_int(int(self.training)), C.c_uint32(0), C.c_void_p(metrics.data_ptr()), self._stream()),
+            "svsr_lrw_forward_precise")
+        return {"loss_total": metrics[0], "loss_category": metrics[1], "loss_audio": metrics[2],
+                "accuracy_top1": metrics[3], "accuracy_top5": metrics[4]}
+
     def _native_backward(self, grad_metrics: torch.Tensor) -> None:
         """d(loss_total) only: the other returned entries are metrics (the reference logs them, never differentiates
         them separately). Accumulates into the flat gradient arena."""

@@ -97,6 +97,33 @@ def test_forward_matches_reference_golden(Module, name, golden_dir):
         ("resnet.conv1", "resnet.bn1", "resnet.fc")))
 
 
+@pytest.mark.parametrize("name", ["lrw_c1_vq", "lrw_c1_a2", "lrw_96_d2"])
+def test_parity_mode_forward_matches_reference_within_1e3(Module, name, golden_dir):
+    """north_star tolerance: last_hidden_state, logits_audio and loss_total within 1e-3 relative of the fp32 reference.
+    Parity mode = fp32 activations + split-bf16 operands through the SAME tcgen05 kernels (csrc/precise.cuh)."""
+    fx = torch.load(golden_dir / f"{name}.pt")
+    meta = fx["meta"]
+    m, P, (videos, tokens, labels, wm) = _native(Module, meta)
+    out = m.forward_precise(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    g = fx["metrics"]
+    for k in ("loss_total", "loss_category", "loss_audio"):
+        assert float(out[k]) == pytest.approx(g[k], rel=1e-4), k
+    assert float(out["accuracy_top1"]) == g["accuracy_top1"] and float(out["accuracy_top5"]) == g["accuracy_top5"]
+    last = m.last_hidden_state().cpu()
+    assert rel(last[:, 0, :], fx["last_hidden_state_cls"]) < 1e-3
+    assert rel(last[:, 7, :], fx["last_hidden_state_t7"]) < 1e-3
+    assert last.double().abs().sum().item() == pytest.approx(fx["last_hidden_state_abs"], rel=1e-4)
+    la = m.logits_audio().cpu().reshape(meta["B"], 29, -1)
+    assert rel(la[:, 3, :], fx["logits_audio_t3"]) < 1e-3
+    assert la.double().abs().sum().item() == pytest.approx(fx["logits_audio_abs"], rel=1e-3)
+    assert rel(m.logits_category().cpu(), fx["logits_category"]) < 1e-3
+    emb = m._named_tensor("inputs_embeds", (meta["B"], 30, 512))[:, 1:].cpu()
+    assert rel(emb.flatten(0, 1)[:2], fx["inputs_embeds_t0"]) < 1e-3
+    # parity mode must not touch the running BatchNorm buffers
+    assert int(m.state_dict()["stem3d.1.num_batches_tracked"]) == 0
+    assert float(m.state_dict()["stem3d.1.running_var"].mean()) == 1.0
+
+
 def test_forward_backward_vs_oracle_same_storage_points(Module):
     """Oracle run with bf16 rounding at the CUDA path's storage points: tight on scalars, bf16-chaos-limited on deep
     tensors; gradients of the heads/encoder agree to bf16 precision, trunk gradients in direction and norm."""
