@@ -41,10 +41,10 @@ int svsr_batchnorm_bwd(const void* dout, const void* relu_ref, const void* c, in
   SVSR_REQUIRE(dout && c && coef && dc && stats_scratch && kcoef_scratch, "batchnorm_bwd: null pointer");
   SVSR_CHECK_CUDA(cudaMemsetAsync(stats_scratch, 0, 2 * C * sizeof(double), ST(stream)));
   RC(bn_bwd_reduce(static_cast<const bf16*>(dout), static_cast<const bf16*>(relu_ref), static_cast<const bf16*>(c),
-                   coef, rows, C, stats_scratch, ST(stream)));
+                   coef, rows, C, stats_scratch, 0, ST(stream)));
   RC(bn_bwd_finalize(stats_scratch, rows, C, dgamma, dbeta, kcoef_scratch, ST(stream)));
   return bn_bwd_apply(static_cast<const bf16*>(dout), static_cast<const bf16*>(relu_ref), static_cast<const bf16*>(c),
-                      coef, kcoef_scratch, static_cast<bf16*>(dc), static_cast<bf16*>(gmask_out), rows, C, ST(stream));
+                      coef, kcoef_scratch, static_cast<bf16*>(dc), static_cast<bf16*>(gmask_out), rows, C, 0, ST(stream));
 }
 
 int svsr_stem_bn_gelu_pool_fwd(const void* y0, const float* coef, void* out, uint8_t* argmax, int N, int IH, int IW,

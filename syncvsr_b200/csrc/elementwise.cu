@@ -26,9 +26,21 @@ __device__ __forceinline__ F8 ldf8(const float* p) {
   r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
   return r;
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of every tensor these kernels
+// write): 2 MUFU + ~8 FMA instead of libdevice's branchy erff -- the stem's BN+GELU+pool passes are erf-bound otherwise.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  return 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
 inline unsigned grid_for(long long work_items, int per_block, int max_blocks = 148 * 8) {
@@ -164,10 +176,11 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                      const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef, long long rows, int C,
-                     double* stats) {
+                     double* stats, int self_mask) {
   const int cg = C >> 3;
   const int g = threadIdx.x % cg, slot = threadIdx.x / cg, rpb = 256 / cg;
   const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
+  const F8 scl = ldf8(coef + 2 * C + g * 8), shf = ldf8(coef + 3 * C + g * 8);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -180,6 +193,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
     }
     const F8 cv = ld8(c + off);
+    if (self_mask) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gv.v[k] = (cv.v[k] * scl.v[k] + shf.v[k]) > 0.f ? gv.v[k] : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       acc[k] += gv.v[k];
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
                     const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
-                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C) {
+                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C, int self_mask) {
   const int cg = C >> 3;
   const long long total = rows * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -217,9 +234,14 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
 #pragma unroll
       for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
     }
-    if (gmask_out) st8(gmask_out + off, gv);
     const F8 cv = ld8(c + off);
     const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8), sc = ldf8(coef + 2 * C + g * 8);
+    if (self_mask) {
+      const F8 shf = ldf8(coef + 3 * C + g * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gv.v[k] = (cv.v[k] * sc.v[k] + shf.v[k]) > 0.f ? gv.v[k] : 0.f;
+    }
+    if (gmask_out) st8(gmask_out + off, gv);
     const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
     F8 o;
 #pragma unroll
@@ -452,6 +474,43 @@ __global__ void pack_linear_weight_kernel(const float* __restrict__ w, __nv_bflo
     }
   }
 }
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob jb = jobs[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jb.type == 0) {
+    const int Cout = jb.a, Cin = jb.b, RS = jb.c;
+    const long long total = (long long)Cout * Cin * RS;
+    for (long long i = i0; i < total; i += stride) {
+      const int rs = (int)(i % RS);
+      const int ci = (int)((i / RS) % Cin);
+      const int co = (int)(i / ((long long)RS * Cin));
+      const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
+      jb.dst0[(long long)co * RS * Cin + (long long)rs * Cin + ci] = v;
+      if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
+    }
+  } else if (jb.type == 1) {
+    // linear: coalesced read of [N,K]; the transposed copy is written with stride (weights are small, L2 absorbs it)
+    const int N = jb.a, K = jb.b, ldb = jb.c, ldt = jb.d;
+    const long long total = (long long)N * K;
+    for (long long i = i0; i < total; i += stride) {
+      const int k = (int)(i % K);
+      const long long n = i / K;
+      const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
+      jb.dst0[n * ldb + k] = v;
+      if (jb.dst1) jb.dst1[(long long)k * ldt + n] = v;
+    }
+  } else {
+    for (long long i = i0; i < 64 * 320; i += stride) {
+      const int co = (int)(i / 320), k = (int)(i % 320);
+      const int kt = k / 64, kh = (k % 64) / 8, kw = k % 8;
+      float v = 0.f;
+      if (kh < 7 && kw < 7) v = jb.src[((co * 5 + kt) * 7 + kh) * 7 + kw];
+      jb.dst0[i] = __float2bfloat16(v);
+    }
+  }
+}
+
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db, int M,
                                    int N) {
   // block handles 64 columns x a slab of rows; threads: 64 columns x 4 row lanes
@@ -522,10 +581,10 @@ int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res
   return SVSR_OK;
 }
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                  long long rows, int C, double* stats, cudaStream_t s) {
+                  long long rows, int C, double* stats, int self_mask, cudaStream_t s) {
   SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   const int rpb = 256 / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats);
+  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -536,10 +595,10 @@ int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, f
   return SVSR_OK;
 }
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C,
+                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
                  cudaStream_t s) {
   bn_bwd_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out,
-                                                                       rows, C);
+                                                                       rows, C, self_mask);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -596,6 +655,12 @@ int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int
                        cudaStream_t s) {
   dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
   pack_linear_weight_kernel<<<grid, block, 0, s>>>(w, wb, wt, N, K, ldb, ldt);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
+  dim3 grid(64, (unsigned)njobs);
+  pack_all_kernel<<<grid, 256, 0, s>>>(jobs_dev);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

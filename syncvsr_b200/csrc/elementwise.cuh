@@ -19,15 +19,16 @@ int bn_finalize(const double* stats, long long rows, int C, const float* gamma, 
 // out = act(x*scale+shift (+ res*rscale+rshift | + res)); coef/rcoef are the [4][C] blocks of bn_finalize
 int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res, const float* rcoef, int relu,
              __nv_bfloat16* out, long long rows, int C, cudaStream_t s);
+// self_mask = 1: the ReLU that follows this BN is recomputed from c (mask = c*scale+shift > 0), relu_ref unused.
 // backward reductions: g = dout * (ref > 0 if ref) ; stats[0..C) += sum g ; stats[C..2C) += sum g * xhat
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                  long long rows, int C, double* stats, cudaStream_t s);
+                  long long rows, int C, double* stats, int self_mask, cudaStream_t s);
 // dgamma += sum g*xhat ; dbeta += sum g ; kcoef[0..C) = sum g / rows ; kcoef[C..2C) = sum g*xhat / rows
 int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, float* dbeta, float* kcoef,
                     cudaStream_t s);
 // dc = scale * (g - k1 - xhat*k2); optionally also writes g (the relu-masked upstream gradient) to gmask_out
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C,
+                 const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
                  cudaStream_t s);
 
 // stem epilogue: y0 [N,IH,IW,64] -> max_pool3x3s2p1(gelu(bn(y0))) [N,OH,OW,64] + argmax slot (uint8)
@@ -51,6 +52,15 @@ int pack_stem_weight(const float* w, __nv_bfloat16* wp, cudaStream_t s);  // [64
 int unpack_stem_wgrad(const float* d, float* grad, cudaStream_t s);        // [5*64, 64] -> [64,1,5,7,7] (+=)
 int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int N, int K, int ldb, int ldt,
                        cudaStream_t s);
+// All weight packs of a step in ONE launch: a device table of jobs, blockIdx.y selects the job.
+struct PackJob {
+  const float* src;
+  __nv_bfloat16* dst0;  // conv: fprop layout; linear: [N, ldb]; stem: [64, 320]
+  __nv_bfloat16* dst1;  // conv: dgrad layout; linear: transposed [K, ldt] (may be null)
+  int type;             // 0 = conv [Cout,Cin,R,S], 1 = linear [N,K], 2 = stem
+  int a, b, c, d;       // conv: Cout, Cin, RS, -; linear: N, K, ldb, ldt
+};
+int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s);
 // db[N] += column sums of dy[M, N] (bf16, pitch ld)
 int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);

@@ -105,6 +105,9 @@ struct LrwEngine {
   // workspace offsets
   size_t patches, y0, x1, argmax, xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a,
       logits_c, dlogits_c, acc, bad_token, rot, stats_arena, stats_arena_bytes;
+  size_t pack_jobs;  // device table for the single-launch weight repack
+  int n_pack_jobs = 0;
+  bool pack_table_ready = false;
   size_t dx, dxb[3], t_du, t_dh[2], t_dyn, t_do, t_dqkv[2], gbuf[9], stem_dz, wgrad_tmp;
   // weight-gradient side stream (backward): forked from / joined to the caller's stream with events
   cudaStream_t side = nullptr;
@@ -322,6 +325,7 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   for (int i = 0; i < 9; ++i) e.gbuf[i] = b.take(n1 * 2);
   e.stem_dz = b.take(n0 * 2);
   e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
+  e.pack_jobs = b.take(128 * sizeof(PackJob));
   e.ws_bytes = b.off;
   {  // parity-mode scratch (only allocated by the caller when forward_precise is used)
     Bump pb;
@@ -438,38 +442,39 @@ static int bn_fwd(const LrwEngine& e, const bf16* x, long long rows, const BnRef
 }
 // full BN backward: returns dc (may alias nothing); optionally emits the relu-masked upstream gradient
 static int bn_bwd(const LrwEngine& e, const bf16* dout, const bf16* relu_ref, const bf16* c, long long rows,
-                  const BnRef& bn, bf16* dc, bf16* gmask_out, cudaStream_t s) {
-  RC(bn_bwd_reduce(dout, relu_ref, c, e.ws<float>(bn.coef), rows, bn.C, e.ws<double>(bn.stats_b), s));
+                  const BnRef& bn, bf16* dc, bf16* gmask_out, cudaStream_t s, int self_mask = 0) {
+  RC(bn_bwd_reduce(dout, relu_ref, c, e.ws<float>(bn.coef), rows, bn.C, e.ws<double>(bn.stats_b), self_mask, s));
   RC(bn_bwd_finalize(e.ws<double>(bn.stats_b), rows, bn.C, e.G + bn.gamma, e.G + bn.beta, e.ws<float>(bn.kcoef), s));
-  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, gmask_out, rows, bn.C, s);
+  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, gmask_out, rows, bn.C,
+                      self_mask, s);
 }
 
 // ------------------------------------------------------------------------------------------------
 static int engine_pack(LrwEngine& e, cudaStream_t s) {
-  RC(pack_stem_weight(e.P + e.stem_conv.w, e.ws<bf16>(e.stem_conv.wf), s));
-  for (auto& blk : e.blocks) {
-    RC(pack_conv_weight(e.P + blk.conv1.w, e.ws<bf16>(blk.conv1.wf), e.ws<bf16>(blk.conv1.wd), blk.conv1.cout,
-                        blk.conv1.cin, 3, 3, s));
-    RC(pack_conv_weight(e.P + blk.conv2.w, e.ws<bf16>(blk.conv2.wf), e.ws<bf16>(blk.conv2.wd), blk.conv2.cout,
-                        blk.conv2.cin, 3, 3, s));
-    if (blk.ds)
-      RC(pack_conv_weight(e.P + blk.convds.w, e.ws<bf16>(blk.convds.wf), e.ws<bf16>(blk.convds.wd), blk.convds.cout,
-                          blk.convds.cin, 1, 1, s));
+  if (!e.pack_table_ready) {  // build the job table once per binding (pointers are static afterwards)
+    std::vector<PackJob> jobs;
+    jobs.push_back({e.P + e.stem_conv.w, e.ws<bf16>(e.stem_conv.wf), nullptr, 2, 0, 0, 0, 0});
+    auto conv = [&](const ConvRef& c) {
+      jobs.push_back({e.P + c.w, e.ws<bf16>(c.wf), e.ws<bf16>(c.wd), 0, c.cout, c.cin, c.R * c.R, 0});
+    };
+    for (auto& blk : e.blocks) {
+      conv(blk.conv1), conv(blk.conv2);
+      if (blk.ds) conv(blk.convds);
+    }
+    auto lin = [&](const LinRef& l) { jobs.push_back({e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), 1, l.N, l.K, l.K, l.ldt}); };
+    for (auto& L : e.enc) lin(L.qkv), lin(L.out), lin(L.ff1), lin(L.ff2);
+    lin(e.cat), lin(e.aud);
+    SVSR_REQUIRE(jobs.size() <= 128, "lrw: too many pack jobs (%zu)", jobs.size());
+    e.n_pack_jobs = (int)jobs.size();
+    SVSR_CHECK_CUDA(cudaMemcpyAsync(e.ws<PackJob>(e.pack_jobs), jobs.data(), jobs.size() * sizeof(PackJob),
+                                    cudaMemcpyHostToDevice, s));
+    SVSR_CHECK_CUDA(cudaStreamSynchronize(s));  // `jobs` is a stack vector
+    // padding columns of transposed operands (category head: 500 -> 512) stay zero forever
+    if (e.cat.ldt != e.cat.N) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<bf16>(e.cat.wt), 0, (size_t)e.cat.K * e.cat.ldt * 2, s));
+    RC(rotary_table(e.ws<float>(e.rot), e.cfg.T + 1, s));
+    e.pack_table_ready = true;
   }
-  auto pack_lin = [&](const LinRef& l) -> int {
-    if (l.ldt != l.N) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<bf16>(l.wt), 0, (size_t)l.K * l.ldt * 2, s));
-    return pack_linear_weight(e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), l.N, l.K, l.K, l.ldt, s);
-  };
-  for (auto& L : e.enc) {
-    RC(pack_lin(L.qkv));
-    RC(pack_lin(L.out));
-    RC(pack_lin(L.ff1));
-    RC(pack_lin(L.ff2));
-  }
-  RC(pack_lin(e.cat));
-  RC(pack_lin(e.aud));
-  RC(rotary_table(e.ws<float>(e.rot), e.cfg.T + 1, s));
-  return SVSR_OK;
+  return pack_all_weights(e.ws<PackJob>(e.pack_jobs), e.n_pack_jobs, s);
 }
 
 static int engine_forward(LrwEngine& e, const float* videos, const long long* tokens, long long tok_stride_b,
@@ -850,7 +855,8 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
     if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
     RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
-    RC(bn_bwd(e, T0, e.ws<bf16>(blk.a1), e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s));
+    // bn1 is followed directly by ReLU: mask recomputed from c1 (saves reading a1 in both passes)
+    RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, 1));
     RC(sq.fork());  // dc1 complete
     RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
     if (blk.ds) {
@@ -951,6 +957,7 @@ int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* wo
   SVSR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0,
                "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
   e->P = params, e->G = grads, e->BUF = buffers, e->WS = static_cast<uint8_t*>(workspace);
+  e->pack_table_ready = false;
   if (!e->side) {  // first bind happens on the GPU box: create the weight-gradient stream and its events
     SVSR_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) {
