@@ -490,15 +490,27 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
       if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
     }
   } else if (jb.type == 1) {
-    // linear: coalesced read of [N,K]; the transposed copy is written with stride (weights are small, L2 absorbs it)
+    // linear [N,K]: 32x32 tiles through shared memory so that the plain copy AND the transposed copy are both
+    // written with full 64-byte rows (the encoder holds 38 M of the 63 M parameters)
+    __shared__ float tile[32][33];
     const int N = jb.a, K = jb.b, ldb = jb.c, ldt = jb.d;
-    const long long total = (long long)N * K;
-    for (long long i = i0; i < total; i += stride) {
-      const int k = (int)(i % K);
-      const long long n = i / K;
-      const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
-      jb.dst0[n * ldb + k] = v;
-      if (jb.dst1) jb.dst1[(long long)k * ldt + n] = v;
+    const int tk = (K + 31) / 32, tn = (N + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
+      const int k0 = (t % tk) * 32, n0 = (t / tk) * 32;
+      __syncthreads();
+      for (int j = ty; j < 32; j += 8) {
+        const int n = n0 + j, k = k0 + tx;
+        const float v = (n < N && k < K) ? jb.src[(long long)n * K + k] : 0.f;
+        tile[j][tx] = v;
+        if (n < N && k < K) jb.dst0[(long long)n * ldb + k] = __float2bfloat16(v);
+      }
+      __syncthreads();
+      if (jb.dst1)
+        for (int j = ty; j < 32; j += 8) {
+          const int k = k0 + j, n = n0 + tx;
+          if (n < N && k < K) jb.dst1[(long long)k * ldt + n] = __float2bfloat16(tile[tx][j]);
+        }
     }
   } else {
     for (long long i = i0; i < 64 * 320; i += stride) {

@@ -31,11 +31,14 @@ struct IgemmKParams {
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
 };
 
-template <int BN, int STAGES>
+// A pipeline stage holds KPS consecutive 64-wide k-blocks (A sub-tile + B sub-tile each): one mbarrier round trip
+// (~200 cycles of issue-side latency) is then amortised over 4*KPS MMAs, which matters when N is small.
+template <int BN, int STAGES, int KPS>
 struct IgemmSmem {
   static constexpr int A_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16 (one 128B swizzle row each)
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = KPS * SUB_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFFSET = BAR_OFFSET;  // 2 x [128 rows x 128 B] epilogue staging tiles (1024-aligned)
   static constexpr int BAR_OFFSET2 = STAGING_OFFSET + 2 * 16384;
@@ -60,13 +63,13 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KPS>
 __global__ void __launch_bounds__(192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const IgemmKParams p) {
   // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
   // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
-  using L = IgemmSmem<BN, STAGES>;
+  using L = IgemmSmem<BN, STAGES, KPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET2);
@@ -116,16 +119,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int n0 = tn * p.bn, oh0 = th * p.bh, ow0 = tw * p.bw;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
+          const int nk = min(KPS, num_kb - kb0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int tap = kb / p.cblocks;
-          const int cc = kb - tap * p.cblocks;
-          uint8_t* sA = smem + stage * L::STAGE_BYTES;
-          uint8_t* sB = sA + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + L::B_BYTES));
-          tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
-                      oh0 * p.stride + p.tap_dh[tap], n0);
-          tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(nk * (p.a_box_bytes + L::B_BYTES)));
+          for (int u = 0; u < nk; ++u) {
+            const int kb = kb0 + u;
+            const int tap = kb / p.cblocks;
+            const int cc = kb - tap * p.cblocks;
+            uint8_t* sA = smem + stage * L::STAGE_BYTES + u * L::SUB_BYTES;
+            uint8_t* sB = sA + L::A_BYTES;
+            tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
+                        oh0 * p.stride + p.tap_dh[tap], n0);
+            tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -146,17 +153,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
+          const int nk = min(KPS, num_kb - kb0);
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
-          const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = umma_smem_desc_sw128(b_addr, 16, 1024);
+          for (int u = 0; u < nk; ++u) {
+            const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES + u * L::SUB_BYTES);
+            const uint32_t b_addr = a_addr + L::A_BYTES;
+            const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t b_desc = umma_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb0 | u | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           if (++stage == STAGES) {
@@ -351,17 +361,17 @@ void igemm_choose_box(int o_N, int OH, int OW, int* pbn, int* pbh, int* pbw) {
   *pbn = best[0], *pbh = best[1], *pbw = best[2];
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KPS>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
                     dim3 grid, cudaStream_t stream) {
-  using L = IgemmSmem<BN, STAGES>;
+  using L = IgemmSmem<BN, STAGES, KPS>;
   static bool attr_done = false;
   if (!attr_done) {
-    SVSR_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL));
     attr_done = true;
   }
-  igemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
+  igemm_kernel<BN, STAGES, KPS><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
@@ -445,9 +455,9 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   prof_begin(PROF_IGEMM, flops, stream);
   int rc;
   switch (BN) {
-    case 64: rc = launch_t<64, 7>(tmA, tmB, tmC, kp, grid, stream); break;
-    case 128: rc = launch_t<128, 5>(tmA, tmB, tmC, kp, grid, stream); break;
-    default: rc = launch_t<256, 3>(tmA, tmB, tmC, kp, grid, stream); break;
+    case 64: rc = launch_t<64, 3, 2>(tmA, tmB, tmC, kp, grid, stream); break;    // 3 x 48 KB
+    case 128: rc = launch_t<128, 2, 2>(tmA, tmB, tmC, kp, grid, stream); break;  // 2 x 64 KB
+    default: rc = launch_t<256, 3, 1>(tmA, tmB, tmC, kp, grid, stream); break;   // 3 x 48 KB
   }
   prof_end(stream);
   return rc;
