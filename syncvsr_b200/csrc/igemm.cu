@@ -43,7 +43,8 @@ struct IgemmSmem {
   static constexpr int STAGING_OFFSET = BAR_OFFSET;  // 2 x [128 rows x 128 B] epilogue staging tiles (1024-aligned)
   static constexpr int BAR_OFFSET2 = STAGING_OFFSET + 2 * 16384;
   static constexpr int STATS_OFFSET = BAR_OFFSET2 + 256;  // fp32 [4 warps][2][512] per-CTA BatchNorm partial sums
-  static constexpr int TOTAL = STATS_OFFSET + 4 * 4096 + 1024;  // + alignment slack
+  static constexpr int VALID_OFFSET = STATS_OFFSET + 4 * 4096;  // 128 row-validity bytes of the current tile
+  static constexpr int TOTAL = VALID_OFFSET + 128 + 1024;  // + alignment slack
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
   static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block too small");
 };
@@ -79,6 +80,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [4][2][512], one slice per epilogue warp
+  uint8_t* s_valid = smem + L::VALID_OFFSET;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,6 +191,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int dw = rem - dh * p.bw;
     int j = 0;
     int gcount = 0;
+    float st_sum[BN / 64], st_sq[BN / 64];  // per-thread BatchNorm partial sums (smem-staged path)
+#pragma unroll
+    for (int g2 = 0; g2 < BN / 64; ++g2) st_sum[g2] = 0.f, st_sq[g2] = 0.f;
+    int stat_nt = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
       const int tw = mt % p.tiles_w;
@@ -201,6 +207,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
       const long long row_off = pix * p.ldc + p.c_off;
       const int acc = j & 1;
+      if (p.bn_stats && p.tma_store) s_valid[r] = row_valid ? 1 : 0;  // read after the group barriers below
       mbar_wait(&tmem_full_bar[acc], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
 
@@ -210,7 +217,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
         tmem_ld_wait();
         const int col0 = nt * BN + ch * 32;
-        if (p.bn_stats) {  // fused BatchNorm statistics of the fp32 accumulators (whole warp participates)
+        if (p.bn_stats && !p.tma_store) {  // register path (fp32 outputs): transposed warp reduction of the chunk
           float a[32], b[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -244,7 +251,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 f[4 * j] += t.x, f[4 * j + 1] += t.y, f[4 * j + 2] += t.z, f[4 * j + 3] += t.w;
               }
             } else {
-              for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += rp[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n_cols) f[j] += rp[j];
             }
           } else {
             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + row_off + col0;
@@ -257,7 +266,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 f[8 * j + 4] += c.x, f[8 * j + 5] += c.y, f[8 * j + 6] += d.x, f[8 * j + 7] += d.y;
               }
             } else {
-              for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) f[j] += __bfloat162float(rp[j]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n_cols) f[j] += __bfloat162float(rp[j]);
             }
           }
         }
@@ -268,7 +279,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int j = 0; j < 8; ++j)
               reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = f[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n_cols) op[j] = f[j];
           }
         } else if (p.tma_store) {
           // stage 64 output channels (two 32-column chunks) per pixel row in a SWIZZLE_128B tile, then one TMA store
@@ -296,6 +309,40 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                            n0);
               tma_store_commit();
             }
+            if (p.bn_stats) {
+              // fused BatchNorm statistics from the staged (bf16-rounded = exactly what BN will normalise) tile: thread t
+              // owns column t & 63 over half of the rows; partial sums live in registers across all tiles of this CTA
+              const int tcol = (threadIdx.x - 64) & 63, half = (threadIdx.x - 64) >> 6;
+              const int rows_in_box = p.bn * hw;
+              // rows of the box that fall outside the tensor were computed from zero-filled operands only if ALL taps
+              // are outside, which is not guaranteed: mask them explicitly with the same validity rule as the store
+              float s1 = 0.f, s2 = 0.f;
+              const int rbeg = half * 64, rend = min(rbeg + 64, rows_in_box);
+#pragma unroll 8
+              for (int rr = rbeg; rr < rend; ++rr) {
+                if (!s_valid[rr]) continue;
+                const int chunk = (tcol >> 3) ^ (rr & 7);
+                const float v2 = __bfloat162float(
+                    *reinterpret_cast<const __nv_bfloat16*>(stg + rr * 128 + chunk * 16 + (tcol & 7) * 2));
+                s1 += v2;
+                s2 = fmaf(v2, v2, s2);
+              }
+              const int gi = (ch >> 1);
+              if (nt != stat_nt) {  // switched to another column tile: spill the register partials first
+                if (stat_nt >= 0) {
+#pragma unroll
+                  for (int g2 = 0; g2 < BN / 64; ++g2) {
+                    s_stats[half * 1024 + stat_nt * BN + g2 * 64 + tcol] += st_sum[g2];
+                    s_stats[half * 1024 + 512 + stat_nt * BN + g2 * 64 + tcol] += st_sq[g2];
+                    st_sum[g2] = 0.f, st_sq[g2] = 0.f;
+                  }
+                }
+                stat_nt = nt;
+              }
+#pragma unroll
+              for (int g2 = 0; g2 < BN / 64; ++g2)
+                if (g2 == gi) st_sum[g2] += s1, st_sq[g2] += s2;
+            }
           }
         } else {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
@@ -310,7 +357,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               reinterpret_cast<uint4*>(op)[j] = t;
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.n_cols; ++j) op[j] = __float2bfloat16(f[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n_cols) op[j] = __float2bfloat16(f[j]);
           }
         }
       }
@@ -321,6 +370,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
+    if (p.bn_stats && p.tma_store && stat_nt >= 0) {
+      const int tcol = (threadIdx.x - 64) & 63, half = (threadIdx.x - 64) >> 6;
+#pragma unroll
+      for (int g2 = 0; g2 < BN / 64; ++g2) {
+        s_stats[half * 1024 + stat_nt * BN + g2 * 64 + tcol] += st_sum[g2];
+        s_stats[half * 1024 + 512 + stat_nt * BN + g2 * 64 + tcol] += st_sq[g2];
+      }
+    }
     if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       const int t = threadIdx.x - 64;
