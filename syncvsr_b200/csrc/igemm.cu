@@ -191,9 +191,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int dw = rem - dh * p.bw;
     int j = 0;
     int gcount = 0;
-    float st_sum[BN / 64], st_sq[BN / 64];  // per-thread BatchNorm partial sums (smem-staged path)
+    float st_sum[BN / 64][2], st_sq[BN / 64][2];  // per-thread BatchNorm partial sums (smem-staged path)
 #pragma unroll
-    for (int g2 = 0; g2 < BN / 64; ++g2) st_sum[g2] = 0.f, st_sq[g2] = 0.f;
+    for (int g2 = 0; g2 < BN / 64; ++g2) st_sum[g2][0] = st_sum[g2][1] = st_sq[g2][0] = st_sq[g2][1] = 0.f;
     int stat_nt = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
@@ -207,7 +207,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ((long long)n * p.o_H + (long long)oh * p.o_sh + p.o_oh) * p.o_W + (long long)ow * p.o_sw + p.o_ow;
       const long long row_off = pix * p.ldc + p.c_off;
       const int acc = j & 1;
-      if (p.bn_stats && p.tma_store) s_valid[r] = row_valid ? 1 : 0;  // read after the group barriers below
+      const bool tile_all_valid = (n0 + p.bn <= p.o_N) && (oh0 + p.bh <= p.OH) && (ow0 + p.bw <= p.OW);
+      if (p.bn_stats && p.tma_store && !tile_all_valid) s_valid[r] = row_valid ? 1 : 0;  // read after the group barriers
       mbar_wait(&tmem_full_bar[acc], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
 
@@ -310,38 +311,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_store_commit();
             }
             if (p.bn_stats) {
-              // fused BatchNorm statistics from the staged (bf16-rounded = exactly what BN will normalise) tile: thread t
-              // owns column t & 63 over half of the rows; partial sums live in registers across all tiles of this CTA
-              const int tcol = (threadIdx.x - 64) & 63, half = (threadIdx.x - 64) >> 6;
+              // fused BatchNorm statistics from the staged (bf16-rounded = exactly what BN will normalise) tile: lane l of
+              // epilogue warp w owns the column pair (2l, 2l+1) over rows [32w, 32w+32): 32 conflict-free LDS.32 per
+              // 64-column group; partial sums stay in registers across all tiles of this CTA.
+              const int ew = (threadIdx.x - 64) >> 5;
               const int rows_in_box = p.bn * hw;
-              // rows of the box that fall outside the tensor were computed from zero-filled operands only if ALL taps
-              // are outside, which is not guaranteed: mask them explicitly with the same validity rule as the store
-              float s1 = 0.f, s2 = 0.f;
-              const int rbeg = half * 64, rend = min(rbeg + 64, rows_in_box);
+              const int rbeg = ew * 32, rend = min(rbeg + 32, rows_in_box);
+              float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+              const uint8_t* colbase = stg + (lane & 3) * 4;
+              const int cpos = lane >> 2;
+              if (tile_all_valid) {
 #pragma unroll 8
-              for (int rr = rbeg; rr < rend; ++rr) {
-                if (!s_valid[rr]) continue;
-                const int chunk = (tcol >> 3) ^ (rr & 7);
-                const float v2 = __bfloat162float(
-                    *reinterpret_cast<const __nv_bfloat16*>(stg + rr * 128 + chunk * 16 + (tcol & 7) * 2));
-                s1 += v2;
-                s2 = fmaf(v2, v2, s2);
+                for (int rr = rbeg; rr < rend; ++rr) {
+                  const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + rr * 128 + ((cpos ^ (rr & 7)) << 4)));
+                  s1a += v2.x, s1b += v2.y;
+                  s2a = fmaf(v2.x, v2.x, s2a), s2b = fmaf(v2.y, v2.y, s2b);
+                }
+              } else {
+                for (int rr = rbeg; rr < rend; ++rr) {
+                  if (!s_valid[rr]) continue;
+                  const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(colbase + rr * 128 + ((cpos ^ (rr & 7)) << 4)));
+                  s1a += v2.x, s1b += v2.y;
+                  s2a = fmaf(v2.x, v2.x, s2a), s2b = fmaf(v2.y, v2.y, s2b);
+                }
               }
               const int gi = (ch >> 1);
               if (nt != stat_nt) {  // switched to another column tile: spill the register partials first
                 if (stat_nt >= 0) {
 #pragma unroll
                   for (int g2 = 0; g2 < BN / 64; ++g2) {
-                    s_stats[half * 1024 + stat_nt * BN + g2 * 64 + tcol] += st_sum[g2];
-                    s_stats[half * 1024 + 512 + stat_nt * BN + g2 * 64 + tcol] += st_sq[g2];
-                    st_sum[g2] = 0.f, st_sq[g2] = 0.f;
+                    float* sl = s_stats + ew * 1024 + stat_nt * BN + g2 * 64 + 2 * lane;
+                    sl[0] += st_sum[g2][0], sl[1] += st_sum[g2][1];
+                    sl[512] += st_sq[g2][0], sl[513] += st_sq[g2][1];
+                    st_sum[g2][0] = st_sum[g2][1] = st_sq[g2][0] = st_sq[g2][1] = 0.f;
                   }
                 }
                 stat_nt = nt;
               }
 #pragma unroll
               for (int g2 = 0; g2 < BN / 64; ++g2)
-                if (g2 == gi) st_sum[g2] += s1, st_sq[g2] += s2;
+                if (g2 == gi) st_sum[g2][0] += s1a, st_sum[g2][1] += s1b, st_sq[g2][0] += s2a, st_sq[g2][1] += s2b;
             }
           }
         } else {
@@ -371,11 +380,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
     if (p.bn_stats && p.tma_store && stat_nt >= 0) {
-      const int tcol = (threadIdx.x - 64) & 63, half = (threadIdx.x - 64) >> 6;
+      const int ew = (threadIdx.x - 64) >> 5;
 #pragma unroll
       for (int g2 = 0; g2 < BN / 64; ++g2) {
-        s_stats[half * 1024 + stat_nt * BN + g2 * 64 + tcol] += st_sum[g2];
-        s_stats[half * 1024 + 512 + stat_nt * BN + g2 * 64 + tcol] += st_sq[g2];
+        float* sl = s_stats + ew * 1024 + stat_nt * BN + g2 * 64 + 2 * lane;
+        sl[0] += st_sum[g2][0], sl[1] += st_sum[g2][1];
+        sl[512] += st_sq[g2][0], sl[513] += st_sq[g2][1];
       }
     }
     if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
