@@ -116,3 +116,75 @@ def reference_config(encoder_type: str = "x-transformers", depth: int = 12, use_
         cfg["model"]["bert"]["attn_dropout"] = 0.0
         cfg["model"]["bert"]["emb_dropout"] = 0.0
     return AttrDict.wrap(cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LRS sentence-level reference (vendored espnet under LRS/video): only `timm` needs a stub.
+# ------------------------------------------------------------------------------------------------------------------
+REF_LRS_ROOT = REF_ROOT / "LRS" / "video"
+_ref_lrs = None
+
+
+def reference_lrs_available() -> bool:
+    return (REF_LRS_ROOT / "espnet" / "nets" / "pytorch_backend" / "e2e_asr_transformer.py").exists()
+
+
+def load_reference_lrs():
+    """Returns the reference's `E2E` class (LRS/video/espnet/nets/pytorch_backend/e2e_asr_transformer.py), unmodified."""
+    global _ref_lrs
+    if _ref_lrs is not None:
+        return _ref_lrs
+    if not reference_lrs_available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    import torchvision
+    import transformers  # noqa: F401  -- before stubbing timm
+
+    had = sys.modules.get("timm")
+    if had is None:
+        timm = types.ModuleType("timm")
+        timm.create_model = lambda name, **kw: getattr(torchvision.models, name)(**kw)
+        sys.modules["timm"] = timm
+    saved_utils = sys.modules.pop("utils", None)  # LRS/video/utils.py vs LRW/video/src/utils.py
+    sys.path.insert(0, str(REF_LRS_ROOT))
+    try:
+        from espnet.nets.pytorch_backend.e2e_asr_transformer import E2E
+
+        _ref_lrs = E2E
+    finally:
+        sys.path.remove(str(REF_LRS_ROOT))
+        if saved_utils is not None:
+            sys.modules["utils"] = saved_utils
+    return _ref_lrs
+
+
+def reference_lrs_args(**overrides):
+    """model.visual_backbone of LRS/video/config/lrs2.yaml as an argparse.Namespace; every dropout zeroed by default."""
+    import argparse
+
+    import yaml
+
+    cfg = yaml.safe_load((REF_LRS_ROOT / "config" / "lrs2.yaml").read_text())["model"]["visual_backbone"]
+    cfg["dropout_rate"] = 0.0
+    cfg["transformer_attn_dropout_rate"] = 0.0
+    cfg.update(overrides)
+    return argparse.Namespace(**cfg)
+
+
+def build_reference_lrs(P, *, odim: int, audio_alignment: int, audio_vocab_size: int, n_audio: int, tokens, **overrides):
+    """Reference E2E with the audio head enabled without the network download of e2e_asr_transformer.py:148
+    (SURVEY.md section 8c): codec attributes set by hand, `forward_audios` returns the pre-made tokens."""
+    import torch.nn as nn
+
+    E2E = load_reference_lrs()
+    m = E2E(odim, reference_lrs_args(**overrides))
+    adim = overrides.get("adim", 768)
+    m.codec = "wav2vec2"
+    m.audio_alignment = audio_alignment
+    m.audio_vocab_size = audio_vocab_size
+    m.audio_weight = 10.0
+    m.audio_classifier = nn.Linear(adim, n_audio)
+    m.forward_audios = lambda audios: tokens
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all("num_batches_tracked" in k for k in missing), missing
+    return m
