@@ -95,6 +95,12 @@ int svsr_stem_bn_gelu_pool_fwd(const void* y0, const float* coef, void* out, uin
                                void* stream);
 int svsr_stem_pool_gelu_bwd(const void* dout, const uint8_t* argmax, const void* y0, const float* coef, void* dz, int N,
                             int IH, int IW, void* stream);
+/* The whole stem backward between the trunk gradient and the conv weight gradient in two passes, without storing dz:
+ * MaxPool3d scatter * GELU' (lightning.py:52-53) -> BatchNorm3d backward (lightning.py:51). dgamma/dbeta += ;
+ * dc = d loss / d y0 (bf16 [N,IH,IW,64]); dout is overwritten with the routed gradient dout * GELU'. stats_scratch: fp64 [128]; kcoef_scratch: fp32 [128]. */
+int svsr_stem_bwd_fused(void* dout, const uint8_t* argmax, const void* y0, const float* coef, float* dgamma,
+                        float* dbeta, void* dc, double* stats_scratch, float* kcoef_scratch, int N, int IH, int IW,
+                        void* stream);
 /* hidden.mean((2,3)) + CLS concat (lightning.py:118,148-150): x_stream fp32 [B, T+1, C] */
 int svsr_meanpool_cls_fwd(const void* a, const float* cls, float* x_stream, int B, int T, int HW, int C, void* stream);
 int svsr_meanpool_cls_bwd(const float* dx, void* dout, float* dcls, int B, int T, int HW, int C, void* stream);

@@ -57,6 +57,15 @@ int svsr_stem_pool_gelu_bwd(const void* dout, const uint8_t* argmax, const void*
                             static_cast<bf16*>(dz), N, IH, IW, ST(stream));
 }
 
+int svsr_stem_bwd_fused(void* dout, const uint8_t* argmax, const void* y0, const float* coef, float* dgamma,
+                        float* dbeta, void* dc, double* stats_scratch, float* kcoef_scratch, int N, int IH, int IW,
+                        void* stream) {
+  SVSR_REQUIRE(dout && argmax && y0 && coef && dgamma && dbeta && dc && stats_scratch && kcoef_scratch,
+               "stem_bwd_fused: null pointer");
+  return stem_bwd_fused(static_cast<bf16*>(dout), argmax, static_cast<const bf16*>(y0), coef, dgamma, dbeta,
+                        static_cast<bf16*>(dc), stats_scratch, kcoef_scratch, N, IH, IW, ST(stream));
+}
+
 int svsr_meanpool_cls_fwd(const void* a, const float* cls, float* x_stream, int B, int T, int HW, int C, void* stream) {
   return meanpool_cls(static_cast<const bf16*>(a), cls, x_stream, B, T, HW, C, ST(stream));
 }

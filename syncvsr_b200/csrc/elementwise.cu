@@ -28,9 +28,15 @@ __device__ __forceinline__ F8 ldf8(const float* p) {
 }
 // erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of every tensor these kernels
 // write): 2 MUFU + ~8 FMA instead of libdevice's branchy erff -- the stem's BN+GELU+pool passes are erf-bound otherwise.
+// MUFU.RCP only (1 ulp): __frcp_rn expands to a Newton fix-up plus a slow-path CALL per element
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -184,23 +190,32 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (long long r = (long long)blockIdx.x * rpb + slot; r < rows; r += (long long)gridDim.x * rpb) {
-    const long long off = r * C + g * 8;
-    F8 gv = ld8(dout + off);
+  // two rows per iteration, every load issued before the first use (this pass is latency-bound otherwise)
+  const long long rstep = (long long)gridDim.x * rpb;
+  for (long long r = (long long)blockIdx.x * rpb + slot; r < rows; r += 2 * rstep) {
+    const bool two = r + rstep < rows;
+    const long long off0 = r * C + g * 8, off1 = (two ? r + rstep : r) * C + g * 8;
+    F8 gv[2] = {ld8(dout + off0), ld8(dout + off1)};
+    const F8 cv[2] = {ld8(c + off0), ld8(c + off1)};
     if (relu_ref) {
-      const F8 o = ld8(relu_ref + off);
+      const F8 o[2] = {ld8(relu_ref + off0), ld8(relu_ref + off1)};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
-    }
-    const F8 cv = ld8(c + off);
-    if (self_mask) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gv.v[k] = (cv.v[k] * scl.v[k] + shf.v[k]) > 0.f ? gv.v[k] : 0.f;
+        for (int k = 0; k < 8; ++k) gv[u].v[k] = o[u].v[k] > 0.f ? gv[u].v[k] : 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[k] += gv.v[k];
-      acc[8 + k] += gv.v[k] * (cv.v[k] - mean.v[k]) * invstd.v[k];
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      if (self_mask) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[u].v[k] = (cv[u].v[k] * scl.v[k] + shf.v[k]) > 0.f ? gv[u].v[k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k] += gv[u].v[k];
+        acc[8 + k] += gv[u].v[k] * (cv[u].v[k] - mean.v[k]) * invstd.v[k];
+      }
     }
   }
   block_channel_reduce(acc, cg, C, stats);
@@ -355,6 +370,130 @@ stem_pool_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t*
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = acc[k] == 0.f ? 0.f : acc[k] * gelu_grad_f(v.v[k] * sc.v[k] + sh.v[k]);
     st8(dz + pix * C + g * 8, o);
+  }
+}
+
+// Fused stem backward (max-pool scatter * GELU' -> BatchNorm3d backward) without ever materialising dz:
+//   dz(n,ih,iw,c) = gelu'(bn(y0)) * (sum of dout over the <= 4 pooling windows that contain (ih,iw) and selected it)
+//   REDUCE (one thread per POOLED element group): every pooled output routes its gradient to exactly one input, so
+//     sum dz = sum_windows dout * gelu'(z_sel) and sum dz*xhat likewise -- a gather of the selected y0 values, 4x fewer
+//     elements than the input grid and no window search;
+//   APPLY (one thread per input pixel x 8 channels): dc = scale * (dz - k1 - xhat * k2), window membership resolved
+//     with byte-wise SIMD compares (vcmpeq4 + prmt build bf16x2 lane masks).
+// Replaces stem_pool_gelu_bwd + bn_bwd_reduce + bn_bwd_apply (3.4 GB of traffic, instruction-bound) by 1.7 GB.
+__device__ __forceinline__ float gelu_grad_shared_exp(float z) {
+  const float ax = fabsf(z) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(ax * ax * -1.4426950408889634f);  // = exp(-z^2/2): shared by erf and by the density term
+  const float half_erf = copysignf(fmaf(-0.5f * p * t, e, 0.5f), z);
+  return fmaf(z * 0.3989422804014327f, e, 0.5f + half_erf);
+}
+
+// x / d for x * d < 2^32 with m = 2^32 / d + 1 (host-computed): one IMAD.HI instead of a ~20-instruction division
+__device__ __forceinline__ unsigned fastdiv(unsigned x, unsigned m) { return __umulhi(x, m); }
+
+// REDUCE: also overwrites dout in place with dzp = dout * gelu'(z_sel) (bf16), the per-window routed gradient the
+// APPLY pass scatters -- GELU' is evaluated once per pooled element instead of once per input element.
+__global__ void __launch_bounds__(256)
+stem_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
+                       const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef, double* stats,
+                       unsigned npool, unsigned IH, unsigned IW, unsigned OH, unsigned OW, unsigned mOH, unsigned mOW) {
+  constexpr unsigned C = 64;
+  const unsigned g = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
+  const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (unsigned pix = blockIdx.x * 32u + slot; pix < npool; pix += gridDim.x * 32u) {
+    const unsigned t1 = fastdiv(pix, mOW), ow = pix - t1 * OW, n = fastdiv(t1, mOH), oh = t1 - n * OH;
+    const unsigned o = pix * C + g * 8;
+    const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
+    const F8 d = ld8(dout + o);
+    const unsigned base = ((n * IH + 2 * oh - 1) * IW + 2 * ow - 1) * C + g * 8;  // window origin (mod 2^32 is fine)
+    float cv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned pos = ((k < 4 ? am.x : am.y) >> (8 * (k & 3))) & 0xff;
+      const unsigned kh = (pos * 11u) >> 5, kw = pos - kh * 3u;  // pos / 3 for pos < 9
+      cv[k] = __bfloat162float(y0[base + (kh * IW + kw) * C + k]);
+    }
+    F8 dzp;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dzp.v[k] = d.v[k] * gelu_grad_shared_exp(fmaf(cv[k], sc.v[k], sh.v[k]));
+      acc[k] += dzp.v[k];
+      acc[8 + k] += dzp.v[k] * (cv[k] - mean.v[k]) * invstd.v[k];
+    }
+    st8(dout + o, dzp);
+  }
+  block_channel_reduce(acc, 8, C, stats);
+}
+
+// bf16x2 lane mask of channels (2j, 2j+1) from the byte-wise "selected" mask m (0xff per selected channel byte)
+__device__ __forceinline__ uint32_t pair_mask(uint32_t m, int j) { return __byte_perm(m, 0, j ? 0x3322 : 0x1100); }
+
+// APPLY: dc = scale * (dz - k1 - xhat * k2) with dz = sum of the dzp of the <= 4 windows that selected this input.
+__global__ void __launch_bounds__(256)
+stem_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dzp, const uint8_t* __restrict__ argmax,
+                      const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef,
+                      const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc, unsigned npix, unsigned IH,
+                      unsigned IW, unsigned OH, unsigned OW, unsigned mIH, unsigned mIW) {
+  constexpr unsigned C = 64;
+  const unsigned g = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  F8 sc, ca, cb;  // dc = dz*sc + (v*cb + ca): cb = -sc*k2*invstd, ca = -sc*k1 + sc*k2*mean*invstd
+  {
+    const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
+    const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
+    sc = ldf8(coef + 2 * C + g * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cb.v[k] = -sc.v[k] * k2.v[k] * invstd.v[k];
+      ca.v[k] = -sc.v[k] * k1.v[k] - cb.v[k] * mean.v[k];
+    }
+  }
+  for (unsigned pix = blockIdx.x * 32u + slot; pix < npix; pix += gridDim.x * 32u) {
+    const unsigned t1 = fastdiv(pix, mIW), iw = pix - t1 * IW, n = fastdiv(t1, mIH), ih = t1 - n * IH;
+    const unsigned oh0 = ih >> 1, oh1 = (ih + 1) >> 1, ow0 = iw >> 1, ow1 = (iw + 1) >> 1;
+    const bool vh1 = (oh1 != oh0) && (oh1 < OH), vw1 = (ow1 != ow0) && (ow1 < OW);
+    const unsigned oh1c = vh1 ? oh1 : oh0, ow1c = vw1 ? ow1 : ow0;
+    const unsigned r0 = (n * OH + oh0) * OW, r1 = (n * OH + oh1c) * OW;
+    const unsigned o[4] = {(r0 + ow0) * C + g * 8, (r0 + ow1c) * C + g * 8, (r1 + ow0) * C + g * 8,
+                           (r1 + ow1c) * C + g * 8};
+    // window position of (ih,iw) inside window (oh,ow): (ih - 2*oh + 1) * 3 + (iw - 2*ow + 1), replicated to 4 bytes;
+    // windows that do not exist get the impossible position 0xff
+    const unsigned ph0 = (ih - 2 * oh0 + 1) * 3, ph1 = (ih - 2 * oh1c + 1) * 3;
+    const unsigned pw0 = iw - 2 * ow0 + 1, pw1 = iw - 2 * ow1c + 1;
+    const uint32_t pp[4] = {(ph0 + pw0) * 0x01010101u, vw1 ? (ph0 + pw1) * 0x01010101u : 0xffffffffu,
+                            vh1 ? (ph1 + pw0) * 0x01010101u : 0xffffffffu,
+                            (vh1 && vw1) ? (ph1 + pw1) * 0x01010101u : 0xffffffffu};
+    uint2 am[4];
+    uint4 dd[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {  // all loads first
+      am[w] = *reinterpret_cast<const uint2*>(argmax + o[w]);
+      dd[w] = *reinterpret_cast<const uint4*>(dzp + o[w]);
+    }
+    const F8 v = ld8(y0 + pix * C + g * 8);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t mlo = __vcmpeq4(am[w].x, pp[w]), mhi = __vcmpeq4(am[w].y, pp[w]);
+      const float2 a = unpack_bf16x2(dd[w].x & pair_mask(mlo, 0)), b = unpack_bf16x2(dd[w].y & pair_mask(mlo, 1));
+      const float2 c2 = unpack_bf16x2(dd[w].z & pair_mask(mhi, 0)), d2 = unpack_bf16x2(dd[w].w & pair_mask(mhi, 1));
+      acc[0] += a.x, acc[1] += a.y, acc[2] += b.x, acc[3] += b.y;
+      acc[4] += c2.x, acc[5] += c2.y, acc[6] += d2.x, acc[7] += d2.y;
+    }
+    F8 out;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out.v[k] = fmaf(acc[k], sc.v[k], fmaf(v.v[k], cb.v[k], ca.v[k]));
+    st8(dc + pix * C + g * 8, out);
   }
 }
 
@@ -596,7 +735,7 @@ int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, cons
                   long long rows, int C, double* stats, int self_mask, cudaStream_t s) {
   SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   const int rpb = 256 / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask);
+  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 6), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -627,6 +766,28 @@ int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const _
   const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
   stem_pool_gelu_bwd_kernel<<<grid_for((long long)N * IH * IW * 8, 256 * 2), 256, 0, s>>>(dout, argmax, y0, coef, dz,
                                                                                        N, IH, IW, OH, OW);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
+                   float* dgamma, float* dbeta, __nv_bfloat16* dc, double* stats_scratch, float* kcoef_scratch, int N,
+                   int IH, int IW, cudaStream_t s) {
+  const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
+  const long long npix = (long long)N * IH * IW, npool = (long long)N * OH * OW;
+  SVSR_REQUIRE(npix * 64 < (1LL << 31) && npix * (IH > IW ? IH : IW) < (1LL << 32),
+               "stem_bwd_fused: %lld input pixels exceed 32-bit indexing", npix);
+  auto magic = [](int d) { return (unsigned)((1ULL << 32) / (unsigned)d + 1ULL); };
+  SVSR_CHECK_CUDA(cudaMemsetAsync(stats_scratch, 0, 2 * 64 * sizeof(double), s));
+  stem_bwd_reduce_kernel<<<grid_for(npool, 32 * 4), 256, 0, s>>>(dout, argmax, y0, coef, stats_scratch, (unsigned)npool,
+                                                                 (unsigned)IH, (unsigned)IW, (unsigned)OH, (unsigned)OW,
+                                                                 magic(OH), magic(OW));
+  LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<1, 128, 0, s>>>(stats_scratch, npix, 64, dgamma, dbeta, kcoef_scratch);
+  LAUNCH_CHECK();
+  stem_bwd_apply_kernel<<<grid_for(npix, 32 * 8, 148 * 16), 256, 0, s>>>(dout, argmax, y0, coef, kcoef_scratch, dc,
+                                                                         (unsigned)npix, (unsigned)IH, (unsigned)IW,
+                                                                         (unsigned)OH, (unsigned)OW, magic(IH),
+                                                                         magic(IW));
   LAUNCH_CHECK();
   return SVSR_OK;
 }

@@ -38,6 +38,12 @@ int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16*
 int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
                        __nv_bfloat16* dz, int N, int IH, int IW, cudaStream_t s);
 
+// Fused stem backward: the three passes above (pool scatter * GELU', BN reduce, BN apply) as two, dz never stored.
+// dgamma/dbeta += ; dc = d loss / d y0 (bf16). dout is OVERWRITTEN (dout * gelu'(z_selected), the routed gradient). stats_scratch: fp64 [128], kcoef_scratch: fp32 [128].
+int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
+                   float* dgamma, float* dbeta, __nv_bfloat16* dc, double* stats_scratch, float* kcoef_scratch, int N,
+                   int IH, int IW, cudaStream_t s);
+
 // x_stream[b, t+1, :] = mean over HW of a[b*T+t, :, :]; x_stream[b, 0, :] = cls  (fp32 [B,T+1,C])
 int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,
                  cudaStream_t s);

@@ -873,9 +873,9 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
 
   // ---- stem ----
   bf16* dz = e.ws<bf16>(e.stem_dz);
-  RC(stem_pool_gelu_bwd(T0, e.ws<uint8_t>(e.argmax), e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), dz, e.N, e.H0,
-                        e.H0, s));
-  RC(bn_bwd(e, dz, nullptr, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, dz, nullptr, s));
+  RC(stem_bwd_fused(T0, e.ws<uint8_t>(e.argmax), e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), e.G + e.stem_bn.gamma,
+                    e.G + e.stem_bn.beta, dz, e.ws<double>(e.stem_bn.stats_b), e.ws<float>(e.stem_bn.kcoef), e.N, e.H0,
+                    e.H0, s));
   RC(sq.fork());
   {
     float* tmp = e.ws<float>(e.wgrad_tmp);

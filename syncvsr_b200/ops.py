@@ -182,6 +182,21 @@ def stem_pool_gelu_bwd(dout, argmax, y0, coef):
     return dz
 
 
+def stem_bwd_fused(dout, argmax, y0, coef):
+    """Pool scatter * GELU' -> BatchNorm backward in two passes. Returns (dc bf16, dgamma, dbeta)."""
+    N, IH, IW, _ = y0.shape
+    dout = dout.clone()  # the op overwrites its upstream gradient
+    dc = torch.empty_like(y0)
+    dgamma = torch.zeros(64, device=y0.device)
+    dbeta = torch.zeros(64, device=y0.device)
+    scratch = torch.zeros(128, device=y0.device, dtype=torch.float64)
+    kcoef = torch.empty(128, device=y0.device)
+    check(lib().svsr_stem_bwd_fused(ptr(dout), ptr(argmax), ptr(y0), ptr(coef), ptr(dgamma), ptr(dbeta), ptr(dc),
+                                    ptr(scratch), ptr(kcoef), _i(N), _i(IH), _i(IW), stream_ptr()),
+          "svsr_stem_bwd_fused")
+    return dc, dgamma, dbeta
+
+
 def meanpool_cls_fwd(a, cls, B, T):
     N, H, W, Cc = a.shape
     xs = torch.empty(B, T + 1, Cc, device=a.device, dtype=torch.float32)

@@ -172,6 +172,33 @@ def test_stem_bn_gelu_pool_fwd_bwd(ops):
     assert rel(dz, gz.permute(0, 2, 3, 1)) < BF16_TOL
 
 
+def test_stem_bwd_fused_matches_three_pass_and_autograd(ops):
+    """svsr_stem_bwd_fused == stem_pool_gelu_bwd -> batchnorm_bwd (the path it replaces) and == autograd through
+    BatchNorm3d(train) -> GELU -> MaxPool (lightning.py:51-53); odd sizes exercise clipped windows."""
+    for N, IH, seed in ((5, 44, 60), (3, 7, 70)):
+        y0 = randn(N, IH, IH, 64, seed=seed)
+        gamma = randn(64, seed=seed + 1, dtype=torch.float32).abs() + 0.5
+        beta = randn(64, seed=seed + 2, dtype=torch.float32) * 0.3
+        yf = y0.float().reshape(-1, 64)
+        mean, var = yf.mean(0), yf.var(0, unbiased=False)
+        invstd = (var + 1e-5).rsqrt()
+        coef = torch.stack((mean, invstd, gamma * invstd, beta - mean * gamma * invstd)).contiguous()
+        out, am = ops.stem_bn_gelu_pool_fwd(y0, coef)
+        dout = randn(*out.shape, seed=seed + 3)
+        dc, dgamma, dbeta = ops.stem_bwd_fused(dout, am, y0, coef)
+        # (a) the three-pass path it replaces (dz rounded to bf16 in between)
+        dz = ops.stem_pool_gelu_bwd(dout, am, y0, coef)
+        dc3, dg3, db3, _ = ops.batchnorm_bwd(dz, None, y0, coef)
+        assert rel(dc, dc3) < BF16_TOL and rel(dgamma, dg3) < 2e-3 and rel(dbeta, db3) < 2e-3
+        # (b) autograd on the same (bf16-valued) inputs
+        x = y0.float().permute(0, 3, 1, 2).requires_grad_(True)
+        g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        ref = F.max_pool2d(F.gelu(F.batch_norm(x, None, None, g, b, True, 0.1, 1e-5)), 3, 2, 1)
+        gx, gg, gb = torch.autograd.grad(ref, (x, g, b), dout.float().permute(0, 3, 1, 2))
+        assert rel(dc, gx.permute(0, 2, 3, 1)) < BF16_TOL
+        assert rel(dgamma, gg) < 2e-3 and rel(dbeta, gb) < 2e-3
+
+
 def test_meanpool_cls(ops):
     B, T, C = 3, 29, 512
     a = randn(B * T, 3, 3, C, seed=40)
