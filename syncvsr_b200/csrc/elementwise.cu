@@ -49,6 +49,14 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// Swish / SiLU (LRS frontend: conv3d_extractor.py:36, modules/resnet.py relu_type="swish"; convolution.py:78-83)
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + __expf(-x)); }
+__device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float swish_grad_f(float x) {
+  const float sg = sigmoid_f(x);
+  return sg * fmaf(x, 1.0f - sg, 1.0f);
+}
+
 inline unsigned grid_for(long long work_items, int per_block, int max_blocks = 148 * 8) {
   long long b = (work_items + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -171,9 +179,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
 #pragma unroll
       for (int k = 0; k < 8; ++k) v.v[k] += rv.v[k];
     }
-    if (relu) {
+    if (relu == 1) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+    } else if (relu == 2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = swish_f(v.v[k]);
     }
     st8(out + off, v);
   }
@@ -182,7 +193,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                      const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef, long long rows, int C,
-                     double* stats, int self_mask) {
+                     double* stats, int self_mask, const __nv_bfloat16* __restrict__ sw_res,
+                     const float* __restrict__ sw_rcoef) {
   const int cg = C >> 3;
   const int g = threadIdx.x % cg, slot = threadIdx.x / cg, rpb = 256 / cg;
   const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
@@ -207,9 +219,25 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
-      if (self_mask) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
+      if (self_mask == 1) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
 #pragma unroll
         for (int k = 0; k < 8; ++k) gv[u].v[k] = (cv[u].v[k] * scl.v[k] + shf.v[k]) > 0.f ? gv[u].v[k] : 0.f;
+      } else if (self_mask == 2) {  // Swish follows (this BN output [+ residual branch]): g = dout * swish'(pre-activation)
+        F8 pre;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pre.v[k] = cv[u].v[k] * scl.v[k] + shf.v[k];
+        if (sw_res) {
+          F8 rv = ld8(sw_res + (u ? off1 : off0));
+          if (sw_rcoef) {
+            const F8 rs = ldf8(sw_rcoef + 2 * C + g * 8), rh = ldf8(sw_rcoef + 3 * C + g * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pre.v[k] += rv.v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[u].v[k] *= swish_grad_f(pre.v[k]);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -236,7 +264,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
                     const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
-                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C, int self_mask) {
+                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C, int self_mask,
+                    const __nv_bfloat16* __restrict__ sw_res, const float* __restrict__ sw_rcoef) {
   const int cg = C >> 3;
   const long long total = rows * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -251,10 +280,27 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
     }
     const F8 cv = ld8(c + off);
     const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8), sc = ldf8(coef + 2 * C + g * 8);
-    if (self_mask) {
+    if (self_mask == 1) {
       const F8 shf = ldf8(coef + 3 * C + g * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) gv.v[k] = (cv.v[k] * sc.v[k] + shf.v[k]) > 0.f ? gv.v[k] : 0.f;
+    } else if (self_mask == 2) {
+      const F8 shf = ldf8(coef + 3 * C + g * 8);
+      F8 pre;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pre.v[k] = cv.v[k] * sc.v[k] + shf.v[k];
+      if (sw_res) {
+        F8 rv = ld8(sw_res + off);
+        if (sw_rcoef) {
+          const F8 rs = ldf8(sw_rcoef + 2 * C + g * 8), rh = ldf8(sw_rcoef + 3 * C + g * 8);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pre.v[k] += rv.v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gv.v[k] *= swish_grad_f(pre.v[k]);
     }
     if (gmask_out) st8(gmask_out + off, gv);
     const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
@@ -272,7 +318,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
 __global__ void __launch_bounds__(256)
 stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef,
                          __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ argmax, int N, int IH, int IW, int OH,
-                         int OW) {
+                         int OW, int swish) {
   constexpr int C = 64, cg = 8;
   const long long total = (long long)N * OH * OW * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -311,7 +357,8 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
     int bi[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float a = gelu_f(zmax[k]), b = gelu_f(zmin[k]);
+      // Swish is unimodal as well (minimum at z ~ -1.278): the same two-candidate argument holds
+      const float a = swish ? swish_f(zmax[k]) : gelu_f(zmax[k]), b = swish ? swish_f(zmin[k]) : gelu_f(zmin[k]);
       // first maximum wins (torch max_pool semantics): on a tie the earlier window position
       const bool take_min = (b > a) || (b == a && imin[k] < imax[k]);
       best[k] = take_min ? b : a;
@@ -401,7 +448,8 @@ __device__ __forceinline__ unsigned fastdiv(unsigned x, unsigned m) { return __u
 __global__ void __launch_bounds__(256)
 stem_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
                        const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef, double* stats,
-                       unsigned npool, unsigned IH, unsigned IW, unsigned OH, unsigned OW, unsigned mOH, unsigned mOW) {
+                       unsigned npool, unsigned IH, unsigned IW, unsigned OH, unsigned OW, unsigned mOH, unsigned mOW,
+                       int swish) {
   constexpr unsigned C = 64;
   const unsigned g = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
@@ -425,7 +473,8 @@ stem_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, const uint8_t* __restri
     F8 dzp;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      dzp.v[k] = d.v[k] * gelu_grad_shared_exp(fmaf(cv[k], sc.v[k], sh.v[k]));
+      const float z = fmaf(cv[k], sc.v[k], sh.v[k]);
+      dzp.v[k] = d.v[k] * (swish ? swish_grad_f(z) : gelu_grad_shared_exp(z));
       acc[k] += dzp.v[k];
       acc[8 + k] += dzp.v[k] * (cv[k] - mean.v[k]) * invstd.v[k];
     }
@@ -732,10 +781,12 @@ int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res
   return SVSR_OK;
 }
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                  long long rows, int C, double* stats, int self_mask, cudaStream_t s) {
+                  long long rows, int C, double* stats, int self_mask, cudaStream_t s, const __nv_bfloat16* sw_res,
+                  const float* sw_rcoef) {
   SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   const int rpb = 256 / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 6), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask);
+  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 6), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask,
+                                                                        sw_res, sw_rcoef);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -747,17 +798,17 @@ int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, f
 }
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
                  const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
-                 cudaStream_t s) {
+                 cudaStream_t s, const __nv_bfloat16* sw_res, const float* sw_rcoef) {
   bn_bwd_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out,
-                                                                       rows, C, self_mask);
+                                                                       rows, C, self_mask, sw_res, sw_rcoef);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16* out, uint8_t* argmax, int N, int IH,
-                      int IW, cudaStream_t s) {
+                      int IW, cudaStream_t s, int swish) {
   const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
   stem_bn_gelu_pool_kernel<<<grid_for((long long)N * OH * OW * 8, 256 * 2), 256, 0, s>>>(y0, coef, out, argmax, N, IH,
-                                                                                      IW, OH, OW);
+                                                                                      IW, OH, OW, swish);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -771,7 +822,7 @@ int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const _
 }
 int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
                    float* dgamma, float* dbeta, __nv_bfloat16* dc, double* stats_scratch, float* kcoef_scratch, int N,
-                   int IH, int IW, cudaStream_t s) {
+                   int IH, int IW, cudaStream_t s, int swish) {
   const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
   const long long npix = (long long)N * IH * IW, npool = (long long)N * OH * OW;
   SVSR_REQUIRE(npix * 64 < (1LL << 31) && npix * (IH > IW ? IH : IW) < (1LL << 32),
@@ -780,7 +831,7 @@ int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat
   SVSR_CHECK_CUDA(cudaMemsetAsync(stats_scratch, 0, 2 * 64 * sizeof(double), s));
   stem_bwd_reduce_kernel<<<grid_for(npool, 32 * 4), 256, 0, s>>>(dout, argmax, y0, coef, stats_scratch, (unsigned)npool,
                                                                  (unsigned)IH, (unsigned)IW, (unsigned)OH, (unsigned)OW,
-                                                                 magic(OH), magic(OW));
+                                                                 magic(OH), magic(OW), swish);
   LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<1, 128, 0, s>>>(stats_scratch, npix, 64, dgamma, dbeta, kcoef_scratch);
   LAUNCH_CHECK();

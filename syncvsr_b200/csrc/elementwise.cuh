@@ -16,24 +16,28 @@ int bn_stats(const __nv_bfloat16* x, long long rows, int C, double* stats, cudaS
 int bn_finalize(const double* stats, long long rows, int C, const float* gamma, const float* beta, float eps,
                 float momentum, float* running_mean, float* running_var, float* coef, int update_running,
                 cudaStream_t s);
-// out = act(x*scale+shift (+ res*rscale+rshift | + res)); coef/rcoef are the [4][C] blocks of bn_finalize
+// out = act(x*scale+shift (+ res*rscale+rshift | + res)); coef/rcoef are the [4][C] blocks of bn_finalize.
+// relu: 0 = identity, 1 = ReLU, 2 = Swish (LRS frontend)
 int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res, const float* rcoef, int relu,
              __nv_bfloat16* out, long long rows, int C, cudaStream_t s);
 // self_mask = 1: the ReLU that follows this BN is recomputed from c (mask = c*scale+shift > 0), relu_ref unused.
+// self_mask = 2: Swish follows: g = dout * swish'(c*scale+shift [+ sw_res*rscale+rshift | + sw_res]) (sw_rcoef optional).
 // backward reductions: g = dout * (ref > 0 if ref) ; stats[0..C) += sum g ; stats[C..2C) += sum g * xhat
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
-                  long long rows, int C, double* stats, int self_mask, cudaStream_t s);
+                  long long rows, int C, double* stats, int self_mask, cudaStream_t s,
+                  const __nv_bfloat16* sw_res = nullptr, const float* sw_rcoef = nullptr);
 // dgamma += sum g*xhat ; dbeta += sum g ; kcoef[0..C) = sum g / rows ; kcoef[C..2C) = sum g*xhat / rows
 int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, float* dbeta, float* kcoef,
                     cudaStream_t s);
 // dc = scale * (g - k1 - xhat*k2); optionally also writes g (the relu-masked upstream gradient) to gmask_out
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
                  const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
-                 cudaStream_t s);
+                 cudaStream_t s, const __nv_bfloat16* sw_res = nullptr, const float* sw_rcoef = nullptr);
 
 // stem epilogue: y0 [N,IH,IW,64] -> max_pool3x3s2p1(gelu(bn(y0))) [N,OH,OW,64] + argmax slot (uint8)
+// swish = 1: Swish instead of GELU (LRS frontend3D, conv3d_extractor.py:31-38)
 int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16* out, uint8_t* argmax, int N, int IH,
-                      int IW, cudaStream_t s);
+                      int IW, cudaStream_t s, int swish = 0);
 // dz[N,IH,IW,64] = (scatter of dout through argmax) * gelu'(bn(y0))
 int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
                        __nv_bfloat16* dz, int N, int IH, int IW, cudaStream_t s);
@@ -42,7 +46,7 @@ int stem_pool_gelu_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, const _
 // dgamma/dbeta += ; dc = d loss / d y0 (bf16). dout is OVERWRITTEN (dout * gelu'(z_selected), the routed gradient). stats_scratch: fp64 [128], kcoef_scratch: fp32 [128].
 int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat16* y0, const float* coef,
                    float* dgamma, float* dbeta, __nv_bfloat16* dc, double* stats_scratch, float* kcoef_scratch, int N,
-                   int IH, int IW, cudaStream_t s);
+                   int IH, int IW, cudaStream_t s, int swish = 0);
 
 // x_stream[b, t+1, :] = mean over HW of a[b*T+t, :, :]; x_stream[b, 0, :] = cls  (fp32 [B,T+1,C])
 int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,

@@ -2,66 +2,12 @@
 // Owns the layout of the flat parameter / gradient / buffer arenas, the activation workspace and the bf16 operand
 // copies of the weights, and sequences every kernel of forward and backward on one stream (no autograd, no
 // per-op Python): stem3d -> resnet.layer1-4 -> mean pool + CLS -> x-transformers encoder -> the two loss heads.
-#include <cmath>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/svsr.h"
-#include "common.cuh"
-#include "elementwise.cuh"
+#include "engine_common.cuh"
 #include "encoder.cuh"
 #include "heads.cuh"
-#include "igemm.cuh"
 #include "precise.cuh"
-#include "wgrad.cuh"
 
 namespace svsr {
-
-#define RC(expr)              \
-  do {                        \
-    int _rc = (expr);         \
-    if (_rc) return _rc;      \
-  } while (0)
-
-typedef __nv_bfloat16 bf16;
-
-struct ParamInfo {
-  std::string name;
-  int ndim;
-  long long shape[5];
-  long long offset;  // elements into the fp32 arena
-  long long numel;
-  int decay;  // AdamW weight decay applies (ndim >= 2; lightning.py:217-219)
-};
-
-struct BnRef {
-  long long gamma, beta;  // param arena offsets
-  long long rmean, rvar;  // buffer arena offsets
-  int C;
-  size_t coef, kcoef, stats_f, stats_b;  // workspace offsets
-};
-
-struct ConvRef {
-  long long w;  // param arena offset
-  int cin, cout, R, stride, pad;
-  size_t wf, wd;  // packed bf16 operands (fprop / dgrad)
-};
-
-struct BlockRef {
-  int cin, cout, stride, Hin, Hout;
-  bool ds;
-  ConvRef conv1, conv2, convds;
-  BnRef bn1, bn2, bnds;
-  size_t c1, a1, c2, out, cds;  // saved activations (bf16)
-};
-
-struct LinRef {
-  long long w, b;  // param arena offsets (b < 0: no bias)
-  int N, K;
-  size_t wb, wt;  // bf16 [N, K] and transposed [K, ldt]
-  int ldt;
-};
 
 struct EncLayerRef {
   long long g_a, g_f;
@@ -69,51 +15,24 @@ struct EncLayerRef {
   size_t xn_a, inv_a, qkvbuf, obuf, xn_f, inv_f, hbuf, ubuf;
 };
 
-// The parameter arena is [decayed (ndim >= 2) | non-decayed]; `nodecay_base` is where the second region starts
-// (found by a first sizing pass of engine_build). Buffers use one region.
-struct ArenaCount {
-  long long decay = 0, nodecay = 0, nodecay_base = 0;
-};
-
-struct LrwEngine {
+struct LrwEngine : EngineBase {
   svsr_lrw_config cfg;
-  int N;   // frames = B*T
-  int M;   // tokens = B*(T+1)
-  int H0;  // stem conv output size
-  int H1;  // pooled size (layer1 input)
-  std::vector<ParamInfo> params;
-  std::vector<ParamInfo> buffers;
-  long long param_count = 0, buffer_count = 0, decay_count = 0;
-  ArenaCount pc, bc;
-  size_t ws_bytes = 0;
-
-  // bound storage
-  float* P = nullptr;
-  float* G = nullptr;
-  float* BUF = nullptr;
-  uint8_t* WS = nullptr;
+  int M;  // tokens = B*(T+1)
+  Frontend fe;  // stem3d + resnet.layer1-4
 
   // model structure
-  ConvRef stem_conv;
-  BnRef stem_bn;
-  BlockRef blocks[8];
   long long cls_off;
   std::vector<EncLayerRef> enc;
   LinRef cat, aud;
   int cat_ld;  // padded pitch of category logits
 
   // workspace offsets
-  size_t patches, y0, x1, argmax, xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a,
-      logits_c, dlogits_c, acc, bad_token, rot, stats_arena, stats_arena_bytes;
+  size_t xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a, logits_c, dlogits_c, acc,
+      bad_token, rot;
   size_t pack_jobs;  // device table for the single-launch weight repack
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
-  size_t dx, dxb[3], t_du, t_dh[2], t_dyn, t_do, t_dqkv[2], gbuf[9], stem_dz, wgrad_tmp;
-  // weight-gradient side stream (backward): forked from / joined to the caller's stream with events
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
-  int fork_idx = 0;
+  size_t dx, dxb[3], t_du, t_dh[2], t_dyn, t_do, t_dqkv[2];
   // parity-mode (fp32 activations, split-bf16 operands) scratch layout: offsets into a caller-provided buffer
   size_t p_patches, p_y0, p_act[6], p_s3, p_w3, p_xs[2], p_xn, p_qkv, p_o, p_h, p_u, p_lc, p_lf, p_bytes = 0;
   // forward inputs remembered for backward
@@ -123,76 +42,8 @@ struct LrwEngine {
   bool fwd_done = false;
   bool bwd_stage0_done = false;
 
-  template <class T>
-  T* ws(size_t off) const {
-    return reinterpret_cast<T*>(WS + off);
-  }
   float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * cfg.dim; }
 };
-
-namespace {
-
-struct Bump {
-  size_t off = 0;
-  size_t take(size_t bytes) {
-    size_t o = off;
-    off += (bytes + 255) & ~size_t(255);
-    return o;
-  }
-};
-
-long long add_param(std::vector<ParamInfo>& v, ArenaCount& count, const std::string& name,
-                    std::initializer_list<long long> shape) {
-  ParamInfo p;
-  p.name = name;
-  p.ndim = (int)shape.size();
-  p.numel = 1;
-  int i = 0;
-  for (long long s : shape) p.shape[i++] = s, p.numel *= s;
-  for (; i < 5; ++i) p.shape[i] = 1;
-  p.decay = p.ndim >= 2;
-  const long long padded = (p.numel + 3) & ~3LL;  // keep every tensor 16-byte aligned inside the arena
-  if (p.decay) {
-    p.offset = count.decay;
-    count.decay += padded;
-  } else {
-    p.offset = count.nodecay_base + count.nodecay;
-    count.nodecay += padded;
-  }
-  v.push_back(p);
-  return p.offset;
-}
-
-void add_bn(LrwEngine& e, BnRef& bn, const std::string& prefix, int C, Bump& b) {
-  bn.C = C;
-  bn.gamma = add_param(e.params, e.pc, prefix + ".weight", {C});
-  bn.beta = add_param(e.params, e.pc, prefix + ".bias", {C});
-  bn.rmean = add_param(e.buffers, e.bc, prefix + ".running_mean", {C});
-  bn.rvar = add_param(e.buffers, e.bc, prefix + ".running_var", {C});
-  bn.coef = b.take(4 * C * sizeof(float));
-  bn.kcoef = b.take(2 * C * sizeof(float));
-}
-
-void add_conv(LrwEngine& e, ConvRef& c, const std::string& name, int cin, int cout, int R, int stride, int pad,
-              Bump& b) {
-  c.cin = cin, c.cout = cout, c.R = R, c.stride = stride, c.pad = pad;
-  c.w = add_param(e.params, e.pc, name, {cout, cin, R, R});
-  c.wf = b.take((size_t)cout * R * R * cin * 2);
-  c.wd = b.take((size_t)cin * R * R * cout * 2);
-}
-
-void add_linear(LrwEngine& e, LinRef& l, const std::string& wname, const std::string& bname, int N, int K, Bump& b) {
-  l.N = N, l.K = K;
-  l.w = add_param(e.params, e.pc, wname, {N, K});
-  l.b = bname.empty() ? -1 : add_param(e.params, e.pc, bname, {N});
-  l.ldt = (N + 63) / 64 * 64;
-  l.wb = b.take((size_t)N * K * 2);
-  l.wt = b.take((size_t)K * l.ldt * 2);
-}
-
-int conv_out(int h, int k, int s, int p) { return (h + 2 * p - k) / s + 1; }
-
-}  // namespace
 
 static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.params.clear(), e.buffers.clear();
@@ -209,44 +60,13 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   SVSR_REQUIRE((c.audio_alignment * c.vq_groups * c.audio_vocab) % 64 == 0,
                "lrw: audio logits per frame (%d) must be a multiple of 64",
                c.audio_alignment * c.vq_groups * c.audio_vocab);
-  e.N = c.B * c.T;
   e.M = c.B * (c.T + 1);
-  e.H0 = conv_out(c.H, 7, 2, 3);
-  e.H1 = conv_out(e.H0, 3, 2, 1);
   Bump b;
 
   // ---- parameters (reference state-dict names) + packed operand storage ----
-  e.stem_conv.cin = 1, e.stem_conv.cout = 64;
-  e.stem_conv.w = add_param(e.params, e.pc, "stem3d.0.weight", {64, 1, 5, 7, 7});
-  e.stem_conv.wf = b.take(64 * 320 * 2);
-  add_bn(e, e.stem_bn, "stem3d.1", 64, b);
-  int cin = 64, h = e.H1;
-  const int widths[4] = {64, 128, 256, 512};
-  for (int li = 0; li < 4; ++li) {
-    for (int bi = 0; bi < 2; ++bi) {
-      BlockRef& blk = e.blocks[li * 2 + bi];
-      const std::string pre = "resnet.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
-      blk.cin = bi == 0 ? cin : widths[li];
-      blk.cout = widths[li];
-      blk.stride = (bi == 0 && li > 0) ? 2 : 1;
-      blk.Hin = h;
-      blk.Hout = conv_out(h, 3, blk.stride, 1);
-      blk.ds = (bi == 0 && li > 0);
-      add_conv(e, blk.conv1, pre + ".conv1.weight", blk.cin, blk.cout, 3, blk.stride, 1, b);
-      add_bn(e, blk.bn1, pre + ".bn1", blk.cout, b);
-      add_conv(e, blk.conv2, pre + ".conv2.weight", blk.cout, blk.cout, 3, 1, 1, b);
-      add_bn(e, blk.bn2, pre + ".bn2", blk.cout, b);
-      if (blk.ds) {
-        add_conv(e, blk.convds, pre + ".downsample.0.weight", blk.cin, blk.cout, 1, blk.stride, 0, b);
-        add_bn(e, blk.bnds, pre + ".downsample.1", blk.cout, b);
-      }
-      h = blk.Hout;
-      const size_t act = (size_t)e.N * blk.Hout * blk.Hout * blk.cout * 2;
-      blk.c1 = b.take(act), blk.a1 = b.take(act), blk.c2 = b.take(act), blk.out = b.take(act);
-      blk.cds = blk.ds ? b.take(act) : 0;
-    }
-    cin = widths[li];
-  }
+  e.fe.B = c.B, e.fe.T = c.T, e.fe.H = c.H, e.fe.swish = 0;
+  e.bn_eps = c.bn_eps, e.bn_momentum = c.bn_momentum;
+  RC(frontend_build(e, e.fe, "stem3d.0.weight", "stem3d.1", "resnet", b));
   e.cls_off = add_param(e.params, e.pc, "cls_token", {1, 1, c.dim});
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   e.enc.resize(c.depth);
@@ -277,12 +97,9 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.cat_ld = (c.num_labels + 63) / 64 * 64;
 
   // ---- activations ----
-  const size_t n0 = (size_t)e.N * e.H0 * e.H0 * 64;
-  e.patches = b.take(n0 * 2);
-  e.y0 = b.take(n0 * 2);
-  const size_t n1 = (size_t)e.N * e.H1 * e.H1 * 64;
-  e.x1 = b.take(n1 * 2);
-  e.argmax = b.take(n1);
+  frontend_alloc(e, e.fe, b);
+  const size_t n0 = (size_t)e.N * e.fe.H0 * e.fe.H0 * 64;
+  const size_t n1 = (size_t)e.N * e.fe.H1 * e.fe.H1 * 64;
   e.xs = b.take((size_t)(2 * c.depth + 1) * e.M * D * 4);
   e.lastb_cls = b.take((size_t)c.B * D * 2);
   e.lastb_frames = b.take((size_t)e.N * D * 2);
@@ -293,27 +110,6 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.acc = b.take(8 * sizeof(double));
   e.bad_token = b.take(sizeof(int));
   e.rot = b.take((size_t)(c.T + 1) * 32 * 4);
-  // BN statistic accumulators (fp64): forward and backward slot per BN, zeroed once per step
-  {
-    Bump sb;
-    auto slot = [&](BnRef& bn) {
-      bn.stats_f = sb.take(2 * bn.C * sizeof(double));
-      bn.stats_b = sb.take(2 * bn.C * sizeof(double));
-    };
-    slot(e.stem_bn);
-    for (auto& blk : e.blocks) {
-      slot(blk.bn1), slot(blk.bn2);
-      if (blk.ds) slot(blk.bnds);
-    }
-    e.stats_arena_bytes = sb.off;
-    e.stats_arena = b.take(sb.off);
-    auto fix = [&](BnRef& bn) { bn.stats_f += e.stats_arena, bn.stats_b += e.stats_arena; };
-    fix(e.stem_bn);
-    for (auto& blk : e.blocks) {
-      fix(blk.bn1), fix(blk.bn2);
-      if (blk.ds) fix(blk.bnds);
-    }
-  }
   // ---- backward scratch ----
   e.dx = b.take((size_t)e.M * D * 4);
   for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * D * 2);
@@ -322,9 +118,6 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.t_dyn = b.take((size_t)e.M * D * 2);
   e.t_do = b.take((size_t)e.M * inner * 2);
   for (int i = 0; i < 2; ++i) e.t_dqkv[i] = b.take((size_t)e.M * 3 * inner * 2);
-  for (int i = 0; i < 9; ++i) e.gbuf[i] = b.take(n1 * 2);
-  e.stem_dz = b.take(n0 * 2);
-  e.wgrad_tmp = b.take((size_t)9 * 512 * 512 * 4);
   e.pack_jobs = b.take(128 * sizeof(PackJob));
   e.ws_bytes = b.off;
   {  // parity-mode scratch (only allocated by the caller when forward_precise is used)
@@ -358,109 +151,10 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// small launch helpers
-// ------------------------------------------------------------------------------------------------
-static int linear_fwd(const LrwEngine& e, const bf16* x, int M, const LinRef& l, void* out, int ldc, int out_fp32,
-                      const void* resid, int resid_fp32, cudaStream_t s) {
-  IgemmProblem p;
-  p.a = x, p.a_N = M, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
-  p.o_N = M;
-  p.b = e.ws<bf16>(l.wb), p.b_rows = l.N, p.b_cols = l.K;
-  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
-  p.bias = l.b >= 0 ? e.P + l.b : nullptr;
-  p.resid = resid, p.resid_fp32 = resid_fp32;
-  return igemm_launch(p, s);
-}
-// dx[M, K] = dy[M, N(ld = ldy)] . W   (uses the transposed operand copy)
-static int linear_dgrad(const LrwEngine& e, const bf16* dy, int ldy, int M, const LinRef& l, void* out, int ldc,
-                        int out_fp32, cudaStream_t s) {
-  IgemmProblem p;
-  p.a = dy, p.a_N = M, p.a_C = ldy, p.cin = l.ldt, p.ntaps = 1;
-  p.o_N = M;
-  p.b = e.ws<bf16>(l.wt), p.b_rows = l.K, p.b_cols = l.ldt;
-  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
-  return igemm_launch(p, s);
-}
-static int linear_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, int M, const LinRef& l,
-                        cudaStream_t s) {
-  WgradProblem p;
-  p.a = dy, p.a_N = M, p.a_C = ldy, p.a_cin = l.ldt, p.ntaps = 1;
-  p.b = x, p.b_C = l.K, p.n_cols = l.K;
-  p.k_N = M;
-  p.out = e.G + l.w, p.ldo = l.K, p.m_valid = l.N;
-  RC(wgrad_launch(p, s));
-  if (l.b >= 0) RC(colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s));
-  return SVSR_OK;
-}
-
-static int conv_fwd(const LrwEngine& e, const bf16* x, int Hin, const ConvRef& c, bf16* y, double* bn_stats,
-                    cudaStream_t s) {
-  IgemmProblem p;
-  p.a = x, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = c.cin, p.cin = c.cin, p.stride = c.stride;
-  p.ntaps = c.R * c.R;
-  for (int r = 0; r < c.R; ++r)
-    for (int q = 0; q < c.R; ++q) {
-      const int t = r * c.R + q;
-      p.tap_dh[t] = r - c.pad, p.tap_dw[t] = q - c.pad, p.tap_kbase[t] = t * c.cin;
-    }
-  const int Ho = conv_out(Hin, c.R, c.stride, c.pad);
-  p.o_N = e.N, p.OH = Ho, p.OW = Ho;
-  p.b = e.ws<bf16>(c.wf), p.b_rows = c.cout, p.b_cols = c.R * c.R * c.cin;
-  p.out = y, p.ldc = c.cout, p.o_H = Ho, p.o_W = Ho;
-  p.bn_stats = bn_stats;
-  return igemm_launch(p, s);
-}
-extern "C" int svsr_conv2d_dgrad(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int,
-                                 int, int, void*);
-static int conv_dgrad(const LrwEngine& e, const bf16* dy, int Hin, const ConvRef& c, bf16* dx, const bf16* resid,
-                      cudaStream_t s) {
-  return svsr_conv2d_dgrad(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride, c.pad, 0,
-                           s);
-}
-static int conv_wgrad(const LrwEngine& e, const bf16* x, int Hin, const bf16* dy, const ConvRef& c, cudaStream_t s) {
-  float* tmp = e.ws<float>(e.wgrad_tmp);
-  const size_t n = (size_t)c.R * c.R * c.cin * c.cout;
-  SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, n * 4, s));
-  WgradProblem p;
-  p.a = x, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = c.cin, p.a_cin = c.cin, p.a_stride = c.stride;
-  p.ntaps = c.R * c.R;
-  for (int r = 0; r < c.R; ++r)
-    for (int q = 0; q < c.R; ++q) p.tap_dh[r * c.R + q] = r - c.pad, p.tap_dw[r * c.R + q] = q - c.pad;
-  const int Ho = conv_out(Hin, c.R, c.stride, c.pad);
-  p.b = dy, p.b_C = c.cout, p.n_cols = c.cout;
-  p.k_N = e.N, p.k_H = Ho, p.k_W = Ho;
-  p.out = tmp, p.ldo = c.cout;
-  RC(wgrad_launch(p, s));
-  return unpack_conv_wgrad(tmp, e.G + c.w, c.cout, c.cin, c.R, c.R, s);
-}
-
-// batch statistics were accumulated by the producing conv's epilogue (IgemmProblem::bn_stats)
-static int bn_fwd(const LrwEngine& e, const bf16* x, long long rows, const BnRef& bn, int train, cudaStream_t s) {
-  (void)x;
-  return bn_finalize(e.ws<double>(bn.stats_f), rows, bn.C, e.P + bn.gamma, e.P + bn.beta, e.cfg.bn_eps,
-                     e.cfg.bn_momentum, e.BUF + bn.rmean, e.BUF + bn.rvar, e.ws<float>(bn.coef), train ? 1 : -1, s);
-}
-// full BN backward: returns dc (may alias nothing); optionally emits the relu-masked upstream gradient
-static int bn_bwd(const LrwEngine& e, const bf16* dout, const bf16* relu_ref, const bf16* c, long long rows,
-                  const BnRef& bn, bf16* dc, bf16* gmask_out, cudaStream_t s, int self_mask = 0) {
-  RC(bn_bwd_reduce(dout, relu_ref, c, e.ws<float>(bn.coef), rows, bn.C, e.ws<double>(bn.stats_b), self_mask, s));
-  RC(bn_bwd_finalize(e.ws<double>(bn.stats_b), rows, bn.C, e.G + bn.gamma, e.G + bn.beta, e.ws<float>(bn.kcoef), s));
-  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, gmask_out, rows, bn.C,
-                      self_mask, s);
-}
-
-// ------------------------------------------------------------------------------------------------
 static int engine_pack(LrwEngine& e, cudaStream_t s) {
   if (!e.pack_table_ready) {  // build the job table once per binding (pointers are static afterwards)
     std::vector<PackJob> jobs;
-    jobs.push_back({e.P + e.stem_conv.w, e.ws<bf16>(e.stem_conv.wf), nullptr, 2, 0, 0, 0, 0});
-    auto conv = [&](const ConvRef& c) {
-      jobs.push_back({e.P + c.w, e.ws<bf16>(c.wf), e.ws<bf16>(c.wd), 0, c.cout, c.cin, c.R * c.R, 0});
-    };
-    for (auto& blk : e.blocks) {
-      conv(blk.conv1), conv(blk.conv2);
-      if (blk.ds) conv(blk.convds);
-    }
+    frontend_pack_jobs(e, e.fe, jobs);
     auto lin = [&](const LinRef& l) { jobs.push_back({e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), 1, l.N, l.K, l.K, l.ldt}); };
     for (auto& L : e.enc) lin(L.qkv), lin(L.out), lin(L.ff1), lin(L.ff2);
     lin(e.cat), lin(e.aud);
@@ -482,52 +176,12 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
                           unsigned long long dropout_seed, float* metrics, int videos_only, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
-  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.stats_arena), 0, e.stats_arena_bytes, s));
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));  // acc + bad_token
-
-  // ---- stem3d (lightning.py:49-54): 7x7/s2 patch gather, 5-tap temporal implicit GEMM, BN3d+GELU+maxpool ----
-  RC(stem_patch(videos, e.ws<bf16>(e.patches), c.B, c.T, c.H, c.W, s));
-  {
-    IgemmProblem p;
-    p.a = e.ws<bf16>(e.patches), p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 64, p.cin = 64;
-    p.ntaps = 5;
-    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0, p.tap_kbase[kt] = kt * 64;
-    p.o_N = c.B, p.OH = c.T, p.OW = e.H0 * e.H0;
-    p.b = e.ws<bf16>(e.stem_conv.wf), p.b_rows = 64, p.b_cols = 320;
-    p.out = e.ws<bf16>(e.y0), p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
-    p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
-    p.bn_stats = train ? e.ws<double>(e.stem_bn.stats_f) : nullptr;
-    RC(igemm_launch(p, s));
-  }
-  RC(bn_fwd(e, e.ws<bf16>(e.y0), (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
-  RC(stem_bn_gelu_pool(e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), e.ws<bf16>(e.x1), e.ws<uint8_t>(e.argmax), e.N,
-                       e.H0, e.H0, s));
-
-  // ---- resnet.layer1-4 (lightning.py:114-117) ----
-  const bf16* x = e.ws<bf16>(e.x1);
-  for (auto& blk : e.blocks) {
-    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
-    RC(conv_fwd(e, x, blk.Hin, blk.conv1, e.ws<bf16>(blk.c1), train ? e.ws<double>(blk.bn1.stats_f) : nullptr, s));
-    RC(bn_fwd(e, e.ws<bf16>(blk.c1), rows, blk.bn1, train, s));
-    RC(bn_apply(e.ws<bf16>(blk.c1), e.ws<float>(blk.bn1.coef), nullptr, nullptr, 1, e.ws<bf16>(blk.a1), rows, blk.cout,
-                s));
-    RC(conv_fwd(e, e.ws<bf16>(blk.a1), blk.Hout, blk.conv2, e.ws<bf16>(blk.c2),
-                train ? e.ws<double>(blk.bn2.stats_f) : nullptr, s));
-    RC(bn_fwd(e, e.ws<bf16>(blk.c2), rows, blk.bn2, train, s));
-    if (blk.ds) {
-      RC(conv_fwd(e, x, blk.Hin, blk.convds, e.ws<bf16>(blk.cds), train ? e.ws<double>(blk.bnds.stats_f) : nullptr,
-                  s));
-      RC(bn_fwd(e, e.ws<bf16>(blk.cds), rows, blk.bnds, train, s));
-      RC(bn_apply(e.ws<bf16>(blk.c2), e.ws<float>(blk.bn2.coef), e.ws<bf16>(blk.cds), e.ws<float>(blk.bnds.coef), 1,
-                  e.ws<bf16>(blk.out), rows, blk.cout, s));
-    } else {
-      RC(bn_apply(e.ws<bf16>(blk.c2), e.ws<float>(blk.bn2.coef), x, nullptr, 1, e.ws<bf16>(blk.out), rows, blk.cout,
-                  s));
-    }
-    x = e.ws<bf16>(blk.out);
-  }
+  // ---- stem3d + resnet.layer1-4 (lightning.py:49-54,112-117) ----
+  const bf16* x = nullptr;
+  RC(frontend_forward(e, e.fe, videos, train, &x, s));
   // ---- mean((2,3)) + CLS concat (lightning.py:118,148-150) ----
-  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_cls(x, e.P + e.cls_off, e.xs_buf(0), c.B, c.T, HW4, D, s));
   if (videos_only) return SVSR_OK;
 
@@ -627,7 +281,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
   const svsr_lrw_config& c = e.cfg;
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
-  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.stats_arena), 0, e.stats_arena_bytes, s));
+  SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.fe.stats_arena), 0, e.fe.stats_arena_bytes, s));
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));
   RC(rotary_table(e.ws<float>(e.rot), c.T + 1, s));
   // ---- stem ----
@@ -635,25 +289,25 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
   {
     bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
     bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
-    RC(split3_f32(PF(e.p_patches), S3, (long long)e.N * e.H0 * e.H0, 64, s));
-    RC(pack_stem_weight_split(e.P + e.stem_conv.w, W3, s));
+    RC(split3_f32(PF(e.p_patches), S3, (long long)e.N * e.fe.H0 * e.fe.H0, 64, s));
+    RC(pack_stem_weight_split(e.P + e.fe.stem_conv.w, W3, s));
     IgemmProblem p;
-    p.a = S3, p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 192, p.cin = 192;
+    p.a = S3, p.a_N = c.B, p.a_H = c.T, p.a_W = e.fe.H0 * e.fe.H0, p.a_C = 192, p.cin = 192;
     p.ntaps = 5;
     for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0, p.tap_kbase[kt] = kt * 192;
-    p.o_N = c.B, p.OH = c.T, p.OW = e.H0 * e.H0;
+    p.o_N = c.B, p.OH = c.T, p.OW = e.fe.H0 * e.fe.H0;
     p.b = W3, p.b_rows = 64, p.b_cols = 960;
-    p.out = PF(e.p_y0), p.out_fp32 = 1, p.ldc = 64, p.o_H = c.T, p.o_W = e.H0 * e.H0;
-    p.bn_stats = train ? e.ws<double>(e.stem_bn.stats_f) : nullptr;
+    p.out = PF(e.p_y0), p.out_fp32 = 1, p.ldc = 64, p.o_H = c.T, p.o_W = e.fe.H0 * e.fe.H0;
+    p.bn_stats = train ? e.ws<double>(e.fe.stem_bn.stats_f) : nullptr;
     RC(igemm_launch(p, s));
   }
-  RC(precise_bn_coef(e, (long long)e.N * e.H0 * e.H0, e.stem_bn, train, s));
+  RC(precise_bn_coef(e, (long long)e.N * e.fe.H0 * e.fe.H0, e.fe.stem_bn, train, s));
   float* x = PF(e.p_act[0]);
   float* nxt = PF(e.p_act[1]);
   float *C1 = PF(e.p_act[2]), *A1 = PF(e.p_act[3]), *C2 = PF(e.p_act[4]), *CDS = PF(e.p_act[5]);
-  RC(stem_bn_gelu_pool_f32(PF(e.p_y0), e.ws<float>(e.stem_bn.coef), x, e.N, e.H0, e.H0, s));
+  RC(stem_bn_gelu_pool_f32(PF(e.p_y0), e.ws<float>(e.fe.stem_bn.coef), x, e.N, e.fe.H0, e.fe.H0, s));
   // ---- trunk ----
-  for (auto& blk : e.blocks) {
+  for (auto& blk : e.fe.blocks) {
     const long long rows = (long long)e.N * blk.Hout * blk.Hout;
     RC(precise_conv(e, PW, x, blk.Hin, blk.conv1, C1, train ? e.ws<double>(blk.bn1.stats_f) : nullptr, s));
     RC(precise_bn_coef(e, rows, blk.bn1, train, s));
@@ -670,7 +324,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
     float* t = x;
     x = nxt, nxt = t;
   }
-  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   float* xa = PF(e.p_xs[0]);
   float* xb = PF(e.p_xs[1]);
   RC(meanpool_cls_f32(x, e.P + e.cls_off, xa, c.B, c.T, HW4, D, s));
@@ -712,39 +366,6 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
   return SVSR_OK;
 }
 
-// Backward runs on two streams: `s` carries the critical chain (dgrad GEMMs, BatchNorm / attention / norm backward),
-// `e.side` carries every weight-gradient GEMM (+ bias column sums, gradient unpack). The side work only reads
-// tensors the chain has finished (fork event) and the chain never overwrites a tensor the side stream may still be
-// reading: the hazard buffers (dc*, dxb, dh, dqkv) are double buffered and the chain waits for the side stream's
-// unit k-2 before starting unit k (bounded lag). HBM-bound BN kernels thereby overlap tensor-bound wgrad kernels.
-struct SideQueue {
-  LrwEngine& e;
-  cudaStream_t s;
-  int unit = 0;
-  int rc = SVSR_OK;
-  SideQueue(LrwEngine& e_, cudaStream_t s_) : e(e_), s(s_) {}
-  // everything enqueued on `s` so far becomes visible to the side stream
-  int fork() {
-    cudaEvent_t ev = e.ev_fork[e.fork_idx++ & 3];
-    SVSR_CHECK_CUDA(cudaEventRecord(ev, s));
-    SVSR_CHECK_CUDA(cudaStreamWaitEvent(e.side, ev, 0));
-    return SVSR_OK;
-  }
-  // close unit `unit` on the side stream and make the chain wait for unit-1 (so unit-2's buffers are reusable next)
-  int end_unit() {
-    SVSR_CHECK_CUDA(cudaEventRecord(e.ev_done[unit & 3], e.side));
-    if (unit >= 1) SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, e.ev_done[(unit - 1) & 3], 0));
-    ++unit;
-    return SVSR_OK;
-  }
-  int join() {
-    cudaEvent_t ev = e.ev_done[unit & 3];
-    SVSR_CHECK_CUDA(cudaEventRecord(ev, e.side));
-    SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, ev, 0));
-    return SVSR_OK;
-  }
-};
-
 // stage 0: loss heads + encoder + mean-pool/CLS (completes the gradients of cls_token, encoder and head weights);
 // stage 1: ResNet trunk + stem. stage < 0: both. Each stage joins the side stream before returning.
 static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cudaStream_t s) {
@@ -761,9 +382,7 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   float* dx = e.ws<float>(e.dx);
   SideQueue sq(e, s);
   cudaStream_t w = e.side;  // weight-gradient stream
-  bf16* T0 = e.ws<bf16>(e.gbuf[0]);  // dOut of the current block, later da1
-  bf16* T2 = e.ws<bf16>(e.gbuf[1]);  // relu-masked upstream gradient (identity shortcut branch)
-  bf16* T4 = e.ws<bf16>(e.gbuf[2]);  // dX of the current block
+  bf16* T0 = e.ws<bf16>(e.fe.gbuf[0]);  // d loss / d (last block output): input of frontend_backward
   if (stage <= 0) {
   if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
@@ -834,65 +453,14 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   }
 
   // ---- mean pool / CLS ----
-  const int HW4 = e.blocks[7].Hout * e.blocks[7].Hout;
+  const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, D, s));
   e.bwd_stage0_done = true;
   if (stage == 0) return sq.join();
   }  // stage <= 0
 
-  // ---- resnet trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
-  for (int bi = 7; bi >= 0; --bi) {
-    BlockRef& blk = e.blocks[bi];
-    bf16* DC2 = e.ws<bf16>(e.gbuf[3 + (bi & 1)]);
-    bf16* DC1 = e.ws<bf16>(e.gbuf[5 + (bi & 1)]);
-    bf16* DCD = e.ws<bf16>(e.gbuf[7 + (bi & 1)]);
-    const bf16* xin = bi == 0 ? e.ws<bf16>(e.x1) : e.ws<bf16>(e.blocks[bi - 1].out);
-    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
-    const bf16* out = e.ws<bf16>(blk.out);
-    RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : T2, s));
-    if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
-    RC(sq.fork());  // dc2 (and dcds) complete
-    RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
-    if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
-    RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
-    // bn1 is followed directly by ReLU: mask recomputed from c1 (saves reading a1 in both passes)
-    RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, 1));
-    RC(sq.fork());  // dc1 complete
-    RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
-    if (blk.ds) {
-      SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
-      RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, T4, nullptr, s));
-      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s));
-    } else {
-      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T2, s));
-    }
-    bf16* t = T0;
-    T0 = T4, T4 = t;
-    RC(sq.end_unit());
-  }
-
-  // ---- stem ----
-  bf16* dz = e.ws<bf16>(e.stem_dz);
-  RC(stem_bwd_fused(T0, e.ws<uint8_t>(e.argmax), e.ws<bf16>(e.y0), e.ws<float>(e.stem_bn.coef), e.G + e.stem_bn.gamma,
-                    e.G + e.stem_bn.beta, dz, e.ws<double>(e.stem_bn.stats_b), e.ws<float>(e.stem_bn.kcoef), e.N, e.H0,
-                    e.H0, s));
-  RC(sq.fork());
-  {
-    float* tmp = e.ws<float>(e.wgrad_tmp);
-    SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, 320 * 64 * 4, w));
-    WgradProblem p;
-    p.a = e.ws<bf16>(e.patches), p.a_N = c.B, p.a_H = c.T, p.a_W = e.H0 * e.H0, p.a_C = 64, p.a_cin = 64;
-    p.ntaps = 5;
-    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0;
-    p.b = dz, p.b_C = 64, p.n_cols = 64;
-    p.k_N = c.B, p.k_H = c.T, p.k_W = e.H0 * e.H0;
-    p.out = tmp, p.ldo = 64;
-    p.algo_flops = 2.0 * e.N * e.H0 * e.H0 * 64.0 * 245.0;
-    RC(wgrad_launch(p, w));
-    RC(unpack_stem_wgrad(tmp, e.G + e.stem_conv.w, w));
-  }
-  RC(sq.join());
-  return SVSR_OK;
+  // ---- resnet trunk + stem ----
+  return frontend_backward(e, e.fe, sq, s);
 }
 
 }  // namespace svsr
@@ -919,10 +487,7 @@ int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle) {
 }
 int svsr_lrw_destroy(void* h) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
-  if (e && e->side) {
-    cudaStreamDestroy(e->side);
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(e->ev_fork[i]), cudaEventDestroy(e->ev_done[i]);
-  }
+  if (e) engine_base_destroy(*e);
   delete e;
   return SVSR_OK;
 }
@@ -933,21 +498,11 @@ int64_t svsr_lrw_workspace_bytes(void* h) { return (int64_t)static_cast<LrwEngin
 int svsr_lrw_num_params(void* h) { return (int)static_cast<LrwEngine*>(h)->params.size(); }
 int svsr_lrw_num_buffers(void* h) { return (int)static_cast<LrwEngine*>(h)->buffers.size(); }
 
-static int info(const std::vector<ParamInfo>& v, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset,
-                int* decay) {
-  SVSR_REQUIRE(i >= 0 && i < (int)v.size(), "lrw: tensor index %d out of range", i);
-  *name = v[i].name.c_str();
-  *ndim = v[i].ndim;
-  for (int k = 0; k < 5; ++k) shape[k] = v[i].shape[k];
-  *offset = v[i].offset;
-  if (decay) *decay = v[i].decay;
-  return SVSR_OK;
-}
 int svsr_lrw_param_info(void* h, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset, int* decay) {
-  return info(static_cast<LrwEngine*>(h)->params, i, name, ndim, shape, offset, decay);
+  return tensor_info(static_cast<LrwEngine*>(h)->params, i, name, ndim, shape, offset, decay);
 }
 int svsr_lrw_buffer_info(void* h, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset) {
-  return info(static_cast<LrwEngine*>(h)->buffers, i, name, ndim, shape, offset, nullptr);
+  return tensor_info(static_cast<LrwEngine*>(h)->buffers, i, name, ndim, shape, offset, nullptr);
 }
 int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* workspace, int64_t workspace_bytes) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
@@ -956,16 +511,8 @@ int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* wo
                (long long)workspace_bytes, e->ws_bytes);
   SVSR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0,
                "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
-  e->P = params, e->G = grads, e->BUF = buffers, e->WS = static_cast<uint8_t*>(workspace);
   e->pack_table_ready = false;
-  if (!e->side) {  // first bind happens on the GPU box: create the weight-gradient stream and its events
-    SVSR_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) {
-      SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming));
-      SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
-    }
-  }
-  return SVSR_OK;
+  return engine_base_bind(*e, params, grads, buffers, workspace);
 }
 int svsr_lrw_pack_weights(void* h, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
@@ -1042,13 +589,13 @@ int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* 
   }
   if (n == "logits_audio") return set(e->logits_a, (int64_t)e->N * AGV, 0);
   if (n == "logits_category") return set(e->logits_c, (int64_t)c.B * e->cat_ld, 0);
-  if (n == "stem_conv") return set(e->y0, (int64_t)e->N * e->H0 * e->H0 * 64, 1);
-  if (n == "stem_out") return set(e->x1, (int64_t)e->N * e->H1 * e->H1 * 64, 1);
+  if (n == "stem_conv") return set(e->fe.y0, (int64_t)e->N * e->fe.H0 * e->fe.H0 * 64, 1);
+  if (n == "stem_out") return set(e->fe.x1, (int64_t)e->N * e->fe.H1 * e->fe.H1 * 64, 1);
   if (n == "bad_token") return set(e->bad_token, 1, 3);
   if (n.rfind("block", 0) == 0 && n.size() >= 6) {  // "block<i>.out|c1|a1|c2"
     const int bi = n[5] - '0';
     SVSR_REQUIRE(bi >= 0 && bi < 8 && n.size() > 7, "lrw_tensor: bad block tensor %s", name);
-    const BlockRef& blk = e->blocks[bi];
+    const BlockRef& blk = e->fe.blocks[bi];
     const int64_t ne = (int64_t)e->N * blk.Hout * blk.Hout * blk.cout;
     const std::string f = n.substr(7);
     if (f == "out") return set(blk.out, ne, 1);

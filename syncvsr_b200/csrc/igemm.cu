@@ -27,6 +27,9 @@ struct IgemmKParams {
   int o_H, o_W, o_sh, o_sw, o_oh, o_ow;
   int n_cols;
   float alpha;
+  float bias_scale;
+  int relu;
+  const void* relu_mask;
   double* bn_stats;
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
 };
@@ -239,7 +242,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.bias) {
   #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n_cols) f[j] += __ldg(p.bias + col0 + j);
+            if (col0 + j < p.n_cols) f[j] = fmaf(__ldg(p.bias + col0 + j), p.bias_scale, f[j]);
         }
         const bool full_chunk = (col0 + 32 <= p.n_cols);
         if (p.resid && row_valid) {
@@ -271,6 +274,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n_cols) f[j] += __bfloat162float(rp[j]);
             }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.relu_mask && row_valid) {
+          const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.relu_mask) + row_off + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = reinterpret_cast<const uint4*>(mp)[j];
+              const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+              f[8 * j] = a.x > 0.f ? f[8 * j] : 0.f, f[8 * j + 1] = a.y > 0.f ? f[8 * j + 1] : 0.f;
+              f[8 * j + 2] = b.x > 0.f ? f[8 * j + 2] : 0.f, f[8 * j + 3] = b.y > 0.f ? f[8 * j + 3] : 0.f;
+              f[8 * j + 4] = c.x > 0.f ? f[8 * j + 4] : 0.f, f[8 * j + 5] = c.y > 0.f ? f[8 * j + 5] : 0.f;
+              f[8 * j + 6] = d.x > 0.f ? f[8 * j + 6] : 0.f, f[8 * j + 7] = d.y > 0.f ? f[8 * j + 7] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n_cols) f[j] = __bfloat162float(mp[j]) > 0.f ? f[j] : 0.f;
           }
         }
         if (p.out_fp32) {
@@ -475,6 +500,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.o_H = p.o_H, kp.o_W = p.o_W, kp.o_sh = p.o_sh, kp.o_sw = p.o_sw, kp.o_oh = p.o_oh, kp.o_ow = p.o_ow;
   kp.n_cols = p.b_rows;
   kp.alpha = p.alpha;
+  kp.bias_scale = p.bias_scale, kp.relu = p.relu, kp.relu_mask = p.relu_mask;
   kp.bn_stats = p.bn_stats;
   SVSR_REQUIRE(!p.bn_stats || p.b_rows <= 512, "igemm: fused BN statistics support at most 512 output channels");
 

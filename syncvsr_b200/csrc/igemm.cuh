@@ -41,7 +41,11 @@ struct IgemmProblem {
   const float* bias = nullptr;  // [b_rows] fp32 or null
   const void* resid = nullptr;  // same geometry as out (pitch ldc, offset c_off), or null
   int resid_fp32 = 0;
-  float alpha = 1.0f;  // out = alpha*acc (+bias) (+resid)
+  float alpha = 1.0f;  // out = act(alpha*acc (+bias_scale*bias) (+resid)) (* [relu_mask > 0])
+  float bias_scale = 1.0f;
+  int relu = 0;                     // apply ReLU last (Conformer FFN w_1: positionwise_feed_forward.py:28-30)
+  const void* relu_mask = nullptr;  // bf16, same geometry as out: zero the result where mask <= 0 (ReLU backward fused
+                                    // into the input-gradient GEMM of the following Linear)
   // optional fused BatchNorm statistics: fp64 [2][b_rows] accumulators (+=): per-output-channel sum and sum of
   // squares of the fp32 accumulators over all valid pixels (train-mode BN of the conv output, lightning.py:51)
   double* bn_stats = nullptr;
