@@ -2,7 +2,8 @@
  *
  * The reference (KAIST-AILab/SyncVSR) is pure Python: its "FFI" for this path is the set of torch.nn
  * calls made by LRW/video/src/lightning.py:49-55,82,107-119,133-191 (stem3d, resnet.layer1-4, encoder,
- * audio_projection, category_classifier, the two cross-entropies). Each entry point below replaces one
+ * audio_projection, category_classifier, the two cross-entropies) and, for the sentence-level model, by
+ * LRS/video/espnet/nets/pytorch_backend/e2e_asr_transformer.py:186-227 and the modules it calls. Each entry point below replaces one
  * (or a fused group) of those library calls; the file:line of the call it replaces is cited per symbol.
  *
  * Conventions
@@ -187,6 +188,100 @@ int svsr_lrw_backward_stage(void* handle, const float* grad_scale, int stage, vo
 int svsr_lrw_early_grad_region(void* handle, int64_t* begin, int64_t* end);
 /* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */
 int svsr_lrw_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LRS sentence-level operators (reference: LRS/video/espnet/nets/pytorch_backend/, paths below relative to it).
+ * --------------------------------------------------------------------------------------------------------- */
+/* transformer/layer_norm.py:12-33 (eps 1e-12): y = (x-mean)*rstd*gamma+beta over the last dim D (multiple of 128,
+ * <= 1024); x fp32 [M,D]; y_bf16 and/or y_f32; stats fp32 [M,2] = mean, rstd (saved for backward). */
+int svsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* stats,
+                       int M, int D, float eps, void* stream);
+/* dy is bf16 (dy_f32 NULL) or fp32 (may alias dx); dx = or += (accumulate); dgamma/dbeta += . */
+int svsr_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma, const float* stats,
+                       float* dx, int accumulate, float* dgamma, float* dbeta, int M, int D, void* stream);
+/* transformer/convolution.py:61 GLU over channels: u[M,C] = h[:, :C] * sigmoid(h[:, C:]) and its backward */
+int svsr_glu_fwd(const void* h, void* u, int64_t M, int C, void* stream);
+int svsr_glu_bwd(const void* h, const void* du, void* dh, int64_t M, int C, void* stream);
+/* transformer/convolution.py:40-48,64 depthwise Conv1d along time: x,y bf16 [B,T,C]; w fp32 [C,K] (K odd <= 31);
+ * flip=1 applies the reversed kernel (input gradient). wgrad: dw[C,K] +=, dbias[C] += . */
+int svsr_dwconv1d_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K, int flip,
+                      void* stream);
+int svsr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int B, int T, int C, int K, void* stream);
+/* BatchNorm1d column reductions over [rows, C] (C % 64 == 0; convolution.py:49,65): mode 0: stats[0..C) += sum x,
+ * stats[C..2C) += sum x^2; mode 1: g = dout * swish'(x*scale+shift), stats += sum g, sum g*xhat (coef fp32 [4][C]). */
+int svsr_bn_col_reduce(const void* x, const void* dout, const float* coef, int64_t rows, int C, double* stats, int mode,
+                       void* stream);
+/* Multi-head attention core, d_k = 64 (transformer/attention.py:38-108 and RelPositionMultiHeadedAttention 192-278 with
+ * rel_shift as the index map bd[i,j] = raw[i, j-i+Tk-1]): scores = scale*((q+u).k_j + (q+v).p[j-i+Tk-1]); keys
+ * j >= klen[b] and (causal) j > i masked; softmax with masked probabilities zero; . V. q/k/v/o bf16 row-major with
+ * pitches ld*, head h in columns [h*64, h*64+64); p bf16 [2Tk-1, ldp] or NULL; bias_u/v fp32 [H,64] or NULL;
+ * klen int32 [B] or NULL; lse fp32 [B,H,Tq] (saved for backward). */
+int svsr_attention_core_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
+                            int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
+                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, void* stream);
+/* dq/dk/dv bf16 (pitches as q/k/v); dp fp32 [2Tk-1, H*64] +=; dbias_u/v fp32 [H,64] +=;
+ * scratch: svsr_attention_scratch_bytes(B,H,Tq,Tk) bytes. */
+int64_t svsr_attention_scratch_bytes(int B, int H, int Tq, int Tk);
+int svsr_attention_core_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
+                            int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
+                            int H, int Tq, int Tk, float scale, const void* o, int ldo, const float* lse,
+                            const void* d_o, void* dq, void* dk, void* dv, float* dp, float* dbias_u, float* dbias_v,
+                            void* scratch, void* stream);
+/* ctc.py:64-73,83-151: log_softmax + CTCLoss(reduction="sum", zero_infinity=True), blank 0. logits fp32 [B*T, ld]
+ * (V valid columns); labels int64 [B,Lmax] padded with -1; in_len int32 [B]. acc[slot] += sum_b nll_b (fp64);
+ * dlogits bf16 [B*T, ld] (optional) = dscale * d(sum nll)/dlogits. scratch: svsr_ctc_scratch_bytes(B,T,Lmax). */
+int64_t svsr_ctc_scratch_bytes(int B, int T, int Lmax);
+int svsr_ctc_loss(const float* logits, int ld, int V, const int64_t* labels, int Lmax, const int* in_len, int B, int T,
+                  void* dlogits, double* acc, int slot, float dscale, void* scratch, void* stream);
+/* transformer/label_smoothing_loss.py:41-63 (normalize_length=False) + nets_utils.py:303 th_accuracy: logits fp32
+ * [rows, ld]; target int64 [rows], -1 ignored. acc[slot] += sum KL, acc[slot+1] += #correct, acc[slot+2] += #scored;
+ * dlogits bf16 [rows, ld] (optional) = dscale * (softmax - smoothed one-hot). */
+int svsr_label_smoothing_loss(const float* logits, int ld, int V, const int64_t* target, int rows, float smoothing,
+                              void* dlogits, double* acc, int slot, float dscale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LRS sentence-level model step executor: E2E.forward (e2e_asr_transformer.py:186-227) and its backward. Same
+ * arena conventions as the LRW executor; parameter names are the reference's state-dict keys
+ * (encoder.frontend.*, encoder.embed.0.*, encoder.encoders.N.*, encoder.after_norm.*, decoder.*, ctc.ctc_lo.*,
+ * audio_classifier.*). linear_q/k/v of every attention are adjacent so that they run as one GEMM.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct svsr_lrs_config {
+  int B, T, H, W;               /* clips per step on this GPU, padded frames per clip, crop height/width */
+  int adim, aheads, eunits, elayers; /* model.visual_backbone.{adim,aheads,eunits,elayers} (lrs2.yaml:16-19); d_k = 64 */
+  int dlayers, dunits;          /* decoder depth / FFN width (ddim == adim, dheads == aheads) */
+  int odim;                     /* vocabulary incl. <blank> = 0 and <sos/eos> = odim-1 */
+  int cnn_kernel;               /* cnn_module_kernel (31) */
+  int audio_alignment, vq_groups, audio_vocab; /* e2e_asr_transformer.py:130-160; alignment 0 = codec None */
+  int Lmax;                     /* longest decoder input (label length + 1) the workspace is sized for */
+  float mtlalpha, lsm_weight, audio_weight;    /* lrs2.yaml:15,34,36 */
+  float bn_eps, bn_momentum;
+} svsr_lrs_config;
+
+int svsr_lrs_create(const svsr_lrs_config* cfg, void** handle);
+int svsr_lrs_destroy(void* handle);
+int64_t svsr_lrs_param_count(void* handle);
+int64_t svsr_lrs_decay_count(void* handle);
+int64_t svsr_lrs_buffer_count(void* handle);
+int64_t svsr_lrs_workspace_bytes(void* handle);
+int svsr_lrs_num_params(void* handle);
+int svsr_lrs_num_buffers(void* handle);
+int svsr_lrs_param_info(void* handle, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset, int* decay);
+int svsr_lrs_buffer_info(void* handle, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset);
+int svsr_lrs_bind(void* handle, float* params, float* grads, float* buffers, void* workspace, int64_t workspace_bytes);
+int svsr_lrs_pack_weights(void* handle, void* stream);
+/* x fp32 [B,T,1,H,W]; lengths int64 [B]; tokens int64 [B, >=T*A, G] (batch stride tok_stride_b) or NULL (no audio
+ * loss); label int64 [B,label_len] padded with -1 (sos/eos are added on the device, add_sos_eos.py:12-31).
+ * metrics (device fp32[5]) = loss, loss_ctc, loss_att, loss_audio, acc  (e2e_asr_transformer.py:227). */
+int svsr_lrs_forward(void* handle, const float* x, const int64_t* lengths, const int64_t* tokens, int64_t tok_stride_b,
+                     const int64_t* label, int label_len, int train, float* metrics, void* stream);
+/* Encoder.forward only (transformer/encoder.py:257-289; called directly by inference, LRS/video/lightning.py:100):
+ * fills "encoder_out" fp32 [B,T,adim]. lengths may be NULL (masks=None). */
+int svsr_lrs_encode(void* handle, const float* x, const int64_t* lengths, int train, void* stream);
+/* (*grad_scale) * d loss / d params accumulated (+=) into the gradient arena; one backward per (train) forward. */
+int svsr_lrs_backward(void* handle, const float* grad_scale, void* stream);
+/* named tensors: encoder_out, embed_out, frontend, logits_audio, ctc_logits, pred, ys_in, ys_out, layer<i>.x<k>;
+ * dtype 0=f32 1=bf16 2=u8 3=i32 4=i64 */
+int svsr_lrs_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
 
 /* Fused global-norm clip + AdamW over the flat arenas (lightning.py:216-221; Trainer gradient_clip_val). The arena
  * is [decayed | non-decayed]: the first n_decay elements get weight decay. grad_div divides gradients first (world

@@ -5,6 +5,7 @@
 #include "elementwise.cuh"
 #include "encoder.cuh"
 #include "heads.cuh"
+#include "conformer.cuh"
 
 using namespace svsr;
 typedef __nv_bfloat16 bf16;
@@ -110,6 +111,82 @@ int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const f
                      float eps, void* dlogits, int ldd, double* acc, float dscale, void* stream) {
   return category_ce(logits, ld, reinterpret_cast<const long long*>(labels), soft_labels, B, C, eps,
                      static_cast<bf16*>(dlogits), ldd, acc, dscale, ST(stream));
+}
+
+// ---- LRS sentence-level operators (csrc/conformer.cu) ----
+int svsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* stats,
+                       int M, int D, float eps, void* stream) {
+  return layernorm_fwd(x, gamma, beta, static_cast<bf16*>(y_bf16), y_f32, stats, M, D, eps, ST(stream));
+}
+int svsr_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma, const float* stats,
+                       float* dx, int accumulate, float* dgamma, float* dbeta, int M, int D, void* stream) {
+  return layernorm_bwd(static_cast<const bf16*>(dy_bf16), dy_f32, x, gamma, stats, dx, accumulate, dgamma, dbeta, M, D,
+                       ST(stream));
+}
+int svsr_glu_fwd(const void* h, void* u, int64_t M, int C, void* stream) {
+  return glu_fwd(static_cast<const bf16*>(h), static_cast<bf16*>(u), M, C, ST(stream));
+}
+int svsr_glu_bwd(const void* h, const void* du, void* dh, int64_t M, int C, void* stream) {
+  return glu_bwd(static_cast<const bf16*>(h), static_cast<const bf16*>(du), static_cast<bf16*>(dh), M, C, ST(stream));
+}
+int svsr_dwconv1d_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K, int flip,
+                      void* stream) {
+  return dwconv1d_fwd(static_cast<const bf16*>(x), w, bias, static_cast<bf16*>(y), B, T, C, K, flip, ST(stream));
+}
+int svsr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int B, int T, int C, int K,
+                        void* stream) {
+  return dwconv1d_wgrad(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), dw, dbias, B, T, C, K, ST(stream));
+}
+int svsr_bn_col_reduce(const void* x, const void* dout, const float* coef, int64_t rows, int C, double* stats, int mode,
+                       void* stream) {
+  return bn_col_reduce(static_cast<const bf16*>(x), static_cast<const bf16*>(dout), coef, rows, C, stats, mode,
+                       ST(stream));
+}
+static void fill_attn(AttnProblem& a, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                      const void* p, int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal,
+                      int B, int H, int Tq, int Tk, float scale, const void* o, int ldo, const float* lse) {
+  a.q = static_cast<const bf16*>(q), a.k = static_cast<const bf16*>(k), a.v = static_cast<const bf16*>(v);
+  a.ldq = ldq, a.ldk = ldk, a.ldv = ldv;
+  a.p = static_cast<const bf16*>(p), a.ldp = ldp;
+  a.bias_u = bias_u, a.bias_v = bias_v, a.klen = klen, a.causal = causal;
+  a.B = B, a.H = H, a.Tq = Tq, a.Tk = Tk, a.scale = scale;
+  a.o = const_cast<bf16*>(static_cast<const bf16*>(o)), a.ldo = ldo, a.lse = const_cast<float*>(lse);
+}
+int svsr_attention_core_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
+                            int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
+                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, void* stream) {
+  AttnProblem a;
+  fill_attn(a, q, ldq, k, ldk, v, ldv, p, ldp, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale, o, ldo, lse);
+  return attention_core_fwd(a, ST(stream));
+}
+int64_t svsr_attention_scratch_bytes(int B, int H, int Tq, int Tk) {
+  return (int64_t)attention_scratch_bytes(B, H, Tq, Tk);
+}
+int svsr_attention_core_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
+                            int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
+                            int H, int Tq, int Tk, float scale, const void* o, int ldo, const float* lse,
+                            const void* d_o, void* dq, void* dk, void* dv, float* dp, float* dbias_u, float* dbias_v,
+                            void* scratch, void* stream) {
+  AttnProblem a;
+  fill_attn(a, q, ldq, k, ldk, v, ldv, p, ldp, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale, o, ldo, lse);
+  AttnGrads g;
+  g.d_o = static_cast<const bf16*>(d_o);
+  g.dq = static_cast<bf16*>(dq), g.dk = static_cast<bf16*>(dk), g.dv = static_cast<bf16*>(dv);
+  g.lddq = ldq, g.lddk = ldk, g.lddv = ldv;
+  g.dp = dp, g.dbias_u = dbias_u, g.dbias_v = dbias_v;
+  g.scratch = static_cast<float*>(scratch);
+  return attention_core_bwd(a, g, ST(stream));
+}
+int64_t svsr_ctc_scratch_bytes(int B, int T, int Lmax) { return (int64_t)ctc_scratch_bytes(B, T, Lmax); }
+int svsr_ctc_loss(const float* logits, int ld, int V, const int64_t* labels, int Lmax, const int* in_len, int B, int T,
+                  void* dlogits, double* acc, int slot, float dscale, void* scratch, void* stream) {
+  return ctc_loss_fwd_bwd(logits, ld, V, reinterpret_cast<const long long*>(labels), Lmax, in_len, B, T,
+                          static_cast<bf16*>(dlogits), acc, slot, dscale, static_cast<float*>(scratch), ST(stream));
+}
+int svsr_label_smoothing_loss(const float* logits, int ld, int V, const int64_t* target, int rows, float smoothing,
+                              void* dlogits, double* acc, int slot, float dscale, void* stream) {
+  return label_smoothing_loss(logits, ld, V, reinterpret_cast<const long long*>(target), rows, smoothing,
+                              static_cast<bf16*>(dlogits), acc, slot, dscale, ST(stream));
 }
 
 }  // extern "C"

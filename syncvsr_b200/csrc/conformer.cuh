@@ -72,8 +72,8 @@ size_t attention_scratch_bytes(int B, int H, int Tq, int Tk);
 // rel: row r of [2T-1, D] encodes relative position T-1-r (bf16, GEMM operand of linear_pos)
 int rel_pos_table(__nv_bfloat16* pe, int T, int D, cudaStream_t s);
 // decoder input: x[b,l,:] = emb[tok[b,l]] * sqrt(D) + pe_abs[l]   (fp32 stream) and its weight gradient (+=, atomics)
-int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, cudaStream_t s);
-int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, cudaStream_t s);
+int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, int V, cudaStream_t s);
+int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, int V, cudaStream_t s);
 
 // ---- CTC (ctc.py:64-73,83-151: log_softmax + CTCLoss(reduction=sum, zero_infinity) / batch) ------------------------------
 // logits fp32 [B*T, ld] (V valid columns); labels int64 [B, Lmax] padded with -1; in_len int [B].
@@ -89,9 +89,18 @@ size_t ctc_scratch_bytes(int B, int T, int Lmax);
 int label_smoothing_loss(const float* logits, int ld, int V, const long long* target, int rows, float smoothing,
                          __nv_bfloat16* dlogits, double* acc, int slot, float dscale, cudaStream_t s);
 
+// out[0..4] = loss, loss_ctc, loss_att, loss_audio, acc (e2e_asr_transformer.py:218-227) from the fp64 accumulators
+// acc[0] audio nll sum, acc[1] ctc nll sum, acc[2] KL sum, acc[3] #correct, acc[4] #scored
+int lrs_finalize_metrics(const double* acc, float* out, int B, long long audio_rows, float mtlalpha, float audio_weight,
+                         int has_audio, cudaStream_t s);
+
+// AdaptiveAvgPool2d(1) of the trunk output (resnet.py:126,175-176): feats[n,:] = mean_hw a[n,hw,:] (bf16) and backward
+int meanpool_bf16(const __nv_bfloat16* a, __nv_bfloat16* out, long long N, int HW, int C, cudaStream_t s);
+int meanpool_bf16_bwd(const __nv_bfloat16* df, __nv_bfloat16* dout, long long N, int HW, int C, cudaStream_t s);
+
 // small helpers
-int add_f32(float* dst, const float* src, long long n, cudaStream_t s);                   // dst += src
-int cast_f32_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);         // y = bf16(x)
-int lengths_i64_to_i32(const long long* in, int* out, int n, int maxv, cudaStream_t s);   // clamp to [0, maxv]
+int add_f32(float* dst, const float* src, long long n, cudaStream_t s);                                 // dst += src
+int cast_scale_f32_bf16(const float* x, __nv_bfloat16* y, long long n, float alpha, cudaStream_t s);     // y = bf16(alpha*x)
+int lengths_i64_to_i32(const long long* in, int* out, int n, int maxv, cudaStream_t s);                 // clamp to [0, maxv]
 
 }  // namespace svsr

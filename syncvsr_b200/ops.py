@@ -322,3 +322,140 @@ def conv2d_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, R: int, S: int
                                           _i(Cout), _i(R), _i(S), _i(stride), _i(pad), stream_ptr()),
           "svsr_conv2d_fprop_bnstats")
     return y, stats
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LRS sentence-level operators (csrc/conformer.cu)
+# ----------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-12):
+    """x fp32 [M,D] -> (y bf16, y fp32, stats fp32 [M,2])."""
+    _req(x, torch.float32, "x")
+    M, D = x.shape
+    yb = torch.empty(M, D, device=x.device, dtype=torch.bfloat16)
+    yf = torch.empty(M, D, device=x.device, dtype=torch.float32)
+    stats = torch.empty(M, 2, device=x.device, dtype=torch.float32)
+    check(lib().svsr_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(yb), ptr(yf), ptr(stats), C.c_int(M), C.c_int(D),
+                                   C.c_float(eps), stream_ptr()), "svsr_layernorm_fwd")
+    return yb, yf, stats
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, stats: torch.Tensor,
+                  dx: torch.Tensor | None = None):
+    """dy bf16 or fp32 [M,D]; returns (dx fp32 [= or += if given], dgamma, dbeta)."""
+    M, D = x.shape
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty(M, D, device=x.device, dtype=torch.float32)
+    dg = torch.zeros(D, device=x.device)
+    db = torch.zeros(D, device=x.device)
+    is_f32 = dy.dtype == torch.float32
+    check(lib().svsr_layernorm_bwd(ptr(None if is_f32 else dy), ptr(dy if is_f32 else None), ptr(x), ptr(gamma),
+                                   ptr(stats), ptr(dx), C.c_int(int(acc)), ptr(dg), ptr(db), C.c_int(M), C.c_int(D),
+                                   stream_ptr()), "svsr_layernorm_bwd")
+    return dx, dg, db
+
+
+def glu_fwd(h: torch.Tensor) -> torch.Tensor:
+    _req(h, torch.bfloat16, "h")
+    M, C2 = h.shape
+    u = torch.empty(M, C2 // 2, device=h.device, dtype=torch.bfloat16)
+    check(lib().svsr_glu_fwd(ptr(h), ptr(u), C.c_int64(M), C.c_int(C2 // 2), stream_ptr()), "svsr_glu_fwd")
+    return u
+
+
+def glu_bwd(h: torch.Tensor, du: torch.Tensor) -> torch.Tensor:
+    _req(h, torch.bfloat16, "h"), _req(du, torch.bfloat16, "du")
+    dh = torch.empty_like(h)
+    check(lib().svsr_glu_bwd(ptr(h), ptr(du), ptr(dh), C.c_int64(h.shape[0]), C.c_int(h.shape[1] // 2), stream_ptr()),
+          "svsr_glu_bwd")
+    return dh
+
+
+def dwconv1d_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, flip: bool = False) -> torch.Tensor:
+    """x bf16 [B,T,C]; w fp32 [C,K]."""
+    _req(x, torch.bfloat16, "x"), _req(w, torch.float32, "w")
+    B, T, Cc = x.shape
+    y = torch.empty_like(x)
+    check(lib().svsr_dwconv1d_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), C.c_int(B), C.c_int(T), C.c_int(Cc),
+                                  C.c_int(w.shape[1]), C.c_int(int(flip)), stream_ptr()), "svsr_dwconv1d_fwd")
+    return y
+
+
+def dwconv1d_wgrad(x: torch.Tensor, dy: torch.Tensor, K: int):
+    B, T, Cc = x.shape
+    dw = torch.zeros(Cc, K, device=x.device)
+    db = torch.zeros(Cc, device=x.device)
+    check(lib().svsr_dwconv1d_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), C.c_int(B), C.c_int(T), C.c_int(Cc), C.c_int(K),
+                                    stream_ptr()), "svsr_dwconv1d_wgrad")
+    return dw, db
+
+
+def bn_col_reduce(x: torch.Tensor, dout: torch.Tensor | None = None, coef: torch.Tensor | None = None) -> torch.Tensor:
+    """x bf16 [rows, C] -> fp64 [2, C] (mode 0: sum, sum of squares; mode 1 with dout/coef: sum g, sum g*xhat)."""
+    rows, Cc = x.shape
+    stats = torch.zeros(2, Cc, device=x.device, dtype=torch.float64)
+    check(lib().svsr_bn_col_reduce(ptr(x), ptr(dout), ptr(coef), C.c_int64(rows), C.c_int(Cc), ptr(stats),
+                                   C.c_int(0 if dout is None else 1), stream_ptr()), "svsr_bn_col_reduce")
+    return stats
+
+
+def _attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale):
+    return (ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(v), C.c_int(v.stride(0)), ptr(p),
+            C.c_int(p.stride(0) if p is not None else 0), ptr(bias_u), ptr(bias_v), ptr(klen), C.c_int(int(causal)),
+            C.c_int(B), C.c_int(H), C.c_int(Tq), C.c_int(Tk), C.c_float(scale))
+
+
+def attention_core_fwd(q, k, v, B: int, H: int, Tq: int, Tk: int, p=None, bias_u=None, bias_v=None, klen=None,
+                       causal: bool = False, scale: float = 0.125):
+    """q [B*Tq, >=H*64] / k, v [B*Tk, ...] bf16 row-major VIEWS (row pitch = stride(0)); returns (o bf16 [B*Tq,H*64], lse)."""
+    o = torch.empty(B * Tq, H * 64, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Tq, device=q.device, dtype=torch.float32)
+    check(lib().svsr_attention_core_fwd(*_attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale),
+                                        ptr(o), C.c_int(H * 64), ptr(lse), stream_ptr()), "svsr_attention_core_fwd")
+    return o, lse
+
+
+def attention_core_bwd(q, k, v, o, lse, d_o, B: int, H: int, Tq: int, Tk: int, p=None, bias_u=None, bias_v=None,
+                       klen=None, causal: bool = False, scale: float = 0.125):
+    """Returns dq, dk, dv (bf16, same pitches as q/k/v: pass contiguous-row views), dp fp32, dbias_u, dbias_v."""
+    L = lib()
+    L.svsr_attention_scratch_bytes.restype = C.c_int64
+    dq = torch.zeros(q.shape[0], q.stride(0), device=q.device, dtype=torch.bfloat16)
+    dk = torch.zeros(k.shape[0], k.stride(0), device=q.device, dtype=torch.bfloat16)
+    dv = torch.zeros(v.shape[0], v.stride(0), device=q.device, dtype=torch.bfloat16)
+    dp = torch.zeros(2 * Tk - 1, H * 64, device=q.device) if p is not None else None
+    dbu = torch.zeros(H, 64, device=q.device) if bias_u is not None else None
+    dbv = torch.zeros(H, 64, device=q.device) if bias_v is not None else None
+    scratch = torch.empty(L.svsr_attention_scratch_bytes(B, H, Tq, Tk), device=q.device, dtype=torch.uint8)
+    check(L.svsr_attention_core_bwd(*_attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale),
+                                    ptr(o), C.c_int(H * 64), ptr(lse), ptr(d_o), ptr(dq), ptr(dk), ptr(dv), ptr(dp),
+                                    ptr(dbu), ptr(dbv), ptr(scratch), stream_ptr()), "svsr_attention_core_bwd")
+    return dq[:, : H * 64], dk[:, : H * 64], dv[:, : H * 64], dp, dbu, dbv
+
+
+def ctc_loss(logits: torch.Tensor, V: int, labels: torch.Tensor, in_len: torch.Tensor, B: int, T: int,
+             dscale: float = 1.0):
+    """logits fp32 [B*T, ld]; labels int64 [B,Lmax] (-1 padded); in_len int32 [B]. Returns (sum nll, dlogits bf16)."""
+    L = lib()
+    L.svsr_ctc_scratch_bytes.restype = C.c_int64
+    _req(logits, torch.float32, "logits"), _req(labels, torch.int64, "labels"), _req(in_len, torch.int32, "in_len")
+    ld, Lmax = logits.shape[1], labels.shape[1]
+    dl = torch.empty(B * T, ld, device=logits.device, dtype=torch.bfloat16)
+    acc = torch.zeros(4, device=logits.device, dtype=torch.float64)
+    scratch = torch.empty(L.svsr_ctc_scratch_bytes(B, T, Lmax), device=logits.device, dtype=torch.uint8)
+    check(L.svsr_ctc_loss(ptr(logits), C.c_int(ld), C.c_int(V), ptr(labels), C.c_int(Lmax), ptr(in_len), C.c_int(B),
+                          C.c_int(T), ptr(dl), ptr(acc), C.c_int(0), C.c_float(dscale), ptr(scratch), stream_ptr()),
+          "svsr_ctc_loss")
+    return acc[0], dl
+
+
+def label_smoothing_loss(logits: torch.Tensor, V: int, target: torch.Tensor, smoothing: float, dscale: float = 1.0):
+    """logits fp32 [rows, ld]; target int64 [rows]. Returns (acc fp64 [KL sum, #correct, #scored], dlogits bf16)."""
+    _req(logits, torch.float32, "logits"), _req(target, torch.int64, "target")
+    rows, ld = logits.shape
+    dl = torch.empty(rows, ld, device=logits.device, dtype=torch.bfloat16)
+    acc = torch.zeros(4, device=logits.device, dtype=torch.float64)
+    check(lib().svsr_label_smoothing_loss(ptr(logits), C.c_int(ld), C.c_int(V), ptr(target), C.c_int(rows),
+                                          C.c_float(smoothing), ptr(dl), ptr(acc), C.c_int(0), C.c_float(dscale),
+                                          stream_ptr()), "svsr_label_smoothing_loss")
+    return acc, dl

@@ -1,0 +1,444 @@
+"""LRS sentence-level path on the GPU: (1) kernel-level parity of the Conformer / CTC / decoder operators (through the C
+ABI) against plain fp32 PyTorch on identical inputs, (2) model-level parity of the native E2E step against the oracle
+(oracle/lrs_oracle.py, pinned to the reference's own E2E module) and the committed golden vectors.
+
+Tolerances as in test_kernels_gpu.py: bf16-stored outputs carry one bf16 rounding (rel-L2 < 4e-3), fp32 outputs agree
+to ~2e-4; integer work (sos/eos insertion, token indexing) is bit-exact."""
+import math
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import lrs_oracle as O
+from oracle.lrw_oracle import bf16_ste
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 4e-3
+F32_TOL = 2e-4
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def cosine(a, b):
+    a, b = a.float().cpu().flatten(), b.float().cpu().flatten()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from syncvsr_b200 import ops as o
+
+    return o
+
+
+def randn(*shape, seed=0, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+# ---------------------------------------------------------------- LayerNorm / GLU / depthwise conv / BN1d --------
+@pytest.mark.parametrize("M,D", [(37, 256), (2400, 768), (301, 512), (9, 1024)])
+def test_layernorm_fwd_bwd(ops, M, D):
+    x = randn(M, D, seed=1, scale=2.0, dtype=torch.float32) + 0.3
+    g, b = 1 + 0.1 * randn(D, seed=2, dtype=torch.float32), 0.1 * randn(D, seed=3, dtype=torch.float32)
+    yb, yf, stats = ops.layernorm_fwd(x, g, b)
+    xt, gt, bt = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xt, (D,), gt, bt, 1e-12)
+    assert rel(yf, ref) < 1e-5 and rel(yb, ref) < BF16_TOL
+    dy = randn(M, D, seed=4, dtype=torch.float32)
+    gx, gg, gb = torch.autograd.grad(ref, (xt, gt, bt), dy)
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, stats)
+    assert rel(dx, gx) < 1e-4 and rel(dg, gg) < F32_TOL and rel(db, gb) < F32_TOL
+    # bf16 upstream gradient, accumulated into an existing fp32 stream gradient (the engine's residual form)
+    base = randn(M, D, seed=5, dtype=torch.float32)
+    dyb = dy.to(torch.bfloat16)
+    gx2 = torch.autograd.grad(F.layer_norm(xt, (D,), gt, bt, 1e-12), xt, dyb.float())[0]
+    dx2, _, _ = ops.layernorm_bwd(dyb, x, g, stats, dx=base.clone())
+    assert rel(dx2, base + gx2) < 1e-4
+    # in place: dy aliases dx (after_norm / norm_final backward)
+    buf = dy.clone()
+    dx3, _, _ = ops.layernorm_bwd(buf, x, g, stats, dx=None)
+    assert rel(dx3, gx) < 1e-4
+
+
+def test_glu_fwd_bwd(ops):
+    h = randn(1000, 2 * 768, seed=6)
+    ht = h.float().requires_grad_(True)
+    ref = F.glu(ht, dim=1)
+    assert rel(ops.glu_fwd(h), ref) < BF16_TOL
+    du = randn(1000, 768, seed=7)
+    assert rel(ops.glu_bwd(h, du), torch.autograd.grad(ref, ht, du.float())[0]) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,T,C,K", [(3, 40, 256, 31), (2, 150, 768, 31), (2, 9, 128, 7)])
+def test_depthwise_conv1d(ops, B, T, C, K):
+    x = randn(B, T, C, seed=8)
+    w = randn(C, K, seed=9, scale=K ** -0.5, dtype=torch.float32)
+    bias = 0.1 * randn(C, seed=10, dtype=torch.float32)
+    xt = x.float().transpose(1, 2).requires_grad_(True)
+    wt, bt = w.view(C, 1, K).clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = F.conv1d(xt, wt, bt, padding=(K - 1) // 2, groups=C)
+    y = ops.dwconv1d_fwd(x, w, bias)
+    assert rel(y, ref.transpose(1, 2)) < BF16_TOL
+    dy = randn(B, T, C, seed=11)
+    gx, gw, gb = torch.autograd.grad(ref, (xt, wt, bt), dy.float().transpose(1, 2))
+    assert rel(ops.dwconv1d_fwd(dy, w, None, flip=True), gx.transpose(1, 2)) < BF16_TOL
+    dw, db = ops.dwconv1d_wgrad(x, dy, K)
+    assert rel(dw, gw.view(C, K)) < F32_TOL and rel(db, gb) < F32_TOL
+
+
+def test_bn1d_column_reductions(ops):
+    rows, C = 2400, 768
+    x = randn(rows, C, seed=12, scale=1.5) + 0.25
+    st = ops.bn_col_reduce(x)
+    xf = x.double()
+    assert rel(st[0], xf.sum(0)) < 1e-5 and rel(st[1], (xf * xf).sum(0)) < 1e-5
+    mean, var = xf.mean(0), xf.var(0, unbiased=False)
+    invstd = 1 / torch.sqrt(var + 1e-5)
+    gamma, beta = 1 + 0.1 * randn(C, seed=13, dtype=torch.float32), 0.1 * randn(C, seed=14, dtype=torch.float32)
+    scale = gamma.double() * invstd
+    coef = torch.stack([mean, invstd, scale, beta.double() - mean * scale]).float().contiguous()
+    dout = randn(rows, C, seed=15)
+    pre = xf * scale + (beta.double() - mean * scale)
+    sg = torch.sigmoid(pre)
+    gg = dout.double() * sg * (1 + pre * (1 - sg))
+    st1 = ops.bn_col_reduce(x, dout, coef)
+    assert rel(st1[0], gg.sum(0)) < 2e-4 and rel(st1[1], (gg * (xf - mean) * invstd).sum(0)) < 2e-4
+
+
+# ---------------------------------------------------------------- attention core ---------------------------------
+def _attention_reference(q, k, v, p, bu, bv, klen, causal, B, H, Tq, Tk, scale):
+    """transformer/attention.py:59-88,238-278 in fp32 autograd (rel_shift as the index map of oracle/lrs_oracle.py)."""
+    qh = q.view(B, Tq, H, 64)
+    kh = k.view(B, Tk, H, 64).transpose(1, 2)
+    vh = v.view(B, Tk, H, 64).transpose(1, 2)
+    qu = (qh + (bu if bu is not None else 0)).transpose(1, 2)
+    scores = qu @ kh.transpose(-2, -1)
+    if p is not None:
+        ph = p.view(1, 2 * Tk - 1, H, 64).transpose(1, 2)
+        qv = (qh + bv).transpose(1, 2)
+        raw = qv @ ph.transpose(-2, -1)
+        idx = (torch.arange(Tk).view(1, Tk) - torch.arange(Tq).view(Tq, 1) + Tk - 1).to(q.device)
+        scores = scores + raw.gather(-1, idx.view(1, 1, Tq, Tk).expand(B, H, Tq, Tk))
+    scores = scores * scale
+    mask = torch.ones(B, 1, Tq, Tk, dtype=torch.bool, device=q.device)
+    if klen is not None:
+        mask = mask & (torch.arange(Tk, device=q.device).view(1, 1, 1, Tk) < klen.view(B, 1, 1, 1))
+    if causal:
+        mask = mask & torch.tril(torch.ones(Tq, Tk, dtype=torch.bool, device=q.device)).view(1, 1, Tq, Tk)
+    scores = scores.masked_fill(~mask, -1e10)
+    attn = torch.softmax(scores, -1).masked_fill(~mask, 0.0)
+    return (attn @ vh).transpose(1, 2).reshape(B * Tq, H * 64)
+
+
+ATTN_CASES = [
+    # name, B, H, Tq, Tk, rel, klen, causal
+    ("enc_rel", 3, 4, 40, 40, True, True, False),
+    ("enc_rel_c3", 2, 12, 150, 150, True, True, False),
+    ("enc_rel_odd", 2, 2, 37, 37, True, False, False),
+    ("dec_self", 3, 4, 9, 9, False, False, True),
+    ("dec_src", 3, 4, 9, 40, False, True, False),
+    ("dec_src_c4", 2, 12, 41, 250, False, True, False),
+]
+
+
+@pytest.mark.parametrize("name,B,H,Tq,Tk,use_rel,use_klen,causal", ATTN_CASES)
+def test_attention_core_fwd_bwd(ops, name, B, H, Tq, Tk, use_rel, use_klen, causal):
+    D = H * 64
+    fused = Tq == Tk  # self-attention: q | k | v are column blocks of one [rows, 3D] buffer (the engine's layout)
+    if fused:
+        qkv = randn(B * Tq, 3 * D, seed=20, scale=0.7)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    else:
+        q = randn(B * Tq, D, seed=20, scale=0.7)
+        kv = randn(B * Tk, 2 * D, seed=21, scale=0.7)
+        k, v = kv[:, :D], kv[:, D:]
+    p = randn(2 * Tk - 1, D, seed=22, scale=0.7) if use_rel else None
+    bu = 0.3 * randn(H, 64, seed=23, dtype=torch.float32) if use_rel else None
+    bv = 0.3 * randn(H, 64, seed=24, dtype=torch.float32) if use_rel else None
+    klen = None
+    if use_klen:
+        klen = torch.randint(max(Tk // 2, 1), Tk + 1, (B,), generator=torch.Generator().manual_seed(5)).int()
+        klen[0] = Tk
+        klen = klen.cuda()
+    o, lse = ops.attention_core_fwd(q, k, v, B, H, Tq, Tk, p=p, bias_u=bu, bias_v=bv, klen=klen, causal=causal)
+    leaves = [t.float().contiguous().requires_grad_(True) for t in (q, k, v)]
+    pl = p.float().requires_grad_(True) if use_rel else None
+    bul = bu.clone().requires_grad_(True) if use_rel else None
+    bvl = bv.clone().requires_grad_(True) if use_rel else None
+    ref = _attention_reference(leaves[0], leaves[1], leaves[2], pl, bul, bvl, klen, causal, B, H, Tq, Tk, 0.125)
+    assert rel(o, ref) < BF16_TOL, name
+    d_o = randn(B * Tq, D, seed=25, scale=0.5)
+    wrt = leaves + ([pl, bul, bvl] if use_rel else [])
+    grads = torch.autograd.grad(ref, wrt, d_o.float())
+    dq, dk, dv, dp, dbu, dbv = ops.attention_core_bwd(q, k, v, o, lse, d_o, B, H, Tq, Tk, p=p, bias_u=bu, bias_v=bv,
+                                                      klen=klen, causal=causal)
+    assert rel(dq, grads[0]) < 6e-3 and rel(dk, grads[1]) < 6e-3 and rel(dv, grads[2]) < 6e-3, name
+    if use_rel:
+        assert rel(dp, grads[3]) < 2e-3 and rel(dbu, grads[4]) < 2e-3 and rel(dbv, grads[5]) < 2e-3, name
+    if use_klen:  # masked keys receive exactly zero gradient
+        for b in range(B):
+            n = int(klen[b])
+            assert float(dk.view(B, Tk, D)[b, n:].float().abs().sum()) == 0.0
+            assert float(dv.view(B, Tk, D)[b, n:].float().abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------- CTC / label smoothing --------------------------
+@pytest.mark.parametrize("B,T,V,Lmax", [(3, 12, 300, 8), (4, 150, 5049, 40), (2, 6, 50, 5)])
+def test_ctc_matches_torch(ops, B, T, V, Lmax):
+    g = torch.Generator().manual_seed(30)
+    ld = (V + 63) // 64 * 64
+    logits = torch.randn(B * T, ld, generator=g) * 2
+    lab_len = torch.randint(1, Lmax + 1, (B,), generator=g)
+    lab_len[0] = Lmax
+    labels = torch.full((B, Lmax), -1, dtype=torch.long)
+    for b in range(B):
+        labels[b, : lab_len[b]] = torch.randint(1, V - 1, (int(lab_len[b]),), generator=g)
+    if Lmax >= 3:
+        labels[0, 1] = labels[0, 0]  # a repeated label: the blank between them is mandatory
+    in_len = torch.randint(max(T // 2, 1), T + 1, (B,), generator=g)
+    in_len[0] = T
+    if B > 1 and T < 10:
+        in_len[1] = 1  # too short for its labels unless a single label: exercises zero_infinity
+        if lab_len[1] < 2:
+            labels[1, 1] = 7
+            lab_len[1] = 2
+    lt = logits[:, :V].view(B, T, V).clone().requires_grad_(True)
+    lp = lt.log_softmax(2).transpose(0, 1)
+    ys = torch.cat([labels[b, : lab_len[b]] for b in range(B)])
+    ref = F.ctc_loss(lp, ys, in_len, lab_len, blank=0, reduction="sum", zero_infinity=True)
+    gref = torch.autograd.grad(ref, lt)[0]
+    nll, dl = ops.ctc_loss(logits.cuda(), V, labels.cuda(), in_len.int().cuda(), B, T)
+    assert float(nll) == pytest.approx(float(ref), rel=2e-5, abs=1e-5)
+    dl = dl.float().cpu().view(B, T, ld)
+    assert float(dl[:, :, V:].abs().sum()) == 0.0
+    assert rel(dl[:, :, :V], gref) < BF16_TOL
+    for b in range(B):  # frames beyond the clip's length and infeasible samples get a zero gradient
+        assert float(dl[b, int(in_len[b]):].abs().sum()) == 0.0
+
+
+def test_label_smoothing_loss_and_accuracy(ops):
+    g = torch.Generator().manual_seed(31)
+    B, L, V = 4, 9, 5049
+    ld = (V + 63) // 64 * 64
+    logits = torch.randn(B * L, ld, generator=g) * 2
+    target = torch.randint(0, V, (B, L), generator=g)
+    target[1, 5:] = -1
+    target[3, 2:] = -1
+    logits[0, int(target[0, 0])] = 30.0  # at least one correct argmax
+    lt = logits[:, :V].view(B, L, V).clone().requires_grad_(True)
+    ref = O.label_smoothing_loss(lt, target, 0.1) * B  # the oracle divides by the batch size
+    gref = torch.autograd.grad(ref, lt)[0]
+    acc, dl = ops.label_smoothing_loss(logits.cuda(), V, target.flatten().cuda(), 0.1)
+    assert float(acc[0]) == pytest.approx(float(ref), rel=2e-5)
+    assert float(acc[1]) / float(acc[2]) == pytest.approx(O.th_accuracy(lt.detach(), target))
+    dl = dl.float().cpu().view(B, L, ld)
+    assert rel(dl[:, :, :V], gref) < BF16_TOL and float(dl[:, :, V:].abs().sum()) == 0.0
+    assert float(dl[1, 5:].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------- model level ------------------------------------
+def _args(c, codec="wav2vec2"):
+    return SimpleNamespace(adim=c["adim"], aheads=c["heads"], eunits=c["eunits"], elayers=c["elayers"], ddim=c["adim"],
+                           dheads=c["heads"], dunits=c["eunits"], dlayers=c["dlayers"], mtlalpha=0.1, lsm_weight=0.1,
+                           dropout_rate=0.0, transformer_attn_dropout_rate=0.0, transformer_input_layer="conv3d",
+                           transformer_encoder_attn_layer_type="rel_mha", macaron_style=True, use_cnn_module=True,
+                           cnn_module_kernel=31, zero_triu=False, a_upsample_ratio=1, relu_type="swish",
+                           transformer_length_normalized_loss=False, ctc_type="builtin", rel_pos_type="latest",
+                           codec=codec, audio_weight=10.0, audio_alignment=c["A"], vq_groups=c["G"],
+                           audio_vocab_size=c["V"], max_label_len=16)
+
+
+def _kwargs(c):
+    return dict(adim=c["adim"], heads=c["heads"], eunits=c["eunits"], elayers=c["elayers"], dlayers=c["dlayers"],
+                odim=c["odim"], n_audio=c["A"] * c["G"] * c["V"])
+
+
+@pytest.fixture(scope="module")
+def E2E():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from syncvsr_b200.e2e import E2E as cls
+
+    return cls
+
+
+def _native(E2E, c, train=True):
+    m = E2E(c["odim"], _args(c)).train(train)
+    P = O.make_params(c["seed_p"], **_kwargs(c))
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all("num_batches_tracked" in k for k in missing), missing
+    inputs = O.make_inputs(c["seed_x"], c["B"], c["T"], S=c["S"], A=c["A"], G=c["G"], V=c["V"], odim=c["odim"],
+                           extra_tokens=c["extra_tokens"])
+    return m, P, inputs
+
+
+def _oracle(c, P, inputs, q=None, train=True):
+    x, lengths, tokens, label = inputs
+    return O.lrs_forward(P, x, lengths, tokens, label, elayers=c["elayers"], dlayers=c["dlayers"], heads=c["heads"],
+                         odim=c["odim"], audio_alignment=c["A"], audio_vocab_size=c["V"], q=q, train=train)
+
+
+def test_state_dict_keys_match_reference_module(E2E, golden_dir):
+    """Every parameter / buffer key and shape of the reference E2E (recorded in the golden fixture's grad_norms plus the
+    oracle's parameter factory, which the reference module loads strictly) exists in the native module."""
+    c = torch.load(golden_dir / "lrs_small.pt")["meta"]
+    m = E2E(c["odim"], _args(c))
+    sd = m.state_dict()
+    P = O.make_params(c["seed_p"], **_kwargs(c))
+    for k, v in P.items():
+        assert k in sd and tuple(sd[k].shape) == tuple(v.shape), k
+    extra = [k for k in sd if k not in P and "num_batches_tracked" not in k]
+    assert not extra, extra
+    # AdamW decay split of the reference (LRS/video/lightning.py:89-92): ndim >= 2 decays
+    for k, p in m.named_parameters():
+        off = m._offsets[k][0]
+        assert (off < m.n_decay) == (p.ndim >= 2), k
+
+
+@pytest.mark.parametrize("name", ["lrs_small", "lrs_c3_w768"])
+def test_forward_matches_reference_golden(E2E, name, golden_dir):
+    """Golden vectors come from the reference's own E2E.forward (tests/golden/make_golden_lrs.py)."""
+    fx = torch.load(golden_dir / f"{name}.pt")
+    c = fx["meta"]
+    m, P, (x, lengths, tokens, label) = _native(E2E, c)
+    loss, loss_ctc, loss_att, loss_audio, acc = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    g = fx["metrics"]
+    assert float(loss) == pytest.approx(g["loss"], rel=2e-3)
+    assert float(loss_audio) == pytest.approx(g["loss_audio"], rel=1e-3)
+    assert float(loss_ctc) == pytest.approx(g["loss_ctc"], rel=5e-3)
+    assert float(loss_att) == pytest.approx(g["loss_att"], rel=2e-3)
+    assert float(acc) == pytest.approx(g["acc"], abs=0.13)  # a handful of scored tokens: one argmax flip allowed
+    # integer path: sos/eos insertion and the audio-target flattening are bit exact
+    ys_in, ys_out = O.add_sos_eos(label, c["odim"] - 1, c["odim"] - 1)
+    L = label.shape[1] + 1
+    assert torch.equal(m._named_tensor("ys_in", (c["B"], L)).cpu()[:, : ys_in.shape[1]], ys_in)
+    assert torch.equal(m._named_tensor("ys_out", (c["B"], L)).cpu()[:, : ys_out.shape[1]], ys_out)
+    assert int(m._named_tensor("bad_token")[0]) == 0
+    # tensors: bf16 storage noise vs the fp32 reference
+    enc = m.encoder_out().cpu()
+    assert rel(enc[:, 3, :], fx["encoder_out_t3"]) < 5e-2
+    assert rel(enc[:, -1, :], fx["encoder_out_last"]) < 5e-2
+    assert enc.double().abs().sum().item() == pytest.approx(fx["encoder_out_abs"], rel=1e-2)
+    assert rel(m.logits_audio().cpu()[:, 2, :], fx["logits_audio_t2"]) < 5e-2
+    assert rel(m.ctc_logits().cpu()[:, 1, :], fx["ctc_logits_t1"]) < 5e-2
+    assert rel(m.pred().cpu()[:, 0, :], fx["pred_l0"]) < 5e-2
+    sd = m.state_dict()
+    e0 = "encoder.encoders.0"
+    assert rel(sd[e0 + ".conv_module.norm.running_var"], fx["running_var_bn1d"]) < 2e-2
+    assert (sd[e0 + ".conv_module.norm.running_mean"].cpu() - fx["running_mean_bn1d"]).abs().max().item() < 2e-2
+    assert rel(sd["encoder.frontend.frontend3D.1.running_var"], fx["running_var_stem"]) < 2e-2
+    assert int(sd["encoder.frontend.frontend3D.1.num_batches_tracked"]) == 1
+
+
+def test_forward_backward_vs_oracle_same_storage_points(E2E, golden_dir):
+    """Oracle with bf16 rounding at the CUDA path's storage points; every parameter gradient is compared."""
+    c = torch.load(golden_dir / "lrs_small.pt")["meta"]
+    m, P, inputs = _native(E2E, c)
+    x, lengths, tokens, label = inputs
+    out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = _oracle(c, Pq, inputs, q=bf16_ste)
+    for got, key in zip(out[:4], ("loss", "loss_ctc", "loss_att", "loss_audio")):
+        assert float(got) == pytest.approx(float(o[key]), rel=1e-3), key
+    assert rel(m.encoder_out(), o["encoder_out"].detach()) < 3e-2
+    assert rel(m.logits_audio().flatten(), o["logits_audio"].detach().flatten()) < 3e-2
+    assert rel(m.ctc_logits(), o["ctc_logits"].detach()) < 3e-2
+    assert rel(m.pred()[:, : o["pred"].shape[1]], o["pred"].detach()) < 3e-2
+    out[0].backward()
+    o["loss"].backward()
+    bad = []
+    for k, p in m._param_views.items():
+        ref = Pq[k].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if ref is None or float(ref.norm()) < 1e-6:  # mathematically zero gradients (key bias, conv bias before BN)
+            if float(p.grad.norm()) > 1e-3 * max(1.0, float(p.norm())):
+                bad.append((k, "nonzero", float(p.grad.norm())))
+            continue
+        if k.startswith("encoder.frontend"):  # bf16 chaos of the BN/Swish trunk at tiny batch: direction + norm
+            if cosine(p.grad, ref) < 0.8 or abs(float(p.grad.norm()) / float(ref.norm()) - 1) > 0.15:
+                bad.append((k, cosine(p.grad, ref), float(p.grad.norm()) / float(ref.norm())))
+        elif rel(p.grad, ref) > 6e-2:
+            bad.append((k, rel(p.grad, ref)))
+    assert not bad, bad
+
+
+def test_gradients_match_reference_golden(E2E, golden_dir):
+    """Selected gradients recorded from the reference module's own backward (fp32)."""
+    fx = torch.load(golden_dir / "lrs_small.pt")
+    c = fx["meta"]
+    m, P, (x, lengths, tokens, label) = _native(E2E, c)
+    out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    out[0].backward()
+    G = {k: p.grad for k, p in m._param_views.items()}
+    e0 = "encoder.encoders.0"
+    assert rel(G["audio_classifier.bias"], fx["grad_audio_bias"]) < 3e-2
+    assert rel(G["ctc.ctc_lo.bias"][:64], fx["grad_ctc_b_slice"]) < 5e-2
+    assert rel(G[e0 + ".self_attn.pos_bias_u"], fx["grad_pos_bias_u"]) < 8e-2
+    assert rel(G[e0 + ".self_attn.pos_bias_v"], fx["grad_pos_bias_v"]) < 8e-2
+    assert rel(G[e0 + ".self_attn.linear_pos.weight"][:4], fx["grad_linear_pos_slice"]) < 8e-2
+    assert rel(G[e0 + ".conv_module.depthwise_conv.weight"][:8], fx["grad_dw_slice"]) < 8e-2
+    assert rel(G[e0 + ".conv_module.norm.weight"], fx["grad_bn1d_w"]) < 8e-2
+    assert rel(G[e0 + ".norm_final.weight"], fx["grad_norm_final_w"]) < 8e-2
+    assert rel(G["encoder.embed.0.bias"], fx["grad_embed_b"]) < 8e-2
+    assert float(G["decoder.embed.0.weight"].double().norm()) == pytest.approx(fx["grad_dec_embed_norm"], rel=5e-2)
+    # upstream-gradient linearity: backward of 2*loss doubles every gradient
+    g1 = m.flat_grads.clone()
+    m.flat_grads.zero_()
+    out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    (2.0 * out[0]).backward()
+    assert rel(m.flat_grads, 2 * g1) < 5e-3
+
+
+def test_encoder_call_eval_mode_and_padding_semantics(E2E, golden_dir):
+    c = dict(torch.load(golden_dir / "lrs_small.pt")["meta"])
+    m, P, (x, lengths, tokens, label) = _native(E2E, c, train=False)
+    mask = (torch.arange(c["T"]).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(-2)
+    with torch.no_grad():
+        enc, mk = m.encoder(x.cuda(), mask.cuda())
+        out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    o = _oracle(c, P, (x, lengths, tokens, label), q=bf16_ste, train=False)
+    assert mk is not None and enc.shape == (c["B"], c["T"], c["adim"])
+    assert rel(enc, o["encoder_out"]) < 3e-2
+    assert float(out[0]) == pytest.approx(float(o["loss"]), rel=2e-3)
+    assert int(m.state_dict()["encoder.frontend.frontend3D.1.num_batches_tracked"]) == 0
+    # padded frames are scored by the audio loss (no padding mask): changing a padded frame's token changes loss_audio only
+    assert int(lengths[1]) < c["T"]
+    t2 = tokens.clone()
+    t2[1, -1 - c["extra_tokens"], 0] = (t2[1, -1 - c["extra_tokens"], 0] + 1) % c["V"]
+    with torch.no_grad():
+        out2 = m(x.cuda(), lengths.cuda(), t2.cuda(), label.cuda())
+    assert float(out2[3]) != float(out[3]) and float(out2[1]) == float(out[1]) and float(out2[2]) == float(out[2])
+
+
+def test_c3_geometry_step_properties(E2E):
+    """BASELINE config 3 geometry (lrs2.yaml widths, T=150, B=4 here): size-independent properties."""
+    c = dict(adim=768, heads=12, eunits=3072, elayers=12, dlayers=6, odim=5049, A=2, G=2, V=640)
+    a = _args(c)
+    a.max_label_len = 40
+    m = E2E(5049, a).train()
+    B, T = 4, 150
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(B, T, 1, 88, 88, device="cuda", generator=g)
+    lengths = torch.tensor([150, 75, 120, 99], device="cuda")
+    for b in range(B):
+        x[b, int(lengths[b]):] = 0
+    tokens = torch.randint(0, 640, (B, 2 * T, 2), device="cuda", generator=g)
+    label = torch.full((B, 40), -1, dtype=torch.long, device="cuda")
+    for b, n in enumerate((40, 10, 25, 33)):
+        label[b, :n] = torch.randint(1, 5048, (n,), device="cuda", generator=g)
+    loss, loss_ctc, loss_att, loss_audio, acc = m(x, lengths, tokens, label)
+    assert float(loss) == pytest.approx(0.1 * float(loss_ctc) + 0.9 * float(loss_att) + 10 * float(loss_audio), rel=1e-5)
+    assert 6.0 < float(loss_audio) < 7.5  # ~ ln 640 at init
+    assert math.isfinite(float(loss_ctc)) and float(loss_ctc) > 0 and 0.0 <= float(acc) <= 1.0
+    loss.backward()
+    assert torch.isfinite(m.flat_grads).all() and float(m.flat_grads.norm()) > 0
