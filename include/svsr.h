@@ -38,6 +38,15 @@ const char* svsr_last_error(void);
 int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, int ldc, const float* bias,
                    const void* resid, int M, int N, int K, int out_fp32, int resid_fp32, float alpha, void* stream);
 
+/* svsr_gemm_bf16 with the full epilogue: out = act(alpha * a.b^T + bias_scale * bias + resid) * [relu_mask > 0];
+ * relu != 0 applies ReLU (Conformer/decoder FFN w_1, transformer/positionwise_feed_forward.py:28-30); relu_mask (bf16,
+ * same geometry as out, or NULL) zeroes the result where mask <= 0 (the ReLU backward fused into the input-gradient
+ * GEMM of w_2). alpha/bias_scale carry the macaron 1/2 (encoder_layer.py:90-96) and the x*sqrt(adim) of the
+ * positional encoding (embedding.py:212). */
+int svsr_gemm_bf16_ex(const void* a, int lda, const void* b, int ldb, void* out, int ldc, const float* bias,
+                      const void* resid, int M, int N, int K, int out_fp32, int resid_fp32, float alpha,
+                      float bias_scale, int relu, const void* relu_mask, void* stream);
+
 /* y[N,OH,OW,Cout] = conv2d(x[N,H,W,Cin], w) with w packed as [Cout, R, S, Cin] bf16, zero padding `pad`,
  * stride 1 or 2, no bias (+ resid). Cin % 64 == 0. Replaces the Conv2d calls inside resnet.layer1-4
  * (lightning.py:114-117; timm/torchvision BasicBlock). */

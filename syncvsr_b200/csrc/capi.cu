@@ -29,6 +29,20 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int svsr_gemm_bf16_ex(const void* a, int lda, const void* b, int ldb, void* out, int ldc, const float* bias,
+                      const void* resid, int M, int N, int K, int out_fp32, int resid_fp32, float alpha,
+                      float bias_scale, int relu, const void* relu_mask, void* stream) {
+  SVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  IgemmProblem p;
+  p.a = a, p.a_N = M, p.a_C = lda, p.cin = K, p.ntaps = 1;
+  p.o_N = M;
+  p.b = b, p.b_rows = N, p.b_cols = ldb;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
+  p.bias = bias, p.resid = resid, p.resid_fp32 = resid_fp32;
+  p.alpha = alpha, p.bias_scale = bias_scale, p.relu = relu, p.relu_mask = relu_mask;
+  return igemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
 int svsr_conv2d_fprop(const void* x, const void* w, void* y, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream) {
   SVSR_REQUIRE(R * S <= IGEMM_MAX_TAPS, "conv: %dx%d filter has too many taps", R, S);

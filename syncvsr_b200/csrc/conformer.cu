@@ -217,17 +217,23 @@ dwconv1d_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
     const long long bt = i / cg;
     const int t = (int)(bt % T);
     const long long b = bt / T;
-    F8 acc;
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = bias ? bias[g * 8 + j] : 0.f;
-    const int k0 = max(0, pad - t), k1 = min(K, T + pad - t);
-    for (int k = k0; k < k1; ++k) {
-      const F8 xv = ld8(x + ((b * T + t + k - pad) * (long long)C) + g * 8);
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+    const __nv_bfloat16* xrow = x + (b * T) * (long long)C + g * 8;
+    const float* wg = w + (g * 8) * K;
+    for (int k = 0; k < K; ++k) {
+      const int ts = t + k - pad;
+      if (ts < 0 || ts >= T) continue;
+      const F8 xv = ld8(xrow + (long long)ts * C);
       const int kk = flip ? K - 1 - k : k;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(__ldg(w + (g * 8 + j) * K + kk), xv.v[j], acc.v[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wg[j * K + kk], xv.v[j], acc[j]);
     }
-    st8(y + bt * C + g * 8, acc);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = acc[j];
+    st8(y + bt * C + g * 8, o);
   }
 }
 

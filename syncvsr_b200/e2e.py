@@ -344,9 +344,10 @@ class E2E(nn.Module):
         self._last_BL = (B, int(label.shape[1]) + 1)
         if self.training:
             self._nbt += 1
-        m = self._metrics
         if torch.is_grad_enabled() and self.training:
             m = _StepFunction.apply(self._anchor, self, self._metrics)
+        else:
+            m = self._metrics.clone()  # the metrics buffer is overwritten by the next step
         loss_audio = m[3] if self.codec is not None else None
         # (loss, loss_ctc, loss_att, loss_audio, acc) -- acc stays a device scalar (the reference returns a Python
         # float, which costs a host sync per step; float(acc) gives the same number)

@@ -459,3 +459,18 @@ def label_smoothing_loss(logits: torch.Tensor, V: int, target: torch.Tensor, smo
                                           C.c_float(smoothing), ptr(dl), ptr(acc), C.c_int(0), C.c_float(dscale),
                                           stream_ptr()), "svsr_label_smoothing_loss")
     return acc, dl
+
+
+def gemm_ex(a: torch.Tensor, b: torch.Tensor, bias=None, resid=None, out_dtype=torch.bfloat16, alpha: float = 1.0,
+            bias_scale: float = 1.0, relu: bool = False, relu_mask: torch.Tensor | None = None) -> torch.Tensor:
+    """out = act(alpha * a @ b.T + bias_scale * bias + resid) * [relu_mask > 0]."""
+    _req(a, torch.bfloat16, "a"), _req(b, torch.bfloat16, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    check(lib().svsr_gemm_bf16_ex(ptr(a), C.c_int(K), ptr(b), C.c_int(K), ptr(out), C.c_int(N), ptr(bias), ptr(resid),
+                                  C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(int(out_dtype == torch.float32)),
+                                  C.c_int(int(resid is not None and resid.dtype == torch.float32)), C.c_float(alpha),
+                                  C.c_float(bias_scale), C.c_int(int(relu)), ptr(relu_mask), stream_ptr()),
+          "svsr_gemm_bf16_ex")
+    return out
