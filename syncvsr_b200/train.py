@@ -35,9 +35,12 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(p)
         self.exp_avg_sq = torch.zeros_like(p)
         self.scratch = torch.zeros(8, dtype=torch.float64, device=p.device)
-        L = lib()
-        L.svsr_lrw_decay_count.restype = C.c_int64
-        self.n_decay = int(L.svsr_lrw_decay_count(module._h))
+        if hasattr(module, "n_decay"):  # LRS E2E mirror (e2e.py) records it when it builds its arenas
+            self.n_decay = int(module.n_decay)
+        else:
+            L = lib()
+            L.svsr_lrw_decay_count.restype = C.c_int64
+            self.n_decay = int(L.svsr_lrw_decay_count(module._h))
         self.n_total = p.numel()
         self.t = 0
 
