@@ -116,3 +116,65 @@ def test_flat_gradient_allreduce_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LRS sentence-level engine: arena layout (host code only)
+# ---------------------------------------------------------------------------------------------------------------
+def _lrs_engine(adim=256, heads=4, eunits=512, elayers=2, dlayers=1, odim=300, A=2, G=2, V=64, B=3, T=12, Lmax=17):
+    from syncvsr_b200.e2e import LrsConfig
+
+    L = _lib.lib()
+    for f in ("param_count", "buffer_count", "workspace_bytes", "decay_count"):
+        getattr(L, f"svsr_lrs_{f}").restype = C.c_int64
+    h = C.c_void_p()
+    cfg = LrsConfig(B, T, 88, 88, adim, heads, eunits, elayers, dlayers, eunits, odim, 31, A, G, V, Lmax, 0.1, 0.1, 10.0,
+                    1e-5, 0.1)
+    _lib.check(L.svsr_lrs_create(C.byref(cfg), C.byref(h)), "create")
+    return L, h
+
+
+def test_lrs_arena_layout_matches_reference_state_dict():
+    from oracle import lrs_oracle as OL
+
+    L, h = _lrs_engine()
+    name, ndim, off, decay = C.c_char_p(), C.c_int(), C.c_int64(), C.c_int()
+    shape = (C.c_int64 * 5)()
+    rows = []
+    for i in range(L.svsr_lrs_num_params(h)):
+        _lib.check(L.svsr_lrs_param_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off), C.byref(decay)), "info")
+        rows.append((name.value.decode(), tuple(shape[k] for k in range(ndim.value)), off.value, bool(decay.value)))
+    # oracle.make_params is loaded strictly by the reference E2E module (tests/test_lrs_oracle_cpu.py): same key set
+    ref = OL.make_params(0, adim=256, heads=4, eunits=512, elayers=2, dlayers=1, odim=300, n_audio=256)
+    assert {r[0]: r[1] for r in rows} == {k: tuple(v.shape) for k, v in ref.items() if "running" not in k}
+    n_decay, n_total = L.svsr_lrs_decay_count(h), L.svsr_lrs_param_count(h)
+    spans = sorted((o, o + math.prod(s)) for _, s, o, _ in rows)
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0, "overlapping parameters"
+    assert spans[-1][1] <= n_total
+    for nm, shp, o, dec in rows:
+        assert o % 4 == 0 and dec == (len(shp) >= 2) and (o < n_decay) == dec, nm  # LRS/video/lightning.py:89-92
+    offs = {r[0]: r[2] for r in rows}
+    for pre in ("encoder.encoders.1.self_attn", "decoder.decoders.0.self_attn", "decoder.decoders.0.src_attn"):
+        for kind, step in (("weight", 256 * 256), ("bias", 256)):  # q | k | v adjacent: one fused GEMM operand
+            assert offs[f"{pre}.linear_k.{kind}"] - offs[f"{pre}.linear_q.{kind}"] == step
+            assert offs[f"{pre}.linear_v.{kind}"] - offs[f"{pre}.linear_k.{kind}"] == step
+    bufs = []
+    for i in range(L.svsr_lrs_num_buffers(h)):
+        _lib.check(L.svsr_lrs_buffer_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off)), "info")
+        bufs.append(name.value.decode())
+    assert sorted(bufs) == sorted(k for k in ref if "running" in k)
+    assert L.svsr_lrs_workspace_bytes(h) > 0
+    L.svsr_lrs_destroy(h)
+
+
+def test_lrs_engine_rejects_unsupported_geometry():
+    from syncvsr_b200.e2e import LrsConfig
+
+    L = _lib.lib()
+    h = C.c_void_p()
+    bad = LrsConfig(2, 12, 88, 88, 200, 4, 512, 1, 1, 512, 300, 31, 2, 2, 64, 17, 0.1, 0.1, 10.0, 1e-5, 0.1)  # adim 200
+    assert L.svsr_lrs_create(C.byref(bad), C.byref(h)) != 0
+    assert b"adim" in L.svsr_last_error()
+    bad = LrsConfig(2, 12, 88, 88, 256, 4, 512, 1, 1, 512, 300, 33, 2, 2, 64, 17, 0.1, 0.1, 10.0, 1e-5, 0.1)  # kernel 33
+    assert L.svsr_lrs_create(C.byref(bad), C.byref(h)) != 0
