@@ -42,10 +42,12 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
  * relu != 0 applies ReLU (Conformer/decoder FFN w_1, transformer/positionwise_feed_forward.py:28-30); relu_mask (bf16,
  * same geometry as out, or NULL) zeroes the result where mask <= 0 (the ReLU backward fused into the input-gradient
  * GEMM of w_2). alpha/bias_scale carry the macaron 1/2 (encoder_layer.py:90-96) and the x*sqrt(adim) of the
- * positional encoding (embedding.py:212). */
+ * positional encoding (embedding.py:212). drop_p > 0: Dropout on the branch value (before the residual is added,
+ * encoder_layer.py:94-137), mask = keep(drop_seed, element index in `out`). */
 int svsr_gemm_bf16_ex(const void* a, int lda, const void* b, int ldb, void* out, int ldc, const float* bias,
                       const void* resid, int M, int N, int K, int out_fp32, int resid_fp32, float alpha,
-                      float bias_scale, int relu, const void* relu_mask, void* stream);
+                      float bias_scale, int relu, const void* relu_mask, float drop_p, uint64_t drop_seed,
+                      void* stream);
 
 /* y[N,OH,OW,Cout] = conv2d(x[N,H,W,Cin], w) with w packed as [Cout, R, S, Cin] bf16, zero padding `pad`,
  * stride 1 or 2, no bias (+ resid). Cin % 64 == 0. Replaces the Conv2d calls inside resnet.layer1-4
@@ -227,7 +229,8 @@ int svsr_bn_col_reduce(const void* x, const void* dout, const float* coef, int64
  * klen int32 [B] or NULL; lse fp32 [B,H,Tq] (saved for backward). */
 int svsr_attention_core_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
                             int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
-                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, void* stream);
+                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, float drop_p,
+                            uint64_t drop_seed, void* stream);
 /* dq/dk/dv bf16 (pitches as q/k/v); dp fp32 [2Tk-1, H*64] +=; dbias_u/v fp32 [H,64] +=;
  * scratch: svsr_attention_scratch_bytes(B,H,Tq,Tk) bytes. */
 int64_t svsr_attention_scratch_bytes(int B, int H, int Tq, int Tk);
@@ -235,7 +238,7 @@ int svsr_attention_core_bwd(const void* q, int ldq, const void* k, int ldk, cons
                             int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
                             int H, int Tq, int Tk, float scale, const void* o, int ldo, const float* lse,
                             const void* d_o, void* dq, void* dk, void* dv, float* dp, float* dbias_u, float* dbias_v,
-                            void* scratch, void* stream);
+                            void* scratch, float drop_p, uint64_t drop_seed, void* stream);
 /* ctc.py:64-73,83-151: log_softmax + CTCLoss(reduction="sum", zero_infinity=True), blank 0. logits fp32 [B*T, ld]
  * (V valid columns); labels int64 [B,Lmax] padded with -1; in_len int32 [B]. acc[slot] += sum_b nll_b (fp64);
  * dlogits bf16 [B*T, ld] (optional) = dscale * d(sum nll)/dlogits. scratch: svsr_ctc_scratch_bytes(B,T,Lmax). */
@@ -247,6 +250,10 @@ int svsr_ctc_loss(const float* logits, int ld, int V, const int64_t* labels, int
  * dlogits bf16 [rows, ld] (optional) = dscale * (softmax - smoothed one-hot). */
 int svsr_label_smoothing_loss(const float* logits, int ld, int V, const int64_t* target, int rows, float smoothing,
                               void* dlogits, double* acc, int slot, float dscale, void* stream);
+/* Dropout as a counter-based mask: keep(i) is a pure function of (seed, element index i), so backward regenerates it.
+ * svsr_dropout_mask writes the uint8 keep-mask of n elements (tests); svsr_dropout_bf16 is y = x * keep / (1-p). */
+int svsr_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, void* stream);
+int svsr_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * LRS sentence-level model step executor: E2E.forward (e2e_asr_transformer.py:186-227) and its backward. Same
@@ -264,6 +271,7 @@ typedef struct svsr_lrs_config {
   int Lmax;                     /* longest decoder input (label length + 1) the workspace is sized for */
   float mtlalpha, lsm_weight, audio_weight;    /* lrs2.yaml:15,34,36 */
   float bn_eps, bn_momentum;
+  float dropout_rate, attn_dropout_rate;       /* lrs2.yaml:21-22 (training only; masks seeded per forward call) */
 } svsr_lrs_config;
 
 int svsr_lrs_create(const svsr_lrs_config* cfg, void** handle);
@@ -280,12 +288,15 @@ int svsr_lrs_bind(void* handle, float* params, float* grads, float* buffers, voi
 int svsr_lrs_pack_weights(void* handle, void* stream);
 /* x fp32 [B,T,1,H,W]; lengths int64 [B]; tokens int64 [B, >=T*A, G] (batch stride tok_stride_b) or NULL (no audio
  * loss); label int64 [B,label_len] padded with -1 (sos/eos are added on the device, add_sos_eos.py:12-31).
- * metrics (device fp32[5]) = loss, loss_ctc, loss_att, loss_audio, acc  (e2e_asr_transformer.py:227). */
+ * dropout_seed seeds this step's dropout masks (train only). metrics (device fp32[5]) = loss, loss_ctc, loss_att,
+ * loss_audio, acc  (e2e_asr_transformer.py:227). */
 int svsr_lrs_forward(void* handle, const float* x, const int64_t* lengths, const int64_t* tokens, int64_t tok_stride_b,
-                     const int64_t* label, int label_len, int train, float* metrics, void* stream);
+                     const int64_t* label, int label_len, int train, uint64_t dropout_seed, float* metrics,
+                     void* stream);
 /* Encoder.forward only (transformer/encoder.py:257-289; called directly by inference, LRS/video/lightning.py:100):
  * fills "encoder_out" fp32 [B,T,adim]. lengths may be NULL (masks=None). */
-int svsr_lrs_encode(void* handle, const float* x, const int64_t* lengths, int train, void* stream);
+int svsr_lrs_encode(void* handle, const float* x, const int64_t* lengths, int train, uint64_t dropout_seed,
+                    void* stream);
 /* (*grad_scale) * d loss / d params accumulated (+=) into the gradient arena; one backward per (train) forward. */
 int svsr_lrs_backward(void* handle, const float* grad_scale, void* stream);
 /* named tensors: encoder_out, embed_out, frontend, logits_audio, ctc_logits, pred, ys_in, ys_out, layer<i>.x<k>;

@@ -31,7 +31,8 @@ int svsr_gemm_bf16(const void* a, int lda, const void* b, int ldb, void* out, in
 
 int svsr_gemm_bf16_ex(const void* a, int lda, const void* b, int ldb, void* out, int ldc, const float* bias,
                       const void* resid, int M, int N, int K, int out_fp32, int resid_fp32, float alpha,
-                      float bias_scale, int relu, const void* relu_mask, void* stream) {
+                      float bias_scale, int relu, const void* relu_mask, float drop_p, uint64_t drop_seed,
+                      void* stream) {
   SVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   IgemmProblem p;
   p.a = a, p.a_N = M, p.a_C = lda, p.cin = K, p.ntaps = 1;
@@ -40,6 +41,7 @@ int svsr_gemm_bf16_ex(const void* a, int lda, const void* b, int ldb, void* out,
   p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
   p.bias = bias, p.resid = resid, p.resid_fp32 = resid_fp32;
   p.alpha = alpha, p.bias_scale = bias_scale, p.relu = relu, p.relu_mask = relu_mask;
+  p.drop_p = drop_p, p.drop_seed = (unsigned long long)drop_seed;
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 

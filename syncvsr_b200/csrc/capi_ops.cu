@@ -154,9 +154,11 @@ static void fill_attn(AttnProblem& a, const void* q, int ldq, const void* k, int
 }
 int svsr_attention_core_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* p,
                             int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
-                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, void* stream) {
+                            int H, int Tq, int Tk, float scale, void* o, int ldo, float* lse, float drop_p,
+                            uint64_t drop_seed, void* stream) {
   AttnProblem a;
   fill_attn(a, q, ldq, k, ldk, v, ldv, p, ldp, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale, o, ldo, lse);
+  a.drop_p = drop_p, a.drop_seed = (unsigned long long)drop_seed;
   return attention_core_fwd(a, ST(stream));
 }
 int64_t svsr_attention_scratch_bytes(int B, int H, int Tq, int Tk) {
@@ -166,9 +168,10 @@ int svsr_attention_core_bwd(const void* q, int ldq, const void* k, int ldk, cons
                             int ldp, const float* bias_u, const float* bias_v, const int* klen, int causal, int B,
                             int H, int Tq, int Tk, float scale, const void* o, int ldo, const float* lse,
                             const void* d_o, void* dq, void* dk, void* dv, float* dp, float* dbias_u, float* dbias_v,
-                            void* scratch, void* stream) {
+                            void* scratch, float drop_p, uint64_t drop_seed, void* stream) {
   AttnProblem a;
   fill_attn(a, q, ldq, k, ldk, v, ldv, p, ldp, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale, o, ldo, lse);
+  a.drop_p = drop_p, a.drop_seed = (unsigned long long)drop_seed;
   AttnGrads g;
   g.d_o = static_cast<const bf16*>(d_o);
   g.dq = static_cast<bf16*>(dq), g.dk = static_cast<bf16*>(dk), g.dv = static_cast<bf16*>(dv);
@@ -176,6 +179,12 @@ int svsr_attention_core_bwd(const void* q, int ldq, const void* k, int ldk, cons
   g.dp = dp, g.dbias_u = dbias_u, g.dbias_v = dbias_v;
   g.scratch = static_cast<float*>(scratch);
   return attention_core_bwd(a, g, ST(stream));
+}
+int svsr_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, void* stream) {
+  return dropout_mask_u8(out, n, p, (unsigned long long)seed, ST(stream));
+}
+int svsr_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
+  return dropout_bf16(static_cast<const bf16*>(x), static_cast<bf16*>(y), n, p, (unsigned long long)seed, ST(stream));
 }
 int64_t svsr_ctc_scratch_bytes(int B, int T, int Lmax) { return (int64_t)ctc_scratch_bytes(B, T, Lmax); }
 int svsr_ctc_loss(const float* logits, int ld, int V, const int64_t* labels, int Lmax, const int* in_len, int B, int T,

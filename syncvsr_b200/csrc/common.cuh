@@ -207,6 +207,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------ counter-based dropout -----------------------------------
+// keep(idx) is a pure function of (seed, element index): forward and backward regenerate the same mask, nothing is
+// stored. Every dropout site of a step uses its own seed (step seed + site constant).
+__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long x = seed ^ (idx * 0x9E3779B97F4A7C15ULL);
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (float)((unsigned)(x >> 40)) * (1.0f / 16777216.0f) >= p;
+}
+
 // ------------------------------------ small math helpers --------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

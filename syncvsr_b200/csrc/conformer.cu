@@ -317,13 +317,38 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
     reinterpret_cast<float4*>(dst)[i] = a;
   }
 }
-__global__ void cast_scale_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4, float alpha) {
+__global__ void cast_scale_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4, float alpha,
+                                  float p, unsigned long long seed) {
+  const float ks = p > 0.f ? alpha / (1.0f - p) : alpha;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[i];
+    float v[4] = {a.x * ks, a.y * ks, a.z * ks, a.w * ks};
+    if (p > 0.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!dropout_keep(seed, (unsigned long long)(4 * i + k), p)) v[k] = 0.f;
+    }
     uint2 u;
-    u.x = pack_bf16x2(a.x * alpha, a.y * alpha), u.y = pack_bf16x2(a.z * alpha, a.w * alpha);
+    u.x = pack_bf16x2(v[0], v[1]), u.y = pack_bf16x2(v[2], v[3]);
     reinterpret_cast<uint2*>(y)[i] = u;
   }
+}
+// y = dropout(x) (bf16 -> bf16), and dst(fp32) += dropout-mask * src(bf16): forward / backward of a stand-alone Dropout
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
+                                    float p, unsigned long long seed) {
+  const float ks = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(dropout_keep(seed, (unsigned long long)i, p) ? __bfloat162float(x[i]) * ks : 0.f);
+}
+__global__ void dropout_add_kernel(float* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long n, float p,
+                                   unsigned long long seed) {
+  const float ks = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (dropout_keep(seed, (unsigned long long)i, p)) dst[i] += __bfloat162float(src[i]) * ks;
+}
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, float p, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dropout_keep(seed, (unsigned long long)i, p) ? 1 : 0;
 }
 __global__ void lengths_kernel(const long long* __restrict__ in, int* __restrict__ out, int n, int maxv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,9 +411,11 @@ __global__ void rel_pos_table_kernel(__nv_bfloat16* __restrict__ pe, int T, int 
   }
 }
 __global__ void embed_posenc_kernel(const long long* __restrict__ tok, const float* __restrict__ emb,
-                                    float* __restrict__ x, int rows, int L, int D, int V) {
+                                    float* __restrict__ x, int rows, int L, int D, int V, float p,
+                                    unsigned long long seed) {
   const long long total = (long long)rows * (D / 2);
   const float sc = sqrtf((float)D);
+  const float ks = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % (D / 2));
@@ -401,15 +428,20 @@ __global__ void embed_posenc_kernel(const long long* __restrict__ tok, const flo
     float2 o;
     o.x = e.x * sc + sinf((float)l * div);
     o.y = e.y * sc + cosf((float)l * div);
+    if (p > 0.f) {
+      o.x = dropout_keep(seed, (unsigned long long)(r * D + 2 * k), p) ? o.x * ks : 0.f;
+      o.y = dropout_keep(seed, (unsigned long long)(r * D + 2 * k + 1), p) ? o.y * ks : 0.f;
+    }
     reinterpret_cast<float2*>(x + r * D)[k] = o;
   }
 }
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const float* __restrict__ dx,
-                                 float* __restrict__ demb, int rows, int D, int V) {
+                                 float* __restrict__ demb, int rows, int D, int V, float p, unsigned long long seed) {
   const long long total = (long long)rows * D;
-  const float sc = sqrtf((float)D);
+  const float sc = sqrtf((float)D) * (p > 0.f ? 1.0f / (1.0f - p) : 1.0f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
+    if (p > 0.f && !dropout_keep(seed, (unsigned long long)i, p)) continue;
     const int d = (int)(i % D);
     const long long r = i / D;
     long long t = tok[r];
@@ -417,7 +449,6 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const float*
     atomicAdd(demb + t * D + d, dx[i] * sc);
   }
 }
-
 
 // =================================================================================================
 // Multi-head attention core (d_k = 64) with optional relative-position term, key-length and causal masks.
@@ -443,6 +474,8 @@ struct AttnK {
   int lddq, lddk, lddv;
   float *dp, *dbu, *dbv;
   float *Pg, *DSg;  // scratch [B,H,Tq,Tk] each
+  float drop_p;     // dropout on the attention probabilities (attention.py:81)
+  unsigned long long drop_seed;
 };
 
 struct AttnSmem {
@@ -579,10 +612,12 @@ __global__ void __launch_bounds__(256) attention_core_fwd_kernel(const AttnK a) 
     m = warp_max(m);
     float sum = 0.f;
     if (m > -INFINITY) {
+      const float ks = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+      const unsigned long long e0 = (((unsigned long long)b * a.H + h) * a.Tq + i) * a.Tk;
       for (int j = lane; j < a.Tk; j += 32) {
         const float e = __expf(S[j] - m);
-        S[j] = e;
-        sum += e;
+        sum += e;  // the softmax normaliser is taken before dropout
+        S[j] = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : e * ks;
       }
       sum = warp_sum(sum);
     } else {  // every key masked: the reference's re-masked softmax row is all zero (attention.py:72-77)
@@ -634,10 +669,15 @@ __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a
       }
     }
     float delta = 0.f;
+    const float ks = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const unsigned long long e0 = (((unsigned long long)b * a.H + h) * a.Tq + i) * a.Tk;
     for (int j = lane; j < a.Tk; j += 32) {
       const float sj = S[j];
       const float pj = sj > -INFINITY ? __expf(sj - lse) : 0.f;
+      // dropout mask on the probabilities: d p = mask * d p~ ; the key/value side uses p~ = mask * p
+      const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
       S[j] = pj;
+      S2[j] *= mj;
       delta = fmaf(pj, S2[j], delta);
     }
     delta = warp_sum(delta);
@@ -646,8 +686,9 @@ __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a
     for (int j = lane; j < a.Tk; j += 32) {
       const float pj = S[j];
       const float ds = pj * (S2[j] - delta) * a.scale;
+      const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
       S2[j] = ds;
-      Pg[j] = pj, DSg[j] = ds;
+      Pg[j] = pj * mj, DSg[j] = ds;
     }
     __syncwarp();
     float2 du = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
@@ -1074,9 +1115,29 @@ int add_f32(float* dst, const float* src, long long n, cudaStream_t s) {
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int cast_scale_f32_bf16(const float* x, __nv_bfloat16* y, long long n, float alpha, cudaStream_t s) {
+int cast_scale_f32_bf16(const float* x, __nv_bfloat16* y, long long n, float alpha, cudaStream_t s, float drop_p,
+                        unsigned long long drop_seed) {
   SVSR_REQUIRE(n % 4 == 0, "cast_scale: n must be a multiple of 4");
-  cast_scale_kernel<<<grid_for(n / 4, 256 * 2), 256, 0, s>>>(x, y, n / 4, alpha);
+  cast_scale_kernel<<<grid_for(n / 4, 256 * 2), 256, 0, s>>>(x, y, n / 4, alpha, drop_p, drop_seed);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, float p, unsigned long long seed,
+                 cudaStream_t s) {
+  SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
+  dropout_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n, p, seed);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int dropout_add_bf16_to_f32(float* dst, const __nv_bfloat16* src, long long n, float p, unsigned long long seed,
+                            cudaStream_t s) {
+  SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
+  dropout_add_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(dst, src, n, p, seed);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int dropout_mask_u8(unsigned char* out, long long n, float p, unsigned long long seed, cudaStream_t s) {
+  dropout_mask_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(out, n, p, seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -1101,13 +1162,16 @@ int rel_pos_table(__nv_bfloat16* pe, int T, int D, cudaStream_t s) {
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, int V, cudaStream_t s) {
-  embed_posenc_kernel<<<grid_for((long long)rows * (D / 2), 256), 256, 0, s>>>(tok, emb, x, rows, L, D, V);
+int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, int V, cudaStream_t s,
+                     float drop_p, unsigned long long drop_seed) {
+  embed_posenc_kernel<<<grid_for((long long)rows * (D / 2), 256), 256, 0, s>>>(tok, emb, x, rows, L, D, V, drop_p,
+                                                                              drop_seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, int V, cudaStream_t s) {
-  embed_bwd_kernel<<<grid_for((long long)rows * D, 256), 256, 0, s>>>(tok, dx, demb, rows, D, V);
+int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, int V, cudaStream_t s, float drop_p,
+              unsigned long long drop_seed) {
+  embed_bwd_kernel<<<grid_for((long long)rows * D, 256), 256, 0, s>>>(tok, dx, demb, rows, D, V, drop_p, drop_seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -1129,6 +1193,8 @@ int attn_fill(const AttnProblem& p, AttnK& k) {
   k.o = p.o, k.ldo = p.ldo, k.lse = p.lse;
   k.d_o = nullptr, k.dq = k.dk = k.dv = nullptr, k.lddq = k.lddk = k.lddv = 0;
   k.dp = k.dbu = k.dbv = k.Pg = k.DSg = nullptr;
+  SVSR_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "attention: dropout %f out of [0,1)", p.drop_p);
+  k.drop_p = p.drop_p, k.drop_seed = p.drop_seed;
   return SVSR_OK;
 }
 template <class K>

@@ -302,17 +302,6 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
-// counter-based dropout mask: keep(idx) is a pure function of (seed, element index), so backward regenerates it
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
-  unsigned long long x = seed ^ (idx * 0x9E3779B97F4A7C15ULL);
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return (float)((unsigned)(x >> 40)) * (1.0f / 16777216.0f) >= p;
-}
-
 // u = dropout_p(value * gelu(gate))   (x-transformers FeedForward: GLU -> Dropout(ff_dropout) -> Linear)
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M,
                                  int F, float p, unsigned long long seed) {

@@ -3,7 +3,8 @@
 // Linear embed + relative positional encoding -> macaron Conformer blocks (rel-pos MHA, convolution module) ->
 // after_norm -> audio-token cross-entropy + CTC + attention decoder with label-smoothing loss, and the backward of
 // all of it. Same arena / workspace conventions as the LRW engine (engine.cu); parameter names are the reference's
-// state-dict keys. Dropout is not applied (dropout_rate = 0 configurations; the mirror refuses others loudly).
+// state-dict keys. Dropout (dropout_rate on every sub-block output, FFN hidden, positional encodings, CTC input;
+// transformer_attn_dropout_rate on attention probabilities) uses counter-based masks regenerated in backward.
 #include "engine_common.cuh"
 #include "conformer.cuh"
 #include "heads.cuh"
@@ -43,7 +44,7 @@ struct LrsEngine : EngineBase {
   std::vector<DecLayerRef> dec;
 
   size_t feats, pe_rel, klen, xs, enc_f32, enc_b, logits_a, dlogits_a, logits_c, dlogits_c, ctc_scratch;
-  size_t ys_in, ys_out, xd, dec_yn, pred, dpred, acc, bad_token;
+  size_t ys_in, ys_out, xd, dec_yn, pred, dpred, acc, bad_token, pe_drop, enc_ctc;
   size_t bn_stats_arena = 0, bn_stats_bytes = 0;
   // backward scratch
   size_t dx, dxb, gF, g3D, gD[3], attn_scratch, dp, dpb, dfeat, ddx, ddxb, dkv;
@@ -51,6 +52,12 @@ struct LrsEngine : EngineBase {
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
   int last_L = 0, last_Llab = 0, last_train = 0, last_audio = 0;
+  unsigned long long last_seed = 0;
+  float pd = 0.f, pa = 0.f;  // dropout probabilities in effect for the last forward (0 in eval mode)
+  // per-site seeds: every Dropout module instance of the reference draws an independent mask
+  unsigned long long site(int id) const { return last_seed + 0x632BE59BD9B4E019ULL * (unsigned long long)(id + 1); }
+  static int enc_site(int layer, int k) { return 16 * (layer + 1) + k; }        // k: 0 mac hidden, 1 mac out, 2 attn
+  static int dec_site(int layer, int k) { return 16 * (layer + 65) + k; }       // probs, 3 attn out, 4 conv out, ...
   bool fwd_done = false;
 
   float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * cfg.adim; }
@@ -92,7 +99,8 @@ void fused_ref(LinRef& l, long long w, long long bias, int N, int K, Bump& b) {
 }
 
 int lin_fwd(const EngineBase& e, const bf16* x, int rows, const LinRef& l, void* out, int ldc, int out_fp32,
-            const void* resid, float alpha, int relu, cudaStream_t s) {
+            const void* resid, float alpha, int relu, cudaStream_t s, float drop_p = 0.f,
+            unsigned long long drop_seed = 0) {
   IgemmProblem p;
   p.a = x, p.a_N = rows, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
   p.o_N = rows;
@@ -101,6 +109,7 @@ int lin_fwd(const EngineBase& e, const bf16* x, int rows, const LinRef& l, void*
   p.bias = l.b >= 0 ? e.P + l.b : nullptr;
   p.resid = resid, p.resid_fp32 = 1;
   p.alpha = alpha, p.bias_scale = alpha, p.relu = relu;
+  p.drop_p = drop_p, p.drop_seed = drop_seed;
   return igemm_launch(p, s);
 }
 // out[rows, K] = alpha * dy[rows, N (pitch ldy)] . W (+ resid fp32) (* [relu_mask > 0])
@@ -162,6 +171,8 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
   SVSR_REQUIRE(c.odim >= 3 && c.Lmax >= 2, "lrs: odim=%d Lmax=%d", c.odim, c.Lmax);
   e.AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   SVSR_REQUIRE(e.AGV % 64 == 0, "lrs: audio logits per frame (%d) must be a multiple of 64", e.AGV);
+  SVSR_REQUIRE(c.dropout_rate >= 0.f && c.dropout_rate < 1.f && c.attn_dropout_rate >= 0.f && c.attn_dropout_rate < 1.f,
+               "lrs: dropout rates must be in [0,1)");
   const int D = c.adim, F = c.eunits, Fd = c.dunits, H = c.aheads, T = c.T;
   e.M = c.B * c.T;
   e.Md_max = c.B * c.Lmax;
@@ -271,6 +282,8 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
   e.dpred = b.take((size_t)Md * e.ldv * 2);
   e.acc = b.take(8 * sizeof(double));
   e.bad_token = b.take(sizeof(int));
+  e.pe_drop = b.take((size_t)(2 * T - 1) * D * 2);
+  e.enc_ctc = b.take((size_t)M * D * 2);
   // ---- backward scratch ----
   const size_t R = (size_t)(M > Md ? M : Md);
   const size_t Fm = (size_t)(F > Fd ? F : Fd);
@@ -325,8 +338,12 @@ static int lrs_pack(LrsEngine& e, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // encoder only (Encoder.forward, transformer/encoder.py:257-289): fills enc_f32 / enc_b
 // ------------------------------------------------------------------------------------------------
-static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* lengths, int train, cudaStream_t s) {
+static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* lengths, int train,
+                               unsigned long long seed, cudaStream_t s) {
   const svsr_lrs_config& c = e.cfg;
+  e.last_seed = seed;
+  e.pd = train ? c.dropout_rate : 0.f, e.pa = train ? c.attn_dropout_rate : 0.f;
+  const float pd = e.pd, pa = e.pa;
   const int D = c.adim, F = c.eunits, H = c.aheads, T = c.T, M = e.M;
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.bn_stats_arena), 0, e.bn_stats_bytes, s));
   if (lengths) {
@@ -342,7 +359,12 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_bf16(f4, e.ws<bf16>(e.feats), M, HW4, 512, s));
   // ---- embed: Linear + x * sqrt(D) (encoder.py:170-174; embedding.py:212) ----
-  RC(lin_fwd(e, e.ws<bf16>(e.feats), M, e.embed, e.xs_buf(0), D, 1, nullptr, sqrtf((float)D), 0, s));
+  RC(lin_fwd(e, e.ws<bf16>(e.feats), M, e.embed, e.xs_buf(0), D, 1, nullptr, sqrtf((float)D), 0, s, pd, e.site(1)));
+  const bf16* pe = e.ws<bf16>(e.pe_rel);
+  if (pd > 0.f) {  // the dropped pos_emb tensor is shared by every block (embedding.py:217)
+    RC(dropout_bf16(pe, e.ws<bf16>(e.pe_drop), (long long)(2 * T - 1) * D, pd, e.site(2), s));
+    pe = e.ws<bf16>(e.pe_drop);
+  }
   // ---- Conformer blocks (encoder_layer.py:76-150) ----
   for (int i = 0; i < c.elayers; ++i) {
     ConfLayerRef& L = e.enc[i];
@@ -350,12 +372,13 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
           *x4 = e.xs_buf(5 * i + 4), *x5 = e.xs_buf(5 * i + 5);
     // macaron feed-forward, scaled by 1/2
     RC(ln_fwd(e, x0, L.n_mac, e.ws<bf16>(L.yn[0]), nullptr, M, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.yn[0]), M, L.mac1, e.ws<bf16>(L.h_mac), F, 0, nullptr, 1.f, 1, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.h_mac), M, L.mac2, x1, D, 1, x0, 0.5f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(L.yn[0]), M, L.mac1, e.ws<bf16>(L.h_mac), F, 0, nullptr, 1.f, 1, s, pd,
+               e.site(LrsEngine::enc_site(i, 0))));
+    RC(lin_fwd(e, e.ws<bf16>(L.h_mac), M, L.mac2, x1, D, 1, x0, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 1))));
     // relative-position multi-head self-attention (attention.py:192-278)
     RC(ln_fwd(e, x1, L.n_mha, e.ws<bf16>(L.yn[1]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[1]), M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * D, 0, nullptr, 1.f, 0, s));
-    RC(lin_fwd(e, e.ws<bf16>(e.pe_rel), 2 * T - 1, L.pos, e.ws<bf16>(L.pbuf), D, 0, nullptr, 1.f, 0, s));
+    RC(lin_fwd(e, pe, 2 * T - 1, L.pos, e.ws<bf16>(L.pbuf), D, 0, nullptr, 1.f, 0, s));
     {
       AttnProblem a;
       a.q = e.ws<bf16>(L.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
@@ -364,9 +387,10 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
       a.klen = e.ws<int>(e.klen);
       a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
       a.o = e.ws<bf16>(L.ctx), a.ldo = D, a.lse = e.ws<float>(L.lse);
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(L.ctx), M, L.out, x2, D, 1, x1, 1.f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(L.ctx), M, L.out, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 3))));
     // convolution module (convolution.py:56-75)
     RC(ln_fwd(e, x2, L.n_conv, e.ws<bf16>(L.yn[2]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[2]), M, L.pw1, e.ws<bf16>(L.hpw1), 2 * D, 0, nullptr, 1.f, 0, s));
@@ -375,26 +399,28 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
     if (train) RC(bn_col_reduce(e.ws<bf16>(L.dwo), nullptr, nullptr, M, D, e.ws<double>(L.bn.stats_f), 0, s));
     RC(bn_fwd(e, e.ws<bf16>(L.dwo), M, L.bn, train, s));
     RC(bn_apply(e.ws<bf16>(L.dwo), e.ws<float>(L.bn.coef), nullptr, nullptr, 2, e.ws<bf16>(L.act), M, D, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.act), M, L.pw2, x3, D, 1, x2, 1.f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(L.act), M, L.pw2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 4))));
     // feed-forward, scaled by 1/2, and the block's final LayerNorm
     RC(ln_fwd(e, x3, L.n_ff, e.ws<bf16>(L.yn[3]), nullptr, M, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.yn[3]), M, L.ff1, e.ws<bf16>(L.h_ff), F, 0, nullptr, 1.f, 1, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.h_ff), M, L.ff2, x4, D, 1, x3, 0.5f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(L.yn[3]), M, L.ff1, e.ws<bf16>(L.h_ff), F, 0, nullptr, 1.f, 1, s, pd,
+               e.site(LrsEngine::enc_site(i, 5))));
+    RC(lin_fwd(e, e.ws<bf16>(L.h_ff), M, L.ff2, x4, D, 1, x3, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 6))));
     RC(ln_fwd(e, x4, L.n_fin, nullptr, x5, M, s));
   }
   return ln_fwd(e, e.xs_buf(5 * c.elayers), e.after, e.ws<bf16>(e.enc_b), e.ws<float>(e.enc_f32), M, s);
 }
 
 static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, const long long* tokens,
-                       long long tok_stride_b, const long long* label, int Llab, int train, float* metrics,
-                       cudaStream_t s) {
+                       long long tok_stride_b, const long long* label, int Llab, int train, unsigned long long seed,
+                       float* metrics, cudaStream_t s) {
   const svsr_lrs_config& c = e.cfg;
   const int D = c.adim, Fd = c.dunits, H = c.aheads, T = c.T, M = e.M;
   const int L = Llab + 1, Md = c.B * L;
   SVSR_REQUIRE(Llab >= 1 && L <= c.Lmax, "lrs_forward: label length %d exceeds the engine's Lmax-1 = %d", Llab, c.Lmax - 1);
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));
-  RC(lrs_encoder_forward(e, x, lengths, train, s));
+  RC(lrs_encoder_forward(e, x, lengths, train, seed, s));
   const bf16* enc_b = e.ws<bf16>(e.enc_b);
+  const float pd = e.pd, pa = e.pa;
   // ---- audio-token cross-entropy (e2e_asr_transformer.py:195-201): padded frames are scored too ----
   const int has_audio = (e.AGV > 0 && tokens) ? 1 : 0;
   const long long audio_rows = (long long)M * c.audio_alignment * c.vq_groups;
@@ -405,7 +431,12 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
                 c.audio_weight / (float)audio_rows, s));
   }
   // ---- CTC (ctc.py:83-151) ----
-  RC(lin_fwd(e, enc_b, M, e.ctc, e.ws<float>(e.logits_c), e.ldv, 1, nullptr, 1.f, 0, s));
+  const bf16* enc_ctc = enc_b;  // ctc_lo(dropout(hs_pad)), ctc.py:97
+  if (pd > 0.f) {
+    RC(dropout_bf16(enc_b, e.ws<bf16>(e.enc_ctc), (long long)M * D, pd, e.site(3), s));
+    enc_ctc = e.ws<bf16>(e.enc_ctc);
+  }
+  RC(lin_fwd(e, enc_ctc, M, e.ctc, e.ws<float>(e.logits_c), e.ldv, 1, nullptr, 1.f, 0, s));
   RC(ctc_loss_fwd_bwd(e.ws<float>(e.logits_c), e.ldv, c.odim, label, Llab, e.ws<int>(e.klen), c.B, T,
                       e.ws<bf16>(e.dlogits_c), e.ws<double>(e.acc), 1, c.mtlalpha / (float)c.B,
                       e.ws<float>(e.ctc_scratch), s));
@@ -415,7 +446,7 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
   add_sos_eos_kernel<<<(c.B + 63) / 64, 64, 0, s>>>(label, Llab, ys_in, ys_out, c.B, c.odim - 1, c.odim - 1);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
-  RC(embed_posenc_fwd(ys_in, e.P + e.dec_emb, e.xd_buf(0), Md, L, D, c.odim, s));
+  RC(embed_posenc_fwd(ys_in, e.P + e.dec_emb, e.xd_buf(0), Md, L, D, c.odim, s, pd, e.site(4)));
   for (int i = 0; i < c.dlayers; ++i) {
     DecLayerRef& Ld = e.dec[i];
     float *x0 = e.xd_buf(3 * i), *x1 = e.xd_buf(3 * i + 1), *x2 = e.xd_buf(3 * i + 2), *x3 = e.xd_buf(3 * i + 3);
@@ -427,9 +458,10 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
       a.causal = 1;
       a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
       a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, x1, D, 1, x0, 1.f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, x1, D, 1, x0, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 1))));
     RC(ln_fwd(e, x1, Ld.n2, e.ws<bf16>(Ld.yn[1]), nullptr, Md, s));
     RC(lin_fwd(e, e.ws<bf16>(Ld.yn[1]), Md, Ld.q_c, e.ws<bf16>(Ld.qc), D, 0, nullptr, 1.f, 0, s));
     RC(lin_fwd(e, enc_b, M, Ld.kv_c, e.ws<bf16>(Ld.kvc), 2 * D, 0, nullptr, 1.f, 0, s));
@@ -440,12 +472,14 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
       a.klen = e.ws<int>(e.klen);
       a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
       a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, x2, D, 1, x1, 1.f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 3))));
     RC(ln_fwd(e, x2, Ld.n3, e.ws<bf16>(Ld.yn[2]), nullptr, Md, s));
-    RC(lin_fwd(e, e.ws<bf16>(Ld.yn[2]), Md, Ld.ff1, e.ws<bf16>(Ld.h), Fd, 0, nullptr, 1.f, 1, s));
-    RC(lin_fwd(e, e.ws<bf16>(Ld.h), Md, Ld.ff2, x3, D, 1, x2, 1.f, 0, s));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.yn[2]), Md, Ld.ff1, e.ws<bf16>(Ld.h), Fd, 0, nullptr, 1.f, 1, s, pd,
+               e.site(LrsEngine::dec_site(i, 4))));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.h), Md, Ld.ff2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 5))));
   }
   RC(ln_fwd(e, e.xd_buf(3 * c.dlayers), e.dec_after, e.ws<bf16>(e.dec_yn), nullptr, Md, s));
   RC(lin_fwd(e, e.ws<bf16>(e.dec_yn), Md, e.outl, e.ws<float>(e.pred), e.ldv, 1, nullptr, 1.f, 0, s));
@@ -464,11 +498,14 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
 // ------------------------------------------------------------------------------------------------
 static int ffn_bwd(LrsEngine& e, const bf16* dyb, int rows, const LinRef& w1, const LinRef& w2, const bf16* h,
                    const bf16* yn, const float* x_in, const LnRef& n, float* dx, int F, cudaStream_t s) {
+  // h = dropout(relu(.)) is zero where dropped OR clipped, so the fused `h > 0` mask covers both; surviving units
+  // carry the 1/(1-p) of the dropout
+  const float hs = e.pd > 0.f ? 1.0f / (1.0f - e.pd) : 1.0f;
   const int D = e.cfg.adim;
   bf16* dh = e.ws<bf16>(e.gF);
   bf16* dyn = e.ws<bf16>(e.gD[0]);
   RC(linear_wgrad(e, dyb, D, h, rows, w2, s));
-  RC(lin_dgrad(e, dyb, D, rows, w2, dh, F, 0, nullptr, 1.f, h, s));  // ReLU backward fused: zero where h <= 0
+  RC(lin_dgrad(e, dyb, D, rows, w2, dh, F, 0, nullptr, hs, h, s));  // ReLU backward fused: zero where h <= 0
   RC(linear_wgrad(e, dh, F, yn, rows, w1, s));
   RC(lin_dgrad(e, dh, F, rows, w1, dyn, D, 0, nullptr, 1.f, nullptr, s));
   return ln_bwd(e, dyn, nullptr, x_in, n, dx, 1, rows, s);
@@ -484,6 +521,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   float* dx = e.ws<float>(e.dx);
   bf16* dxb = e.ws<bf16>(e.dxb);
   const bf16* enc_b = e.ws<bf16>(e.enc_b);
+  const float pd = e.pd, pa = e.pa;
   if (grad_scale) {
     if (e.last_audio) RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)M * e.AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)M * e.ldv, grad_scale, s));
@@ -496,8 +534,14 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   } else {
     SVSR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * D * 4, s));
   }
-  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, enc_b, M, e.ctc, s));
-  RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, dx, D, 1, dx, 1.f, nullptr, s));
+  if (pd > 0.f) {  // through the Dropout in front of ctc_lo
+    RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, e.ws<bf16>(e.enc_ctc), M, e.ctc, s));
+    RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, e.ws<bf16>(e.gD[1]), D, 0, nullptr, 1.f, nullptr, s));
+    RC(dropout_add_bf16_to_f32(dx, e.ws<bf16>(e.gD[1]), (long long)M * D, pd, e.site(3), s));
+  } else {
+    RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, enc_b, M, e.ctc, s));
+    RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, dx, D, 1, dx, 1.f, nullptr, s));
+  }
 
   // ---- decoder ----
   {
@@ -515,10 +559,10 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       DecLayerRef& Ld = e.dec[i];
       float *x0 = e.xd_buf(3 * i), *x1 = e.xd_buf(3 * i + 1), *x2 = e.xd_buf(3 * i + 2);
       // feed-forward
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s));
+      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 5))));
       RC(ffn_bwd(e, ddxb, Md, Ld.ff1, Ld.ff2, e.ws<bf16>(Ld.h), e.ws<bf16>(Ld.yn[2]), x2, Ld.n3, ddx, Fd, s));
       // source attention over the encoder output
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s));
+      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 3))));
       RC(linear_wgrad(e, ddxb, D, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, s));
       RC(lin_dgrad(e, ddxb, D, Md, Ld.out_c, dctx, D, 0, nullptr, 1.f, nullptr, s));
       {
@@ -528,6 +572,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
         a.klen = e.ws<int>(e.klen);
         a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
         a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
+        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
         AttnGrads g;
         g.d_o = dctx, g.dq = dq, g.lddq = D, g.dk = dkv, g.dv = dkv + D, g.lddk = g.lddv = 2 * D;
         g.scratch = e.ws<float>(e.attn_scratch);
@@ -539,7 +584,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       RC(lin_dgrad(e, dq, D, Md, Ld.q_c, dyn, D, 0, nullptr, 1.f, nullptr, s));
       RC(ln_bwd(e, dyn, nullptr, x1, Ld.n2, ddx, 1, Md, s));
       // causal self-attention
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s));
+      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 1))));
       RC(linear_wgrad(e, ddxb, D, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, s));
       RC(lin_dgrad(e, ddxb, D, Md, Ld.out_s, dctx, D, 0, nullptr, 1.f, nullptr, s));
       {
@@ -548,6 +593,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
         a.causal = 1;
         a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
         a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
+        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
         AttnGrads g;
         g.d_o = dctx, g.dq = dqkv, g.dk = dqkv + D, g.dv = dqkv + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
         g.scratch = e.ws<float>(e.attn_scratch);
@@ -557,7 +603,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       RC(lin_dgrad(e, dqkv, 3 * D, Md, Ld.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
       RC(ln_bwd(e, dyn, nullptr, x0, Ld.n1, ddx, 1, Md, s));
     }
-    RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s));
+    RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s, pd, e.site(4)));
   }
 
   // ---- encoder.after_norm, then the Conformer blocks in reverse ----
@@ -572,10 +618,10 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
     bf16* g3 = e.ws<bf16>(e.g3D);
     RC(ln_bwd(e, nullptr, dx, x4, Lc.n_fin, dx, 0, M, s));
     // feed-forward (x 1/2)
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s));
+    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 6))));
     RC(ffn_bwd(e, dxb, M, Lc.ff1, Lc.ff2, e.ws<bf16>(Lc.h_ff), e.ws<bf16>(Lc.yn[3]), x3, Lc.n_ff, dx, F, s));
     // convolution module
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s));
+    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 4))));
     RC(linear_wgrad(e, dxb, D, e.ws<bf16>(Lc.act), M, Lc.pw2, s));
     RC(lin_dgrad(e, dxb, D, M, Lc.pw2, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d act
     RC(bn_col_reduce(e.ws<bf16>(Lc.dwo), t1, e.ws<float>(Lc.bn.coef), M, D, e.ws<double>(Lc.bn.stats_b), 1, s));
@@ -590,7 +636,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
     RC(lin_dgrad(e, g3, 2 * D, M, Lc.pw1, dyn, D, 0, nullptr, 1.f, nullptr, s));
     RC(ln_bwd(e, dyn, nullptr, x2, Lc.n_conv, dx, 1, M, s));
     // relative-position self-attention
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s));
+    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 3))));
     RC(linear_wgrad(e, dxb, D, e.ws<bf16>(Lc.ctx), M, Lc.out, s));
     RC(lin_dgrad(e, dxb, D, M, Lc.out, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d ctx
     {
@@ -601,6 +647,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       a.klen = e.ws<int>(e.klen);
       a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
       a.o = e.ws<bf16>(Lc.ctx), a.ldo = D, a.lse = e.ws<float>(Lc.lse);
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
       AttnGrads g;
       g.d_o = t1, g.dq = g3, g.dk = g3 + D, g.dv = g3 + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
       g.dp = e.ws<float>(e.dp), g.dbias_u = e.G + Lc.bias_u, g.dbias_v = e.G + Lc.bias_v;
@@ -609,16 +656,16 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       RC(attention_core_bwd(a, g, s));
     }
     RC(cast_scale_f32_bf16(e.ws<float>(e.dp), e.ws<bf16>(e.dpb), (long long)(2 * T - 1) * D, 1.f, s));
-    RC(linear_wgrad(e, e.ws<bf16>(e.dpb), D, e.ws<bf16>(e.pe_rel), 2 * T - 1, Lc.pos, s));
+    RC(linear_wgrad(e, e.ws<bf16>(e.dpb), D, pd > 0.f ? e.ws<bf16>(e.pe_drop) : e.ws<bf16>(e.pe_rel), 2 * T - 1, Lc.pos, s));
     RC(linear_wgrad(e, g3, 3 * D, e.ws<bf16>(Lc.yn[1]), M, Lc.qkv, s));
     RC(lin_dgrad(e, g3, 3 * D, M, Lc.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
     RC(ln_bwd(e, dyn, nullptr, x1, Lc.n_mha, dx, 1, M, s));
     // macaron feed-forward (x 1/2)
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s));
+    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 1))));
     RC(ffn_bwd(e, dxb, M, Lc.mac1, Lc.mac2, e.ws<bf16>(Lc.h_mac), e.ws<bf16>(Lc.yn[0]), x0, Lc.n_mac, dx, F, s));
   }
   // ---- embed (x * sqrt(D)) -> average pool -> frontend ----
-  RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, sqrtf((float)D), s));
+  RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, sqrtf((float)D), s, pd, e.site(1)));
   RC(linear_wgrad(e, dxb, D, e.ws<bf16>(e.feats), M, e.embed, s));
   RC(lin_dgrad(e, dxb, D, M, e.embed, e.ws<bf16>(e.dfeat), 512, 0, nullptr, 1.f, nullptr, s));
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
@@ -683,22 +730,24 @@ int svsr_lrs_pack_weights(void* h, void* stream) {
   return lrs_pack(*e, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrs_forward(void* h, const float* x, const int64_t* lengths, const int64_t* tokens, int64_t tok_stride_b,
-                     const int64_t* label, int label_len, int train, float* metrics, void* stream) {
+                     const int64_t* label, int label_len, int train, uint64_t dropout_seed, float* metrics,
+                     void* stream) {
   LrsEngine* e = static_cast<LrsEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrs: bind() first");
   SVSR_REQUIRE(x && lengths && label && metrics, "lrs_forward: null input");
   SVSR_REQUIRE(!tokens || tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
                "lrs_forward: audio tokens have fewer than T*alignment rows per clip");
   return lrs_forward(*e, x, reinterpret_cast<const long long*>(lengths), reinterpret_cast<const long long*>(tokens),
-                     tok_stride_b, reinterpret_cast<const long long*>(label), label_len, train, metrics,
-                     static_cast<cudaStream_t>(stream));
+                     tok_stride_b, reinterpret_cast<const long long*>(label), label_len, train,
+                     (unsigned long long)dropout_seed, metrics, static_cast<cudaStream_t>(stream));
 }
-int svsr_lrs_encode(void* h, const float* x, const int64_t* lengths, int train, void* stream) {
+int svsr_lrs_encode(void* h, const float* x, const int64_t* lengths, int train, uint64_t dropout_seed, void* stream) {
   LrsEngine* e = static_cast<LrsEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrs: bind() first");
   SVSR_REQUIRE(x, "lrs_encode: null input");
   e->fwd_done = false;
-  return lrs_encoder_forward(*e, x, reinterpret_cast<const long long*>(lengths), train, static_cast<cudaStream_t>(stream));
+  return lrs_encoder_forward(*e, x, reinterpret_cast<const long long*>(lengths), train, (unsigned long long)dropout_seed,
+                             static_cast<cudaStream_t>(stream));
 }
 int svsr_lrs_backward(void* h, const float* grad_scale, void* stream) {
   LrsEngine* e = static_cast<LrsEngine*>(h);

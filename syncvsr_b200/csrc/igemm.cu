@@ -31,6 +31,8 @@ struct IgemmKParams {
   int relu;
   const void* relu_mask;
   double* bn_stats;
+  float drop_p;
+  unsigned long long drop_seed;
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
 };
 
@@ -245,6 +247,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (col0 + j < p.n_cols) f[j] = fmaf(__ldg(p.bias + col0 + j), p.bias_scale, f[j]);
         }
         const bool full_chunk = (col0 + 32 <= p.n_cols);
+        if (p.drop_p > 0.f && row_valid) {
+          const float ks = 1.0f / (1.0f - p.drop_p);
+          const unsigned long long e0 = (unsigned long long)(row_off + col0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = dropout_keep(p.drop_seed, e0 + j, p.drop_p) ? f[j] * ks : 0.f;
+        }
         if (p.resid && row_valid) {
           if (p.resid_fp32) {
             const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
@@ -502,6 +510,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.alpha = p.alpha;
   kp.bias_scale = p.bias_scale, kp.relu = p.relu, kp.relu_mask = p.relu_mask;
   kp.bn_stats = p.bn_stats;
+  kp.drop_p = p.drop_p, kp.drop_seed = p.drop_seed;
   SVSR_REQUIRE(!p.bn_stats || p.b_rows <= 512, "igemm: fused BN statistics support at most 512 output channels");
 
   // A: [a_N, a_H, a_W, a_C] NHWC, box = (64 ch, bw, bh, bn) pixels, traversal stride for strided convs.

@@ -46,6 +46,11 @@ struct IgemmProblem {
   int relu = 0;                     // apply ReLU last (Conformer FFN w_1: positionwise_feed_forward.py:28-30)
   const void* relu_mask = nullptr;  // bf16, same geometry as out: zero the result where mask <= 0 (ReLU backward fused
                                     // into the input-gradient GEMM of the following Linear)
+  // Dropout on the branch value alpha*acc + bias_scale*bias BEFORE the residual is added (EncoderLayer /
+  // DecoderLayer `residual + dropout(sublayer(x))`, encoder_layer.py:94-137; also commutes with the ReLU of the FFN's
+  // w_1, positionwise_feed_forward.py:30). Mask = dropout_keep(drop_seed, element index in the output tensor).
+  float drop_p = 0.f;
+  unsigned long long drop_seed = 0;
   // optional fused BatchNorm statistics: fp64 [2][b_rows] accumulators (+=): per-output-channel sum and sum of
   // squares of the fp32 accumulators over all valid pixels (train-mode BN of the conv output, lightning.py:51)
   double* bn_stats = nullptr;

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import random
 import weakref
 from typing import Any, Dict, Optional
 
@@ -31,6 +32,7 @@ class LrsConfig(C.Structure):
         ("audio_alignment", C.c_int), ("vq_groups", C.c_int), ("audio_vocab", C.c_int), ("Lmax", C.c_int),
         ("mtlalpha", C.c_float), ("lsm_weight", C.c_float), ("audio_weight", C.c_float),
         ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("dropout_rate", C.c_float), ("attn_dropout_rate", C.c_float),
     ]
 
 
@@ -107,9 +109,11 @@ class E2E(nn.Module):
             raise SvsrError("zero_triu / length-normalised loss are not supported")
         if not (0.0 < self.mtlalpha < 1.0):
             raise SvsrError("the native step needs both CTC and attention losses (0 < mtlalpha < 1)")
-        for key in ("dropout_rate", "transformer_attn_dropout_rate"):
-            if float(_arg(args, key, 0.0)) != 0.0:
-                raise SvsrError(f"{key} > 0 is not supported by the native LRS path yet (set it to 0)")
+        # dropout_rate: every sub-block output, FFN hidden units, positional encodings, CTC input;
+        # transformer_attn_dropout_rate: attention probabilities (encoder and decoder). Training mode only.
+        self.dropout_rate = float(_arg(args, "dropout_rate", 0.0))
+        self.attn_dropout_rate = float(_arg(args, "transformer_attn_dropout_rate", 0.0))
+        self.dropout_seed: Optional[int] = None  # fixed seed for reproducible masks (tests); None = fresh per step
         # Cross-modal sync head (e2e_asr_transformer.py:126-160). Explicit keys win; else derived from the codec name.
         codec = _arg(args, "codec", None)
         self.codec = None
@@ -147,7 +151,8 @@ class E2E(nn.Module):
     def _engine_cfg(self, B, T, H, W) -> LrsConfig:
         return LrsConfig(B, T, H, W, self.adim, self.aheads, self.eunits, self.elayers, self.dlayers, self.dunits,
                          self.odim, self.cnn_kernel, self.audio_alignment, self.vq_groups, self.audio_vocab_size,
-                         self._lmax, self.mtlalpha, self.lsm_weight, self.audio_weight, 1e-5, 0.1)
+                         self._lmax, self.mtlalpha, self.lsm_weight, self.audio_weight, 1e-5, 0.1,
+                         self.dropout_rate, self.attn_dropout_rate)
 
     def _build_engine(self, B, T, H, W, first=False):
         L = lib()
@@ -288,6 +293,11 @@ class E2E(nn.Module):
         flat = self._ws[off: off + numel.value * esz].view(tdt)
         return flat.view(shape) if shape is not None else flat
 
+    def _step_seed(self) -> int:
+        if not self.training or (self.dropout_rate == 0.0 and self.attn_dropout_rate == 0.0):
+            return 0
+        return self.dropout_seed if self.dropout_seed is not None else random.getrandbits(63)
+
     def attach_codec(self, fn) -> None:
         """`fn(audios [B, samples]) -> int64 tokens [B, Ta, G]`: the frozen neural audio quantiser of
         e2e_asr_transformer.py:167-180 (wav2vec 2.0 / vq-wav2vec). It is off the gradient path and needs pretrained
@@ -310,7 +320,8 @@ class E2E(nn.Module):
             lengths = masks.to(self.device_).reshape(B, -1).sum(-1).long().contiguous()
         check(lib().svsr_lrs_encode(self._h, C.c_void_p(xs.data_ptr()),
                                     C.c_void_p(lengths.data_ptr() if lengths is not None else 0),
-                                    C.c_int(int(self.training)), self._stream()), "svsr_lrs_encode")
+                                    C.c_int(int(self.training)), C.c_uint64(self._step_seed()), self._stream()),
+              "svsr_lrs_encode")
         if self.training:
             self._nbt += 1
         if extract_resnet_feats:
@@ -339,8 +350,8 @@ class E2E(nn.Module):
             self._h, C.c_void_p(x.data_ptr()), C.c_void_p(lengths.data_ptr()),
             C.c_void_p(tokens.data_ptr() if tokens is not None else 0),
             C.c_int64(tokens.stride(0) if tokens is not None else 0), C.c_void_p(label.data_ptr()),
-            C.c_int(int(label.shape[1])), C.c_int(int(self.training)), C.c_void_p(self._metrics.data_ptr()),
-            self._stream()), "svsr_lrs_forward")
+            C.c_int(int(label.shape[1])), C.c_int(int(self.training)), C.c_uint64(self._step_seed()),
+            C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrs_forward")
         self._last_BL = (B, int(label.shape[1]) + 1)
         if self.training:
             self._nbt += 1

@@ -406,17 +406,18 @@ def _attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale):
 
 
 def attention_core_fwd(q, k, v, B: int, H: int, Tq: int, Tk: int, p=None, bias_u=None, bias_v=None, klen=None,
-                       causal: bool = False, scale: float = 0.125):
+                       causal: bool = False, scale: float = 0.125, drop_p: float = 0.0, drop_seed: int = 0):
     """q [B*Tq, >=H*64] / k, v [B*Tk, ...] bf16 row-major VIEWS (row pitch = stride(0)); returns (o bf16 [B*Tq,H*64], lse)."""
     o = torch.empty(B * Tq, H * 64, device=q.device, dtype=torch.bfloat16)
     lse = torch.empty(B, H, Tq, device=q.device, dtype=torch.float32)
     check(lib().svsr_attention_core_fwd(*_attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale),
-                                        ptr(o), C.c_int(H * 64), ptr(lse), stream_ptr()), "svsr_attention_core_fwd")
+                                        ptr(o), C.c_int(H * 64), ptr(lse), C.c_float(drop_p), C.c_uint64(drop_seed),
+                                        stream_ptr()), "svsr_attention_core_fwd")
     return o, lse
 
 
 def attention_core_bwd(q, k, v, o, lse, d_o, B: int, H: int, Tq: int, Tk: int, p=None, bias_u=None, bias_v=None,
-                       klen=None, causal: bool = False, scale: float = 0.125):
+                       klen=None, causal: bool = False, scale: float = 0.125, drop_p: float = 0.0, drop_seed: int = 0):
     """Returns dq, dk, dv (bf16, same pitches as q/k/v: pass contiguous-row views), dp fp32, dbias_u, dbias_v."""
     L = lib()
     L.svsr_attention_scratch_bytes.restype = C.c_int64
@@ -429,7 +430,8 @@ def attention_core_bwd(q, k, v, o, lse, d_o, B: int, H: int, Tq: int, Tk: int, p
     scratch = torch.empty(L.svsr_attention_scratch_bytes(B, H, Tq, Tk), device=q.device, dtype=torch.uint8)
     check(L.svsr_attention_core_bwd(*_attn_args(q, k, v, p, bias_u, bias_v, klen, causal, B, H, Tq, Tk, scale),
                                     ptr(o), C.c_int(H * 64), ptr(lse), ptr(d_o), ptr(dq), ptr(dk), ptr(dv), ptr(dp),
-                                    ptr(dbu), ptr(dbv), ptr(scratch), stream_ptr()), "svsr_attention_core_bwd")
+                                    ptr(dbu), ptr(dbv), ptr(scratch), C.c_float(drop_p), C.c_uint64(drop_seed),
+                                    stream_ptr()), "svsr_attention_core_bwd")
     return dq[:, : H * 64], dk[:, : H * 64], dv[:, : H * 64], dp, dbu, dbv
 
 
@@ -462,8 +464,9 @@ def label_smoothing_loss(logits: torch.Tensor, V: int, target: torch.Tensor, smo
 
 
 def gemm_ex(a: torch.Tensor, b: torch.Tensor, bias=None, resid=None, out_dtype=torch.bfloat16, alpha: float = 1.0,
-            bias_scale: float = 1.0, relu: bool = False, relu_mask: torch.Tensor | None = None) -> torch.Tensor:
-    """out = act(alpha * a @ b.T + bias_scale * bias + resid) * [relu_mask > 0]."""
+            bias_scale: float = 1.0, relu: bool = False, relu_mask: torch.Tensor | None = None, drop_p: float = 0.0,
+            drop_seed: int = 0) -> torch.Tensor:
+    """out = act(dropout(alpha * a @ b.T + bias_scale * bias) + resid) * [relu_mask > 0]."""
     _req(a, torch.bfloat16, "a"), _req(b, torch.bfloat16, "b")
     M, K = a.shape
     N = b.shape[0]
@@ -471,6 +474,14 @@ def gemm_ex(a: torch.Tensor, b: torch.Tensor, bias=None, resid=None, out_dtype=t
     check(lib().svsr_gemm_bf16_ex(ptr(a), C.c_int(K), ptr(b), C.c_int(K), ptr(out), C.c_int(N), ptr(bias), ptr(resid),
                                   C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(int(out_dtype == torch.float32)),
                                   C.c_int(int(resid is not None and resid.dtype == torch.float32)), C.c_float(alpha),
-                                  C.c_float(bias_scale), C.c_int(int(relu)), ptr(relu_mask), stream_ptr()),
+                                  C.c_float(bias_scale), C.c_int(int(relu)), ptr(relu_mask), C.c_float(drop_p),
+                                  C.c_uint64(drop_seed), stream_ptr()),
           "svsr_gemm_bf16_ex")
+    return out
+
+
+def dropout_mask(n: int, p: float, seed: int, device="cuda") -> torch.Tensor:
+    """uint8 keep-mask of the counter-based dropout (element i kept iff mask[i] == 1)."""
+    out = torch.empty(n, device=device, dtype=torch.uint8)
+    check(lib().svsr_dropout_mask(ptr(out), C.c_int64(n), C.c_float(p), C.c_uint64(seed), stream_ptr()), "svsr_dropout_mask")
     return out

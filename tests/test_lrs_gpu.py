@@ -66,6 +66,51 @@ def test_gemm_epilogue_relu_mask_scales(ops, M, N, K):
     assert rel(d32, want) < F32_TOL
 
 
+def test_gemm_epilogue_dropout_before_residual(ops):
+    """`residual + alpha * dropout(x W^T + b)` (encoder_layer.py:94-137) with the regenerable counter-based mask."""
+    M, N, K, p, seed = 300, 768, 256, 0.1, 0x1234ABCD5678
+    a, b = randn(M, K, seed=44), randn(N, K, seed=45, scale=K ** -0.5)
+    bias, resid = randn(N, seed=46, dtype=torch.float32), randn(M, N, seed=47, dtype=torch.float32)
+    keep = ops.dropout_mask(M * N, p, seed).view(M, N).float()
+    assert abs(float(keep.mean()) - (1 - p)) < 0.01
+    assert not torch.equal(ops.dropout_mask(M * N, p, seed + 1).view(M, N).float(), keep)
+    branch = 0.5 * (a.float() @ b.float().T + bias)
+    y = ops.gemm_ex(a, b, bias=bias, resid=resid, out_dtype=torch.float32, alpha=0.5, bias_scale=0.5, drop_p=p,
+                    drop_seed=seed)
+    assert rel(y, resid + branch * keep / (1 - p)) < F32_TOL
+    h = ops.gemm_ex(a, b, bias=bias, relu=True, drop_p=p, drop_seed=seed)  # dropout(relu(.)) of the FFN hidden units
+    assert rel(h, torch.relu(2 * branch) * keep / (1 - p)) < BF16_TOL
+
+
+def test_attention_probability_dropout_fwd_bwd(ops):
+    """attention.py:81: p_attn = dropout(softmax(scores)); the kernels regenerate the mask from (seed, b, h, i, j)."""
+    B, H, T, p, seed = 2, 4, 40, 0.1, 987654321
+    D = H * 64
+    qkv = randn(B * T, 3 * D, seed=50, scale=0.7)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    pos = randn(2 * T - 1, D, seed=51, scale=0.7)
+    bu, bv = 0.3 * randn(H, 64, seed=52, dtype=torch.float32), 0.3 * randn(H, 64, seed=53, dtype=torch.float32)
+    klen = torch.tensor([T, 29], dtype=torch.int32, device="cuda")
+    keep = ops.dropout_mask(B * H * T * T, p, seed).view(B, H, T, T).float()
+    o, lse = ops.attention_core_fwd(q, k, v, B, H, T, T, p=pos, bias_u=bu, bias_v=bv, klen=klen, drop_p=p, drop_seed=seed)
+    ql, kl, vl = (t.float().contiguous().requires_grad_(True) for t in (q, k, v))
+    qh = ql.view(B, T, H, 64)
+    kh, vh = kl.view(B, T, H, 64).transpose(1, 2), vl.view(B, T, H, 64).transpose(1, 2)
+    ph = pos.float().view(1, 2 * T - 1, H, 64).transpose(1, 2)
+    raw = (qh + bv).transpose(1, 2) @ ph.transpose(-2, -1)
+    idx = (torch.arange(T).view(1, T) - torch.arange(T).view(T, 1) + T - 1).cuda()
+    scores = ((qh + bu).transpose(1, 2) @ kh.transpose(-2, -1) + raw.gather(-1, idx.view(1, 1, T, T).expand(B, H, T, T))) * 0.125
+    mask = torch.arange(T, device="cuda").view(1, 1, 1, T) < klen.view(B, 1, 1, 1)
+    attn = torch.softmax(scores.masked_fill(~mask, -1e10), -1).masked_fill(~mask, 0.0) * keep / (1 - p)
+    ref = (attn @ vh).transpose(1, 2).reshape(B * T, D)
+    assert rel(o, ref) < BF16_TOL
+    d_o = randn(B * T, D, seed=54, scale=0.5)
+    gq, gk, gv = torch.autograd.grad(ref, (ql, kl, vl), d_o.float())
+    dq, dk, dv, dp, dbu, dbv = ops.attention_core_bwd(q, k, v, o, lse, d_o, B, H, T, T, p=pos, bias_u=bu, bias_v=bv,
+                                                      klen=klen, drop_p=p, drop_seed=seed)
+    assert rel(dq, gq) < 6e-3 and rel(dk, gk) < 6e-3 and rel(dv, gv) < 6e-3
+
+
 # ---------------------------------------------------------------- LayerNorm / GLU / depthwise conv / BN1d --------
 @pytest.mark.parametrize("M,D", [(37, 256), (2400, 768), (301, 512), (9, 1024)])
 def test_layernorm_fwd_bwd(ops, M, D):
@@ -472,3 +517,51 @@ def test_c3_geometry_step_properties(E2E):
     assert math.isfinite(float(loss_ctc)) and float(loss_ctc) > 0 and 0.0 <= float(acc) <= 1.0
     loss.backward()
     assert torch.isfinite(m.flat_grads).all() and float(m.flat_grads.norm()) > 0
+
+
+def test_training_config_dropout_is_consistent_between_forward_and_backward(E2E, golden_dir):
+    """lrs2.yaml trains with dropout_rate = transformer_attn_dropout_rate = 0.1. The masks are stochastic, so the check
+    is structural: a fixed seed reproduces the step bit for bit, a new seed changes it, eval mode ignores it, and the
+    analytic gradient (which regenerates every mask in backward) predicts the loss change along its own direction."""
+    c = dict(torch.load(golden_dir / "lrs_small.pt")["meta"])
+    a = _args(c)
+    a.dropout_rate, a.transformer_attn_dropout_rate = 0.1, 0.1
+    m = E2E(c["odim"], a).train()
+    P = O.make_params(c["seed_p"], **_kwargs(c))
+    m.load_state_dict(P, strict=False)
+    x, lengths, tokens, label = (t.cuda() for t in O.make_inputs(c["seed_x"], c["B"], c["T"], S=c["S"], A=c["A"],
+                                                                 G=c["G"], V=c["V"], odim=c["odim"],
+                                                                 extra_tokens=c["extra_tokens"]))
+    base = float(_oracle(c, P, (x.cpu(), lengths.cpu(), tokens.cpu(), label.cpu()))["loss"])
+    m.dropout_seed = 1234
+    l1 = m(x, lengths, tokens, label)
+    l1[0].backward()
+    g = m.flat_grads.clone()
+    v1 = [float(t) for t in l1[:4]]
+    m.flat_grads.zero_()
+    l2 = m(x, lengths, tokens, label)
+    assert [float(t) for t in l2[:4]] == v1  # same seed: identical masks, identical step
+    l2[0].backward()
+    assert rel(m.flat_grads, g) < 2e-3  # fp32 atomics reorder only
+    m.dropout_seed = 99
+    assert float(m(x, lengths, tokens, label)[0]) != v1[0]
+    assert abs(v1[0] - base) / base < 0.2 and torch.isfinite(g).all()
+    # directional derivative along the gradient with the SAME masks: L(theta -+ h g/|g|) differ by ~ 2 h |g|
+    m.dropout_seed = 1234
+    theta = m.flat_params.clone()
+    gn = float(g.norm())
+    h = 0.5 / gn  # expected central difference: 2 * h * |g| = 1.0
+    with torch.no_grad():
+        m.flat_params.copy_(theta + h * g / gn)
+        m.mark_weights_updated()
+        lp = float(m(x, lengths, tokens, label)[0])
+        m.flat_params.copy_(theta - h * g / gn)
+        m.mark_weights_updated()
+        lm = float(m(x, lengths, tokens, label)[0])
+        m.flat_params.copy_(theta)
+        m.mark_weights_updated()
+    assert (lp - lm) == pytest.approx(2 * h * gn, rel=0.2), (lp, lm, gn)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = float(m(x, lengths, tokens, label)[0]), float(m(x, lengths, tokens, label)[0])
+    assert e1 == e2
