@@ -147,7 +147,7 @@ int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const f
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct svsr_lrw_config {
   int B, T, H, W;                 /* clips per step on this GPU, frames, crop height/width */
-  int dim, depth, heads;          /* model.bert.{dim,depth,heads} (yaml:19-21) */
+  int dim, depth, heads;          /* model.bert.{dim,depth,heads} (yaml:19-21); dim = 512 + data.use_word_boundary */
   int audio_alignment, vq_groups, audio_vocab; /* lightning.py:58-67 (there derived from the codec path) */
   int num_labels;                 /* model.bert.num_labels */
   int rotary_v;                   /* x-transformers 1.9.x rotates v as well (SURVEY Appendix A switch 1) */
@@ -172,13 +172,14 @@ int svsr_lrw_bind(void* handle, float* params, float* grads, float* buffers, voi
 /* fp32 master weights -> bf16 tensor-core operand layouts; call after every optimizer step */
 int svsr_lrw_pack_weights(void* handle, void* stream);
 /* videos fp32 [B,1,T,H,W]; tokens int64 [B, >=T*A, G] with batch stride tok_stride_b (elements); labels int64 [B]
- * or soft_labels fp32 [B,num_labels] (CutMix). train: batch-stat BN + buffer update. skip_mask bit i drops encoder
+ * or soft_labels fp32 [B,num_labels] (CutMix); word_mask fp32 [B,T] when dim = 513 (data.use_word_boundary,
+ * lightning.py:145-150: it becomes channel 512 of every frame token), else NULL. train: batch-stat BN + buffer update. skip_mask bit i drops encoder
  * sublayer i (layer_dropout decided on the host like the reference); dropout_seed seeds this step's ff_dropout masks.
  * metrics (device fp32[5]) = loss_total,
  * loss_category, loss_audio, accuracy_top1, accuracy_top5. */
 int svsr_lrw_forward(void* handle, const float* videos, const int64_t* tokens, int64_t tok_stride_b,
-                     const int64_t* labels, const float* soft_labels, int train, uint32_t skip_mask,
-                     uint64_t dropout_seed, float* metrics, void* stream);
+                     const int64_t* labels, const float* soft_labels, const float* word_mask, int train,
+                     uint32_t skip_mask, uint64_t dropout_seed, float* metrics, void* stream);
 /* Parity-mode forward: same model, fp32 activations and split-bf16 ([hi|lo|hi].[hi|hi|lo]) tensor-core operands through
  * the same tcgen05 kernels (csrc/precise.cuh) -- fp32-class accuracy for north_star's 1e-3 output tolerance.
  * Forward only (no backward, running BatchNorm buffers untouched); results are read with svsr_lrw_tensor

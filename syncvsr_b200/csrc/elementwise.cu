@@ -548,7 +548,7 @@ stem_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dzp, const uint8_t* __re
 
 // -------------------------------------------------------------------------------------------------
 __global__ void meanpool_cls_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ cls,
-                                    float* __restrict__ xs, int B, int T, int HW, int C) {
+                                    float* __restrict__ xs, int B, int T, int HW, int C, int ldx) {
   const int cg = C >> 3;
   const long long total = (long long)B * (T + 1) * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -557,7 +557,7 @@ __global__ void meanpool_cls_kernel(const __nv_bfloat16* __restrict__ a, const f
     const long long row = i / cg;  // b*(T+1) + tt
     const int tt = (int)(row % (T + 1));
     const long long b = row / (T + 1);
-    float* dst = xs + row * C + g * 8;
+    float* dst = xs + row * ldx + g * 8;
     if (tt == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) dst[k] = cls[g * 8 + k];
@@ -579,7 +579,7 @@ __global__ void meanpool_cls_kernel(const __nv_bfloat16* __restrict__ a, const f
 }
 
 __global__ void meanpool_cls_bwd_kernel(const float* __restrict__ dx, __nv_bfloat16* __restrict__ dout,
-                                        float* __restrict__ dcls, int B, int T, int HW, int C) {
+                                        float* __restrict__ dcls, int B, int T, int HW, int C, int ldx) {
   const int cg = C >> 3;
   const long long total = (long long)B * (T + 1) * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -588,7 +588,7 @@ __global__ void meanpool_cls_bwd_kernel(const float* __restrict__ dx, __nv_bfloa
     const long long row = i / cg;
     const int tt = (int)(row % (T + 1));
     const long long b = row / (T + 1);
-    const F8 d = ldf8(dx + row * C + g * 8);
+    const F8 d = ldf8(dx + row * ldx + g * 8);
     if (tt == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) atomicAdd(dcls + g * 8 + k, d.v[k]);
@@ -700,6 +700,25 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
           if (n < N && k < K) jb.dst1[(long long)k * ldt + n] = __float2bfloat16(tile[tx][j]);
         }
     }
+  } else if (jb.type == 3 || jb.type == 4) {
+    // fp32 vector -> zero-padded fp32 copy (type 3; dst0 reinterpreted as float*), or GLU linear [2F, K] -> bf16 rows
+    // remapped to [2Fp, ldb] (value rows at 0, gate rows at Fp) + transposed [K, ldt] (type 4)
+    const int N = jb.a, K = jb.b, ldb = jb.c, ldt = jb.d;
+    if (jb.type == 3) {
+      float* dst = reinterpret_cast<float*>(jb.dst0);
+      const int glu = K;  // b = 1: [2F] -> [2Fp] with the gate half moved to Fp
+      const int F = N / 2, Fp = (F + 63) / 64 * 64;
+      for (long long i = i0; i < N; i += stride) dst[(glu && i >= F) ? i - F + Fp : i] = jb.src[i];
+    } else {
+      const int F = N / 2, Fp = (F + 63) / 64 * 64;
+      for (long long i = i0; i < (long long)N * K; i += stride) {
+        const int n = (int)(i / K), k = (int)(i % K);
+        const int r = n >= F ? n - F + Fp : n;
+        const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
+        jb.dst0[(long long)r * ldb + k] = v;
+        if (jb.dst1) jb.dst1[(long long)k * ldt + r] = v;
+      }
+    }
   } else {
     for (long long i = i0; i < 64 * 320; i += stride) {
       const int co = (int)(i / 320), k = (int)(i % 320);
@@ -711,6 +730,38 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
   }
 }
 
+// word-boundary column (lightning.py:145-150): x[b, 1+t, C] = word_mask[b, t], x[b, 0, C] = cls[C]; and d cls[C]
+__global__ void wb_column_kernel(float* __restrict__ xs, const float* __restrict__ cls, const float* __restrict__ wm,
+                                 int B, int T, int ldx, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * (T + 1)) return;
+  const int tt = i % (T + 1), b = i / (T + 1);
+  xs[(long long)i * ldx + C] = tt == 0 ? cls[C] : wm[b * T + tt - 1];
+}
+__global__ void wb_column_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, int B, int T, int ldx, int C) {
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += dx[(long long)b * (T + 1) * ldx + C];
+  s = warp_sum(s);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    dcls[C] += t;
+  }
+}
+// grad[n, k] += tmp[row(n), k] for a padded weight-gradient scratch [Np, Kp]; glu: row(n) = n < F ? n : n - F + Fp
+__global__ void unpack_linear_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ grad, int N, int K, int Kp,
+                                           int glu) {
+  const int F = N / 2, Fp = (F + 63) / 64 * 64;
+  const long long total = (long long)N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    const int r = (glu && n >= F) ? n - F + Fp : n;
+    grad[i] += tmp[(long long)r * Kp + k];
+  }
+}
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db, int M,
                                    int N) {
   // block handles 64 columns x a slab of rows; threads: 64 columns x 4 row lanes
@@ -843,13 +894,18 @@ int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat
   return SVSR_OK;
 }
 int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,
-                 cudaStream_t s) {
-  meanpool_cls_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(a, cls, x_stream, B, T, HW, C);
+                 cudaStream_t s, int ldx) {
+  if (ldx <= 0) ldx = C;
+  meanpool_cls_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(a, cls, x_stream, B, T, HW, C,
+                                                                                      ldx);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s) {
-  meanpool_cls_bwd_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(dx, dout, dcls, B, T, HW, C);
+int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s,
+                     int ldx) {
+  if (ldx <= 0) ldx = C;
+  meanpool_cls_bwd_kernel<<<grid_for((long long)B * (T + 1) * (C / 8), 128), 128, 0, s>>>(dx, dout, dcls, B, T, HW, C,
+                                                                                          ldx);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -885,6 +941,21 @@ int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int
 int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
   dim3 grid(64, (unsigned)njobs);
   pack_all_kernel<<<grid, 256, 0, s>>>(jobs_dev);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int wb_column(float* xs, const float* cls, const float* wm, int B, int T, int ldx, int C, cudaStream_t s) {
+  wb_column_kernel<<<(B * (T + 1) + 127) / 128, 128, 0, s>>>(xs, cls, wm, B, T, ldx, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int wb_column_bwd(const float* dx, float* dcls, int B, int T, int ldx, int C, cudaStream_t s) {
+  wb_column_bwd_kernel<<<1, 256, 0, s>>>(dx, dcls, B, T, ldx, C);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int unpack_linear_wgrad(const float* tmp, float* grad, int N, int K, int Kp, int glu, cudaStream_t s) {
+  unpack_linear_wgrad_kernel<<<grid_for((long long)N * K, 256), 256, 0, s>>>(tmp, grad, N, K, Kp, glu);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

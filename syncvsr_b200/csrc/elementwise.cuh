@@ -50,9 +50,15 @@ int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat
 
 // x_stream[b, t+1, :] = mean over HW of a[b*T+t, :, :]; x_stream[b, 0, :] = cls  (fp32 [B,T+1,C])
 int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int B, int T, int HW, int C,
-                 cudaStream_t s);
+                 cudaStream_t s, int ldx = 0);  // ldx: row pitch of x_stream (0 = C)
 // dout[b*T+t, hw, :] = dx[b, t+1, :] / HW (bf16); dcls += sum_b dx[b,0,:]
-int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s);
+int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s,
+                     int ldx = 0);
+// word-boundary channel (lightning.py:145-150): column C of the stream = word_mask[b,t] (frames) / cls[C] (CLS row)
+int wb_column(float* xs, const float* cls, const float* wm, int B, int T, int ldx, int C, cudaStream_t s);
+int wb_column_bwd(const float* dx, float* dcls, int B, int T, int ldx, int C, cudaStream_t s);  // dcls[C] += sum_b
+// grad[N,K] += scratch[Np,Kp] (zero-padded weight-gradient scratch; glu = 1: gate rows live at Fp = ceil64(N/2))
+int unpack_linear_wgrad(const float* tmp, float* grad, int N, int K, int Kp, int glu, cudaStream_t s);
 
 // ---- weight packing (fp32 master -> bf16 operand layouts) and gradient unpacking ----
 int pack_conv_weight(const float* w, __nv_bfloat16* w_fprop, __nv_bfloat16* w_dgrad, int Cout, int Cin, int R, int S,
@@ -67,7 +73,8 @@ struct PackJob {
   const float* src;
   __nv_bfloat16* dst0;  // conv: fprop layout; linear: [N, ldb]; stem: [64, 320]
   __nv_bfloat16* dst1;  // conv: dgrad layout; linear: transposed [K, ldt] (may be null)
-  int type;             // 0 = conv [Cout,Cin,R,S], 1 = linear [N,K], 2 = stem
+  int type;             // 0 = conv [Cout,Cin,R,S], 1 = linear [N,K], 2 = stem, 3 = fp32 vector pad copy (a = N,
+                        // b = glu remap), 4 = GLU linear [2F,K] -> rows remapped to [2*ceil64(F), ldb]
   int a, b, c, d;       // conv: Cout, Cin, RS, -; linear: N, K, ldb, ldt
 };
 int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s);

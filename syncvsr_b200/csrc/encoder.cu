@@ -15,11 +15,11 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 template <int MAXI>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ y,
-                   float* __restrict__ inv_out, int M, int D, float eps) {
+                   float* __restrict__ inv_out, int M, int D, float eps, int norm_dim) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ni = D >> 5;
-  const float rs = rsqrtf((float)D);
+  const float rs = rsqrtf((float)norm_dim);
   for (int row = warp; row < M; row += nwarps) {
     const float* xr = x + (long long)row * D;
     float v[MAXI];
@@ -44,7 +44,7 @@ template <int MAXI>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
                    const float* __restrict__ inv_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb,
-                   float* __restrict__ dg, int M, int D, float eps) {
+                   float* __restrict__ dg, int M, int D, float eps, int norm_dim) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ni = D >> 5;
@@ -67,7 +67,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
         dgacc[i] += dv[i] * xv[i] * inv;
       }
     t = warp_sum(t);
-    const float coef = clamped ? 0.f : inv * inv * inv / (float)D * t;
+    const float coef = clamped ? 0.f : inv * inv * inv / (float)norm_dim * t;
 #pragma unroll
     for (int i = 0; i < MAXI; ++i)
       if (i < ni) {
@@ -351,24 +351,27 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv
   note_launch();       \
   SVSR_CHECK_CUDA(cudaGetLastError())
 
-int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s) {
+int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s,
+                int norm_dim) {
+  if (norm_dim <= 0) norm_dim = D;
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
   const int blocks = (M + 7) / 8 < 148 * 4 ? (M + 7) / 8 : 148 * 4;
   if (D <= 512)
-    rmsnorm_fwd_kernel<16><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps);
+    rmsnorm_fwd_kernel<16><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim);
   else
-    rmsnorm_fwd_kernel<32><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps);
+    rmsnorm_fwd_kernel<32><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
-                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s) {
+                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim) {
+  if (norm_dim <= 0) norm_dim = D;
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
   const int blocks = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
   if (D <= 512)
-    rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps);
+    rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
   else
-    rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps);
+    rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

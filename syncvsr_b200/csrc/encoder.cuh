@@ -7,10 +7,13 @@
 namespace svsr {
 
 // y[M,D] (bf16) = x / clamp(||x||_2 * D^-1/2, eps) * g ; inv[M] = 1 / clamp(...)
-int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s);
+// norm_dim (0 = D): the width the RMS is taken over when the row is zero-padded from norm_dim to D columns (the
+// word-boundary variant runs dim 513 on a 576-column pitch; g is then a zero-padded copy)
+int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s,
+                int norm_dim = 0);
 // dx[M,D] (fp32) += d rmsnorm ; dx_bf16 = bf16(dx) ; dg[D] += ...   (dy is the gradient wrt y, bf16)
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
-                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s);
+                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim = 0);
 
 // rotary cos/sin table for positions 0..n-1, 16 frequencies (rotary dim 32): tab[pos*32 + i] = cos, [pos*32+16+i] = sin
 int rotary_table(float* tab, int n, cudaStream_t s);

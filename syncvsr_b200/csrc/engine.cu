@@ -13,11 +13,20 @@ struct EncLayerRef {
   long long g_a, g_f;
   LinRef qkv, out, ff1, ff2;
   size_t xn_a, inv_a, qkvbuf, obuf, xn_f, inv_f, hbuf, ubuf;
+  size_t g_a_pad = 0, g_f_pad = 0;  // word-boundary variant: zero-padded fp32 copies of the RMSNorm weights
 };
 
 struct LrwEngine : EngineBase {
   svsr_lrw_config cfg;
   int M;  // tokens = B*(T+1)
+  // Encoder width: D = model.bert.dim (+1 with data.use_word_boundary, lightning.py:145-150). Every D-wide buffer has
+  // the pitch Dp = ceil64(D) and every 4D-wide one Fp = ceil64(4D); padding columns are exact zeros (the workspace is
+  // cleared once per binding and no kernel ever writes a non-zero there), so the padded GEMMs / norms equal the
+  // unpadded arithmetic. D = 512: Dp = D, Fp = F and nothing is padded.
+  int D = 0, Dp = 0, F = 0, Fp = 0;
+  bool padded = false;
+  size_t dg_pad = 0, bias_tmp = 0;
+  const float* word_mask = nullptr;  // device fp32 [B, T] of the current forward (word-boundary variant)
   Frontend fe;  // stem3d + resnet.layer1-4
 
   // model structure
@@ -42,7 +51,7 @@ struct LrwEngine : EngineBase {
   bool fwd_done = false;
   bool bwd_stage0_done = false;
 
-  float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * cfg.dim; }
+  float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * Dp; }
 };
 
 static int engine_build(LrwEngine& e, long long nodecay_base) {
@@ -52,8 +61,9 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   const svsr_lrw_config& c = e.cfg;
   SVSR_REQUIRE(c.B > 0 && c.T > 0 && c.H > 0 && c.W == c.H, "lrw: bad clip geometry B=%d T=%d H=%d W=%d", c.B, c.T,
                c.H, c.W);
-  SVSR_REQUIRE(c.dim == 512 && c.heads * 64 == 512, "lrw: encoder dim must be 512 with 8 heads of 64 (got %d/%d)",
-               c.dim, c.heads);
+  SVSR_REQUIRE((c.dim == 512 || c.dim == 513) && c.heads * 64 == 512,
+               "lrw: encoder dim must be 512 (or 513 with the word-boundary channel) with 8 heads of 64 (got %d/%d)", c.dim,
+               c.heads);
   SVSR_REQUIRE(c.depth >= 1 && c.depth <= 16, "lrw: depth %d out of range", c.depth);
   SVSR_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f, "lrw: ff_dropout %f out of [0,1)", c.ff_dropout);
   SVSR_REQUIRE(c.T + 1 <= 64, "lrw: sequence length %d too long for the attention core", c.T + 1);
@@ -61,6 +71,8 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
                "lrw: audio logits per frame (%d) must be a multiple of 64",
                c.audio_alignment * c.vq_groups * c.audio_vocab);
   e.M = c.B * (c.T + 1);
+  e.D = c.dim, e.Dp = (c.dim + 63) / 64 * 64, e.F = 4 * c.dim, e.Fp = (4 * c.dim + 63) / 64 * 64;
+  e.padded = e.Dp != e.D;
   Bump b;
 
   // ---- parameters (reference state-dict names) + packed operand storage ----
@@ -68,7 +80,21 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.bn_eps = c.bn_eps, e.bn_momentum = c.bn_momentum;
   RC(frontend_build(e, e.fe, "stem3d.0.weight", "stem3d.1", "resnet", b));
   e.cls_off = add_param(e.params, e.pc, "cls_token", {1, 1, c.dim});
-  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  const int D = e.D, Dp = e.Dp, inner = c.heads * 64, F = e.F, Fp = e.Fp;
+  // Linear [N, K] with a K pitch of ceil64(K) in its bf16 operand copy; glu: value / gate halves of the GEGLU
+  // projection start at rows 0 / ceil64(N/2) of the padded operand (only when N/2 is not a multiple of 64)
+  auto plin = [&](LinRef& l, const std::string& wname, const std::string& bname, int N, int K, bool glu) {
+    l.N = N, l.K = K;
+    l.w = add_param(e.params, e.pc, wname, {N, K});
+    l.b = bname.empty() ? -1 : add_param(e.params, e.pc, bname, {N});
+    l.Kp = (K + 63) / 64 * 64;
+    l.glu = (glu && e.padded) ? 1 : 0;
+    l.Np = l.glu ? 2 * ((N / 2 + 63) / 64 * 64) : N;
+    l.ldt = (l.Np + 63) / 64 * 64;
+    l.wb = b.take((size_t)l.Np * l.Kp * 2);
+    l.wt = b.take((size_t)l.Kp * l.ldt * 2);
+    l.bpad = l.glu ? b.take((size_t)l.Np * 4) : 0;
+  };
   e.enc.resize(c.depth);
   for (int i = 0; i < c.depth; ++i) {
     EncLayerRef& L = e.enc[i];
@@ -79,30 +105,38 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
     L.qkv.w = add_param(e.params, e.pc, a + ".1.to_q.weight", {inner, D});
     add_param(e.params, e.pc, a + ".1.to_k.weight", {inner, D});
     add_param(e.params, e.pc, a + ".1.to_v.weight", {inner, D});
-    L.qkv.ldt = 3 * inner;
-    L.qkv.wb = b.take((size_t)3 * inner * D * 2);
-    L.qkv.wt = b.take((size_t)D * 3 * inner * 2);
-    add_linear(e, L.out, a + ".1.to_out.weight", "", D, inner, b);
+    L.qkv.ldt = 3 * inner, L.qkv.Kp = Dp, L.qkv.Np = 3 * inner;
+    L.qkv.wb = b.take((size_t)3 * inner * Dp * 2);
+    L.qkv.wt = b.take((size_t)Dp * 3 * inner * 2);
+    plin(L.out, a + ".1.to_out.weight", "", D, inner, false);
     L.g_f = add_param(e.params, e.pc, f + ".0.g", {D});
-    add_linear(e, L.ff1, f + ".1.ff.0.proj.weight", f + ".1.ff.0.proj.bias", 2 * F, D, b);
-    add_linear(e, L.ff2, f + ".1.ff.3.weight", f + ".1.ff.3.bias", D, F, b);
-    L.xn_a = b.take((size_t)e.M * D * 2), L.inv_a = b.take((size_t)e.M * 4);
+    plin(L.ff1, f + ".1.ff.0.proj.weight", f + ".1.ff.0.proj.bias", 2 * F, D, true);
+    plin(L.ff2, f + ".1.ff.3.weight", f + ".1.ff.3.bias", D, F, false);
+    L.xn_a = b.take((size_t)e.M * Dp * 2), L.inv_a = b.take((size_t)e.M * 4);
     L.qkvbuf = b.take((size_t)e.M * 3 * inner * 2), L.obuf = b.take((size_t)e.M * inner * 2);
-    L.xn_f = b.take((size_t)e.M * D * 2), L.inv_f = b.take((size_t)e.M * 4);
-    L.hbuf = b.take((size_t)e.M * 2 * F * 2), L.ubuf = b.take((size_t)e.M * F * 2);
+    L.xn_f = b.take((size_t)e.M * Dp * 2), L.inv_f = b.take((size_t)e.M * 4);
+    L.hbuf = b.take((size_t)e.M * 2 * Fp * 2), L.ubuf = b.take((size_t)e.M * Fp * 2);
+    if (e.padded) L.g_a_pad = b.take((size_t)Dp * 4), L.g_f_pad = b.take((size_t)Dp * 4);
   }
-  add_linear(e, e.cat, "category_classifier.weight", "category_classifier.bias", c.num_labels, D, b);
+  plin(e.cat, "category_classifier.weight", "category_classifier.bias", c.num_labels, D, false);
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
-  add_linear(e, e.aud, "audio_projection.weight", "audio_projection.bias", AGV, D, b);
+  plin(e.aud, "audio_projection.weight", "audio_projection.bias", AGV, D, false);
   e.cat_ld = (c.num_labels + 63) / 64 * 64;
 
   // ---- activations ----
   frontend_alloc(e, e.fe, b);
+  if (e.padded) {  // the padded weight-gradient scratch of the widest Linear can exceed the largest conv's
+    size_t need = (size_t)e.enc[0].ff1.Np * e.enc[0].ff1.Kp * 4;
+    if ((size_t)AGV * Dp * 4 > need) need = (size_t)AGV * Dp * 4;
+    if (need > (size_t)9 * 512 * 512 * 4) e.wgrad_tmp = b.take(need);
+    e.bias_tmp = b.take((size_t)e.enc[0].ff1.Np * 4);
+    e.dg_pad = b.take((size_t)2 * c.depth * Dp * 4);
+  }
   const size_t n0 = (size_t)e.N * e.fe.H0 * e.fe.H0 * 64;
   const size_t n1 = (size_t)e.N * e.fe.H1 * e.fe.H1 * 64;
-  e.xs = b.take((size_t)(2 * c.depth + 1) * e.M * D * 4);
-  e.lastb_cls = b.take((size_t)c.B * D * 2);
-  e.lastb_frames = b.take((size_t)e.N * D * 2);
+  e.xs = b.take((size_t)(2 * c.depth + 1) * e.M * Dp * 4);
+  e.lastb_cls = b.take((size_t)c.B * Dp * 2);
+  e.lastb_frames = b.take((size_t)e.N * Dp * 2);
   e.logits_a = b.take((size_t)e.N * AGV * 4);
   e.dlogits_a = b.take((size_t)e.N * AGV * 2);
   e.logits_c = b.take((size_t)c.B * e.cat_ld * 4);
@@ -111,16 +145,16 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.bad_token = b.take(sizeof(int));
   e.rot = b.take((size_t)(c.T + 1) * 32 * 4);
   // ---- backward scratch ----
-  e.dx = b.take((size_t)e.M * D * 4);
-  for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * D * 2);
-  e.t_du = b.take((size_t)e.M * F * 2);
-  for (int i = 0; i < 2; ++i) e.t_dh[i] = b.take((size_t)e.M * 2 * F * 2);
-  e.t_dyn = b.take((size_t)e.M * D * 2);
+  e.dx = b.take((size_t)e.M * Dp * 4);
+  for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * Dp * 2);
+  e.t_du = b.take((size_t)e.M * Fp * 2);
+  for (int i = 0; i < 2; ++i) e.t_dh[i] = b.take((size_t)e.M * 2 * Fp * 2);
+  e.t_dyn = b.take((size_t)e.M * Dp * 2);
   e.t_do = b.take((size_t)e.M * inner * 2);
   for (int i = 0; i < 2; ++i) e.t_dqkv[i] = b.take((size_t)e.M * 3 * inner * 2);
-  e.pack_jobs = b.take(128 * sizeof(PackJob));
+  e.pack_jobs = b.take(192 * sizeof(PackJob));
   e.ws_bytes = b.off;
-  {  // parity-mode scratch (only allocated by the caller when forward_precise is used)
+  {  // parity-mode scratch (only allocated by the caller when forward_precise is used; dim 512 only)
     Bump pb;
     const size_t AGVp = (size_t)AGV;
     e.p_patches = pb.take(n0 * 4);
@@ -153,37 +187,100 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
 // ------------------------------------------------------------------------------------------------
 static int engine_pack(LrwEngine& e, cudaStream_t s) {
   if (!e.pack_table_ready) {  // build the job table once per binding (pointers are static afterwards)
+    // one clear of the whole workspace per binding: every padding row / column of the packed operands (category head
+    // 500 -> 512, word-boundary 513 -> 576, ...) and of the activation pitches is zero from here on
+    SVSR_CHECK_CUDA(cudaMemsetAsync(e.WS, 0, e.ws_bytes, s));
     std::vector<PackJob> jobs;
     frontend_pack_jobs(e, e.fe, jobs);
-    auto lin = [&](const LinRef& l) { jobs.push_back({e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), 1, l.N, l.K, l.K, l.ldt}); };
-    for (auto& L : e.enc) lin(L.qkv), lin(L.out), lin(L.ff1), lin(L.ff2);
+    auto lin = [&](const LinRef& l) {
+      jobs.push_back({e.P + l.w, e.ws<bf16>(l.wb), e.ws<bf16>(l.wt), l.glu ? 4 : 1, l.N, l.K, l.Kp, l.ldt});
+      if (l.glu) jobs.push_back({e.P + l.b, reinterpret_cast<bf16*>(e.ws<float>(l.bpad)), nullptr, 3, l.N, 1, 0, 0});
+    };
+    for (auto& L : e.enc) {
+      lin(L.qkv), lin(L.out), lin(L.ff1), lin(L.ff2);
+      if (e.padded) {
+        jobs.push_back({e.P + L.g_a, reinterpret_cast<bf16*>(e.ws<float>(L.g_a_pad)), nullptr, 3, e.D, 0, 0, 0});
+        jobs.push_back({e.P + L.g_f, reinterpret_cast<bf16*>(e.ws<float>(L.g_f_pad)), nullptr, 3, e.D, 0, 0, 0});
+      }
+    }
     lin(e.cat), lin(e.aud);
-    SVSR_REQUIRE(jobs.size() <= 128, "lrw: too many pack jobs (%zu)", jobs.size());
+    SVSR_REQUIRE(jobs.size() <= 192, "lrw: too many pack jobs (%zu)", jobs.size());
     e.n_pack_jobs = (int)jobs.size();
     SVSR_CHECK_CUDA(cudaMemcpyAsync(e.ws<PackJob>(e.pack_jobs), jobs.data(), jobs.size() * sizeof(PackJob),
                                     cudaMemcpyHostToDevice, s));
     SVSR_CHECK_CUDA(cudaStreamSynchronize(s));  // `jobs` is a stack vector
-    // padding columns of transposed operands (category head: 500 -> 512) stay zero forever
-    if (e.cat.ldt != e.cat.N) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<bf16>(e.cat.wt), 0, (size_t)e.cat.K * e.cat.ldt * 2, s));
     RC(rotary_table(e.ws<float>(e.rot), e.cfg.T + 1, s));
     e.pack_table_ready = true;
   }
   return pack_all_weights(e.ws<PackJob>(e.pack_jobs), e.n_pack_jobs, s);
 }
 
+// Linear forward / input gradient / weight gradient on the (possibly K- or N-padded) bf16 operand copies
+static int lw_fwd(const LrwEngine& e, const bf16* x, int ldx, int M, const LinRef& l, void* out, int ldc, int out_fp32,
+                  const void* resid, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = x, p.a_N = M, p.a_C = ldx, p.cin = l.Kp, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wb), p.b_rows = l.Np, p.b_cols = l.Kp;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
+  p.bias = l.b < 0 ? nullptr : (l.glu ? e.ws<float>(l.bpad) : e.P + l.b);
+  p.resid = resid, p.resid_fp32 = 1;
+  return igemm_launch(p, s);
+}
+static int lw_dgrad(const LrwEngine& e, const bf16* dy, int ldy, int M, const LinRef& l, void* out, int ldc,
+                    cudaStream_t s) {
+  IgemmProblem p;
+  p.a = dy, p.a_N = M, p.a_C = ldy, p.cin = l.ldt, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wt), p.b_rows = l.K, p.b_cols = l.ldt;
+  p.out = out, p.out_fp32 = 0, p.ldc = ldc;
+  return igemm_launch(p, s);
+}
+static int lw_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, int ldx, int M, const LinRef& l,
+                    cudaStream_t s) {
+  WgradProblem p;
+  p.a = dy, p.a_N = M, p.a_C = ldy, p.a_cin = l.ldt, p.ntaps = 1;
+  p.b = x, p.b_C = ldx, p.n_cols = l.Kp;
+  p.k_N = M;
+  if (l.Kp == l.K && !l.glu) {  // rows of the arena matrix are 16-byte aligned: accumulate in place
+    p.out = e.G + l.w, p.ldo = l.K, p.m_valid = l.N;
+    RC(wgrad_launch(p, s));
+    if (l.b >= 0) RC(colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s));
+    return SVSR_OK;
+  }
+  // word-boundary widths (K = 513 / 2052): gradient into a zero-padded scratch, then added into the arena layout
+  float* tmp = e.ws<float>(e.wgrad_tmp);
+  SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, (size_t)l.Np * l.Kp * 4, s));
+  p.out = tmp, p.ldo = l.Kp, p.m_valid = l.Np;
+  RC(wgrad_launch(p, s));
+  RC(unpack_linear_wgrad(tmp, e.G + l.w, l.N, l.K, l.Kp, l.glu, s));
+  if (l.b >= 0) {
+    if (!l.glu) return colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s);
+    float* bt = e.ws<float>(e.bias_tmp);
+    SVSR_CHECK_CUDA(cudaMemsetAsync(bt, 0, (size_t)l.Np * 4, s));
+    RC(colsum_bf16(dy, ldy, bt, M, l.Np, s));
+    RC(unpack_linear_wgrad(bt, e.G + l.b, l.N, 1, 1, 1, s));
+  }
+  return SVSR_OK;
+}
+
 static int engine_forward(LrwEngine& e, const float* videos, const long long* tokens, long long tok_stride_b,
                           const long long* labels, const float* soft_labels, int train, uint32_t skip_mask,
                           unsigned long long dropout_seed, float* metrics, int videos_only, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
-  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  const int D = e.D, Dp = e.Dp, inner = c.heads * 64, Fp = e.Fp;
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));  // acc + bad_token
   // ---- stem3d + resnet.layer1-4 (lightning.py:49-54,112-117) ----
   const bf16* x = nullptr;
   RC(frontend_forward(e, e.fe, videos, train, &x, s));
-  // ---- mean((2,3)) + CLS concat (lightning.py:118,148-150) ----
+  // ---- mean((2,3)) [+ word-boundary channel] + CLS concat (lightning.py:118,145-150) ----
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
-  RC(meanpool_cls(x, e.P + e.cls_off, e.xs_buf(0), c.B, c.T, HW4, D, s));
-  if (videos_only) return SVSR_OK;
+  RC(meanpool_cls(x, e.P + e.cls_off, e.xs_buf(0), c.B, c.T, HW4, 512, s, Dp));
+  if (videos_only) return SVSR_OK;  // forward_videos (lightning.py:112-119) ends before the word-boundary concat
+  if (e.padded) {
+    SVSR_REQUIRE(e.word_mask, "lrw: dim 513 (data.use_word_boundary) needs the word_mask input");
+    RC(wb_column(e.xs_buf(0), e.P + e.cls_off, e.word_mask, c.B, c.T, Dp, 512, s));
+  }
 
   // ---- encoder (lightning.py:158) ----
   for (int i = 0; i < c.depth; ++i) {
@@ -191,32 +288,34 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     float* xa = e.xs_buf(2 * i);
     float* xf = e.xs_buf(2 * i + 1);
     float* xo = e.xs_buf(2 * i + 2);
+    const float* g_a = e.padded ? e.ws<float>(L.g_a_pad) : e.P + L.g_a;
+    const float* g_f = e.padded ? e.ws<float>(L.g_f_pad) : e.P + L.g_f;
     if (skip_mask & (1u << (2 * i))) {
-      SVSR_CHECK_CUDA(cudaMemcpyAsync(xf, xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+      SVSR_CHECK_CUDA(cudaMemcpyAsync(xf, xa, (size_t)e.M * Dp * 4, cudaMemcpyDeviceToDevice, s));
     } else {
-      RC(rmsnorm_fwd(xa, e.P + L.g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, D, 1e-8f, s));
-      RC(linear_fwd(e, e.ws<bf16>(L.xn_a), e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, 0, s));
+      RC(rmsnorm_fwd(xa, g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, Dp, 1e-8f, s, D));
+      RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s));
       RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
                        s));
-      RC(linear_fwd(e, e.ws<bf16>(L.obuf), e.M, L.out, xf, D, 1, xa, 1, s));
+      RC(lw_fwd(e, e.ws<bf16>(L.obuf), inner, e.M, L.out, xf, Dp, 1, xa, s));
     }
     if (skip_mask & (1u << (2 * i + 1))) {
-      SVSR_CHECK_CUDA(cudaMemcpyAsync(xo, xf, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+      SVSR_CHECK_CUDA(cudaMemcpyAsync(xo, xf, (size_t)e.M * Dp * 4, cudaMemcpyDeviceToDevice, s));
     } else {
-      RC(rmsnorm_fwd(xf, e.P + L.g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, D, 1e-8f, s));
-      RC(linear_fwd(e, e.ws<bf16>(L.xn_f), e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * F, 0, nullptr, 0, s));
-      RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, F, train ? c.ff_dropout : 0.f,
+      RC(rmsnorm_fwd(xf, g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, Dp, 1e-8f, s, D));
+      RC(lw_fwd(e, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * Fp, 0, nullptr, s));
+      RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, Fp, train ? c.ff_dropout : 0.f,
                    dropout_seed + 0x1000ULL * (unsigned long long)i, s));
-      RC(linear_fwd(e, e.ws<bf16>(L.ubuf), e.M, L.ff2, xo, D, 1, xf, 1, s));
+      RC(lw_fwd(e, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, xo, Dp, 1, xf, s));
     }
   }
   const float* last = e.xs_buf(2 * c.depth);
-  RC(split_cast_last(last, e.ws<bf16>(e.lastb_cls), e.ws<bf16>(e.lastb_frames), c.B, c.T, D, s));
+  RC(split_cast_last(last, e.ws<bf16>(e.lastb_cls), e.ws<bf16>(e.lastb_frames), c.B, c.T, Dp, s));
 
   // ---- heads + losses (lightning.py:161-174) ----
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
-  RC(linear_fwd(e, e.ws<bf16>(e.lastb_cls), c.B, e.cat, e.ws<float>(e.logits_c), e.cat_ld, 1, nullptr, 0, s));
-  RC(linear_fwd(e, e.ws<bf16>(e.lastb_frames), e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, 0, s));
+  RC(lw_fwd(e, e.ws<bf16>(e.lastb_cls), Dp, c.B, e.cat, e.ws<float>(e.logits_c), e.cat_ld, 1, nullptr, s));
+  RC(lw_fwd(e, e.ws<bf16>(e.lastb_frames), Dp, e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, s));
   const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
   RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing,
                  e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<double>(e.acc), 1.0f / (float)c.B, s));
@@ -279,6 +378,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
                                   long long tok_stride_b, const long long* labels, const float* soft_labels, int train,
                                   uint32_t skip_mask, float* metrics, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
+  SVSR_REQUIRE(!e.padded, "lrw: the parity-mode forward supports dim 512 only");
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.fe.stats_arena), 0, e.fe.stats_arena_bytes, s));
@@ -377,7 +477,7 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     SVSR_REQUIRE(e.bwd_stage0_done, "lrw backward stage 1 called before stage 0");
   }
   const svsr_lrw_config& c = e.cfg;
-  const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  const int D = e.D, Dp = e.Dp, inner = c.heads * 64, Fp = e.Fp;
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   float* dx = e.ws<float>(e.dx);
   SideQueue sq(e, s);
@@ -388,31 +488,36 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)c.B * e.cat_ld, grad_scale, s));
   }
+  if (e.padded) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<float>(e.dg_pad), 0, (size_t)2 * c.depth * Dp * 4, s));
   // ---- heads: d last_hidden_state (fp32 stream gradient), weight/bias gradients ----
   RC(sq.fork());
-  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<bf16>(e.lastb_cls), c.B, e.cat, w));
-  RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), AGV, e.ws<bf16>(e.lastb_frames), e.N, e.aud, w));
+  RC(lw_wgrad(e, e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<bf16>(e.lastb_cls), Dp, c.B, e.cat, w));
+  RC(lw_wgrad(e, e.ws<bf16>(e.dlogits_a), AGV, e.ws<bf16>(e.lastb_frames), Dp, e.N, e.aud, w));
   {
     IgemmProblem p;  // CLS rows: dx[b, 0, :] = dlogits_c[b] . Wc
     p.a = e.ws<bf16>(e.dlogits_c), p.a_N = c.B, p.a_C = e.cat_ld, p.cin = e.cat.ldt, p.ntaps = 1;
     p.o_N = c.B, p.OH = 1, p.OW = 1;
     p.b = e.ws<bf16>(e.cat.wt), p.b_rows = D, p.b_cols = e.cat.ldt;
-    p.out = dx, p.out_fp32 = 1, p.ldc = D, p.o_H = 1, p.o_W = c.T + 1, p.o_ow = 0;
+    p.out = dx, p.out_fp32 = 1, p.ldc = Dp, p.o_H = 1, p.o_W = c.T + 1, p.o_ow = 0;
     RC(igemm_launch(p, s));
     IgemmProblem q;  // frame rows: dx[b, 1+t, :] = dlogits_a[b, t] . Wa
     q.a = e.ws<bf16>(e.dlogits_a), q.a_N = c.B, q.a_H = 1, q.a_W = c.T, q.a_C = AGV, q.cin = AGV, q.ntaps = 1;
     q.o_N = c.B, q.OH = 1, q.OW = c.T;
     q.b = e.ws<bf16>(e.aud.wt), q.b_rows = D, q.b_cols = e.aud.ldt;
-    q.out = dx, q.out_fp32 = 1, q.ldc = D, q.o_H = 1, q.o_W = c.T + 1, q.o_ow = 1;
+    q.out = dx, q.out_fp32 = 1, q.ldc = Dp, q.o_H = 1, q.o_W = c.T + 1, q.o_ow = 1;
     RC(igemm_launch(q, s));
   }
   int xb = 0;  // which dxb buffer holds the current bf16 copy of the stream gradient
-  RC(cast_f32_to_bf16(dx, e.ws<bf16>(e.dxb[xb]), (long long)e.M * D, s));
+  RC(cast_f32_to_bf16(dx, e.ws<bf16>(e.dxb[xb]), (long long)e.M * Dp, s));
   RC(sq.end_unit());
 
   // ---- encoder, reversed: one unit per sublayer ----
   for (int i = c.depth - 1; i >= 0; --i) {
     EncLayerRef& L = e.enc[i];
+    const float* g_a = e.padded ? e.ws<float>(L.g_a_pad) : e.P + L.g_a;
+    const float* g_f = e.padded ? e.ws<float>(L.g_f_pad) : e.P + L.g_f;
+    float* dg_a = e.padded ? e.ws<float>(e.dg_pad) + (size_t)(2 * i) * Dp : e.G + L.g_a;
+    float* dg_f = e.padded ? e.ws<float>(e.dg_pad) + (size_t)(2 * i + 1) * Dp : e.G + L.g_f;
     if (!(e.last_skip & (1u << (2 * i + 1)))) {
       bf16* dxb = e.ws<bf16>(e.dxb[xb]);
       bf16* dxb_next = e.ws<bf16>(e.dxb[(xb + 1) % 3]);  // 3-deep: unit k-1's side work may still read its copy
@@ -420,15 +525,14 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
       bf16* dh = e.ws<bf16>(e.t_dh[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
       RC(sq.fork());  // dxb complete
-      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.ubuf), e.M, L.ff2, w));
-      RC(linear_dgrad(e, dxb, D, e.M, L.ff2, du, F, 0, s));
-      RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, F, e.last_train ? c.ff_dropout : 0.f,
+      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, w));
+      RC(lw_dgrad(e, dxb, Dp, e.M, L.ff2, du, Fp, s));
+      RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, Fp, e.last_train ? c.ff_dropout : 0.f,
                    e.last_seed + 0x1000ULL * (unsigned long long)i, s));
       RC(sq.fork());  // dh complete
-      RC(linear_wgrad(e, dh, 2 * F, e.ws<bf16>(L.xn_f), e.M, L.ff1, w));
-      RC(linear_dgrad(e, dh, 2 * F, e.M, L.ff1, dyn, D, 0, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), e.P + L.g_f, e.ws<float>(L.inv_f), dx, dxb_next, e.G + L.g_f, e.M, D,
-                     1e-8f, s));
+      RC(lw_wgrad(e, dh, 2 * Fp, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, w));
+      RC(lw_dgrad(e, dh, 2 * Fp, e.M, L.ff1, dyn, Dp, s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), g_f, e.ws<float>(L.inv_f), dx, dxb_next, dg_f, e.M, Dp, 1e-8f, s, D));
       xb = (xb + 1) % 3;
       RC(sq.end_unit());
     }
@@ -439,22 +543,27 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
       bf16* dqkv = e.ws<bf16>(e.t_dqkv[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
       RC(sq.fork());
-      RC(linear_wgrad(e, dxb, D, e.ws<bf16>(L.obuf), e.M, L.out, w));
-      RC(linear_dgrad(e, dxb, D, e.M, L.out, d_o, inner, 0, s));
+      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.obuf), inner, e.M, L.out, w));
+      RC(lw_dgrad(e, dxb, Dp, e.M, L.out, d_o, inner, s));
       RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s));
       RC(sq.fork());
-      RC(linear_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), e.M, L.qkv, w));
-      RC(linear_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, D, 0, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), e.P + L.g_a, e.ws<float>(L.inv_a), dx, dxb_next, e.G + L.g_a, e.M, D, 1e-8f,
-                     s));
+      RC(lw_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, w));
+      RC(lw_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, Dp, s));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), g_a, e.ws<float>(L.inv_a), dx, dxb_next, dg_a, e.M, Dp, 1e-8f, s, D));
       xb = (xb + 1) % 3;
       RC(sq.end_unit());
     }
   }
+  if (e.padded)  // RMSNorm weight gradients: padded scratch -> arena
+    for (int i = 0; i < c.depth; ++i) {
+      RC(unpack_linear_wgrad(e.ws<float>(e.dg_pad) + (size_t)(2 * i) * Dp, e.G + e.enc[i].g_a, D, 1, 1, 0, s));
+      RC(unpack_linear_wgrad(e.ws<float>(e.dg_pad) + (size_t)(2 * i + 1) * Dp, e.G + e.enc[i].g_f, D, 1, 1, 0, s));
+    }
 
   // ---- mean pool / CLS ----
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
-  RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, D, s));
+  RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, 512, s, Dp));
+  if (e.padded) RC(wb_column_bwd(dx, e.G + e.cls_off, c.B, c.T, Dp, 512, s));
   e.bwd_stage0_done = true;
   if (stage == 0) return sq.join();
   }  // stage <= 0
@@ -520,9 +629,10 @@ int svsr_lrw_pack_weights(void* h, void* stream) {
   return engine_pack(*e, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
-                     const float* soft_labels, int train, uint32_t skip_mask, uint64_t dropout_seed, float* metrics,
-                     void* stream) {
+                     const float* soft_labels, const float* word_mask, int train, uint32_t skip_mask,
+                     uint64_t dropout_seed, float* metrics, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
+  e->word_mask = word_mask;
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
   SVSR_REQUIRE(videos && tokens && metrics, "lrw_forward: null input");
   SVSR_REQUIRE(tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
@@ -580,11 +690,11 @@ int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* 
     return SVSR_OK;
   };
   if (n == "last_hidden_state") {
-    *ptr = e->xs_buf(2 * c.depth), *numel = (int64_t)e->M * c.dim, *dtype = 0;
+    *ptr = e->xs_buf(2 * c.depth), *numel = (int64_t)e->M * e->Dp, *dtype = 0;  // row pitch Dp = ceil64(dim)
     return SVSR_OK;
   }
   if (n == "inputs_embeds") {
-    *ptr = e->xs_buf(0), *numel = (int64_t)e->M * c.dim, *dtype = 0;
+    *ptr = e->xs_buf(0), *numel = (int64_t)e->M * e->Dp, *dtype = 0;
     return SVSR_OK;
   }
   if (n == "logits_audio") return set(e->logits_a, (int64_t)e->N * AGV, 0);

@@ -62,6 +62,9 @@ struct LinRef {
   int N, K;
   size_t wb, wt;  // bf16 [N, K] and transposed [K, ldt]
   int ldt;
+  // LRW word-boundary variant (engine.cu): K pitch of wb, rows of the padded operand, GEGLU row remap, padded bias
+  int Kp = 0, Np = 0, glu = 0;
+  size_t bpad = 0;
 };
 
 // The parameter arena is [decayed (ndim >= 2) | non-decayed]; `nodecay_base` is where the second region starts

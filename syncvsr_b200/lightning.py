@@ -76,8 +76,6 @@ class TransformerLightningModule(nn.Module):
         self.lambda_audio = float(_cfg_get(config, "optim.lambda_audio", 10.0))
         self.label_smoothing = float(_cfg_get(config, "train.label_smoothing", 0.0))
         self.use_wb = bool(_cfg_get(config, "data.use_word_boundary", False))
-        if self.use_wb:
-            raise SvsrError("data.use_word_boundary=True (hidden dim 513) is not built yet in the sm_100a path")
         if _cfg_get(config, "model.bert.type", "x-transformers") != "x-transformers":
             raise SvsrError("only model.bert.type == 'x-transformers' is implemented natively")
 
@@ -92,7 +90,9 @@ class TransformerLightningModule(nn.Module):
         self.audio_alignment = int(_cfg_get(config, "model.audio_alignment", a))
         self.vq_groups = int(_cfg_get(config, "model.vq_groups", g))
         self.audio_vocab_size = int(_cfg_get(config, "model.audio_vocab_size", v))
-        self.dim = int(_cfg_get(config, "model.bert.dim", 512))
+        # lightning.py:46-47: the word-boundary indicator becomes one extra hidden channel (dim 513)
+        self.dim = int(_cfg_get(config, "model.bert.dim", 512)) + (1 if self.use_wb else 0)
+        self._dim_pitch = (self.dim + 63) // 64 * 64  # row pitch of the engine's dim-wide tensors
         self.depth = int(_cfg_get(config, "model.bert.depth", 12))
         self.heads = int(_cfg_get(config, "model.bert.heads", 8))
         self.layer_dropout = float(_cfg_get(config, "model.bert.layer_dropout", 0.0))
@@ -174,6 +174,8 @@ class TransformerLightningModule(nn.Module):
                 n *= s
             view = self._flat_p[off.value: off.value + n].view(shp)
             self._init_param(key, view, gen)
+            if key == "cls_token" and self.use_wb:
+                view[0, 0, -1] = 0.0  # [CLS] is not part of word_mask (lightning.py:109-110)
             p = nn.Parameter(view)
             self._register(key, p, is_buffer=False)
             self._param_views[key] = p
@@ -215,7 +217,7 @@ class TransformerLightningModule(nn.Module):
             bound = 1.0 / math.sqrt(shp[1])
             view.copy_((torch.rand(shp, generator=gen) * 2 - 1) * bound)
         elif view.dim() == 1:  # Linear bias
-            fan_in = 2048 if "ff.3" in key else 512
+            fan_in = 4 * 512 if "ff.3" in key else 512
             bound = 1.0 / math.sqrt(fan_in)
             view.copy_((torch.rand(shp, generator=gen) * 2 - 1) * bound)
 
@@ -287,7 +289,7 @@ class TransformerLightningModule(nn.Module):
         B, _, T, _, _ = videos.shape
         check(lib().svsr_lrw_forward_videos(self._h, C.c_void_p(videos.data_ptr()), C.c_int(int(self.training)),
                                             self._stream()), "svsr_lrw_forward_videos")
-        return self._named_tensor("inputs_embeds", (B, T + 1, self.dim))[:, 1:, :].clone()
+        return self._named_tensor("inputs_embeds", (B, T + 1, self._dim_pitch))[:, 1:, :512].clone()
 
     def forward(self, videos: torch.Tensor, audio_tokens: torch.Tensor, labels: torch.Tensor,
                 word_mask: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -300,6 +302,11 @@ class TransformerLightningModule(nn.Module):
             raise ValueError(f"audio_tokens must be [B, >=T*{self.audio_alignment}, {self.vq_groups}]")
         if audio_tokens.shape[1] < T * self.audio_alignment:
             raise ValueError("audio_tokens has fewer than seq_len * audio_alignment rows")
+        wm = None
+        if self.use_wb:  # [B, T] 0/1 indicator of the frames inside the target word (data.py:58-64)
+            wm = word_mask.to(self.device_, torch.float32).contiguous()
+            if wm.shape != (B, T):
+                raise ValueError(f"word_mask must be [B, T] = {(B, T)} with data.use_word_boundary, got {tuple(wm.shape)}")
         hard = soft = None
         if labels.dtype in (torch.long, torch.int32, torch.int64):
             hard = labels.long().contiguous()
@@ -313,7 +320,8 @@ class TransformerLightningModule(nn.Module):
         check(lib().svsr_lrw_forward(
             self._h, C.c_void_p(videos.data_ptr()), C.c_void_p(audio_tokens.data_ptr()),
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
-            C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_int(int(self.training)), C.c_uint32(skip),
+            C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_void_p(wm.data_ptr() if wm is not None else 0),
+            C.c_int(int(self.training)), C.c_uint32(skip),
             C.c_uint64(random.getrandbits(63) if (self.training and self.ff_dropout > 0) else 0),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         if self.training:
@@ -329,6 +337,8 @@ class TransformerLightningModule(nn.Module):
                         word_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Parity-mode forward (fp32 activations, split-bf16 tensor-core operands; csrc/precise.cuh): same outputs as
         forward() at fp32-class accuracy. Forward only; `last_hidden_state()` / `logits_audio()` read its results."""
+        if self.use_wb:
+            raise SvsrError("forward_precise (parity mode) supports the dim-512 (no word boundary) configuration only")
         videos = videos.to(self.device_, torch.float32).contiguous()
         audio_tokens = audio_tokens.to(self.device_, torch.long).contiguous()
         labels = labels.to(self.device_)
@@ -365,7 +375,7 @@ class TransformerLightningModule(nn.Module):
     # named intermediate tensors (parity tests)
     def last_hidden_state(self) -> torch.Tensor:
         B, T, _, _ = self._shape_key
-        return self._named_tensor("last_hidden_state", (B, T + 1, self.dim)).clone()
+        return self._named_tensor("last_hidden_state", (B, T + 1, self._dim_pitch))[:, :, : self.dim].clone()
 
     def logits_audio(self) -> torch.Tensor:
         B, T, _, _ = self._shape_key

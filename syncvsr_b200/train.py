@@ -111,3 +111,27 @@ class DataParallelStep:
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
         self.opt.step(lr=lr, grad_div=float(self.world))
         return metrics
+
+
+class SentenceDataParallelStep:
+    """The same data-parallel step for the LRS sentence-level module (syncvsr_b200.e2e.E2E): zero_grad -> forward ->
+    backward -> ONE all-reduce(SUM) of the flat gradient arena -> fused clip + AdamW (LRS/video/lightning.py:89-96,
+    gradient_clip_val 5.0, main.py:33-49). BatchNorm statistics stay per rank, as in the reference."""
+
+    def __init__(self, module, optimizer: FusedAdamW, group=None, warmup: int = 0, total: int = 1):
+        self.module, self.opt, self.group = module, optimizer, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.warmup, self.total, self.global_step = warmup, total, 0
+
+    def __call__(self, x, lengths, audios, label):
+        m = self.module
+        self.opt.zero_grad()
+        with torch.no_grad():
+            out = m(x, lengths, audios, label)
+        check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
+        if self.world > 1:
+            dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        self.global_step += 1
+        lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
+        self.opt.step(lr=lr, grad_div=float(self.world))
+        return out

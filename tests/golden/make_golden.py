@@ -19,17 +19,31 @@ from oracle import ref_loader as rl  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
-def run_case(name: str, B: int, S: int, A: int, V: int, depth: int, seed_p: int, seed_x: int, extra_tokens: int):
+def wb_mask(B: int, T: int = 29, seed: int = 7):
+    """[B, T] 0/1 word-boundary indicator: a centred run of U{5..20} frames (data.py:58-64)."""
+    g = torch.Generator().manual_seed(seed)
+    wm = torch.zeros(B, T)
+    for b in range(B):
+        n = int(torch.randint(5, 21, (1,), generator=g))
+        s0 = (T - n) // 2
+        wm[b, s0 : s0 + n] = 1.0
+    return wm
+
+
+def run_case(name: str, B: int, S: int, A: int, V: int, depth: int, seed_p: int, seed_x: int, extra_tokens: int,
+             wb: bool = False):
     ref = rl.load_reference_lrw()
-    cfg = rl.reference_config(depth=depth)
+    cfg = rl.reference_config(depth=depth, use_wb=wb)
     m = ref.TransformerLightningModule(cfg).train()
     G = 2
     if (A, V) != (4, 320):  # BASELINE.json config 1 (alignment=2, vocab=320): the reference derives these from the
         m.audio_alignment, m.audio_vocab_size = A, V  # codec path string, so set the attributes it reads at run time
         m.audio_projection = torch.nn.Linear(512, A * G * V)
-    P = O.make_params(seed_p, depth=depth, n_audio=A * G * V)
+    P = O.make_params(seed_p, depth=depth, n_audio=A * G * V, dim=513 if wb else 512)
     m.load_state_dict(P, strict=False)
     videos, tokens, labels, wm = O.make_inputs(seed_x, B, S=S, A=A, V=V, extra_tokens=extra_tokens)
+    if wb:
+        wm = wb_mask(B)
 
     cap = {}
     m.encoder.register_forward_hook(lambda mod, i, o: cap.__setitem__("last_hidden_state", o.detach()))
@@ -44,7 +58,8 @@ def run_case(name: str, B: int, S: int, A: int, V: int, depth: int, seed_p: int,
 
     fx = {
         "meta": dict(B=B, S=S, A=A, G=G, V=V, depth=depth, seed_p=seed_p, seed_x=seed_x, extra_tokens=extra_tokens,
-                     torch=str(torch.__version__)),
+                     wb=wb, torch=str(torch.__version__)),
+        "word_mask": wm.clone(),
         "metrics": {k: float(v) for k, v in out.items()},
         "last_hidden_state_cls": cap["last_hidden_state"][:, 0, :].clone(),
         "last_hidden_state_t7": cap["last_hidden_state"][:, 7, :].clone(),
@@ -79,3 +94,5 @@ if __name__ == "__main__":
     run_case("lrw_c1_a2", B=2, S=88, A=2, V=320, depth=12, seed_p=1, seed_x=1235, extra_tokens=5)
     # reference-native 96x96 crop, shallow encoder (fast CPU case)
     run_case("lrw_96_d2", B=3, S=96, A=4, V=320, depth=2, seed_p=2, seed_x=1236, extra_tokens=3)
+    # shipped word-boundary configuration (data.use_word_boundary: true -> hidden dim 513), shallow encoder
+    run_case("lrw_wb_d2", B=3, S=88, A=4, V=320, depth=2, seed_p=4, seed_x=1237, extra_tokens=0, wb=True)

@@ -61,7 +61,7 @@ def test_arena_layout_matches_reference_state_dict_and_decay_rule():
 def test_engine_rejects_unsupported_configs():
     L = _lib.lib()
     h = C.c_void_p()
-    bad = LrwConfig(2, 29, 88, 88, 513, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)
+    bad = LrwConfig(2, 29, 88, 88, 520, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)
     assert L.svsr_lrw_create(C.byref(bad), C.byref(h)) == -1
     assert b"dim" in L.svsr_last_error()
     too_long = LrwConfig(2, 80, 88, 88, 512, 12, 8, 4, 2, 320, 500, 1, 10.0, 0.0, 1e-5, 0.1, 0.0)

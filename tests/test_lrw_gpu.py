@@ -26,14 +26,14 @@ def cosine(a, b):
 
 
 def make_cfg(depth=12, path="./vq-wav2vec_kmeans.pt", label_smoothing=0.0, layer_dropout=0.0, ff_dropout=0.0,
-             extra_model=None):
+             extra_model=None, use_wb=False):
     model = {"resnet": "resnet18", "wav2vec": {"path": path},
              "bert": {"type": "x-transformers", "num_tokens": 1, "dim": 512, "depth": depth, "heads": 8,
                       "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": layer_dropout, "ff_dropout": ff_dropout,
                       "use_rmsnorm": True, "ff_glu": True, "rotary_pos_emb": True, "num_labels": 500}}
     model.update(extra_model or {})
     return AttrDict.wrap({
-        "data": {"use_word_boundary": False, "input_size": 96},
+        "data": {"use_word_boundary": use_wb, "input_size": 96},
         "model": model,
         "optim": {"optimizer": {"lr": 1e-4, "betas": [0.9, 0.999], "eps": 1e-6, "weight_decay": 0.01},
                   "scheduler": {"name": "cosine", "num_warmup_steps": 15000, "num_training_steps": 270000},
@@ -180,7 +180,7 @@ def test_layer_dropout_mask_matches_oracle_skip_set(Module):
     v, t, l = videos.cuda(), tokens.cuda(), labels.cuda()
     m._ensure(v)
     check(lib().svsr_lrw_forward(m._h, C.c_void_p(v.data_ptr()), C.c_void_p(t.data_ptr()), C.c_int64(t.stride(0)),
-                                 C.c_void_p(l.data_ptr()), C.c_void_p(0), C.c_int(1), C.c_uint32(0b0110),
+                                 C.c_void_p(l.data_ptr()), C.c_void_p(0), C.c_void_p(0), C.c_int(1), C.c_uint32(0b0110),
                                  C.c_uint64(0), C.c_void_p(m._metrics.data_ptr()), m._stream()), "fwd")
     o = O.lrw_forward(P, videos, tokens, labels, wm, depth=2, q=O.bf16_ste, skip={1, 2})
     assert float(m._metrics[0]) == pytest.approx(float(o["loss_total"]), rel=1e-3)
@@ -243,3 +243,50 @@ def test_full_size_step_properties(Module):
     assert rel(m.flat_grads, 2 * g1) < 2e-3
     # BatchNorm beta gradients equal the column sums flowing into them: d(shift of bn) of the last block is finite
     assert float(m.resnet.layer4._modules["1"].bn2.bias.grad.abs().sum()) > 0
+
+
+def test_word_boundary_variant_dim_513(Module, golden_dir):
+    """The shipped ..._WB.yaml (data.use_word_boundary: true): word_mask becomes hidden channel 512, every encoder /
+    head tensor is 513 wide (lightning.py:46-47,145-150). Checked against the reference's own forward (golden) and the
+    oracle's gradients, including the parameters whose 513 / 2052-wide rows are stored unaligned in the arena."""
+    fx = torch.load(golden_dir / "lrw_wb_d2.pt")
+    meta = fx["meta"]
+    m = Module(make_cfg(depth=meta["depth"], use_wb=True)).train()
+    assert m.dim == 513 and m.cls_token.shape == (1, 1, 513) and float(m.cls_token[0, 0, -1]) == 0.0
+    P = O.make_params(meta["seed_p"], depth=meta["depth"], dim=513)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected
+    videos, tokens, labels, _ = O.make_inputs(meta["seed_x"], meta["B"])
+    wm = fx["word_mask"]
+    out = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    g = fx["metrics"]
+    assert float(out["loss_total"]) == pytest.approx(g["loss_total"], rel=1e-3)
+    assert float(out["loss_audio"]) == pytest.approx(g["loss_audio"], rel=1e-3)
+    assert float(out["loss_category"]) == pytest.approx(g["loss_category"], rel=2e-3)
+    last = m.last_hidden_state().cpu()
+    assert last.shape == (meta["B"], 30, 513)
+    assert rel(last[:, 0, :], fx["last_hidden_state_cls"]) < 5e-2 and rel(last[:, 7, :], fx["last_hidden_state_t7"]) < 5e-2
+    assert rel(m.logits_category().cpu(), fx["logits_category"]) < 5e-2
+    # the word-boundary channel itself is exact: column 512 of the encoder input = word_mask (frames), cls[512] (CLS)
+    emb = m._named_tensor("inputs_embeds", (meta["B"], 30, 576)).cpu()
+    assert torch.equal(emb[:, 1:, 512], wm) and float(emb[:, 0, 512].abs().sum()) == float(P["cls_token"][0, 0, 512].abs() * meta["B"])
+    assert float(emb[:, :, 513:].abs().sum()) == 0.0 and float(m._named_tensor("last_hidden_state", (meta["B"], 30, 576))[:, :, 513:].abs().sum()) == 0.0
+    # gradients vs the oracle at the same bf16 storage points
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = O.lrw_forward(Pq, videos, tokens, labels, wm, depth=meta["depth"], use_wb=True, q=O.bf16_ste)
+    assert float(out["loss_total"]) == pytest.approx(float(o["loss_total"]), rel=2e-4)
+    out["loss_total"].backward()
+    o["loss_total"].backward()
+    bad = []
+    for k, p in m._param_views.items():
+        ref = Pq[k].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if k.startswith(("encoder", "audio_projection", "category_classifier", "cls_token")):
+            if rel(p.grad, ref) > 4e-2:
+                bad.append((k, round(rel(p.grad, ref), 4)))
+        elif cosine(p.grad, ref) < 0.85:
+            bad.append((k, "cos", round(cosine(p.grad, ref), 3)))
+    assert not bad, bad
+    # golden gradient of the reference module itself
+    assert rel(m.cls_token.grad.cpu(), fx["grad_cls_token"]) < 4e-2
+    assert rel(m._param_views["encoder.layers.0.0.g"].grad.cpu(), fx["grad_enc0_g"]) < 4e-2

@@ -7,19 +7,23 @@ import torch
 from oracle import lrw_oracle as O
 from oracle import ref_loader as rl
 
-CASES = ["lrw_c1_vq", "lrw_c1_a2", "lrw_96_d2"]
+CASES = ["lrw_c1_vq", "lrw_c1_a2", "lrw_96_d2", "lrw_wb_d2"]  # the last: data.use_word_boundary (dim 513)
 
 
-def _run_oracle(meta, need_grad=False):
-    P = O.make_params(meta["seed_p"], depth=meta["depth"], n_audio=meta["A"] * meta["G"] * meta["V"])
+def _run_oracle(meta, need_grad=False, word_mask=None):
+    wb = bool(meta.get("wb", False))
+    P = O.make_params(meta["seed_p"], depth=meta["depth"], n_audio=meta["A"] * meta["G"] * meta["V"],
+                      dim=513 if wb else 512)
     if need_grad:
         for k, v in P.items():
             if "running_" not in k:
                 v.requires_grad_(True)
     videos, tokens, labels, wm = O.make_inputs(meta["seed_x"], meta["B"], S=meta["S"], A=meta["A"], V=meta["V"],
                                                extra_tokens=meta["extra_tokens"])
+    if wb:
+        wm = word_mask
     out = O.lrw_forward(P, videos, tokens, labels, wm, depth=meta["depth"], audio_alignment=meta["A"],
-                        vq_groups=meta["G"], audio_vocab_size=meta["V"])
+                        vq_groups=meta["G"], audio_vocab_size=meta["V"], use_wb=wb)
     return P, (videos, tokens, labels, wm), out
 
 
@@ -27,7 +31,7 @@ def _run_oracle(meta, need_grad=False):
 def test_oracle_matches_reference_golden(name, golden_dir):
     fx = torch.load(golden_dir / f"{name}.pt")
     meta = fx["meta"]
-    P, inputs, out = _run_oracle(meta, need_grad=(name != "lrw_c1_vq"))
+    P, inputs, out = _run_oracle(meta, need_grad=(name != "lrw_c1_vq"), word_mask=fx.get("word_mask"))
     tol = dict(rtol=2e-4, atol=2e-4)
     for k, v in fx["metrics"].items():
         assert float(out[k]) == pytest.approx(v, rel=1e-5, abs=1e-6), k
@@ -37,7 +41,9 @@ def test_oracle_matches_reference_golden(name, golden_dir):
     la = out["logits_audio"].reshape(meta["B"], 29, -1)
     torch.testing.assert_close(la[:, 3, :], fx["logits_audio_t3"], **tol)
     torch.testing.assert_close(out["logits_category"], fx["logits_category"], **tol)
-    torch.testing.assert_close(out["inputs_embeds"].flatten(0, 1)[:2], fx["inputs_embeds_t0"], **tol)
+    torch.testing.assert_close(out["inputs_embeds"].flatten(0, 1)[:2, :512], fx["inputs_embeds_t0"], **tol)
+    if meta.get("wb"):  # the word-boundary channel is the mask itself
+        assert torch.equal(out["inputs_embeds"][..., 512], fx["word_mask"])
     # integer path: bit exact
     assert torch.equal(O.audio_targets(inputs[1], 29, meta["A"]), fx["audio_targets"])
     # BN buffers
