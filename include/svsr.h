@@ -201,6 +201,16 @@ int svsr_lrw_early_grad_region(void* handle, int64_t* begin, int64_t* end);
 /* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */
 int svsr_lrw_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
 
+/* CutMix (LRW/video/src/augment.py:27-118) on the device. The reference mixes clip by clip, in place, with host RNG
+ * decisions; syncvsr_b200/augment.py draws the same decisions and resolves the sequential swaps into source tables, so
+ * one gather suffices: videos_out[i,0,t] = videos_in[vsrc[i,t],0,t] (frame_elems floats per frame),
+ * audio_out[i,a,:] = audio_in[asrc[i,a],a,:] (int64, bit-exact), soft_labels[i] = (1-rate)*onehot(labels[i]) +
+ * rate*onehot(labels[tgt[i]]) and wm_out likewise for clips with mixed[i] != 0, plain one-hot / copy otherwise. */
+int svsr_cutmix_gather(const float* videos_in, float* videos_out, const int* vsrc, int B, int T, int64_t frame_elems,
+                       const int64_t* audio_in, int64_t* audio_out, const int* asrc, int Ta, int G, const int64_t* labels,
+                       const int* tgt, const float* rate, const uint8_t* mixed, float* soft_labels, int num_labels,
+                       const float* wm_in, float* wm_out, int Tw, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * LRS sentence-level operators (reference: LRS/video/espnet/nets/pytorch_backend/, paths below relative to it).
  * --------------------------------------------------------------------------------------------------------- */

@@ -113,6 +113,18 @@ int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const f
                      static_cast<bf16*>(dlogits), ldd, acc, dscale, ST(stream));
 }
 
+int svsr_cutmix_gather(const float* videos_in, float* videos_out, const int* vsrc, int B, int T, int64_t frame_elems,
+                       const int64_t* audio_in, int64_t* audio_out, const int* asrc, int Ta, int G, const int64_t* labels,
+                       const int* tgt, const float* rate, const uint8_t* mixed, float* soft_labels, int num_labels,
+                       const float* wm_in, float* wm_out, int Tw, void* stream) {
+  SVSR_REQUIRE(videos_in && videos_out && vsrc && audio_in && audio_out && asrc && labels && tgt && rate && mixed &&
+                   soft_labels && wm_in && wm_out,
+               "cutmix_gather: null pointer");
+  return cutmix_gather(videos_in, videos_out, vsrc, B, T, frame_elems, reinterpret_cast<const long long*>(audio_in),
+                       reinterpret_cast<long long*>(audio_out), asrc, Ta, G, reinterpret_cast<const long long*>(labels),
+                       tgt, rate, mixed, soft_labels, num_labels, wm_in, wm_out, Tw, ST(stream));
+}
+
 // ---- LRS sentence-level operators (csrc/conformer.cu) ----
 int svsr_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* stats,
                        int M, int D, float eps, void* stream) {

@@ -730,6 +730,51 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
   }
 }
 
+// CutMix (LRW/video/src/augment.py:27-118) as one gather over the ORIGINAL batch: the host resolves the reference's
+// sequential in-place frame swaps into source-clip tables (vsrc[i,t], asrc[i,a]); this kernel moves the frames / audio
+// token rows and builds the mixed soft labels and word masks. One block per (clip, frame) for the video part.
+__global__ void __launch_bounds__(256)
+cutmix_video_kernel(const float4* __restrict__ vin, float4* __restrict__ vout, const int* __restrict__ vsrc, int T,
+                    long long frame_vec4) {
+  const long long bt = blockIdx.x;  // i * T + t
+  const int t = (int)(bt % T);
+  const long long src = (long long)vsrc[bt] * T + t;
+  const float4* s = vin + src * frame_vec4;
+  float4* d = vout + bt * frame_vec4;
+  for (long long k = threadIdx.x; k < frame_vec4; k += blockDim.x) d[k] = s[k];
+}
+__global__ void cutmix_meta_kernel(const long long* __restrict__ ain, long long* __restrict__ aout,
+                                   const int* __restrict__ asrc, int B, int Ta, int G, const long long* __restrict__ labels,
+                                   const int* __restrict__ tgt, const float* __restrict__ rate,
+                                   const unsigned char* __restrict__ mixed, float* __restrict__ soft, int num_labels,
+                                   const float* __restrict__ wm_in, float* __restrict__ wm_out, int Tw) {
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < (long long)B * Ta * G; i += stride) {
+    const int g = (int)(i % G);
+    const long long ba = i / G;
+    const int a = (int)(ba % Ta);
+    aout[i] = ain[((long long)asrc[ba] * Ta + a) * G + g];
+  }
+  for (long long i = i0; i < (long long)B * num_labels; i += stride) {
+    const int b = (int)(i / num_labels), c = (int)(i % num_labels);
+    const float own = labels[b] == c ? 1.f : 0.f;
+    float v = own;
+    if (mixed[b]) {  // (1.0 - mix_rate) * one_hot(org) + mix_rate * one_hot(tar), evaluated in fp32 like torch
+      const float r = rate[b], q = (float)(1.0 - (double)r);
+      v = q * own + r * (labels[tgt[b]] == c ? 1.f : 0.f);
+    }
+    soft[i] = v;
+  }
+  for (long long i = i0; i < (long long)B * Tw; i += stride) {
+    const int b = (int)(i / Tw), t = (int)(i % Tw);
+    float v = wm_in[i];
+    if (mixed[b]) {
+      const float r = rate[b], q = (float)(1.0 - (double)r);
+      v = q * v + r * wm_in[(long long)tgt[b] * Tw + t];
+    }
+    wm_out[i] = v;
+  }
+}
 // word-boundary column (lightning.py:145-150): x[b, 1+t, C] = word_mask[b, t], x[b, 0, C] = cls[C]; and d cls[C]
 __global__ void wb_column_kernel(float* __restrict__ xs, const float* __restrict__ cls, const float* __restrict__ wm,
                                  int B, int T, int ldx, int C) {
@@ -941,6 +986,19 @@ int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int
 int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
   dim3 grid(64, (unsigned)njobs);
   pack_all_kernel<<<grid, 256, 0, s>>>(jobs_dev);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int cutmix_gather(const float* vin, float* vout, const int* vsrc, int B, int T, long long frame_elems,
+                  const long long* ain, long long* aout, const int* asrc, int Ta, int G, const long long* labels,
+                  const int* tgt, const float* rate, const unsigned char* mixed, float* soft, int num_labels,
+                  const float* wm_in, float* wm_out, int Tw, cudaStream_t s) {
+  SVSR_REQUIRE(frame_elems % 4 == 0, "cutmix: frame size %lld must be a multiple of 4 floats", frame_elems);
+  cutmix_video_kernel<<<(unsigned)(B * T), 256, 0, s>>>(reinterpret_cast<const float4*>(vin),
+                                                        reinterpret_cast<float4*>(vout), vsrc, T, frame_elems / 4);
+  LAUNCH_CHECK();
+  cutmix_meta_kernel<<<grid_for((long long)B * (Ta * G > num_labels ? Ta * G : num_labels), 256), 256, 0, s>>>(
+      ain, aout, asrc, B, Ta, G, labels, tgt, rate, mixed, soft, num_labels, wm_in, wm_out, Tw);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

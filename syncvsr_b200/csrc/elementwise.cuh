@@ -54,6 +54,12 @@ int meanpool_cls(const __nv_bfloat16* a, const float* cls, float* x_stream, int 
 // dout[b*T+t, hw, :] = dx[b, t+1, :] / HW (bf16); dcls += sum_b dx[b,0,:]
 int meanpool_cls_bwd(const float* dx, __nv_bfloat16* dout, float* dcls, int B, int T, int HW, int C, cudaStream_t s,
                      int ldx = 0);
+// CutMix gather (augment.py:27-118): vout[i,t] = vin[vsrc[i,t], t]; aout[i,a] = ain[asrc[i,a], a]; soft labels and word
+// masks mixed with (1 - rate, rate) for the clips flagged in `mixed` (tgt = the partner clip)
+int cutmix_gather(const float* vin, float* vout, const int* vsrc, int B, int T, long long frame_elems,
+                  const long long* ain, long long* aout, const int* asrc, int Ta, int G, const long long* labels,
+                  const int* tgt, const float* rate, const unsigned char* mixed, float* soft, int num_labels,
+                  const float* wm_in, float* wm_out, int Tw, cudaStream_t s);
 // word-boundary channel (lightning.py:145-150): column C of the stream = word_mask[b,t] (frames) / cls[C] (CLS row)
 int wb_column(float* xs, const float* cls, const float* wm, int B, int T, int ldx, int C, cudaStream_t s);
 int wb_column_bwd(const float* dx, float* dcls, int B, int T, int ldx, int C, cudaStream_t s);  // dcls[C] += sum_b

@@ -115,6 +115,10 @@ class TransformerLightningModule(nn.Module):
         # does not depend on B/H/W); the workspace is (re)built lazily for the geometry actually fed to forward().
         self._build_engine(B=1, T=29, H=88, W=88, first=True)
 
+        from .augment import CutMix  # on-device mirror of augment.py (pre-quantised audio tokens: wav2vec = None)
+
+        self.cutmix = CutMix(self.word_labels, None).eval()
+
         # parameters the reference's state dict carries but never uses on this path (lightning.py:55 creates the full
         # timm resnet18; only .layer1-4 run): kept for checkpoint compatibility, never receive gradients.
         rn = self.resnet
@@ -392,6 +396,8 @@ class TransformerLightningModule(nn.Module):
 
     def training_step(self, batch, idx: int) -> torch.Tensor:
         self.is_train = True
+        if _cfg_get(self.config, "train.use_cutmix", False):  # lightning.py:196-197
+            batch = self.cutmix(*batch)
         metrics = self(*batch)
         self.log_dict({f"train/{k}": v for k, v in metrics.items()})
         return metrics["loss_total"]
