@@ -208,7 +208,7 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restr
 // y[b,t,c] = bias[c] + sum_k w[c, flip ? K-1-k : k] * x[b, t+k-pad, c]; one thread per (b, t, 8 channels)
 __global__ void __launch_bounds__(256)
 dwconv1d_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                __nv_bfloat16* __restrict__ y, int B, int T, int C, int K, int flip) {
+                __nv_bfloat16* __restrict__ y, int B, int T, int C, int K, int flip, int wt) {
   const int cg = C >> 3, pad = (K - 1) / 2;
   const long long total = (long long)B * T * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -227,8 +227,14 @@ dwconv1d_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
       if (ts < 0 || ts >= T) continue;
       const F8 xv = ld8(xrow + (long long)ts * C);
       const int kk = flip ? K - 1 - k : k;
+      if (wt) {  // w is the transposed copy [K, C]: 8 consecutive channels = two 16-byte loads, coalesced across lanes
+        const F8 wv = ldf8(w + (long long)kk * C + g * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wg[j * K + kk], xv.v[j], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv.v[j], xv.v[j], acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wg[j * K + kk], xv.v[j], acc[j]);
+      }
     }
     F8 o;
 #pragma unroll
@@ -309,6 +315,10 @@ bn_col_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   }
 }
 
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // in [R, Cc] -> out [Cc, R]
+  if (i < R * Cc) out[(i % Cc) * R + i / Cc] = in[i];
+}
 __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<float4*>(dst)[i];
@@ -1081,10 +1091,16 @@ int glu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, 
   LAUNCH_CHECK();
   return SVSR_OK;
 }
+int transpose_f32(const float* in, float* out, int R, int Cc, cudaStream_t s) {
+  transpose_f32_kernel<<<(R * Cc + 255) / 256, 256, 0, s>>>(in, out, R, Cc);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
 int dwconv1d_fwd(const __nv_bfloat16* x, const float* w, const float* bias, __nv_bfloat16* y, int B, int T, int C, int K,
-                 int flip, cudaStream_t s) {
+                 int flip, cudaStream_t s, int w_transposed) {
   SVSR_REQUIRE(C % 8 == 0 && K % 2 == 1 && K <= 31, "dwconv1d: C=%d K=%d unsupported", C, K);
-  dwconv1d_kernel<<<grid_for((long long)B * T * (C / 8), 256), 256, 0, s>>>(x, w, bias, y, B, T, C, K, flip);
+  dwconv1d_kernel<<<grid_for((long long)B * T * (C / 8), 256), 256, 0, s>>>(x, w, bias, y, B, T, C, K, flip,
+                                                                           w_transposed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

@@ -23,8 +23,10 @@ int glu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, 
 
 // ---- depthwise Conv1d along time (convolution.py:40-48,64): x,y [B,T,C] bf16; w fp32 [C,K] (K odd <= 31) ----------
 // flip = 1 correlates with the reversed kernel and no bias: the input gradient of the same convolution.
+// w_transposed = 1: w is a [K, C] copy (transpose_f32) so that the per-tap weight loads are coalesced
 int dwconv1d_fwd(const __nv_bfloat16* x, const float* w, const float* bias, __nv_bfloat16* y, int B, int T, int C, int K,
-                 int flip, cudaStream_t s);
+                 int flip, cudaStream_t s, int w_transposed = 0);
+int transpose_f32(const float* in, float* out, int R, int Cc, cudaStream_t s);  // in [R, Cc] -> out [Cc, R]
 // dw[C,K] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]; dbias[C] += sum dy
 int dwconv1d_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* dbias, int B, int T, int C, int K,
                    cudaStream_t s);

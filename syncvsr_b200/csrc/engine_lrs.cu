@@ -20,6 +20,7 @@ struct ConfLayerRef {
   LnRef n_mac, n_mha, n_conv, n_ff, n_fin;
   LinRef mac1, mac2, qkv, out, pos, pw1, pw2, ff1, ff2;
   long long bias_u, bias_v, dw_w, dw_b;
+  size_t dw_wT = 0;  // fp32 [K, D] transposed copy of the depthwise kernel (coalesced per-tap loads)
   BnRef bn;
   size_t yn[4], h_mac, h_ff, qkvbuf, pbuf, lse, ctx, hpw1, u, dwo, act;
 };
@@ -47,7 +48,8 @@ struct LrsEngine : EngineBase {
   size_t ys_in, ys_out, xd, dec_yn, pred, dpred, acc, bad_token, pe_drop, enc_ctc;
   size_t bn_stats_arena = 0, bn_stats_bytes = 0;
   // backward scratch
-  size_t dx, dxb, gF, g3D, gD[3], attn_scratch, dp, dpb, dfeat, ddx, ddxb, dkv;
+  // gradient temporaries read by weight-gradient GEMMs on the side stream are double buffered by unit parity
+  size_t dx, dxb[2], gF[2], g3D[2], gD[2][3], attn_scratch, dp, dpb[2], dfeat, ddx, ddxb[2], dkv[2];
   size_t pack_jobs;
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
@@ -219,6 +221,7 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
     L.ctx = b.take((size_t)M * D * 2);
     L.hpw1 = b.take((size_t)M * 2 * D * 2);
     L.u = b.take((size_t)M * D * 2), L.dwo = b.take((size_t)M * D * 2), L.act = b.take((size_t)M * D * 2);
+    L.dw_wT = b.take((size_t)c.cnn_kernel * D * 4);
   }
   add_ln(e, e.after, "encoder.after_norm", D, M, b);
   e.dec_emb = add_param(e.params, e.pc, "decoder.embed.0.weight", {c.odim, D});
@@ -288,18 +291,20 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
   const size_t R = (size_t)(M > Md ? M : Md);
   const size_t Fm = (size_t)(F > Fd ? F : Fd);
   e.dx = b.take((size_t)M * D * 4);
-  e.dxb = b.take(R * D * 2);
-  e.gF = b.take(R * Fm * 2);
-  e.g3D = b.take(R * 3 * D * 2);
-  for (int i = 0; i < 3; ++i) e.gD[i] = b.take(R * D * 2);
+  for (int u = 0; u < 2; ++u) {
+    e.dxb[u] = b.take(R * D * 2);
+    e.gF[u] = b.take(R * Fm * 2);
+    e.g3D[u] = b.take(R * 3 * D * 2);
+    for (int i = 0; i < 3; ++i) e.gD[u][i] = b.take(R * D * 2);
+    e.dpb[u] = b.take((size_t)(2 * T - 1) * D * 2);
+    e.ddxb[u] = b.take((size_t)Md * D * 2);
+    e.dkv[u] = b.take((size_t)M * 2 * D * 2);
+  }
   const int Tmax = T > c.Lmax ? T : c.Lmax;
   e.attn_scratch = b.take(attention_scratch_bytes(c.B, H, Tmax, Tmax));
   e.dp = b.take((size_t)(2 * T - 1) * D * 4);
-  e.dpb = b.take((size_t)(2 * T - 1) * D * 2);
   e.dfeat = b.take((size_t)M * 512 * 2);
   e.ddx = b.take((size_t)Md * D * 4);
-  e.ddxb = b.take((size_t)Md * D * 2);
-  e.dkv = b.take((size_t)M * 2 * D * 2);
   e.pack_jobs = b.take(384 * sizeof(PackJob));
   e.ws_bytes = b.off;
   e.decay_count = e.pc.decay;
@@ -332,6 +337,7 @@ static int lrs_pack(LrsEngine& e, cudaStream_t s) {
     RC(rel_pos_table(e.ws<bf16>(e.pe_rel), e.cfg.T, e.cfg.adim, s));
     e.pack_table_ready = true;
   }
+  for (auto& L : e.enc) RC(transpose_f32(e.P + L.dw_w, e.ws<float>(L.dw_wT), e.cfg.adim, e.cfg.cnn_kernel, s));
   return pack_all_weights(e.ws<PackJob>(e.pack_jobs), e.n_pack_jobs, s);
 }
 
@@ -395,7 +401,8 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
     RC(ln_fwd(e, x2, L.n_conv, e.ws<bf16>(L.yn[2]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[2]), M, L.pw1, e.ws<bf16>(L.hpw1), 2 * D, 0, nullptr, 1.f, 0, s));
     RC(glu_fwd(e.ws<bf16>(L.hpw1), e.ws<bf16>(L.u), M, D, s));
-    RC(dwconv1d_fwd(e.ws<bf16>(L.u), e.P + L.dw_w, e.P + L.dw_b, e.ws<bf16>(L.dwo), c.B, T, D, c.cnn_kernel, 0, s));
+    RC(dwconv1d_fwd(e.ws<bf16>(L.u), e.ws<float>(L.dw_wT), e.P + L.dw_b, e.ws<bf16>(L.dwo), c.B, T, D, c.cnn_kernel, 0, s,
+                    1));
     if (train) RC(bn_col_reduce(e.ws<bf16>(L.dwo), nullptr, nullptr, M, D, e.ws<double>(L.bn.stats_f), 0, s));
     RC(bn_fwd(e, e.ws<bf16>(L.dwo), M, L.bn, train, s));
     RC(bn_apply(e.ws<bf16>(L.dwo), e.ws<float>(L.bn.coef), nullptr, nullptr, 2, e.ws<bf16>(L.act), M, D, s));
@@ -493,22 +500,41 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: decoder -> heads -> Conformer blocks -> embed -> frontend. One stream for the encoder/decoder part (the
-// frontend's weight-gradient GEMMs still go to the side stream inside frontend_backward).
+// backward: heads -> decoder -> Conformer blocks -> embed -> frontend. Two streams, as in the LRW engine: `s` carries the
+// critical chain (input-gradient GEMMs, attention / norm / conv-module backward), `e.side` every weight-gradient GEMM
+// (+ bias column sums). One "unit" per sub-block; the temporaries a unit's side work reads are double buffered by unit
+// parity and the chain waits for the side stream's unit k-1 before it starts unit k+1 (SideQueue::end_unit).
 // ------------------------------------------------------------------------------------------------
-static int ffn_bwd(LrsEngine& e, const bf16* dyb, int rows, const LinRef& w1, const LinRef& w2, const bf16* h,
-                   const bf16* yn, const float* x_in, const LnRef& n, float* dx, int F, cudaStream_t s) {
+struct LrsScratch {
+  bf16 *dxb, *gF, *g3D, *gD[3], *dpb, *ddxb, *dkv;
+};
+static LrsScratch lrs_scratch(const LrsEngine& e, int unit) {
+  const int u = unit & 1;
+  LrsScratch t;
+  t.dxb = e.ws<bf16>(e.dxb[u]), t.gF = e.ws<bf16>(e.gF[u]), t.g3D = e.ws<bf16>(e.g3D[u]);
+  for (int i = 0; i < 3; ++i) t.gD[i] = e.ws<bf16>(e.gD[u][i]);
+  t.dpb = e.ws<bf16>(e.dpb[u]), t.ddxb = e.ws<bf16>(e.ddxb[u]), t.dkv = e.ws<bf16>(e.dkv[u]);
+  return t;
+}
+
+// dyb: the (already cast / masked) branch gradient in t.dxb or t.ddxb
+static int ffn_bwd(LrsEngine& e, SideQueue& sq, const LrsScratch& t, const bf16* dyb, int rows, const LinRef& w1,
+                   const LinRef& w2, const bf16* h, const bf16* yn, const float* x_in, const LnRef& n, float* dx, int F,
+                   cudaStream_t s) {
   // h = dropout(relu(.)) is zero where dropped OR clipped, so the fused `h > 0` mask covers both; surviving units
   // carry the 1/(1-p) of the dropout
   const float hs = e.pd > 0.f ? 1.0f / (1.0f - e.pd) : 1.0f;
   const int D = e.cfg.adim;
-  bf16* dh = e.ws<bf16>(e.gF);
-  bf16* dyn = e.ws<bf16>(e.gD[0]);
-  RC(linear_wgrad(e, dyb, D, h, rows, w2, s));
+  bf16* dh = t.gF;
+  bf16* dyn = t.gD[0];
+  RC(sq.fork());  // dyb complete
+  RC(linear_wgrad(e, dyb, D, h, rows, w2, e.side));
   RC(lin_dgrad(e, dyb, D, rows, w2, dh, F, 0, nullptr, hs, h, s));  // ReLU backward fused: zero where h <= 0
-  RC(linear_wgrad(e, dh, F, yn, rows, w1, s));
+  RC(sq.fork());  // dh complete
+  RC(linear_wgrad(e, dh, F, yn, rows, w1, e.side));
   RC(lin_dgrad(e, dh, F, rows, w1, dyn, D, 0, nullptr, 1.f, nullptr, s));
-  return ln_bwd(e, dyn, nullptr, x_in, n, dx, 1, rows, s);
+  RC(ln_bwd(e, dyn, nullptr, x_in, n, dx, 1, rows, s));
+  return sq.end_unit();
 }
 
 static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
@@ -519,89 +545,108 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   const int D = c.adim, F = c.eunits, Fd = c.dunits, H = c.aheads, T = c.T, M = e.M;
   const int L = e.last_L, Md = c.B * L;
   float* dx = e.ws<float>(e.dx);
-  bf16* dxb = e.ws<bf16>(e.dxb);
   const bf16* enc_b = e.ws<bf16>(e.enc_b);
   const float pd = e.pd, pa = e.pa;
+  SideQueue sq(e, s);
+  cudaStream_t w = e.side;
   if (grad_scale) {
     if (e.last_audio) RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)M * e.AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)M * e.ldv, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dpred), (long long)Md * e.ldv, grad_scale, s));
   }
-  // ---- d loss / d encoder output from the audio and CTC heads ----
-  if (e.last_audio) {
-    RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), e.AGV, enc_b, M, e.aud, s));
-    RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_a), e.AGV, M, e.aud, dx, D, 1, nullptr, 1.f, nullptr, s));
-  } else {
-    SVSR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * D * 4, s));
-  }
-  if (pd > 0.f) {  // through the Dropout in front of ctc_lo
-    RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, e.ws<bf16>(e.enc_ctc), M, e.ctc, s));
-    RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, e.ws<bf16>(e.gD[1]), D, 0, nullptr, 1.f, nullptr, s));
-    RC(dropout_add_bf16_to_f32(dx, e.ws<bf16>(e.gD[1]), (long long)M * D, pd, e.site(3), s));
-  } else {
-    RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, enc_b, M, e.ctc, s));
-    RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, dx, D, 1, dx, 1.f, nullptr, s));
+  // ---- unit: d loss / d encoder output from the audio and CTC heads ----
+  {
+    const LrsScratch t = lrs_scratch(e, sq.unit);
+    RC(sq.fork());
+    if (e.last_audio) {
+      RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_a), e.AGV, enc_b, M, e.aud, w));
+      RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_a), e.AGV, M, e.aud, dx, D, 1, nullptr, 1.f, nullptr, s));
+    } else {
+      SVSR_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * D * 4, s));
+    }
+    if (pd > 0.f) {  // through the Dropout in front of ctc_lo
+      RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, e.ws<bf16>(e.enc_ctc), M, e.ctc, w));
+      RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, t.gD[1], D, 0, nullptr, 1.f, nullptr, s));
+      RC(dropout_add_bf16_to_f32(dx, t.gD[1], (long long)M * D, pd, e.site(3), s));
+    } else {
+      RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, enc_b, M, e.ctc, w));
+      RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, dx, D, 1, dx, 1.f, nullptr, s));
+    }
+    RC(sq.end_unit());
   }
 
   // ---- decoder ----
   {
     float* ddx = e.ws<float>(e.ddx);
-    bf16* ddxb = e.ws<bf16>(e.ddxb);
-    bf16* dyn = e.ws<bf16>(e.gD[0]);
-    bf16* dctx = e.ws<bf16>(e.gD[1]);
-    bf16* dq = e.ws<bf16>(e.gD[2]);
-    bf16* dqkv = e.ws<bf16>(e.g3D);
-    bf16* dkv = e.ws<bf16>(e.dkv);
-    RC(linear_wgrad(e, e.ws<bf16>(e.dpred), e.ldv, e.ws<bf16>(e.dec_yn), Md, e.outl, s));
-    RC(lin_dgrad(e, e.ws<bf16>(e.dpred), e.ldv, Md, e.outl, dyn, D, 0, nullptr, 1.f, nullptr, s));
-    RC(ln_bwd(e, dyn, nullptr, e.xd_buf(3 * c.dlayers), e.dec_after, ddx, 0, Md, s));
+    {  // unit: output layer + after_norm
+      const LrsScratch t = lrs_scratch(e, sq.unit);
+      RC(sq.fork());
+      RC(linear_wgrad(e, e.ws<bf16>(e.dpred), e.ldv, e.ws<bf16>(e.dec_yn), Md, e.outl, w));
+      RC(lin_dgrad(e, e.ws<bf16>(e.dpred), e.ldv, Md, e.outl, t.gD[0], D, 0, nullptr, 1.f, nullptr, s));
+      RC(ln_bwd(e, t.gD[0], nullptr, e.xd_buf(3 * c.dlayers), e.dec_after, ddx, 0, Md, s));
+      RC(sq.end_unit());
+    }
     for (int i = c.dlayers - 1; i >= 0; --i) {
       DecLayerRef& Ld = e.dec[i];
       float *x0 = e.xd_buf(3 * i), *x1 = e.xd_buf(3 * i + 1), *x2 = e.xd_buf(3 * i + 2);
-      // feed-forward
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 5))));
-      RC(ffn_bwd(e, ddxb, Md, Ld.ff1, Ld.ff2, e.ws<bf16>(Ld.h), e.ws<bf16>(Ld.yn[2]), x2, Ld.n3, ddx, Fd, s));
-      // source attention over the encoder output
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 3))));
-      RC(linear_wgrad(e, ddxb, D, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, s));
-      RC(lin_dgrad(e, ddxb, D, Md, Ld.out_c, dctx, D, 0, nullptr, 1.f, nullptr, s));
-      {
-        AttnProblem a;
-        a.q = e.ws<bf16>(Ld.qc), a.ldq = D;
-        a.k = e.ws<bf16>(Ld.kvc), a.v = a.k + D, a.ldk = a.ldv = 2 * D;
-        a.klen = e.ws<int>(e.klen);
-        a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
-        a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
-        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
-        AttnGrads g;
-        g.d_o = dctx, g.dq = dq, g.lddq = D, g.dk = dkv, g.dv = dkv + D, g.lddk = g.lddv = 2 * D;
-        g.scratch = e.ws<float>(e.attn_scratch);
-        RC(attention_core_bwd(a, g, s));
+      {  // unit: feed-forward
+        const LrsScratch t = lrs_scratch(e, sq.unit);
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 5))));
+        RC(ffn_bwd(e, sq, t, t.ddxb, Md, Ld.ff1, Ld.ff2, e.ws<bf16>(Ld.h), e.ws<bf16>(Ld.yn[2]), x2, Ld.n3, ddx, Fd, s));
       }
-      RC(linear_wgrad(e, dq, D, e.ws<bf16>(Ld.yn[1]), Md, Ld.q_c, s));
-      RC(linear_wgrad(e, dkv, 2 * D, enc_b, M, Ld.kv_c, s));
-      RC(lin_dgrad(e, dkv, 2 * D, M, Ld.kv_c, dx, D, 1, dx, 1.f, nullptr, s));  // memory gradient accumulates
-      RC(lin_dgrad(e, dq, D, Md, Ld.q_c, dyn, D, 0, nullptr, 1.f, nullptr, s));
-      RC(ln_bwd(e, dyn, nullptr, x1, Ld.n2, ddx, 1, Md, s));
-      // causal self-attention
-      RC(cast_scale_f32_bf16(ddx, ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 1))));
-      RC(linear_wgrad(e, ddxb, D, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, s));
-      RC(lin_dgrad(e, ddxb, D, Md, Ld.out_s, dctx, D, 0, nullptr, 1.f, nullptr, s));
-      {
-        AttnProblem a;
-        a.q = e.ws<bf16>(Ld.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
-        a.causal = 1;
-        a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
-        a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
-        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
-        AttnGrads g;
-        g.d_o = dctx, g.dq = dqkv, g.dk = dqkv + D, g.dv = dqkv + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
-        g.scratch = e.ws<float>(e.attn_scratch);
-        RC(attention_core_bwd(a, g, s));
+      {  // unit: source attention over the encoder output
+        const LrsScratch t = lrs_scratch(e, sq.unit);
+        bf16 *dyn = t.gD[0], *dctx = t.gD[1], *dq = t.gD[2], *dkv = t.dkv;
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 3))));
+        RC(sq.fork());
+        RC(linear_wgrad(e, t.ddxb, D, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, w));
+        RC(lin_dgrad(e, t.ddxb, D, Md, Ld.out_c, dctx, D, 0, nullptr, 1.f, nullptr, s));
+        {
+          AttnProblem a;
+          a.q = e.ws<bf16>(Ld.qc), a.ldq = D;
+          a.k = e.ws<bf16>(Ld.kvc), a.v = a.k + D, a.ldk = a.ldv = 2 * D;
+          a.klen = e.ws<int>(e.klen);
+          a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
+          a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
+          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
+          AttnGrads g;
+          g.d_o = dctx, g.dq = dq, g.lddq = D, g.dk = dkv, g.dv = dkv + D, g.lddk = g.lddv = 2 * D;
+          g.scratch = e.ws<float>(e.attn_scratch);
+          RC(attention_core_bwd(a, g, s));
+        }
+        RC(sq.fork());
+        RC(linear_wgrad(e, dq, D, e.ws<bf16>(Ld.yn[1]), Md, Ld.q_c, w));
+        RC(linear_wgrad(e, dkv, 2 * D, enc_b, M, Ld.kv_c, w));
+        RC(lin_dgrad(e, dkv, 2 * D, M, Ld.kv_c, dx, D, 1, dx, 1.f, nullptr, s));  // memory gradient accumulates
+        RC(lin_dgrad(e, dq, D, Md, Ld.q_c, dyn, D, 0, nullptr, 1.f, nullptr, s));
+        RC(ln_bwd(e, dyn, nullptr, x1, Ld.n2, ddx, 1, Md, s));
+        RC(sq.end_unit());
       }
-      RC(linear_wgrad(e, dqkv, 3 * D, e.ws<bf16>(Ld.yn[0]), Md, Ld.qkv, s));
-      RC(lin_dgrad(e, dqkv, 3 * D, Md, Ld.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
-      RC(ln_bwd(e, dyn, nullptr, x0, Ld.n1, ddx, 1, Md, s));
+      {  // unit: causal self-attention
+        const LrsScratch t = lrs_scratch(e, sq.unit);
+        bf16 *dyn = t.gD[0], *dctx = t.gD[1], *dqkv = t.g3D;
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 1))));
+        RC(sq.fork());
+        RC(linear_wgrad(e, t.ddxb, D, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, w));
+        RC(lin_dgrad(e, t.ddxb, D, Md, Ld.out_s, dctx, D, 0, nullptr, 1.f, nullptr, s));
+        {
+          AttnProblem a;
+          a.q = e.ws<bf16>(Ld.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
+          a.causal = 1;
+          a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
+          a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
+          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
+          AttnGrads g;
+          g.d_o = dctx, g.dq = dqkv, g.dk = dqkv + D, g.dv = dqkv + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
+          g.scratch = e.ws<float>(e.attn_scratch);
+          RC(attention_core_bwd(a, g, s));
+        }
+        RC(sq.fork());
+        RC(linear_wgrad(e, dqkv, 3 * D, e.ws<bf16>(Ld.yn[0]), Md, Ld.qkv, w));
+        RC(lin_dgrad(e, dqkv, 3 * D, Md, Ld.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
+        RC(ln_bwd(e, dyn, nullptr, x0, Ld.n1, ddx, 1, Md, s));
+        RC(sq.end_unit());
+      }
     }
     RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s, pd, e.site(4)));
   }
@@ -612,65 +657,82 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
     ConfLayerRef& Lc = e.enc[i];
     float *x0 = e.xs_buf(5 * i), *x1 = e.xs_buf(5 * i + 1), *x2 = e.xs_buf(5 * i + 2), *x3 = e.xs_buf(5 * i + 3),
           *x4 = e.xs_buf(5 * i + 4);
-    bf16* dyn = e.ws<bf16>(e.gD[0]);
-    bf16* t1 = e.ws<bf16>(e.gD[1]);
-    bf16* t2 = e.ws<bf16>(e.gD[2]);
-    bf16* g3 = e.ws<bf16>(e.g3D);
     RC(ln_bwd(e, nullptr, dx, x4, Lc.n_fin, dx, 0, M, s));
-    // feed-forward (x 1/2)
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 6))));
-    RC(ffn_bwd(e, dxb, M, Lc.ff1, Lc.ff2, e.ws<bf16>(Lc.h_ff), e.ws<bf16>(Lc.yn[3]), x3, Lc.n_ff, dx, F, s));
-    // convolution module
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 4))));
-    RC(linear_wgrad(e, dxb, D, e.ws<bf16>(Lc.act), M, Lc.pw2, s));
-    RC(lin_dgrad(e, dxb, D, M, Lc.pw2, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d act
-    RC(bn_col_reduce(e.ws<bf16>(Lc.dwo), t1, e.ws<float>(Lc.bn.coef), M, D, e.ws<double>(Lc.bn.stats_b), 1, s));
-    RC(bn_bwd_finalize(e.ws<double>(Lc.bn.stats_b), M, D, e.G + Lc.bn.gamma, e.G + Lc.bn.beta,
-                       e.ws<float>(Lc.bn.kcoef), s));
-    RC(bn_bwd_apply(t1, nullptr, e.ws<bf16>(Lc.dwo), e.ws<float>(Lc.bn.coef), e.ws<float>(Lc.bn.kcoef), t2, nullptr, M,
-                    D, 2, s));  // t2 = d dwo
-    RC(dwconv1d_wgrad(e.ws<bf16>(Lc.u), t2, e.G + Lc.dw_w, e.G + Lc.dw_b, c.B, T, D, c.cnn_kernel, s));
-    RC(dwconv1d_fwd(t2, e.P + Lc.dw_w, nullptr, t1, c.B, T, D, c.cnn_kernel, 1, s));  // t1 = d u
-    RC(glu_bwd(e.ws<bf16>(Lc.hpw1), t1, g3, M, D, s));                                // g3 = d hpw1 [M, 2D]
-    RC(linear_wgrad(e, g3, 2 * D, e.ws<bf16>(Lc.yn[2]), M, Lc.pw1, s));
-    RC(lin_dgrad(e, g3, 2 * D, M, Lc.pw1, dyn, D, 0, nullptr, 1.f, nullptr, s));
-    RC(ln_bwd(e, dyn, nullptr, x2, Lc.n_conv, dx, 1, M, s));
-    // relative-position self-attention
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 3))));
-    RC(linear_wgrad(e, dxb, D, e.ws<bf16>(Lc.ctx), M, Lc.out, s));
-    RC(lin_dgrad(e, dxb, D, M, Lc.out, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d ctx
-    {
-      AttnProblem a;
-      a.q = e.ws<bf16>(Lc.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
-      a.p = e.ws<bf16>(Lc.pbuf), a.ldp = D;
-      a.bias_u = e.P + Lc.bias_u, a.bias_v = e.P + Lc.bias_v;
-      a.klen = e.ws<int>(e.klen);
-      a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
-      a.o = e.ws<bf16>(Lc.ctx), a.ldo = D, a.lse = e.ws<float>(Lc.lse);
-      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
-      AttnGrads g;
-      g.d_o = t1, g.dq = g3, g.dk = g3 + D, g.dv = g3 + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
-      g.dp = e.ws<float>(e.dp), g.dbias_u = e.G + Lc.bias_u, g.dbias_v = e.G + Lc.bias_v;
-      g.scratch = e.ws<float>(e.attn_scratch);
-      SVSR_CHECK_CUDA(cudaMemsetAsync(g.dp, 0, (size_t)(2 * T - 1) * D * 4, s));
-      RC(attention_core_bwd(a, g, s));
+    {  // unit: feed-forward (x 1/2)
+      const LrsScratch t = lrs_scratch(e, sq.unit);
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 6))));
+      RC(ffn_bwd(e, sq, t, t.dxb, M, Lc.ff1, Lc.ff2, e.ws<bf16>(Lc.h_ff), e.ws<bf16>(Lc.yn[3]), x3, Lc.n_ff, dx, F, s));
     }
-    RC(cast_scale_f32_bf16(e.ws<float>(e.dp), e.ws<bf16>(e.dpb), (long long)(2 * T - 1) * D, 1.f, s));
-    RC(linear_wgrad(e, e.ws<bf16>(e.dpb), D, pd > 0.f ? e.ws<bf16>(e.pe_drop) : e.ws<bf16>(e.pe_rel), 2 * T - 1, Lc.pos, s));
-    RC(linear_wgrad(e, g3, 3 * D, e.ws<bf16>(Lc.yn[1]), M, Lc.qkv, s));
-    RC(lin_dgrad(e, g3, 3 * D, M, Lc.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
-    RC(ln_bwd(e, dyn, nullptr, x1, Lc.n_mha, dx, 1, M, s));
-    // macaron feed-forward (x 1/2)
-    RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 1))));
-    RC(ffn_bwd(e, dxb, M, Lc.mac1, Lc.mac2, e.ws<bf16>(Lc.h_mac), e.ws<bf16>(Lc.yn[0]), x0, Lc.n_mac, dx, F, s));
+    {  // unit: convolution module
+      const LrsScratch t = lrs_scratch(e, sq.unit);
+      bf16 *dyn = t.gD[0], *t1 = t.gD[1], *t2 = t.gD[2], *g3 = t.g3D;
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 4))));
+      RC(sq.fork());
+      RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(Lc.act), M, Lc.pw2, w));
+      RC(lin_dgrad(e, t.dxb, D, M, Lc.pw2, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d act
+      RC(bn_col_reduce(e.ws<bf16>(Lc.dwo), t1, e.ws<float>(Lc.bn.coef), M, D, e.ws<double>(Lc.bn.stats_b), 1, s));
+      RC(bn_bwd_finalize(e.ws<double>(Lc.bn.stats_b), M, D, e.G + Lc.bn.gamma, e.G + Lc.bn.beta,
+                         e.ws<float>(Lc.bn.kcoef), s));
+      RC(bn_bwd_apply(t1, nullptr, e.ws<bf16>(Lc.dwo), e.ws<float>(Lc.bn.coef), e.ws<float>(Lc.bn.kcoef), t2, nullptr, M,
+                      D, 2, s));  // t2 = d dwo
+      RC(sq.fork());
+      RC(dwconv1d_wgrad(e.ws<bf16>(Lc.u), t2, e.G + Lc.dw_w, e.G + Lc.dw_b, c.B, T, D, c.cnn_kernel, w));
+      RC(dwconv1d_fwd(t2, e.ws<float>(Lc.dw_wT), nullptr, t1, c.B, T, D, c.cnn_kernel, 1, s, 1));  // t1 = d u
+      RC(glu_bwd(e.ws<bf16>(Lc.hpw1), t1, g3, M, D, s));                                            // g3 = d hpw1 [M, 2D]
+      RC(sq.fork());
+      RC(linear_wgrad(e, g3, 2 * D, e.ws<bf16>(Lc.yn[2]), M, Lc.pw1, w));
+      RC(lin_dgrad(e, g3, 2 * D, M, Lc.pw1, dyn, D, 0, nullptr, 1.f, nullptr, s));
+      RC(ln_bwd(e, dyn, nullptr, x2, Lc.n_conv, dx, 1, M, s));
+      RC(sq.end_unit());
+    }
+    {  // unit: relative-position self-attention
+      const LrsScratch t = lrs_scratch(e, sq.unit);
+      bf16 *dyn = t.gD[0], *t1 = t.gD[1], *g3 = t.g3D;
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 3))));
+      RC(sq.fork());
+      RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(Lc.ctx), M, Lc.out, w));
+      RC(lin_dgrad(e, t.dxb, D, M, Lc.out, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d ctx
+      {
+        AttnProblem a;
+        a.q = e.ws<bf16>(Lc.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
+        a.p = e.ws<bf16>(Lc.pbuf), a.ldp = D;
+        a.bias_u = e.P + Lc.bias_u, a.bias_v = e.P + Lc.bias_v;
+        a.klen = e.ws<int>(e.klen);
+        a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
+        a.o = e.ws<bf16>(Lc.ctx), a.ldo = D, a.lse = e.ws<float>(Lc.lse);
+        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
+        AttnGrads g;
+        g.d_o = t1, g.dq = g3, g.dk = g3 + D, g.dv = g3 + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
+        g.dp = e.ws<float>(e.dp), g.dbias_u = e.G + Lc.bias_u, g.dbias_v = e.G + Lc.bias_v;
+        g.scratch = e.ws<float>(e.attn_scratch);
+        SVSR_CHECK_CUDA(cudaMemsetAsync(g.dp, 0, (size_t)(2 * T - 1) * D * 4, s));
+        RC(attention_core_bwd(a, g, s));
+      }
+      RC(cast_scale_f32_bf16(e.ws<float>(e.dp), t.dpb, (long long)(2 * T - 1) * D, 1.f, s));
+      RC(sq.fork());
+      RC(linear_wgrad(e, t.dpb, D, pd > 0.f ? e.ws<bf16>(e.pe_drop) : e.ws<bf16>(e.pe_rel), 2 * T - 1, Lc.pos, w));
+      RC(linear_wgrad(e, g3, 3 * D, e.ws<bf16>(Lc.yn[1]), M, Lc.qkv, w));
+      RC(lin_dgrad(e, g3, 3 * D, M, Lc.qkv, dyn, D, 0, nullptr, 1.f, nullptr, s));
+      RC(ln_bwd(e, dyn, nullptr, x1, Lc.n_mha, dx, 1, M, s));
+      RC(sq.end_unit());
+    }
+    {  // unit: macaron feed-forward (x 1/2)
+      const LrsScratch t = lrs_scratch(e, sq.unit);
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 1))));
+      RC(ffn_bwd(e, sq, t, t.dxb, M, Lc.mac1, Lc.mac2, e.ws<bf16>(Lc.h_mac), e.ws<bf16>(Lc.yn[0]), x0, Lc.n_mac, dx, F, s));
+    }
   }
-  // ---- embed (x * sqrt(D)) -> average pool -> frontend ----
-  RC(cast_scale_f32_bf16(dx, dxb, (long long)M * D, sqrtf((float)D), s, pd, e.site(1)));
-  RC(linear_wgrad(e, dxb, D, e.ws<bf16>(e.feats), M, e.embed, s));
-  RC(lin_dgrad(e, dxb, D, M, e.embed, e.ws<bf16>(e.dfeat), 512, 0, nullptr, 1.f, nullptr, s));
-  const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
-  RC(meanpool_bf16_bwd(e.ws<bf16>(e.dfeat), e.ws<bf16>(e.fe.gbuf[0]), M, HW4, 512, s));
-  SideQueue sq(e, s);
+  // ---- unit: embed (x * sqrt(D)) -> average pool; then the frontend ----
+  {
+    const LrsScratch t = lrs_scratch(e, sq.unit);
+    RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, sqrtf((float)D), s, pd, e.site(1)));
+    RC(sq.fork());
+    RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(e.feats), M, e.embed, w));
+    RC(lin_dgrad(e, t.dxb, D, M, e.embed, e.ws<bf16>(e.dfeat), 512, 0, nullptr, 1.f, nullptr, s));
+    const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
+    RC(meanpool_bf16_bwd(e.ws<bf16>(e.dfeat), e.ws<bf16>(e.fe.gbuf[0]), M, HW4, 512, s));
+    RC(sq.end_unit());
+  }
   return frontend_backward(e, e.fe, sq, s);
 }
 
