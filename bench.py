@@ -146,7 +146,7 @@ def run_native_arm(args):
 
     from syncvsr_b200._lib import check, lib
     from syncvsr_b200.lightning import TransformerLightningModule
-    from syncvsr_b200.train import DataParallelStep, FusedAdamW
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW, PrefetchedStep
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,20 +215,19 @@ def run_native_arm(args):
     # ---- timed region 2: end to end through the public API with pinned HOST inputs ----
     host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    # public API: PrefetchedStep copies every step's inputs from pinned host memory (the copy of step i+1 overlaps the
+    # compute of step i on a second stream) and reads every step's loss back to pinned host memory
+    pipe = PrefetchedStep(step, host_batches[0])
 
-    def e2e_step(i):
-        hb = host_batches[i % n_batches]
-        db = tuple(t.to("cuda", non_blocking=True) for t in hb)
-        m = step(*db)
-        loss_host.copy_(m["loss_total"].reshape(1), non_blocking=True)
+    def e2e_run(n):
+        for i in range(n):
+            nxt = host_batches[(i + 1) % n_batches] if i + 1 < n else None
+            pipe(host_batches[i % n_batches], nxt)
 
-    for i in range(2):
-        e2e_step(i)
+    e2e_run(2)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps

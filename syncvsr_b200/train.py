@@ -135,3 +135,48 @@ class SentenceDataParallelStep:
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
         self.opt.step(lr=lr, grad_div=float(self.world))
         return out
+
+
+class PrefetchedStep:
+    """Feeds a training step from pinned HOST batches: the host->device copy of batch i+1 runs on its own stream while
+    batch i computes (two device buffer sets, event hand-off), and the step's loss is read back to pinned host memory.
+    `step` is a DataParallelStep / SentenceDataParallelStep; batches are tuples of pinned CPU tensors of fixed shapes."""
+
+    def __init__(self, step, example_batch):
+        self.step = step
+        dev = step.module.flat_params.device
+        self.bufs = [tuple(torch.empty_like(t, device=dev) for t in example_batch) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._i = 0
+        self._primed = False
+
+    def _enqueue_copy(self, slot: int, host_batch) -> None:
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])  # the step that last read this slot has finished
+            for d, h in zip(self.bufs[slot], host_batch):
+                d.copy_(h, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+
+    def __call__(self, host_batch, next_host_batch=None):
+        """Runs one step on `host_batch`; if `next_host_batch` is given its copy overlaps this step's compute."""
+        slot = self._i & 1
+        cur = torch.cuda.current_stream()
+        if not self._primed:
+            for ev in self.consumed:
+                ev.record(cur)
+            self._enqueue_copy(slot, host_batch)
+            self._primed = True
+        if next_host_batch is not None:
+            self._enqueue_copy(slot ^ 1, next_host_batch)
+        cur.wait_event(self.copied[slot])
+        out = self.step(*self.bufs[slot])
+        self.consumed[slot].record(cur)
+        loss = out["loss_total"] if isinstance(out, dict) else out[0]
+        self.loss_host.copy_(loss.reshape(1), non_blocking=True)
+        self._i += 1
+        if next_host_batch is None:
+            self._primed = False
+        return out

@@ -290,3 +290,32 @@ def test_word_boundary_variant_dim_513(Module, golden_dir):
     # golden gradient of the reference module itself
     assert rel(m.cls_token.grad.cpu(), fx["grad_cls_token"]) < 4e-2
     assert rel(m._param_views["encoder.layers.0.0.g"].grad.cpu(), fx["grad_enc0_g"]) < 4e-2
+
+
+def test_prefetched_host_pipeline_equals_direct_steps(Module):
+    """PrefetchedStep (pinned host batches, copy of step i+1 overlapped with step i) must produce exactly the same
+    parameter trajectory as feeding the same batches from device memory."""
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW, PrefetchedStep
+
+    def run(prefetch):
+        torch.manual_seed(11)
+        m = Module(make_cfg(depth=1)).train()
+        step = DataParallelStep(m, FusedAdamW.from_config(m))
+        batches = [O.make_inputs(500 + i, 2) for i in range(4)]
+        losses = []
+        if prefetch:
+            host = [tuple(t.pin_memory() for t in b) for b in batches]
+            pipe = PrefetchedStep(step, host[0])
+            for i in range(4):
+                out = pipe(host[i], host[i + 1] if i + 1 < 4 else None)
+                torch.cuda.synchronize()
+                losses.append(float(pipe.loss_host[0]))
+        else:
+            for b in batches:
+                losses.append(float(step(*(t.cuda() for t in b))["loss_total"]))
+        return losses, m.flat_params.clone()
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert l0 == pytest.approx(l1, rel=1e-5)
+    assert rel(p1, p0) < 1e-5
