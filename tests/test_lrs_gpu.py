@@ -565,3 +565,41 @@ def test_training_config_dropout_is_consistent_between_forward_and_backward(E2E,
     with torch.no_grad():
         e1, e2 = float(m(x, lengths, tokens, label)[0]), float(m(x, lengths, tokens, label)[0])
     assert e1 == e2
+
+
+def test_edge_cases_single_clip_short_and_infeasible_ctc(E2E, golden_dir):
+    """Edge cases the loss definitions imply (ctc.py:66-73 zero_infinity; add_sos_eos on ragged labels): a batch of one,
+    a clip shorter than its transcript (no CTC alignment exists -> that sample scores 0 and gets no CTC gradient), and a
+    transcript of a single token."""
+    base = dict(torch.load(golden_dir / "lrs_small.pt")["meta"])
+    # (1) batch of one
+    c = dict(base, B=1, T=9)
+    m, P, inputs = _native(E2E, c)
+    x, lengths, tokens, label = inputs
+    out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    o = _oracle(c, P, inputs, q=bf16_ste)
+    for got, key in zip(out[:4], ("loss", "loss_ctc", "loss_att", "loss_audio")):
+        assert float(got) == pytest.approx(float(o[key]), rel=2e-3), key
+    out[0].backward()
+    assert torch.isfinite(m.flat_grads).all()
+    # (2) clip 1 has 2 valid frames but a 6-token transcript; clip 2 has a single-token transcript
+    c = dict(base, B=3, T=12)
+    m, P, (x, lengths, tokens, label) = _native(E2E, c)
+    lengths = torch.tensor([12, 2, 7])
+    x[1, 2:] = 0
+    x[2, 7:] = 0
+    label = torch.full((3, 6), -1, dtype=torch.long)
+    label[0, :4] = torch.tensor([5, 9, 9, 17])
+    label[1, :6] = torch.tensor([3, 4, 5, 6, 7, 8])
+    label[2, :1] = torch.tensor([11])
+    inputs = (x, lengths, tokens, label)
+    out = m(x.cuda(), lengths.cuda(), tokens.cuda(), label.cuda())
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = _oracle(c, Pq, inputs, q=bf16_ste)
+    for got, key in zip(out[:4], ("loss", "loss_ctc", "loss_att", "loss_audio")):
+        assert float(got) == pytest.approx(float(o[key]), rel=2e-3), key
+    out[0].backward()
+    o["loss"].backward()
+    assert torch.isfinite(m.flat_grads).all()
+    assert rel(m._param_views["ctc.ctc_lo.bias"].grad, Pq["ctc.ctc_lo.bias"].grad) < 5e-2
+    assert rel(m._param_views["decoder.output_layer.bias"].grad, Pq["decoder.output_layer.bias"].grad) < 5e-2

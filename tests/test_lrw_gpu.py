@@ -319,3 +319,22 @@ def test_prefetched_host_pipeline_equals_direct_steps(Module):
     l1, p1 = run(True)
     assert l0 == pytest.approx(l1, rel=1e-5)
     assert rel(p1, p0) < 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(1, 29), (3, 21), (5, 40)])
+def test_edge_geometries_batch_one_and_other_clip_lengths(Module, B, T):
+    """The engine is rebuilt per clip geometry: a single clip, and clip lengths other than LRW's 29 frames."""
+    m = Module(make_cfg(depth=1)).train()
+    P = O.make_params(12, depth=1)
+    m.load_state_dict(P, strict=False)
+    videos, tokens, labels, wm = O.make_inputs(600 + B, B, T=T)
+    out = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = O.lrw_forward(Pq, videos, tokens, labels, wm, depth=1, q=O.bf16_ste)
+    assert float(out["loss_total"]) == pytest.approx(float(o["loss_total"]), rel=1e-3)
+    assert m.last_hidden_state().shape == (B, T + 1, 512)
+    out["loss_total"].backward()
+    o["loss_total"].backward()
+    assert torch.isfinite(m.flat_grads).all()
+    for k in ("audio_projection.bias", "category_classifier.weight", "cls_token"):
+        assert rel(m._param_views[k].grad, Pq[k].grad) < 4e-2, k
