@@ -29,10 +29,18 @@ B_PER_GPU = 64
 T, S = 29, 88
 
 
-def lrw_config(depth=12):
-    from oracle.ref_loader import AttrDict  # plain attr-dict helper only (no oracle arithmetic)
+class _Attrs(dict):
+    """dict with attribute access (stands in for the reference's OmegaConf DictConfig)."""
 
-    return AttrDict.wrap({
+    __getattr__ = dict.get
+
+
+def _attrs(d):
+    return _Attrs({k: _attrs(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+def lrw_config(depth=12):
+    return _attrs({
         "data": {"use_word_boundary": False, "input_size": S},
         "model": {"resnet": "resnet18", "wav2vec": {"path": "./vq-wav2vec_kmeans.pt"},
                   "bert": {"type": "x-transformers", "num_tokens": 1, "dim": 512, "depth": depth, "heads": 8,
