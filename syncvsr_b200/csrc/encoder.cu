@@ -4,9 +4,30 @@ namespace svsr {
 
 namespace {
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of what these kernels store):
+// 2 MUFU + ~8 FMA instead of libdevice's branchy erff
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return copysignf(1.0f - p * t * __expf(-ax * ax), x);
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  return 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y, v[6] = d.x, v[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]), u.y = pack_bf16x2(v[2], v[3]), u.z = pack_bf16x2(v[4], v[5]), u.w = pack_bf16x2(v[6], v[7]);
+  return u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,45 +324,50 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 }
 
 // u = dropout_p(value * gelu(gate))   (x-transformers FeedForward: GLU -> Dropout(ff_dropout) -> Linear)
-__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M,
-                                 int F, float p, unsigned long long seed) {
-  const long long total = M * (F / 2);
+__global__ void __launch_bounds__(256)
+geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M, int F, float p,
+                 unsigned long long seed) {
+  const int fg = F >> 3;  // 8 hidden units (16 bytes) per thread
+  const long long total = M * fg;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / (F / 2);
-    const int c = (int)(i % (F / 2)) * 2;
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + c);
-    const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
-    float o0 = __low2float(v) * gelu_f(__low2float(gt)), o1 = __high2float(v) * gelu_f(__high2float(gt));
-    if (p > 0.f) {
-      o0 = dropout_keep(seed, (unsigned long long)(r * F + c), p) ? o0 * keep_scale : 0.f;
-      o1 = dropout_keep(seed, (unsigned long long)(r * F + c + 1), p) ? o1 * keep_scale : 0.f;
+    const long long r = i / fg;
+    const int c = (int)(i % fg) * 8;
+    float v[8], gt[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + c), v);
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + c), gt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = v[k] * gelu_f(gt[k]);
+      if (p > 0.f) o[k] = dropout_keep(seed, (unsigned long long)(r * F + c + k), p) ? o[k] * keep_scale : 0.f;
     }
-    *reinterpret_cast<__nv_bfloat162*>(u + r * F + c) = __floats2bfloat162_rn(o0, o1);
+    *reinterpret_cast<uint4*>(u + r * F + c) = pack8(o);
   }
 }
-__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ du,
-                                 __nv_bfloat16* __restrict__ dh, long long M, int F, float p,
-                                 unsigned long long seed) {
-  const long long total = M * (F / 2);
+__global__ void __launch_bounds__(256)
+geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ du,
+                 __nv_bfloat16* __restrict__ dh, long long M, int F, float p, unsigned long long seed) {
+  const int fg = F >> 3;
+  const long long total = M * fg;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / (F / 2);
-    const int c = (int)(i % (F / 2)) * 2;
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + c);
-    const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(h + r * 2 * F + F + c);
-    const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(du + r * F + c);
-    const float v0 = __low2float(v), v1 = __high2float(v), g0 = __low2float(gt), g1 = __high2float(gt);
-    float d0 = __low2float(d), d1 = __high2float(d);
-    if (p > 0.f) {
-      d0 = dropout_keep(seed, (unsigned long long)(r * F + c), p) ? d0 * keep_scale : 0.f;
-      d1 = dropout_keep(seed, (unsigned long long)(r * F + c + 1), p) ? d1 * keep_scale : 0.f;
+    const long long r = i / fg;
+    const int c = (int)(i % fg) * 8;
+    float v[8], gt[8], d[8], dv[8], dg[8];
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + c), v);
+    unpack8(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + c), gt);
+    unpack8(*reinterpret_cast<const uint4*>(du + r * F + c), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float dk = d[k];
+      if (p > 0.f) dk = dropout_keep(seed, (unsigned long long)(r * F + c + k), p) ? dk * keep_scale : 0.f;
+      dv[k] = dk * gelu_f(gt[k]);
+      dg[k] = dk * v[k] * gelu_grad_f(gt[k]);
     }
-    *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + c) = __floats2bfloat162_rn(d0 * gelu_f(g0), d1 * gelu_f(g1));
-    *reinterpret_cast<__nv_bfloat162*>(dh + r * 2 * F + F + c) =
-        __floats2bfloat162_rn(d0 * v0 * gelu_grad_f(g0), d1 * v1 * gelu_grad_f(g1));
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + c) = pack8(dv);
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + F + c) = pack8(dg);
   }
 }
 
@@ -367,7 +393,8 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const f
                 __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim) {
   if (norm_dim <= 0) norm_dim = D;
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
-  const int blocks = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
+  // one wave of CTAs, >= 2 rows per warp: halves the per-CTA column-reduction + atomic tail of the weight gradient
+  const int blocks = (M + 15) / 16 < 148 ? (M + 15) / 16 : 148;
   if (D <= 512)
     rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
   else
@@ -409,7 +436,8 @@ int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat1
   return SVSR_OK;
 }
 int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s) {
-  const long long total = (long long)M * (F / 2);
+  SVSR_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+  const long long total = (long long)M * (F / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F, p, seed);
   LAUNCH_CHECK();
@@ -417,7 +445,8 @@ int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, u
 }
 int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, float p,
               unsigned long long seed, cudaStream_t s) {
-  const long long total = (long long)M * (F / 2);
+  SVSR_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+  const long long total = (long long)M * (F / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F, p, seed);
   LAUNCH_CHECK();

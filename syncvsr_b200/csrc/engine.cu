@@ -481,7 +481,7 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   float* dx = e.ws<float>(e.dx);
   SideQueue sq(e, s);
-  cudaStream_t w = e.side;  // weight-gradient stream
+  cudaStream_t w = e.wq;  // weight-gradient stream (set by SideQueue)
   bf16* T0 = e.ws<bf16>(e.fe.gbuf[0]);  // d loss / d (last block output): input of frontend_backward
   if (stage <= 0) {
   if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients

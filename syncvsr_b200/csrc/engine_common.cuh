@@ -7,6 +7,7 @@
 //                                                         backbones/modules/resnet.py:45-177
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,6 +92,8 @@ struct EngineBase {
   size_t wgrad_tmp = 0;  // fp32 scratch of the conv weight-gradient GEMM (largest [R*S*Cin, Cout])
   // weight-gradient side stream (backward): forked from / joined to the caller's stream with events
   cudaStream_t side = nullptr;
+  cudaStream_t wq = nullptr;  // where weight-gradient work goes for the current backward: `side`, or the caller's
+                              // stream when SVSR_SINGLE_STREAM=1 (hazard check: both orders must give the same gradients)
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int fork_idx = 0;
@@ -279,24 +282,27 @@ struct SideQueue {
   cudaStream_t s;
   int unit = 0;
   int rc = SVSR_OK;
-  SideQueue(EngineBase& e_, cudaStream_t s_) : e(e_), s(s_) {}
+  SideQueue(EngineBase& e_, cudaStream_t s_) : e(e_), s(s_) {
+    const char* one = getenv("SVSR_SINGLE_STREAM");
+    e.wq = (one && one[0] == '1') ? s_ : e_.side;
+  }
   // everything enqueued on `s` so far becomes visible to the side stream
   int fork() {
     cudaEvent_t ev = e.ev_fork[e.fork_idx++ & 3];
     SVSR_CHECK_CUDA(cudaEventRecord(ev, s));
-    SVSR_CHECK_CUDA(cudaStreamWaitEvent(e.side, ev, 0));
+    SVSR_CHECK_CUDA(cudaStreamWaitEvent(e.wq, ev, 0));
     return SVSR_OK;
   }
   // close unit `unit` on the side stream and make the chain wait for unit-1 (so unit-2's buffers are reusable next)
   int end_unit() {
-    SVSR_CHECK_CUDA(cudaEventRecord(e.ev_done[unit & 3], e.side));
+    SVSR_CHECK_CUDA(cudaEventRecord(e.ev_done[unit & 3], e.wq));
     if (unit >= 1) SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, e.ev_done[(unit - 1) & 3], 0));
     ++unit;
     return SVSR_OK;
   }
   int join() {
     cudaEvent_t ev = e.ev_done[unit & 3];
-    SVSR_CHECK_CUDA(cudaEventRecord(ev, e.side));
+    SVSR_CHECK_CUDA(cudaEventRecord(ev, e.wq));
     SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, ev, 0));
     return SVSR_OK;
   }
@@ -444,7 +450,7 @@ static int frontend_forward(EngineBase& e, Frontend& f, const float* videos, int
 // Backward of the frontend. On entry gbuf[0] holds d loss / d (last block output) (bf16, NHWC); weight-gradient
 // GEMMs go to the side stream through `sq`. Ends with sq.join().
 static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStream_t s) {
-  cudaStream_t w = e.side;
+  cudaStream_t w = e.wq;
   bf16* T0 = e.ws<bf16>(f.gbuf[0]);  // dOut of the current block, later da1
   bf16* T2 = e.ws<bf16>(f.gbuf[1]);  // activation-masked upstream gradient (identity shortcut branch)
   bf16* T4 = e.ws<bf16>(f.gbuf[2]);  // dX of the current block

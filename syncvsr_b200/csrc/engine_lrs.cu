@@ -528,10 +528,10 @@ static int ffn_bwd(LrsEngine& e, SideQueue& sq, const LrsScratch& t, const bf16*
   bf16* dh = t.gF;
   bf16* dyn = t.gD[0];
   RC(sq.fork());  // dyb complete
-  RC(linear_wgrad(e, dyb, D, h, rows, w2, e.side));
+  RC(linear_wgrad(e, dyb, D, h, rows, w2, e.wq));
   RC(lin_dgrad(e, dyb, D, rows, w2, dh, F, 0, nullptr, hs, h, s));  // ReLU backward fused: zero where h <= 0
   RC(sq.fork());  // dh complete
-  RC(linear_wgrad(e, dh, F, yn, rows, w1, e.side));
+  RC(linear_wgrad(e, dh, F, yn, rows, w1, e.wq));
   RC(lin_dgrad(e, dh, F, rows, w1, dyn, D, 0, nullptr, 1.f, nullptr, s));
   RC(ln_bwd(e, dyn, nullptr, x_in, n, dx, 1, rows, s));
   return sq.end_unit();
@@ -548,7 +548,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   const bf16* enc_b = e.ws<bf16>(e.enc_b);
   const float pd = e.pd, pa = e.pa;
   SideQueue sq(e, s);
-  cudaStream_t w = e.side;
+  cudaStream_t w = e.wq;
   if (grad_scale) {
     if (e.last_audio) RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)M * e.AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)M * e.ldv, grad_scale, s));

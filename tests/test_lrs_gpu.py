@@ -603,3 +603,32 @@ def test_edge_cases_single_clip_short_and_infeasible_ctc(E2E, golden_dir):
     assert torch.isfinite(m.flat_grads).all()
     assert rel(m._param_views["ctc.ctc_lo.bias"].grad, Pq["ctc.ctc_lo.bias"].grad) < 5e-2
     assert rel(m._param_views["decoder.output_layer.bias"].grad, Pq["decoder.output_layer.bias"].grad) < 5e-2
+
+
+def test_two_stream_backward_equals_single_stream_at_c3_width(E2E, monkeypatch):
+    """Hazard check of the two-stream backward (weight gradients on the side stream, double-buffered temporaries): the
+    same step with every kernel on ONE stream (SVSR_SINGLE_STREAM=1) must give the same gradients up to fp32 atomics."""
+    c = dict(adim=768, heads=12, eunits=3072, elayers=3, dlayers=2, odim=5049, A=2, G=2, V=640)
+    a = _args(c)
+    a.max_label_len = 24
+    a.dropout_rate, a.transformer_attn_dropout_rate = 0.1, 0.1
+    torch.manual_seed(3)
+    m = E2E(5049, a).train()
+    m.dropout_seed = 77
+    B, T = 6, 150
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(B, T, 1, 88, 88, device="cuda", generator=g)
+    lengths = torch.tensor([150, 75, 120, 99, 150, 133], device="cuda")
+    tokens = torch.randint(0, 640, (B, 2 * T, 2), device="cuda", generator=g)
+    label = torch.full((B, 24), -1, dtype=torch.long, device="cuda")
+    for b, n in enumerate((24, 10, 17, 21, 5, 13)):
+        label[b, :n] = torch.randint(1, 5048, (n,), device="cuda", generator=g)
+    grads = []
+    for single in ("0", "1", "0"):
+        monkeypatch.setenv("SVSR_SINGLE_STREAM", single)
+        m.flat_grads.zero_()
+        out = m(x, lengths, tokens, label)
+        out[0].backward()
+        torch.cuda.synchronize()
+        grads.append(m.flat_grads.clone())
+    assert rel(grads[0], grads[1]) < 1e-4 and rel(grads[2], grads[1]) < 1e-4

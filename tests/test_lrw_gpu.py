@@ -338,3 +338,20 @@ def test_edge_geometries_batch_one_and_other_clip_lengths(Module, B, T):
     assert torch.isfinite(m.flat_grads).all()
     for k in ("audio_projection.bias", "category_classifier.weight", "cls_token"):
         assert rel(m._param_views[k].grad, Pq[k].grad) < 4e-2, k
+
+
+def test_two_stream_backward_equals_single_stream_full_batch(Module, monkeypatch):
+    """Hazard check of the LRW two-stream backward at the bench geometry (B=64, 12 layers)."""
+    m = Module(make_cfg(depth=12)).train()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B = 64
+    batch = (torch.randn(B, 1, 29, 88, 88, device="cuda", generator=g), torch.randint(0, 320, (B, 116, 2), device="cuda", generator=g),
+             torch.randint(0, 500, (B,), device="cuda", generator=g), torch.zeros(B, 1, device="cuda"))
+    grads = []
+    for single in ("0", "1", "0"):
+        monkeypatch.setenv("SVSR_SINGLE_STREAM", single)
+        m.flat_grads.zero_()
+        m(*batch)["loss_total"].backward()
+        torch.cuda.synchronize()
+        grads.append(m.flat_grads.clone())
+    assert rel(grads[0], grads[1]) < 1e-4 and rel(grads[2], grads[1]) < 1e-4
