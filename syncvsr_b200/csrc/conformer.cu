@@ -464,8 +464,12 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const float*
 // Multi-head attention core (d_k = 64) with optional relative-position term, key-length and causal masks.
 // One CTA = AQT query rows of one (clip, head); K, V and the window of P rows those queries can reach stay in
 // shared memory as bf16 with a 33-word row pitch (lanes iterate over keys: conflict-free); fp32 math.
+// Register blocking: a warp owns 4 query rows and every lane 4 keys (16 accumulators), so one shared-memory word of K / P
+// feeds 4 rows and one broadcast q pair feeds 4 keys: 8 LDS per 32 FMA instead of 5 per 8. The relative-position term
+// is computed against the P window in the window's own index (rows shared by the 4 queries) and added into the score
+// at its shifted position; P.V and dS.K / dS.P read the score rows as float4 broadcasts.
 // =================================================================================================
-constexpr int AQT = 16;
+constexpr int AQT = 32;   // query rows per CTA (8 warps x 4 rows)
 constexpr int APITCH = 66;  // bf16 elements per shared-memory row (33 words)
 
 struct AttnK {
@@ -492,11 +496,13 @@ struct AttnSmem {
   __nv_bfloat16 *Ks, *Vs, *Ps;
   float *S, *S2, *qu, *qv, *dO;
 };
+// row pitch (floats) of the score tiles: holds Tk keys or, in backward, the Tk + AQT - 1 window positions; multiple of 4
+__host__ __device__ inline int attn_spitch(int Tk) { return (Tk + AQT - 1 + 3) & ~3; }
 __host__ __device__ inline size_t attn_smem_bytes(int Tk, bool rel, bool bwd) {
   size_t b = (size_t)2 * Tk * APITCH * 2;
   if (rel) b += (size_t)(Tk + AQT - 1) * APITCH * 2;
   b = (b + 15) & ~size_t(15);
-  b += (size_t)AQT * Tk * 4 * (bwd ? 2 : 1);
+  b += (size_t)AQT * attn_spitch(Tk) * 4 * (bwd ? 2 : 1);
   b += (size_t)AQT * 64 * 4 * (bwd ? 3 : 2);
   return b + 16;
 }
@@ -508,9 +514,9 @@ __device__ __forceinline__ AttnSmem attn_carve(uint8_t* base, int Tk, bool rel, 
   size_t off = (size_t)2 * Tk * APITCH * 2 + (rel ? (size_t)(Tk + AQT - 1) * APITCH * 2 : 0);
   off = (off + 15) & ~size_t(15);
   s.S = reinterpret_cast<float*>(base + off);
-  off += (size_t)AQT * Tk * 4;
+  off += (size_t)AQT * attn_spitch(Tk) * 4;
   s.S2 = reinterpret_cast<float*>(base + off);
-  if (bwd) off += (size_t)AQT * Tk * 4;
+  if (bwd) off += (size_t)AQT * attn_spitch(Tk) * 4;
   s.qu = reinterpret_cast<float*>(base + off);
   s.qv = s.qu + AQT * 64;
   s.dO = s.qv + AQT * 64;
@@ -549,44 +555,87 @@ __device__ __forceinline__ void attn_load_q(float* qd, const __nv_bfloat16* src,
   }
 }
 
-// dot products of one fp32 query-side row (64 values in shared memory) with 4 x 32 bf16 rows (lane + 32*u + j0),
-// row index clamped to [0, nrows): out-of-range results are discarded by the caller.
-__device__ __forceinline__ void attn_dot4(const float* qrow, const __nv_bfloat16* M, int j0, int row_shift, int nrows,
-                                          float (&acc)[4]) {
+// acc[r][u] += q_{r} . M_{row(j0 + 32u + lane)} for the 4 consecutive fp32 query-side rows at qrows (64 floats each) and 4 x 32
+// bf16 rows of M (row index clamped to [0, nrows): out-of-range results are discarded by the caller)
+__device__ __forceinline__ void attn_dot4x4(const float* qrows, const __nv_bfloat16* M, int j0, int nrows,
+                                            float (&acc)[4][4]) {
   const int lane = threadIdx.x & 31;
   const uint32_t* rows[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    int j = j0 + 32 * u + lane + row_shift;
-    j = j < 0 ? 0 : (j >= nrows ? nrows - 1 : j);
+    int j = j0 + 32 * u + lane;
+    j = j >= nrows ? nrows - 1 : j;
     rows[u] = reinterpret_cast<const uint32_t*>(M + (size_t)j * APITCH);
   }
-#pragma unroll 8
+#pragma unroll 4
   for (int w = 0; w < 32; ++w) {
-    const float2 qq = reinterpret_cast<const float2*>(qrow)[w];
+    float2 qq[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) qq[r] = reinterpret_cast<const float2*>(qrows + r * 64)[w];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float2 kk = unpack_bf16x2(rows[u][w]);
-      acc[u] = fmaf(qq.x, kk.x, acc[u]);
-      acc[u] = fmaf(qq.y, kk.y, acc[u]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][u] = fmaf(qq[r].x, kk.x, fmaf(qq[r].y, kk.y, acc[r][u]));
     }
   }
 }
 
-// raw masked scores of query row ii into S[ii][0..Tk): scale * (qu.k_j + qv.p_{j-i+Tk-1}), -inf where masked
-__device__ __forceinline__ void attn_scores_row(const AttnK& a, const AttnSmem& sm, int ii, int i, int klen) {
+// raw (unscaled, unmasked) scores of the warp's 4 query rows ii0..ii0+3 into S: (q+u).k_j + (q+v).p_{j-i+Tk-1}
+__device__ __forceinline__ void attn_scores4(const AttnK& a, const AttnSmem& sm, int ii0, int sp) {
   const int lane = threadIdx.x & 31;
-  const int shift = AQT - 1 - ii;
   for (int j0 = 0; j0 < a.Tk; j0 += 128) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    attn_dot4(sm.qu + ii * 64, sm.Ks, j0, 0, a.Tk, acc);
-    if (a.p) attn_dot4(sm.qv + ii * 64, sm.Ps, j0, shift, a.Tk + AQT - 1, acc);
+    float acc[4][4] = {};
+    attn_dot4x4(sm.qu + ii0 * 64, sm.Ks, j0, a.Tk, acc);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 32 * u + lane;
       if (j < a.Tk) {
-        const bool masked = j >= klen || (a.causal && j > i);
-        sm.S[ii * a.Tk + j] = masked ? -INFINITY : acc[u] * a.scale;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sm.S[(ii0 + r) * sp + j] = acc[r][u];
+      }
+    }
+  }
+  if (a.p) {
+    __syncwarp();
+    const int nP = a.Tk + AQT - 1;  // window row rl of query ii pairs with key j = rl - (AQT - 1 - ii)
+    for (int r0 = 0; r0 < nP; r0 += 128) {
+      float acc[4][4] = {};
+      attn_dot4x4(sm.qv + ii0 * 64, sm.Ps, r0, nP, acc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rl = r0 + 32 * u + lane;
+        if (rl < nP) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int j = rl - (AQT - 1 - (ii0 + r));
+            if (j >= 0 && j < a.Tk) sm.S[(ii0 + r) * sp + j] += acc[r][u];  // exactly one writer per (row, key)
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// o[r] += sum_x W[(ii0 + r)][x] * M[x][2*lane .. 2*lane+1] over x in [0, n) (n rounded up to 4: the pad weights are 0);
+// W rows (pitch sp, 16-byte aligned) are read as float4 broadcasts, M rows (bf16, pitch 33 words) one word per lane
+__device__ __forceinline__ void attn_wsum4(const float* W, int sp, int ii0, const __nv_bfloat16* M, int n, int nrows,
+                                           float2 (&o)[4]) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t* Mw = reinterpret_cast<const uint32_t*>(M) + lane;
+  for (int x = 0; x < n; x += 4) {
+    float4 wv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) wv[r] = *reinterpret_cast<const float4*>(W + (ii0 + r) * sp + x);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int xx = x + t < nrows ? x + t : nrows - 1;
+      const float2 mv = unpack_bf16x2(Mw[(size_t)xx * (APITCH / 2)]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float wgt = t == 0 ? wv[r].x : (t == 1 ? wv[r].y : (t == 2 ? wv[r].z : wv[r].w));
+        o[r].x = fmaf(wgt, mv.x, o[r].x), o[r].y = fmaf(wgt, mv.y, o[r].y);
       }
     }
   }
@@ -608,17 +657,25 @@ __global__ void __launch_bounds__(256) attention_core_fwd_kernel(const AttnK a) 
   const AttnSmem sm = attn_carve(attn_smem_raw, a.Tk, a.p != nullptr, false);
   const int i0 = blockIdx.x * AQT, h = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sp = attn_spitch(a.Tk), ii0 = warp * 4;
   attn_stage(a, sm, b, h, i0);
   __syncthreads();
+  if (i0 + ii0 >= a.Tq) return;  // no block-level barrier below
   const int klen = a.klen ? min(a.klen[b], a.Tk) : a.Tk;
-  for (int ii = warp; ii < AQT; ii += 8) {
-    const int i = i0 + ii;
-    if (i >= a.Tq) break;
-    attn_scores_row(a, sm, ii, i, klen);
-    __syncwarp();
-    float* S = sm.S + ii * a.Tk;
+  const int Tk4 = (a.Tk + 3) & ~3;
+  attn_scores4(a, sm, ii0, sp);
+  float inv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ii0 + r;
+    float* S = sm.S + (ii0 + r) * sp;
     float m = -INFINITY;
-    for (int j = lane; j < a.Tk; j += 32) m = fmaxf(m, S[j]);
+    for (int j = lane; j < a.Tk; j += 32) {
+      const bool masked = j >= klen || (a.causal && j > i) || i >= a.Tq;
+      const float sj = masked ? -INFINITY : S[j] * a.scale;
+      S[j] = sj;
+      m = fmaxf(m, sj);
+    }
     m = warp_max(m);
     float sum = 0.f;
     if (m > -INFINITY) {
@@ -633,57 +690,64 @@ __global__ void __launch_bounds__(256) attention_core_fwd_kernel(const AttnK a) 
     } else {  // every key masked: the reference's re-masked softmax row is all zero (attention.py:72-77)
       for (int j = lane; j < a.Tk; j += 32) S[j] = 0.f;
     }
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    if (lane == 0 && a.lse) a.lse[((long long)b * a.H + h) * a.Tq + i] = sum > 0.f ? m + logf(sum) : 0.f;
-    __syncwarp();
-    float2 o = make_float2(0.f, 0.f);
-    const uint32_t* V = reinterpret_cast<const uint32_t*>(sm.Vs) + lane;
-    for (int j = 0; j < a.Tk; ++j) {
-      const float pj = S[j];
-      const float2 vv = unpack_bf16x2(V[(size_t)j * (APITCH / 2)]);
-      o.x = fmaf(pj, vv.x, o.x), o.y = fmaf(pj, vv.y, o.y);
-    }
-    *reinterpret_cast<uint32_t*>(a.o + ((long long)b * a.Tq + i) * a.ldo + h * 64 + 2 * lane) =
-        pack_bf16x2(o.x * inv, o.y * inv);
+    if (lane < Tk4 - a.Tk) S[a.Tk + lane] = 0.f;  // pad weights of the float4 reads
+    inv[r] = sum > 0.f ? 1.0f / sum : 0.f;
+    if (lane == 0 && a.lse && i < a.Tq) a.lse[((long long)b * a.H + h) * a.Tq + i] = sum > 0.f ? m + logf(sum) : 0.f;
+  }
+  __syncwarp();
+  float2 o[4] = {};
+  attn_wsum4(sm.S, sp, ii0, sm.Vs, Tk4, a.Tk, o);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ii0 + r;
+    if (i < a.Tq)
+      *reinterpret_cast<uint32_t*>(a.o + ((long long)b * a.Tq + i) * a.ldo + h * 64 + 2 * lane) =
+          pack_bf16x2(o[r].x * inv[r], o[r].y * inv[r]);
   }
 }
 
-// Backward, kernel A: per query tile recompute p, ds = scale * p * (dp - delta); store p / ds for kernels B and C;
+// Backward, kernel A: per query tile recompute p, ds = scale * p * (dp - delta); store p~ / ds for kernels B and C;
 // dq = ds . K + ds . P_shift; per-CTA partial sums of dbias_u / dbias_v.
 __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a) {
   extern __shared__ __align__(16) uint8_t attn_smem_raw[];
   const AttnSmem sm = attn_carve(attn_smem_raw, a.Tk, a.p != nullptr, true);
   const int i0 = blockIdx.x * AQT, h = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sp = attn_spitch(a.Tk), ii0 = warp * 4;
   attn_stage(a, sm, b, h, i0);
   attn_load_q(sm.dO, a.d_o + (long long)b * a.Tq * a.ldo + h * 64, a.ldo, i0, a.Tq, nullptr);
   __syncthreads();
+  if (i0 + ii0 >= a.Tq) return;
   const int klen = a.klen ? min(a.klen[b], a.Tk) : a.Tk;
-  float2 su = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
-  for (int ii = warp; ii < AQT; ii += 8) {
-    const int i = i0 + ii;
-    if (i >= a.Tq) break;
-    attn_scores_row(a, sm, ii, i, klen);
-    __syncwarp();
-    float* S = sm.S + ii * a.Tk;
-    float* S2 = sm.S2 + ii * a.Tk;
-    const float lse = a.lse[((long long)b * a.H + h) * a.Tq + i];
-    // dp[j] = dO_i . v_j
-    for (int j0 = 0; j0 < a.Tk; j0 += 128) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      attn_dot4(sm.dO + ii * 64, sm.Vs, j0, 0, a.Tk, acc);
+  const int Tk4 = (a.Tk + 3) & ~3, nP = a.Tk + AQT - 1, nP4 = (nP + 3) & ~3;
+  attn_scores4(a, sm, ii0, sp);
+  // dp[j] = dO_i . v_j for the 4 rows
+  for (int j0 = 0; j0 < a.Tk; j0 += 128) {
+    float acc[4][4] = {};
+    attn_dot4x4(sm.dO + ii0 * 64, sm.Vs, j0, a.Tk, acc);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + 32 * u + lane;
-        if (j < a.Tk) S2[j] = acc[u];
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      if (j < a.Tk) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sm.S2[(ii0 + r) * sp + j] = acc[r][u];
       }
     }
-    float delta = 0.f;
-    const float ks = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  }
+  __syncwarp();
+  const float ks = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ii0 + r;
+    float* S = sm.S + (ii0 + r) * sp;
+    float* S2 = sm.S2 + (ii0 + r) * sp;
+    const bool row_ok = i < a.Tq;
+    const float lse = row_ok ? a.lse[((long long)b * a.H + h) * a.Tq + i] : 0.f;
     const unsigned long long e0 = (((unsigned long long)b * a.H + h) * a.Tq + i) * a.Tk;
+    float delta = 0.f;
     for (int j = lane; j < a.Tk; j += 32) {
-      const float sj = S[j];
-      const float pj = sj > -INFINITY ? __expf(sj - lse) : 0.f;
+      const bool masked = j >= klen || (a.causal && j > i) || !row_ok;
+      const float pj = masked ? 0.f : __expf(S[j] * a.scale - lse);
       // dropout mask on the probabilities: d p = mask * d p~ ; the key/value side uses p~ = mask * p
       const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
       S[j] = pj;
@@ -698,27 +762,37 @@ __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a
       const float ds = pj * (S2[j] - delta) * a.scale;
       const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
       S2[j] = ds;
-      Pg[j] = pj * mj, DSg[j] = ds;
+      if (row_ok) Pg[j] = pj * mj, DSg[j] = ds;
     }
-    __syncwarp();
-    float2 du = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
-    const uint32_t* K = reinterpret_cast<const uint32_t*>(sm.Ks) + lane;
-    for (int j = 0; j < a.Tk; ++j) {
-      const float ds = S2[j];
-      const float2 kk = unpack_bf16x2(K[(size_t)j * (APITCH / 2)]);
-      du.x = fmaf(ds, kk.x, du.x), du.y = fmaf(ds, kk.y, du.y);
-    }
-    if (a.p) {
-      const uint32_t* P = reinterpret_cast<const uint32_t*>(sm.Ps) + (size_t)(AQT - 1 - ii) * (APITCH / 2) + lane;
-      for (int j = 0; j < a.Tk; ++j) {
-        const float ds = S2[j];
-        const float2 pp = unpack_bf16x2(P[(size_t)j * (APITCH / 2)]);
-        dv.x = fmaf(ds, pp.x, dv.x), dv.y = fmaf(ds, pp.y, dv.y);
+    if (lane < Tk4 - a.Tk) S2[a.Tk + lane] = 0.f;
+  }
+  __syncwarp();
+  float2 du[4] = {}, dv[4] = {};
+  attn_wsum4(sm.S2, sp, ii0, sm.Ks, Tk4, a.Tk, du);
+  if (a.p) {
+    // ds re-indexed by window position: DSs[ii][rl] = ds[ii][rl - (AQT-1-ii)] (zero outside) into the S rows
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int shift = AQT - 1 - (ii0 + r);
+      float* S = sm.S + (ii0 + r) * sp;
+      const float* S2 = sm.S2 + (ii0 + r) * sp;
+      for (int rl = lane; rl < nP4; rl += 32) {
+        const int j = rl - shift;
+        S[rl] = (j >= 0 && j < a.Tk) ? S2[j] : 0.f;
       }
     }
-    *reinterpret_cast<uint32_t*>(a.dq + ((long long)b * a.Tq + i) * a.lddq + h * 64 + 2 * lane) =
-        pack_bf16x2(du.x + dv.x, du.y + dv.y);
-    su.x += du.x, su.y += du.y, sv.x += dv.x, sv.y += dv.y;
+    __syncwarp();
+    attn_wsum4(sm.S, sp, ii0, sm.Ps, nP4, nP, dv);
+  }
+  float2 su = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ii0 + r;
+    if (i < a.Tq) {
+      *reinterpret_cast<uint32_t*>(a.dq + ((long long)b * a.Tq + i) * a.lddq + h * 64 + 2 * lane) =
+          pack_bf16x2(du[r].x + dv[r].x, du[r].y + dv[r].y);
+      su.x += du[r].x, su.y += du[r].y, sv.x += dv[r].x, sv.y += dv[r].y;
+    }
   }
   if (a.dbu) atomicAdd(a.dbu + h * 64 + 2 * lane, su.x), atomicAdd(a.dbu + h * 64 + 2 * lane + 1, su.y);
   if (a.dbv) atomicAdd(a.dbv + h * 64 + 2 * lane, sv.x), atomicAdd(a.dbv + h * 64 + 2 * lane + 1, sv.y);
