@@ -155,6 +155,11 @@ typedef struct svsr_lrw_config {
   float label_smoothing;          /* train.label_smoothing */
   float bn_eps, bn_momentum;      /* torch.nn.BatchNorm defaults 1e-5 / 0.1 */
   float ff_dropout;               /* model.bert.ff_dropout (training only; mask seeded per forward call) */
+  /* model.bert.type: 0 = x-transformers Encoder (lightning.py:95-105), 1 = HuggingFace BertModel(BertConfig(**cfg))
+   * (lightning.py:90-92): dim = hidden_size (512), depth = num_hidden_layers, heads = num_attention_heads (head 64) */
+  int enc_type;
+  int bert_intermediate, bert_max_pos; /* intermediate_size, max_position_embeddings */
+  float bert_ln_eps, bert_hidden_dropout, bert_attn_dropout; /* layer_norm_eps, hidden_dropout_prob, attention_probs_dropout_prob */
 } svsr_lrw_config;
 
 int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle);

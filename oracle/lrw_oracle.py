@@ -158,6 +158,51 @@ def encoder(x: Tensor, P, depth: int, heads: int, q: QFn = None, skip: Optional[
     return x
 
 
+def hf_bert_encoder(x: Tensor, P: Dict[str, Tensor], cfg: dict, train: bool) -> Tensor:
+    """BertModel(BertConfig(**cfg))(inputs_embeds=x, output_hidden_states=True).last_hidden_state with the module's
+    parameters taken from (and sharing autograd with) P["encoder.<name>"]."""
+    from torch.func import functional_call
+    from transformers import BertConfig, BertModel
+
+    m = BertModel(BertConfig(**cfg))
+    m.train(train)
+    params = {k[len("encoder."):]: v for k, v in P.items() if k.startswith("encoder.")}
+    for k, v in m.state_dict().items():  # members forward() never touches (word embeddings, pooler) keep their init
+        params.setdefault(k, v)
+    return functional_call(m, params, kwargs=dict(inputs_embeds=x, output_hidden_states=True)).last_hidden_state
+
+
+def make_hf_params(P: Dict[str, Tensor], cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
+    """Replaces the x-transformers encoder entries of a make_params() dict by seeded BertModel parameters."""
+    g = torch.Generator().manual_seed(seed)
+    D, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
+    out = {k: v for k, v in P.items() if not k.startswith("encoder.")}
+
+    def randn(*shape, std=0.05):
+        return torch.randn(*shape, generator=g) * std
+
+    def ln(prefix):
+        out[prefix + ".weight"] = 1.0 + 0.05 * randn(D, std=1.0)
+        out[prefix + ".bias"] = 0.02 * randn(D, std=1.0)
+
+    e = "encoder.embeddings."
+    out[e + "position_embeddings.weight"] = randn(cfg["max_position_embeddings"], D, std=0.3)
+    out[e + "token_type_embeddings.weight"] = randn(2, D, std=0.3)
+    ln(e + "LayerNorm")
+    for i in range(L):
+        pre = f"encoder.encoder.layer.{i}."
+        for name in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+            out[pre + name + ".weight"] = randn(D, D, std=(3 * D) ** -0.5 * 2)
+            out[pre + name + ".bias"] = 0.02 * randn(D, std=1.0)
+        ln(pre + "attention.output.LayerNorm")
+        out[pre + "intermediate.dense.weight"] = randn(I, D, std=(3 * D) ** -0.5 * 2)
+        out[pre + "intermediate.dense.bias"] = 0.02 * randn(I, std=1.0)
+        out[pre + "output.dense.weight"] = randn(D, I, std=(3 * I) ** -0.5 * 2)
+        out[pre + "output.dense.bias"] = 0.02 * randn(D, std=1.0)
+        ln(pre + "output.LayerNorm")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # audio target indexing (integer, bit-exact): lightning.py:147,170-171 == README.md:47-53
 #   tokens[:, :T*A] -> flatten; row r of logits_audio.reshape(-1, V) is (b, t, c) with c = a*G + g and
@@ -171,7 +216,7 @@ def lrw_forward(P: Dict[str, Tensor], videos: Tensor, audio_tokens: Tensor, labe
                 depth: int = 12, heads: int = 8, audio_alignment: int = 4, vq_groups: int = 2,
                 audio_vocab_size: int = 320, lambda_audio: float = 10.0, label_smoothing: float = 0.0,
                 use_wb: bool = False, train: bool = True, q: QFn = None, skip: Optional[set] = None,
-                cap: Optional[dict] = None):
+                cap: Optional[dict] = None, hf_bert: Optional[dict] = None):
     """lightning.py:133-191. Returns the reference's metric dict plus last_hidden_state / logits and new BN buffers."""
     new_stats: Dict[str, Tensor] = {}
     emb = forward_videos(videos, P, train, new_stats, q, cap)
@@ -180,7 +225,12 @@ def lrw_forward(P: Dict[str, Tensor], videos: Tensor, audio_tokens: Tensor, labe
     B, T, D = emb.shape
     tok = audio_targets(audio_tokens, T, audio_alignment)
     x = torch.cat((P["cls_token"].expand(B, -1, -1), emb), dim=1)
-    last = encoder(x, P, depth, heads, q, skip)
+    if hf_bert is not None:
+        # lightning.py:90-92,152-156 (`type: huggingface`): the encoder IS the third-party transformers.BertModel, which is
+        # importable here, so the oracle runs the library itself on the reference-named parameters ("encoder.*")
+        last = hf_bert_encoder(x, P, hf_bert, train)
+    else:
+        last = encoder(x, P, depth, heads, q, skip)
 
     lq = _q(q, last)
     logits_category = F.linear(lq[:, 0, :], _q(q, P["category_classifier.weight"]), P["category_classifier.bias"]).float()

@@ -371,6 +371,66 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __res
   }
 }
 
+// ---- HuggingFace BERT encoder pieces (lightning.py:90-92,152-156; transformers BertEmbeddings / BertIntermediate) ----
+// h = gelu(pre) (erf form, hidden_act "gelu"), dpre = dh * gelu'(pre); 8 elements per thread
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ h, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(reinterpret_cast<const uint4*>(pre)[i], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = gelu_f(v[k]);
+    reinterpret_cast<uint4*>(h)[i] = pack8(v);
+  }
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dh,
+                __nv_bfloat16* __restrict__ dpre, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8], d[8];
+    unpack8(reinterpret_cast<const uint4*>(pre)[i], v);
+    unpack8(reinterpret_cast<const uint4*>(dh)[i], d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] *= gelu_grad_f(v[k]);
+    reinterpret_cast<uint4*>(dpre)[i] = pack8(d);
+  }
+}
+// E[m,:] = x[m,:] + pos[m % L, :] + tt[0,:]   (inputs_embeds + position_embeddings + token_type_embeddings(0))
+__global__ void bert_embed_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tt,
+                                  float* __restrict__ E, long long M, int L, int D) {
+  const long long total = M * (D / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (D / 4));
+    const long long m = i / (D / 4);
+    const float4 a = reinterpret_cast<const float4*>(x + m * D)[c];
+    const float4 p = reinterpret_cast<const float4*>(pos + (m % L) * D)[c];
+    const float4 t = reinterpret_cast<const float4*>(tt)[c];
+    reinterpret_cast<float4*>(E + m * D)[c] = make_float4(a.x + p.x + t.x, a.y + p.y + t.y, a.z + p.z + t.z, a.w + p.w + t.w);
+  }
+}
+// dpos[l,:] += sum_b dE[b*L + l, :]; dtt[0,:] += sum_m dE[m,:]
+__global__ void bert_embed_bwd_kernel(const float* __restrict__ dE, float* __restrict__ dpos, float* __restrict__ dtt,
+                                      int B, int L, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * D) return;
+  const int l = i / D, d = i % D;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += dE[((long long)b * L + l) * D + d];
+  dpos[i] += s;
+  atomicAdd(dtt + d, s);
+}
+// Dropout on an fp32 tensor in place (+ optional bf16 copy): forward of nn.Dropout after the embedding LayerNorm, and
+// (same call on the gradient) its backward
+__global__ void dropout_f32_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xb, long long n, float p,
+                                   unsigned long long seed) {
+  const float ks = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = dropout_keep(seed, (unsigned long long)i, p) ? x[i] * ks : 0.f;
+    x[i] = v;
+    if (xb) xb[i] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK() \
@@ -450,6 +510,39 @@ int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh
   const long long total = (long long)M * (F / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F, p, seed);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+
+int gelu_fwd(const __nv_bfloat16* pre, __nv_bfloat16* h, long long n, cudaStream_t s) {
+  SVSR_REQUIRE(n % 8 == 0, "gelu: n must be a multiple of 8");
+  const long long n8 = n / 8;
+  gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8), 256, 0, s>>>(pre, h, n8);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int gelu_bwd(const __nv_bfloat16* pre, const __nv_bfloat16* dh, __nv_bfloat16* dpre, long long n, cudaStream_t s) {
+  SVSR_REQUIRE(n % 8 == 0, "gelu: n must be a multiple of 8");
+  const long long n8 = n / 8;
+  gelu_bwd_kernel<<<(unsigned)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8), 256, 0, s>>>(pre, dh, dpre, n8);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bert_embed_fwd(const float* x, const float* pos, const float* tt, float* E, long long M, int L, int D, cudaStream_t s) {
+  SVSR_REQUIRE(D % 4 == 0, "bert_embed: D must be a multiple of 4");
+  const long long total = M * (D / 4);
+  bert_embed_kernel<<<(unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, s>>>(x, pos, tt, E, M, L, D);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int bert_embed_bwd(const float* dE, float* dpos, float* dtt, int B, int L, int D, cudaStream_t s) {
+  bert_embed_bwd_kernel<<<(L * D + 255) / 256, 256, 0, s>>>(dE, dpos, dtt, B, L, D);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int dropout_f32_inplace(float* x, __nv_bfloat16* xb, long long n, float p, unsigned long long seed, cudaStream_t s) {
+  SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
+  dropout_f32_kernel<<<(unsigned)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8), 256, 0, s>>>(x, xb, n, p, seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

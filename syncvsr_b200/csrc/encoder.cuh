@@ -30,4 +30,14 @@ int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, u
 int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, float p,
               unsigned long long seed, cudaStream_t s);
 
+// ---- HuggingFace BERT encoder pieces (`model.bert.type: huggingface`, lightning.py:90-92,152-156) ----
+int gelu_fwd(const __nv_bfloat16* pre, __nv_bfloat16* h, long long n, cudaStream_t s);  // BertIntermediate: erf GELU
+int gelu_bwd(const __nv_bfloat16* pre, const __nv_bfloat16* dh, __nv_bfloat16* dpre, long long n, cudaStream_t s);
+// BertEmbeddings with inputs_embeds: E = x + position_embeddings[arange(L)] + token_type_embeddings[0]; and the
+// gradients of the two tables (dpos[l] += sum over clips, dtt[0] += sum over all tokens)
+int bert_embed_fwd(const float* x, const float* pos, const float* tt, float* E, long long M, int L, int D, cudaStream_t s);
+int bert_embed_bwd(const float* dE, float* dpos, float* dtt, int B, int L, int D, cudaStream_t s);
+// x = dropout(x) in place on fp32 (+ bf16 copy): nn.Dropout after the embedding LayerNorm, and its backward on dx
+int dropout_f32_inplace(float* x, __nv_bfloat16* xb, long long n, float p, unsigned long long seed, cudaStream_t s);
+
 }  // namespace svsr

@@ -4,6 +4,7 @@
 // per-op Python): stem3d -> resnet.layer1-4 -> mean pool + CLS -> x-transformers encoder -> the two loss heads.
 #include "engine_common.cuh"
 #include "encoder.cuh"
+#include "conformer.cuh"
 #include "heads.cuh"
 #include "precise.cuh"
 
@@ -14,6 +15,13 @@ struct EncLayerRef {
   LinRef qkv, out, ff1, ff2;
   size_t xn_a, inv_a, qkvbuf, obuf, xn_f, inv_f, hbuf, ubuf;
   size_t g_a_pad = 0, g_f_pad = 0;  // word-boundary variant: zero-padded fp32 copies of the RMSNorm weights
+};
+
+// `model.bert.type: huggingface` (lightning.py:90-92,152-156): post-LN BERT layer
+struct BertLayerRef {
+  LinRef qkv, out, inter, outd;
+  long long ln1_g, ln1_b, ln2_g, ln2_b;
+  size_t qkvbuf, lse, ctx, A, st1, x1, x1b, pre, h, O, st2;
 };
 
 struct LrwEngine : EngineBase {
@@ -27,6 +35,14 @@ struct LrwEngine : EngineBase {
   bool padded = false;
   size_t dg_pad = 0, bias_tmp = 0;
   const float* word_mask = nullptr;  // device fp32 [B, T] of the current forward (word-boundary variant)
+  // HuggingFace BERT encoder variant
+  std::vector<BertLayerRef> bert;
+  long long b_pos = 0, b_tt = 0, b_eln_g = 0, b_eln_b = 0;
+  size_t b_E = 0, b_est = 0, b_x = 0, b_xb = 0, b_dA = 0, b_g1 = 0, b_g2 = 0, b_gI[2] = {0, 0}, b_dqkv = 0, b_attn = 0;
+  float* bx(int i) const { return ws<float>(b_x) + (size_t)i * M * cfg.dim; }
+  bf16* bxb(int i) const { return ws<bf16>(b_xb) + (size_t)i * M * cfg.dim; }
+  float* last_hidden() const { return cfg.enc_type == 1 ? bx(cfg.depth) : xs_buf(2 * cfg.depth); }
+  unsigned long long bsite(int id) const { return last_seed + 0x632BE59BD9B4E019ULL * (unsigned long long)(id + 1); }
   Frontend fe;  // stem3d + resnet.layer1-4
 
   // model structure
@@ -65,6 +81,7 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
                "lrw: encoder dim must be 512 (or 513 with the word-boundary channel) with 8 heads of 64 (got %d/%d)", c.dim,
                c.heads);
   SVSR_REQUIRE(c.depth >= 1 && c.depth <= 16, "lrw: depth %d out of range", c.depth);
+  SVSR_REQUIRE(c.enc_type == 0 || c.enc_type == 1, "lrw: enc_type %d unknown", c.enc_type);
   SVSR_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f, "lrw: ff_dropout %f out of [0,1)", c.ff_dropout);
   SVSR_REQUIRE(c.T + 1 <= 64, "lrw: sequence length %d too long for the attention core", c.T + 1);
   SVSR_REQUIRE((c.audio_alignment * c.vq_groups * c.audio_vocab) % 64 == 0,
@@ -95,8 +112,57 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
     l.wt = b.take((size_t)l.Kp * l.ldt * 2);
     l.bpad = l.glu ? b.take((size_t)l.Np * 4) : 0;
   };
-  e.enc.resize(c.depth);
-  for (int i = 0; i < c.depth; ++i) {
+  if (c.enc_type == 1) {
+    SVSR_REQUIRE(!e.padded, "lrw: the HuggingFace BERT encoder variant supports hidden_size 512 only");
+    SVSR_REQUIRE(c.bert_intermediate > 0 && c.bert_intermediate % 64 == 0 && c.bert_max_pos >= c.T + 1,
+                 "lrw: bert intermediate_size %d must be a multiple of 64 and max_position_embeddings %d >= %d",
+                 c.bert_intermediate, c.bert_max_pos, c.T + 1);
+    SVSR_REQUIRE(c.bert_hidden_dropout >= 0.f && c.bert_hidden_dropout < 1.f && c.bert_attn_dropout >= 0.f &&
+                     c.bert_attn_dropout < 1.f, "lrw: bert dropout probabilities must be in [0,1)");
+    const int I = c.bert_intermediate;
+    const std::string eb = "encoder.embeddings.";
+    e.b_pos = add_param(e.params, e.pc, eb + "position_embeddings.weight", {c.bert_max_pos, D});
+    e.b_tt = add_param(e.params, e.pc, eb + "token_type_embeddings.weight", {2, D});
+    e.b_eln_g = add_param(e.params, e.pc, eb + "LayerNorm.weight", {D});
+    e.b_eln_b = add_param(e.params, e.pc, eb + "LayerNorm.bias", {D});
+    e.bert.resize(c.depth);
+    for (int i = 0; i < c.depth; ++i) {
+      BertLayerRef& L = e.bert[i];
+      const std::string pre = "encoder.encoder.layer." + std::to_string(i);
+      // query | key | value adjacent: one [3D, D] operand (weights in the decayed region, biases in the other)
+      L.qkv.N = 3 * D, L.qkv.K = D;
+      L.qkv.w = add_param(e.params, e.pc, pre + ".attention.self.query.weight", {D, D});
+      add_param(e.params, e.pc, pre + ".attention.self.key.weight", {D, D});
+      add_param(e.params, e.pc, pre + ".attention.self.value.weight", {D, D});
+      L.qkv.b = add_param(e.params, e.pc, pre + ".attention.self.query.bias", {D});
+      add_param(e.params, e.pc, pre + ".attention.self.key.bias", {D});
+      add_param(e.params, e.pc, pre + ".attention.self.value.bias", {D});
+      L.qkv.ldt = 3 * D, L.qkv.Kp = D, L.qkv.Np = 3 * D;
+      L.qkv.wb = b.take((size_t)3 * D * D * 2), L.qkv.wt = b.take((size_t)D * 3 * D * 2);
+      plin(L.out, pre + ".attention.output.dense.weight", pre + ".attention.output.dense.bias", D, D, false);
+      L.ln1_g = add_param(e.params, e.pc, pre + ".attention.output.LayerNorm.weight", {D});
+      L.ln1_b = add_param(e.params, e.pc, pre + ".attention.output.LayerNorm.bias", {D});
+      plin(L.inter, pre + ".intermediate.dense.weight", pre + ".intermediate.dense.bias", I, D, false);
+      plin(L.outd, pre + ".output.dense.weight", pre + ".output.dense.bias", D, I, false);
+      L.ln2_g = add_param(e.params, e.pc, pre + ".output.LayerNorm.weight", {D});
+      L.ln2_b = add_param(e.params, e.pc, pre + ".output.LayerNorm.bias", {D});
+      L.qkvbuf = b.take((size_t)e.M * 3 * D * 2), L.lse = b.take((size_t)c.B * c.heads * (c.T + 1) * 4);
+      L.ctx = b.take((size_t)e.M * D * 2);
+      L.A = b.take((size_t)e.M * D * 4), L.st1 = b.take((size_t)e.M * 8);
+      L.x1 = b.take((size_t)e.M * D * 4), L.x1b = b.take((size_t)e.M * D * 2);
+      L.pre = b.take((size_t)e.M * I * 2), L.h = b.take((size_t)e.M * I * 2);
+      L.O = b.take((size_t)e.M * D * 4), L.st2 = b.take((size_t)e.M * 8);
+    }
+    e.b_E = b.take((size_t)e.M * D * 4), e.b_est = b.take((size_t)e.M * 8);
+    e.b_x = b.take((size_t)(c.depth + 1) * e.M * D * 4), e.b_xb = b.take((size_t)(c.depth + 1) * e.M * D * 2);
+    e.b_dA = b.take((size_t)e.M * D * 4);
+    e.b_g1 = b.take((size_t)e.M * D * 2), e.b_g2 = b.take((size_t)e.M * D * 2);
+    for (int k = 0; k < 2; ++k) e.b_gI[k] = b.take((size_t)e.M * I * 2);
+    e.b_dqkv = b.take((size_t)e.M * 3 * D * 2);
+    e.b_attn = b.take(attention_scratch_bytes(c.B, c.heads, c.T + 1, c.T + 1));
+  }
+  e.enc.resize(c.enc_type == 1 ? 0 : c.depth);
+  for (int i = 0; i < (int)e.enc.size(); ++i) {
     EncLayerRef& L = e.enc[i];
     const std::string a = "encoder.layers." + std::to_string(2 * i), f = "encoder.layers." + std::to_string(2 * i + 1);
     L.g_a = add_param(e.params, e.pc, a + ".0.g", {D});
@@ -126,10 +192,10 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   // ---- activations ----
   frontend_alloc(e, e.fe, b);
   if (e.padded) {  // the padded weight-gradient scratch of the widest Linear can exceed the largest conv's
-    size_t need = (size_t)e.enc[0].ff1.Np * e.enc[0].ff1.Kp * 4;
+    size_t need = e.enc.empty() ? 0 : (size_t)e.enc[0].ff1.Np * e.enc[0].ff1.Kp * 4;
     if ((size_t)AGV * Dp * 4 > need) need = (size_t)AGV * Dp * 4;
     if (need > (size_t)9 * 512 * 512 * 4) e.wgrad_tmp = b.take(need);
-    e.bias_tmp = b.take((size_t)e.enc[0].ff1.Np * 4);
+    e.bias_tmp = b.take(e.enc.empty() ? 256 : (size_t)e.enc[0].ff1.Np * 4);
     e.dg_pad = b.take((size_t)2 * c.depth * Dp * 4);
   }
   const size_t n0 = (size_t)e.N * e.fe.H0 * e.fe.H0 * 64;
@@ -203,6 +269,7 @@ static int engine_pack(LrwEngine& e, cudaStream_t s) {
         jobs.push_back({e.P + L.g_f, reinterpret_cast<bf16*>(e.ws<float>(L.g_f_pad)), nullptr, 3, e.D, 0, 0, 0});
       }
     }
+    for (auto& L : e.bert) lin(L.qkv), lin(L.out), lin(L.inter), lin(L.outd);
     lin(e.cat), lin(e.aud);
     SVSR_REQUIRE(jobs.size() <= 192, "lrw: too many pack jobs (%zu)", jobs.size());
     e.n_pack_jobs = (int)jobs.size();
@@ -264,6 +331,110 @@ static int lw_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, 
   return SVSR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// HuggingFace BERT encoder variant (BertModel(inputs_embeds=...).last_hidden_state, lightning.py:152-156): embeddings
+// (+ position, + token type 0, LayerNorm, dropout) and post-LN layers (self-attention, GELU FFN). Single stream.
+// ------------------------------------------------------------------------------------------------
+static int blin_fwd(const LrwEngine& e, const bf16* x, int M, const LinRef& l, void* out, int out_fp32, const float* resid,
+                    float drop_p, unsigned long long drop_seed, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = x, p.a_N = M, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wb), p.b_rows = l.N, p.b_cols = l.K;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = l.N;
+  p.bias = e.P + l.b;
+  p.resid = resid, p.resid_fp32 = 1;
+  p.drop_p = drop_p, p.drop_seed = drop_seed;
+  return igemm_launch(p, s);
+}
+static int blin_dgrad(const LrwEngine& e, const bf16* dy, int M, const LinRef& l, void* out, int out_fp32,
+                      const float* resid, cudaStream_t s) {
+  IgemmProblem p;
+  p.a = dy, p.a_N = M, p.a_C = l.N, p.cin = l.ldt, p.ntaps = 1;
+  p.o_N = M;
+  p.b = e.ws<bf16>(l.wt), p.b_rows = l.K, p.b_cols = l.ldt;
+  p.out = out, p.out_fp32 = out_fp32, p.ldc = l.K;
+  p.resid = resid, p.resid_fp32 = 1;
+  return igemm_launch(p, s);
+}
+static int bert_forward(LrwEngine& e, int train, cudaStream_t s) {
+  const svsr_lrw_config& c = e.cfg;
+  const int D = e.D, M = e.M, L1 = c.T + 1, I = c.bert_intermediate;
+  const float pd = train ? c.bert_hidden_dropout : 0.f, pa = train ? c.bert_attn_dropout : 0.f;
+  RC(bert_embed_fwd(e.xs_buf(0), e.P + e.b_pos, e.P + e.b_tt, e.ws<float>(e.b_E), M, L1, D, s));
+  RC(layernorm_fwd(e.ws<float>(e.b_E), e.P + e.b_eln_g, e.P + e.b_eln_b, e.bxb(0), e.bx(0), e.ws<float>(e.b_est), M, D,
+                   c.bert_ln_eps, s));
+  if (pd > 0.f) RC(dropout_f32_inplace(e.bx(0), e.bxb(0), (long long)M * D, pd, e.bsite(1), s));
+  for (int i = 0; i < c.depth; ++i) {
+    BertLayerRef& Lb = e.bert[i];
+    RC(blin_fwd(e, e.bxb(i), M, Lb.qkv, e.ws<bf16>(Lb.qkvbuf), 0, nullptr, 0.f, 0, s));
+    {
+      AttnProblem a;
+      a.q = e.ws<bf16>(Lb.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
+      a.B = c.B, a.H = c.heads, a.Tq = L1, a.Tk = L1, a.scale = 0.125f;
+      a.o = e.ws<bf16>(Lb.ctx), a.ldo = D, a.lse = e.ws<float>(Lb.lse);
+      a.drop_p = pa, a.drop_seed = e.bsite(16 * (i + 1));
+      RC(attention_core_fwd(a, s));
+    }
+    // BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
+    RC(blin_fwd(e, e.ws<bf16>(Lb.ctx), M, Lb.out, e.ws<float>(Lb.A), 1, e.bx(i), pd, e.bsite(16 * (i + 1) + 1), s));
+    RC(layernorm_fwd(e.ws<float>(Lb.A), e.P + Lb.ln1_g, e.P + Lb.ln1_b, e.ws<bf16>(Lb.x1b), e.ws<float>(Lb.x1),
+                     e.ws<float>(Lb.st1), M, D, c.bert_ln_eps, s));
+    // BertIntermediate (erf GELU) + BertOutput: LayerNorm(dropout(dense(h)) + x1)
+    RC(blin_fwd(e, e.ws<bf16>(Lb.x1b), M, Lb.inter, e.ws<bf16>(Lb.pre), 0, nullptr, 0.f, 0, s));
+    RC(gelu_fwd(e.ws<bf16>(Lb.pre), e.ws<bf16>(Lb.h), (long long)M * I, s));
+    RC(blin_fwd(e, e.ws<bf16>(Lb.h), M, Lb.outd, e.ws<float>(Lb.O), 1, e.ws<float>(Lb.x1), pd, e.bsite(16 * (i + 1) + 2), s));
+    RC(layernorm_fwd(e.ws<float>(Lb.O), e.P + Lb.ln2_g, e.P + Lb.ln2_b, e.bxb(i + 1), e.bx(i + 1), e.ws<float>(Lb.st2), M, D,
+                     c.bert_ln_eps, s));
+  }
+  return SVSR_OK;
+}
+// dx (fp32 [M, D]) holds d loss / d last_hidden_state on entry and d loss / d inputs_embeds on exit
+static int bert_backward(LrwEngine& e, float* dx, cudaStream_t s) {
+  const svsr_lrw_config& c = e.cfg;
+  const int D = e.D, M = e.M, L1 = c.T + 1, I = c.bert_intermediate;
+  const float pd = e.last_train ? c.bert_hidden_dropout : 0.f, pa = e.last_train ? c.bert_attn_dropout : 0.f;
+  float* dA = e.ws<float>(e.b_dA);
+  bf16 *g1 = e.ws<bf16>(e.b_g1), *g2 = e.ws<bf16>(e.b_g2), *dh = e.ws<bf16>(e.b_gI[0]), *dpre = e.ws<bf16>(e.b_gI[1]);
+  bf16* dqkv = e.ws<bf16>(e.b_dqkv);
+  for (int i = c.depth - 1; i >= 0; --i) {
+    BertLayerRef& Lb = e.bert[i];
+    // output.LayerNorm -> dO (fp32, in dA); FFN branch gradient = dropout mask * dO
+    RC(layernorm_bwd(nullptr, dx, e.ws<float>(Lb.O), e.P + Lb.ln2_g, e.ws<float>(Lb.st2), dA, 0, e.G + Lb.ln2_g,
+                     e.G + Lb.ln2_b, M, D, s));
+    RC(cast_scale_f32_bf16(dA, g1, (long long)M * D, 1.f, s, pd, e.bsite(16 * (i + 1) + 2)));
+    RC(lw_wgrad(e, g1, D, e.ws<bf16>(Lb.h), I, M, Lb.outd, s));
+    RC(blin_dgrad(e, g1, M, Lb.outd, dh, 0, nullptr, s));
+    RC(gelu_bwd(e.ws<bf16>(Lb.pre), dh, dpre, (long long)M * I, s));
+    RC(lw_wgrad(e, dpre, I, e.ws<bf16>(Lb.x1b), D, M, Lb.inter, s));
+    RC(blin_dgrad(e, dpre, M, Lb.inter, dx, 1, dA, s));  // dx := d x1 = dO (residual) + dpre . W_inter
+    // attention.output.LayerNorm -> dA; attention branch gradient = dropout mask * dA
+    RC(layernorm_bwd(nullptr, dx, e.ws<float>(Lb.A), e.P + Lb.ln1_g, e.ws<float>(Lb.st1), dA, 0, e.G + Lb.ln1_g,
+                     e.G + Lb.ln1_b, M, D, s));
+    RC(cast_scale_f32_bf16(dA, g1, (long long)M * D, 1.f, s, pd, e.bsite(16 * (i + 1) + 1)));
+    RC(lw_wgrad(e, g1, D, e.ws<bf16>(Lb.ctx), D, M, Lb.out, s));
+    RC(blin_dgrad(e, g1, M, Lb.out, g2, 0, nullptr, s));  // g2 = d ctx
+    {
+      AttnProblem a;
+      a.q = e.ws<bf16>(Lb.qkvbuf), a.k = a.q + D, a.v = a.q + 2 * D, a.ldq = a.ldk = a.ldv = 3 * D;
+      a.B = c.B, a.H = c.heads, a.Tq = L1, a.Tk = L1, a.scale = 0.125f;
+      a.o = e.ws<bf16>(Lb.ctx), a.ldo = D, a.lse = e.ws<float>(Lb.lse);
+      a.drop_p = pa, a.drop_seed = e.bsite(16 * (i + 1));
+      AttnGrads g;
+      g.d_o = g2, g.dq = dqkv, g.dk = dqkv + D, g.dv = dqkv + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
+      g.scratch = e.ws<float>(e.b_attn);
+      RC(attention_core_bwd(a, g, s));
+    }
+    RC(lw_wgrad(e, dqkv, 3 * D, e.bxb(i), D, M, Lb.qkv, s));
+    RC(blin_dgrad(e, dqkv, M, Lb.qkv, dx, 1, dA, s));  // dx := d x_i = dA (residual) + dqkv . W_qkv
+  }
+  // embeddings: dropout, LayerNorm, the two learned tables
+  if (pd > 0.f) RC(dropout_f32_inplace(dx, nullptr, (long long)M * D, pd, e.bsite(1), s));
+  RC(layernorm_bwd(nullptr, dx, e.ws<float>(e.b_E), e.P + e.b_eln_g, e.ws<float>(e.b_est), dx, 0, e.G + e.b_eln_g,
+                   e.G + e.b_eln_b, M, D, s));
+  return bert_embed_bwd(dx, e.G + e.b_pos, e.G + e.b_tt, c.B, L1, D, s);
+}
+
 static int engine_forward(LrwEngine& e, const float* videos, const long long* tokens, long long tok_stride_b,
                           const long long* labels, const float* soft_labels, int train, uint32_t skip_mask,
                           unsigned long long dropout_seed, float* metrics, int videos_only, cudaStream_t s) {
@@ -282,8 +453,10 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     RC(wb_column(e.xs_buf(0), e.P + e.cls_off, e.word_mask, c.B, c.T, Dp, 512, s));
   }
 
-  // ---- encoder (lightning.py:158) ----
-  for (int i = 0; i < c.depth; ++i) {
+  // ---- encoder (lightning.py:152-158) ----
+  e.last_seed = dropout_seed;
+  if (c.enc_type == 1) RC(bert_forward(e, train, s));
+  for (int i = 0; i < (int)e.enc.size(); ++i) {
     EncLayerRef& L = e.enc[i];
     float* xa = e.xs_buf(2 * i);
     float* xf = e.xs_buf(2 * i + 1);
@@ -309,7 +482,7 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
       RC(lw_fwd(e, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, xo, Dp, 1, xf, s));
     }
   }
-  const float* last = e.xs_buf(2 * c.depth);
+  const float* last = e.last_hidden();
   RC(split_cast_last(last, e.ws<bf16>(e.lastb_cls), e.ws<bf16>(e.lastb_frames), c.B, c.T, Dp, s));
 
   // ---- heads + losses (lightning.py:161-174) ----
@@ -378,7 +551,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
                                   long long tok_stride_b, const long long* labels, const float* soft_labels, int train,
                                   uint32_t skip_mask, float* metrics, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
-  SVSR_REQUIRE(!e.padded, "lrw: the parity-mode forward supports dim 512 only");
+  SVSR_REQUIRE(!e.padded && c.enc_type == 0, "lrw: the parity-mode forward supports the dim-512 x-transformers config only");
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.fe.stats_arena), 0, e.fe.stats_arena_bytes, s));
@@ -511,8 +684,14 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   RC(cast_f32_to_bf16(dx, e.ws<bf16>(e.dxb[xb]), (long long)e.M * Dp, s));
   RC(sq.end_unit());
 
+  if (c.enc_type == 1) {  // HuggingFace BERT variant: single stream (weight gradients included)
+    RC(sq.join());
+    e.wq = s;
+    RC(bert_backward(e, dx, s));
+    e.wq = sq.w0;
+  }
   // ---- encoder, reversed: one unit per sublayer ----
-  for (int i = c.depth - 1; i >= 0; --i) {
+  for (int i = (int)e.enc.size() - 1; i >= 0; --i) {
     EncLayerRef& L = e.enc[i];
     const float* g_a = e.padded ? e.ws<float>(L.g_a_pad) : e.P + L.g_a;
     const float* g_f = e.padded ? e.ws<float>(L.g_f_pad) : e.P + L.g_f;
@@ -555,7 +734,7 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     }
   }
   if (e.padded)  // RMSNorm weight gradients: padded scratch -> arena
-    for (int i = 0; i < c.depth; ++i) {
+    for (int i = 0; i < (int)e.enc.size(); ++i) {
       RC(unpack_linear_wgrad(e.ws<float>(e.dg_pad) + (size_t)(2 * i) * Dp, e.G + e.enc[i].g_a, D, 1, 1, 0, s));
       RC(unpack_linear_wgrad(e.ws<float>(e.dg_pad) + (size_t)(2 * i + 1) * Dp, e.G + e.enc[i].g_f, D, 1, 1, 0, s));
     }
@@ -690,7 +869,7 @@ int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* 
     return SVSR_OK;
   };
   if (n == "last_hidden_state") {
-    *ptr = e->xs_buf(2 * c.depth), *numel = (int64_t)e->M * e->Dp, *dtype = 0;  // row pitch Dp = ceil64(dim)
+    *ptr = e->last_hidden(), *numel = (int64_t)e->M * e->Dp, *dtype = 0;  // row pitch Dp = ceil64(dim)
     return SVSR_OK;
   }
   if (n == "inputs_embeds") {

@@ -282,9 +282,10 @@ struct SideQueue {
   cudaStream_t s;
   int unit = 0;
   int rc = SVSR_OK;
+  cudaStream_t w0;  // the weight-gradient stream chosen for this backward
   SideQueue(EngineBase& e_, cudaStream_t s_) : e(e_), s(s_) {
     const char* one = getenv("SVSR_SINGLE_STREAM");
-    e.wq = (one && one[0] == '1') ? s_ : e_.side;
+    e.wq = w0 = (one && one[0] == '1') ? s_ : e_.side;
   }
   // everything enqueued on `s` so far becomes visible to the side stream
   int fork() {

@@ -29,6 +29,8 @@ class LrwConfig(C.Structure):
         ("num_labels", C.c_int), ("rotary_v", C.c_int),
         ("lambda_audio", C.c_float), ("label_smoothing", C.c_float),
         ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("ff_dropout", C.c_float),
+        ("enc_type", C.c_int), ("bert_intermediate", C.c_int), ("bert_max_pos", C.c_int),
+        ("bert_ln_eps", C.c_float), ("bert_hidden_dropout", C.c_float), ("bert_attn_dropout", C.c_float),
     ]
 
 
@@ -76,8 +78,9 @@ class TransformerLightningModule(nn.Module):
         self.lambda_audio = float(_cfg_get(config, "optim.lambda_audio", 10.0))
         self.label_smoothing = float(_cfg_get(config, "train.label_smoothing", 0.0))
         self.use_wb = bool(_cfg_get(config, "data.use_word_boundary", False))
-        if _cfg_get(config, "model.bert.type", "x-transformers") != "x-transformers":
-            raise SvsrError("only model.bert.type == 'x-transformers' is implemented natively")
+        self.encoder_type = str(_cfg_get(config, "model.bert.type", "x-transformers"))
+        if self.encoder_type not in ("x-transformers", "huggingface"):
+            raise SvsrError(f"model.bert.type={self.encoder_type!r}: only 'x-transformers' and 'huggingface' exist")
 
         # codec constants: explicit keys win, else derived from the codec path exactly like lightning.py:58-67
         path = str(_cfg_get(config, "model.wav2vec.path", "vq"))
@@ -92,12 +95,34 @@ class TransformerLightningModule(nn.Module):
         self.audio_vocab_size = int(_cfg_get(config, "model.audio_vocab_size", v))
         # lightning.py:46-47: the word-boundary indicator becomes one extra hidden channel (dim 513)
         self.dim = int(_cfg_get(config, "model.bert.dim", 512)) + (1 if self.use_wb else 0)
+        self.hf: Dict[str, Any] = {}
+        if self.encoder_type == "huggingface":
+            # lightning.py:90-92: BertModel(BertConfig(**config.model.bert)); BertConfig defaults apply to absent keys
+            g = lambda k, d: _cfg_get(config, f"model.bert.{k}", d)  # noqa: E731
+            self.hf = dict(hidden_size=int(g("hidden_size", 768)), num_hidden_layers=int(g("num_hidden_layers", 12)),
+                           num_attention_heads=int(g("num_attention_heads", 12)),
+                           intermediate_size=int(g("intermediate_size", 3072)), vocab_size=int(g("vocab_size", 30522)),
+                           max_position_embeddings=int(g("max_position_embeddings", 512)),
+                           layer_norm_eps=float(g("layer_norm_eps", 1e-12)),
+                           hidden_dropout_prob=float(g("hidden_dropout_prob", 0.1)),
+                           attention_probs_dropout_prob=float(g("attention_probs_dropout_prob", 0.1)),
+                           hidden_act=str(g("hidden_act", "gelu")), type_vocab_size=int(g("type_vocab_size", 2)))
+            if self.use_wb or self.hf["hidden_size"] != 512 or self.hf["hidden_size"] != 64 * self.hf["num_attention_heads"]:
+                raise SvsrError("huggingface encoder: hidden_size must be 512 (the trunk's width, no word boundary) with "
+                                "heads of 64; other BertConfig geometries cannot consume forward_videos() either")
+            if self.hf["hidden_act"] != "gelu" or self.hf["type_vocab_size"] != 2:
+                raise SvsrError("huggingface encoder: only hidden_act='gelu' and type_vocab_size=2 are native")
+            self.dim = 512
         self._dim_pitch = (self.dim + 63) // 64 * 64  # row pitch of the engine's dim-wide tensors
         self.depth = int(_cfg_get(config, "model.bert.depth", 12))
         self.heads = int(_cfg_get(config, "model.bert.heads", 8))
+        if self.hf:
+            self.depth, self.heads = self.hf["num_hidden_layers"], self.hf["num_attention_heads"]
         self.layer_dropout = float(_cfg_get(config, "model.bert.layer_dropout", 0.0))
         self.ff_dropout = float(_cfg_get(config, "model.bert.ff_dropout", 0.0))
         for key in ("emb_dropout", "attn_dropout"):
+            if self.hf and key == "attn_dropout":
+                continue  # an x-transformers key; BertConfig ignores it
             if float(_cfg_get(config, f"model.bert.{key}", 0.0)) != 0.0:
                 # element-wise dropouts are not wired into the native kernels yet; refuse silently-different maths
                 raise SvsrError(f"model.bert.{key} > 0 is not supported by the native path yet (set it to 0)")
@@ -121,6 +146,11 @@ class TransformerLightningModule(nn.Module):
 
         # parameters the reference's state dict carries but never uses on this path (lightning.py:55 creates the full
         # timm resnet18; only .layer1-4 run): kept for checkpoint compatibility, never receive gradients.
+        if self.hf:  # BertModel members that forward(inputs_embeds=...).last_hidden_state never touches
+            emb = self.encoder._modules["embeddings"]
+            emb.word_embeddings = nn.Embedding(self.hf["vocab_size"], 512, padding_idx=0).to(self.device_)
+            self.encoder.pooler = _Node()
+            self.encoder.pooler.dense = nn.Linear(512, 512).to(self.device_)
         rn = self.resnet
         rn.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         rn.bn1 = nn.BatchNorm2d(64)
@@ -132,9 +162,13 @@ class TransformerLightningModule(nn.Module):
     # engine / arena management
     # ------------------------------------------------------------------------------------------------------------
     def _engine_cfg(self, B, T, H, W) -> LrwConfig:
+        hf = self.hf
         return LrwConfig(B, T, H, W, self.dim, self.depth, self.heads, self.audio_alignment, self.vq_groups,
                          self.audio_vocab_size, self.word_labels, int(self.rotary_v), self.lambda_audio,
-                         self.label_smoothing, 1e-5, 0.1, self.ff_dropout)
+                         self.label_smoothing, 1e-5, 0.1, self.ff_dropout, 1 if hf else 0,
+                         hf.get("intermediate_size", 0), hf.get("max_position_embeddings", 0),
+                         hf.get("layer_norm_eps", 1e-12), hf.get("hidden_dropout_prob", 0.0),
+                         hf.get("attention_probs_dropout_prob", 0.0))
 
     def _build_engine(self, B, T, H, W, first=False):
         L = lib()
@@ -205,6 +239,14 @@ class TransformerLightningModule(nn.Module):
         import math
 
         shp = view.shape
+        if key.startswith(("encoder.embeddings.", "encoder.encoder.layer.")):  # BertPreTrainedModel._init_weights
+            if "LayerNorm" in key:
+                view.fill_(1.0) if key.endswith("weight") else view.zero_()
+            elif key.endswith("bias"):
+                view.zero_()
+            else:
+                view.copy_(torch.randn(shp, generator=gen) * 0.02)
+            return
         is_bn = ".bn" in key or "stem3d.1" in key or "downsample.1" in key
         if key.endswith(".g") or (is_bn and key.endswith("weight")):
             view.fill_(1.0)
@@ -326,7 +368,7 @@ class TransformerLightningModule(nn.Module):
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
             C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_void_p(wm.data_ptr() if wm is not None else 0),
             C.c_int(int(self.training)), C.c_uint32(skip),
-            C.c_uint64(random.getrandbits(63) if (self.training and self.ff_dropout > 0) else 0),
+            C.c_uint64(random.getrandbits(63) if (self.training and (self.ff_dropout > 0 or self.hf)) else 0),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         if self.training:
             self._nbt += 1
@@ -341,8 +383,8 @@ class TransformerLightningModule(nn.Module):
                         word_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Parity-mode forward (fp32 activations, split-bf16 tensor-core operands; csrc/precise.cuh): same outputs as
         forward() at fp32-class accuracy. Forward only; `last_hidden_state()` / `logits_audio()` read its results."""
-        if self.use_wb:
-            raise SvsrError("forward_precise (parity mode) supports the dim-512 (no word boundary) configuration only")
+        if self.use_wb or self.hf:
+            raise SvsrError("forward_precise (parity mode) supports the dim-512 x-transformers configuration only")
         videos = videos.to(self.device_, torch.float32).contiguous()
         audio_tokens = audio_tokens.to(self.device_, torch.long).contiguous()
         labels = labels.to(self.device_)

@@ -355,3 +355,61 @@ def test_two_stream_backward_equals_single_stream_full_batch(Module, monkeypatch
         torch.cuda.synchronize()
         grads.append(m.flat_grads.clone())
     assert rel(grads[0], grads[1]) < 1e-4 and rel(grads[2], grads[1]) < 1e-4
+
+
+def test_huggingface_bert_encoder_variant(Module, golden_dir):
+    """`model.bert.type: huggingface` (lightning.py:90-92,152-156): the encoder is transformers.BertModel. Forward is
+    checked against the reference module's own outputs (golden), gradients against the oracle, which runs the
+    transformers library itself on the same reference-named parameters."""
+    fx = torch.load(golden_dir / "lrw_hf_d2.pt")
+    meta, hf = fx["meta"], fx["meta"]["hf"]
+    cfg = make_cfg(depth=meta["depth"])
+    cfg["model"]["bert"]["type"] = "huggingface"
+    for k, v in hf.items():
+        cfg["model"]["bert"][k] = v
+    m = Module(cfg).train()
+    P = O.make_hf_params(O.make_params(meta["seed_p"], depth=meta["depth"]), hf, seed=meta["seed_p"] + 100)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all(("num_batches_tracked" in k) or k.startswith(("resnet.conv1", "resnet.bn1", "resnet.fc", "encoder.pooler",
+                                                             "encoder.embeddings.word_embeddings")) for k in missing), missing
+    videos, tokens, labels, wm = O.make_inputs(meta["seed_x"], meta["B"])
+    out = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    g = fx["metrics"]
+    assert float(out["loss_total"]) == pytest.approx(g["loss_total"], rel=1e-3)
+    assert float(out["loss_audio"]) == pytest.approx(g["loss_audio"], rel=1e-3)
+    assert float(out["loss_category"]) == pytest.approx(g["loss_category"], rel=2e-3)
+    last = m.last_hidden_state().cpu()
+    assert rel(last[:, 0, :], fx["last_hidden_state_cls"]) < 5e-2 and rel(last[:, 7, :], fx["last_hidden_state_t7"]) < 5e-2
+    assert rel(m.logits_category().cpu(), fx["logits_category"]) < 5e-2
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = O.lrw_forward(Pq, videos, tokens, labels, wm, depth=meta["depth"], hf_bert=hf, q=O.bf16_ste)
+    out["loss_total"].backward()
+    o["loss_total"].backward()
+    bad = []
+    for k, p in m._param_views.items():
+        ref = Pq[k].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if ref is None or float(ref.norm()) < 1e-6:
+            continue
+        if k.startswith(("encoder", "audio_projection", "category_classifier", "cls_token")):
+            if rel(p.grad, ref) > 5e-2:
+                bad.append((k, round(rel(p.grad, ref), 4)))
+    assert not bad, bad
+    assert rel(m._param_views["encoder.encoder.layer.0.attention.output.LayerNorm.weight"].grad.cpu(), fx["grad_enc0_g"]) < 5e-2
+    # BertConfig's default dropouts (0.1) in training mode: stochastic, finite, eval mode deterministic
+    cfg["model"]["bert"]["hidden_dropout_prob"] = 0.1
+    cfg["model"]["bert"]["attention_probs_dropout_prob"] = 0.1
+    md = Module(cfg).train()
+    md.load_state_dict(P, strict=False)
+    v, t, l, w = videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda()
+    losses = []
+    for _ in range(3):
+        od = md(v, t, l, w)
+        od["loss_total"].backward()
+        losses.append(float(od["loss_total"]))
+        assert torch.isfinite(md.flat_grads).all()
+    assert len(set(losses)) > 1 and all(abs(x - g["loss_total"]) / g["loss_total"] < 0.15 for x in losses)
+    md.eval()
+    with torch.no_grad():
+        assert float(md(v, t, l, w)["loss_total"]) == float(md(v, t, l, w)["loss_total"])
