@@ -160,6 +160,7 @@ typedef struct svsr_lrw_config {
   int enc_type;
   int bert_intermediate, bert_max_pos; /* intermediate_size, max_position_embeddings */
   float bert_ln_eps, bert_hidden_dropout, bert_attn_dropout; /* layer_norm_eps, hidden_dropout_prob, attention_probs_dropout_prob */
+  float emb_dropout, attn_dropout; /* model.bert.emb_dropout (lightning.py:106,150), model.bert.attn_dropout (x-transformers) */
 } svsr_lrw_config;
 
 int svsr_lrw_create(const svsr_lrw_config* cfg, void** handle);

@@ -215,9 +215,22 @@ __device__ __forceinline__ void mm_tile_2x8(const float* Lm, const float* R, int
   }
 }
 
+// p[i][j] *= keep / (1 - p_drop) (and, if `other` is given, the same mask applied to other[i][j]: dP in backward)
+__device__ __forceinline__ void dropout_probs(float* sp, float* other, int n, unsigned long long base, float p,
+                                              unsigned long long seed) {
+  const float ks = 1.0f / (1.0f - p);
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t - i * n;
+    const float m = dropout_keep(seed, base + (unsigned long long)t, p) ? ks : 0.f;
+    sp[i * AT_LD + j] *= m;
+    if (other) other[i * AT_LD + j] *= m;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
-                     __nv_bfloat16* __restrict__ o, int n, int heads, int rotary_v) {
+                     __nv_bfloat16* __restrict__ o, int n, int heads, int rotary_v, float drop_p,
+                     unsigned long long drop_seed) {
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + n * AT_LD;
@@ -233,6 +246,10 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   __syncthreads();
   softmax_rows(sp, n);
   __syncthreads();
+  if (drop_p > 0.f) {  // Attention(dropout=attn_dropout): mask on the probabilities, index ((b*H+h)*n + i)*n + j
+    dropout_probs(sp, nullptr, n, (unsigned long long)blockIdx.x * n * n, drop_p, drop_seed);
+    __syncthreads();
+  }
   const int nrp = (n + 1) >> 1;
   for (int t = threadIdx.x; t < nrp * 8; t += blockDim.x) {
     const int rp = t >> 3, cq = t & 7;
@@ -252,7 +269,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 __global__ void __launch_bounds__(128)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
                      const __nv_bfloat16* __restrict__ d_o, __nv_bfloat16* __restrict__ dqkv, int n, int heads,
-                     int rotary_v) {
+                     int rotary_v, float drop_p, unsigned long long drop_seed) {
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + n * AT_LD;
@@ -277,9 +294,17 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
     for (int r = warp; r < n; r += nw) {
       const float pa = lane < n ? sp[r * AT_LD + lane] : 0.f, pb = lane + 32 < n ? sp[r * AT_LD + lane + 32] : 0.f;
       const float da = lane < n ? sds[r * AT_LD + lane] : 0.f, db = lane + 32 < n ? sds[r * AT_LD + lane + 32] : 0.f;
-      const float dot = warp_sum(pa * da + pb * db);
-      if (lane < n) sds[r * AT_LD + lane] = pa * (da - dot);
-      if (lane + 32 < n) sds[r * AT_LD + lane + 32] = pb * (db - dot);
+      float ma = 1.f, mb = 1.f;
+      if (drop_p > 0.f) {  // d p = mask * d p~ ; dV below uses p~ = mask * p
+        const float ks = 1.0f / (1.0f - drop_p);
+        const unsigned long long base = ((unsigned long long)blockIdx.x * n + r) * n;
+        ma = (lane < n && dropout_keep(drop_seed, base + lane, drop_p)) ? ks : 0.f;
+        mb = (lane + 32 < n && dropout_keep(drop_seed, base + lane + 32, drop_p)) ? ks : 0.f;
+      }
+      const float dam = da * ma, dbm = db * mb;
+      const float dot = warp_sum(pa * dam + pb * dbm);
+      if (lane < n) sds[r * AT_LD + lane] = pa * (dam - dot), sp[r * AT_LD + lane] = pa * ma;
+      if (lane + 32 < n) sds[r * AT_LD + lane + 32] = pb * (dbm - dot), sp[r * AT_LD + lane + 32] = pb * mb;
     }
   }
   __syncthreads();
@@ -469,7 +494,7 @@ int rotary_table(float* tab, int n, cudaStream_t s) {
   return SVSR_OK;
 }
 int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
-                  int rotary_v, cudaStream_t s) {
+                  int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
   const int smem = 4 * n * AT_LD * sizeof(float);
   const int smem_max = 4 * AT_MAXN * AT_LD * sizeof(float);
@@ -478,12 +503,12 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
     SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
-  attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v);
+  attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v, drop_p, drop_seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
-                  int n, int heads, int rotary_v, cudaStream_t s) {
+                  int n, int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
   const int smem = 6 * n * AT_LD * sizeof(float);
   const int smem_max = 6 * AT_MAXN * AT_LD * sizeof(float);
@@ -492,7 +517,7 @@ int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat1
     SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
-  attention_bwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v);
+  attention_bwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v, drop_p, drop_seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

@@ -19,10 +19,11 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const f
 int rotary_table(float* tab, int n, cudaStream_t s);
 
 // qkv [B*n, 3*heads*64] bf16 (q | k | v) -> o [B*n, heads*64] bf16; rotary on the first 32 dims of q, k and v
+// drop_p: Attention(dropout=attn_dropout) on the softmax probabilities (counter-based mask, regenerated in backward)
 int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
-                  int rotary_v, cudaStream_t s);
+                  int rotary_v, cudaStream_t s, float drop_p = 0.f, unsigned long long drop_seed = 0);
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
-                  int n, int heads, int rotary_v, cudaStream_t s);
+                  int n, int heads, int rotary_v, cudaStream_t s, float drop_p = 0.f, unsigned long long drop_seed = 0);
 
 // u[M,F] = dropout_p(h[:, :F] * gelu(h[:, F:])) ; dh from du. The dropout mask is a counter-based function of
 // (seed, element index): forward and backward regenerate the same mask, nothing is stored. p = 0 disables it.

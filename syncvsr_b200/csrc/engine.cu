@@ -83,6 +83,8 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   SVSR_REQUIRE(c.depth >= 1 && c.depth <= 16, "lrw: depth %d out of range", c.depth);
   SVSR_REQUIRE(c.enc_type == 0 || c.enc_type == 1, "lrw: enc_type %d unknown", c.enc_type);
   SVSR_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f, "lrw: ff_dropout %f out of [0,1)", c.ff_dropout);
+  SVSR_REQUIRE(c.emb_dropout >= 0.f && c.emb_dropout < 1.f && c.attn_dropout >= 0.f && c.attn_dropout < 1.f,
+               "lrw: emb_dropout / attn_dropout out of [0,1)");
   SVSR_REQUIRE(c.T + 1 <= 64, "lrw: sequence length %d too long for the attention core", c.T + 1);
   SVSR_REQUIRE((c.audio_alignment * c.vq_groups * c.audio_vocab) % 64 == 0,
                "lrw: audio logits per frame (%d) must be a multiple of 64",
@@ -453,6 +455,9 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     RC(wb_column(e.xs_buf(0), e.P + e.cls_off, e.word_mask, c.B, c.T, Dp, 512, s));
   }
 
+  // emb_dropout_bert on cat(cls_tokens, inputs_embeds) (lightning.py:150)
+  if (train && c.emb_dropout > 0.f)
+    RC(dropout_f32_inplace(e.xs_buf(0), nullptr, (long long)e.M * Dp, c.emb_dropout, dropout_seed + 0x3000ULL, s));
   // ---- encoder (lightning.py:152-158) ----
   e.last_seed = dropout_seed;
   if (c.enc_type == 1) RC(bert_forward(e, train, s));
@@ -469,7 +474,7 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
       RC(rmsnorm_fwd(xa, g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, Dp, 1e-8f, s, D));
       RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s));
       RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
-                       s));
+                       s, train ? c.attn_dropout : 0.f, dropout_seed + 0x2000ULL * (unsigned long long)(i + 1)));
       RC(lw_fwd(e, e.ws<bf16>(L.obuf), inner, e.M, L.out, xf, Dp, 1, xa, s));
     }
     if (skip_mask & (1u << (2 * i + 1))) {
@@ -724,7 +729,8 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
       RC(sq.fork());
       RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.obuf), inner, e.M, L.out, w));
       RC(lw_dgrad(e, dxb, Dp, e.M, L.out, d_o, inner, s));
-      RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s));
+      RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s,
+                       e.last_train ? c.attn_dropout : 0.f, e.last_seed + 0x2000ULL * (unsigned long long)(i + 1)));
       RC(sq.fork());
       RC(lw_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, w));
       RC(lw_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, Dp, s));
@@ -739,7 +745,9 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
       RC(unpack_linear_wgrad(e.ws<float>(e.dg_pad) + (size_t)(2 * i + 1) * Dp, e.G + e.enc[i].g_f, D, 1, 1, 0, s));
     }
 
-  // ---- mean pool / CLS ----
+  // ---- emb_dropout, mean pool / CLS ----
+  if (e.last_train && c.emb_dropout > 0.f)
+    RC(dropout_f32_inplace(dx, nullptr, (long long)e.M * Dp, c.emb_dropout, e.last_seed + 0x3000ULL, s));
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, 512, s, Dp));
   if (e.padded) RC(wb_column_bwd(dx, e.G + e.cls_off, c.B, c.T, Dp, 512, s));

@@ -31,6 +31,7 @@ class LrwConfig(C.Structure):
         ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("ff_dropout", C.c_float),
         ("enc_type", C.c_int), ("bert_intermediate", C.c_int), ("bert_max_pos", C.c_int),
         ("bert_ln_eps", C.c_float), ("bert_hidden_dropout", C.c_float), ("bert_attn_dropout", C.c_float),
+        ("emb_dropout", C.c_float), ("attn_dropout", C.c_float),
     ]
 
 
@@ -120,12 +121,10 @@ class TransformerLightningModule(nn.Module):
             self.depth, self.heads = self.hf["num_hidden_layers"], self.hf["num_attention_heads"]
         self.layer_dropout = float(_cfg_get(config, "model.bert.layer_dropout", 0.0))
         self.ff_dropout = float(_cfg_get(config, "model.bert.ff_dropout", 0.0))
-        for key in ("emb_dropout", "attn_dropout"):
-            if self.hf and key == "attn_dropout":
-                continue  # an x-transformers key; BertConfig ignores it
-            if float(_cfg_get(config, f"model.bert.{key}", 0.0)) != 0.0:
-                # element-wise dropouts are not wired into the native kernels yet; refuse silently-different maths
-                raise SvsrError(f"model.bert.{key} > 0 is not supported by the native path yet (set it to 0)")
+        # Dropout(emb_dropout) on cat(cls, inputs_embeds) (lightning.py:106,150) and x-transformers' attn_dropout on the
+        # attention probabilities: both 0.0 in the shipped yamls, honoured in training mode when set
+        self.emb_dropout = float(_cfg_get(config, "model.bert.emb_dropout", 0.0))
+        self.attn_dropout = 0.0 if self.hf else float(_cfg_get(config, "model.bert.attn_dropout", 0.0))
         self.rotary_v = bool(_cfg_get(config, "model.bert.rotary_v", True))
 
         self._h = C.c_void_p()
@@ -168,7 +167,7 @@ class TransformerLightningModule(nn.Module):
                          self.label_smoothing, 1e-5, 0.1, self.ff_dropout, 1 if hf else 0,
                          hf.get("intermediate_size", 0), hf.get("max_position_embeddings", 0),
                          hf.get("layer_norm_eps", 1e-12), hf.get("hidden_dropout_prob", 0.0),
-                         hf.get("attention_probs_dropout_prob", 0.0))
+                         hf.get("attention_probs_dropout_prob", 0.0), self.emb_dropout, self.attn_dropout)
 
     def _build_engine(self, B, T, H, W, first=False):
         L = lib()
@@ -368,7 +367,7 @@ class TransformerLightningModule(nn.Module):
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
             C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_void_p(wm.data_ptr() if wm is not None else 0),
             C.c_int(int(self.training)), C.c_uint32(skip),
-            C.c_uint64(random.getrandbits(63) if (self.training and (self.ff_dropout > 0 or self.hf)) else 0),
+            C.c_uint64(self._step_seed()),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         if self.training:
             self._nbt += 1
@@ -377,6 +376,13 @@ class TransformerLightningModule(nn.Module):
             m = _StepFunction.apply(self._anchor, self, self._metrics)
         return {"loss_total": m[0], "loss_category": m[1], "loss_audio": m[2], "accuracy_top1": m[3],
                 "accuracy_top5": m[4]}
+
+    def _step_seed(self) -> int:
+        """Seed of this step's dropout masks (training mode only); `self.dropout_seed` pins it for reproducible tests."""
+        if not self.training or not (self.ff_dropout > 0 or self.hf or self.emb_dropout > 0 or self.attn_dropout > 0):
+            return 0
+        fixed = getattr(self, "dropout_seed", None)
+        return fixed if fixed is not None else random.getrandbits(63)
 
     @torch.no_grad()
     def forward_precise(self, videos: torch.Tensor, audio_tokens: torch.Tensor, labels: torch.Tensor,

@@ -413,3 +413,43 @@ def test_huggingface_bert_encoder_variant(Module, golden_dir):
     md.eval()
     with torch.no_grad():
         assert float(md(v, t, l, w)["loss_total"]) == float(md(v, t, l, w)["loss_total"])
+
+
+def test_all_x_transformers_dropouts_are_consistent_between_forward_and_backward(Module):
+    """emb_dropout (lightning.py:106,150), attn_dropout and ff_dropout together: masks are regenerated (never stored) in
+    backward, so with a pinned seed the analytic gradient must predict the loss change along its own direction."""
+    meta = dict(B=3, S=88, A=4, G=2, V=320, depth=2, seed_p=21, seed_x=91, extra_tokens=0)
+    cfg = make_cfg(depth=2, ff_dropout=0.2)
+    cfg["model"]["bert"]["emb_dropout"] = 0.1
+    cfg["model"]["bert"]["attn_dropout"] = 0.1
+    m = Module(cfg).train()
+    P = O.make_params(meta["seed_p"], depth=2)
+    m.load_state_dict(P, strict=False)
+    v, t, l, w = (x.cuda() for x in O.make_inputs(meta["seed_x"], meta["B"]))
+    base = float(O.lrw_forward(P, v.cpu(), t.cpu(), l.cpu(), w.cpu(), depth=2)["loss_total"])
+    m.dropout_seed = 4242
+    out = m(v, t, l, w)
+    out["loss_total"].backward()
+    g = m.flat_grads.clone()
+    l1 = float(out["loss_total"])
+    m.flat_grads.zero_()
+    assert float(m(v, t, l, w)["loss_total"]) == l1  # same seed, same masks
+    m.dropout_seed = 4243
+    assert float(m(v, t, l, w)["loss_total"]) != l1
+    assert abs(l1 - base) / base < 0.2 and torch.isfinite(g).all()
+    m.dropout_seed = 4242
+    theta = m.flat_params.clone()
+    gn = float(g.norm())
+    h = 0.5 / gn
+    with torch.no_grad():
+        vals = []
+        for sgn in (1.0, -1.0):
+            m.flat_params.copy_(theta + sgn * h * g / gn)
+            m.mark_weights_updated()
+            vals.append(float(m(v, t, l, w)["loss_total"]))
+        m.flat_params.copy_(theta)
+        m.mark_weights_updated()
+    assert (vals[0] - vals[1]) == pytest.approx(2 * h * gn, rel=0.2), (vals, gn)
+    m.eval()
+    with torch.no_grad():
+        assert float(m(v, t, l, w)["loss_total"]) == float(m(v, t, l, w)["loss_total"])
