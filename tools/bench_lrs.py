@@ -5,6 +5,7 @@ resident in HBM, CUDA-event timing. Prints one JSON line (a developer tool: the 
 import argparse
 import ctypes as C
 import json
+import os
 import sys
 from pathlib import Path
 from types import SimpleNamespace
@@ -15,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from syncvsr_b200._lib import check, lib  # noqa: E402
 from syncvsr_b200.e2e import E2E  # noqa: E402
-from syncvsr_b200.train import FusedAdamW  # noqa: E402
+from syncvsr_b200.train import FusedAdamW, SentenceDataParallelStep  # noqa: E402
 
 # algorithmic forward GFLOP per clip (2*MAC; SURVEY.md section 8d probe, 88x88, adim 768): frontend + conformer + audio
 # head + decoder (L=40); fwd+bwd = 3x forward minus the stem's input gradient (1.76 GF/29 frames per frame)
@@ -41,10 +42,18 @@ def main():
     ap.add_argument("--phases", action="store_true")
     a = ap.parse_args()
     B, T, Lmax = a.B, a.T, 40
+    # data parallel under torchrun (one process per GPU, NCCL): SentenceDataParallelStep all-reduces the flat gradient arena
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(1234)
     m = E2E(5049, args_ns(Lmax)).train()
     opt = FusedAdamW(m, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.03, max_grad_norm=5.0)
-    g = torch.Generator(device="cuda").manual_seed(1234)
+    dp = SentenceDataParallelStep(m, opt) if world > 1 else None
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     x = torch.randn(B, T, 1, 88, 88, device="cuda", generator=g)
     lengths = torch.randint(T // 2, T + 1, (B,), device="cuda", generator=g)
     lengths[0] = T
@@ -63,6 +72,10 @@ def main():
         return torch.cuda.Event(enable_timing=True)
 
     def step(rec=None):
+        if dp is not None:
+            out = dp(x, lengths, tokens, label)
+            m._ensure(x, Lmax)
+            return out
         opt.zero_grad()
         if rec:
             rec[0].record()
@@ -90,14 +103,26 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # replicas must stay bit-identical: same all-reduced gradients, same AdamW
+        chk = torch.stack([m.flat_params.double().sum(), m.flat_params.double().abs().max()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN), dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "parameter replicas diverged"
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     launches = (L.svsr_launch_count() - n0) // a.steps
     gf = FWD_GF.get(T, FWD_GF[150] * T / 150) * 3 - 1.76 * T / 29
     line = {"workload": f"LRS E2E step (Conformer-12L adim768 + CTC + decoder-6L + audio CE), x[{B},{T},1,88,88], bf16",
-            "ms_per_step": ms, "clips_per_s": B * 1e3 / ms, "frames_per_s": B * T * 1e3 / ms,
-            "algorithmic_tflops": B * gf / ms, "launches_per_step": int(launches),
+            "n_gpus": world, "ms_per_step": ms, "clips_per_s": world * B * 1e3 / ms, "frames_per_s": world * B * T * 1e3 / ms,
+            "algorithmic_tflops_per_gpu": B * gf / ms, "launches_per_step": int(launches),
             "loss": [float(v) for v in out[:4]], "acc": float(out[4]), "workspace_gb": m._ws.numel() / 2**30,
             "params_M": m.flat_params.numel() / 1e6}
-    if a.phases:
+    if a.phases and world == 1:
         acc = [0.0, 0.0, 0.0]
         for _ in range(5):
             rec = [ev() for _ in range(4)]
@@ -107,6 +132,8 @@ def main():
                 acc[i] += rec[i].elapsed_time(rec[i + 1]) / 5
         line["phase_ms"] = {"fwd": acc[0], "bwd": acc[1], "opt+repack": acc[2]}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
