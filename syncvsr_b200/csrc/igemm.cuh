@@ -59,6 +59,11 @@ struct IgemmProblem {
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
 
+// igemm_halo.cu: single-load halo-tile kernel for 3x3 / stride-1 / 64 -> 64 channel problems (resnet.layer1); igemm_launch()
+// dispatches to it when igemm_halo_matches() (SVSR_HALO_CONV=0 in the environment keeps the generic kernel).
+bool igemm_halo_matches(const IgemmProblem& p);
+int igemm_halo_launch(const IgemmProblem& p, cudaStream_t stream);
+
 // Chooses the pixel box (bn, bh, bw) with bn*bh*bw <= 128 that wastes the fewest MMA rows.
 void igemm_choose_box(int o_N, int OH, int OW, int* bn, int* bh, int* bw);
 

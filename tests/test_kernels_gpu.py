@@ -87,6 +87,33 @@ def test_conv_fused_batchnorm_statistics(ops, N, H, W, Cin, Cout, R, stride, pad
     assert rel(stats[1], (ref.double() ** 2).sum((0, 2, 3))) < 2e-3
 
 
+@pytest.mark.parametrize("N,H,W", [(40, 22, 22), (3, 24, 24), (5, 7, 25), (2, 1, 2), (9, 13, 5), (1, 30, 11)])
+def test_halo_conv_matches_generic_igemm(ops, monkeypatch, N, H, W):
+    """igemm_halo.cu (one activation load per tile, resident weights) against the tap-by-tap kernel it replaces for the
+    64 -> 64 channel 3x3 convs, and against fp32 PyTorch: forward (+ fused BN statistics) and input gradient (+ residual)."""
+    x, w = randn(N, H, W, 64, seed=31), randn(64, 64, 3, 3, seed=32, scale=0.05)
+    dy, base = randn(N, H, W, 64, seed=33, scale=0.1), randn(N, H, W, 64, seed=34)
+    wp, wd = ops.pack_conv_weight(w), ops.pack_conv_weight_dgrad(w)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVSR_HALO_CONV", mode)
+        y, stats = ops.conv2d_fprop_bnstats(x, wp, 3, 3, 1, 1)
+        dx = ops.conv2d_dgrad(dy, wd, H, W, 3, 3, 1, 1, resid=base)
+        res[mode] = (y.clone(), stats.clone(), dx.clone(), ops.conv2d_fprop(x, wp, 3, 3, 1, 1, resid=base).clone())
+    # same MMA sequence per output pixel -> identical bf16 results
+    assert torch.equal(res["1"][0], res["0"][0])
+    assert torch.equal(res["1"][2], res["0"][2])
+    assert torch.equal(res["1"][3], res["0"][3])
+    assert rel(res["1"][1], res["0"][1]) < 1e-6
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.conv2d(xt, w.float(), padding=1)
+    assert rel(res["1"][0], ref.permute(0, 2, 3, 1)) < BF16_TOL
+    gx, = torch.autograd.grad(ref, xt, dy.float().permute(0, 3, 1, 2))
+    assert rel(res["1"][2], gx.permute(0, 2, 3, 1) + base.float()) < BF16_TOL
+    yd = res["1"][0].double()
+    assert rel(res["1"][1][0], yd.sum((0, 1, 2))) < 1e-4 and rel(res["1"][1][1], (yd ** 2).sum((0, 1, 2))) < 1e-4
+
+
 def test_conv_dgrad_accumulates_residual_in_place(ops):
     dy, w = randn(4, 11, 11, 128, seed=7), randn(128, 64, 3, 3, seed=8, scale=0.05)
     base = randn(4, 22, 22, 64, seed=9)
