@@ -218,6 +218,33 @@ int svsr_cutmix_gather(const float* videos_in, float* videos_out, const int* vsr
                        const float* wm_in, float* wm_out, int Tw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Data path (reference: LRW/video/src/data.py:32-68 Dataset.__getitem__ and the transform
+ * pipelines of data.py:156-171, run there per sample on CPU DataLoader workers).
+ * --------------------------------------------------------------------------------------------------------- */
+#define SVSR_JPEG_DESC_INTS 24
+#define SVSR_JPEG_HUFF_BYTES 1536
+/* HOST function (no GPU needed): walks the markers of n concatenated baseline JPEG files (frame f = blob[offsets[f],
+ * offsets[f+1])) and writes one descriptor per frame (layout in csrc/datapath.cu) plus the pools of distinct
+ * quantisation tables (natural order, u16 [qcap][64]) and decode-ready Huffman tables (u8 [hcap][SVSR_JPEG_HUFF_BYTES]).
+ * Supports what TurboJPEG.encode writes (data.py:41 decodes it): 8-bit sequential Huffman, 1 or 3 components in one
+ * interleaved scan, any sampling factors, restart intervals. Progressive / arithmetic files are refused. */
+int svsr_jpeg_parse(const uint8_t* blob, const int64_t* offsets, int n, int32_t* desc, uint16_t* qtabs, int qcap, int* n_q,
+                    uint8_t* htabs, int hcap, int* n_h);
+/* data.py:41 `jpeg.decode(img, pixel_format=TJPF_GRAY)` for a batch: out u8 [n, H, W] = luminance plane, bit-identical to
+ * libjpeg-turbo (integer "islow" IDCT). All frames must share W x H; blocks_w x blocks_h is the luminance block grid
+ * (ceil(W / (8*hmax)) * h0 by ceil(H / (8*vmax)) * v0); coef_scratch holds n*blocks_w*blocks_h*64 int16. */
+int svsr_jpeg_decode_gray(const uint8_t* blob_dev, const int32_t* desc_dev, int n, const uint16_t* qtabs_dev,
+                          const uint8_t* htabs_dev, int16_t* coef_scratch, uint8_t* out, int W, int H, int blocks_w,
+                          int blocks_h, void* stream);
+/* data.py:157-171 transform pipeline for a batch of decoded clips: frames u8 [B,T,H,W] -> out f32 [B,1,T,OH,OW]:
+ * x/255 -> horizontal flip -> crop (top,left,h,w) + antialiased bilinear resize to OH x OW (RandomResizedCrop / Resize /
+ * CenterCrop) -> TimeMask: frames [t0,t1) <- mean of the clip (augment.py:120-143) -> (x-mean)/std.
+ * xform int32 [B][8] = {flip, top, left, crop_h, crop_w, mask_t0, mask_t1, 0}, drawn on the host in the reference's RNG
+ * order (syncvsr_b200/data.py). clip_sum: B doubles of scratch (needed when time_mask != 0). */
+int svsr_video_transform(const uint8_t* frames, const int* xform, float* out, double* clip_sum, int B, int T, int H, int W,
+                         int OH, int OW, float mean, float stdv, int time_mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * LRS sentence-level operators (reference: LRS/video/espnet/nets/pytorch_backend/, paths below relative to it).
  * --------------------------------------------------------------------------------------------------------- */
 /* transformer/layer_norm.py:12-33 (eps 1e-12): y = (x-mean)*rstd*gamma+beta over the last dim D (multiple of 128,
