@@ -121,6 +121,13 @@ class JpegBatchDecoder:
 
     def __init__(self, device: torch.device | str = "cuda"):
         self.device = torch.device(device)
+        self._stage = None  # reusable pinned staging buffer for the JPEG bytes
+        self._copied = None  # event recorded after the last H2D copy out of it
+
+    def _pinned(self, nbytes: int) -> torch.Tensor:
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(max(nbytes * 5 // 4, 1 << 20), dtype=torch.uint8).pin_memory()
+        return self._stage[:nbytes]
 
     def parse(self, frames: Sequence[bytes]):
         """Host side only (works without a GPU): concatenated blob, per-frame descriptors, table pools, geometry."""
@@ -153,8 +160,15 @@ class JpegBatchDecoder:
     def decode(self, frames: Sequence[bytes]) -> torch.Tensor:
         p = self.parse(frames)
         dev = self.device
-        up = lambda a: torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)  # noqa: E731
-        blob, desc, qt, ht = up(p["blob"].copy()), up(p["desc"]), up(p["qt"].view(np.int16)), up(p["ht"])
+        up = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)  # noqa: E731
+        if self._copied is not None:
+            self._copied.synchronize()  # the previous batch's H2D copy has left the staging buffer
+        stage = self._pinned(p["blob"].size)
+        stage.numpy()[:] = p["blob"]
+        blob = stage.to(dev, non_blocking=True)
+        self._copied = torch.cuda.Event()
+        self._copied.record()
+        desc, qt, ht = up(p["desc"]), up(p["qt"].view(np.int16)), up(p["ht"])
         n, W, H, bw, bh = p["n"], p["W"], p["H"], p["bw"], p["bh"]
         coef = torch.empty(n * bw * bh * 64, device=dev, dtype=torch.int16)
         out = torch.empty(n, H, W, device=dev, dtype=torch.uint8)
