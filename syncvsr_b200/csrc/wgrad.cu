@@ -1,6 +1,7 @@
 // tcgen05 weight-gradient kernel (see wgrad.cuh). Same warp roles as igemm.cu.
 // smem stage = A: two 64-channel blocks [128 pixel rows x 128 B] + B: BN/64 such blocks, all SWIZZLE_128B, MN-major.
 #include "wgrad.cuh"
+#include <stdlib.h>
 #include "igemm.cuh"  // igemm_choose_box
 #include "tmap.h"
 
@@ -225,11 +226,28 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
   if (kp.mb_per_cta > num_mblocks) kp.mb_per_cta = num_mblocks;
   const int gx = (num_mblocks + kp.mb_per_cta - 1) / kp.mb_per_cta;
   const int gy = (p.n_cols + BN - 1) / BN;
-  // split-K: enough CTAs to fill the chip twice, but at least ~4 pixel tiles per CTA so that the fixed cost
-  // (TMEM alloc, pipeline fill, fp32 red.add of the whole tile) is amortised
-  int nsplit = (2 * 148 + gx * gy - 1) / (gx * gy);
-  if (nsplit > (kp.ktiles + 3) / 4) nsplit = (kp.ktiles + 3) / 4;
-  if (nsplit < 1) nsplit = 1;
+  // split-K factor from a small cost model (microseconds): one CTA per SM is resident (192 KB of smem), so the launch
+  // runs in ceil(ctas / 148) waves of  t_fixed + mb_per_cta * (ktiles_per_cta * t_stage + t_epilogue);  the fp32 red.add
+  // traffic of all splits is added at L2 atomic throughput. The previous rule (ceil(296 / (gx*gy)) splits) produced
+  // 297-, 300-, 306- and 324-CTA grids: a third wave with a handful of CTAs, i.e. +50 % time on the layer2-4 convs.
+  const double t_stage = BN == 256 ? 0.93 : (BN == 128 ? 0.53 : 0.33);  // 8 MMAs: (smem operand read + math) cycles
+  const double t_epi = 0.5 + 2.0 * BN / 256.0, t_fixed = 2.5;
+  int nsplit = 1;
+  double best = 1e30;
+  for (int n = 1; n <= kp.ktiles && n <= 1024; ++n) {
+    const int ctas = gx * gy * n, waves = (ctas + 147) / 148, kt = (kp.ktiles + n - 1) / n;
+    const double t_cta = t_fixed + kp.mb_per_cta * (kt * t_stage + t_epi);
+    const double red_bytes = (double)ctas * kp.mb_per_cta * 128.0 * BN * 4.0;
+    const double cost = waves * t_cta + 0.5 * red_bytes / 3.0e6;
+    if (cost < best * 0.98) best = cost, nsplit = n;  // ties go to fewer splits (less atomic traffic)
+  }
+  if (const char* e = getenv("SVSR_WGRAD_SPLIT_LEGACY")) {
+    if (e[0] == '1') {
+      nsplit = (2 * 148 + gx * gy - 1) / (gx * gy);
+      if (nsplit > (kp.ktiles + 3) / 4) nsplit = (kp.ktiles + 3) / 4;
+      if (nsplit < 1) nsplit = 1;
+    }
+  }
 
   CUtensorMap tmA, tmB;
   {
