@@ -190,15 +190,17 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ c
   }
 }
 
-__global__ void __launch_bounds__(256)
+template <int MODE>  // 0: plain / ReLU mask from relu_ref, 1: ReLU mask from this BN's own output, 2: Swish follows
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                      const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef, long long rows, int C,
                      double* stats, int self_mask, const __nv_bfloat16* __restrict__ sw_res,
                      const float* __restrict__ sw_rcoef) {
   const int cg = C >> 3;
   const int g = threadIdx.x % cg, slot = threadIdx.x / cg, rpb = 256 / cg;
-  const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
-  const F8 scl = ldf8(coef + 2 * C + g * 8), shf = ldf8(coef + 3 * C + g * 8);
+  const F8 mean = ldf8(coef + g * 8);
+  F8 scl, shf;  // only the self-masking modes keep these live across the loop
+  if (MODE != 0) scl = ldf8(coef + 2 * C + g * 8), shf = ldf8(coef + 3 * C + g * 8);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -209,7 +211,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     const long long off0 = r * C + g * 8, off1 = (two ? r + rstep : r) * C + g * 8;
     F8 gv[2] = {ld8(dout + off0), ld8(dout + off1)};
     const F8 cv[2] = {ld8(c + off0), ld8(c + off1)};
-    if (relu_ref) {
+    if (MODE == 0 && relu_ref) {
       const F8 o[2] = {ld8(relu_ref + off0), ld8(relu_ref + off1)};
 #pragma unroll
       for (int u = 0; u < 2; ++u)
@@ -219,10 +221,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
-      if (self_mask == 1) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
+      if (MODE == 1) {  // ReLU directly follows this BN: its mask is the sign of the BN output, no extra tensor read
 #pragma unroll
         for (int k = 0; k < 8; ++k) gv[u].v[k] = (cv[u].v[k] * scl.v[k] + shf.v[k]) > 0.f ? gv[u].v[k] : 0.f;
-      } else if (self_mask == 2) {  // Swish follows (this BN output [+ residual branch]): g = dout * swish'(pre-activation)
+      } else if (MODE == 2) {  // Swish follows (this BN output [+ residual branch]): g = dout * swish'(pre-activation)
         F8 pre;
 #pragma unroll
         for (int k = 0; k < 8; ++k) pre.v[k] = cv[u].v[k] * scl.v[k] + shf.v[k];
@@ -242,9 +244,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         acc[k] += gv[u].v[k];
-        acc[8 + k] += gv[u].v[k] * (cv[u].v[k] - mean.v[k]) * invstd.v[k];
+        acc[8 + k] += gv[u].v[k] * (cv[u].v[k] - mean.v[k]);  // x invstd once, after the loop
       }
     }
+  }
+  {
+    const F8 invstd = ldf8(coef + C + g * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[8 + k] *= invstd.v[k];
   }
   block_channel_reduce(acc, cg, C, stats);
 }
@@ -260,7 +267,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, long lo
   kcoef[C + c] = (float)(sgx / (double)rows);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
                     const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
@@ -881,8 +888,13 @@ int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, cons
                   const float* sw_rcoef) {
   SVSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   const int rpb = 256 / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, rpb * 8, 148 * 6), 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask,
-                                                                        sw_res, sw_rcoef);
+  const unsigned grid = grid_for(rows, rpb * 8, 148 * 3);  // 3 CTAs per SM are resident (<= 85 registers)
+  if (self_mask == 1)
+    bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask, sw_res, sw_rcoef);
+  else if (self_mask == 2)
+    bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask, sw_res, sw_rcoef);
+  else
+    bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, rows, C, stats, self_mask, sw_res, sw_rcoef);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

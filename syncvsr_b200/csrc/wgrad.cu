@@ -241,6 +241,10 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
     const double cost = waves * t_cta + 0.5 * red_bytes / 3.0e6;
     if (cost < best * 0.98) best = cost, nsplit = n;  // ties go to fewer splits (less atomic traffic)
   }
+  if (const char* e = getenv("SVSR_WGRAD_NSPLIT")) {  // tuning override (tools/wgrad_bench.py)
+    const int n = atoi(e);
+    if (n >= 1) nsplit = n < kp.ktiles ? n : kp.ktiles;
+  }
   if (const char* e = getenv("SVSR_WGRAD_SPLIT_LEGACY")) {
     if (e[0] == '1') {
       nsplit = (2 * 148 + gx * gy - 1) / (gx * gy);

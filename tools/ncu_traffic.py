@@ -31,6 +31,8 @@ def main():
     fam = collections.defaultdict(lambda: {"launches": 0, "bytes": 0.0, "us": 0.0})
     for k in step:
         f = re.sub(r"<.*", "", k["name"]).strip()
+        if f == "conv3x3_c64_halo_kernel":  # same family as igemm_kernel in bench.py's per-launch events (PROF_IGEMM)
+            f = "igemm_kernel"
         fam[f]["launches"] += 1
         fam[f]["bytes"] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
         fam[f]["us"] += k.get("us", 0.0)
