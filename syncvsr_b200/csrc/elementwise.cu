@@ -14,6 +14,14 @@ __device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
   r.v[0] = a.x, r.v[1] = a.y, r.v[2] = b.x, r.v[3] = b.y, r.v[4] = c.x, r.v[5] = c.y, r.v[6] = d.x, r.v[7] = d.y;
   return r;
 }
+// raw 16-byte load / late unpack: unrolled streaming loops keep 4 registers per in-flight load instead of 8
+__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x, r.v[1] = a.y, r.v[2] = b.x, r.v[3] = b.y, r.v[4] = c.x, r.v[5] = c.y, r.v[6] = d.x, r.v[7] = d.y;
+  return r;
+}
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
   uint4 u;
   u.x = pack_bf16x2(r.v[0], r.v[1]), u.y = pack_bf16x2(r.v[2], r.v[3]);
@@ -155,38 +163,60 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long r
   }
 }
 
-__global__ void __launch_bounds__(256)
+// Each thread owns one 8-channel group (grid stride is a multiple of C/8: coefficients load once, no index division)
+// and walks rows four at a time with every load issued before the first use (this pass is pure HBM streaming; one
+// 16-byte load per thread in flight left it at half the bandwidth).
+__global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
                 const __nv_bfloat16* __restrict__ res, const float* __restrict__ rcoef, int relu,
                 __nv_bfloat16* __restrict__ out, long long rows, int C) {
-  const int cg = C >> 3;
-  const long long total = rows * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long off = (i / cg) * C + g * 8;
-    F8 v = ld8(x + off);
-    const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+  constexpr int U = 6;
+  const int cg = C >> 3, rpb = 256 / cg;  // rows per block pass; threads beyond rpb*cg idle (C = 768: 192 of 256 work)
+  if (threadIdx.x >= rpb * cg) return;
+  const int g = threadIdx.x % cg;
+  const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+  const long long rstep = (long long)gridDim.x * rpb;
+  for (long long r = (long long)blockIdx.x * rpb + threadIdx.x / cg; r < rows; r += U * rstep) {
+    uint4 xr[U], rr[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v.v[k] = v.v[k] * sc.v[k] + sh.v[k];
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * rstep;
+      xr[u] = ldraw(x + (ru < rows ? ru : r) * C + g * 8);
+    }
     if (res) {
-      F8 rv = ld8(res + off);
-      if (rcoef) {
-        const F8 rs = ldf8(rcoef + 2 * C + g * 8), rh = ldf8(rcoef + 3 * C + g * 8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+      for (int u = 0; u < U; ++u) {
+        const long long ru = r + u * rstep;
+        rr[u] = ldraw(res + (ru < rows ? ru : r) * C + g * 8);
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v.v[k] += rv.v[k];
     }
-    if (relu == 1) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
-    } else if (relu == 2) {
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * rstep;
+      if (ru < rows) {
+        F8 v = unpack8(xr[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v.v[k] = swish_f(v.v[k]);
+        for (int k = 0; k < 8; ++k) v.v[k] = v.v[k] * sc.v[k] + sh.v[k];
+        if (res) {
+          F8 rv = unpack8(rr[u]);
+          if (rcoef) {  // downsample branch only (3 of 16 launches): coefficients re-read from L1, not kept live
+            const F8 rs = ldf8(rcoef + 2 * C + g * 8), rh = ldf8(rcoef + 3 * C + g * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] += rv.v[k];
+        }
+        if (relu == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+        } else if (relu == 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] = swish_f(v.v[k]);
+        }
+        st8(out + ru * C + g * 8, v);
+      }
     }
-    st8(out + off, v);
   }
 }
 
@@ -267,57 +297,74 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, long lo
   kcoef[C + c] = (float)(sgx / (double)rows);
 }
 
-__global__ void __launch_bounds__(256, 3)
+// dc = sc * (g - k1 - xhat * k2) with g = dout masked by the activation that follows the BN, regrouped as
+// dc = sc * g + cB * c + cD (cB = -sc*invstd*k2, cD = sc*(invstd*k2*mean - k1)): three coefficient vectors stay in
+// registers instead of five. Each thread owns one 8-channel group (the grid stride is a multiple of C/8, so no index
+// division in the loop) and walks rows two at a time with all loads issued before the first use.
+template <int MODE>  // 0: plain / ReLU mask from relu_ref, 1: ReLU mask from this BN's own output, 2: Swish follows
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ relu_ref,
                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
                     const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
-                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C, int self_mask,
+                    __nv_bfloat16* __restrict__ gmask_out, long long rows, int C,
                     const __nv_bfloat16* __restrict__ sw_res, const float* __restrict__ sw_rcoef) {
-  const int cg = C >> 3;
-  const long long total = rows * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long off = (i / cg) * C + g * 8;
-    F8 gv = ld8(dout + off);
-    if (relu_ref) {
-      const F8 o = ld8(relu_ref + off);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gv.v[k] = o.v[k] > 0.f ? gv.v[k] : 0.f;
-    }
-    const F8 cv = ld8(c + off);
-    const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8), sc = ldf8(coef + 2 * C + g * 8);
-    if (self_mask == 1) {
-      const F8 shf = ldf8(coef + 3 * C + g * 8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gv.v[k] = (cv.v[k] * sc.v[k] + shf.v[k]) > 0.f ? gv.v[k] : 0.f;
-    } else if (self_mask == 2) {
-      const F8 shf = ldf8(coef + 3 * C + g * 8);
-      F8 pre;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pre.v[k] = cv.v[k] * sc.v[k] + shf.v[k];
-      if (sw_res) {
-        F8 rv = ld8(sw_res + off);
-        if (sw_rcoef) {
-          const F8 rs = ldf8(sw_rcoef + 2 * C + g * 8), rh = ldf8(sw_rcoef + 3 * C + g * 8);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pre.v[k] += rv.v[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gv.v[k] *= swish_grad_f(pre.v[k]);
-    }
-    if (gmask_out) st8(gmask_out + off, gv);
+  const int cg = C >> 3, rpb = 256 / cg;
+  if (threadIdx.x >= rpb * cg) return;
+  const int g = threadIdx.x % cg;
+  F8 sc = ldf8(coef + 2 * C + g * 8), cB, cD, shf;
+  {
+    const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
     const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
-    F8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (cv.v[k] - mean.v[k]) * invstd.v[k];
-      o.v[k] = sc.v[k] * (gv.v[k] - k1.v[k] - xh * k2.v[k]);
+      const float t = sc.v[k] * invstd.v[k] * k2.v[k];
+      cB.v[k] = -t, cD.v[k] = t * mean.v[k] - sc.v[k] * k1.v[k];
     }
-    st8(dc + off, o);
+  }
+  if (MODE != 0) shf = ldf8(coef + 3 * C + g * 8);
+  const long long rstep = (long long)gridDim.x * rpb;
+  for (long long r = (long long)blockIdx.x * rpb + threadIdx.x / cg; r < rows; r += 2 * rstep) {
+    const bool two = r + rstep < rows;
+    const long long offs[2] = {r * C + g * 8, (two ? r + rstep : r) * C + g * 8};
+    F8 gv[2] = {ld8(dout + offs[0]), ld8(dout + offs[1])};
+    const F8 cv[2] = {ld8(c + offs[0]), ld8(c + offs[1])};
+    if (MODE == 0 && relu_ref) {
+      const F8 o[2] = {ld8(relu_ref + offs[0]), ld8(relu_ref + offs[1])};
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[u].v[k] = o[u].v[k] > 0.f ? gv[u].v[k] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long off = offs[u];
+      if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[u].v[k] = (cv[u].v[k] * sc.v[k] + shf.v[k]) > 0.f ? gv[u].v[k] : 0.f;
+      } else if (MODE == 2) {
+        F8 pre;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pre.v[k] = cv[u].v[k] * sc.v[k] + shf.v[k];
+        if (sw_res) {
+          F8 rv = ld8(sw_res + off);
+          if (sw_rcoef) {
+            const F8 rs = ldf8(sw_rcoef + 2 * C + g * 8), rh = ldf8(sw_rcoef + 3 * C + g * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rv.v[k] = rv.v[k] * rs.v[k] + rh.v[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pre.v[k] += rv.v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[u].v[k] *= swish_grad_f(pre.v[k]);
+      }
+      if (gmask_out) st8(gmask_out + off, gv[u]);
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = sc.v[k] * gv[u].v[k] + (cB.v[k] * cv[u].v[k] + cD.v[k]);
+      st8(dc + off, o);
+    }
   }
 }
 
@@ -879,7 +926,8 @@ int bn_finalize(const double* stats, long long rows, int C, const float* gamma, 
 }
 int bn_apply(const __nv_bfloat16* x, const float* coef, const __nv_bfloat16* res, const float* rcoef, int relu,
              __nv_bfloat16* out, long long rows, int C, cudaStream_t s) {
-  bn_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(x, coef, res, rcoef, relu, out, rows, C);
+  SVSR_REQUIRE(C % 8 == 0 && C <= 2048, "bn_apply: unsupported channel count %d", C);
+  bn_apply_kernel<<<grid_for(rows, (256 / (C / 8)) * 4, 148 * 2), 256, 0, s>>>(x, coef, res, rcoef, relu, out, rows, C);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -907,8 +955,14 @@ int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, f
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
                  const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
                  cudaStream_t s, const __nv_bfloat16* sw_res, const float* sw_rcoef) {
-  bn_bwd_apply_kernel<<<grid_for(rows * (C / 8), 256 * 4), 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out,
-                                                                       rows, C, self_mask, sw_res, sw_rcoef);
+  SVSR_REQUIRE(C % 8 == 0 && C <= 2048, "bn_bwd_apply: unsupported channel count %d", C);
+  const unsigned grid = grid_for(rows, (256 / (C / 8)) * 4, 148 * 3);
+  if (self_mask == 1)
+    bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
+  else if (self_mask == 2)
+    bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
+  else
+    bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
