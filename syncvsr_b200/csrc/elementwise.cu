@@ -721,15 +721,43 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (jb.type == 0) {
+    // conv [Cout][Cin][RS] -> fprop layout dst0 [Cout][RS][Cin] and dgrad layout dst1 [Cin][RS][Cout]: tiles of
+    // 32 co x 32 ci x RS through shared memory, so the read (32*RS contiguous floats per co) and BOTH writes (32
+    // contiguous bf16 per (row, tap)) are coalesced; element-wise scatter cost 2-byte writes to 22 M distinct sectors.
     const int Cout = jb.a, Cin = jb.b, RS = jb.c;
-    const long long total = (long long)Cout * Cin * RS;
-    for (long long i = i0; i < total; i += stride) {
-      const int rs = (int)(i % RS);
-      const int ci = (int)((i / RS) % Cin);
-      const int co = (int)(i / ((long long)RS * Cin));
-      const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
-      jb.dst0[(long long)co * RS * Cin + (long long)rs * Cin + ci] = v;
-      if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
+    if (RS <= 9 && Cout % 32 == 0 && Cin % 32 == 0) {
+      __shared__ float ctile[32 * (32 * 9 + 1)];
+      const int pitch = 32 * RS + 1;
+      const int tci = Cin / 32, ntiles = (Cout / 32) * tci;
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int co0 = (t / tci) * 32, ci0 = (t % tci) * 32;
+        __syncthreads();
+        for (int col = warp; col < 32; col += 8) {
+          const float* srow = jb.src + ((long long)(co0 + col) * Cin + ci0) * RS;
+          for (int e = lane; e < 32 * RS; e += 32) ctile[col * pitch + e] = srow[e];
+        }
+        __syncthreads();
+        for (int pr = warp; pr < 32 * RS; pr += 8) {
+          const int row = pr / RS, rs = pr - row * RS;
+          // dst0: row = co_l, lane = ci_l
+          jb.dst0[((long long)(co0 + row) * RS + rs) * Cin + ci0 + lane] = __float2bfloat16(ctile[row * pitch + lane * RS + rs]);
+          // dst1: row = ci_l, lane = co_l
+          if (jb.dst1)
+            jb.dst1[((long long)(ci0 + row) * RS + rs) * Cout + co0 + lane] =
+                __float2bfloat16(ctile[lane * pitch + row * RS + rs]);
+        }
+      }
+    } else {
+      const long long total = (long long)Cout * Cin * RS;
+      for (long long i = i0; i < total; i += stride) {
+        const int rs = (int)(i % RS);
+        const int ci = (int)((i / RS) % Cin);
+        const int co = (int)(i / ((long long)RS * Cin));
+        const __nv_bfloat16 v = __float2bfloat16(jb.src[i]);
+        jb.dst0[(long long)co * RS * Cin + (long long)rs * Cin + ci] = v;
+        if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
+      }
     }
   } else if (jb.type == 1) {
     // linear [N,K]: 32x32 tiles through shared memory so that the plain copy AND the transposed copy are both
@@ -1050,7 +1078,9 @@ int pack_linear_weight(const float* w, __nv_bfloat16* wb, __nv_bfloat16* wt, int
   return SVSR_OK;
 }
 int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
-  dim3 grid(64, (unsigned)njobs);
+  // 512 CTAs per job: the largest jobs (FF linears, 2048 tiles) then run 4 tiles per CTA instead of 32 in sequence --
+  // with 64 the kernel lasted as long as its longest per-CTA chain (288 us for 466 MB); CTAs without a tile exit at once
+  dim3 grid(512, (unsigned)njobs);
   pack_all_kernel<<<grid, 256, 0, s>>>(jobs_dev);
   LAUNCH_CHECK();
   return SVSR_OK;
