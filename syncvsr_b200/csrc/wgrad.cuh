@@ -31,4 +31,9 @@ struct WgradProblem {
 
 int wgrad_launch(const WgradProblem& p, cudaStream_t stream);
 
+// wgrad_halo.cu: single-load halo-tile kernel for 3x3 / stride-1 / 64 -> 64 channel problems (resnet.layer1);
+// wgrad_launch() dispatches to it when wgrad_halo_matches() (SVSR_HALO_CONV=0 keeps the generic kernel).
+bool wgrad_halo_matches(const WgradProblem& p);
+int wgrad_halo_launch(const WgradProblem& p, cudaStream_t stream);
+
 }  // namespace svsr

@@ -114,6 +114,23 @@ def test_halo_conv_matches_generic_igemm(ops, monkeypatch, N, H, W):
     assert rel(res["1"][1][0], yd.sum((0, 1, 2))) < 1e-4 and rel(res["1"][1][1], (yd ** 2).sum((0, 1, 2))) < 1e-4
 
 
+@pytest.mark.parametrize("N,H,W", [(40, 22, 22), (3, 24, 24), (5, 7, 25), (2, 1, 2), (9, 13, 5), (300, 22, 22)])
+def test_halo_wgrad_matches_generic_and_autograd(ops, monkeypatch, N, H, W):
+    """wgrad_halo.cu (one activation + one gradient load per pixel tile, tap pairs as descriptor offsets) against the
+    generic split-K kernel and fp32 autograd; accumulation into a non-zero gradient buffer."""
+    x, dy = randn(N, H, W, 64, seed=41), randn(N, H, W, 64, seed=42, scale=0.1)
+    base = torch.randn(9 * 64, 64, device="cuda")
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVSR_HALO_CONV", mode)
+        res[mode] = ops.conv2d_wgrad(x, dy, 3, 3, 1, 1, out=base.clone())
+    assert rel(res["1"] - base, res["0"] - base) < 2e-5  # same products, different fp32 summation order
+    xt = x.float().permute(0, 3, 1, 2)
+    wt = torch.zeros(64, 64, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(xt, wt, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(ops.unpack_conv_wgrad(res["1"] - base, 64, 3, 3), wt.grad) < F32_TOL
+
+
 def test_conv_dgrad_accumulates_residual_in_place(ops):
     dy, w = randn(4, 11, 11, 128, seed=7), randn(128, 64, 3, 3, seed=8, scale=0.05)
     base = randn(4, 22, 22, 64, seed=9)
