@@ -24,13 +24,16 @@ def load(path):
 def main():
     recs = load(sys.argv[1])
     idx = [i for i, r in enumerate(recs) if "stem_patch" in r[0]]
-    step = recs[idx[-1]:]
+    # the last COMPLETE step: a capture cut by `ncu -c N` ends inside a step, which shows as a shorter last segment
+    segs = [recs[a:b] for a, b in zip(idx, idx[1:] + [len(recs)])]
+    full = max(len(sg) for sg in segs)
+    step = [sg for sg in segs if len(sg) == full][-1]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for name, us, _ in step:
         agg[name][0] += 1
         agg[name][1] += us
     tot = sum(v[1] for v in agg.values())
-    print(f"last step: {tot/1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches (ncu-serialised, cold cache)")
+    print(f"last complete step: {tot/1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches (ncu-serialised, cold cache)")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{v[1]/1e3:8.3f} ms {100*v[1]/tot:5.1f}%  n={v[0]:4d}  {k[:80]}")
     if "--grids" in sys.argv:
