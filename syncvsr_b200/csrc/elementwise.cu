@@ -374,58 +374,79 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
                          __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ argmax, int N, int IH, int IW, int OH,
                          int OW, int swish) {
   constexpr int C = 64, cg = 8;
-  const long long total = (long long)N * OH * OW * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long long pix = i / cg;
-    const int ow = (int)(pix % OW);
-    long long t1 = pix / OW;
-    const int oh = (int)(t1 % OH);
-    const long long n = t1 / OH;
-    const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
-    // GELU is unimodal (decreasing below ~-0.75, increasing above), so the window maximum of gelu(z) is attained at
-    // the largest or the smallest z: track both extremes (first occurrence) and evaluate erf twice instead of 9 times.
-    float zmax[8], zmin[8];
-    int imax[8], imin[8];
+  const unsigned total = (unsigned)N * OH * OW * cg;  // < 2^31 (checked by the launcher): 32-bit index arithmetic
+  const int g = threadIdx.x & 7;                       // the grid stride is a multiple of 8
+  const F8 sc = ldf8(coef + 2 * C + g * 8), sh = ldf8(coef + 3 * C + g * 8);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i >> 3;
+    const unsigned ow = pix % (unsigned)OW, t1 = pix / (unsigned)OW;
+    const unsigned oh = t1 % (unsigned)OH, n = t1 / (unsigned)OH;
+    // GELU (and Swish) are unimodal -- decreasing below z ~ -0.75 (-1.278), increasing above, negative for z < 0 -- so the
+    // window maximum of act(z) is act(max z) whenever max z >= 0: one activation per output instead of nine, and only the
+    // running maximum to track. The rare all-negative window takes the two-candidate path (largest or smallest z).
+    float zmax[8];
+    int imax[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, zmin[k] = INFINITY, imax[k] = 0, imin[k] = 0;
+    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, imax[k] = 0;
+    const __nv_bfloat16* img = y0 + (size_t)n * IH * IW * C + g * 8;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int ih = 2 * oh + kh - 1;
+      const int ih = 2 * (int)oh + kh - 1;
       if (ih < 0 || ih >= IH) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int iw = 2 * ow + kw - 1;
+        const int iw = 2 * (int)ow + kw - 1;
         if (iw < 0 || iw >= IW) continue;
-        const F8 v = ld8(y0 + ((n * IH + ih) * IW + iw) * C + g * 8);
+        const F8 v = ld8(img + (size_t)(ih * IW + iw) * C);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float z = v.v[k] * sc.v[k] + sh.v[k];
           if (z > zmax[k]) zmax[k] = z, imax[k] = kh * 3 + kw;
-          if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
         }
       }
     }
     float best[8];
-    int bi[8];
+    bool any_neg = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      // Swish is unimodal as well (minimum at z ~ -1.278): the same two-candidate argument holds
-      const float a = swish ? swish_f(zmax[k]) : gelu_f(zmax[k]), b = swish ? swish_f(zmin[k]) : gelu_f(zmin[k]);
-      // first maximum wins (torch max_pool semantics): on a tie the earlier window position
-      const bool take_min = (b > a) || (b == a && imin[k] < imax[k]);
-      best[k] = take_min ? b : a;
-      bi[k] = take_min ? imin[k] : imax[k];
+      best[k] = swish ? swish_f(zmax[k]) : gelu_f(zmax[k]);
+      any_neg |= zmax[k] < 0.f;
+    }
+    if (any_neg) {
+      float zmin[8];
+      int imin[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zmin[k] = INFINITY, imin[k] = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = 2 * (int)oh + kh - 1;
+        if (ih < 0 || ih >= IH) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = 2 * (int)ow + kw - 1;
+          if (iw < 0 || iw >= IW) continue;
+          const F8 v = ld8(img + (size_t)(ih * IW + iw) * C);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float z = v.v[k] * sc.v[k] + sh.v[k];
+            if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!(zmax[k] < 0.f)) continue;
+        const float bmin = swish ? swish_f(zmin[k]) : gelu_f(zmin[k]);
+        // first maximum wins (torch max_pool semantics): on a tie the earlier window position
+        if ((bmin > best[k]) || (bmin == best[k] && imin[k] < imax[k])) best[k] = bmin, imax[k] = imin[k];
+      }
     }
     F8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = best[k];
-    st8(out + pix * C + g * 8, o);
+    st8(out + (size_t)pix * C + g * 8, o);
     uint2 packed;
-    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(argmax + pix * C + g * 8) = packed;
+    packed.x = (uint32_t)imax[0] | ((uint32_t)imax[1] << 8) | ((uint32_t)imax[2] << 16) | ((uint32_t)imax[3] << 24);
+    packed.y = (uint32_t)imax[4] | ((uint32_t)imax[5] << 8) | ((uint32_t)imax[6] << 16) | ((uint32_t)imax[7] << 24);
+    *reinterpret_cast<uint2*>(argmax + (size_t)pix * C + g * 8) = packed;
   }
 }
 
@@ -997,6 +1018,7 @@ int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const
 int stem_bn_gelu_pool(const __nv_bfloat16* y0, const float* coef, __nv_bfloat16* out, uint8_t* argmax, int N, int IH,
                       int IW, cudaStream_t s, int swish) {
   const int OH = (IH + 2 - 3) / 2 + 1, OW = (IW + 2 - 3) / 2 + 1;
+  SVSR_REQUIRE((long long)N * OH * OW * 8 < (1LL << 31), "stem_bn_gelu_pool: %d frames exceed 32-bit indexing", N);
   stem_bn_gelu_pool_kernel<<<grid_for((long long)N * OH * OW * 8, 256 * 2), 256, 0, s>>>(y0, coef, out, argmax, N, IH,
                                                                                       IW, OH, OW, swish);
   LAUNCH_CHECK();
