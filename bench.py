@@ -168,7 +168,7 @@ def run_native_arm(args):
     torch.manual_seed(1234 + rank)
     model = TransformerLightningModule(lrw_config()).train()
     opt = FusedAdamW.from_config(model)
-    step = DataParallelStep(model, opt)
+    step = DataParallelStep(model, opt, graph=bool(args.graph), high_priority=bool(args.priority))
 
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     B = B_PER_GPU
@@ -198,7 +198,7 @@ def run_native_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = L.svsr_launch_count()
+    launches0 = L.svsr_launch_count() + step.graph_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -207,11 +207,12 @@ def run_native_arm(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = L.svsr_launch_count() - launches0
+    launches = L.svsr_launch_count() + step.graph_launches - launches0  # graph replays are counted by the step
     # ---- timed region 1b: the same K steps again with a CUDA-event pair around every tensor-core launch (on the
     # launching stream) -> per-family kernel time for the roofline; kept out of region 1 so that the ~300 extra event
     # records per step do not tax `value`
     check(L.svsr_prof_enable(1), "prof_enable")
+    step.graph = False  # event pairs around single launches need kernel-by-kernel launches
     barrier()
     e0.record()
     for i in range(args.steps):
@@ -226,6 +227,7 @@ def run_native_arm(args):
         check(L.svsr_prof_read(kind, C.byref(ms), C.byref(fl), C.byref(n)), "prof_read")
         prof[name] = {"ms": ms.value, "flops": fl.value, "launches": n.value}
     check(L.svsr_prof_enable(0), "prof_enable")
+    step.graph = bool(args.graph)
     loss = float(metrics["loss_total"])
     ms_per_step = ms_total / args.steps
     value = world * B * 1e3 / ms_per_step
@@ -282,6 +284,8 @@ def run_native_arm(args):
                                f"[{B},1,29,88,88] per GPU (BASELINE configs[1])",
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "per-step working set 4.5 GB >> 126 MB L2; two alternating input batches",
+                   "launch_mode": ("cuda-graph replay of zero_grad+repack+fwd+bwd" if args.graph else "kernel by kernel")
+                                  + (", high-priority main stream" if args.priority else ""),
                    "loss_total": loss},
         "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
@@ -306,6 +310,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step's launches from a CUDA graph (train.py)")
+    ap.add_argument("--priority", type=int, default=1, help="run the step's main stream at high priority")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -66,6 +66,11 @@ int svsr_conv2d_fprop_bnstats(const void* x, const void* w, void* y, double* bn_
  * [T, OH*OW] patch image (lightning.py:50). */
 int svsr_conv_taps_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int ntaps,
                          const int* tap_dh, const int* tap_dw, int out_fp32, void* stream);
+/* The same with bf16 output and the fused per-channel statistics of svsr_conv2d_fprop_bnstats (bn_stats fp64
+ * [2][Cout], +=): exactly the call the stem makes for Conv3d -> BatchNorm3d (lightning.py:50-51). 5 taps (dh in
+ * [-2, 2], dw = 0) over 64 -> 64 columns with W % 16 == 0 run on the temporal-halo kernel (csrc/igemm_stem.cu). */
+int svsr_conv_taps_fprop_bnstats(const void* x, const void* w, void* y, double* bn_stats, int N, int H, int W, int Cin,
+                                 int Cout, int ntaps, const int* tap_dh, const int* tap_dw, void* stream);
 
 /* dx[N,H,W,Cin] = conv2d input-gradient of dy[N,OH,OW,Cout]; wd is the weight packed for dgrad as
  * [Cin, R*S*Cout] bf16 (column (r*S+s)*Cout+co holds W[co][ci][r][s]). If resid != NULL it is added (it may alias

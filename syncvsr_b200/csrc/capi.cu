@@ -98,6 +98,20 @@ int svsr_conv_taps_fprop(const void* x, const void* w, void* y, int N, int H, in
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int svsr_conv_taps_fprop_bnstats(const void* x, const void* w, void* y, double* bn_stats, int N, int H, int W, int Cin,
+                                 int Cout, int ntaps, const int* tap_dh, const int* tap_dw, void* stream) {
+  SVSR_REQUIRE(ntaps >= 1 && ntaps <= IGEMM_MAX_TAPS && tap_dh && tap_dw && bn_stats, "conv_taps_bnstats: bad arguments");
+  IgemmProblem p;
+  p.a = x, p.a_N = N, p.a_H = H, p.a_W = W, p.a_C = Cin, p.cin = Cin, p.stride = 1;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) p.tap_dh[t] = tap_dh[t], p.tap_dw[t] = tap_dw[t], p.tap_kbase[t] = t * Cin;
+  p.o_N = N, p.OH = H, p.OW = W;
+  p.b = w, p.b_rows = Cout, p.b_cols = ntaps * Cin;
+  p.out = y, p.out_fp32 = 0, p.ldc = Cout, p.o_H = H, p.o_W = W;
+  p.bn_stats = bn_stats;
+  return igemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
 int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream) {
   SVSR_REQUIRE(R * S <= IGEMM_MAX_TAPS, "dgrad: %dx%d filter has too many taps", R, S);

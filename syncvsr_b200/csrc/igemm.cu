@@ -486,6 +486,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   SVSR_REQUIRE(p.ldc % 8 == 0 && p.c_off % 8 == 0, "igemm: output pitch/offset must be multiples of 8");
   SVSR_REQUIRE(p.stride == 1 || p.stride == 2, "igemm: stride must be 1 or 2");
   if (igemm_halo_matches(p)) return igemm_halo_launch(p, stream);
+  if (igemm_stem_matches(p)) return igemm_stem_launch(p, stream);
 
   IgemmKParams kp{};
   igemm_choose_box(p.o_N, p.OH, p.OW, &kp.bn, &kp.bh, &kp.bw);

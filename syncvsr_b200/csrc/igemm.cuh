@@ -64,6 +64,12 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
 bool igemm_halo_matches(const IgemmProblem& p);
 int igemm_halo_launch(const IgemmProblem& p, cudaStream_t stream);
 
+// igemm_stem.cu: temporal-halo kernel for the 3-D conv stem's 5-tap / 64 -> 64 column contraction over [clips, frames,
+// pixels, 64] patch rows (one activation load per 8-frame x 16-pixel tile, resident weights); igemm_launch() dispatches
+// to it when igemm_stem_matches() (SVSR_STEM_HALO=0 in the environment keeps the generic kernel).
+bool igemm_stem_matches(const IgemmProblem& p);
+int igemm_stem_launch(const IgemmProblem& p, cudaStream_t stream);
+
 // Chooses the pixel box (bn, bh, bw) with bn*bh*bw <= 128 that wastes the fewest MMA rows.
 void igemm_choose_box(int o_N, int OH, int OW, int* bn, int* bh, int* bw);
 

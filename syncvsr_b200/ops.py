@@ -309,6 +309,21 @@ def conv2d_fprop_generic(x: torch.Tensor, w_packed: torch.Tensor, taps, out_dtyp
     return y
 
 
+def conv_taps_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, taps):
+    """conv2d_fprop_generic with bf16 output + fused per-channel (sum, sum of squares): returns (y, stats fp64 [2, Cout])."""
+    _req(x, torch.bfloat16, "x"), _req(w_packed, torch.bfloat16, "w_packed")
+    N, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    n = len(taps)
+    dh = (C.c_int * n)(*[int(t[0]) for t in taps])
+    dw = (C.c_int * n)(*[int(t[1]) for t in taps])
+    y = torch.empty(N, H, W, Cout, device=x.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2, Cout, device=x.device, dtype=torch.float64)
+    check(lib().svsr_conv_taps_fprop_bnstats(ptr(x), ptr(w_packed), ptr(y), ptr(stats), _i(N), _i(H), _i(W), _i(Cin),
+                                             _i(Cout), _i(n), dh, dw, stream_ptr()), "svsr_conv_taps_fprop_bnstats")
+    return y, stats
+
+
 def conv2d_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, R: int, S: int, stride: int, pad: int):
     """conv fprop + fused per-channel (sum, sum of squares) of the output; returns (y bf16, stats fp64 [2, Cout])."""
     _req(x, torch.bfloat16, "x"), _req(w_packed, torch.bfloat16, "w_packed")

@@ -75,9 +75,21 @@ class DataParallelStep:
     """zero_grad -> forward -> backward -> all-reduce(SUM) of the flat gradient arena -> fused clip+AdamW.
 
     The native forward/backward are called directly (no autograd graph); the reference-facing
-    `module(...)`/`loss.backward()` API is equivalent and is what the parity tests use."""
+    `module(...)`/`loss.backward()` API is equivalent and is what the parity tests use.
 
-    def __init__(self, module: TransformerLightningModule, optimizer: FusedAdamW, group=None):
+    graph=True: zero_grad + weight repack + forward + backward (~470 launches on two streams) are captured ONCE per
+    set of input buffers into a CUDA graph and replayed; on N > 1 ranks they are two graphs (heads + encoder | trunk +
+    stem) so that the first all-reduce still overlaps the trunk backward. Only a step whose launch sequence is
+    the same every time can be replayed: a module with layer_dropout or any dropout probability > 0 (per-step host
+    RNG: skipped sublayers, mask seeds are kernel arguments) keeps launching kernel by kernel.
+    high_priority=True: the step's main stream is a high-priority stream, so that whenever an SM frees up the
+    critical chain (forward, input gradients, BatchNorm backward) is scheduled before the weight-gradient kernels
+    the engine runs beside it on its own (default-priority) stream."""
+
+    MAX_GRAPH_SETS = 4
+
+    def __init__(self, module: TransformerLightningModule, optimizer: FusedAdamW, group=None, graph: bool = False,
+                 high_priority: bool = False, staged: Optional[bool] = None):
         self.module, self.opt, self.group = module, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         sch = dict(_cfg_get(module.config, "optim.scheduler", {}) or {})
@@ -87,26 +99,119 @@ class DataParallelStep:
         a, b = C.c_int64(), C.c_int64()
         check(lib().svsr_lrw_early_grad_region(module._h, C.byref(a), C.byref(b)), "svsr_lrw_early_grad_region")
         self._early = (int(a.value), int(b.value))
+        self.graph = bool(graph)
+        self.staged = (self.world > 1) if staged is None else bool(staged)
+        self._hi = torch.cuda.Stream(device=module.flat_params.device, priority=-1) if high_priority else None
+        self._graphs: Dict[tuple, dict] = {}
+        self._static_inputs = None  # used once more than MAX_GRAPH_SETS distinct input buffer sets have been seen
+        self.graph_launches = 0     # kernels launched by graph replays (the library's counter only sees captures)
+        self.graph_replays = 0
+        lib().svsr_launch_count.restype = C.c_longlong
+
+    # ---- the three pieces of a step; `stage` as in svsr_lrw_backward_stage (-1 = whole backward) ----
+    def _forward(self, batch):
+        self.opt.zero_grad()
+        with torch.no_grad():
+            return self.module(*batch)
+
+    def _backward(self, stage: int) -> None:
+        m = self.module
+        if stage < 0:
+            check(lib().svsr_lrw_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrw_backward")
+        else:
+            check(lib().svsr_lrw_backward_stage(m._h, C.c_void_p(0), C.c_int(stage), m._stream()),
+                  f"backward stage {stage}")
+
+    def _reduce_early(self):
+        g, (a, b) = self.module.flat_grads, self._early
+        return [dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+
+    def _reduce_late(self):
+        g, (a, b) = self.module.flat_grads, self._early
+        return [dist.all_reduce(g[:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True),
+                dist.all_reduce(g[b:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+
+    def _replayable(self) -> bool:
+        m = self.module
+        return (self.graph and m.training and not m.hf and m.layer_dropout == 0.0 and m.ff_dropout == 0.0
+                and m.emb_dropout == 0.0 and m.attn_dropout == 0.0 and m._shape_key is not None)
+
+    def _capture(self, batch) -> dict:
+        m = self.module
+        cap_stream = self._hi if self._hi is not None else torch.cuda.Stream(device=m.flat_params.device)
+        cap_stream.wait_stream(torch.cuda.current_stream())
+        n0 = lib().svsr_launch_count()
+        graphs, pool = [], None
+        m._weights_dirty = True  # the repack belongs to every replay: the optimizer has always just run
+        for part in ((0, 1) if self.staged else (-1,)):
+            g = torch.cuda.CUDAGraph()
+            # thread_local: NCCL's watchdog thread polls events while we capture
+            with torch.cuda.graph(g, pool=pool, stream=cap_stream, capture_error_mode="thread_local"):
+                if part <= 0:
+                    metrics = self._forward(batch)
+                self._backward(part)
+            pool = g.pool()
+            graphs.append(g)
+        return {"graphs": graphs, "metrics": metrics, "batch": batch,
+                "launches": int(lib().svsr_launch_count() - n0)}
+
+    def _graph_entry(self, batch):
+        key = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in batch if isinstance(t, torch.Tensor))
+        ent = self._graphs.get(key)
+        if ent is None and self._static_inputs is None and len(self._graphs) >= self.MAX_GRAPH_SETS:
+            # the caller hands over fresh tensors every step: copy them into one static set from now on
+            self._static_inputs = tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in batch)
+        if self._static_inputs is not None and ent is None:
+            for d, src in zip(self._static_inputs, batch):
+                if isinstance(d, torch.Tensor):
+                    d.copy_(src, non_blocking=True)
+            batch = self._static_inputs
+            key = ("static",)
+            ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(batch)
+        return ent
 
     def __call__(self, videos, audio_tokens, labels, word_mask=None) -> Dict[str, torch.Tensor]:
         m = self.module
-        self.opt.zero_grad()
-        with torch.no_grad():
-            metrics = m(videos, audio_tokens, labels, word_mask)
-        if self.world == 1:
-            check(lib().svsr_lrw_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrw_backward")
+        batch = (videos, audio_tokens, labels, word_mask)
+        cur = torch.cuda.current_stream()
+        if self._replayable() and m._shape_key == (videos.shape[0], videos.shape[2], videos.shape[3], videos.shape[4]):
+            ent = self._graph_entry(batch)
+            graphs = ent["graphs"]
+            graphs[0].replay()
+            if self.staged:
+                hs = self._reduce_early() if self.world > 1 else []
+                graphs[1].replay()
+                hs += self._reduce_late() if self.world > 1 else []
+                for h in hs:
+                    h.wait()
+            m._weights_dirty = False  # (num_batches_tracked += 1 is a device op: it is part of the graph)
+            self.graph_replays += 1
+            self.graph_launches += ent["launches"]
+            metrics = ent["metrics"]
         else:
-            # overlap: the encoder/head gradients (~160 MB, finished first) are all-reduced on NCCL's stream while
-            # the ResNet trunk + stem backward still runs; the remaining ~45 MB follow at the end.
-            g = m.flat_grads
-            a, b = self._early
-            check(lib().svsr_lrw_backward_stage(m._h, C.c_void_p(0), C.c_int(0), m._stream()), "backward stage 0")
-            h1 = dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            check(lib().svsr_lrw_backward_stage(m._h, C.c_void_p(0), C.c_int(1), m._stream()), "backward stage 1")
-            h2 = dist.all_reduce(g[:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            h3 = dist.all_reduce(g[b:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            for h in (h1, h2, h3):
-                h.wait()
+            # kernel-by-kernel launches (also the first step of a module: the engine is built and bound here)
+            if self._hi is not None:
+                self._hi.wait_stream(cur)
+                torch.cuda.set_stream(self._hi)
+            try:
+                metrics = self._forward(batch)
+                if not self.staged:
+                    self._backward(-1)
+                else:
+                    # overlap: the encoder/head gradients (~160 MB, finished first) are all-reduced on NCCL's stream
+                    # while the ResNet trunk + stem backward still runs; the remaining ~45 MB follow at the end.
+                    self._backward(0)
+                    hs = self._reduce_early() if self.world > 1 else []
+                    self._backward(1)
+                    hs += self._reduce_late() if self.world > 1 else []
+                    for h in hs:
+                        h.wait()
+            finally:
+                if self._hi is not None:
+                    torch.cuda.set_stream(cur)
+                    cur.wait_stream(self._hi)
         self.global_step += 1
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
         self.opt.step(lr=lr, grad_div=float(self.world))

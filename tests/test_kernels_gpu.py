@@ -114,6 +114,34 @@ def test_halo_conv_matches_generic_igemm(ops, monkeypatch, N, H, W):
     assert rel(res["1"][1][0], yd.sum((0, 1, 2))) < 1e-4 and rel(res["1"][1][1], (yd ** 2).sum((0, 1, 2))) < 1e-4
 
 
+@pytest.mark.parametrize("N,T,W", [(2, 29, 1936), (1, 8, 16), (3, 5, 48), (1, 1, 32), (2, 150, 64), (5, 21, 2304)])
+def test_stem_temporal_halo_conv_matches_generic_igemm(ops, monkeypatch, N, T, W):
+    """igemm_stem.cu (one activation load per 8-frame x 16-pixel tile, resident weights) against the tap-by-tap kernel
+    it replaces for the stem's temporal 5-tap contraction (lightning.py:50), and against fp32 PyTorch: output and fused
+    BatchNorm statistics; clip lengths that are not multiples of the 8-frame tile, a single frame, LRS length."""
+    x, w = randn(N, T, W, 64, seed=41), randn(64, 64, 5, 1, seed=42, scale=0.05)
+    wp = ops.pack_conv_weight(w)  # [64, 5*64], K = kt*64 + c
+    taps = [(kt - 2, 0) for kt in range(5)]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVSR_STEM_HALO", mode)
+        y, stats = ops.conv_taps_fprop_bnstats(x, wp, taps)
+        torch.cuda.synchronize()
+        res[mode] = (y.clone(), stats.clone())
+    assert torch.equal(res["1"][0], res["0"][0])  # same MMA sequence per output -> identical bf16 results
+    assert rel(res["1"][1], res["0"][1]) < 1e-6
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=(2, 0)).permute(0, 2, 3, 1)
+    assert rel(res["1"][0], ref) < BF16_TOL
+    yd = res["1"][0].double()
+    assert rel(res["1"][1][0], yd.sum((0, 1, 2))) < 1e-4 and rel(res["1"][1][1], (yd ** 2).sum((0, 1, 2))) < 1e-4
+    # a width that is not a multiple of the 16-pixel tile stays on the generic kernel
+    x2 = randn(1, 6, 40, 64, seed=43)
+    monkeypatch.setenv("SVSR_STEM_HALO", "1")
+    y2, _ = ops.conv_taps_fprop_bnstats(x2, wp, taps)
+    ref2 = F.conv2d(x2.float().permute(0, 3, 1, 2), w.float(), padding=(2, 0)).permute(0, 2, 3, 1)
+    assert rel(y2, ref2) < BF16_TOL
+
+
 @pytest.mark.parametrize("N,H,W", [(40, 22, 22), (3, 24, 24), (5, 7, 25), (2, 1, 2), (9, 13, 5), (300, 22, 22)])
 def test_halo_wgrad_matches_generic_and_autograd(ops, monkeypatch, N, H, W):
     """wgrad_halo.cu (one activation + one gradient load per pixel tile, tap pairs as descriptor offsets) against the

@@ -321,6 +321,58 @@ def test_prefetched_host_pipeline_equals_direct_steps(Module):
     assert rel(p1, p0) < 1e-5
 
 
+@pytest.mark.parametrize("staged,priority", [(False, False), (True, True)])
+def test_graph_replayed_step_equals_kernel_by_kernel_step(Module, staged, priority):
+    """DataParallelStep(graph=True) replays zero_grad + repack + forward + backward from a CUDA graph (one graph, or
+    the two all-reduce-overlap stages); losses and the parameter trajectory over 5 steps on two alternating buffer
+    sets must equal the kernel-by-kernel step (split-K `red.add` order is the only run-to-run freedom), BatchNorm's
+    num_batches_tracked included. More buffer sets than MAX_GRAPH_SETS switch to one static input set."""
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW
+
+    def run(graph, fresh_inputs=False):
+        torch.manual_seed(11)
+        m = Module(make_cfg(depth=2)).train()
+        step = DataParallelStep(m, FusedAdamW.from_config(m), graph=graph, high_priority=priority and graph,
+                                staged=staged)
+        batches = [tuple(t.cuda() for t in O.make_inputs(700 + i, 2)) for i in range(2)]
+        losses = []
+        n = 8 if fresh_inputs else 5
+        for i in range(n):
+            b = tuple(t.clone() for t in batches[i % 2]) if fresh_inputs else batches[i % 2]
+            if fresh_inputs:
+                step._keep = getattr(step, "_keep", []) + [b]  # distinct addresses: nothing is freed and reused
+            losses.append(float(step(*b)["loss_total"]))
+        torch.cuda.synchronize()
+        step.last_grads = m.flat_grads.clone()  # of the last step (the optimizer leaves the arena in place)
+        return losses, m.flat_params.clone(), m._nbt.clone(), step
+
+    l0, p0, n0, s0 = run(False)
+    l1, p1, n1, s1 = run(True)
+    assert rel(s1.last_grads, s0.last_grads) < 5e-2
+    assert s1.graph_replays == 4 and len(s1._graphs) == 2 and s1.graph_launches > 4 * 100  # step 0 builds the engine
+    assert l1 == pytest.approx(l0, rel=2e-4)
+    assert rel(p1, p0) < 1e-5
+    assert torch.equal(n0, n1)
+    if not staged:
+        l2, p2, n2, s2 = run(True, fresh_inputs=True)
+        l3, p3, n3, _ = run(False, fresh_inputs=True)
+        assert s2._static_inputs is not None and s2.graph_replays == 7
+        assert l2 == pytest.approx(l3, rel=2e-4) and rel(p2, p3) < 1e-5 and torch.equal(n2, n3)
+
+
+def test_step_with_dropout_is_never_replayed_from_a_graph(Module):
+    """A module whose launch sequence depends on per-step host RNG (layer_dropout, dropout seeds) keeps launching kernel
+    by kernel even when graph=True."""
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW
+
+    m = Module(make_cfg(depth=2, layer_dropout=0.2, ff_dropout=0.3)).train()
+    step = DataParallelStep(m, FusedAdamW.from_config(m), graph=True)
+    b = tuple(t.cuda() for t in O.make_inputs(710, 2))
+    for _ in range(3):
+        out = step(*b)
+    assert step.graph_replays == 0 and torch.isfinite(out["loss_total"])
+
+
 @pytest.mark.parametrize("B,T", [(1, 29), (3, 21), (5, 40)])
 def test_edge_geometries_batch_one_and_other_clip_lengths(Module, B, T):
     """The engine is rebuilt per clip geometry: a single clip, and clip lengths other than LRW's 29 frames."""
