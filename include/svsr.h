@@ -85,6 +85,13 @@ int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resi
 int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                       int stride, int pad, void* stream);
 
+/* Weight gradient of svsr_conv_taps_fprop: dw[ntaps*Cin, Cout] (fp32, += accumulate), row t*Cin+ci, column co
+ * = sum over pixels of x[n, h+dh[t], w+dw[t], ci] * dy[n, h, w, co]. The stem's Conv3d backward-weight
+ * (lightning.py:50) runs through this with taps (kt-2, 0) over the [T, OH*OW] patch image; that shape (5 taps, 64 -> 64
+ * columns, W % 16 == 0) is served by the temporal-halo kernel (csrc/wgrad_stem.cu). */
+int svsr_conv_taps_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int ntaps,
+                         const int* tap_dh, const int* tap_dw, void* stream);
+
 /* dw[N,K] (fp32, pitch ldw, += accumulate) = dy[M,N]^T . x[M,K]; dy, x bf16 with pitches ldy, ldx.
  * Replaces autograd's Linear backward-weight. N % 64 == 0. */
 int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,

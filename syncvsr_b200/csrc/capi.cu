@@ -159,6 +159,19 @@ int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   return wgrad_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int svsr_conv_taps_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int ntaps,
+                         const int* tap_dh, const int* tap_dw, void* stream) {
+  SVSR_REQUIRE(ntaps >= 1 && ntaps <= WGRAD_MAX_TAPS && tap_dh && tap_dw, "conv_taps_wgrad: bad tap list");
+  WgradProblem p;
+  p.a = x, p.a_N = N, p.a_H = H, p.a_W = W, p.a_C = Cin, p.a_coff = 0, p.a_cin = Cin, p.a_stride = 1;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) p.tap_dh[t] = tap_dh[t], p.tap_dw[t] = tap_dw[t];
+  p.b = dy, p.b_C = Cout, p.b_coff = 0, p.n_cols = Cout;
+  p.k_N = N, p.k_H = H, p.k_W = W;
+  p.out = dw, p.ldo = Cout;
+  return wgrad_launch(p, static_cast<cudaStream_t>(stream));
+}
+
 int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, int ldw, int M, int N, int K,
                     void* stream) {
   SVSR_REQUIRE(N % 64 == 0, "gemm_wgrad: N=%d must be a multiple of 64", N);

@@ -205,6 +205,7 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
   SVSR_REQUIRE(p.a_stride == 1 || p.a_stride == 2, "wgrad: stride must be 1 or 2");
   SVSR_REQUIRE(p.n_cols > 0 && p.ldo >= p.n_cols, "wgrad: bad output geometry");
   if (wgrad_halo_matches(p)) return wgrad_halo_launch(p, stream);
+  if (wgrad_stem_matches(p)) return wgrad_stem_launch(p, stream);
 
   WgradKParams kp{};
   igemm_choose_box(p.k_N, p.k_H, p.k_W, &kp.bn, &kp.bh, &kp.bw);

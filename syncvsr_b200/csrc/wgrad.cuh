@@ -36,4 +36,9 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream);
 bool wgrad_halo_matches(const WgradProblem& p);
 int wgrad_halo_launch(const WgradProblem& p, cudaStream_t stream);
 
+// wgrad_stem.cu: temporal-halo kernel for the stem's 5-tap / 64 -> 64 column weight gradient over [clips, frames,
+// pixels, 64] rows; wgrad_launch() dispatches to it when wgrad_stem_matches() (SVSR_STEM_HALO=0 keeps the generic kernel).
+bool wgrad_stem_matches(const WgradProblem& p);
+int wgrad_stem_launch(const WgradProblem& p, cudaStream_t stream);
+
 }  // namespace svsr

@@ -324,6 +324,21 @@ def conv_taps_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, taps):
     return y, stats
 
 
+def conv_taps_wgrad(x: torch.Tensor, dy: torch.Tensor, taps, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Weight gradient of conv2d_fprop_generic: fp32 [len(taps)*Cin, Cout], row t*Cin+ci; accumulates into `out`."""
+    _req(x, torch.bfloat16, "x"), _req(dy, torch.bfloat16, "dy")
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    n = len(taps)
+    dh = (C.c_int * n)(*[int(t[0]) for t in taps])
+    dw = (C.c_int * n)(*[int(t[1]) for t in taps])
+    if out is None:
+        out = torch.zeros(n * Cin, Cout, device=x.device, dtype=torch.float32)
+    check(lib().svsr_conv_taps_wgrad(ptr(x), ptr(dy), ptr(out), _i(N), _i(H), _i(W), _i(Cin), _i(Cout), _i(n), dh, dw,
+                                     stream_ptr()), "svsr_conv_taps_wgrad")
+    return out
+
+
 def conv2d_fprop_bnstats(x: torch.Tensor, w_packed: torch.Tensor, R: int, S: int, stride: int, pad: int):
     """conv fprop + fused per-channel (sum, sum of squares) of the output; returns (y bf16, stats fp64 [2, Cout])."""
     _req(x, torch.bfloat16, "x"), _req(w_packed, torch.bfloat16, "w_packed")

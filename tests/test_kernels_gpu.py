@@ -159,6 +159,25 @@ def test_halo_wgrad_matches_generic_and_autograd(ops, monkeypatch, N, H, W):
     assert rel(ops.unpack_conv_wgrad(res["1"] - base, 64, 3, 3), wt.grad) < F32_TOL
 
 
+@pytest.mark.parametrize("N,T,W", [(2, 29, 1936), (1, 8, 16), (3, 5, 48), (1, 1, 32), (2, 150, 64), (40, 29, 1936)])
+def test_stem_temporal_halo_wgrad_matches_generic_and_autograd(ops, monkeypatch, N, T, W):
+    """wgrad_stem.cu (one patch tile + one gradient tile per 8-frame x 16-pixel tile, tap pairs as descriptor offsets)
+    against the generic split-K kernel and fp32 autograd; accumulation into a non-zero gradient buffer."""
+    x, dy = randn(N, T, W, 64, seed=51), randn(N, T, W, 64, seed=52, scale=0.1)
+    taps = [(kt - 2, 0) for kt in range(5)]
+    base = torch.randn(5 * 64, 64, device="cuda")
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVSR_STEM_HALO", mode)
+        res[mode] = ops.conv_taps_wgrad(x, dy, taps, out=base.clone())
+        torch.cuda.synchronize()
+    assert rel(res["1"] - base, res["0"] - base) < 2e-5  # same products, different fp32 summation order
+    xt = x.float().permute(0, 3, 1, 2)
+    wt = torch.zeros(64, 64, 5, 1, device="cuda", requires_grad=True)
+    F.conv2d(xt, wt, padding=(2, 0)).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(ops.unpack_conv_wgrad(res["1"] - base, 64, 5, 1), wt.grad) < F32_TOL
+
+
 def test_conv_dgrad_accumulates_residual_in_place(ops):
     dy, w = randn(4, 11, 11, 128, seed=7), randn(128, 64, 3, 3, seed=8, scale=0.05)
     base = randn(4, 22, 22, 64, seed=9)
