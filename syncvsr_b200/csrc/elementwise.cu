@@ -382,12 +382,14 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
     const unsigned ow = pix % (unsigned)OW, t1 = pix / (unsigned)OW;
     const unsigned oh = t1 % (unsigned)OH, n = t1 / (unsigned)OH;
     // GELU (and Swish) are unimodal -- decreasing below z ~ -0.75 (-1.278), increasing above, negative for z < 0 -- so the
-    // window maximum of act(z) is act(max z) whenever max z >= 0: one activation per output instead of nine, and only the
-    // running maximum to track. The rare all-negative window takes the two-candidate path (largest or smallest z).
-    float zmax[8];
-    int imax[8];
+    // window maximum of act(z) is act(max z) whenever max z >= 0: one activation per output instead of nine. An
+    // all-negative window has two candidates (its largest or its smallest z).
+    // Both extrema are tracked in the ONE pass over the window: nearly every warp holds at least one all-negative
+    // (channel, window) pair, so a second pass over the nine pixels used to run warp-wide.
+    float zmax[8], zmin[8];
+    int imax[8], imin[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, imax[k] = 0;
+    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, imax[k] = 0, zmin[k] = INFINITY, imin[k] = 0;
     const __nv_bfloat16* img = y0 + (size_t)n * IH * IW * C + g * 8;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -402,38 +404,15 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
         for (int k = 0; k < 8; ++k) {
           const float z = v.v[k] * sc.v[k] + sh.v[k];
           if (z > zmax[k]) zmax[k] = z, imax[k] = kh * 3 + kw;
+          if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
         }
       }
     }
     float best[8];
-    bool any_neg = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       best[k] = swish ? swish_f(zmax[k]) : gelu_f(zmax[k]);
-      any_neg |= zmax[k] < 0.f;
-    }
-    if (any_neg) {
-      float zmin[8];
-      int imin[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) zmin[k] = INFINITY, imin[k] = 0;
-      for (int kh = 0; kh < 3; ++kh) {
-        const int ih = 2 * (int)oh + kh - 1;
-        if (ih < 0 || ih >= IH) continue;
-        for (int kw = 0; kw < 3; ++kw) {
-          const int iw = 2 * (int)ow + kw - 1;
-          if (iw < 0 || iw >= IW) continue;
-          const F8 v = ld8(img + (size_t)(ih * IW + iw) * C);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float z = v.v[k] * sc.v[k] + sh.v[k];
-            if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (!(zmax[k] < 0.f)) continue;
+      if (zmax[k] < 0.f) {  // all-negative window: the largest or the smallest z carries the maximum
         const float bmin = swish ? swish_f(zmin[k]) : gelu_f(zmin[k]);
         // first maximum wins (torch max_pool semantics): on a tie the earlier window position
         if ((bmin > best[k]) || (bmin == best[k] && imin[k] < imax[k])) best[k] = bmin, imax[k] = imin[k];

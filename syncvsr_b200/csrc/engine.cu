@@ -57,6 +57,7 @@ struct LrwEngine : EngineBase {
   size_t pack_jobs;  // device table for the single-launch weight repack
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
+  bool pack_deferred = false;  // svsr_lrw_pack_weights() was called: the repack is enqueued by the next forward
   size_t dx, dxb[3], t_du, t_dh[2], t_dyn, t_do, t_dqkv[2];
   // parity-mode (fp32 activations, split-bf16 operands) scratch layout: offsets into a caller-provided buffer
   size_t p_patches, p_y0, p_act[6], p_s3, p_w3, p_xs[2], p_xn, p_qkv, p_o, p_h, p_u, p_lc, p_lf, p_bytes = 0;
@@ -284,6 +285,27 @@ static int engine_pack(LrwEngine& e, cudaStream_t s) {
   return pack_all_weights(e.ws<PackJob>(e.pack_jobs), e.n_pack_jobs, s);
 }
 
+// The 253 MB -> 2 x 126 MB repack (~270 us) is only needed from resnet.layer1 on: job 0 (the stem's [64, 320] operand)
+// goes on the caller's stream, the rest on the side stream beside the stem's patch gather / temporal conv /
+// BN+GELU+pool (frontend_forward joins before the first BasicBlock). SVSR_PACK_OVERLAP=0 or SVSR_SINGLE_STREAM=1 keep it
+// on one stream. Fork and join are enqueued inside ONE forward call, so a stream capture always holds both.
+static int engine_pack_deferred(LrwEngine& e, cudaStream_t s, bool may_overlap) {
+  if (!e.pack_deferred) return SVSR_OK;
+  e.pack_deferred = false;
+  const char* ov = getenv("SVSR_PACK_OVERLAP");
+  const char* one = getenv("SVSR_SINGLE_STREAM");
+  if (!may_overlap || !e.pack_table_ready || e.n_pack_jobs < 2 || (ov && ov[0] == '0') || (one && one[0] == '1'))
+    return engine_pack(e, s);
+  const PackJob* jobs = e.ws<PackJob>(e.pack_jobs);
+  RC(pack_all_weights(jobs, 1, s));
+  SVSR_CHECK_CUDA(cudaEventRecord(e.ev_pack_fork, s));
+  SVSR_CHECK_CUDA(cudaStreamWaitEvent(e.side, e.ev_pack_fork, 0));
+  RC(pack_all_weights(jobs + 1, e.n_pack_jobs - 1, e.side));
+  SVSR_CHECK_CUDA(cudaEventRecord(e.ev_pack_done, e.side));
+  e.pack_pending = true;
+  return SVSR_OK;
+}
+
 // Linear forward / input gradient / weight gradient on the (possibly K- or N-padded) bf16 operand copies
 static int lw_fwd(const LrwEngine& e, const bf16* x, int ldx, int M, const LinRef& l, void* out, int ldc, int out_fp32,
                   const void* resid, cudaStream_t s) {
@@ -443,6 +465,7 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   const svsr_lrw_config& c = e.cfg;
   const int D = e.D, Dp = e.Dp, inner = c.heads * 64, Fp = e.Fp;
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));  // acc + bad_token
+  RC(engine_pack_deferred(e, s, true));
   // ---- stem3d + resnet.layer1-4 (lightning.py:49-54,112-117) ----
   const bf16* x = nullptr;
   RC(frontend_forward(e, e.fe, videos, train, &x, s));
@@ -557,6 +580,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
                                   uint32_t skip_mask, float* metrics, cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
   SVSR_REQUIRE(!e.padded && c.enc_type == 0, "lrw: the parity-mode forward supports the dim-512 x-transformers config only");
+  RC(engine_pack_deferred(e, s, false));
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.fe.stats_arena), 0, e.fe.stats_arena_bytes, s));
@@ -808,12 +832,15 @@ int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* wo
   SVSR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)params & 15) == 0 && ((uintptr_t)grads & 15) == 0,
                "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
   e->pack_table_ready = false;
+  e->pack_deferred = false, e->pack_pending = false;
   return engine_base_bind(*e, params, grads, buffers, workspace);
 }
 int svsr_lrw_pack_weights(void* h, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
-  return engine_pack(*e, static_cast<cudaStream_t>(stream));
+  if (!e->pack_table_ready) return engine_pack(*e, static_cast<cudaStream_t>(stream));  // first call of a binding
+  e->pack_deferred = true;  // enqueued by the next forward, overlapped with its stem (engine_pack_deferred)
+  return SVSR_OK;
 }
 int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
                      const float* soft_labels, const float* word_mask, int train, uint32_t skip_mask,

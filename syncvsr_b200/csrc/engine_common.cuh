@@ -97,6 +97,9 @@ struct EngineBase {
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int fork_idx = 0;
+  // weight repack left running on the side stream while the stem computes (engine.cu: engine_pack_overlapped)
+  cudaEvent_t ev_pack_fork = nullptr, ev_pack_done = nullptr;
+  bool pack_pending = false;
 
   template <class T>
   T* ws(size_t off) const {
@@ -277,6 +280,15 @@ static int bn_bwd(const EngineBase& e, const bf16* dout, const bf16* relu_ref, c
 // tensors the chain has finished (fork event) and the chain never overwrites a tensor the side stream may still be
 // reading: the hazard buffers (dc*, dxb, dh, dqkv) are double buffered and the chain waits for the side stream's
 // unit k-2 before starting unit k (bounded lag). HBM-bound BN kernels thereby overlap tensor-bound wgrad kernels.
+// The caller's stream waits for a repack that was left running on the side stream (no-op otherwise).
+static int pack_join(EngineBase& e, cudaStream_t s) {
+  if (e.pack_pending) {
+    SVSR_CHECK_CUDA(cudaStreamWaitEvent(s, e.ev_pack_done, 0));
+    e.pack_pending = false;
+  }
+  return SVSR_OK;
+}
+
 struct SideQueue {
   EngineBase& e;
   cudaStream_t s;
@@ -422,6 +434,7 @@ static int frontend_forward(EngineBase& e, Frontend& f, const float* videos, int
   RC(stem_bn_gelu_pool(e.ws<bf16>(f.y0), e.ws<float>(f.stem_bn.coef), e.ws<bf16>(f.x1), e.ws<uint8_t>(f.argmax), e.N,
                        f.H0, f.H0, s, f.swish));
   // ---- the eight BasicBlocks ----
+  RC(pack_join(e, s));  // trunk / encoder operand copies repacked beside the stem
   const bf16* x = e.ws<bf16>(f.x1);
   for (auto& blk : f.blocks) {
     const long long rows = (long long)e.N * blk.Hout * blk.Hout;
@@ -529,6 +542,8 @@ static int engine_base_bind(EngineBase& e, float* params, float* grads, float* b
       SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e.ev_fork[i], cudaEventDisableTiming));
       SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e.ev_done[i], cudaEventDisableTiming));
     }
+    SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e.ev_pack_fork, cudaEventDisableTiming));
+    SVSR_CHECK_CUDA(cudaEventCreateWithFlags(&e.ev_pack_done, cudaEventDisableTiming));
   }
   return SVSR_OK;
 }
@@ -536,6 +551,7 @@ static void engine_base_destroy(EngineBase& e) {
   if (e.side) {
     cudaStreamDestroy(e.side);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(e.ev_fork[i]), cudaEventDestroy(e.ev_done[i]);
+    cudaEventDestroy(e.ev_pack_fork), cudaEventDestroy(e.ev_pack_done);
     e.side = nullptr;
   }
 }
