@@ -188,8 +188,8 @@ int svsr_lrw_param_info(void* handle, int i, const char** name, int* ndim, int64
 int svsr_lrw_buffer_info(void* handle, int i, const char** name, int* ndim, int64_t* shape, int64_t* offset);
 int svsr_lrw_bind(void* handle, float* params, float* grads, float* buffers, void* workspace, int64_t workspace_bytes);
 /* fp32 master weights -> bf16 tensor-core operand layouts; call after every optimizer step. Apart from the first call
- * of a binding the repack is enqueued by the NEXT forward call (on its stream): the stem's operand first, the rest on
- * the engine's side stream beside the stem kernels (SVSR_PACK_OVERLAP=0: everything on the caller's stream). */
+ * of a binding the repack is enqueued by the NEXT forward call, on its stream (SVSR_PACK_OVERLAP=1: the stem's operand
+ * first, the rest on the engine's side stream beside the stem kernels -- measured neutral, off by default). */
 int svsr_lrw_pack_weights(void* handle, void* stream);
 /* videos fp32 [B,1,T,H,W]; tokens int64 [B, >=T*A, G] with batch stride tok_stride_b (elements); labels int64 [B]
  * or soft_labels fp32 [B,num_labels] (CutMix); word_mask fp32 [B,T] when dim = 513 (data.use_word_boundary,

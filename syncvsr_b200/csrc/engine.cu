@@ -285,16 +285,18 @@ static int engine_pack(LrwEngine& e, cudaStream_t s) {
   return pack_all_weights(e.ws<PackJob>(e.pack_jobs), e.n_pack_jobs, s);
 }
 
-// The 253 MB -> 2 x 126 MB repack (~270 us) is only needed from resnet.layer1 on: job 0 (the stem's [64, 320] operand)
-// goes on the caller's stream, the rest on the side stream beside the stem's patch gather / temporal conv /
-// BN+GELU+pool (frontend_forward joins before the first BasicBlock). SVSR_PACK_OVERLAP=0 or SVSR_SINGLE_STREAM=1 keep it
-// on one stream. Fork and join are enqueued inside ONE forward call, so a stream capture always holds both.
+// SVSR_PACK_OVERLAP=1 (off by default): the 253 MB -> 2 x 126 MB repack (~270 us) is only needed from resnet.layer1
+// on, so job 0 (the stem's [64, 320] operand) goes on the caller's stream and the rest on the side stream beside the
+// stem's patch gather / temporal conv / BN+GELU+pool (frontend_forward joins before the first BasicBlock). Measured: no
+// gain (11.68 vs 11.65 ms per step) -- the stem kernels are HBM-bound themselves, the repack only competes with them
+// for the same bandwidth -- hence opt-in. Fork and join are enqueued inside ONE forward call, so a stream capture always
+// holds both.
 static int engine_pack_deferred(LrwEngine& e, cudaStream_t s, bool may_overlap) {
   if (!e.pack_deferred) return SVSR_OK;
   e.pack_deferred = false;
   const char* ov = getenv("SVSR_PACK_OVERLAP");
   const char* one = getenv("SVSR_SINGLE_STREAM");
-  if (!may_overlap || !e.pack_table_ready || e.n_pack_jobs < 2 || (ov && ov[0] == '0') || (one && one[0] == '1'))
+  if (!may_overlap || !e.pack_table_ready || e.n_pack_jobs < 2 || !(ov && ov[0] == '1') || (one && one[0] == '1'))
     return engine_pack(e, s);
   const PackJob* jobs = e.ws<PackJob>(e.pack_jobs);
   RC(pack_all_weights(jobs, 1, s));
