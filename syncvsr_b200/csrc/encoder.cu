@@ -129,26 +129,40 @@ constexpr int AT_MAXN = 64;
 constexpr int AT_D = 64;
 constexpr int AT_LD = 65;  // padded row pitch (floats) against bank conflicts
 
-__device__ __forceinline__ void load_rot(const __nv_bfloat16* __restrict__ src, int ld, const float* __restrict__ rot,
-                                         float* dst, int n, bool rotate) {
-  // src points at token 0 of this (b, head, q|k|v) slice; rows are `ld` elements apart
+// q, k, v (and dO in backward) of one (batch, head) in ONE pass: all global loads of a thread are in flight together and
+// the CTA synchronises twice in total, instead of one dependent global round trip + two barriers per tensor.
+__device__ __forceinline__ void load_qkv_rot(const __nv_bfloat16* __restrict__ base, int ld, int inner,
+                                             const __nv_bfloat16* __restrict__ dout, const float* __restrict__ rot,
+                                             float* sq, float* sk, float* sv, float* sdo, int n, bool rotary_v) {
   for (int i = threadIdx.x; i < n * 32; i += blockDim.x) {
     const int pos = i >> 5, d2 = (i & 31) * 2;
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + (long long)pos * ld + d2);
-    dst[pos * AT_LD + d2] = __low2float(v);
-    dst[pos * AT_LD + d2 + 1] = __high2float(v);
+    const __nv_bfloat16* src = base + (long long)pos * ld + d2;
+    const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(src);
+    const __nv_bfloat162 k = *reinterpret_cast<const __nv_bfloat162*>(src + inner);
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + 2 * inner);
+    __nv_bfloat162 g = q;
+    if (dout) g = *reinterpret_cast<const __nv_bfloat162*>(dout + (long long)pos * inner + d2);
+    const int o = pos * AT_LD + d2;
+    sq[o] = __low2float(q), sq[o + 1] = __high2float(q);
+    sk[o] = __low2float(k), sk[o + 1] = __high2float(k);
+    sv[o] = __low2float(v), sv[o + 1] = __high2float(v);
+    if (dout) sdo[o] = __low2float(g), sdo[o + 1] = __high2float(g);
   }
   __syncthreads();
-  if (rotate) {
-    for (int i = threadIdx.x; i < n * 16; i += blockDim.x) {
-      const int pos = i >> 4, f = i & 15;
-      const float c = rot[pos * 32 + f], s = rot[pos * 32 + 16 + f];
-      const float a = dst[pos * AT_LD + f], b = dst[pos * AT_LD + 16 + f];
-      dst[pos * AT_LD + f] = a * c - b * s;
-      dst[pos * AT_LD + 16 + f] = b * c + a * s;
+  for (int i = threadIdx.x; i < n * 16; i += blockDim.x) {
+    const int pos = i >> 4, f = i & 15;
+    const float c = rot[pos * 32 + f], s = rot[pos * 32 + 16 + f];
+    const int o = pos * AT_LD + f;
+    float a = sq[o], b = sq[o + 16];
+    sq[o] = a * c - b * s, sq[o + 16] = b * c + a * s;
+    a = sk[o], b = sk[o + 16];
+    sk[o] = a * c - b * s, sk[o + 16] = b * c + a * s;
+    if (rotary_v) {
+      a = sv[o], b = sv[o + 16];
+      sv[o] = a * c - b * s, sv[o + 16] = b * c + a * s;
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 // out[r][c] = scale * sum_d A[r][d] * B[c][d]  (both [n x 64] in smem): register tile of 2 rows x 4 columns per thread,
@@ -239,9 +253,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int inner = heads * AT_D, ld = 3 * inner;
   const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
-  load_rot(base, ld, rot, sq, n, true);
-  load_rot(base + inner, ld, rot, sk, n, true);
-  load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
+  load_qkv_rot(base, ld, inner, nullptr, rot, sq, sk, sv, nullptr, n, rotary_v != 0);
   mm_abt(sq, sk, sp, n, 0.125f);
   __syncthreads();
   softmax_rows(sp, n);
@@ -280,10 +292,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int inner = heads * AT_D, ld = 3 * inner;
   const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
-  load_rot(base, ld, rot, sq, n, true);
-  load_rot(base + inner, ld, rot, sk, n, true);
-  load_rot(base + 2 * inner, ld, rot, sv, n, rotary_v != 0);
-  load_rot(d_o + (long long)b * n * inner + h * AT_D, inner, rot, sdo, n, false);
+  load_qkv_rot(base, ld, inner, d_o + (long long)b * n * inner + h * AT_D, rot, sq, sk, sv, sdo, n, rotary_v != 0);
   mm_abt(sq, sk, sp, n, 0.125f);  // S
   mm_abt(sdo, sv, sds, n, 1.0f);  // dP = dO V'^T
   __syncthreads();
@@ -474,6 +483,74 @@ int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, in
   LAUNCH_CHECK();
   return SVSR_OK;
 }
+// D % 128 == 0 variant (the dim-512 stream): every lane owns NCH chunks of 4 consecutive columns, so a row is NCH
+// 16-byte loads per operand instead of 4 * NCH scalar ones, and the old dx values are fetched together with x / dy --
+// before the row reduction, not after it. The kernel is latency bound (one row per warp, ncu: 12 % warps active): what
+// it costs is the length of that dependent chain.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
+                       const float* __restrict__ inv_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb,
+                       float* __restrict__ dg, int M, int D, float eps, int norm_dim) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float4 gv[NCH], dgacc[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    gv[i] = *reinterpret_cast<const float4*>(g + 128 * i + 4 * lane);
+    dgacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = warp; row < M; row += nwarps) {
+    const long long base = (long long)row * D + 4 * lane;
+    float4 xv[NCH], dv[NCH], ov[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      xv[i] = *reinterpret_cast<const float4*>(x + base + 128 * i);
+      const uint2 d2 = *reinterpret_cast<const uint2*>(dy + base + 128 * i);
+      const float2 lo = unpack_bf16x2(d2.x), hi = unpack_bf16x2(d2.y);
+      dv[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      ov[i] = *reinterpret_cast<const float4*>(dx + base + 128 * i);
+    }
+    const float inv = inv_in[row];
+    const bool clamped = inv >= 1.0f / eps;  // norm <= eps: the scale is a constant there
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      t += dv[i].x * gv[i].x * xv[i].x + dv[i].y * gv[i].y * xv[i].y + dv[i].z * gv[i].z * xv[i].z +
+           dv[i].w * gv[i].w * xv[i].w;
+      dgacc[i].x += dv[i].x * xv[i].x * inv, dgacc[i].y += dv[i].y * xv[i].y * inv;
+      dgacc[i].z += dv[i].z * xv[i].z * inv, dgacc[i].w += dv[i].w * xv[i].w * inv;
+    }
+    t = warp_sum(t);
+    const float coef = clamped ? 0.f : inv * inv * inv / (float)norm_dim * t;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      float4 nv;
+      nv.x = ov[i].x + gv[i].x * inv * dv[i].x - coef * xv[i].x;
+      nv.y = ov[i].y + gv[i].y * inv * dv[i].y - coef * xv[i].y;
+      nv.z = ov[i].z + gv[i].z * inv * dv[i].z - coef * xv[i].z;
+      nv.w = ov[i].w + gv[i].w * inv * dv[i].w - coef * xv[i].w;
+      *reinterpret_cast<float4*>(dx + base + 128 * i) = nv;
+      uint2 pk;
+      pk.x = pack_bf16x2(nv.x, nv.y), pk.y = pack_bf16x2(nv.z, nv.w);
+      *reinterpret_cast<uint2*>(dxb + base + 128 * i) = pk;
+    }
+  }
+  // reduce dg over the block's warps, then one atomic per element per block
+  __shared__ float4 sdg[8][32 * NCH];
+  const int w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) sdg[w][32 * i + lane] = dgacc[i];  // float4 slot 32 i + lane = columns 128 i + 4 lane ..
+  __syncthreads();
+  const float* sflat = reinterpret_cast<const float*>(&sdg[0][0]);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float sum = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) sum += sflat[ww * 128 * NCH + j];
+    atomicAdd(dg + j, sum);
+  }
+}
+
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
                 __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim) {
   if (norm_dim <= 0) norm_dim = D;
@@ -481,7 +558,11 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const f
   // one row per warp: the kernel is latency bound (ncu: 12 % warps active, every pipe < 5 %), so more resident warps
   // win over fewer column atomics (measured: 240 CTAs 19 us, 120 CTAs 32 us at M = 1920)
   const int blocks = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
-  if (D <= 512)
+  const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx_bf16)) & 7) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (D == 512 && al16)
+    rmsnorm_bwd_vec_kernel<4><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
+  else if (D <= 512)
     rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
   else
     rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
