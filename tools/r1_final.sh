@@ -13,3 +13,6 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/fina
 echo "smoke rc=$?"
 cat gpurun_out/final_bench.json
 ls -la gpurun_out/*.ncu-rep
+timeout 300 python tools/bench_lrs.py --T 150 --B 16 > gpurun_out/final_lrs_c3.json 2> gpurun_out/final_lrs_c3.err
+timeout 300 python tools/bench_lrs.py --T 250 --B 8 > gpurun_out/final_lrs_c4.json 2> gpurun_out/final_lrs_c4.err
+tail -c 400 gpurun_out/final_lrs_c3.json
