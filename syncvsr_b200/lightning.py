@@ -177,6 +177,7 @@ class TransformerLightningModule(nn.Module):
         if self._h:
             L.svsr_lrw_destroy(self._h)
             self._h = C.c_void_p()
+        self._engine_gen = getattr(self, "_engine_gen", 0) + 1  # captured graphs of an older engine are void
         cfg = self._engine_cfg(B, T, H, W)
         check(L.svsr_lrw_create(C.byref(cfg), C.byref(self._h)), "svsr_lrw_create")
         if first:

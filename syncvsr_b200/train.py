@@ -103,6 +103,7 @@ class DataParallelStep:
         self.staged = (self.world > 1) if staged is None else bool(staged)
         self._hi = torch.cuda.Stream(device=module.flat_params.device, priority=-1) if high_priority else None
         self._graphs: Dict[tuple, dict] = {}
+        self._graph_gen = None      # engine generation the cached graphs were captured against
         self._static_inputs = None  # used once more than MAX_GRAPH_SETS distinct input buffer sets have been seen
         self.graph_launches = 0     # kernels launched by graph replays (the library's counter only sees captures)
         self.graph_replays = 0
@@ -156,6 +157,11 @@ class DataParallelStep:
                 "launches": int(lib().svsr_launch_count() - n0)}
 
     def _graph_entry(self, batch):
+        gen = getattr(self.module, "_engine_gen", 0)
+        if gen != self._graph_gen:  # the engine (workspace, handle) was rebuilt for another clip geometry
+            self._graphs.clear()
+            self._static_inputs = None
+            self._graph_gen = gen
         key = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in batch if isinstance(t, torch.Tensor))
         ent = self._graphs.get(key)
         if ent is None and self._static_inputs is None and len(self._graphs) >= self.MAX_GRAPH_SETS:

@@ -360,6 +360,27 @@ def test_graph_replayed_step_equals_kernel_by_kernel_step(Module, staged, priori
         assert l2 == pytest.approx(l3, rel=2e-4) and rel(p2, p3) < 1e-5 and torch.equal(n2, n3)
 
 
+def test_graph_step_drops_its_graphs_when_the_engine_is_rebuilt(Module):
+    """A batch of another geometry rebuilds the native engine (new handle and workspace): graphs captured against the
+    old one must not be replayed when the first geometry comes back."""
+    from syncvsr_b200.train import DataParallelStep, FusedAdamW
+
+    def run(graph):
+        torch.manual_seed(13)
+        m = Module(make_cfg(depth=1)).train()
+        step = DataParallelStep(m, FusedAdamW.from_config(m), graph=graph)
+        small = tuple(t.cuda() for t in O.make_inputs(720, 2))
+        big = tuple(t.cuda() for t in O.make_inputs(721, 3))
+        losses = [float(step(*b)["loss_total"]) for b in (small, small, small, big, big, small, small, small)]
+        torch.cuda.synchronize()
+        return losses, m.flat_params.clone(), step
+
+    l0, p0, _ = run(False)
+    l1, p1, s1 = run(True)
+    assert s1.graph_replays == 5  # per geometry the first step builds the engine kernel by kernel: 2 + 1 + 2 replays
+    assert l1 == pytest.approx(l0, rel=2e-4) and rel(p1, p0) < 1e-5
+
+
 def test_step_with_dropout_is_never_replayed_from_a_graph(Module):
     """A module whose launch sequence depends on per-step host RNG (layer_dropout, dropout seeds) keeps launching kernel
     by kernel even when graph=True."""

@@ -31,8 +31,10 @@ def main():
     fam = collections.defaultdict(lambda: {"launches": 0, "bytes": 0.0, "us": 0.0})
     for k in step:
         f = re.sub(r"<.*", "", k["name"]).strip()
-        if f == "conv3x3_c64_halo_kernel":  # same family as igemm_kernel in bench.py's per-launch events (PROF_IGEMM)
+        if f in ("conv3x3_c64_halo_kernel", "conv_t5_c64_halo_kernel"):  # bench.py's PROF_IGEMM family
             f = "igemm_kernel"
+        if f in ("wgrad3x3_c64_halo_kernel", "wgrad_t5_c64_halo_kernel"):  # bench.py's PROF_WGRAD family
+            f = "wgrad_kernel"
         fam[f]["launches"] += 1
         fam[f]["bytes"] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
         fam[f]["us"] += k.get("us", 0.0)
