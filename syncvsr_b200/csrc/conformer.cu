@@ -111,12 +111,15 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dyb, const float* dyf /* 
   for (int i = 0; i < NV; ++i) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = warp; r < M; r += nwarps) {
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float4 xh[NV], g[NV];
+    float4 xh[NV], g[NV], prev[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       const float4 xv = reinterpret_cast<const float4*>(x + (size_t)r * D)[c4];
+      // the value dx accumulates into is fetched with the other operands, ahead of the row reduction: the kernel is one
+      // dependent chain per row (this warp is the only writer of the row, dyf may alias dx)
+      prev[i] = accumulate ? reinterpret_cast<const float4*>(dx + (size_t)r * D)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 d;
       if (dyf) {
         d = reinterpret_cast<const float4*>(dyf + (size_t)r * D)[c4];
@@ -141,10 +144,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dyb, const float* dyf /* 
       o.x = rstd * (g[i].x - c1 - xh[i].x * c2), o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
       o.z = rstd * (g[i].z - c1 - xh[i].z * c2), o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
       float4* dst = reinterpret_cast<float4*>(dx + (size_t)r * D) + c4;
-      if (accumulate) {
-        const float4 p = *dst;
-        o.x += p.x, o.y += p.y, o.z += p.z, o.w += p.w;
-      }
+      o.x += prev[i].x, o.y += prev[i].y, o.z += prev[i].z, o.w += prev[i].w;
       *dst = o;
     }
   }
@@ -1147,7 +1147,9 @@ int layernorm_bwd(const __nv_bfloat16* dy_bf16, const float* dy_f32, const float
                   cudaStream_t s) {
   SVSR_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128,1024]", D);
   SVSR_REQUIRE(dy_bf16 || dy_f32, "layernorm_bwd: no upstream gradient");
-  const unsigned grid = grid_for(M, 8 * 4, 148 * 2);  // >= 4 rows per warp: fewer column atomics
+  // one row per warp: latency bound, so resident warps win over fewer column atomics (the same
+  // measurement as rmsnorm_bwd in encoder.cu)
+  const unsigned grid = grid_for(M, 8, 148 * 2);  // at D = 768 one CTA is resident per SM (173 registers): two waves
   LN_DISPATCH(D / 128, layernorm_bwd_kernel, dy_bf16, dy_f32, x, gamma, stats, dx, accumulate, dgamma, dbeta, M);
   LAUNCH_CHECK();
   return SVSR_OK;

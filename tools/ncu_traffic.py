@@ -27,7 +27,10 @@ def main():
             d["us"] = v / 1e3 if unit == "ns" else v * 1e3 if unit == "ms" else v
     ks = list(per_id.values())
     idx = [i for i, k in enumerate(ks) if "stem_patch" in k["name"]]
-    step = ks[idx[-1]:] if idx else ks
+    # the last COMPLETE step: a capture cut by `ncu -c N` ends inside a step, which shows as a shorter last segment
+    segs = [ks[a:b] for a, b in zip(idx, idx[1:] + [len(ks)])] if idx else [ks]
+    full = max(len(sg) for sg in segs)
+    step = [sg for sg in segs if len(sg) == full][-1]
     fam = collections.defaultdict(lambda: {"launches": 0, "bytes": 0.0, "us": 0.0})
     for k in step:
         f = re.sub(r"<.*", "", k["name"]).strip()
