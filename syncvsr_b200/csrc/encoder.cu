@@ -167,9 +167,9 @@ __device__ __forceinline__ void load_qkv_rot(const __nv_bfloat16* __restrict__ b
 
 // out[r][c] = scale * sum_d A[r][d] * B[c][d]  (both [n x 64] in smem): register tile of 2 rows x 4 columns per thread,
 // 8 FMAs per 6 shared loads, bank-conflict free with the 65-float pitch.
-__device__ __forceinline__ void mm_abt(const float* sa, const float* sb, float* out, int n, float scale) {
-  const int nrp = (n + 1) >> 1, ncq = (n + 3) >> 2;
-  for (int t = threadIdx.x; t < nrp * ncq; t += blockDim.x) {
+__device__ __forceinline__ void mm_abt_item(const float* sa, const float* sb, float* out, int n, float scale, int t) {
+  const int ncq = (n + 3) >> 2;
+  {
     const int rp = t / ncq, cq = t - rp * ncq;
     const int r0 = 2 * rp, r1 = min(r0 + 1, n - 1);
     int c[4];
@@ -192,6 +192,23 @@ __device__ __forceinline__ void mm_abt(const float* sa, const float* sb, float* 
         out[r0 * AT_LD + 4 * cq + j] = acc[0][j] * scale;
         if (r0 + 1 < n) out[(r0 + 1) * AT_LD + 4 * cq + j] = acc[1][j] * scale;
       }
+  }
+}
+
+__device__ __forceinline__ void mm_abt(const float* sa, const float* sb, float* out, int n, float scale) {
+  const int items = ((n + 1) >> 1) * ((n + 3) >> 2);
+  for (int t = threadIdx.x; t < items; t += blockDim.x) mm_abt_item(sa, sb, out, n, scale, t);
+}
+// two independent products in one sweep (backward: S = Q K^T / 8 and dP = dO V^T), so that a 256-thread CTA runs both at once
+__device__ __forceinline__ void mm_abt_pair(const float* a0, const float* b0, float* o0, float s0, const float* a1,
+                                            const float* b1, float* o1, float s1, int n) {
+  const int items = ((n + 1) >> 1) * ((n + 3) >> 2);
+  const int split = (items + 31) & ~31;  // the second product starts on a warp boundary: no warp runs both loops
+  for (int t = threadIdx.x; t < split + items; t += blockDim.x) {
+    if (t < items)
+      mm_abt_item(a0, b0, o0, n, s0, t);
+    else if (t >= split)
+      mm_abt_item(a1, b1, o1, n, s1, t - split);
   }
 }
 
@@ -278,7 +295,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
                      const __nv_bfloat16* __restrict__ d_o, __nv_bfloat16* __restrict__ dqkv, int n, int heads,
                      int rotary_v, float drop_p, unsigned long long drop_seed) {
@@ -293,8 +310,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   const int inner = heads * AT_D, ld = 3 * inner;
   const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * AT_D;
   load_qkv_rot(base, ld, inner, d_o + (long long)b * n * inner + h * AT_D, rot, sq, sk, sv, sdo, n, rotary_v != 0);
-  mm_abt(sq, sk, sp, n, 0.125f);  // S
-  mm_abt(sdo, sv, sds, n, 1.0f);  // dP = dO V'^T
+  mm_abt_pair(sq, sk, sp, 0.125f, sdo, sv, sds, 1.0f, n);  // S = Q' K'^T / 8 and dP = dO V'^T
   __syncthreads();
   softmax_rows(sp, n);
   __syncthreads();
@@ -598,7 +614,8 @@ int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat1
     SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
-  attention_bwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v, drop_p, drop_seed);
+  // 256 threads: S and dP (2 x 120 register tiles at n = 30) in one round, the three gradient products (360) in two
+  attention_bwd_kernel<<<B * heads, 256, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v, drop_p, drop_seed);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
