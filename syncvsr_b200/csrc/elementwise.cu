@@ -759,27 +759,31 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
         if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
       }
     }
-  } else if (jb.type == 1) {
+  } else if (jb.type == 1 || (jb.type == 4 && (jb.a / 2) % 32 == 0)) {
     // linear [N,K]: 32x32 tiles through shared memory so that the plain copy AND the transposed copy are both
-    // written with full 64-byte rows (the encoder holds 38 M of the 63 M parameters)
+    // written with full 64-byte rows (the encoder holds 38 M of the 63 M parameters). GLU projections (type 4, 25 M of
+    // them: rows [0,F) = values, [F,2F) = gates, gate rows remapped to start at Fp) take the same path whenever a
+    // 32-row tile cannot straddle the value / gate boundary: all rows of a tile then share one row shift.
     __shared__ float tile[32][33];
     const int N = jb.a, K = jb.b, ldb = jb.c, ldt = jb.d;
+    const int F = N / 2, gate_shift = jb.type == 4 ? (F + 63) / 64 * 64 - F : 0;
     const int tk = (K + 31) / 32, tn = (N + 31) / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
       const int k0 = (t % tk) * 32, n0 = (t / tk) * 32;
+      const int shift = (jb.type == 4 && n0 >= F) ? gate_shift : 0;  // output row = source row + shift
       __syncthreads();
       for (int j = ty; j < 32; j += 8) {
         const int n = n0 + j, k = k0 + tx;
         const float v = (n < N && k < K) ? jb.src[(long long)n * K + k] : 0.f;
         tile[j][tx] = v;
-        if (n < N && k < K) jb.dst0[(long long)n * ldb + k] = __float2bfloat16(v);
+        if (n < N && k < K) jb.dst0[(long long)(n + shift) * ldb + k] = __float2bfloat16(v);
       }
       __syncthreads();
       if (jb.dst1)
         for (int j = ty; j < 32; j += 8) {
           const int k = k0 + j, n = n0 + tx;
-          if (n < N && k < K) jb.dst1[(long long)k * ldt + n] = __float2bfloat16(tile[tx][j]);
+          if (n < N && k < K) jb.dst1[(long long)k * ldt + n + shift] = __float2bfloat16(tile[tx][j]);
         }
     }
   } else if (jb.type == 3 || jb.type == 4) {
