@@ -717,6 +717,7 @@ __global__ void pack_linear_weight_kernel(const float* __restrict__ w, __nv_bflo
   }
 }
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
+  __shared__ float pack_smem[32 * (32 * 9 + 1)];  // conv tile (32 co x 32 ci x 9 taps) or linear tile [64][65]
   const PackJob jb = jobs[blockIdx.y];
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
     // contiguous bf16 per (row, tap)) are coalesced; element-wise scatter cost 2-byte writes to 22 M distinct sectors.
     const int Cout = jb.a, Cin = jb.b, RS = jb.c;
     if (RS <= 9 && Cout % 32 == 0 && Cin % 32 == 0) {
-      __shared__ float ctile[32 * (32 * 9 + 1)];
+      float* ctile = pack_smem;
       const int pitch = 32 * RS + 1;
       const int tci = Cin / 32, ntiles = (Cout / 32) * tci;
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -759,32 +760,53 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
         if (jb.dst1) jb.dst1[(long long)ci * RS * Cout + (long long)rs * Cout + co] = v;
       }
     }
-  } else if (jb.type == 1 || (jb.type == 4 && (jb.a / 2) % 32 == 0)) {
-    // linear [N,K]: 32x32 tiles through shared memory so that the plain copy AND the transposed copy are both
-    // written with full 64-byte rows (the encoder holds 38 M of the 63 M parameters). GLU projections (type 4, 25 M of
-    // them: rows [0,F) = values, [F,2F) = gates, gate rows remapped to start at Fp) take the same path whenever a
-    // 32-row tile cannot straddle the value / gate boundary: all rows of a tile then share one row shift.
-    __shared__ float tile[32][33];
+  } else if (jb.type == 1 || (jb.type == 4 && (jb.a / 2) % 64 == 0)) {
+    // linear [N,K]: 64x64 tiles through shared memory so that the plain copy AND the transposed copy are both written
+    // with full rows (the encoder holds 38 M of the 63 M parameters). 16 loads per thread are in flight before the first
+    // barrier: with 32x32 tiles (4 per thread) the pass was bound by two global round trips per 4 KB. GLU projections
+    // (type 4, 25 M of them: rows [0,F) = values, [F,2F) = gates, gate rows remapped to start at Fp) take the same path
+    // whenever a 64-row tile cannot straddle the value / gate boundary: all rows of a tile then share one row shift.
+    float (*tile)[65] = reinterpret_cast<float (*)[65]>(pack_smem);
     const int N = jb.a, K = jb.b, ldb = jb.c, ldt = jb.d;
     const int F = N / 2, gate_shift = jb.type == 4 ? (F + 63) / 64 * 64 - F : 0;
-    const int tk = (K + 31) / 32, tn = (N + 31) / 32;
+    const int tk = (K + 63) / 64, tn = (N + 63) / 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
-      const int k0 = (t % tk) * 32, n0 = (t / tk) * 32;
+      const int k0 = (t % tk) * 64, n0 = (t / tk) * 64;
       const int shift = (jb.type == 4 && n0 >= F) ? gate_shift : 0;  // output row = source row + shift
       __syncthreads();
-      for (int j = ty; j < 32; j += 8) {
-        const int n = n0 + j, k = k0 + tx;
-        const float v = (n < N && k < K) ? jb.src[(long long)n * K + k] : 0.f;
-        tile[j][tx] = v;
-        if (n < N && k < K) jb.dst0[(long long)(n + shift) * ldb + k] = __float2bfloat16(v);
+      float v[8][2];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int n = n0 + ty + 8 * jj;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = k0 + tx + 32 * h;
+          v[jj][h] = (n < N && k < K) ? jb.src[(long long)n * K + k] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = ty + 8 * jj, n = n0 + j;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = k0 + tx + 32 * h;
+          tile[j][tx + 32 * h] = v[jj][h];
+          if (n < N && k < K) jb.dst0[(long long)(n + shift) * ldb + k] = __float2bfloat16(v[jj][h]);
+        }
       }
       __syncthreads();
-      if (jb.dst1)
-        for (int j = ty; j < 32; j += 8) {
-          const int k = k0 + j, n = n0 + tx;
-          if (n < N && k < K) jb.dst1[(long long)k * ldt + n + shift] = __float2bfloat16(tile[tx][j]);
+      if (jb.dst1) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = ty + 8 * jj, k = k0 + j;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = n0 + tx + 32 * h;
+            if (n < N && k < K) jb.dst1[(long long)k * ldt + n + shift] = __float2bfloat16(tile[tx + 32 * h][j]);
+          }
         }
+      }
     }
   } else if (jb.type == 3 || jb.type == 4) {
     // fp32 vector -> zero-padded fp32 copy (type 3; dst0 reinterpreted as float*), or GLU linear [2F, K] -> bf16 rows
