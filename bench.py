@@ -27,6 +27,8 @@ METRIC = "clips/sec (fwd+bwd) LRW-shape [B,1,29,88,88]"
 FLOPS_PER_CLIP = 62.61e9  # fwd 21.46 GF, fwd+bwd 62.61 GF (2*MAC, A*G*V = 2560)
 B_PER_GPU = 64
 T, S = 29, 88
+WORKLOAD = ("LRW word-level ResNet18+Transformer-12L (x-transformers), fwd+bwd+allreduce+AdamW, "
+            f"[{B_PER_GPU},1,29,88,88] per GPU (BASELINE configs[1])")
 
 
 class _Attrs(dict):
@@ -115,7 +117,7 @@ def cpu_reference_clips_per_s(steps: int, warmup: int, batch: int = 2):
             v.grad = None
         out = O.lrw_forward(P, videos, tokens, labels, wm)
         out["loss_total"].backward()
-        return float(out["loss_total"])
+        return float(out["loss_total"].detach())
 
     for _ in range(warmup):
         one()
@@ -138,7 +140,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LRW word-level ResNet18+Transformer-12L, fwd+bwd, [2,1,29,88,88] per step (CPU sample)"},
+        "config": {"workload": WORKLOAD, "global_batch": args.gpus * B_PER_GPU, "parallelism": f"dp{args.gpus}",
+                   "sample": "each CPU step is a bounded sample of that workload: [2,1,29,88,88] clips, fwd+bwd, fp32"},
         "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -291,8 +294,7 @@ def run_native_arm(args):
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "LRW word-level ResNet18+Transformer-12L (x-transformers), fwd+bwd+allreduce+AdamW, "
-                               f"[{B},1,29,88,88] per GPU (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "per-step working set 4.5 GB >> 126 MB L2; two alternating input batches",
                    "launch_mode": ("cuda-graph replay of zero_grad+repack+fwd+bwd" if args.graph else "kernel by kernel")
