@@ -368,6 +368,16 @@ int svsr_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t n_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     float max_norm, float grad_div, void* scratch, void* stream);
 
+/* The same step with per-range Adam step counts: seg_begin = nseg+1 ascending HOST element offsets (multiples of 4,
+ * seg_begin[0] = 0, seg_begin[nseg] = n_total), seg_step = nseg HOST step counts; a range with step 0 received no
+ * gradient this step (`p.grad is None` in the reference: a sublayer dropped by layer_dropout, lightning.py:95-105) and is
+ * left untouched -- no weight decay, no moment update, no step increment -- exactly like torch.optim.AdamW. */
+#define SVSR_ADAMW_MAX_SEGMENTS 160
+int svsr_adamw_step_segmented(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_decay,
+                              int64_t n_total, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              const int64_t* seg_begin, const int32_t* seg_step, int nseg, float max_norm,
+                              float grad_div, void* scratch, void* stream);
+
 /* Kernels launched by this library so far in this process (bench.py reports the per-region difference). */
 long long svsr_launch_count(void);
 /* Per-launch CUDA-event timing of the tensor-core kernels: enable (resets), run, synchronise, read.
@@ -375,8 +385,6 @@ long long svsr_launch_count(void);
 int svsr_prof_enable(int on);
 int svsr_prof_read(int kind, double* total_ms, double* total_flops, int* launches);
 
-/* Developer hardware probe (see csrc/debug_probe.cu); not part of the product path. */
-int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream);
 
 #ifdef __cplusplus
 }

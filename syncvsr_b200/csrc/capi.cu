@@ -5,7 +5,6 @@
 #include "wgrad.cuh"
 
 namespace svsr {
-int debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, cudaStream_t stream);
 }
 
 using namespace svsr;
@@ -184,8 +183,5 @@ int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, 
   return wgrad_launch(p, static_cast<cudaStream_t>(stream));
 }
 
-int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream) {
-  return debug_rowshift(a, b, out, shift, mode, static_cast<cudaStream_t>(stream));
-}
 
 }  // extern "C"

@@ -1106,8 +1106,9 @@ label_smoothing_kernel(const float* __restrict__ logits, int ld, int V, const lo
 }
 
 __global__ void lrs_finalize_kernel(const double* acc, float* out, int B, long long audio_rows, float mtlalpha,
-                                    float audio_weight, int has_audio) {
-  const double la = has_audio ? acc[0] / (double)audio_rows : 0.0;
+                                    float audio_weight, int has_audio, const int* bad) {
+  double la = has_audio ? acc[0] / (double)audio_rows : 0.0;
+  if (has_audio && bad && bad[0]) la = (double)NAN;  // an audio token outside its vocabulary (see heads.cuh)
   const double lc = acc[1] / (double)B, lt = acc[2] / (double)B;
   out[0] = (float)((double)mtlalpha * lc + (1.0 - (double)mtlalpha) * lt + (has_audio ? la * (double)audio_weight : 0.0));
   out[1] = (float)lc;
@@ -1386,8 +1387,8 @@ int label_smoothing_loss(const float* logits, int ld, int V, const long long* ta
   return SVSR_OK;
 }
 int lrs_finalize_metrics(const double* acc, float* out, int B, long long audio_rows, float mtlalpha, float audio_weight,
-                         int has_audio, cudaStream_t s) {
-  lrs_finalize_kernel<<<1, 1, 0, s>>>(acc, out, B, audio_rows, mtlalpha, audio_weight, has_audio);
+                         int has_audio, cudaStream_t s, const int* bad) {
+  lrs_finalize_kernel<<<1, 1, 0, s>>>(acc, out, B, audio_rows, mtlalpha, audio_weight, has_audio, bad);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

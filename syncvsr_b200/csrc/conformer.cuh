@@ -98,7 +98,7 @@ int label_smoothing_loss(const float* logits, int ld, int V, const long long* ta
 // out[0..4] = loss, loss_ctc, loss_att, loss_audio, acc (e2e_asr_transformer.py:218-227) from the fp64 accumulators
 // acc[0] audio nll sum, acc[1] ctc nll sum, acc[2] KL sum, acc[3] #correct, acc[4] #scored
 int lrs_finalize_metrics(const double* acc, float* out, int B, long long audio_rows, float mtlalpha, float audio_weight,
-                         int has_audio, cudaStream_t s);
+                         int has_audio, cudaStream_t s, const int* bad = nullptr);
 
 // AdaptiveAvgPool2d(1) of the trunk output (resnet.py:126,175-176): feats[n,:] = mean_hw a[n,hw,:] (bf16) and backward
 int meanpool_bf16(const __nv_bfloat16* a, __nv_bfloat16* out, long long N, int HW, int C, cudaStream_t s);

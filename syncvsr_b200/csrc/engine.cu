@@ -521,11 +521,11 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   RC(lw_fwd(e, e.ws<bf16>(e.lastb_frames), Dp, e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, s));
   const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
   RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing,
-                 e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<double>(e.acc), 1.0f / (float)c.B, s));
+                 e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<double>(e.acc), 1.0f / (float)c.B, s, e.ws<int>(e.bad_token)));
   RC(audio_ce(e.ws<float>(e.logits_a), AGV, tokens, tok_stride_b, c.B, c.T, c.audio_alignment, c.vq_groups,
               c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc), e.ws<int>(e.bad_token),
               c.lambda_audio / (float)audio_rows, s));
-  RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s));
+  RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s, e.ws<int>(e.bad_token)));
   e.last_skip = skip_mask;
   e.last_seed = dropout_seed;
   e.last_train = train;

@@ -493,7 +493,8 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
   // ---- label-smoothing loss + accuracy (label_smoothing_loss.py:41-63; nets_utils.py:303) ----
   RC(label_smoothing_loss(e.ws<float>(e.pred), e.ldv, c.odim, ys_out, Md, c.lsm_weight, e.ws<bf16>(e.dpred),
                           e.ws<double>(e.acc), 2, (1.f - c.mtlalpha) / (float)c.B, s));
-  RC(lrs_finalize_metrics(e.ws<double>(e.acc), metrics, c.B, audio_rows, c.mtlalpha, c.audio_weight, has_audio, s));
+  RC(lrs_finalize_metrics(e.ws<double>(e.acc), metrics, c.B, audio_rows, c.mtlalpha, c.audio_weight, has_audio, s,
+                          e.ws<int>(e.bad_token)));
   e.last_L = L, e.last_Llab = Llab, e.last_train = train, e.last_audio = has_audio;
   e.fwd_done = true;
   return SVSR_OK;

@@ -20,8 +20,12 @@ audio_ce_kernel(const float* __restrict__ logits, int ld, const long long* __res
     const long long b = bt / T;
     const int a = c / G, g = c - a * G;
     const long long tgt = tokens[b * tok_stride_b + (long long)(t * A + a) * G + g];
-    if (tgt < 0 || tgt >= V) {
-      if (lane == 0) *bad_token = 1;
+    if (tgt < 0 || tgt >= V) {  // F.cross_entropy would raise: flag it (the step's metrics become NaN) and leave a
+      if (lane == 0) *bad_token = 1;  // zero gradient row instead of last step's stale one
+      if (dlogits) {
+        __nv_bfloat16* drow = dlogits + bt * ld + (long long)c * V;
+        for (int j = lane; j < V; j += 32) drow[j] = __float2bfloat16(0.f);
+      }
       continue;
     }
     const float* row = logits + bt * ld + (long long)c * V;
@@ -55,12 +59,18 @@ audio_ce_kernel(const float* __restrict__ logits, int ld, const long long* __res
 __global__ void __launch_bounds__(256)
 category_ce_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ labels,
                    const float* __restrict__ soft, int B, int C, float eps, __nv_bfloat16* __restrict__ dlogits,
-                   int ldd, double* acc, float dscale) {
+                   int ldd, double* acc, float dscale, int* bad_label) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = warp; r < B; r += nwarps) {
     const float* row = logits + (long long)r * ld;
+    if (!soft && (labels[r] < 0 || labels[r] >= C)) {  // out-of-range class index: flag, zero gradient row, no reads
+      if (lane == 0 && bad_label) *bad_label = 1;
+      if (dlogits)
+        for (int j = lane; j < ldd; j += 32) dlogits[(long long)r * ldd + j] = __float2bfloat16(0.f);
+      continue;
+    }
     float m = -INFINITY;
     for (int j = lane; j < C; j += 32) m = fmaxf(m, row[j]);
     m = warp_max(m);
@@ -110,8 +120,12 @@ category_ce_kernel(const float* __restrict__ logits, int ld, const long long* __
   }
 }
 
-__global__ void finalize_metrics_kernel(const double* acc, float* out, float lambda_audio, int B, long long audio_rows) {
-  const double la = acc[0] / (double)audio_rows, lc = acc[1] / (double)B;
+__global__ void finalize_metrics_kernel(const double* acc, float* out, float lambda_audio, int B, long long audio_rows,
+                                        const int* bad) {
+  double la = acc[0] / (double)audio_rows, lc = acc[1] / (double)B;
+  // an audio token / class label outside its vocabulary (F.cross_entropy raises a device assert in the reference):
+  // the native step cannot raise from a kernel, so its losses read NaN -- loud in any log and any `isfinite` guard
+  if (bad && bad[0]) la = lc = (double)NAN;
   out[0] = (float)(lc + la * (double)lambda_audio);
   out[1] = (float)lc;
   out[2] = (float)la;
@@ -148,16 +162,18 @@ int audio_ce(const float* logits, int ld, const long long* tokens, long long tok
   return SVSR_OK;
 }
 int category_ce(const float* logits, int ld, const long long* labels, const float* soft_labels, int B, int C, float eps,
-                __nv_bfloat16* dlogits, int ldd, double* acc, float dscale, cudaStream_t s) {
+                __nv_bfloat16* dlogits, int ldd, double* acc, float dscale, cudaStream_t s, int* bad_label) {
   SVSR_REQUIRE((labels != nullptr) != (soft_labels != nullptr), "category_ce: exactly one of labels/soft_labels");
   const int blocks = (B + 7) / 8;
-  category_ce_kernel<<<blocks, 256, 0, s>>>(logits, ld, labels, soft_labels, B, C, eps, dlogits, ldd, acc, dscale);
+  category_ce_kernel<<<blocks, 256, 0, s>>>(logits, ld, labels, soft_labels, B, C, eps, dlogits, ldd, acc, dscale,
+                                            bad_label);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
-int finalize_metrics(const double* acc, float* out, float lambda_audio, int B, long long audio_rows, cudaStream_t s) {
-  finalize_metrics_kernel<<<1, 1, 0, s>>>(acc, out, lambda_audio, B, audio_rows);
+int finalize_metrics(const double* acc, float* out, float lambda_audio, int B, long long audio_rows, cudaStream_t s,
+                     const int* bad) {
+  finalize_metrics_kernel<<<1, 1, 0, s>>>(acc, out, lambda_audio, B, audio_rows, bad);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;

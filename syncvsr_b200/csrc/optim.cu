@@ -68,6 +68,54 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// Segmented variant: the arena is cut into ranges [begin[i], begin[i+1]) that carry their own Adam step count.
+// A range whose parameters received no gradient this step (a sublayer dropped by x-transformers' layer_dropout:
+// `p.grad is None` in the reference, so torch.optim.AdamW leaves the parameter, its moments and its step count
+// untouched -- lightning.py:216-221) has bc1 = 0 and is skipped entirely: no decay, no moments.
+struct AdamSegs {
+  long long begin[SVSR_ADAMW_MAX_SEGMENTS + 1];  // element offsets, multiples of 4, ascending; begin[n] = end
+  float bc1[SVSR_ADAMW_MAX_SEGMENTS];            // 1 - beta1^step of the range; 0 = skip the range this step
+  float bc2s[SVSR_ADAMW_MAX_SEGMENTS];           // sqrt(1 - beta2^step)
+  int n;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 long long first, long long n, long long n_decay, const double* __restrict__ scratch, float lr, float b1,
+                 float b2, float eps, float wd, const __grid_constant__ AdamSegs segs) {
+  const float coef = reinterpret_cast<const float*>(scratch + 1)[0];
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = first + (i << 2);
+    int lo = 0, hi = segs.n - 1;  // last range whose begin <= e
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (segs.begin[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    const float bc1 = segs.bc1[lo], bc2_sqrt = segs.bc2s[lo];
+    if (bc1 == 0.f) continue;
+    const float decay = e < n_decay ? 1.f - lr * wd : 1.f;
+    float4 pv = reinterpret_cast<float4*>(p + first)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g + first)[i];
+    float4 mv = reinterpret_cast<float4*>(m + first)[i], vv = reinterpret_cast<float4*>(v + first)[i];
+    float* pp = &pv.x;
+    const float* gg = &gv.x;
+    float* mm = &mv.x;
+    float* vq = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = gg[k] * coef;
+      mm[k] = b1 * mm[k] + (1.f - b1) * gr;
+      vq[k] = b2 * vq[k] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(vq[k]) / bc2_sqrt + eps;
+      pp[k] = pp[k] * decay - (lr / bc1) * (mm[k] / denom);
+    }
+    reinterpret_cast<float4*>(p + first)[i] = pv;
+    reinterpret_cast<float4*>(m + first)[i] = mv;
+    reinterpret_cast<float4*>(v + first)[i] = vv;
+  }
+}
+
 }  // namespace
 }  // namespace svsr
 
@@ -97,6 +145,39 @@ int svsr_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
     adamw_kernel<<<148 * 2, 256, 0, s>>>(params + n_decay, grads + n_decay, exp_avg + n_decay, exp_avg_sq + n_decay,
                                          n_total - n_decay, sc, lr, beta1, beta2, eps, 0.f, bc1, bc2s);
   for (int i = 0; i < 3 + (n_total > n_decay ? 1 : 0); ++i) note_launch();
+  SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+
+// Per-range step counts (see AdamSegs). seg_begin: host array of nseg+1 ascending element offsets (multiples of 4,
+// seg_begin[0] = 0, seg_begin[nseg] = n_total); seg_step: host array of nseg Adam step counts, 0 = the range got no
+// gradient this step and is left untouched. One launch over the whole arena.
+int svsr_adamw_step_segmented(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_decay,
+                              int64_t n_total, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              const int64_t* seg_begin, const int32_t* seg_step, int nseg, float max_norm,
+                              float grad_div, void* scratch, void* stream) {
+  SVSR_REQUIRE(params && grads && exp_avg && exp_avg_sq && scratch && seg_begin && seg_step, "adamw: null pointer");
+  SVSR_REQUIRE(nseg >= 1 && nseg <= SVSR_ADAMW_MAX_SEGMENTS, "adamw: %d ranges (max %d)", nseg, SVSR_ADAMW_MAX_SEGMENTS);
+  SVSR_REQUIRE(n_decay % 4 == 0 && n_total % 4 == 0 && n_decay <= n_total, "adamw: bad sizes");
+  SVSR_REQUIRE(seg_begin[0] == 0 && seg_begin[nseg] == n_total, "adamw: ranges must cover [0, n_total)");
+  AdamSegs segs;
+  segs.n = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    SVSR_REQUIRE(seg_begin[i] % 4 == 0 && seg_begin[i] < seg_begin[i + 1] && seg_step[i] >= 0,
+                 "adamw: range %d is not ascending / 4-aligned / has a negative step", i);
+    segs.begin[i] = seg_begin[i];
+    segs.bc1[i] = seg_step[i] > 0 ? 1.f - powf(beta1, (float)seg_step[i]) : 0.f;
+    segs.bc2s[i] = seg_step[i] > 0 ? sqrtf(1.f - powf(beta2, (float)seg_step[i])) : 1.f;
+  }
+  segs.begin[nseg] = n_total;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* sc = static_cast<double*>(scratch);
+  SVSR_CHECK_CUDA(cudaMemsetAsync(sc, 0, 32, s));
+  sumsq_kernel<<<148 * 4, 256, 0, s>>>(grads, n_total, sc);
+  clip_coef_kernel<<<1, 1, 0, s>>>(sc, max_norm, grad_div);
+  adamw_seg_kernel<<<148 * 8, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, 0, n_total, n_decay, sc, lr, beta1, beta2,
+                                           eps, weight_decay, segs);
+  for (int i = 0; i < 3; ++i) note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }

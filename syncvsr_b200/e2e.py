@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from ._lib import SvsrError, check, lib
+from .lightning import allreduce_mean_
 
 
 class LrsConfig(C.Structure):
@@ -135,12 +136,17 @@ class E2E(nn.Module):
         self._codec_fn = None
         self._lmax = int(_arg(args, "max_label_len", 64)) + 1
 
+        from ._engines import EngineCache
+
+        self._engines = EngineCache("svsr_lrs", self.device_)
+        self._ent = None
+        self._native_updates = 0
+        self.sync_grads = True  # see lightning.TransformerLightningModule.sync_grads
         self._h = C.c_void_p()
         self._shape_key = None
         self._flat_p = self._flat_g = self._flat_b = self._ws = None
         self._metrics = torch.zeros(8, device=self.device_, dtype=torch.float32)
         self._anchor = torch.zeros((), device=self.device_, requires_grad=True)
-        self._weights_dirty = True
         self._param_views: Dict[str, nn.Parameter] = {}
         self._offsets: Dict[str, tuple] = {}
         self.encoder = _EncoderNode(self)
@@ -155,26 +161,28 @@ class E2E(nn.Module):
                          self.dropout_rate, self.attn_dropout_rate)
 
     def _build_engine(self, B, T, H, W, first=False):
+        """Selects (building it on first use) the engine of this clip geometry; see _engines.EngineCache. The LRS
+        datamodule pads every batch to its own longest clip (datamodule/data_module.py:12-43), so T changes almost every
+        step: engines already built are kept (LRU, SVSR_ENGINE_CACHE_GB) instead of rebuilt."""
         L = lib()
         for f in ("param_count", "buffer_count", "workspace_bytes", "decay_count"):
             getattr(L, f"svsr_lrs_{f}").restype = C.c_int64
-        if self._h:
-            L.svsr_lrs_destroy(self._h)
-            self._h = C.c_void_p()
-        cfg = self._engine_cfg(B, T, H, W)
-        check(L.svsr_lrs_create(C.byref(cfg), C.byref(self._h)), "svsr_lrs_create")
-        if first:
-            self._create_arenas()
-        ws_bytes = L.svsr_lrs_workspace_bytes(self._h)
-        self._ws = None
-        torch.cuda.empty_cache()
-        self._ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=self.device_)
-        ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
-        check(L.svsr_lrs_bind(self._h, C.c_void_p(self._flat_p.data_ptr()), C.c_void_p(self._flat_g.data_ptr()),
-                              C.c_void_p(self._flat_b.data_ptr()), C.c_void_p(ws_ptr), C.c_int64(ws_bytes)),
-              "svsr_lrs_bind")
+        key = (B, T, H, W, self._lmax)
+        ent = self._engines.get(key)
+        if ent is None:
+            def bind(h, ws_ptr, ws_bytes):
+                check(L.svsr_lrs_bind(h, C.c_void_p(self._flat_p.data_ptr()), C.c_void_p(self._flat_g.data_ptr()),
+                                      C.c_void_p(self._flat_b.data_ptr()), C.c_void_p(ws_ptr), C.c_int64(ws_bytes)),
+                      "svsr_lrs_bind")
+
+            def arenas(h):
+                self._h = h
+                self._create_arenas()
+
+            ent = self._engines.create(key, self._engine_cfg(B, T, H, W), bind, arenas if first else None)
+        self._ent, self._h, self._ws = ent, ent.h, ent.ws
+        self._engine_gen = ent.id
         self._shape_key = (B, T, H, W)
-        self._weights_dirty = True
 
     def _create_arenas(self):
         L = lib()
@@ -259,12 +267,20 @@ class E2E(nn.Module):
         return self._flat_g
 
     def mark_weights_updated(self) -> None:
-        self._weights_dirty = True
+        """See lightning.TransformerLightningModule.mark_weights_updated (torch-side updates are detected)."""
+        self._native_updates += 1
 
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._weights_dirty = True
-        return out
+    @property
+    def _weights_dirty(self) -> bool:
+        e = self._ent
+        return e is None or e.packed_native != self._native_updates or e.packed_version != self._flat_p._version
+
+    @_weights_dirty.setter
+    def _weights_dirty(self, dirty: bool) -> None:
+        if dirty:
+            self._native_updates += 1
+        elif self._ent is not None:
+            self._ent.packed_native, self._ent.packed_version = self._native_updates, self._flat_p._version
 
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -370,6 +386,7 @@ class E2E(nn.Module):
         if need_attach:
             self._flat_g.zero_()
         check(lib().svsr_lrs_backward(self._h, C.c_void_p(g.data_ptr()), self._stream()), "svsr_lrs_backward")
+        allreduce_mean_(self._flat_g, self.sync_grads)
         if need_attach:
             self._attach_grads()
 
@@ -395,7 +412,6 @@ class E2E(nn.Module):
 
     def __del__(self):
         try:
-            if self._h:
-                lib().svsr_lrs_destroy(self._h)
+            self._engines.destroy()
         except Exception:
             pass

@@ -47,6 +47,17 @@ def _cfg_get(cfg: Any, path: str, default: Any = None) -> Any:
     return default if cur is None else cur
 
 
+def allreduce_mean_(flat: torch.Tensor, enabled: bool = True, group=None) -> torch.Tensor:
+    """What DDP's reducer does for the reference (`Trainer(strategy="ddp")`, LRW/video/src/train.py:28): average the
+    gradients over the ranks -- here ONE all-reduce over the flat arena. No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(dist.get_world_size(group))
+    return flat
+
+
 class _Node(nn.Module):
     """Anonymous container used to reproduce the reference's module tree (and therefore its state-dict keys)."""
 
@@ -127,12 +138,22 @@ class TransformerLightningModule(nn.Module):
         self.attn_dropout = 0.0 if self.hf else float(_cfg_get(config, "model.bert.attn_dropout", 0.0))
         self.rotary_v = bool(_cfg_get(config, "model.bert.rotary_v", True))
 
+        from ._engines import EngineCache
+
+        self._engines = EngineCache("svsr_lrw", self.device_)
+        self._ent = None
+        self._native_updates = 0  # bumped by mark_weights_updated(): parameter writes torch cannot see (raw pointers)
         self._h = C.c_void_p()
         self._shape_key = None
         self._flat_p = self._flat_g = self._flat_b = self._ws = None
         self._metrics = torch.zeros(8, device=self.device_, dtype=torch.float32)
         self._anchor = torch.zeros((), device=self.device_, requires_grad=True)
-        self._weights_dirty = True
+        self._last_skip = 0  # layer_dropout mask of the last forward (bit i = sublayer i dropped); read by FusedAdamW
+        # Gradient synchronisation: gradients are written straight into the flat arena (no autograd graph through the
+        # parameters), so torch DDP's reducer never sees them. Under torchrun (process group initialised) the native
+        # backward all-reduces the arena itself (SUM / world = DDP's mean); DataParallelStep does its own staged
+        # all-reduce and calls the backward entry points directly. Do NOT wrap the module in DistributedDataParallel.
+        self.sync_grads = True
         self._param_views: Dict[str, nn.Parameter] = {}
         self._offsets: Dict[str, tuple] = {}
         # geometry-independent part: parameter arenas. Built with a nominal clip geometry (the parameter layout
@@ -170,28 +191,26 @@ class TransformerLightningModule(nn.Module):
                          hf.get("attention_probs_dropout_prob", 0.0), self.emb_dropout, self.attn_dropout)
 
     def _build_engine(self, B, T, H, W, first=False):
+        """Selects (building it on first use) the engine of this clip geometry; see _engines.EngineCache."""
         L = lib()
         L.svsr_lrw_param_count.restype = C.c_int64
         L.svsr_lrw_buffer_count.restype = C.c_int64
-        L.svsr_lrw_workspace_bytes.restype = C.c_int64
-        if self._h:
-            L.svsr_lrw_destroy(self._h)
-            self._h = C.c_void_p()
-        self._engine_gen = getattr(self, "_engine_gen", 0) + 1  # captured graphs of an older engine are void
-        cfg = self._engine_cfg(B, T, H, W)
-        check(L.svsr_lrw_create(C.byref(cfg), C.byref(self._h)), "svsr_lrw_create")
-        if first:
-            self._create_arenas()
-        ws_bytes = L.svsr_lrw_workspace_bytes(self._h)
-        self._ws = None
-        torch.cuda.empty_cache()
-        self._ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=self.device_)
-        ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
-        check(L.svsr_lrw_bind(self._h, C.c_void_p(self._flat_p.data_ptr()), C.c_void_p(self._flat_g.data_ptr()),
-                              C.c_void_p(self._flat_b.data_ptr()), C.c_void_p(ws_ptr), C.c_int64(ws_bytes)),
-              "svsr_lrw_bind")
-        self._shape_key = (B, T, H, W)
-        self._weights_dirty = True
+        key = (B, T, H, W)
+        ent = self._engines.get(key)
+        if ent is None:
+            def bind(h, ws_ptr, ws_bytes):
+                check(L.svsr_lrw_bind(h, C.c_void_p(self._flat_p.data_ptr()), C.c_void_p(self._flat_g.data_ptr()),
+                                      C.c_void_p(self._flat_b.data_ptr()), C.c_void_p(ws_ptr), C.c_int64(ws_bytes)),
+                      "svsr_lrw_bind")
+
+            def arenas(h):
+                self._h = h
+                self._create_arenas()
+
+            ent = self._engines.create(key, self._engine_cfg(B, T, H, W), bind, arenas if first else None)
+        self._ent, self._h, self._ws = ent, ent.h, ent.ws
+        self._engine_gen = ent.id  # CUDA graphs are captured against one engine (train.DataParallelStep keys them by it)
+        self._shape_key = key
 
     def _create_arenas(self):
         L = lib()
@@ -294,13 +313,22 @@ class TransformerLightningModule(nn.Module):
         return self._flat_g
 
     def mark_weights_updated(self) -> None:
-        """Call after parameters changed (optimizer step, load_state_dict): bf16 operand copies are repacked lazily."""
-        self._weights_dirty = True
+        """Parameters were written through raw pointers (the native optimizer): every engine's bf16 operand copies are
+        stale and are repacked lazily. Torch-side writes (torch.optim.*, load_state_dict, p.data.add_) need no call:
+        they bump the arena's autograd version counter, which _ensure() compares."""
+        self._native_updates += 1
 
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._weights_dirty = True
-        return out
+    @property
+    def _weights_dirty(self) -> bool:
+        e = self._ent
+        return e is None or e.packed_native != self._native_updates or e.packed_version != self._flat_p._version
+
+    @_weights_dirty.setter
+    def _weights_dirty(self, dirty: bool) -> None:
+        if dirty:
+            self._native_updates += 1
+        elif self._ent is not None:  # (a replayed CUDA graph contains the repack of the current engine)
+            self._ent.packed_native, self._ent.packed_version = self._native_updates, self._flat_p._version
 
     # ------------------------------------------------------------------------------------------------------------
     # reference API
@@ -311,6 +339,10 @@ class TransformerLightningModule(nn.Module):
         B, _, T, H, W = videos.shape
         if self._shape_key != (B, T, H, W):
             self._build_engine(B, T, H, W)
+        # The bf16 operand copies go stale whenever the fp32 arena changes. The native optimizer (raw pointers) says so
+        # through mark_weights_updated(); any torch-side in-place update of a parameter view (torch.optim.*, the
+        # optimizers configure_optimizers() returns, manual `p.data.add_`) bumps the arena's autograd version counter,
+        # which every view shares.
         if self._weights_dirty:
             check(lib().svsr_lrw_pack_weights(self._h, self._stream()), "svsr_lrw_pack_weights")
             self._weights_dirty = False
@@ -360,9 +392,10 @@ class TransformerLightningModule(nn.Module):
             soft = labels.float().contiguous()
         skip = 0
         if self.training and self.layer_dropout > 0.0:  # host RNG per sublayer, like x-transformers' layer_dropout
-            for i in range(2 * self.depth):
+            for i in range(2 * self.depth):  # (the engine refuses depth > 16, so 32 bits hold every sublayer)
                 if random.random() < self.layer_dropout:
                     skip |= 1 << i
+        self._last_skip = skip
         check(lib().svsr_lrw_forward(
             self._h, C.c_void_p(videos.data_ptr()), C.c_void_p(audio_tokens.data_ptr()),
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
@@ -372,9 +405,10 @@ class TransformerLightningModule(nn.Module):
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         if self.training:
             self._nbt += 1
-        m = self._metrics
         if torch.is_grad_enabled():
             m = _StepFunction.apply(self._anchor, self, self._metrics)
+        else:  # the persistent buffer is overwritten by the next forward: hand out a copy (epoch averages collect these)
+            m = self._metrics.clone()
         return {"loss_total": m[0], "loss_category": m[1], "loss_audio": m[2], "accuracy_top1": m[3],
                 "accuracy_top5": m[4]}
 
@@ -422,6 +456,7 @@ class TransformerLightningModule(nn.Module):
         if need_attach:  # zero_grad(set_to_none=True) dropped the views: start from a clean arena
             self._flat_g.zero_()
         check(lib().svsr_lrw_backward(self._h, C.c_void_p(g.data_ptr()), self._stream()), "svsr_lrw_backward")
+        allreduce_mean_(self._flat_g, self.sync_grads)
         if need_attach:
             self._attach_grads()
 
@@ -480,8 +515,7 @@ class TransformerLightningModule(nn.Module):
 
     def __del__(self):
         try:
-            if self._h:
-                lib().svsr_lrw_destroy(self._h)
+            self._engines.destroy()
         except Exception:
             pass
 

@@ -43,6 +43,30 @@ class FusedAdamW:
             self.n_decay = int(L.svsr_lrw_decay_count(module._h))
         self.n_total = p.numel()
         self.t = 0
+        self._build_segments()
+
+    def _build_segments(self) -> None:
+        """Ranges of the arena that share an Adam step count. Group 0 = everything that gets a gradient every step;
+        group 1+i = x-transformers sublayer i (`encoder.layers.<i>.*`), which layer_dropout may skip on a step -- the
+        reference's torch.optim.AdamW then leaves those parameters, their moments and their per-parameter step count
+        untouched (`p.grad is None`, lightning.py:216-221)."""
+        import re
+
+        offs = getattr(self.module, "_offsets", None) or {}
+        items = []
+        for key, (off, n, _shp, _decay) in offs.items():
+            mt = re.match(r"encoder\.layers\.(\d+)\.", key)
+            items.append((off, (n + 3) // 4 * 4, 1 + int(mt.group(1)) if mt else 0))
+        items.sort()
+        ranges = []  # [begin, group]
+        for off, _n, grp in items:
+            if not ranges or ranges[-1][1] != grp:
+                ranges.append([off, grp])
+        if not ranges or ranges[0][0] != 0:
+            ranges.insert(0, [0, 0])
+        self._seg_group = [g for _, g in ranges]
+        self._seg_begin = (C.c_int64 * (len(ranges) + 1))(*[b for b, _ in ranges], self.n_total)
+        self._group_steps: Dict[int, int] = {g: 0 for g in set(self._seg_group)}
 
     @classmethod
     def from_config(cls, module: TransformerLightningModule) -> "FusedAdamW":
@@ -54,16 +78,26 @@ class FusedAdamW:
     def zero_grad(self) -> None:
         self.module.flat_grads.zero_()
 
-    def step(self, lr: Optional[float] = None, grad_div: float = 1.0) -> None:
+    def step(self, lr: Optional[float] = None, grad_div: float = 1.0, skip_mask: Optional[int] = None) -> None:
+        """skip_mask: bit i set = x-transformers sublayer i was dropped in the forward this gradient came from (default:
+        the module's last forward). Dropped sublayers are left untouched, like `p.grad is None` under torch.optim.AdamW."""
         self.t += 1
         m = self.module
-        check(lib().svsr_adamw_step(
+        if skip_mask is None:
+            skip_mask = int(getattr(m, "_last_skip", 0))
+        for g in self._group_steps:
+            if g == 0 or not (skip_mask >> (g - 1)) & 1:
+                self._group_steps[g] += 1
+        nseg = len(self._seg_group)
+        steps = (C.c_int32 * nseg)(*[
+            0 if (g > 0 and (skip_mask >> (g - 1)) & 1) else self._group_steps[g] for g in self._seg_group])
+        check(lib().svsr_adamw_step_segmented(
             C.c_void_p(m.flat_params.data_ptr()), C.c_void_p(m.flat_grads.data_ptr()),
             C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_int64(self.n_decay),
             C.c_int64(self.n_total), C.c_float(self.lr if lr is None else lr), C.c_float(self.betas[0]),
-            C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.weight_decay), C.c_int(self.t),
-            C.c_float(self.max_grad_norm), C.c_float(grad_div), C.c_void_p(self.scratch.data_ptr()),
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "svsr_adamw_step")
+            C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.weight_decay), self._seg_begin, steps,
+            C.c_int(nseg), C.c_float(self.max_grad_norm), C.c_float(grad_div), C.c_void_p(self.scratch.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "svsr_adamw_step_segmented")
         m.mark_weights_updated()
 
     def grad_norm(self) -> torch.Tensor:
@@ -105,6 +139,7 @@ class DataParallelStep:
         self._graphs: Dict[tuple, dict] = {}
         self._graph_gen = None      # engine generation the cached graphs were captured against
         self._static_inputs = None  # used once more than MAX_GRAPH_SETS distinct input buffer sets have been seen
+        self._static: Dict[int, tuple] = {}  # ... per engine
         self.graph_launches = 0     # kernels launched by graph replays (the library's counter only sees captures)
         self.graph_replays = 0
         lib().svsr_launch_count.restype = C.c_longlong
@@ -113,7 +148,8 @@ class DataParallelStep:
     def _forward(self, batch):
         self.opt.zero_grad()
         with torch.no_grad():
-            return self.module(*batch)
+            out = self.module(*batch)
+        return out
 
     def _backward(self, stage: int) -> None:
         m = self.module
@@ -158,21 +194,26 @@ class DataParallelStep:
 
     def _graph_entry(self, batch):
         gen = getattr(self.module, "_engine_gen", 0)
-        if gen != self._graph_gen:  # the engine (workspace, handle) was rebuilt for another clip geometry
-            self._graphs.clear()
-            self._static_inputs = None
+        if gen != self._graph_gen:  # another clip geometry = another engine: its graphs are kept while it is alive
+            alive = self.module._engines.alive
+            for k in [k for k in self._graphs if not alive(k[0])]:
+                del self._graphs[k]
+            for g in [g for g in self._static if not alive(g)]:
+                del self._static[g]
             self._graph_gen = gen
-        key = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in batch if isinstance(t, torch.Tensor))
+        self._static_inputs = self._static.get(gen)
+        key = (gen,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in batch if isinstance(t, torch.Tensor))
         ent = self._graphs.get(key)
-        if ent is None and self._static_inputs is None and len(self._graphs) >= self.MAX_GRAPH_SETS:
+        if ent is None and self._static_inputs is None and sum(k[0] == gen for k in self._graphs) >= self.MAX_GRAPH_SETS:
             # the caller hands over fresh tensors every step: copy them into one static set from now on
-            self._static_inputs = tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in batch)
+            self._static_inputs = self._static[gen] = tuple(
+                t.clone() if isinstance(t, torch.Tensor) else t for t in batch)
         if self._static_inputs is not None and ent is None:
             for d, src in zip(self._static_inputs, batch):
                 if isinstance(d, torch.Tensor):
                     d.copy_(src, non_blocking=True)
             batch = self._static_inputs
-            key = ("static",)
+            key = (gen, "static")
             ent = self._graphs.get(key)
         if ent is None:
             ent = self._graphs[key] = self._capture(batch)
@@ -218,8 +259,9 @@ class DataParallelStep:
                 if self._hi is not None:
                     torch.cuda.set_stream(cur)
                     cur.wait_stream(self._hi)
-        self.global_step += 1
+        # the reference's scheduler is stepped AFTER optimizer.step(): step k (0-based) runs at lr(k), lr(0) = 0
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
+        self.global_step += 1
         self.opt.step(lr=lr, grad_div=float(self.world))
         return metrics
 
@@ -242,8 +284,8 @@ class SentenceDataParallelStep:
         check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
         if self.world > 1:
             dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
-        self.global_step += 1
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
+        self.global_step += 1
         self.opt.step(lr=lr, grad_div=float(self.world))
         return out
 

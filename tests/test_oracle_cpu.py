@@ -113,3 +113,21 @@ def test_oracle_matches_live_reference_module():
     o = O.lrw_forward({k: v.clone() for k, v in P.items()}, videos, tokens, labels, wm, depth=2)
     for k in ("loss_total", "loss_category", "loss_audio", "accuracy_top1", "accuracy_top5"):
         assert float(o[k]) == pytest.approx(float(r[k]), rel=1e-6, abs=1e-7), k
+
+
+def test_eager_baseline_module_equals_oracle():
+    """bench.py's `--impl eager` / `gpu_baseline` arm (oracle/eager_module.py: the reference's module graph from stock
+    torch.nn modules) computes the same function as the pinned oracle on the same state dict."""
+    from oracle.eager_module import EagerLRW
+
+    torch.manual_seed(0)
+    P = O.make_params(21, depth=2)
+    videos, tokens, labels, wm = O.make_inputs(22, 2)
+    m = EagerLRW(depth=2).train()
+    m.load_oracle_params(P)
+    out = m(videos, tokens, labels, wm)
+    ref = O.lrw_forward(P, videos, tokens, labels, wm, depth=2)
+    for k in ("loss_total", "loss_category", "loss_audio"):
+        assert float(out[k]) == pytest.approx(float(ref[k]), rel=1e-5), k
+    assert torch.allclose(out["last_hidden_state"], ref["last_hidden_state"], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(out["logits_audio"], ref["logits_audio"], rtol=1e-4, atol=1e-4)

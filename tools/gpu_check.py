@@ -151,7 +151,21 @@ def case_gemm_wgrad(M, N, K):
 def case_rowshift():
     import ctypes as C
     import torch
+    import subprocess
+    from pathlib import Path
     from syncvsr_b200._lib import check, lib, ptr, stream_ptr
+
+    # the probe lives outside the product library: build it on demand against libsvsr.so (tensor-map + error helpers)
+    root = Path(__file__).resolve().parent
+    out_dir = root / "probes" / "_build"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    so = out_dir / "libprobe.so"
+    pkg = root.parent / "syncvsr_b200"
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                    "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-o", str(so), str(root / "probes" / "debug_probe.cu"),
+                    f"-L{pkg}", "-lsvsr", f"-Xlinker=-rpath={pkg}", "-lcuda"], check=True)
+    lib()  # libsvsr.so first (RTLD_GLOBAL not needed: the probe links against it)
+    probe = C.CDLL(str(so))
 
     g = torch.Generator(device="cuda").manual_seed(6)
     res = []
@@ -161,7 +175,7 @@ def case_rowshift():
         b = torch.randn(256 if mn else 64, 64, device="cuda", generator=g).to(torch.bfloat16)
         for shift in (0, 8, 1, 3, 13, 50):
             out = torch.zeros(128, 64, device="cuda")
-            check(lib().svsr_debug_rowshift(ptr(a), ptr(b), ptr(out), C.c_int(shift), C.c_int(mode), stream_ptr()),
+            check(probe.svsr_debug_rowshift(ptr(a), ptr(b), ptr(out), C.c_int(shift), C.c_int(mode), stream_ptr()),
                   "rowshift")
             torch.cuda.synchronize()
             if mn:

@@ -1,9 +1,10 @@
-// Hardware probe (developer tool, reachable through svsr_debug_rowshift): does a UMMA shared-memory descriptor
+// Hardware probe (developer tool, NOT part of libsvsr.so: tools/gpu_check.py builds it on demand into
+// tools/probes/_build/libprobe.so and calls svsr_debug_rowshift from there): does a UMMA shared-memory descriptor
 // whose start address is offset by a whole number of 128-byte rows (not a multiple of the 1024-byte swizzle atom)
 // still address a SWIZZLE_128B tile correctly? This decides whether one halo tile in shared memory can serve all
 // filter taps of a convolution (tap shift == row offset) instead of one TMA load per tap.
-#include "common.cuh"
-#include "tmap.h"
+#include "../../syncvsr_b200/csrc/common.cuh"
+#include "../../syncvsr_b200/csrc/tmap.h"
 
 namespace svsr {
 
@@ -109,3 +110,7 @@ int debug_rowshift(const void* a, const void* b, float* out, int shift, int mode
 }
 
 }  // namespace svsr
+
+extern "C" int svsr_debug_rowshift(const void* a, const void* b, float* out, int shift, int mode, void* stream) {
+  return svsr::debug_rowshift(a, b, out, shift, mode, static_cast<cudaStream_t>(stream));
+}
