@@ -219,6 +219,201 @@ def run_eager_arm(args):
 
 
 # -------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] (C5): audio-head stress -- seq 400, A=4, G=8, V=1024 (32 768 logits per frame), H=768, B=16/GPU.
+# A step = fused head forward (projection + reshape + log-softmax + NLL, svsr_audio_head_fwd) + backward (recompute ->
+# d logits bf16, input-gradient GEMM, weight-gradient GEMM). No exchange step exists on this path: ranks are replicas.
+# -------------------------------------------------------------------------------------------------------------------
+def head_stress(steps: int, warmup: int, B: int = 16, H: int = 768, seed: int = 0):
+    import torch
+
+    from syncvsr_b200 import ops
+
+    T_, A, G, V = 400, 4, 8, 1024
+    N, M = A * G * V, B * T_
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(M, H, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, H, device="cuda", generator=g) * 0.02).bfloat16()
+    wt = w.t().contiguous()
+    bias = torch.zeros(N, device="cuda")
+    tokens = torch.randint(0, V, (B, T_ * A, G), device="cuda", generator=g)
+    head = ops.AudioHead(B, T_, A, G, V, H)
+    dx = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros(N, H, device="cuda")
+
+    def step():
+        loss = head.forward(x, w, bias, tokens)
+        head.backward(x, w, wt, bias, tokens, dx=dx, dw=dw, want_db=False)
+        return loss
+
+    for _ in range(warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fused_bytes = M * H * 2 + N * H * 2 + tokens.numel() * 8 + M * H * 2 + N * H * 4  # X + W + tokens + dX + dW
+    moved_bytes = fused_bytes + 3 * M * N * 2  # + d logits written once, read by the two gradient GEMMs
+    flops = 3 * 2.0 * M * N * H                # algorithmic: projection + dX + dW (the recompute is not counted)
+    return {"workload": f"audio-head stress: seq 400, A=4, G=8, V=1024, H={H}, B={B} (BASELINE configs[4])",
+            "ms_per_step": ms, "frames_per_s": M * 1e3 / ms, "loss": float(loss), "algorithmic_tflops": flops / ms / 1e9,
+            "algorithmic_MB": fused_bytes / 1e6, "algorithmic_GBps": fused_bytes / ms / 1e6,
+            "designed_traffic_MB": moved_bytes / 1e6,
+            "note": "fp32 logits never written; d logits cross HBM once in bf16 (TMEM cannot hold a [128 x H] dX accumulator "
+                    "next to the logits tile, DESIGN.md section 3)"}
+
+
+def run_head_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    r = head_stress(args.steps, max(args.warmup, 3), seed=rank)
+    ms = r["ms_per_step"]
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        tf = r["algorithmic_tflops"] * r["ms_per_step"] / ms
+        print(json.dumps({
+            "metric": "frames/sec through the fused audio head (fwd+bwd), seq 400 x 32768 logits/frame", "config_id": "c5",
+            "value": world * 6400 * 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": r["workload"], "parallelism": f"replicas x{world} (no exchange step on this path)",
+                       "l2": "per-step working set 0.6 GB >> 126 MB L2", "loss": r["loss"]},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_MB": r["algorithmic_MB"], "designed_traffic_MB": r["designed_traffic_MB"]},
+            "clocks": clocks, "gpu_launches": 5 * args.steps}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] / [3] (C3 = LRS2 T=150 B=16/GPU, C4 = LRS3 T=250 B=8/GPU): the LRS sentence-level step
+# (Conformer-12L adim 768 + CTC + 6-layer decoder + audio CE), zero_grad + forward + backward + all-reduce + clip/AdamW.
+# -------------------------------------------------------------------------------------------------------------------
+LRS_FWD_GF = {150: 94.8 + 54.9 + 0.59 + 6.5, 250: 158.1 + 93.4 + 0.98 + 8.0}  # SURVEY.md 8(d), per clip, forward
+
+
+def lrs_args(lmax):
+    from types import SimpleNamespace
+
+    return SimpleNamespace(adim=768, aheads=12, eunits=3072, elayers=12, ddim=768, dheads=12, dunits=3072, dlayers=6,
+                           mtlalpha=0.1, lsm_weight=0.1, dropout_rate=0.0, transformer_attn_dropout_rate=0.0,
+                           transformer_input_layer="conv3d", transformer_encoder_attn_layer_type="rel_mha",
+                           macaron_style=True, use_cnn_module=True, cnn_module_kernel=31, zero_triu=False,
+                           a_upsample_ratio=1, relu_type="swish", transformer_length_normalized_loss=False,
+                           ctc_type="builtin", rel_pos_type="latest", codec="wav2vec2", audio_weight=10.0,
+                           max_label_len=lmax)
+
+
+def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: int = 1):
+    import torch
+    import torch.distributed as dist
+
+    from syncvsr_b200.e2e import E2E
+    from syncvsr_b200.train import FusedAdamW, SentenceDataParallelStep
+
+    Lmax = 40
+    torch.manual_seed(1234)
+    m = E2E(5049, lrs_args(Lmax)).train()
+    opt = FusedAdamW(m, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.03, max_grad_norm=5.0)
+    dp = SentenceDataParallelStep(m, opt)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.randn(B, T_, 1, S, S, device="cuda", generator=g)
+    lengths = torch.randint(T_ // 2, T_ + 1, (B,), device="cuda", generator=g)
+    lengths[0] = T_
+    for b in range(B):
+        x[b, int(lengths[b]):] = 0
+    tokens = torch.randint(0, 640, (B, 2 * T_, 2), device="cuda", generator=g)
+    label = torch.full((B, Lmax), -1, dtype=torch.long, device="cuda")
+    for b in range(B):
+        n = int(torch.randint(10, Lmax + 1, (1,), generator=g, device="cuda"))
+        label[b, :n] = torch.randint(1, 5048, (n,), device="cuda", generator=g)
+    label[0, :] = torch.randint(1, 5048, (Lmax,), device="cuda", generator=g)
+
+    def step():
+        out = dp(x, lengths, tokens, label)
+        m._ensure(x, Lmax)  # the bf16 weight repack belongs to the step
+        return out
+
+    for _ in range(warmup):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gf = LRS_FWD_GF.get(T_, LRS_FWD_GF[150] * T_ / 150) * 3 - 1.76 * T_ / 29
+    res = {"ms_per_step": ms, "clips_per_s": world * B * 1e3 / ms, "frames_per_s": world * B * T_ * 1e3 / ms,
+           "algorithmic_tflops_per_gpu": B * gf / ms, "loss": [float(v) for v in out[:4]], "acc": float(out[4]),
+           "workspace_gb": m._ws.numel() / 2 ** 30, "params_M": m.flat_params.numel() / 1e6}
+    del dp, opt, m
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_lrs_arm(args, T_: int, B: int, cid: str):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    r = lrs_step_ms(args.steps, max(args.warmup, 3), T_, B, rank, world)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peak_tf, _, peak_src = measured_peaks()
+        print(json.dumps({
+            "metric": f"clips/sec (fwd+bwd) LRS-shape [B,{T_},1,88,88]", "config_id": cid, "value": r["clips_per_s"],
+            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"LRS E2E step: Conformer-12L adim 768 + CTC + decoder-6L + audio CE, x[{B},{T_},1,88,88] "
+                                   f"per GPU, fwd+bwd+allreduce+AdamW (BASELINE configs[{2 if T_ == 150 else 3}])",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "loss": r["loss"], "acc": r["acc"],
+                       "frames_per_s": r["frames_per_s"], "workspace_gb": r["workspace_gb"]},
+            "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": r["algorithmic_tflops_per_gpu"],
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": r["algorithmic_tflops_per_gpu"] / peak_tf,
+                         "peak_source": peak_src, "traffic": None},
+            "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------------------------------------
 # native arm
 # -------------------------------------------------------------------------------------------------------------------
 def run_native_arm(args):
@@ -383,6 +578,16 @@ def run_native_arm(args):
     if world == 1 and not args.no_gpu_baseline:
         del pipe, step, opt, model
         torch.cuda.empty_cache()
+        # the other BASELINE configs, measured in the same run on the same GPU (their own arms: --config c3 | c4 | c5)
+        also = {}
+        try:
+            also["c5_audio_head_stress"] = head_stress(steps=10, warmup=3)
+            peak_tf_, _, _ = measured_peaks()
+            also["c5_audio_head_stress"]["frac_of_tensor_peak"] = also["c5_audio_head_stress"]["algorithmic_tflops"] / peak_tf_
+            also["c3_lrs2_T150_B16"] = lrs_step_ms(steps=5, warmup=3, T_=150, B=16)
+        except Exception as ex:  # never lose the headline line to a side measurement
+            also["error"] = repr(ex)
+        line["also"] = also
         gcps, gms, gloss = eager_clips_per_s(steps=min(args.steps, 10), warmup=5, batch=B)
         line["gpu_baseline"] = {"value": gcps, "unit": "clips/s", "ms_per_step": gms, "kind": "torch.cuda eager",
                                 "native_over_eager": value / gcps, "loss_total": gloss,
@@ -405,6 +610,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "eager"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config: c2 = LRW B=64/GPU (the headline, default), c3 / c4 = LRS2 / LRS3 step, "
+                         "c5 = audio-head stress")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the step's launches from a CUDA graph (train.py)")
@@ -415,6 +623,10 @@ def main():
         run_reference_arm(args)
     elif args.impl == "eager":
         run_eager_arm(args)
+    elif args.config == "c5":
+        run_head_arm(args)
+    elif args.config in ("c3", "c4"):
+        run_lrs_arm(args, 150 if args.config == "c3" else 250, 16 if args.config == "c3" else 8, args.config)
     else:
         run_native_arm(args)
 

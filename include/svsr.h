@@ -145,6 +145,20 @@ int svsr_geglu_bwd(const void* h, const void* du, void* dh, int M, int F, float 
  * dlogits (bf16, optional) = (softmax - onehot) * dscale; *bad_token = 1 if a token is outside [0,V). */
 int svsr_audio_ce(const float* logits, int ld, const int64_t* tokens, int64_t tok_stride_b, int B, int T, int A, int G,
                   int V, void* dlogits, double* acc, int* bad_token, float dscale, void* stream);
+/* The fused audio head: `audio_projection` + reshape [B,T,A*G,V] + log-softmax + NLL in ONE tcgen05 kernel per direction
+ * (LRW/video/src/lightning.py:82,168-171; LRS twin e2e_asr_transformer.py:142/157,198-201; README.md:47-53). The fp32
+ * logits live only in TMEM / registers, never in HBM; target indexing tokens[b*tok_stride_b + (t*A+a)*G + g] is int64.
+ *  x bf16 [B*T, ldx] (K = hidden columns, multiple of 64), w bf16 [A*G*V, ldw], bias fp32 [A*G*V] or null; V % 64 == 0.
+ *  fwd: part = scratch of B*T * (A*G*V/64) float2, xt / lse = fp32 [B*T*A*G]; *loss_sum (fp64) += sum_rows (lse - x[target]);
+ *       *bad_token = 1 when a token is outside [0,V) (that row adds nothing; its gradient row is zero).
+ *  bwd: recomputes the projection tile by tile and writes dlogits bf16 [B*T, A*G*V] = (softmax - onehot) * dscale
+ *       (* *grad_scale, optional device scalar) -- the operand of svsr_gemm_bf16 (dX = dlogits.W) and svsr_gemm_wgrad. */
+int svsr_audio_head_fwd(const void* x, int ldx, const void* w, int ldw, int K, const float* bias, const int64_t* tokens,
+                        int64_t tok_stride_b, int B, int T, int A, int G, int V, void* part, float* xt, float* lse,
+                        double* loss_sum, int* bad_token, void* stream);
+int svsr_audio_head_bwd(const void* x, int ldx, const void* w, int ldw, int K, const float* bias, const int64_t* tokens,
+                        int64_t tok_stride_b, int B, int T, int A, int G, int V, const float* lse, float dscale,
+                        const float* grad_scale, void* dlogits, int* bad_token, void* stream);
 /* F.cross_entropy(logits_category, labels, label_smoothing) with int64 or soft fp32 labels (lightning.py:161-165);
  * acc[1] += sum loss, acc[2] += #top1, acc[3] += #top5 (lightning.py:177-183). */
 int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const float* soft_labels, int B, int C,
@@ -213,6 +227,10 @@ int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* 
 /* (*grad_scale) * d loss_total / d params accumulated (+=) into the gradient arena; grad_scale is a DEVICE fp32
  * scalar (the upstream gradient autograd hands to loss_total) or NULL for 1. One backward per forward. */
 int svsr_lrw_backward(void* handle, const float* grad_scale, void* stream);
+/* The native step never writes the audio logits to HBM (the projection is fused with reshape + log-softmax + NLL,
+ * lightning.py:168-171); this call materialises `logits_audio` (fp32 [B*T, A*G*V], svsr_lrw_tensor("logits_audio")) once
+ * from the last forward's hidden states, for inspection / parity tests. */
+int svsr_lrw_logits_audio(void* handle, void* stream);
 /* The same backward in two stages so that the data-parallel step can overlap communication with compute:
  * stage 0 = loss heads + encoder + mean-pool (completes the gradient arena range returned by
  * svsr_lrw_early_grad_region: cls_token, encoder and head weights, ~160 MB), stage 1 = ResNet trunk + stem. */
@@ -360,6 +378,8 @@ int svsr_lrs_backward(void* handle, const float* grad_scale, void* stream);
 /* named tensors: encoder_out, embed_out, frontend, logits_audio, ctc_logits, pred, ys_in, ys_out, layer<i>.x<k>;
  * dtype 0=f32 1=bf16 2=u8 3=i32 4=i64 */
 int svsr_lrs_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);
+/* LRS twin of svsr_lrw_logits_audio: fills "logits_audio" (fp32 [B*T, A*G*V]) from the last forward's encoder output. */
+int svsr_lrs_logits_audio(void* handle, void* stream);
 
 /* Fused global-norm clip + AdamW over the flat arenas (lightning.py:216-221; Trainer gradient_clip_val). The arena
  * is [decayed | non-decayed]: the first n_decay elements get weight decay. grad_div divides gradients first (world

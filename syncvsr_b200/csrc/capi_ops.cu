@@ -5,6 +5,7 @@
 #include "elementwise.cuh"
 #include "encoder.cuh"
 #include "heads.cuh"
+#include "igemm.cuh"
 #include "conformer.cuh"
 
 using namespace svsr;
@@ -107,6 +108,49 @@ int svsr_audio_ce(const float* logits, int ld, const int64_t* tokens, int64_t to
   return audio_ce(logits, ld, reinterpret_cast<const long long*>(tokens), tok_stride_b, B, T, A, G, V,
                   static_cast<bf16*>(dlogits), acc, bad_token, dscale, ST(stream));
 }
+// ---- fused audio head (igemm.cuh IgemmCe; heads.cuh ce_finalize) ----
+static int audio_head_problem(IgemmProblem& p, const void* x, int ldx, const void* w, int ldw, int K, const float* bias,
+                              const int64_t* tokens, int64_t tok_stride_b, int B, int T, int A, int G, int V,
+                              int* bad_token) {
+  SVSR_REQUIRE(x && w && tokens && bad_token, "audio_head: null pointer");
+  SVSR_REQUIRE(B > 0 && T > 0 && A > 0 && G > 0 && V > 0 && V % 64 == 0 && K > 0 && K % 64 == 0,
+               "audio_head: B=%d T=%d A=%d G=%d V=%d (multiple of 64) K=%d (multiple of 64)", B, T, A, G, V, K);
+  SVSR_REQUIRE(tok_stride_b >= (int64_t)T * A * G, "audio_head: audio_tokens has fewer than T*alignment rows per clip");
+  p.a = x, p.a_N = B * T, p.a_C = ldx, p.cin = K, p.ntaps = 1;
+  p.o_N = B * T;
+  p.b = w, p.b_rows = A * G * V, p.b_cols = ldw;
+  p.bias = bias;
+  p.ldc = A * G * V;
+  p.ce.T = T, p.ce.A = A, p.ce.G = G, p.ce.V = V, p.ce.AG = A * G;
+  p.ce.tokens = reinterpret_cast<const long long*>(tokens), p.ce.tok_stride_b = tok_stride_b;
+  p.ce.bad_token = bad_token;
+  return SVSR_OK;
+}
+int svsr_audio_head_fwd(const void* x, int ldx, const void* w, int ldw, int K, const float* bias, const int64_t* tokens,
+                        int64_t tok_stride_b, int B, int T, int A, int G, int V, void* part, float* xt, float* lse,
+                        double* loss_sum, int* bad_token, void* stream) {
+  SVSR_REQUIRE(part && xt && lse && loss_sum, "audio_head_fwd: null buffer");
+  IgemmProblem p;
+  int rc = audio_head_problem(p, x, ldx, w, ldw, K, bias, tokens, tok_stride_b, B, T, A, G, V, bad_token);
+  if (rc) return rc;
+  p.ce.mode = 1, p.ce.part = static_cast<float2*>(part), p.ce.xt = xt;
+  rc = igemm_launch(p, ST(stream));
+  if (rc) return rc;
+  return ce_finalize(static_cast<const float2*>(part), xt, p.ce.tokens, tok_stride_b, B, T, A, G, V, lse, loss_sum,
+                     ST(stream));
+}
+int svsr_audio_head_bwd(const void* x, int ldx, const void* w, int ldw, int K, const float* bias, const int64_t* tokens,
+                        int64_t tok_stride_b, int B, int T, int A, int G, int V, const float* lse, float dscale,
+                        const float* grad_scale, void* dlogits, int* bad_token, void* stream) {
+  SVSR_REQUIRE(lse && dlogits, "audio_head_bwd: null buffer");
+  IgemmProblem p;
+  int rc = audio_head_problem(p, x, ldx, w, ldw, K, bias, tokens, tok_stride_b, B, T, A, G, V, bad_token);
+  if (rc) return rc;
+  p.ce.mode = 2, p.ce.lse = lse, p.ce.dscale = dscale, p.ce.grad_scale = grad_scale;
+  p.out = dlogits;
+  return igemm_launch(p, ST(stream));
+}
+
 int svsr_category_ce(const float* logits, int ld, const int64_t* labels, const float* soft_labels, int B, int C,
                      float eps, void* dlogits, int ldd, double* acc, float dscale, void* stream) {
   return category_ce(logits, ld, reinterpret_cast<const long long*>(labels), soft_labels, B, C, eps,

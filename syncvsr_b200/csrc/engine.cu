@@ -54,6 +54,7 @@ struct LrwEngine : EngineBase {
   // workspace offsets
   size_t xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a, logits_c, dlogits_c, acc,
       bad_token, rot;
+  size_t ce_part, ce_xt, ce_lse, ce_tok;  // fused audio head: per-slot (max, sum) partials, target logits, lse, token copy
   size_t pack_jobs;  // device table for the single-launch weight repack
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
@@ -69,6 +70,10 @@ struct LrwEngine : EngineBase {
   bool bwd_stage0_done = false;
 
   float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * Dp; }
+  // audio_projection + reshape + log-softmax + NLL in the GEMM epilogue (igemm.cuh, IgemmCe): softmax width % 64 == 0
+  bool fused_head() const {
+    return cfg.audio_vocab % 64 == 0 && cfg.audio_alignment * cfg.vq_groups * cfg.audio_vocab >= 128;
+  }
 };
 
 static int engine_build(LrwEngine& e, long long nodecay_base) {
@@ -213,6 +218,10 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.acc = b.take(8 * sizeof(double));
   e.bad_token = b.take(sizeof(int));
   e.rot = b.take((size_t)(c.T + 1) * 32 * 4);
+  e.ce_part = b.take((size_t)e.N * (AGV / 64) * sizeof(float2));
+  e.ce_xt = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 4);
+  e.ce_lse = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 4);
+  e.ce_tok = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 8);
   // ---- backward scratch ----
   e.dx = b.take((size_t)e.M * Dp * 4);
   for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * Dp * 2);
@@ -355,6 +364,31 @@ static int lw_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, 
     RC(unpack_linear_wgrad(bt, e.G + l.b, l.N, 1, 1, 1, s));
   }
   return SVSR_OK;
+}
+
+// audio_projection fused with reshape + log-softmax + NLL (lightning.py:168-171): mode 1 = forward (per-slot partials +
+// target logits, no logits in HBM), mode 2 = backward (tile recomputed, d logits emitted in bf16). The audio tokens of
+// the step were copied into the workspace by the forward ([B, T*A, G] contiguous), so backward needs no caller memory.
+static int audio_head_gemm(const LrwEngine& e, int mode, const float* grad_scale, cudaStream_t s) {
+  const svsr_lrw_config& c = e.cfg;
+  const LinRef& l = e.aud;
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
+  IgemmProblem p;
+  p.a = e.ws<bf16>(e.lastb_frames), p.a_N = e.N, p.a_C = e.Dp, p.cin = l.Kp, p.ntaps = 1;
+  p.o_N = e.N;
+  p.b = e.ws<bf16>(l.wb), p.b_rows = l.Np, p.b_cols = l.Kp;
+  p.bias = e.P + l.b;
+  p.ldc = AGV;
+  p.out = mode == 2 ? e.ws<bf16>(e.dlogits_a) : nullptr;
+  p.ce.mode = mode;
+  p.ce.T = c.T, p.ce.A = c.audio_alignment, p.ce.G = c.vq_groups, p.ce.V = c.audio_vocab;
+  p.ce.AG = c.audio_alignment * c.vq_groups;
+  p.ce.tokens = e.ws<long long>(e.ce_tok), p.ce.tok_stride_b = (long long)c.T * c.audio_alignment * c.vq_groups;
+  p.ce.part = e.ws<float2>(e.ce_part), p.ce.xt = e.ws<float>(e.ce_xt), p.ce.lse = e.ws<float>(e.ce_lse);
+  p.ce.bad_token = e.ws<int>(e.bad_token);
+  p.ce.dscale = c.lambda_audio / (float)audio_rows, p.ce.grad_scale = grad_scale;
+  return igemm_launch(p, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -518,13 +552,25 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   // ---- heads + losses (lightning.py:161-174) ----
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   RC(lw_fwd(e, e.ws<bf16>(e.lastb_cls), Dp, c.B, e.cat, e.ws<float>(e.logits_c), e.cat_ld, 1, nullptr, s));
-  RC(lw_fwd(e, e.ws<bf16>(e.lastb_frames), Dp, e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, s));
   const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
+  {  // audio_tokens[:, :T*A] (lightning.py:147) -> workspace copy [B, T*A, G] that backward can still read
+    const size_t rowb = (size_t)c.T * c.audio_alignment * c.vq_groups * 8;
+    SVSR_CHECK_CUDA(cudaMemcpy2DAsync(e.ws<uint8_t>(e.ce_tok), rowb, tokens, (size_t)tok_stride_b * 8, rowb, c.B,
+                                      cudaMemcpyDeviceToDevice, s));
+  }
+  if (e.fused_head()) {
+    RC(audio_head_gemm(e, 1, nullptr, s));
+    RC(ce_finalize(e.ws<float2>(e.ce_part), e.ws<float>(e.ce_xt), e.ws<long long>(e.ce_tok),
+                   (long long)c.T * c.audio_alignment * c.vq_groups, c.B, c.T, c.audio_alignment, c.vq_groups,
+                   c.audio_vocab, e.ws<float>(e.ce_lse), e.ws<double>(e.acc), s));
+  } else {  // a vocabulary that is not a multiple of 64: projection, then the separate log-softmax + NLL kernel
+    RC(lw_fwd(e, e.ws<bf16>(e.lastb_frames), Dp, e.N, e.aud, e.ws<float>(e.logits_a), AGV, 1, nullptr, s));
+    RC(audio_ce(e.ws<float>(e.logits_a), AGV, e.ws<long long>(e.ce_tok), (long long)c.T * c.audio_alignment * c.vq_groups,
+                c.B, c.T, c.audio_alignment, c.vq_groups, c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc),
+                e.ws<int>(e.bad_token), c.lambda_audio / (float)audio_rows, s));
+  }
   RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing,
                  e.ws<bf16>(e.dlogits_c), e.cat_ld, e.ws<double>(e.acc), 1.0f / (float)c.B, s, e.ws<int>(e.bad_token)));
-  RC(audio_ce(e.ws<float>(e.logits_a), AGV, tokens, tok_stride_b, c.B, c.T, c.audio_alignment, c.vq_groups,
-              c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc), e.ws<int>(e.bad_token),
-              c.lambda_audio / (float)audio_rows, s));
   RC(finalize_metrics(e.ws<double>(e.acc), metrics, c.lambda_audio, c.B, audio_rows, s, e.ws<int>(e.bad_token)));
   e.last_skip = skip_mask;
   e.last_seed = dropout_seed;
@@ -688,10 +734,13 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   cudaStream_t w = e.wq;  // weight-gradient stream (set by SideQueue)
   bf16* T0 = e.ws<bf16>(e.fe.gbuf[0]);  // d loss / d (last block output): input of frontend_backward
   if (stage <= 0) {
-  if (grad_scale) {  // upstream d(loss_total): every gradient is linear in the stored logits gradients
+  // audio head: recompute the logits tile by tile and emit d logits (bf16), scaled by the upstream d(loss_total)
+  if (e.fused_head())
+    RC(audio_head_gemm(e, 2, grad_scale, s));
+  else if (grad_scale)
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)e.N * AGV, grad_scale, s));
+  if (grad_scale)  // every other gradient is linear in the stored category-logits gradient
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)c.B * e.cat_ld, grad_scale, s));
-  }
   if (e.padded) SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<float>(e.dg_pad), 0, (size_t)2 * c.depth * Dp * 4, s));
   // ---- heads: d last_hidden_state (fp32 stream gradient), weight/bias gradients ----
   RC(sq.fork());
@@ -890,6 +939,16 @@ int svsr_lrw_backward_stage(void* h, const float* grad_scale, int stage, void* s
   SVSR_REQUIRE(stage == 0 || stage == 1, "lrw_backward_stage: stage must be 0 or 1");
   return engine_backward(*e, grad_scale, stage, static_cast<cudaStream_t>(stream));
 }
+// The step never writes the audio logits to HBM (fused head); this materialises them once, on request, from the last
+// forward's hidden states: fp32 [B*T, A*G*V] readable through svsr_lrw_tensor("logits_audio").
+int svsr_lrw_logits_audio(void* h, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  const svsr_lrw_config& c = e->cfg;
+  const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
+  return lw_fwd(*e, e->ws<bf16>(e->lastb_frames), e->Dp, e->N, e->aud, e->ws<float>(e->logits_a), AGV, 1, nullptr,
+                static_cast<cudaStream_t>(stream));
+}
 int svsr_lrw_early_grad_region(void* h, int64_t* begin, int64_t* end) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   *begin = e->cls_off, *end = e->decay_count;
@@ -913,7 +972,7 @@ int svsr_lrw_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* 
     *ptr = e->xs_buf(0), *numel = (int64_t)e->M * e->Dp, *dtype = 0;
     return SVSR_OK;
   }
-  if (n == "logits_audio") return set(e->logits_a, (int64_t)e->N * AGV, 0);
+  if (n == "logits_audio") return set(e->logits_a, (int64_t)e->N * AGV, 0);  // filled by svsr_lrw_logits_audio()
   if (n == "logits_category") return set(e->logits_c, (int64_t)c.B * e->cat_ld, 0);
   if (n == "stem_conv") return set(e->fe.y0, (int64_t)e->N * e->fe.H0 * e->fe.H0 * 64, 1);
   if (n == "stem_out") return set(e->fe.x1, (int64_t)e->N * e->fe.H1 * e->fe.H1 * 64, 1);

@@ -45,6 +45,9 @@ struct LrsEngine : EngineBase {
   std::vector<DecLayerRef> dec;
 
   size_t feats, pe_rel, klen, xs, enc_f32, enc_b, logits_a, dlogits_a, logits_c, dlogits_c, ctc_scratch;
+  size_t ce_part = 0, ce_xt = 0, ce_lse = 0, ce_tok = 0;  // fused audio head (igemm.cuh IgemmCe)
+  // audio_classifier + unflatten + log-softmax + NLL in the GEMM epilogue: softmax width % 64 == 0
+  bool fused_head() const { return AGV >= 128 && cfg.audio_vocab % 64 == 0; }
   size_t ys_in, ys_out, xd, dec_yn, pred, dpred, acc, bad_token, pe_drop, enc_ctc;
   size_t bn_stats_arena = 0, bn_stats_bytes = 0;
   // backward scratch
@@ -124,6 +127,29 @@ int lin_dgrad(const EngineBase& e, const bf16* dy, int ldy, int rows, const LinR
   p.out = out, p.out_fp32 = out_fp32, p.ldc = ldc;
   p.resid = resid, p.resid_fp32 = 1;
   p.alpha = alpha, p.relu_mask = relu_mask;
+  return igemm_launch(p, s);
+}
+
+// audio_classifier fused with unflatten + log-softmax + NLL (e2e_asr_transformer.py:198-201): mode 1 = forward, mode 2 =
+// backward (recompute, emit d logits bf16). Tokens were copied to the workspace ([B, T*A, G] contiguous) by the forward.
+int lrs_audio_head_gemm(const LrsEngine& e, int mode, const float* grad_scale, cudaStream_t s) {
+  const svsr_lrs_config& c = e.cfg;
+  const LinRef& l = e.aud;
+  const long long audio_rows = (long long)e.M * c.audio_alignment * c.vq_groups;
+  IgemmProblem p;
+  p.a = e.ws<bf16>(e.enc_b), p.a_N = e.M, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
+  p.o_N = e.M;
+  p.b = e.ws<bf16>(l.wb), p.b_rows = l.N, p.b_cols = l.K;
+  p.bias = l.b >= 0 ? e.P + l.b : nullptr;
+  p.ldc = e.AGV;
+  p.out = mode == 2 ? e.ws<bf16>(e.dlogits_a) : nullptr;
+  p.ce.mode = mode;
+  p.ce.T = c.T, p.ce.A = c.audio_alignment, p.ce.G = c.vq_groups, p.ce.V = c.audio_vocab;
+  p.ce.AG = c.audio_alignment * c.vq_groups;
+  p.ce.tokens = e.ws<long long>(e.ce_tok), p.ce.tok_stride_b = (long long)c.T * c.audio_alignment * c.vq_groups;
+  p.ce.part = e.ws<float2>(e.ce_part), p.ce.xt = e.ws<float>(e.ce_xt), p.ce.lse = e.ws<float>(e.ce_lse);
+  p.ce.bad_token = e.ws<int>(e.bad_token);
+  p.ce.dscale = c.audio_weight / (float)audio_rows, p.ce.grad_scale = grad_scale;
   return igemm_launch(p, s);
 }
 
@@ -275,6 +301,11 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
   const size_t agv = e.AGV > 0 ? e.AGV : 64;
   e.logits_a = b.take((size_t)M * agv * 4);
   e.dlogits_a = b.take((size_t)M * agv * 2);
+  {
+    const size_t ag = (size_t)(c.audio_alignment * c.vq_groups > 0 ? c.audio_alignment * c.vq_groups : 1);
+    e.ce_part = b.take((size_t)M * (agv / 64) * sizeof(float2));
+    e.ce_xt = b.take((size_t)M * ag * 4), e.ce_lse = b.take((size_t)M * ag * 4), e.ce_tok = b.take((size_t)M * ag * 8);
+  }
   e.logits_c = b.take((size_t)M * e.ldv * 4);
   e.dlogits_c = b.take((size_t)M * e.ldv * 2);
   e.ctc_scratch = b.take(ctc_scratch_bytes(c.B, T, c.Lmax));
@@ -432,10 +463,19 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
   const int has_audio = (e.AGV > 0 && tokens) ? 1 : 0;
   const long long audio_rows = (long long)M * c.audio_alignment * c.vq_groups;
   if (has_audio) {
-    RC(lin_fwd(e, enc_b, M, e.aud, e.ws<float>(e.logits_a), e.AGV, 1, nullptr, 1.f, 0, s));
-    RC(audio_ce(e.ws<float>(e.logits_a), e.AGV, tokens, tok_stride_b, c.B, T, c.audio_alignment, c.vq_groups,
-                c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc), e.ws<int>(e.bad_token),
-                c.audio_weight / (float)audio_rows, s));
+    const long long tsb = (long long)T * c.audio_alignment * c.vq_groups;
+    SVSR_CHECK_CUDA(cudaMemcpy2DAsync(e.ws<uint8_t>(e.ce_tok), (size_t)tsb * 8, tokens, (size_t)tok_stride_b * 8,
+                                      (size_t)tsb * 8, c.B, cudaMemcpyDeviceToDevice, s));
+    if (e.fused_head()) {
+      RC(lrs_audio_head_gemm(e, 1, nullptr, s));
+      RC(ce_finalize(e.ws<float2>(e.ce_part), e.ws<float>(e.ce_xt), e.ws<long long>(e.ce_tok), tsb, c.B, T,
+                     c.audio_alignment, c.vq_groups, c.audio_vocab, e.ws<float>(e.ce_lse), e.ws<double>(e.acc), s));
+    } else {
+      RC(lin_fwd(e, enc_b, M, e.aud, e.ws<float>(e.logits_a), e.AGV, 1, nullptr, 1.f, 0, s));
+      RC(audio_ce(e.ws<float>(e.logits_a), e.AGV, e.ws<long long>(e.ce_tok), tsb, c.B, T, c.audio_alignment, c.vq_groups,
+                  c.audio_vocab, e.ws<bf16>(e.dlogits_a), e.ws<double>(e.acc), e.ws<int>(e.bad_token),
+                  c.audio_weight / (float)audio_rows, s));
+    }
   }
   // ---- CTC (ctc.py:83-151) ----
   const bf16* enc_ctc = enc_b;  // ctc_lo(dropout(hs_pad)), ctc.py:97
@@ -550,8 +590,10 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   const float pd = e.pd, pa = e.pa;
   SideQueue sq(e, s);
   cudaStream_t w = e.wq;
+  if (e.last_audio && e.fused_head()) RC(lrs_audio_head_gemm(e, 2, grad_scale, s));
   if (grad_scale) {
-    if (e.last_audio) RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)M * e.AGV, grad_scale, s));
+    if (e.last_audio && !e.fused_head())
+      RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_a), (long long)M * e.AGV, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dlogits_c), (long long)M * e.ldv, grad_scale, s));
     RC(scale_bf16_by_device_scalar(e.ws<bf16>(e.dpred), (long long)Md * e.ldv, grad_scale, s));
   }
@@ -816,6 +858,14 @@ int svsr_lrs_backward(void* h, const float* grad_scale, void* stream) {
   LrsEngine* e = static_cast<LrsEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrs: bind() first");
   return lrs_backward(*e, grad_scale, static_cast<cudaStream_t>(stream));
+}
+// The step never writes the audio logits to HBM (fused head); materialise them once, on request (svsr_lrs_tensor
+// "logits_audio"), from the last forward's encoder output.
+int svsr_lrs_logits_audio(void* h, void* stream) {
+  LrsEngine* e = static_cast<LrsEngine*>(h);
+  SVSR_REQUIRE(e->WS && e->AGV > 0, "lrs_logits_audio: bind() first / no audio head configured");
+  return lin_fwd(*e, e->ws<bf16>(e->enc_b), e->M, e->aud, e->ws<float>(e->logits_a), e->AGV, 1, nullptr, 1.f, 0,
+                 static_cast<cudaStream_t>(stream));
 }
 int svsr_lrs_tensor(void* h, const char* name, void** ptr, int64_t* numel, int* dtype) {
   LrsEngine* e = static_cast<LrsEngine*>(h);

@@ -133,6 +133,41 @@ __global__ void finalize_metrics_kernel(const double* acc, float* out, float lam
   out[4] = (float)(acc[3] / (double)B);
 }
 
+// Second half of the fused audio head's forward (igemm.cuh, IgemmCe mode 1): one thread per (frame, c) softmax merges the
+// (max, sum exp) partials its V/64 column slots left behind into the log-sum-exp, adds lse - logit[target] to the loss.
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ xt, const long long* __restrict__ tokens,
+                   long long tok_stride_b, int T, int A, int G, int V, long long nrows, float* __restrict__ lse,
+                   double* acc) {
+  const int AG = A * G, spc = V >> 6, nslots = AG * spc;
+  float local = 0.f;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nrows; r += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(r % AG);
+    const long long bt = r / AG;
+    const float2* pp = part + bt * nslots + (long long)c * spc;
+    float m = -INFINITY;
+    for (int i = 0; i < spc; ++i) m = fmaxf(m, pp[i].x);
+    float se = 0.f;
+    for (int i = 0; i < spc; ++i) se += pp[i].y * exp2f((pp[i].x - m) * 1.4426950408889634f);
+    const float l = m + logf(se);
+    lse[r] = l;
+    const int t = (int)(bt % T);
+    const long long b = bt / T;
+    const int a = c / G, g = c - a * G;
+    const long long tgt = tokens[b * tok_stride_b + (long long)(t * A + a) * G + g];
+    if (tgt >= 0 && tgt < V) local += l - xt[r];
+  }
+  local = warp_sum(local);
+  __shared__ float sp[8];
+  if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += sp[i];
+    atomicAdd(acc, s);
+  }
+}
+
 __global__ void scale_bf16_kernel(__nv_bfloat16* x, long long n, const float* __restrict__ scale) {
   const float sc = *scale;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -157,6 +192,16 @@ int audio_ce(const float* logits, int ld, const long long* tokens, long long tok
   if (blocks > 148 * 8) blocks = 148 * 8;
   audio_ce_kernel<<<(unsigned)blocks, 256, 0, s>>>(logits, ld, tokens, tok_stride_b, T, A, G, V, nrows, dlogits, acc,
                                                    bad_token, dscale);
+  note_launch();
+  SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+int ce_finalize(const float2* part, const float* xt, const long long* tokens, long long tok_stride_b, int B, int T, int A,
+                int G, int V, float* lse, double* acc, cudaStream_t s) {
+  const long long nrows = (long long)B * T * A * G;
+  long long blocks = (nrows + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ce_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(part, xt, tokens, tok_stride_b, T, A, G, V, nrows, lse, acc);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;

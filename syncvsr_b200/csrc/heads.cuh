@@ -12,6 +12,11 @@ namespace svsr {
 int audio_ce(const float* logits, int ld, const long long* tokens, long long tok_stride_b, int B, int T, int A, int G,
              int V, __nv_bfloat16* dlogits, double* acc, int* bad_token, float dscale, cudaStream_t s);
 
+// Fused audio head, forward part 2 (part 1 = the projection GEMM with IgemmCe mode 1, igemm.cuh): merges the per-slot
+// (max, sum exp) partials [B*T, A*G*V/64] into lse [B*T*A*G] and adds sum(lse - logit[target]) to acc[0].
+int ce_finalize(const float2* part, const float* xt, const long long* tokens, long long tok_stride_b, int B, int T, int A,
+                int G, int V, float* lse, double* acc, cudaStream_t s);
+
 // logits fp32 [B, C] (pitch ld). Hard labels (int64 [B]) or soft labels (fp32 [B,C]); label smoothing eps.
 // acc[1] += sum loss ; acc[2] += #top1 ; acc[3] += #top5. dlogits (bf16, pitch ldd, columns >= C zeroed up to ldd).
 int category_ce(const float* logits, int ld, const long long* labels, const float* soft_labels, int B, int C, float eps,

@@ -1,7 +1,10 @@
-// tcgen05 implicit-GEMM kernel (see igemm.cuh). Warp roles (192 threads):
+// tcgen05 implicit-GEMM kernel (see igemm.cuh). Warp roles (320 threads):
 //   warp 0    : TMA producer  (one elected lane)
 //   warp 1    : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2-5 : epilogue, one TMEM lane-quarter each (warp_id % 4 selects the quarter tcgen05.ld may touch)
+//   warps 2-5 : epilogue group 0, warps 6-9 : epilogue group 1. Each warp reads the TMEM lane quarter warp_id % 4
+//               (32 accumulator rows); the two groups take the two COLUMN HALVES of the same tile, so a launch that
+//               owns one tile per CTA (the encoder's small GEMMs, the K = 2048 / 4096 input gradients) drains it in
+//               half the time, and a multi-tile CTA drains tile j in half the MMA time of tile j+1.
 #include "igemm.cuh"
 #include "tmap.h"
 
@@ -34,6 +37,7 @@ struct IgemmKParams {
   float drop_p;
   unsigned long long drop_seed;
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
+  IgemmCe ce;     // fused cross-entropy epilogue (mode 0 = off)
 };
 
 // A pipeline stage holds KPS consecutive 64-wide k-blocks (A sub-tile + B sub-tile each): one mbarrier round trip
@@ -45,9 +49,12 @@ struct IgemmSmem {
   static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = KPS * SUB_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_OFFSET = BAR_OFFSET;  // 2 x [128 rows x 128 B] epilogue staging tiles (1024-aligned)
-  static constexpr int BAR_OFFSET2 = STAGING_OFFSET + 2 * 16384;
-  static constexpr int STATS_OFFSET = BAR_OFFSET2 + 256;  // fp32 [4 warps][2][512] per-CTA BatchNorm partial sums
+  // epilogue staging tiles [128 rows x 128 B] (1024-aligned): a double buffer per epilogue group (BN = 64: the two
+  // groups fill the two halves of ONE 64-column tile, so one double buffer)
+  static constexpr int N_STAGING = BN >= 128 ? 4 : 2;
+  static constexpr int STAGING_OFFSET = BAR_OFFSET;
+  static constexpr int BAR_OFFSET2 = STAGING_OFFSET + N_STAGING * 16384;
+  static constexpr int STATS_OFFSET = BAR_OFFSET2 + 256;  // fp32 [4 lane quarters][2][512] per-CTA BatchNorm partial sums
   static constexpr int VALID_OFFSET = STATS_OFFSET + 4 * 4096;  // 128 row-validity bytes of the current tile
   static constexpr int TOTAL = VALID_OFFSET + 128 + 1024;  // + alignment slack
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
@@ -69,10 +76,16 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
   }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int IGEMM_THREADS = 320;
+
 template <int BN, int STAGES, int KPS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmC, const IgemmKParams p) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmKParams p) {
   // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
   // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
   using L = IgemmSmem<BN, STAGES, KPS>;
@@ -84,7 +97,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [4][2][512], one slice per epilogue warp
+  float* s_stats = reinterpret_cast<float*>(smem + L::STATS_OFFSET);  // [4][2][512], one slice per TMEM lane quarter
   uint8_t* s_valid = smem + L::VALID_OFFSET;
 
   const int warp = threadIdx.x >> 5;
@@ -104,7 +117,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -187,8 +200,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // accumulator row == pixel slot in the box
+    constexpr bool SHARED_TILE = (BN == 64);          // both groups fill one 64-column staging tile
+    constexpr int CPG = SHARED_TILE ? 1 : BN / 64;    // 32-column chunks per epilogue group and tile
+    constexpr int NPAIR = SHARED_TILE ? 1 : BN / 128;  // 64-column staging tiles per group and tile
+    const int grp = (warp - 2) >> 2;                  // epilogue group = column half
+    const int ewg = (warp - 2) & 3;                   // warp index inside the group (row block of the staged tile)
+    const int q = warp & 3;                           // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                      // accumulator row == pixel slot in the box
+    const int bar_id = SHARED_TILE ? 1 : 1 + grp;
+    const int bar_n = SHARED_TILE ? 256 : 128;
+    const bool leader = SHARED_TILE ? (threadIdx.x == 64) : (threadIdx.x == 64 + 128 * grp);  // issues the TMA stores
     const int hw = p.bh * p.bw;
     const int dn = r / hw;
     const int rem = r - dn * hw;
@@ -196,10 +217,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int dw = rem - dh * p.bw;
     int j = 0;
     int gcount = 0;
-    float st_sum[BN / 64][2], st_sq[BN / 64][2];  // per-thread BatchNorm partial sums (smem-staged path)
+    float st_sum[NPAIR][2], st_sq[NPAIR][2];  // per-thread BatchNorm partial sums (smem-staged path)
 #pragma unroll
-    for (int g2 = 0; g2 < BN / 64; ++g2) st_sum[g2][0] = st_sum[g2][1] = st_sq[g2][0] = st_sq[g2][1] = 0.f;
+    for (int g2 = 0; g2 < NPAIR; ++g2) st_sum[g2][0] = st_sum[g2][1] = st_sq[g2][0] = st_sq[g2][1] = 0.f;
     int stat_nt = -1;
+    const bool do_staged_stats = p.bn_stats && p.tma_store && (!SHARED_TILE || grp == 0);
+    float ce_scale = 1.f;
+    if (p.ce.mode == 2) ce_scale = p.ce.dscale * (p.ce.grad_scale ? __ldg(p.ce.grad_scale) : 1.f);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
       const int tw = mt % p.tiles_w;
@@ -214,11 +238,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int acc = j & 1;
       const bool tile_all_valid = (n0 + p.bn <= p.o_N) && (oh0 + p.bh <= p.OH) && (ow0 + p.bw <= p.OW);
       if (p.bn_stats && p.tma_store && !tile_all_valid) s_valid[r] = row_valid ? 1 : 0;  // read after the group barriers
+      // fused cross-entropy: this row is frame (b, t) of the clip batch
+      int ce_b = 0, ce_t = 0;
+      float ce_m = -INFINITY, ce_s = 0.f;
+      if (p.ce.mode) ce_b = n / p.ce.T, ce_t = n - ce_b * p.ce.T;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
 
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int cc = 0; cc < CPG; ++cc) {
+        const int ch = grp * CPG + cc;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
         tmem_ld_wait();
@@ -226,13 +255,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.bn_stats && !p.tma_store) {  // register path (fp32 outputs): transposed warp reduction of the chunk
           float a[32], b[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            a[j] = row_valid ? __uint_as_float(v[j]) : 0.f;
-            b[j] = a[j] * a[j];
+          for (int jj = 0; jj < 32; ++jj) {
+            a[jj] = row_valid ? __uint_as_float(v[jj]) : 0.f;
+            b[jj] = a[jj] * a[jj];
           }
           warp_transpose_reduce32(a, lane);
           warp_transpose_reduce32(b, lane);
-          if (col0 + lane < p.n_cols) {  // private slice per warp, fixed order: run-to-run deterministic
+          if (col0 + lane < p.n_cols) {  // slice per lane quarter; the two groups own disjoint columns
             s_stats[q * 1024 + col0 + lane] += a[0];
             s_stats[q * 1024 + 512 + col0 + lane] += b[0];
           }
@@ -240,116 +269,166 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (!p.tma_store && (!row_valid || col0 >= p.n_cols)) continue;
         float f[32];
   #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]) * p.alpha;
         if (p.bias) {
   #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n_cols) f[j] = fmaf(__ldg(p.bias + col0 + j), p.bias_scale, f[j]);
+          for (int jj = 0; jj < 32; ++jj)
+            if (col0 + jj < p.n_cols) f[jj] = fmaf(__ldg(p.bias + col0 + jj), p.bias_scale, f[jj]);
         }
         const bool full_chunk = (col0 + 32 <= p.n_cols);
+        if (p.ce.mode) {
+          // ---- fused projection + reshape + log-softmax + NLL (lightning.py:168-171, e2e_asr_transformer.py:198-201) ----
+          // columns [c*V, (c+1)*V) of this row are the V logits of target tokens[b, t*A + a, g], c = a*G + g (int64,
+          // bit-exact index arithmetic); V % 64 == 0, so a 64-column slot never straddles two softmaxes.
+          const int c = col0 / p.ce.V;
+          const int a = c / p.ce.G, g = c - a * p.ce.G;
+          long long tgt = -1;
+          if (row_valid && col0 < p.n_cols)
+            tgt = p.ce.tokens[(long long)ce_b * p.ce.tok_stride_b + (long long)(ce_t * p.ce.A + a) * p.ce.G + g];
+          const bool bad = tgt < 0 || tgt >= p.ce.V;
+          const int tj = bad ? -1 : (int)tgt - (col0 - c * p.ce.V);  // position of the target inside this chunk (if any)
+          if (p.ce.mode == 1) {
+            if (row_valid && col0 < p.n_cols) {
+              if (bad) *p.ce.bad_token = 1;
+              float m = f[0];
+#pragma unroll
+              for (int jj = 1; jj < 32; ++jj) m = fmaxf(m, f[jj]);
+              float se = 0.f, xt = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                se += exp2f((f[jj] - m) * 1.4426950408889634f);
+                if (jj == tj) xt = f[jj];
+              }
+              const long long rc = (long long)n * p.ce.AG + c;
+              if (tj >= 0 && tj < 32) p.ce.xt[rc] = xt;  // exactly one chunk of the row holds the target logit
+              // merge the two 32-column chunks of a 64-column slot in registers, one (max, sum) partial per slot
+              if ((ch & 1) == 0) {
+                ce_m = m, ce_s = se;
+              } else {
+                const float mm = fmaxf(ce_m, m);
+                const float ss = ce_s * exp2f((ce_m - mm) * 1.4426950408889634f) + se * exp2f((m - mm) * 1.4426950408889634f);
+                p.ce.part[(long long)n * (p.n_cols >> 6) + (col0 >> 6)] = make_float2(mm, ss);
+              }
+            }
+            continue;  // forward: nothing is stored but the partials -- the logits never leave the SM
+          }
+          // backward: d logits = (softmax - onehot) * dscale from the recomputed tile and the saved log-sum-exp
+          float lse = 0.f;
+          if (row_valid && col0 < p.n_cols) lse = p.ce.lse[(long long)n * p.ce.AG + c];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float pr = exp2f((f[jj] - lse) * 1.4426950408889634f);
+            f[jj] = bad ? 0.f : (pr - (jj == tj ? 1.f : 0.f)) * ce_scale;
+          }
+        }
         if (p.drop_p > 0.f && row_valid) {
           const float ks = 1.0f / (1.0f - p.drop_p);
           const unsigned long long e0 = (unsigned long long)(row_off + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = dropout_keep(p.drop_seed, e0 + j, p.drop_p) ? f[j] * ks : 0.f;
+          for (int jj = 0; jj < 32; ++jj) f[jj] = dropout_keep(p.drop_seed, e0 + jj, p.drop_p) ? f[jj] * ks : 0.f;
         }
         if (p.resid && row_valid) {
           if (p.resid_fp32) {
             const float* rp = reinterpret_cast<const float*>(p.resid) + row_off + col0;
             if (full_chunk) {
   #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 t = reinterpret_cast<const float4*>(rp)[j];
-                f[4 * j] += t.x, f[4 * j + 1] += t.y, f[4 * j + 2] += t.z, f[4 * j + 3] += t.w;
+              for (int jj = 0; jj < 8; ++jj) {
+                float4 t = reinterpret_cast<const float4*>(rp)[jj];
+                f[4 * jj] += t.x, f[4 * jj + 1] += t.y, f[4 * jj + 2] += t.z, f[4 * jj + 3] += t.w;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.n_cols) f[j] += rp[j];
+              for (int jj = 0; jj < 32; ++jj)
+                if (col0 + jj < p.n_cols) f[jj] += rp[jj];
             }
           } else {
             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + row_off + col0;
             if (full_chunk) {
   #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 t = reinterpret_cast<const uint4*>(rp)[j];
+              for (int jj = 0; jj < 4; ++jj) {
+                uint4 t = reinterpret_cast<const uint4*>(rp)[jj];
                 float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-                f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += b.x, f[8 * j + 3] += b.y;
-                f[8 * j + 4] += c.x, f[8 * j + 5] += c.y, f[8 * j + 6] += d.x, f[8 * j + 7] += d.y;
+                f[8 * jj] += a.x, f[8 * jj + 1] += a.y, f[8 * jj + 2] += b.x, f[8 * jj + 3] += b.y;
+                f[8 * jj + 4] += c.x, f[8 * jj + 5] += c.y, f[8 * jj + 6] += d.x, f[8 * jj + 7] += d.y;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.n_cols) f[j] += __bfloat162float(rp[j]);
+              for (int jj = 0; jj < 32; ++jj)
+                if (col0 + jj < p.n_cols) f[jj] += __bfloat162float(rp[jj]);
             }
           }
         }
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.f);
         }
         if (p.relu_mask && row_valid) {
           const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.relu_mask) + row_off + col0;
           if (full_chunk) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 t = reinterpret_cast<const uint4*>(mp)[j];
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint4 t = reinterpret_cast<const uint4*>(mp)[jj];
               const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-              f[8 * j] = a.x > 0.f ? f[8 * j] : 0.f, f[8 * j + 1] = a.y > 0.f ? f[8 * j + 1] : 0.f;
-              f[8 * j + 2] = b.x > 0.f ? f[8 * j + 2] : 0.f, f[8 * j + 3] = b.y > 0.f ? f[8 * j + 3] : 0.f;
-              f[8 * j + 4] = c.x > 0.f ? f[8 * j + 4] : 0.f, f[8 * j + 5] = c.y > 0.f ? f[8 * j + 5] : 0.f;
-              f[8 * j + 6] = d.x > 0.f ? f[8 * j + 6] : 0.f, f[8 * j + 7] = d.y > 0.f ? f[8 * j + 7] : 0.f;
+              f[8 * jj] = a.x > 0.f ? f[8 * jj] : 0.f, f[8 * jj + 1] = a.y > 0.f ? f[8 * jj + 1] : 0.f;
+              f[8 * jj + 2] = b.x > 0.f ? f[8 * jj + 2] : 0.f, f[8 * jj + 3] = b.y > 0.f ? f[8 * jj + 3] : 0.f;
+              f[8 * jj + 4] = c.x > 0.f ? f[8 * jj + 4] : 0.f, f[8 * jj + 5] = c.y > 0.f ? f[8 * jj + 5] : 0.f;
+              f[8 * jj + 6] = d.x > 0.f ? f[8 * jj + 6] : 0.f, f[8 * jj + 7] = d.y > 0.f ? f[8 * jj + 7] : 0.f;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n_cols) f[j] = __bfloat162float(mp[j]) > 0.f ? f[j] : 0.f;
+            for (int jj = 0; jj < 32; ++jj)
+              if (col0 + jj < p.n_cols) f[jj] = __bfloat162float(mp[jj]) > 0.f ? f[jj] : 0.f;
           }
         }
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + row_off + col0;
           if (full_chunk) {
   #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int jj = 0; jj < 8; ++jj)
+              reinterpret_cast<float4*>(op)[jj] = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n_cols) op[j] = f[j];
+            for (int jj = 0; jj < 32; ++jj)
+              if (col0 + jj < p.n_cols) op[jj] = f[jj];
           }
         } else if (p.tma_store) {
-          // stage 64 output channels (two 32-column chunks) per pixel row in a SWIZZLE_128B tile, then one TMA store
-          const int grp = gcount + (ch >> 1);  // running 64-column group index of this CTA (selects the buffer)
-          uint8_t* stg = s_stage + (grp & 1) * 16384;
-          if ((ch & 1) == 0) {
-            if (threadIdx.x == 64) tma_store_wait_read<1>();  // the store that last used this buffer has read it
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+          // stage 64 output channels (two 32-column chunks) per pixel row in a SWIZZLE_128B tile, then one TMA store.
+          // BN >= 128: the group owns whole 64-column tiles (its own double buffer and 128-thread barrier);
+          // BN == 64: group g writes half g of the CTA's single tile (256-thread barrier, thread 64 stores).
+          const int half = SHARED_TILE ? grp : (cc & 1);
+          const bool first_half = SHARED_TILE || (cc & 1) == 0;
+          const bool last_half = SHARED_TILE || (cc & 1) == 1;
+          const int pair = SHARED_TILE ? 0 : (cc >> 1);
+          const int bufi = SHARED_TILE ? (gcount & 1) : (grp * 2 + ((gcount + pair) & 1));
+          uint8_t* stg = s_stage + bufi * 16384;
+          if (first_half) {
+            if (leader) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+            named_bar_sync(bar_id, bar_n);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int jj = 0; jj < 4; ++jj) {
             uint4 t;
-            t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-            t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            const int chunk = ((ch & 1) * 4 + j) ^ (r & 7);  // 16-byte chunk position after the 128B swizzle
+            t.x = pack_bf16x2(f[8 * jj], f[8 * jj + 1]);
+            t.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+            t.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+            t.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+            const int chunk = (half * 4 + jj) ^ (r & 7);  // 16-byte chunk position after the 128B swizzle
             *reinterpret_cast<uint4*>(stg + r * 128 + chunk * 16) = t;
           }
-          if ((ch & 1) == 1) {
+          if (last_half) {
             fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-              tma_store_4d(&tmC, stg, p.c_off + nt * BN + (ch >> 1) * 64, ow0 * p.o_sw + p.o_ow, oh0 * p.o_sh + p.o_oh,
-                           n0);
+            named_bar_sync(bar_id, bar_n);
+            const int cgrp = SHARED_TILE ? 0 : (grp * NPAIR + pair);  // 64-column group of the tile
+            if (leader) {
+              tma_store_4d(&tmC, stg, p.c_off + nt * BN + cgrp * 64, ow0 * p.o_sw + p.o_ow, oh0 * p.o_sh + p.o_oh, n0);
               tma_store_commit();
             }
-            if (p.bn_stats) {
+            if (do_staged_stats) {
               // fused BatchNorm statistics from the staged (bf16-rounded = exactly what BN will normalise) tile: lane l of
-              // epilogue warp w owns the column pair (2l, 2l+1) over rows [32w, 32w+32): 32 conflict-free LDS.32 per
+              // group warp w owns the column pair (2l, 2l+1) over rows [32w, 32w+32): 32 conflict-free LDS.32 per
               // 64-column group; partial sums stay in registers across all tiles of this CTA.
-              const int ew = (threadIdx.x - 64) >> 5;
               const int rows_in_box = p.bn * hw;
-              const int rbeg = ew * 32, rend = min(rbeg + 32, rows_in_box);
+              const int rbeg = ewg * 32, rend = min(rbeg + 32, rows_in_box);
               float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
               const uint8_t* colbase = stg + (lane & 3) * 4;
               const int cpos = lane >> 2;
@@ -368,12 +447,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   s2a = fmaf(v2.x, v2.x, s2a), s2b = fmaf(v2.y, v2.y, s2b);
                 }
               }
-              const int gi = (ch >> 1);
               if (nt != stat_nt) {  // switched to another column tile: spill the register partials first
                 if (stat_nt >= 0) {
 #pragma unroll
-                  for (int g2 = 0; g2 < BN / 64; ++g2) {
-                    float* sl = s_stats + ew * 1024 + stat_nt * BN + g2 * 64 + 2 * lane;
+                  for (int g2 = 0; g2 < NPAIR; ++g2) {
+                    float* sl = s_stats + ewg * 1024 + stat_nt * BN + (SHARED_TILE ? 0 : (grp * NPAIR + g2) * 64) + 2 * lane;
                     sl[0] += st_sum[g2][0], sl[1] += st_sum[g2][1];
                     sl[512] += st_sq[g2][0], sl[513] += st_sq[g2][1];
                     st_sum[g2][0] = st_sum[g2][1] = st_sq[g2][0] = st_sq[g2][1] = 0.f;
@@ -382,49 +460,48 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 stat_nt = nt;
               }
 #pragma unroll
-              for (int g2 = 0; g2 < BN / 64; ++g2)
-                if (g2 == gi) st_sum[g2][0] += s1a, st_sum[g2][1] += s1b, st_sq[g2][0] += s2a, st_sq[g2][1] += s2b;
+              for (int g2 = 0; g2 < NPAIR; ++g2)
+                if (g2 == pair) st_sum[g2][0] += s1a, st_sum[g2][1] += s1b, st_sq[g2][0] += s2a, st_sq[g2][1] += s2b;
             }
           }
         } else {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
           if (full_chunk) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int jj = 0; jj < 4; ++jj) {
               uint4 t;
-              t.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-              t.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              t.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              t.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              reinterpret_cast<uint4*>(op)[j] = t;
+              t.x = pack_bf16x2(f[8 * jj], f[8 * jj + 1]);
+              t.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+              t.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+              t.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+              reinterpret_cast<uint4*>(op)[jj] = t;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n_cols) op[j] = __float2bfloat16(f[j]);
+            for (int jj = 0; jj < 32; ++jj)
+              if (col0 + jj < p.n_cols) op[jj] = __float2bfloat16(f[jj]);
           }
         }
       }
-      gcount += BN / 64;
+      gcount += NPAIR;
       // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();  // smem must outlive the last bulk store
-    if (p.bn_stats && p.tma_store && stat_nt >= 0) {
-      const int ew = (threadIdx.x - 64) >> 5;
+    if (p.tma_store && leader) tma_store_wait_all();  // smem must outlive the last bulk store
+    if (do_staged_stats && stat_nt >= 0) {
 #pragma unroll
-      for (int g2 = 0; g2 < BN / 64; ++g2) {
-        float* sl = s_stats + ew * 1024 + stat_nt * BN + g2 * 64 + 2 * lane;
+      for (int g2 = 0; g2 < NPAIR; ++g2) {
+        float* sl = s_stats + ewg * 1024 + stat_nt * BN + (SHARED_TILE ? 0 : (grp * NPAIR + g2) * 64) + 2 * lane;
         sl[0] += st_sum[g2][0], sl[1] += st_sum[g2][1];
         sl[512] += st_sq[g2][0], sl[513] += st_sq[g2][1];
       }
     }
     if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      named_bar_sync(3, 256);  // the eight epilogue warps only
       const int t = threadIdx.x - 64;
-      for (int cidx = t; cidx < p.n_cols; cidx += 128) {
+      for (int cidx = t; cidx < p.n_cols; cidx += 256) {
         const double su = (double)s_stats[cidx] + (double)s_stats[1024 + cidx] + (double)s_stats[2048 + cidx] +
                           (double)s_stats[3072 + cidx];
         const double sq2 = (double)s_stats[512 + cidx] + (double)s_stats[1536 + cidx] + (double)s_stats[2560 + cidx] +
@@ -471,14 +548,26 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
                                          L::TOTAL));
     attr_done = true;
   }
-  igemm_kernel<BN, STAGES, KPS><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
+  igemm_kernel<BN, STAGES, KPS><<<grid, IGEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
 }
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
-  SVSR_REQUIRE(p.a && p.b && p.out, "igemm: null operand");
+  SVSR_REQUIRE(p.a && p.b && (p.out || p.ce.mode == 1), "igemm: null operand");
+  if (p.ce.mode) {
+    SVSR_REQUIRE(p.ce.mode == 1 || p.ce.mode == 2, "igemm: ce.mode %d unknown", p.ce.mode);
+    SVSR_REQUIRE(p.ntaps == 1 && p.OH == 1 && p.OW == 1 && p.o_H == 1 && p.o_W == 1 && p.stride == 1,
+                 "igemm: the fused cross-entropy epilogue needs a dense GEMM");
+    SVSR_REQUIRE(p.ce.V > 0 && p.ce.V % 64 == 0 && p.ce.AG == p.ce.A * p.ce.G && p.b_rows == p.ce.AG * p.ce.V &&
+                     p.b_rows >= 128 &&
+                     p.ce.T > 0 && p.o_N % p.ce.T == 0,
+                 "igemm: fused cross-entropy geometry (V=%d must be a multiple of 64, N=%d = A*G*V, rows %d = B*T)", p.ce.V,
+                 p.b_rows, p.o_N);
+    SVSR_REQUIRE(p.ce.tokens && p.ce.bad_token && (p.ce.mode == 1 ? (p.ce.part && p.ce.xt) : (p.ce.lse && !p.out_fp32)),
+                 "igemm: fused cross-entropy buffers missing");
+  }
   SVSR_REQUIRE(p.cin > 0 && p.cin % 64 == 0, "igemm: cin=%d must be a positive multiple of 64", p.cin);
   SVSR_REQUIRE(p.a_C % 8 == 0 && p.a_coff % 8 == 0, "igemm: A channel pitch/offset must be multiples of 8");
   SVSR_REQUIRE(p.b_cols % 8 == 0, "igemm: B pitch %d must be a multiple of 8", p.b_cols);
@@ -530,7 +619,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   const long long m_tiles = (long long)tiles_n * kp.tiles_h * kp.tiles_w;
   int BN = p.b_rows <= 64 ? 64 : (p.b_rows <= 128 ? 128 : 256);
   if (BN == 256 && m_tiles * ((p.b_rows + 255) / 256) < 100) BN = 128;
-  if (BN == 128 && m_tiles * ((p.b_rows + 127) / 128) < 100) BN = 64;
+  if (BN == 128 && m_tiles * ((p.b_rows + 127) / 128) < 100 && !p.ce.mode) BN = 64;
   {
     uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
     uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
@@ -545,7 +634,8 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   // bf16 outputs whose channel count is a multiple of 64 leave through TMA tensor stores (the map mirrors the output
   // geometry: pitch ldc, pixel strides o_s*, so hardware clips pixels outside the tensor)
   CUtensorMap tmC = tmA;
-  kp.tma_store = (!p.out_fp32 && p.b_rows % 64 == 0) ? 1 : 0;
+  kp.tma_store = (!p.out_fp32 && p.b_rows % 64 == 0 && p.ce.mode != 1) ? 1 : 0;
+  kp.ce = p.ce;
   if (kp.tma_store) {
     uint64_t dims[4] = {(uint64_t)p.ldc, (uint64_t)p.o_W, (uint64_t)p.o_H, (uint64_t)p.o_N};
     uint64_t strides[3] = {(uint64_t)p.ldc * 2, (uint64_t)p.o_W * p.ldc * 2, (uint64_t)p.o_H * p.o_W * p.ldc * 2};

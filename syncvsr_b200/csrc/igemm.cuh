@@ -11,6 +11,28 @@ namespace svsr {
 
 constexpr int IGEMM_MAX_TAPS = 16;
 
+// Fused cross-entropy epilogue of a dense GEMM whose output columns are A*G softmaxes of V classes per row (the audio
+// head `audio_projection` -> reshape [B,T,A*G,V] -> F.cross_entropy, LRW/video/src/lightning.py:168-171; LRS twin
+// e2e_asr_transformer.py:198-201). Row r of the GEMM is frame (b, t) = (r / T, r % T); columns [c*V, (c+1)*V) are the
+// logits of target tokens[b*tok_stride_b + (t*A + a)*G + g], c = a*G + g. V % 64 == 0. The fp32 logits never leave the SM:
+//   mode 1 (forward): every 64-column slot of a row leaves a (max, sum exp) partial in `part` [rows, cols/64] and the
+//     chunk that holds the target column writes its logit to `xt` [rows, A*G]; ce_finalize() merges the partials into
+//     `lse` [rows, A*G] and the loss sum. Nothing else is stored (IgemmProblem::out may be null).
+//   mode 2 (backward): the tile is recomputed and the epilogue emits d logits = (exp(x - lse) - onehot) * dscale
+//     (* *grad_scale when given) as the GEMM's bf16 output -- the operand of the input- and weight-gradient GEMMs.
+struct IgemmCe {
+  int mode = 0;
+  int T = 1, A = 1, G = 1, V = 64, AG = 1;
+  const long long* tokens = nullptr;
+  long long tok_stride_b = 0;
+  float2* part = nullptr;
+  float* xt = nullptr;
+  const float* lse = nullptr;
+  int* bad_token = nullptr;          // set to 1 when a token is outside [0, V)
+  float dscale = 1.f;
+  const float* grad_scale = nullptr;  // optional device scalar (upstream d loss)
+};
+
 // Host-side problem description. All channel counts are in elements (bf16).
 struct IgemmProblem {
   // ---- A operand (activations), NHWC ----
@@ -55,6 +77,7 @@ struct IgemmProblem {
   // squares of the fp32 accumulators over all valid pixels (train-mode BN of the conv output, lightning.py:51)
   double* bn_stats = nullptr;
   double algo_flops = 0;  // algorithmic FLOPs of this launch for the profiler (0 = 2*pixels*N*taps*cin)
+  IgemmCe ce;             // fused cross-entropy epilogue (dense GEMMs only)
 };
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);

@@ -400,6 +400,7 @@ class E2E(nn.Module):
 
     def logits_audio(self) -> torch.Tensor:
         B, T, _, _ = self._shape_key
+        check(lib().svsr_lrs_logits_audio(self._h, self._stream()), "svsr_lrs_logits_audio")  # not written by the step
         return self._named_tensor("logits_audio", (B, T, -1)).clone()
 
     def ctc_logits(self) -> torch.Tensor:

@@ -403,6 +403,7 @@ class TransformerLightningModule(nn.Module):
             C.c_int(int(self.training)), C.c_uint32(skip),
             C.c_uint64(self._step_seed()),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
+        self._precise_logits = False
         if self.training:
             self._nbt += 1
         if torch.is_grad_enabled():
@@ -445,6 +446,7 @@ class TransformerLightningModule(nn.Module):
             C.c_void_p(hard.data_ptr() if hard is not None else 0), C.c_void_p(soft.data_ptr() if soft is not None else 0),
             C.c_int(int(self.training)), C.c_uint32(0), C.c_void_p(metrics.data_ptr()), self._stream()),
             "svsr_lrw_forward_precise")
+        self._precise_logits = True
         return {"loss_total": metrics[0], "loss_category": metrics[1], "loss_audio": metrics[2],
                 "accuracy_top1": metrics[3], "accuracy_top5": metrics[4]}
 
@@ -466,7 +468,11 @@ class TransformerLightningModule(nn.Module):
         return self._named_tensor("last_hidden_state", (B, T + 1, self._dim_pitch))[:, :, : self.dim].clone()
 
     def logits_audio(self) -> torch.Tensor:
+        """lightning.py:168-169 `logits_audio`: NOT produced by the step (fused head) -- materialised here on request
+        (after forward_precise the buffer already holds the parity-mode logits)."""
         B, T, _, _ = self._shape_key
+        if not getattr(self, "_precise_logits", False):
+            check(lib().svsr_lrw_logits_audio(self._h, self._stream()), "svsr_lrw_logits_audio")
         return self._named_tensor("logits_audio", (B, T, self.audio_alignment * self.vq_groups,
                                                    self.audio_vocab_size)).clone()
 

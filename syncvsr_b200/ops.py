@@ -282,6 +282,47 @@ def audio_ce(logits, tokens, T, A, G, V, dscale=1.0, want_grad=True):
     return acc[0] / (B * T * A * G), dl, bad
 
 
+class AudioHead:
+    """The fused audio head as an operator: audio_projection + reshape + log-softmax + NLL (lightning.py:82,168-171)
+    without fp32 logits in HBM. forward() -> mean loss; backward() -> (dx bf16 [B*T, K], dw fp32 [A*G*V, K], db fp32)."""
+
+    def __init__(self, B: int, T: int, A: int, G: int, V: int, K: int, device="cuda"):
+        self.B, self.T, self.A, self.G, self.V, self.K = B, T, A, G, V, K
+        rows, N = B * T, A * G * V
+        self.part = torch.empty(rows * (N // 64), 2, device=device, dtype=torch.float32)
+        self.xt = torch.zeros(rows * A * G, device=device, dtype=torch.float32)
+        self.lse = torch.empty(rows * A * G, device=device, dtype=torch.float32)
+        self.acc = torch.zeros(1, device=device, dtype=torch.float64)
+        self.bad = torch.zeros(1, device=device, dtype=torch.int32)
+        self.dlogits = None
+
+    def _args(self, x, w, bias, tokens):
+        _req(x, torch.bfloat16, "x"), _req(w, torch.bfloat16, "w"), _req(tokens, torch.int64, "tokens")
+        assert x.shape == (self.B * self.T, self.K) and w.shape == (self.A * self.G * self.V, self.K)
+        return (ptr(x), _i(self.K), ptr(w), _i(self.K), _i(self.K), ptr(bias), ptr(tokens), C.c_int64(tokens.stride(0)),
+                _i(self.B), _i(self.T), _i(self.A), _i(self.G), _i(self.V))
+
+    def forward(self, x, w, bias, tokens):
+        self.acc.zero_(), self.bad.zero_()
+        check(lib().svsr_audio_head_fwd(*self._args(x, w, bias, tokens), ptr(self.part), ptr(self.xt), ptr(self.lse),
+                                        ptr(self.acc), ptr(self.bad), stream_ptr()), "svsr_audio_head_fwd")
+        return self.acc[0] / (self.B * self.T * self.A * self.G)
+
+    def backward(self, x, w, wt, bias, tokens, dscale=None, dx=None, dw=None, want_db=True):
+        """wt = w.t().contiguous() (the input-gradient GEMM's operand). dscale defaults to 1/rows (mean reduction)."""
+        rows = self.B * self.T * self.A * self.G
+        N = self.A * self.G * self.V
+        if self.dlogits is None:
+            self.dlogits = torch.empty(self.B * self.T, N, device=x.device, dtype=torch.bfloat16)
+        check(lib().svsr_audio_head_bwd(*self._args(x, w, bias, tokens), ptr(self.lse),
+                                        C.c_float(1.0 / rows if dscale is None else dscale), ptr(None), ptr(self.dlogits),
+                                        ptr(self.bad), stream_ptr()), "svsr_audio_head_bwd")
+        dx = gemm(self.dlogits, wt, out=dx)
+        dw = gemm_wgrad(self.dlogits, x, out=dw)
+        db = self.dlogits.float().sum(0) if want_db else None
+        return dx, dw, db
+
+
 def category_ce(logits, labels, num_classes, label_smoothing=0.0, dscale=1.0):
     """logits fp32 [B, ld>=C]; labels int64 [B] or fp32 [B,C]. Returns (loss_mean, top1, top5, dlogits bf16 [B, ld])."""
     B, ld = logits.shape
