@@ -79,6 +79,16 @@ int svsr_conv_taps_fprop_bnstats(const void* x, const void* w, void* y, double* 
  * Replaces autograd's conv backward-data for resnet.layer1-4 (lightning.py:114-117). */
 int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
+/* The same input-gradient GEMM with the BatchNorm-backward reduction of its CONSUMER fused into the epilogue (timm
+ * BasicBlock via lightning.py:114-117): dx = (W^T dy + resid) * mask, mask = [relu_mask > 0] (bf16 tensor of dx's geometry,
+ * the ReLU after `out = relu(bn2(c2) + shortcut)`) or -- self_mask -- [c0*scale0 + shift0 > 0] (the ReLU directly after
+ * bn1). For each consuming BatchNorm i (one or two: bn2 and downsample.1 share the gradient) with input c_i (bf16, dx's
+ * geometry) and coef_i (fp32 [4][Cin]: mean, invstd, scale, shift): stats_i[0..Cin) += sum dx, stats_i[Cin..2Cin) +=
+ * sum dx * xhat_i -- exactly what svsr_batchnorm_bwd's reduce pass would compute from (dx, c_i). Cin % 64 == 0. */
+int svsr_conv2d_dgrad_bnbwd(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                            int Cout, int R, int S, int stride, int pad, const void* relu_mask, int self_mask,
+                            const void* c0, const float* coef0, double* stats0, const void* c1, const float* coef1,
+                            double* stats1, void* stream);
 
 /* dw[R*S*Cin, Cout] (fp32, += accumulate) = weight gradient of conv2d: row (r*S+s)*Cin+ci, column co.
  * x[N,H,W,Cin], dy[N,OH,OW,Cout] bf16. Replaces autograd's conv backward-weight. */

@@ -111,8 +111,10 @@ int svsr_conv_taps_fprop_bnstats(const void* x, const void* w, void* y, double* 
   return igemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 
-int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
-                      int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream) {
+// Shared by svsr_conv2d_dgrad and its fused variant below.
+static int conv2d_dgrad_impl(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, int stride, int pad, int out_fp32, const void* relu_mask,
+                             const IgemmBnBwd* bnb, cudaStream_t stream) {
   SVSR_REQUIRE(R * S <= IGEMM_MAX_TAPS, "dgrad: %dx%d filter has too many taps", R, S);
   SVSR_REQUIRE(stride == 1 || stride == 2, "dgrad: stride must be 1 or 2");
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
@@ -131,6 +133,7 @@ int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resi
           p.tap_kbase[t] = (r * S + s) * Cout;
         }
       }
+      SVSR_REQUIRE(p.ntaps > 0 || !bnb || !bnb->n, "dgrad: a pixel class without taps cannot carry fused statistics");
       if (p.ntaps == 0) continue;
       p.o_N = N, p.OH = (H - a + stride - 1) / stride, p.OW = (W - b + stride - 1) / stride;
       if (p.OH <= 0 || p.OW <= 0) continue;
@@ -138,10 +141,34 @@ int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resi
       p.out = dx, p.out_fp32 = out_fp32, p.ldc = Cin, p.c_off = 0;
       p.o_H = H, p.o_W = W, p.o_sh = stride, p.o_sw = stride, p.o_oh = a, p.o_ow = b;
       p.resid = resid, p.resid_fp32 = out_fp32;
-      int rc = igemm_launch(p, static_cast<cudaStream_t>(stream));
+      p.relu_mask = relu_mask;
+      if (bnb) p.bnb = *bnb;
+      int rc = igemm_launch(p, stream);
       if (rc) return rc;
     }
   return SVSR_OK;
+}
+
+int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                      int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream) {
+  return conv2d_dgrad_impl(dy, wd, dx, resid, N, H, W, Cin, Cout, R, S, stride, pad, out_fp32, nullptr, nullptr,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int svsr_conv2d_dgrad_bnbwd(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                            int Cout, int R, int S, int stride, int pad, const void* relu_mask, int self_mask,
+                            const void* c0, const float* coef0, double* stats0, const void* c1, const float* coef1,
+                            double* stats1, void* stream) {
+  SVSR_REQUIRE(c0 && coef0 && stats0, "dgrad_bnbwd: the first BatchNorm's buffers are required");
+  SVSR_REQUIRE(!(self_mask && relu_mask), "dgrad_bnbwd: self_mask and relu_mask are exclusive");
+  IgemmBnBwd b;
+  b.n = c1 ? 2 : 1;
+  b.c[0] = c0, b.coef[0] = coef0, b.stats[0] = stats0;
+  b.c[1] = c1, b.coef[1] = coef1, b.stats[1] = stats1;
+  b.self_mask = self_mask;
+  SVSR_REQUIRE(!c1 || (coef1 && stats1), "dgrad_bnbwd: the second BatchNorm's buffers are incomplete");
+  return conv2d_dgrad_impl(dy, wd, dx, resid, N, H, W, Cin, Cout, R, S, stride, pad, 0, relu_mask, &b,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int svsr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,

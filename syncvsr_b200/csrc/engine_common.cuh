@@ -241,6 +241,23 @@ static int conv_dgrad(const EngineBase& e, const bf16* dy, int Hin, const ConvRe
   return svsr_conv2d_dgrad(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride, c.pad, 0,
                            s);
 }
+// Input gradient with the BatchNorm-backward reduction of its consumer(s) fused into the epilogue (igemm.cuh,
+// IgemmBnBwd): dx = (W^T dy + resid) * mask; mask from `relu_mask` (> 0) or, self_mask, from bn_a's own output sign.
+static int conv_dgrad_bnb(const EngineBase& e, const bf16* dy, int Hin, const ConvRef& c, bf16* dx, const bf16* resid,
+                          const bf16* relu_mask, int self_mask, const bf16* ca, const BnRef& bna, const bf16* cb,
+                          const BnRef* bnb, cudaStream_t s) {
+  return svsr_conv2d_dgrad_bnbwd(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride, c.pad,
+                                 relu_mask, self_mask, ca, e.ws<float>(bna.coef), e.ws<double>(bna.stats_b), cb,
+                                 bnb ? e.ws<float>(bnb->coef) : nullptr, bnb ? e.ws<double>(bnb->stats_b) : nullptr, s);
+}
+// BatchNorm backward whose reduction already happened in the producing GEMM's epilogue: finalize + apply on the
+// pre-masked gradient g (dc = scale * (g - k1 - xhat * k2))
+static int bn_bwd_prereduced(const EngineBase& e, const bf16* g, const bf16* c, long long rows, const BnRef& bn, bf16* dc,
+                             cudaStream_t s) {
+  RC(bn_bwd_finalize(e.ws<double>(bn.stats_b), rows, bn.C, e.G + bn.gamma, e.G + bn.beta, e.ws<float>(bn.kcoef), s));
+  return bn_bwd_apply(g, nullptr, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, nullptr, rows, bn.C, 0, s);
+}
+
 static int conv_wgrad(const EngineBase& e, const bf16* x, int Hin, const bf16* dy, const ConvRef& c, cudaStream_t s) {
   float* tmp = e.ws<float>(e.wgrad_tmp);
   const size_t n = (size_t)c.R * c.R * c.cin * c.cout;
@@ -468,47 +485,117 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
   bf16* T0 = e.ws<bf16>(f.gbuf[0]);  // dOut of the current block, later da1
   bf16* T2 = e.ws<bf16>(f.gbuf[1]);  // activation-masked upstream gradient (identity shortcut branch)
   bf16* T4 = e.ws<bf16>(f.gbuf[2]);  // dX of the current block
-  // ---- trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
-  for (int bi = 7; bi >= 0; --bi) {
-    BlockRef& blk = f.blocks[bi];
-    bf16* DC2 = e.ws<bf16>(f.gbuf[3 + (bi & 1)]);
-    bf16* DC1 = e.ws<bf16>(f.gbuf[5 + (bi & 1)]);
-    bf16* DCD = e.ws<bf16>(f.gbuf[7 + (bi & 1)]);
-    const bf16* xin = bi == 0 ? e.ws<bf16>(f.x1) : e.ws<bf16>(f.blocks[bi - 1].out);
-    const long long rows = (long long)e.N * blk.Hout * blk.Hout;
-    const bf16* out = e.ws<bf16>(blk.out);
-    if (!f.swish) {
-      RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : T2, s));
-      if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
-    } else {
-      // Swish(bn2(c2) + shortcut): the pre-activation is rebuilt from c2 and the shortcut operand (resnet.py:104-105)
-      if (blk.ds) {
-        RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, nullptr, s, 2, e.ws<bf16>(blk.cds),
-                  e.ws<float>(blk.bnds.coef)));
-        RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s, 2, e.ws<bf16>(blk.c2),
-                  e.ws<float>(blk.bn2.coef)));
+  // SVSR_BN_BWD_FUSED=1 (off by default) moves the BatchNorm-backward reductions into the epilogues of the input-gradient
+  // GEMMs that produce the gradient (igemm.cuh, IgemmBnBwd). Measured at the bench geometry (profiles/r2_bn_bwd_fused_ab.md):
+  // the 19 reduce launches (1.36 ms) disappear, but the transposed warp reductions double the epilogue-bound dgrad
+  // kernels (1.67 -> 3.1 ms) and the step does not move (11.07 vs 11.01 ms) -- and the trunk backward is bounded by the
+  // dgrad + wgrad tensor kernels time-sharing the SMs anyway (3.55 of its 3.98 ms), so the reduce passes run in the
+  // weight-gradient kernels' shadow. Kept as a tested option.
+  const char* fuse = getenv("SVSR_BN_BWD_FUSED");
+  const bool fused = !f.swish && fuse && fuse[0] == '1';
+  if (fused) {
+    // ---- ReLU trunk (LRW), reversed, BatchNorm-backward reductions fused into the producing input-gradient GEMMs ----
+    // G  = relu-masked gradient w.r.t. the block's output (produced masked by the NEXT block's conv1 dgrad, which also
+    //      left sum g / sum g*xhat of bn2 (and downsample.1) in their stats slots); the last block's comes from the
+    //      mean pool and goes through the standalone reduce.
+    // DA = conv2's input gradient, masked by bn1's own ReLU in the conv2-dgrad epilogue (+ bn1's sums).
+    bf16* G = T0;
+    bf16* DA = T2;
+    bf16* NX = T4;
+    for (int bi = 7; bi >= 0; --bi) {
+      BlockRef& blk = f.blocks[bi];
+      bf16* DC2 = e.ws<bf16>(f.gbuf[3 + (bi & 1)]);
+      bf16* DC1 = e.ws<bf16>(f.gbuf[5 + (bi & 1)]);
+      bf16* DCD = e.ws<bf16>(f.gbuf[7 + (bi & 1)]);
+      const bf16* xin = bi == 0 ? e.ws<bf16>(f.x1) : e.ws<bf16>(f.blocks[bi - 1].out);
+      const long long rows = (long long)e.N * blk.Hout * blk.Hout;
+      if (bi == 7) {  // G = d loss / d out, not yet masked: the classic three-kernel BatchNorm backward, which also masks
+        RC(bn_bwd(e, G, e.ws<bf16>(blk.out), e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : DA, s));
+        if (blk.ds) RC(bn_bwd(e, G, e.ws<bf16>(blk.out), e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
+        if (!blk.ds) {  // the masked gradient (identity-shortcut term) was written to DA: make it G
+          bf16* t = G;
+          G = DA, DA = t;
+        }
       } else {
-        RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, T2, s, 2, xin, nullptr));
+        RC(bn_bwd_prereduced(e, G, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, s));
+        if (blk.ds && blk.cout <= 256) RC(bn_bwd_prereduced(e, G, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, s));
+        // (two fused reductions over 512 channels do not fit the epilogue's shared-memory slices: layer4.0's
+        //  downsample BatchNorm -- a 17 MB tensor -- keeps the standalone reduce, on the already masked gradient)
+        if (blk.ds && blk.cout > 256) RC(bn_bwd(e, G, nullptr, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s, 0));
       }
+      RC(sq.fork());  // dc2 (and dcds) complete
+      RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
+      if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
+      // DA := relu'(bn1) * conv2^T dc2, with bn1's backward sums
+      RC(conv_dgrad_bnb(e, DC2, blk.Hout, blk.conv2, DA, nullptr, nullptr, 1, e.ws<bf16>(blk.c1), blk.bn1, nullptr,
+                        nullptr, s));
+      RC(bn_bwd_prereduced(e, DA, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, s));
+      RC(sq.fork());  // dc1 complete
+      RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
+      // NX := gradient w.r.t. the block's input = conv1^T dc1 + shortcut term; for bi > 0 it is the previous block's
+      // output gradient: mask it with that block's ReLU (xin > 0) and leave the sums of its bn2 (and downsample.1)
+      const bf16* shortcut = G;
+      if (blk.ds) {
+        SVSR_CHECK_CUDA(cudaMemsetAsync(NX, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
+        RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, NX, nullptr, s));
+        shortcut = NX;
+      }
+      if (bi > 0) {
+        BlockRef& pb = f.blocks[bi - 1];
+        const bool two = pb.ds && pb.cout <= 256;
+        RC(conv_dgrad_bnb(e, DC1, blk.Hin, blk.conv1, NX, shortcut, xin, 0, e.ws<bf16>(pb.c2), pb.bn2,
+                          two ? e.ws<bf16>(pb.cds) : nullptr, two ? &pb.bnds : nullptr, s));
+      } else {
+        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, NX, shortcut, s));
+      }
+      bf16* t = G;
+      G = NX, NX = t;
+      RC(sq.end_unit());
     }
-    RC(sq.fork());  // dc2 (and dcds) complete
-    RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
-    if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
-    RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
-    // bn1 is followed directly by its activation: mask / derivative recomputed from c1 (a1 is not read)
-    RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, f.swish ? 2 : 1));
-    RC(sq.fork());  // dc1 complete
-    RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
-    if (blk.ds) {
-      SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
-      RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, T4, nullptr, s));
-      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s));
-    } else {
-      RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T2, s));
+    T0 = G;
+  } else {
+    // ---- trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
+    for (int bi = 7; bi >= 0; --bi) {
+      BlockRef& blk = f.blocks[bi];
+      bf16* DC2 = e.ws<bf16>(f.gbuf[3 + (bi & 1)]);
+      bf16* DC1 = e.ws<bf16>(f.gbuf[5 + (bi & 1)]);
+      bf16* DCD = e.ws<bf16>(f.gbuf[7 + (bi & 1)]);
+      const bf16* xin = bi == 0 ? e.ws<bf16>(f.x1) : e.ws<bf16>(f.blocks[bi - 1].out);
+      const long long rows = (long long)e.N * blk.Hout * blk.Hout;
+      const bf16* out = e.ws<bf16>(blk.out);
+      if (!f.swish) {
+        RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : T2, s));
+        if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
+      } else {
+        // Swish(bn2(c2) + shortcut): the pre-activation is rebuilt from c2 and the shortcut operand (resnet.py:104-105)
+        if (blk.ds) {
+          RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, nullptr, s, 2, e.ws<bf16>(blk.cds),
+                    e.ws<float>(blk.bnds.coef)));
+          RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s, 2, e.ws<bf16>(blk.c2),
+                    e.ws<float>(blk.bn2.coef)));
+        } else {
+          RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, T2, s, 2, xin, nullptr));
+        }
+      }
+      RC(sq.fork());  // dc2 (and dcds) complete
+      RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
+      if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
+      RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
+      // bn1 is followed directly by its activation: mask / derivative recomputed from c1 (a1 is not read)
+      RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, f.swish ? 2 : 1));
+      RC(sq.fork());  // dc1 complete
+      RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
+      if (blk.ds) {
+        SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
+        RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, T4, nullptr, s));
+        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s));
+      } else {
+        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T2, s));
+      }
+      bf16* t = T0;
+      T0 = T4, T4 = t;
+      RC(sq.end_unit());
     }
-    bf16* t = T0;
-    T0 = T4, T4 = t;
-    RC(sq.end_unit());
   }
   // ---- stem ----
   bf16* dz = e.ws<bf16>(f.stem_dz);

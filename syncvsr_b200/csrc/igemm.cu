@@ -38,6 +38,7 @@ struct IgemmKParams {
   unsigned long long drop_seed;
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
   IgemmCe ce;     // fused cross-entropy epilogue (mode 0 = off)
+  IgemmBnBwd bnb;  // fused BatchNorm-backward statistics (n = 0: off)
 };
 
 // A pipeline stage holds KPS consecutive 64-wide k-blocks (A sub-tile + B sub-tile each): one mbarrier round trip
@@ -82,7 +83,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 constexpr int IGEMM_THREADS = 320;
 
-template <int BN, int STAGES, int KPS>
+template <int BN, int STAGES, int KPS, bool BNB>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmKParams p) {
@@ -122,7 +123,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-  if (p.bn_stats)
+  if (p.bn_stats || BNB)
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_stats[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
@@ -380,6 +381,60 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (col0 + jj < p.n_cols) f[jj] = __bfloat162float(mp[jj]) > 0.f ? f[jj] : 0.f;
           }
         }
+        if constexpr (BNB) {
+          // ---- fused BatchNorm-backward statistics (IgemmBnBwd): mask, then per-channel sums over the tile's 128 rows ----
+          const bool live = row_valid && full_chunk;
+          const int sstride = p.bnb.n == 2 ? 256 : 512;
+          float gq[32];
+#pragma unroll 1
+          for (int bi = 0; bi < p.bnb.n; ++bi) {
+            float cv[32];
+            if (live) {
+              const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.c[bi]) + row_off + col0);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint4 t = __ldg(cp + jj);
+                const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+                cv[8 * jj] = a.x, cv[8 * jj + 1] = a.y, cv[8 * jj + 2] = b.x, cv[8 * jj + 3] = b.y;
+                cv[8 * jj + 4] = c.x, cv[8 * jj + 5] = c.y, cv[8 * jj + 6] = d.x, cv[8 * jj + 7] = d.y;
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) cv[jj] = 0.f;
+            }
+            const float* cf = p.bnb.coef[bi];
+            if (bi == 0) {
+              if (p.bnb.self_mask) {  // the ReLU that follows BN 0: its mask is the sign of c*scale + shift
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(cf + 2 * p.n_cols + col0) + jj);
+                  const float4 sh = __ldg(reinterpret_cast<const float4*>(cf + 3 * p.n_cols + col0) + jj);
+                  f[4 * jj] = fmaf(cv[4 * jj], sc.x, sh.x) > 0.f ? f[4 * jj] : 0.f;
+                  f[4 * jj + 1] = fmaf(cv[4 * jj + 1], sc.y, sh.y) > 0.f ? f[4 * jj + 1] : 0.f;
+                  f[4 * jj + 2] = fmaf(cv[4 * jj + 2], sc.z, sh.z) > 0.f ? f[4 * jj + 2] : 0.f;
+                  f[4 * jj + 3] = fmaf(cv[4 * jj + 3], sc.w, sh.w) > 0.f ? f[4 * jj + 3] : 0.f;
+                }
+              }
+              // the statistics are those of the STORED (bf16-rounded) gradient, exactly what bn_bwd_apply reads back
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) gq[jj] = live ? __bfloat162float(__float2bfloat16(f[jj])) : 0.f;
+              float a[32];
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) a[jj] = gq[jj];
+              warp_transpose_reduce32(a, lane);
+              if (col0 + lane < p.n_cols) s_stats[q * 1024 + col0 + lane] += a[0];
+            }
+            float b[32];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 mu = __ldg(reinterpret_cast<const float4*>(cf + col0) + jj);
+              b[4 * jj] = gq[4 * jj] * (cv[4 * jj] - mu.x), b[4 * jj + 1] = gq[4 * jj + 1] * (cv[4 * jj + 1] - mu.y);
+              b[4 * jj + 2] = gq[4 * jj + 2] * (cv[4 * jj + 2] - mu.z), b[4 * jj + 3] = gq[4 * jj + 3] * (cv[4 * jj + 3] - mu.w);
+            }
+            warp_transpose_reduce32(b, lane);
+            if (col0 + lane < p.n_cols) s_stats[q * 1024 + (1 + bi) * sstride + col0 + lane] += b[0];
+          }
+        }
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + row_off + col0;
           if (full_chunk) {
@@ -498,6 +553,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         sl[512] += st_sq[g2][0], sl[513] += st_sq[g2][1];
       }
     }
+    if constexpr (BNB) {  // fused BatchNorm-backward sums: sum g is shared, sum g*(c - mean) gets its invstd here
+      named_bar_sync(3, 256);
+      const int sstride = p.bnb.n == 2 ? 256 : 512;
+      for (int cidx = threadIdx.x - 64; cidx < p.n_cols; cidx += 256) {
+        const double sg = (double)s_stats[cidx] + (double)s_stats[1024 + cidx] + (double)s_stats[2048 + cidx] +
+                          (double)s_stats[3072 + cidx];
+        for (int bi = 0; bi < p.bnb.n; ++bi) {
+          const int o = (1 + bi) * sstride + cidx;
+          const double sx = (double)s_stats[o] + (double)s_stats[1024 + o] + (double)s_stats[2048 + o] +
+                            (double)s_stats[3072 + o];
+          atomicAdd(p.bnb.stats[bi] + cidx, sg);
+          atomicAdd(p.bnb.stats[bi] + p.n_cols + cidx, sx * (double)__ldg(p.bnb.coef[bi] + p.n_cols + cidx));
+        }
+      }
+    }
     if (p.bn_stats) {  // flush this CTA's partial sums once (fp64 across CTAs)
       named_bar_sync(3, 256);  // the eight epilogue warps only
       const int t = threadIdx.x - 64;
@@ -538,20 +608,27 @@ void igemm_choose_box(int o_N, int OH, int OW, int* pbn, int* pbh, int* pbw) {
   *pbn = best[0], *pbh = best[1], *pbw = best[2];
 }
 
-template <int BN, int STAGES, int KPS>
-static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
-                    dim3 grid, cudaStream_t stream) {
+template <int BN, int STAGES, int KPS, bool BNB>
+static int launch_tb(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
+                     dim3 grid, cudaStream_t stream) {
   using L = IgemmSmem<BN, STAGES, KPS>;
   static bool attr_done = false;
   if (!attr_done) {
-    SVSR_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, KPS, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL));
     attr_done = true;
   }
-  igemm_kernel<BN, STAGES, KPS><<<grid, IGEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
+  igemm_kernel<BN, STAGES, KPS, BNB><<<grid, IGEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
   return SVSR_OK;
+}
+// (the fused BatchNorm-backward statistics are a separate instantiation: the common launches carry none of their registers)
+template <int BN, int STAGES, int KPS>
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
+                    dim3 grid, cudaStream_t stream) {
+  return kp.bnb.n ? launch_tb<BN, STAGES, KPS, true>(tmA, tmB, tmC, kp, grid, stream)
+                  : launch_tb<BN, STAGES, KPS, false>(tmA, tmB, tmC, kp, grid, stream);
 }
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
@@ -636,6 +713,15 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   CUtensorMap tmC = tmA;
   kp.tma_store = (!p.out_fp32 && p.b_rows % 64 == 0 && p.ce.mode != 1) ? 1 : 0;
   kp.ce = p.ce;
+  kp.bnb = p.bnb;
+  if (p.bnb.n) {
+    SVSR_REQUIRE(p.bnb.n == 1 || p.bnb.n == 2, "igemm: bnb.n = %d", p.bnb.n);
+    SVSR_REQUIRE(kp.tma_store && !p.bn_stats && p.c_off == 0 && p.b_rows == p.ldc && p.b_rows <= (p.bnb.n == 2 ? 256 : 512),
+                 "igemm: fused BatchNorm-backward statistics need a bf16 output of %d..%d channels (multiple of 64) that "
+                 "fills the pixel", 64, p.bnb.n == 2 ? 256 : 512);
+    for (int i = 0; i < p.bnb.n; ++i)
+      SVSR_REQUIRE(p.bnb.c[i] && p.bnb.coef[i] && p.bnb.stats[i], "igemm: bnb buffers of BatchNorm %d missing", i);
+  }
   if (kp.tma_store) {
     uint64_t dims[4] = {(uint64_t)p.ldc, (uint64_t)p.o_W, (uint64_t)p.o_H, (uint64_t)p.o_N};
     uint64_t strides[3] = {(uint64_t)p.ldc * 2, (uint64_t)p.o_W * p.ldc * 2, (uint64_t)p.o_H * p.o_W * p.ldc * 2};

@@ -33,6 +33,21 @@ struct IgemmCe {
   const float* grad_scale = nullptr;  // optional device scalar (upstream d loss)
 };
 
+// BatchNorm-backward statistics fused into the epilogue of the input-gradient GEMM that PRODUCES the gradient flowing
+// into the BatchNorm (timm BasicBlock bn1 / bn2 / downsample.1 via lightning.py:114-117): the launch's output is
+// g = (acc + resid) * [activation mask] (the mask from IgemmProblem::relu_mask, or -- self_mask -- from the sign of BN 0's
+// own output c*scale + shift, i.e. the ReLU that directly follows it), and per output channel the epilogue accumulates
+//   stats[i][0..C)  += sum_pixels g          stats[i][C..2C) += sum_pixels g * xhat_i,   xhat_i = (c_i - mean_i) * invstd_i
+// for up to two BatchNorms i that consume the same gradient (bn2 and downsample.1 of a strided block). The separate
+// reduce pass over (gradient, c, mask) disappears; bn_bwd_finalize / bn_bwd_apply run unchanged on these sums.
+struct IgemmBnBwd {
+  int n = 0;                                    // 0 = off
+  const void* c[2] = {nullptr, nullptr};        // conv outputs (bf16), same geometry / pitch as the GEMM output
+  const float* coef[2] = {nullptr, nullptr};    // fp32 [4][C]: mean, invstd, scale, shift (bn_finalize)
+  double* stats[2] = {nullptr, nullptr};        // fp64 [2][C] accumulators (+=)
+  int self_mask = 0;
+};
+
 // Host-side problem description. All channel counts are in elements (bf16).
 struct IgemmProblem {
   // ---- A operand (activations), NHWC ----
@@ -78,6 +93,7 @@ struct IgemmProblem {
   double* bn_stats = nullptr;
   double algo_flops = 0;  // algorithmic FLOPs of this launch for the profiler (0 = 2*pixels*N*taps*cin)
   IgemmCe ce;             // fused cross-entropy epilogue (dense GEMMs only)
+  IgemmBnBwd bnb;         // fused BatchNorm-backward statistics (bf16 outputs with a multiple of 64 channels)
 };
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);

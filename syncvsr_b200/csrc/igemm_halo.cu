@@ -30,7 +30,23 @@ struct HaloParams {
   int a_bytes;       // bytes of one halo box
   const void* resid;  // bf16 [N, H, W, 64] or null
   double* bn_stats;   // fp64 [2][64] (+=) or null
+  const void* relu_mask;  // bf16 [N, H, W, 64] or null: zero the result where mask <= 0
+  IgemmBnBwd bnb;         // fused BatchNorm-backward statistics of ONE BatchNorm (igemm.cuh), n = 0: off
 };
+
+// Transposed warp reduction (see igemm.cu): afterwards lane l holds in v[0] the sum over the 32 lanes of value l.
+__device__ __forceinline__ void warp_transpose_reduce32h(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
 
 struct HaloSmem {
   static constexpr int B_OFFSET = 0;
@@ -42,6 +58,7 @@ struct HaloSmem {
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
 };
 
+template <bool BNB>  // BNB: fused BatchNorm-backward statistics (+ activation masks) in the epilogue
 __global__ void __launch_bounds__(320, 1)
 conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
@@ -139,18 +156,20 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int bar_id = 1 + g;
     uint8_t* stg = s_stage + g * 16384;
     float st_sum[2] = {0.f, 0.f}, st_sq[2] = {0.f, 0.f};
+    float bg[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f};  // fused BatchNorm-backward sums of column ch*32 + lane
     int j = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
       if ((j & 1) != g) continue;
       const int n = tile / p.tiles_per_img, h0 = (tile - n * p.tiles_per_img) * p.RT;
       const bool valid = col_ok && (h0 + hr) < p.H;
       uint4 rv[8];
-      if (p.resid && valid) {
+      if (p.resid && valid && !BNB) {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
                                                          (((long long)n * p.H + h0 + hr) * p.W + (c - 1)) * 64);
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = __ldg(rp + i);
       }
+      const long long pix_off = (((long long)n * p.H + h0 + hr) * p.W + (c - 1)) * 64;
       mbar_wait(&tmem_full_bar[g], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
       if (leader) tma_store_wait_read<0>();  // this group's previous store has read the staging buffer
@@ -159,8 +178,94 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + ch * 32), v);
+        uint4 mv[4], cq[4];  // activation-mask reference and BatchNorm input of this row's 32 channels
+        if (BNB && p.relu_mask && valid) {
+          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.relu_mask) + pix_off + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mv[i] = __ldg(mp + i);
+        }
+        if (BNB && valid) {
+          const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.c[0]) + pix_off + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cq[i] = __ldg(cp + i);
+          if (p.resid) {  // (the fused-statistics path fetches the residual chunk by chunk: fewer live registers)
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix_off + ch * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rv[i] = __ldg(rp + i);
+          }
+        }
         tmem_ld_wait();
-        if (valid) {
+        if constexpr (BNB) {  // all 32 lanes take part in the transposed reduction: rows outside the image contribute zeros
+          float f[32], cv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) : 0.f;
+          if (p.resid && valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 t = rv[i];
+              const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), cc = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+              f[8 * i] += a.x, f[8 * i + 1] += a.y, f[8 * i + 2] += b.x, f[8 * i + 3] += b.y;
+              f[8 * i + 4] += cc.x, f[8 * i + 5] += cc.y, f[8 * i + 6] += d.x, f[8 * i + 7] += d.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (valid) {
+              const float2 a = unpack_bf16x2(cq[i].x), b = unpack_bf16x2(cq[i].y), cc = unpack_bf16x2(cq[i].z), d = unpack_bf16x2(cq[i].w);
+              cv[8 * i] = a.x, cv[8 * i + 1] = a.y, cv[8 * i + 2] = b.x, cv[8 * i + 3] = b.y;
+              cv[8 * i + 4] = cc.x, cv[8 * i + 5] = cc.y, cv[8 * i + 6] = d.x, cv[8 * i + 7] = d.y;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) cv[8 * i + k] = 0.f;
+            }
+          }
+          if (p.relu_mask && valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = unpack_bf16x2(mv[i].x), b = unpack_bf16x2(mv[i].y), cc = unpack_bf16x2(mv[i].z), d = unpack_bf16x2(mv[i].w);
+              f[8 * i] = a.x > 0.f ? f[8 * i] : 0.f, f[8 * i + 1] = a.y > 0.f ? f[8 * i + 1] : 0.f;
+              f[8 * i + 2] = b.x > 0.f ? f[8 * i + 2] : 0.f, f[8 * i + 3] = b.y > 0.f ? f[8 * i + 3] : 0.f;
+              f[8 * i + 4] = cc.x > 0.f ? f[8 * i + 4] : 0.f, f[8 * i + 5] = cc.y > 0.f ? f[8 * i + 5] : 0.f;
+              f[8 * i + 6] = d.x > 0.f ? f[8 * i + 6] : 0.f, f[8 * i + 7] = d.y > 0.f ? f[8 * i + 7] : 0.f;
+            }
+          }
+          const float* cf = p.bnb.coef[0];
+          if (p.bnb.self_mask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(cf + 128 + ch * 32) + i);
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(cf + 192 + ch * 32) + i);
+              f[4 * i] = fmaf(cv[4 * i], sc.x, sh.x) > 0.f ? f[4 * i] : 0.f;
+              f[4 * i + 1] = fmaf(cv[4 * i + 1], sc.y, sh.y) > 0.f ? f[4 * i + 1] : 0.f;
+              f[4 * i + 2] = fmaf(cv[4 * i + 2], sc.z, sh.z) > 0.f ? f[4 * i + 2] : 0.f;
+              f[4 * i + 3] = fmaf(cv[4 * i + 3], sc.w, sh.w) > 0.f ? f[4 * i + 3] : 0.f;
+            }
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 t;
+              t.x = pack_bf16x2(f[8 * i], f[8 * i + 1]), t.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+              t.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), t.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+              const int chunk = (ch * 4 + i) ^ (srow & 7);
+              *reinterpret_cast<uint4*>(stg + srow * 128 + chunk * 16) = t;
+            }
+          }
+          // sums of the STORED (bf16-rounded) gradient: sum g and sum g * (c - mean), invstd applied at the flush
+          float a[32], b[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(cf + ch * 32) + i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[4 * i + k] = __bfloat162float(__float2bfloat16(f[4 * i + k]));
+            b[4 * i] = a[4 * i] * (cv[4 * i] - mu.x), b[4 * i + 1] = a[4 * i + 1] * (cv[4 * i + 1] - mu.y);
+            b[4 * i + 2] = a[4 * i + 2] * (cv[4 * i + 2] - mu.z), b[4 * i + 3] = a[4 * i + 3] * (cv[4 * i + 3] - mu.w);
+          }
+          warp_transpose_reduce32h(a, lane);
+          warp_transpose_reduce32h(b, lane);
+          bg[ch] += a[0], bx[ch] += b[0];
+        }
+        if (!BNB && valid) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -207,6 +312,19 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
     if (leader) tma_store_wait_all();
+    if constexpr (BNB) {
+      float* sl = s_stats + (warp - 2) * 128;
+      sl[lane] = bg[0], sl[32 + lane] = bg[1], sl[64 + lane] = bx[0], sl[96 + lane] = bx[1];
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const int t = threadIdx.x - 64;  // t < 64: sum g of channel t; 64 <= t < 128: sum g * xhat of channel t - 64
+      if (t < 128) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += (double)s_stats[w * 128 + t];
+        if (t >= 64) sacc *= (double)__ldg(p.bnb.coef[0] + 64 + (t - 64));  // x invstd
+        atomicAdd(p.bnb.stats[0] + t, sacc);
+      }
+    }
     if (p.bn_stats) {
       float* sl = s_stats + (warp - 2) * 128 + 2 * lane;
       sl[0] = st_sum[0], sl[1] = st_sum[1], sl[64] = st_sq[0], sl[65] = st_sq[1];
@@ -230,8 +348,13 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
 // y[N,H,W,64] = sum_t x[n, h + dh_t, w + dw_t, :] . Wm[:, kbase_t .. kbase_t+64)^T (+ resid); Wm bf16 [64, 576]
 int conv3x3_c64_halo(const void* x, const void* wm, int w_pitch, void* y, const void* resid, int N, int H, int W,
-                     const int* tap_dh, const int* tap_dw, const int* tap_kbase, double* bn_stats, cudaStream_t stream) {
+                     const int* tap_dh, const int* tap_dw, const int* tap_kbase, double* bn_stats, cudaStream_t stream,
+                     const void* relu_mask = nullptr, const IgemmBnBwd* bnb = nullptr) {
   HaloParams p{};
+  p.relu_mask = relu_mask;
+  if (bnb) p.bnb = *bnb;
+  SVSR_REQUIRE(p.bnb.n <= 1 && !(p.bnb.n && bn_stats), "halo conv: at most one fused BatchNorm backward, not with forward stats");
+  SVSR_REQUIRE(!p.bnb.n || (p.bnb.c[0] && p.bnb.coef[0] && p.bnb.stats[0]), "halo conv: bnb buffers missing");
   p.N = N, p.H = H, p.W = W, p.P = W + 2;
   p.RT = 128 / p.P;
   SVSR_REQUIRE(p.P <= 27 && p.RT >= 1, "halo conv: image width %d unsupported", W);
@@ -265,13 +388,18 @@ int conv3x3_c64_halo(const void* x, const void* wm, int w_pitch, void* y, const 
   }
   static bool attr_done = false;
   if (!attr_done) {
-    SVSR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_c64_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HaloSmem::TOTAL));
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_c64_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HaloSmem::TOTAL));
     attr_done = true;
   }
   const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
   prof_begin(PROF_IGEMM, 2.0 * N * H * W * 64.0 * 576.0, stream);
-  conv3x3_c64_halo_kernel<<<grid, 320, HaloSmem::TOTAL, stream>>>(tmA, tmB, tmC, p);
+  if (p.bnb.n || p.relu_mask)
+    conv3x3_c64_halo_kernel<true><<<grid, 320, HaloSmem::TOTAL, stream>>>(tmA, tmB, tmC, p);
+  else
+    conv3x3_c64_halo_kernel<false><<<grid, 320, HaloSmem::TOTAL, stream>>>(tmA, tmB, tmC, p);
   note_launch();
   prof_end(stream);
   SVSR_CHECK_CUDA(cudaGetLastError());
@@ -284,7 +412,8 @@ bool igemm_halo_matches(const IgemmProblem& p) {
   if (!(p.ntaps == 9 && p.cin == 64 && p.b_rows == 64 && p.stride == 1 && p.a_C == 64 && p.a_coff == 0)) return false;
   if (p.out_fp32 || p.ldc != 64 || p.c_off != 0 || p.o_sh != 1 || p.o_sw != 1 || p.o_oh != 0 || p.o_ow != 0) return false;
   if (p.OH != p.a_H || p.OW != p.a_W || p.o_H != p.OH || p.o_W != p.OW || p.o_N != p.a_N) return false;
-  if (p.bias || p.alpha != 1.0f || p.relu || p.relu_mask || p.drop_p > 0.f || (p.resid && p.resid_fp32)) return false;
+  if (p.bias || p.alpha != 1.0f || p.relu || p.drop_p > 0.f || (p.resid && p.resid_fp32) || p.ce.mode || p.bnb.n > 1) return false;
+  if (p.relu_mask && !p.bnb.n) return false;  // the masked epilogue only exists with the fused statistics
   if (p.a_W + 2 > 27 || p.a_W < 2) return false;
   for (int t = 0; t < 9; ++t)
     if (p.tap_dh[t] < -1 || p.tap_dh[t] > 1 || p.tap_dw[t] < -1 || p.tap_dw[t] > 1) return false;
@@ -294,7 +423,7 @@ bool igemm_halo_matches(const IgemmProblem& p) {
 
 int igemm_halo_launch(const IgemmProblem& p, cudaStream_t stream) {
   return conv3x3_c64_halo(p.a, p.b, p.b_cols, p.out, p.resid, p.a_N, p.a_H, p.a_W, p.tap_dh, p.tap_dw, p.tap_kbase,
-                          p.bn_stats, stream);
+                          p.bn_stats, stream, p.relu_mask, &p.bnb);
 }
 
 }  // namespace svsr

@@ -82,6 +82,27 @@ def conv2d_dgrad(dy: torch.Tensor, wd_packed: torch.Tensor, H: int, W: int, R: i
     return dx
 
 
+def conv2d_dgrad_bnbwd(dy: torch.Tensor, wd_packed: torch.Tensor, H: int, W: int, R: int, S: int, stride: int, pad: int,
+                       c0: torch.Tensor, coef0: torch.Tensor, resid: torch.Tensor | None = None,
+                       relu_mask: torch.Tensor | None = None, self_mask: bool = False, c1: torch.Tensor | None = None,
+                       coef1: torch.Tensor | None = None, dx: torch.Tensor | None = None):
+    """Input gradient with the consumer BatchNorm's backward reduction fused into the epilogue (svsr_conv2d_dgrad_bnbwd).
+    Returns (dx bf16 [N,H,W,Cin] already masked, stats0 fp64 [2,Cin], stats1 | None)."""
+    _req(dy, torch.bfloat16, "dy"), _req(wd_packed, torch.bfloat16, "wd_packed"), _req(c0, torch.bfloat16, "c0")
+    N, OH, OW, Cout = dy.shape
+    Cin = wd_packed.shape[0]
+    if dx is None:
+        dx = torch.zeros(N, H, W, Cin, device=dy.device, dtype=torch.bfloat16)
+    st0 = torch.zeros(2, Cin, device=dy.device, dtype=torch.float64)
+    st1 = torch.zeros(2, Cin, device=dy.device, dtype=torch.float64) if c1 is not None else None
+    rc = lib().svsr_conv2d_dgrad_bnbwd(ptr(dy), ptr(wd_packed), ptr(dx), ptr(resid), C.c_int(N), C.c_int(H), C.c_int(W),
+                                       C.c_int(Cin), C.c_int(Cout), C.c_int(R), C.c_int(S), C.c_int(stride), C.c_int(pad),
+                                       ptr(relu_mask), C.c_int(int(self_mask)), ptr(c0), ptr(coef0), ptr(st0), ptr(c1),
+                                       ptr(coef1), ptr(st1), stream_ptr())
+    check(rc, "svsr_conv2d_dgrad_bnbwd")
+    return dx, st0, st1
+
+
 def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, R: int, S: int, stride: int, pad: int,
                  out: torch.Tensor | None = None) -> torch.Tensor:
     """Returns dw as fp32 [R*S*Cin, Cout] (row (r*S+s)*Cin+ci); accumulates into `out` if given."""

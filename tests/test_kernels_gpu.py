@@ -87,6 +87,65 @@ def test_conv_fused_batchnorm_statistics(ops, N, H, W, Cin, Cout, R, stride, pad
     assert rel(stats[1], (ref.double() ** 2).sum((0, 2, 3))) < 2e-3
 
 
+BNB_CASES = [
+    # N, H, W, Cin, Cout, stride, mask ("self" | "ref"), resid, two BatchNorms     (the launches of frontend_backward)
+    (40, 22, 22, 64, 64, 1, "self", False, False),    # layer1 conv2 dgrad (halo kernel): bn1's own ReLU
+    (40, 22, 22, 64, 64, 1, "ref", True, False),      # layer1.1 conv1 dgrad (halo): + identity shortcut, relu(out) of layer1.0
+    (3, 24, 24, 64, 64, 1, "ref", True, False),       # 96x96 crops
+    (35, 22, 22, 64, 128, 2, "ref", True, False),     # layer2.0 conv1 dgrad: stride 2 (4 pixel classes), in-place shortcut
+    (33, 11, 11, 128, 128, 1, "self", False, False),  # layer2 conv2 dgrad (generic kernel)
+    (33, 11, 11, 128, 128, 1, "ref", True, True),     # layer2.1 conv1 dgrad: feeds bn2 AND downsample.1 of layer2.0
+    (41, 6, 6, 256, 256, 1, "ref", True, True),       # layer3.1 conv1 dgrad, two BatchNorms over 256 channels
+    (300, 3, 3, 512, 512, 1, "ref", True, False),     # layer4.1 conv1 dgrad, 512 channels
+    (300, 3, 3, 512, 512, 1, "self", False, False),
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,stride,mask,with_resid,two", BNB_CASES)
+def test_dgrad_with_fused_batchnorm_backward_statistics(ops, N, H, W, Cin, Cout, stride, mask, with_resid, two):
+    """svsr_conv2d_dgrad_bnbwd: the masked input gradient equals (plain dgrad + shortcut) * mask bit for bit, and the sums it
+    leaves are those of the standalone BatchNorm-backward reduce over the STORED gradient: sum g, sum g * xhat."""
+    OH = (H + 2 - 3) // stride + 1
+    w = randn(Cout, Cin, 3, 3, seed=41, scale=0.05)
+    dy = randn(N, OH, OH, Cout, seed=42, scale=0.1)
+    wd = ops.pack_conv_weight_dgrad(w)
+    c0, c1 = randn(N, H, W, Cin, seed=43), randn(N, H, W, Cin, seed=44)
+    resid = randn(N, H, W, Cin, seed=45, scale=0.3) if with_resid else None
+    ref_mask = randn(N, H, W, Cin, seed=46)
+    g = torch.Generator(device="cuda").manual_seed(47)
+
+    def coef_of(c):
+        mean, var = c.float().mean((0, 1, 2)), c.float().var((0, 1, 2), unbiased=False)
+        gamma = 1 + 0.2 * torch.randn(Cin, device="cuda", generator=g)
+        beta = 0.3 * torch.randn(Cin, device="cuda", generator=g)
+        inv = torch.rsqrt(var + 1e-5)
+        return torch.stack([mean, inv, gamma * inv, beta - mean * gamma * inv]).contiguous()
+
+    cf0, cf1 = coef_of(c0), coef_of(c1)
+    plain = ops.conv2d_dgrad(dy, wd, H, W, 3, 3, stride, 1, resid=resid)
+    ambiguous = torch.zeros(N, H, W, Cin, dtype=torch.bool, device="cuda")
+    if mask == "self":
+        z = c0.double() * cf0[2].double() + cf0[3].double()
+        keep = z > 0
+        # the kernel evaluates fma(c, scale, shift) in fp32: a pre-activation within rounding of zero may fall either way
+        ambiguous = z.abs() < 1e-6 * ((c0.double() * cf0[2].double()).abs() + cf0[3].double().abs())
+    else:
+        keep = ref_mask.float() > 0
+    want = torch.where(keep, plain.float(), torch.zeros((), device="cuda")).bfloat16()
+    dx_buf = resid.clone() if (with_resid and stride == 2) else None  # the engine's strided blocks add in place
+    dx, st0, st1 = ops.conv2d_dgrad_bnbwd(dy, wd, H, W, 3, 3, stride, 1, c0, cf0, resid=dx_buf if dx_buf is not None else resid,
+                                          relu_mask=None if mask == "self" else ref_mask, self_mask=mask == "self",
+                                          c1=c1 if two else None, coef1=cf1 if two else None, dx=dx_buf)
+    assert torch.equal(dx[~ambiguous], want[~ambiguous]) and int(ambiguous.sum()) < 50
+    gd = dx.double()
+    for st, c, cf in ((st0, c0, cf0), (st1, c1, cf1)):
+        if st is None:
+            continue
+        xhat = (c.double() - cf[0].double()) * cf[1].double()
+        assert rel(st[0], gd.sum((0, 1, 2))) < 1e-5
+        assert rel(st[1], (gd * xhat).sum((0, 1, 2))) < 1e-4
+
+
 @pytest.mark.parametrize("N,H,W", [(40, 22, 22), (3, 24, 24), (5, 7, 25), (2, 1, 2), (9, 13, 5), (1, 30, 11)])
 def test_halo_conv_matches_generic_igemm(ops, monkeypatch, N, H, W):
     """igemm_halo.cu (one activation load per tile, resident weights) against the tap-by-tap kernel it replaces for the
