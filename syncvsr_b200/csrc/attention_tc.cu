@@ -1,0 +1,389 @@
+// x-transformers attention core on the tensor cores (reference: x_transformers.Encoder sublayer "a" called at
+// LRW/video/src/lightning.py:95-105,158 -- SURVEY.md Appendix A: rotary on the first 32 dims of q, k (and v), scale 64^-1/2,
+// fp32 softmax, attn_dropout on the probabilities): n <= 64 tokens, 64-dim heads.
+//
+// The sequence is tiny (n = 30 at T = 29), so ONE 128-row UMMA tile carries PPT = 128 / BS (batch, head) pairs, each
+// padded to BS = 32 (or 64) rows: S = Q' K'^T is a single [128 x 128] tcgen05 product whose diagonal BS x BS blocks are
+// the pairs' score matrices (the off-diagonal blocks are never read), P is written back block-diagonally (zeros
+// elsewhere) and O = P V' is a second [128 x 64] product. Thread r of the 128-thread CTA owns tile row r = TMEM lane r:
+// it loads its q / k / v row (16-byte loads), applies the rotation in registers, stores the bf16 row into the
+// 128-byte-swizzled operand tile, and later reads its own score row from TMEM -- softmax needs no shuffles.
+// The same shared-memory bytes serve as K-major operands (rows = M/N index, 64 K elements per 128-byte row) and as
+// MN-major operands (rows = K index), so the backward's five products
+//     S = Q'K'^T   dP = dO V'^T   dV' = P^T dO   dQ' = dS K'   dK' = dS^T Q'
+// need no transposed copies: 4 + 4 + 8 + 8 + 8 MMAs on tiles that are written once.
+#include "encoder.cuh"
+
+namespace svsr {
+namespace {
+
+constexpr int TC_D = 64;
+constexpr int TILE_BYTES = 128 * 128;  // [128 rows x 64 bf16], SWIZZLE_128B
+constexpr float LOG2E = 1.4426950408889634f;
+
+// 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint8_t* sw_chunk(uint8_t* tile, int r, int c) { return tile + r * 128 + ((c ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y, f[4] = c.x, f[5] = c.y, f[6] = d.x, f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]), u.y = pack_bf16x2(f[2], f[3]), u.z = pack_bf16x2(f[4], f[5]), u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// Loads one 64-wide bf16 row (or zeros), rotates the pairs (f, f + 16), f < 16, by the row's angles when `rotate`, and
+// stores it as bf16 into row r of a swizzled tile. cs = this row's [16 cos | 16 sin].
+__device__ __forceinline__ void load_rot_store(const __nv_bfloat16* __restrict__ src, bool valid, bool rotate,
+                                               const float* cs, uint8_t* tile, int r) {
+  float x[64];
+  if (valid) {
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) unpack8(__ldg(p + c), x + 8 * c);
+    if (rotate) {
+#pragma unroll
+      for (int f = 0; f < 16; ++f) {
+        const float a = x[f], b = x[f + 16];
+        x[f] = a * cs[f] - b * cs[16 + f];
+        x[f + 16] = b * cs[f] + a * cs[16 + f];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) x[i] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sw_chunk(tile, r, c)) = pack8(x + 8 * c);
+}
+
+// K-major operand whose K extent is one 128-byte row (64 elements): 4 MMAs of K = 16
+__device__ __forceinline__ void mma_k64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
+  const uint64_t a = umma_smem_desc_sw128(a_addr, 16, 1024), b = umma_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, k != 0);
+}
+// D[128 x 64] = X[128 x 128 (K)] . Y[128 (K) x 64]: X = two-block tile (block kb = K columns [64 kb, 64 kb + 64)) read
+// K-major, or -- a_mn -- the same tile read MN-major (D = X^T . Y, M = the tile's columns); Y MN-major (rows = K index)
+__device__ __forceinline__ void mma_k128(uint32_t d_tmem, uint32_t x_addr, uint32_t y_addr, bool a_mn) {
+  const uint32_t idesc = umma_idesc_bf16(128, 64, a_mn ? 1 : 0, 1);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t a = a_mn ? umma_smem_desc_sw128(x_addr + ks * 2048, TILE_BYTES, 1024)
+                            : umma_smem_desc_sw128(x_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
+    const uint64_t b = umma_smem_desc_sw128(y_addr + ks * 2048, TILE_BYTES, 1024);
+    umma_bf16(d_tmem, a, b, idesc, ks != 0);
+  }
+}
+
+// softmax of this thread's score row (BS columns of its pair's block, columns >= n masked); p[] = probabilities
+template <int BS>
+__device__ __forceinline__ void softmax_row(const float (&s)[BS], int n, float (&p)[BS]) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < BS; ++j)
+    if (j < n) m = fmaxf(m, s[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    p[j] = j < n ? exp2f((s[j] - m) * (0.125f * LOG2E)) : 0.f;  // scale 64^-1/2 folded in: max commutes with it
+    sum += p[j];
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < BS; ++j) p[j] *= inv;
+}
+
+template <int BS>
+__device__ __forceinline__ void tmem_row(uint32_t taddr, float (&s)[BS]) {
+#pragma unroll
+  for (int c = 0; c < BS / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[c * 32 + j] = __uint_as_float(v[j]);
+  }
+}
+
+// bf16 row of a block-diagonal [128 x 128] two-block tile: this row's BS columns start at column blk * BS
+template <int BS>
+__device__ __forceinline__ void store_block_row(uint8_t* tile2, int r, int blk, const float (&x)[BS]) {
+#pragma unroll
+  for (int c = 0; c < BS / 8; ++c) {
+    const int cg = blk * (BS / 8) + c;  // 16-byte chunk index inside the 256-byte logical row
+    *reinterpret_cast<uint4*>(sw_chunk(tile2 + (cg >> 3) * TILE_BYTES, r, cg & 7)) = pack8(&x[8 * c]);
+  }
+}
+
+struct AttnTcParams {
+  const __nv_bfloat16* qkv;
+  const float* rot;
+  const __nv_bfloat16* d_o;
+  __nv_bfloat16* o;     // forward output / unused in backward
+  __nv_bfloat16* dqkv;  // backward output
+  int n, heads, pairs, rotary_v;
+  float drop_p;
+  unsigned long long drop_seed;
+};
+
+template <int BS>
+__global__ void __launch_bounds__(128, 1) attention_tc_fwd_kernel(const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sP = sV + TILE_BYTES;  // two blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  constexpr int PPT = 128 / BS;
+  const int r = threadIdx.x, warp = r >> 5;
+  const int blk = r / BS, t = r - blk * BS;
+  const int pair = blockIdx.x * PPT + blk;
+  const bool valid = t < p.n && pair < p.pairs;
+  const int b = pair / p.heads, h = pair - b * p.heads;
+  const int inner = p.heads * TC_D, ld = 3 * inner;
+
+  if (r == 0) {
+    mbar_init(&bar[0], 1), mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 256);
+  {  // P is block diagonal: everything outside the pairs' own blocks stays zero
+    uint4* z = reinterpret_cast<uint4*>(sP);
+    for (int i = r; i < 2 * TILE_BYTES / 16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  float cs[32] = {};
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.rot + t * 32) + i);
+      cs[4 * i] = v.x, cs[4 * i + 1] = v.y, cs[4 * i + 2] = v.z, cs[4 * i + 3] = v.w;
+    }
+  }
+  const __nv_bfloat16* src = p.qkv + ((long long)b * p.n + t) * ld + h * TC_D;
+  load_rot_store(src, valid, true, cs, sQ, r);
+  load_rot_store(src + inner, valid, true, cs, sK, r);
+  load_rot_store(src + 2 * inner, valid, p.rotary_v != 0, cs, sV, r);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (r == 0) {
+    mma_k64(tmem, smem_u32(sQ), smem_u32(sK), umma_idesc_bf16(128, 128, 0, 0));  // S -> columns [0, 128)
+    umma_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tcgen05_fence_after();
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  {
+    float s[BS], pr[BS];
+    tmem_row<BS>(lane_base + (uint32_t)(blk * BS), s);
+    softmax_row<BS>(s, p.n, pr);
+    if (p.drop_p > 0.f) {  // Attention(dropout=attn_dropout): element index ((b*H + h)*n + i)*n + j
+      const float ks = 1.0f / (1.0f - p.drop_p);
+      const unsigned long long base = ((unsigned long long)pair * p.n + t) * p.n;
+#pragma unroll
+      for (int j = 0; j < BS; ++j)
+        pr[j] = (j < p.n && dropout_keep(p.drop_seed, base + j, p.drop_p)) ? pr[j] * ks : 0.f;
+    }
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) pr[j] = 0.f;
+    }
+    store_block_row<BS>(sP, r, blk, pr);
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (r == 0) {
+    mma_k128(tmem + 128, smem_u32(sP), smem_u32(sV), false);  // O = P V' -> columns [128, 192)
+    umma_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tcgen05_fence_after();
+  {
+    float ov[64];
+    tmem_row<64>(lane_base + 128u, ov);
+    if (valid) {
+      uint4* dst = reinterpret_cast<uint4*>(p.o + ((long long)b * p.n + t) * inner + h * TC_D);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c] = pack8(ov + 8 * c);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// rotate a gradient row back (transpose of the rotation) and store it as bf16
+__device__ __forceinline__ void unrot_store(float (&x)[64], bool rotate, const float* cs, __nv_bfloat16* dst) {
+  if (rotate) {
+#pragma unroll
+    for (int f = 0; f < 16; ++f) {
+      const float a = x[f], b = x[f + 16];
+      x[f] = a * cs[f] + b * cs[16 + f];
+      x[f + 16] = b * cs[f] - a * cs[16 + f];
+    }
+  }
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) d4[c] = pack8(x + 8 * c);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128, 1) attention_tc_bwd_kernel(const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sO = sV + TILE_BYTES;   // dO
+  uint8_t* sP = sO + TILE_BYTES;   // two blocks
+  uint8_t* sS = sP + 2 * TILE_BYTES;  // dS, two blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + 2 * TILE_BYTES);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  constexpr int PPT = 128 / BS;
+  const int r = threadIdx.x, warp = r >> 5;
+  const int blk = r / BS, t = r - blk * BS;
+  const int pair = blockIdx.x * PPT + blk;
+  const bool valid = t < p.n && pair < p.pairs;
+  const int b = pair / p.heads, h = pair - b * p.heads;
+  const int inner = p.heads * TC_D, ld = 3 * inner;
+
+  if (r == 0) {
+    mbar_init(&bar[0], 1), mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  {
+    uint4* z = reinterpret_cast<uint4*>(sP);  // P and dS are contiguous
+    for (int i = r; i < 4 * TILE_BYTES / 16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  float cs[32] = {};
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.rot + t * 32) + i);
+      cs[4 * i] = v.x, cs[4 * i + 1] = v.y, cs[4 * i + 2] = v.z, cs[4 * i + 3] = v.w;
+    }
+  }
+  const long long row = (long long)b * p.n + t;
+  const __nv_bfloat16* src = p.qkv + row * ld + h * TC_D;
+  load_rot_store(src, valid, true, cs, sQ, r);
+  load_rot_store(src + inner, valid, true, cs, sK, r);
+  load_rot_store(src + 2 * inner, valid, p.rotary_v != 0, cs, sV, r);
+  load_rot_store(p.d_o + row * inner + h * TC_D, valid, false, cs, sO, r);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (r == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+    mma_k64(tmem, smem_u32(sQ), smem_u32(sK), idesc);        // S  -> columns [0, 128)
+    mma_k64(tmem + 128, smem_u32(sO), smem_u32(sV), idesc);  // dP -> columns [128, 256)
+    umma_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tcgen05_fence_after();
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  {
+    float s[BS], pr[BS], dp[BS];
+    tmem_row<BS>(lane_base + (uint32_t)(blk * BS), s);
+    softmax_row<BS>(s, p.n, pr);
+    tmem_row<BS>(lane_base + 128u + (uint32_t)(blk * BS), dp);
+    // d p = mask * d p~ ; dS = P o (dP - rowsum(dP o P)) * scale ; dV' uses p~ = mask * p
+    float dot = 0.f;
+    if (p.drop_p > 0.f) {
+      const float ks = 1.0f / (1.0f - p.drop_p);
+      const unsigned long long base = ((unsigned long long)pair * p.n + t) * p.n;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const float m = (j < p.n && dropout_keep(p.drop_seed, base + j, p.drop_p)) ? ks : 0.f;
+        dp[j] *= m;
+        dot += pr[j] * dp[j];
+        s[j] = pr[j] * m;  // p~
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) dot += pr[j] * dp[j], s[j] = pr[j];
+    }
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      dp[j] = valid ? pr[j] * (dp[j] - dot) * 0.125f : 0.f;  // dS (the 64^-1/2 of the scores folded in)
+      if (!valid) s[j] = 0.f;
+    }
+    store_block_row<BS>(sP, r, blk, s);
+    store_block_row<BS>(sS, r, blk, dp);
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (r == 0) {
+    mma_k128(tmem + 256, smem_u32(sP), smem_u32(sO), true);   // dV' = P~^T dO -> [256, 320)
+    mma_k128(tmem + 320, smem_u32(sS), smem_u32(sK), false);  // dQ' = dS K'   -> [320, 384)
+    mma_k128(tmem + 384, smem_u32(sS), smem_u32(sQ), true);   // dK' = dS^T Q' -> [384, 448)
+    umma_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tcgen05_fence_after();
+  {
+    __nv_bfloat16* dst = p.dqkv + row * ld + h * TC_D;
+    float g[64];
+    tmem_row<64>(lane_base + 320u, g);
+    if (valid) unrot_store(g, true, cs, dst);
+    tmem_row<64>(lane_base + 384u, g);
+    if (valid) unrot_store(g, true, cs, dst + inner);
+    tmem_row<64>(lane_base + 256u, g);
+    if (valid) unrot_store(g, p.rotary_v != 0, cs, dst + 2 * inner);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int BS>
+int launch_tc(const AttnTcParams& p, bool bwd, cudaStream_t s) {
+  constexpr int PPT = 128 / BS;
+  const int grid = (p.pairs + PPT - 1) / PPT;
+  const int smem = (bwd ? 8 : 5) * TILE_BYTES + 64 + 1024;
+  static bool done[2] = {false, false};
+  if (!done[bwd]) {
+    if (bwd)
+      SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_bwd_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else
+      SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_fwd_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done[bwd] = true;
+  }
+  if (bwd)
+    attention_tc_bwd_kernel<BS><<<grid, 128, smem, s>>>(p);
+  else
+    attention_tc_fwd_kernel<BS><<<grid, 128, smem, s>>>(p);
+  note_launch();
+  SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+
+}  // namespace
+
+int attention_tc_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads, int rotary_v,
+                     cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+  SVSR_REQUIRE(n >= 1 && n <= 64, "attention: n=%d must be in [1,64]", n);
+  AttnTcParams p{qkv, rot, nullptr, o, nullptr, n, heads, B * heads, rotary_v, drop_p, drop_seed};
+  return n <= 32 ? launch_tc<32>(p, false, s) : launch_tc<64>(p, false, s);
+}
+int attention_tc_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int n,
+                     int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+  SVSR_REQUIRE(n >= 1 && n <= 64, "attention: n=%d must be in [1,64]", n);
+  AttnTcParams p{qkv, rot, d_o, nullptr, dqkv, n, heads, B * heads, rotary_v, drop_p, drop_seed};
+  return n <= 32 ? launch_tc<32>(p, true, s) : launch_tc<64>(p, true, s);
+}
+
+}  // namespace svsr

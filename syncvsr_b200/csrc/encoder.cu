@@ -1,4 +1,5 @@
 #include "encoder.cuh"
+#include <stdlib.h>
 
 namespace svsr {
 
@@ -590,9 +591,15 @@ int rotary_table(float* tab, int n, cudaStream_t s) {
   LAUNCH_CHECK();
   return SVSR_OK;
 }
+// SVSR_ATTN_TC=0 keeps the CUDA-core fp32 kernels below (A/B); the default is the tcgen05 pair of attention_tc.cu.
+static bool attn_use_tc() {
+  const char* e = getenv("SVSR_ATTN_TC");
+  return !(e && e[0] == '0');
+}
 int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
                   int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
+  if (attn_use_tc()) return attention_tc_fwd(qkv, rot, o, B, n, heads, rotary_v, s, drop_p, drop_seed);
   const int smem = 4 * n * AT_LD * sizeof(float);
   const int smem_max = 4 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;
@@ -607,6 +614,7 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
                   int n, int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
+  if (attn_use_tc()) return attention_tc_bwd(qkv, rot, d_o, dqkv, B, n, heads, rotary_v, s, drop_p, drop_seed);
   const int smem = 6 * n * AT_LD * sizeof(float);
   const int smem_max = 6 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;

@@ -25,6 +25,13 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
                   int n, int heads, int rotary_v, cudaStream_t s, float drop_p = 0.f, unsigned long long drop_seed = 0);
 
+// attention_tc.cu: the same two operators on the tensor cores (tcgen05 + TMEM; 128 / 32 (batch, head) pairs per UMMA
+// tile); attention_fwd / attention_bwd dispatch to them unless SVSR_ATTN_TC=0.
+int attention_tc_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads, int rotary_v,
+                     cudaStream_t s, float drop_p, unsigned long long drop_seed);
+int attention_tc_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int n,
+                     int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed);
+
 // u[M,F] = dropout_p(h[:, :F] * gelu(h[:, F:])) ; dh from du. The dropout mask is a counter-based function of
 // (seed, element index): forward and backward regenerate the same mask, nothing is stored. p = 0 disables it.
 int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s);
