@@ -28,7 +28,8 @@ FLOPS_PER_CLIP = 62.61e9  # fwd 21.46 GF, fwd+bwd 62.61 
 B_PER_GPU = 64
 T, S = 29, 88
 WORKLOAD = ("LRW word-level ResNet18+Transformer-12L (x-transformers), fwd+bwd+allreduce+AdamW, "
-            f"[{B_PER_GPU},1,29,88,88] per GPU (BASELINE configs[1])")
+            f"[{B_PER_GPU},1,29,88,88] per GPU (BASELINE configs[1]); dropouts 0 = every sublayer runs every step "
+            "(the shipped layer_dropout .2 / ff_dropout .3 step is timed beside it: `shipped_dropouts`)")
 
 
 class _Attrs(dict):
@@ -41,12 +42,13 @@ def _attrs(d):
     return _Attrs({k: _attrs(v) if isinstance(v, dict) else v for k, v in d.items()})
 
 
-def lrw_config(depth=12):
+def lrw_config(depth=12, layer_dropout=0.0, ff_dropout=0.0):
     return _attrs({
         "data": {"use_word_boundary": False, "input_size": S},
         "model": {"resnet": "resnet18", "wav2vec": {"path": "./vq-wav2vec_kmeans.pt"},
                   "bert": {"type": "x-transformers", "num_tokens": 1, "dim": 512, "depth": depth, "heads": 8,
-                           "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": 0.0, "ff_dropout": 0.0,
+                           "emb_dropout": 0.0, "attn_dropout": 0.0, "layer_dropout": layer_dropout,
+                           "ff_dropout": ff_dropout,
                            "use_rmsnorm": True, "ff_glu": True, "rotary_pos_emb": True, "num_labels": 500}},
         "optim": {"optimizer": {"lr": 1e-4, "betas": [0.9, 0.999], "eps": 1e-6, "weight_decay": 0.01},
                   "scheduler": {"name": "cosine", "num_warmup_steps": 15000, "num_training_steps": 270000},
@@ -578,6 +580,30 @@ def run_native_arm(args):
     if world == 1 and not args.no_gpu_baseline:
         del pipe, step, opt, model
         torch.cuda.empty_cache()
+        # the reference's shipped training config (LRW/video/config/bert-12l-512d_...yaml:25-28): layer_dropout .2 drops
+        # ~20 % of the 24 sublayers per step (host RNG), ff_dropout .3 -- replayed from ONE CUDA graph through the
+        # device-resident step control (svsr_lrw_step_control)
+        try:
+            torch.manual_seed(1234)
+            m2 = TransformerLightningModule(lrw_config(layer_dropout=0.2, ff_dropout=0.3)).train()
+            st2 = DataParallelStep(m2, FusedAdamW.from_config(m2), graph=bool(args.graph), high_priority=bool(args.priority))
+            for i in range(max(args.warmup, 3)):
+                st2(*dev_batches[i % n_batches])
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(2 * args.steps):
+                st2(*dev_batches[i % n_batches])
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / (2 * args.steps)
+            line["shipped_dropouts"] = {"value": B * 1e3 / ms2, "unit": "clips/s", "ms_per_step": ms2,
+                                        "steps": 2 * args.steps, "graph_replays": st2.graph_replays,
+                                        "config": "layer_dropout 0.2, ff_dropout 0.3 (the reference's yaml); the mask and "
+                                                  "the dropout seed change every step, the captured graph does not"}
+            del st2, m2
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line["shipped_dropouts"] = {"error": repr(ex)}
         # the other BASELINE configs, measured in the same run on the same GPU (their own arms: --config c3 | c4 | c5)
         also = {}
         try:

@@ -241,6 +241,13 @@ int svsr_lrw_backward(void* handle, const float* grad_scale, void* stream);
  * lightning.py:168-171); this call materialises `logits_audio` (fp32 [B*T, A*G*V], svsr_lrw_tensor("logits_audio")) once
  * from the last forward's hidden states, for inspection / parity tests. */
 int svsr_lrw_logits_audio(void* handle, void* stream);
+/* Device-resident step control. The reference drops x-transformers sublayers with host RNG (layer_dropout,
+ * lightning.py:95-105) and seeds its dropouts per step; as kernel ARGUMENTS those make every step a different launch
+ * sequence. mode 1: {skip_mask, dropout_seed} are written to two control words in the workspace (on `stream`) and the
+ * engine launches every sublayer's kernels each step, predicated on its bit -- svsr_lrw_forward's skip_mask /
+ * dropout_seed arguments are ignored until mode 0 -- so ONE captured CUDA graph replays any step of the shipped
+ * layer_dropout .2 / ff_dropout .3 config (call this before each replay). mode 0: host-valued control again. */
+int svsr_lrw_step_control(void* handle, int mode, uint32_t skip_mask, uint64_t dropout_seed, void* stream);
 /* The same backward in two stages so that the data-parallel step can overlap communication with compute:
  * stage 0 = loss heads + encoder + mean-pool (completes the gradient arena range returned by
  * svsr_lrw_early_grad_region: cls_token, encoder and head weights, ~160 MB), stage 1 = ResNet trunk + stem. */
@@ -385,6 +392,10 @@ int svsr_lrs_encode(void* handle, const float* x, const int64_t* lengths, int tr
                     void* stream);
 /* (*grad_scale) * d loss / d params accumulated (+=) into the gradient arena; one backward per (train) forward. */
 int svsr_lrs_backward(void* handle, const float* grad_scale, void* stream);
+/* The same backward in three stages, called in order: 0 = loss heads + attention decoder, 1 = encoder.after_norm + the
+ * Conformer blocks, 2 = embed + visual frontend. When a stage returns, the gradients of ITS parameters are final on
+ * `stream`, so a data-parallel caller all-reduces them while the next stage computes (syncvsr_b200/train.py). */
+int svsr_lrs_backward_stage(void* handle, const float* grad_scale, int stage, void* stream);
 /* named tensors: encoder_out, embed_out, frontend, logits_audio, ctc_logits, pred, ys_in, ys_out, layer<i>.x<k>;
  * dtype 0=f32 1=bf16 2=u8 3=i32 4=i64 */
 int svsr_lrs_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);

@@ -127,10 +127,13 @@ struct AttnTcParams {
   int n, heads, pairs, rotary_v;
   float drop_p;
   unsigned long long drop_seed;
+  StepCtl ctl;
 };
 
 template <int BS>
 __global__ void __launch_bounds__(128, 1) attention_tc_fwd_kernel(const AttnTcParams p) {
+  if (ctl_skipped(p.ctl)) return;
+  const unsigned long long drop_seed = ctl_seed(p.ctl, p.drop_seed);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128, 1) attention_tc_fwd_kernel(const AttnTcPa
       const unsigned long long base = ((unsigned long long)pair * p.n + t) * p.n;
 #pragma unroll
       for (int j = 0; j < BS; ++j)
-        pr[j] = (j < p.n && dropout_keep(p.drop_seed, base + j, p.drop_p)) ? pr[j] * ks : 0.f;
+        pr[j] = (j < p.n && dropout_keep(drop_seed, base + j, p.drop_p)) ? pr[j] * ks : 0.f;
     }
     if (!valid) {
 #pragma unroll
@@ -238,6 +241,8 @@ __device__ __forceinline__ void unrot_store(float (&x)[64], bool rotate, const f
 
 template <int BS>
 __global__ void __launch_bounds__(128, 1) attention_tc_bwd_kernel(const AttnTcParams p) {
+  if (ctl_skipped(p.ctl)) return;
+  const unsigned long long drop_seed = ctl_seed(p.ctl, p.drop_seed);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(128, 1) attention_tc_bwd_kernel(const AttnTcPa
       const unsigned long long base = ((unsigned long long)pair * p.n + t) * p.n;
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
-        const float m = (j < p.n && dropout_keep(p.drop_seed, base + j, p.drop_p)) ? ks : 0.f;
+        const float m = (j < p.n && dropout_keep(drop_seed, base + j, p.drop_p)) ? ks : 0.f;
         dp[j] *= m;
         dot += pr[j] * dp[j];
         s[j] = pr[j] * m;  // p~
@@ -374,15 +379,16 @@ int launch_tc(const AttnTcParams& p, bool bwd, cudaStream_t s) {
 }  // namespace
 
 int attention_tc_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads, int rotary_v,
-                     cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+                     cudaStream_t s, float drop_p, unsigned long long drop_seed, const StepCtl* ctl) {
   SVSR_REQUIRE(n >= 1 && n <= 64, "attention: n=%d must be in [1,64]", n);
-  AttnTcParams p{qkv, rot, nullptr, o, nullptr, n, heads, B * heads, rotary_v, drop_p, drop_seed};
+  AttnTcParams p{qkv, rot, nullptr, o, nullptr, n, heads, B * heads, rotary_v, drop_p, drop_seed, ctl ? *ctl : StepCtl()};
   return n <= 32 ? launch_tc<32>(p, false, s) : launch_tc<64>(p, false, s);
 }
 int attention_tc_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int n,
-                     int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+                     int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed,
+                     const StepCtl* ctl) {
   SVSR_REQUIRE(n >= 1 && n <= 64, "attention: n=%d must be in [1,64]", n);
-  AttnTcParams p{qkv, rot, d_o, nullptr, dqkv, n, heads, B * heads, rotary_v, drop_p, drop_seed};
+  AttnTcParams p{qkv, rot, d_o, nullptr, dqkv, n, heads, B * heads, rotary_v, drop_p, drop_seed, ctl ? *ctl : StepCtl()};
   return n <= 32 ? launch_tc<32>(p, true, s) : launch_tc<64>(p, true, s);
 }
 

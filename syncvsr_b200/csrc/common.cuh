@@ -220,6 +220,25 @@ __host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, u
   return (float)((unsigned)(x >> 40)) * (1.0f / 16777216.0f) >= p;
 }
 
+// ------------------------------------ device-resident step control ----------------------------
+// What changes from step to step WITHOUT changing the launch sequence lives in device memory, so that one captured CUDA
+// graph serves every step of the shipped training config (layer_dropout .2, ff_dropout .3, LRW/video/config/*.yaml:25-28):
+//   skip : bit i set = x-transformers sublayer i is dropped this step (layer_dropout: host RNG, like the reference's
+//          Python random()); every kernel of that sublayer is launched and returns at once (bit = its sublayer's bit)
+//   seed : the step's dropout seed; a dropout site adds its own constant
+// A null `skip` / `seed` pointer means "not device controlled" (the host-valued arguments apply).
+struct StepCtl {
+  const unsigned* skip = nullptr;
+  unsigned bit = 0;
+  const unsigned long long* seed = nullptr;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ bool ctl_skipped(const StepCtl& c) { return c.skip && (__ldg(c.skip) & c.bit) != 0u; }
+__device__ __forceinline__ unsigned long long ctl_seed(const StepCtl& c, unsigned long long site) {
+  return c.seed ? __ldg(c.seed) + site : site;
+}
+#endif
+
 // ------------------------------------ small math helpers --------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

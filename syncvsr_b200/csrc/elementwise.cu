@@ -916,7 +916,8 @@ __global__ void unpack_linear_wgrad_kernel(const float* __restrict__ tmp, float*
   }
 }
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db, int M,
-                                   int N) {
+                                   int N, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
   // block handles 64 columns x a slab of rows; threads: 64 columns x 4 row lanes
   const int col = blockIdx.x * 64 + (threadIdx.x & 63);
   const int lane_r = threadIdx.x >> 6;
@@ -927,6 +928,17 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld,
   s[threadIdx.x] = acc;
   __syncthreads();
   if (lane_r == 0 && col < N) atomicAdd(db + col, s[threadIdx.x] + s[threadIdx.x + 64] + s[threadIdx.x + 128] + s[threadIdx.x + 192]);
+}
+// dst = src when the sublayer's bit is set in the device-resident skip mask (residual stream passes through a dropped
+// sublayer, lightning.py:95-105 layer_dropout), nothing otherwise
+__global__ void copy_if_skipped_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long n4,
+                                       const StepCtl ctl) {
+  if (!ctl_skipped(ctl)) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+__global__ void set_step_ctl_kernel(unsigned* skip, unsigned long long* seed, unsigned skip_mask, unsigned long long s) {
+  *skip = skip_mask, *seed = s;
 }
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1140,9 +1152,22 @@ int unpack_linear_wgrad(const float* tmp, float* grad, int N, int K, int Kp, int
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s) {
+int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s, const StepCtl* ctl) {
   dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64 < 1 ? 1 : (M + 63) / 64));
-  colsum_bf16_kernel<<<grid, 256, 0, s>>>(dy, ld, db, M, N);
+  colsum_bf16_kernel<<<grid, 256, 0, s>>>(dy, ld, db, M, N, ctl ? *ctl : StepCtl());
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int copy_if_skipped(float* dst, const float* src, long long n, const StepCtl& ctl, cudaStream_t s) {
+  SVSR_REQUIRE(n % 4 == 0, "copy_if_skipped: n must be a multiple of 4");
+  copy_if_skipped_kernel<<<grid_for(n / 4, 256 * 2), 256, 0, s>>>(reinterpret_cast<float4*>(dst),
+                                                                  reinterpret_cast<const float4*>(src), n / 4, ctl);
+  LAUNCH_CHECK();
+  return SVSR_OK;
+}
+int set_step_ctl(unsigned* skip, unsigned long long* seed, unsigned skip_mask, unsigned long long seed_value,
+                 cudaStream_t s) {
+  set_step_ctl_kernel<<<1, 1, 0, s>>>(skip, seed, skip_mask, seed_value);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

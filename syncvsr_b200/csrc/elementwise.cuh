@@ -85,7 +85,11 @@ struct PackJob {
 };
 int pack_all_weights(const PackJob* jobs_dev, int njobs, cudaStream_t s);
 // db[N] += column sums of dy[M, N] (bf16, pitch ld)
-int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s);
+int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s, const StepCtl* ctl = nullptr);
+// device-resident step control (common.cuh StepCtl): dst = src iff the sublayer's bit is set; write the control words
+int copy_if_skipped(float* dst, const float* src, long long n, const StepCtl& ctl, cudaStream_t s);
+int set_step_ctl(unsigned* skip, unsigned long long* seed, unsigned skip_mask, unsigned long long seed_value,
+                 cudaStream_t s);
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
 // last [B, T+1, D] fp32 -> cls rows [B, D] and frame rows [B*T, D], both bf16
 int split_cast_last(const float* last, __nv_bfloat16* cls, __nv_bfloat16* frames, int B, int T, int D, cudaStream_t s);

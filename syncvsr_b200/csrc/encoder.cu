@@ -37,7 +37,8 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 template <int MAXI>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, __nv_bfloat16* __restrict__ y,
-                   float* __restrict__ inv_out, int M, int D, float eps, int norm_dim) {
+                   float* __restrict__ inv_out, int M, int D, float eps, int norm_dim, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ni = D >> 5;
@@ -66,7 +67,13 @@ template <int MAXI>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
                    const float* __restrict__ inv_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb,
-                   float* __restrict__ dg, int M, int D, float eps, int norm_dim) {
+                   float* __restrict__ dg, int M, int D, float eps, int norm_dim, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) {  // dropped sublayer: the stream gradient passes through; only its bf16 copy moves on
+    const long long n = (long long)M * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      dxb[i] = __float2bfloat16(dx[i]);
+    return;
+  }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ni = D >> 5;
@@ -262,7 +269,9 @@ __device__ __forceinline__ void dropout_probs(float* sp, float* other, int n, un
 __global__ void __launch_bounds__(128)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
                      __nv_bfloat16* __restrict__ o, int n, int heads, int rotary_v, float drop_p,
-                     unsigned long long drop_seed) {
+                     unsigned long long drop_seed, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
+  drop_seed = ctl_seed(ctl, drop_seed);
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + n * AT_LD;
@@ -299,7 +308,9 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 __global__ void __launch_bounds__(256)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rot,
                      const __nv_bfloat16* __restrict__ d_o, __nv_bfloat16* __restrict__ dqkv, int n, int heads,
-                     int rotary_v, float drop_p, unsigned long long drop_seed) {
+                     int rotary_v, float drop_p, unsigned long long drop_seed, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
+  drop_seed = ctl_seed(ctl, drop_seed);
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + n * AT_LD;
@@ -377,7 +388,9 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 // u = dropout_p(value * gelu(gate))   (x-transformers FeedForward: GLU -> Dropout(ff_dropout) -> Linear)
 __global__ void __launch_bounds__(256)
 geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ u, long long M, int F, float p,
-                 unsigned long long seed) {
+                 unsigned long long seed, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
+  seed = ctl_seed(ctl, seed);
   const int fg = F >> 3;  // 8 hidden units (16 bytes) per thread
   const long long total = M * fg;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -398,7 +411,10 @@ geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict_
 }
 __global__ void __launch_bounds__(256)
 geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ du,
-                 __nv_bfloat16* __restrict__ dh, long long M, int F, float p, unsigned long long seed) {
+                 __nv_bfloat16* __restrict__ dh, long long M, int F, float p, unsigned long long seed,
+                 const StepCtl ctl) {
+  if (ctl_skipped(ctl)) return;
+  seed = ctl_seed(ctl, seed);
   const int fg = F >> 3;
   const long long total = M * fg;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -473,7 +489,8 @@ __global__ void bert_embed_bwd_kernel(const float* __restrict__ dE, float* __res
 // Dropout on an fp32 tensor in place (+ optional bf16 copy): forward of nn.Dropout after the embedding LayerNorm, and
 // (same call on the gradient) its backward
 __global__ void dropout_f32_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xb, long long n, float p,
-                                   unsigned long long seed) {
+                                   unsigned long long seed, const StepCtl ctl) {
+  seed = ctl_seed(ctl, seed);
   const float ks = 1.0f / (1.0f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = dropout_keep(seed, (unsigned long long)i, p) ? x[i] * ks : 0.f;
@@ -489,14 +506,14 @@ __global__ void dropout_f32_kernel(float* __restrict__ x, __nv_bfloat16* __restr
   SVSR_CHECK_CUDA(cudaGetLastError())
 
 int rmsnorm_fwd(const float* x, const float* g, __nv_bfloat16* y, float* inv, int M, int D, float eps, cudaStream_t s,
-                int norm_dim) {
+                int norm_dim, const StepCtl* ctl) {
   if (norm_dim <= 0) norm_dim = D;
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
   const int blocks = (M + 7) / 8 < 148 * 4 ? (M + 7) / 8 : 148 * 4;
   if (D <= 512)
-    rmsnorm_fwd_kernel<16><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim);
+    rmsnorm_fwd_kernel<16><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim, ctl ? *ctl : StepCtl());
   else
-    rmsnorm_fwd_kernel<32><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim);
+    rmsnorm_fwd_kernel<32><<<blocks, 256, 0, s>>>(x, g, y, inv, M, D, eps, norm_dim, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -508,7 +525,13 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
                        const float* __restrict__ inv_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb,
-                       float* __restrict__ dg, int M, int D, float eps, int norm_dim) {
+                       float* __restrict__ dg, int M, int D, float eps, int norm_dim, const StepCtl ctl) {
+  if (ctl_skipped(ctl)) {  // dropped sublayer: the stream gradient passes through; only its bf16 copy moves on
+    const long long n = (long long)M * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      dxb[i] = __float2bfloat16(dx[i]);
+    return;
+  }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   float4 gv[NCH], dgacc[NCH];
@@ -569,7 +592,8 @@ rmsnorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const float* __rest
 }
 
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const float* inv, float* dx,
-                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim) {
+                __nv_bfloat16* dx_bf16, float* dg, int M, int D, float eps, cudaStream_t s, int norm_dim,
+                const StepCtl* ctl) {
   if (norm_dim <= 0) norm_dim = D;
   SVSR_REQUIRE(D % 32 == 0 && D <= 1024, "rmsnorm: D=%d unsupported", D);
   // one row per warp: the kernel is latency bound (ncu: 12 % warps active, every pipe < 5 %), so more resident warps
@@ -578,11 +602,11 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* g, const f
   const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx_bf16)) & 7) == 0 &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
   if (D == 512 && al16)
-    rmsnorm_bwd_vec_kernel<4><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
+    rmsnorm_bwd_vec_kernel<4><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim, ctl ? *ctl : StepCtl());
   else if (D <= 512)
-    rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
+    rmsnorm_bwd_kernel<16><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim, ctl ? *ctl : StepCtl());
   else
-    rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim);
+    rmsnorm_bwd_kernel<32><<<blocks, 256, 0, s>>>(dy, x, g, inv, dx, dx_bf16, dg, M, D, eps, norm_dim, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -597,9 +621,9 @@ static bool attn_use_tc() {
   return !(e && e[0] == '0');
 }
 int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, int B, int n, int heads,
-                  int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+                  int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed, const StepCtl* ctl) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
-  if (attn_use_tc()) return attention_tc_fwd(qkv, rot, o, B, n, heads, rotary_v, s, drop_p, drop_seed);
+  if (attn_use_tc()) return attention_tc_fwd(qkv, rot, o, B, n, heads, rotary_v, s, drop_p, drop_seed, ctl);
   const int smem = 4 * n * AT_LD * sizeof(float);
   const int smem_max = 4 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;
@@ -607,14 +631,16 @@ int attention_fwd(const __nv_bfloat16* qkv, const float* rot, __nv_bfloat16* o, 
     SVSR_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     done = true;
   }
-  attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v, drop_p, drop_seed);
+  attention_fwd_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v, drop_p, drop_seed,
+                                                    ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B,
-                  int n, int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed) {
+                  int n, int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed,
+                  const StepCtl* ctl) {
   SVSR_REQUIRE(n >= 1 && n <= AT_MAXN, "attention: n=%d must be in [1,%d]", n, AT_MAXN);
-  if (attn_use_tc()) return attention_tc_bwd(qkv, rot, d_o, dqkv, B, n, heads, rotary_v, s, drop_p, drop_seed);
+  if (attn_use_tc()) return attention_tc_bwd(qkv, rot, d_o, dqkv, B, n, heads, rotary_v, s, drop_p, drop_seed, ctl);
   const int smem = 6 * n * AT_LD * sizeof(float);
   const int smem_max = 6 * AT_MAXN * AT_LD * sizeof(float);
   static bool done = false;
@@ -623,24 +649,26 @@ int attention_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bfloat1
     done = true;
   }
   // 256 threads: S and dP (2 x 120 register tiles at n = 30) in one round, the three gradient products (360) in two
-  attention_bwd_kernel<<<B * heads, 256, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v, drop_p, drop_seed);
+  attention_bwd_kernel<<<B * heads, 256, smem, s>>>(qkv, rot, d_o, dqkv, n, heads, rotary_v, drop_p, drop_seed,
+                                                    ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s) {
+int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s,
+              const StepCtl* ctl) {
   SVSR_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
   const long long total = (long long)M * (F / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F, p, seed);
+  geglu_fwd_kernel<<<blocks, 256, 0, s>>>(h, u, M, F, p, seed, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int geglu_bwd(const __nv_bfloat16* h, const __nv_bfloat16* du, __nv_bfloat16* dh, int M, int F, float p,
-              unsigned long long seed, cudaStream_t s) {
+              unsigned long long seed, cudaStream_t s, const StepCtl* ctl) {
   SVSR_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
   const long long total = (long long)M * (F / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F, p, seed);
+  geglu_bwd_kernel<<<blocks, 256, 0, s>>>(h, du, dh, M, F, p, seed, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -671,9 +699,10 @@ int bert_embed_bwd(const float* dE, float* dpos, float* dtt, int B, int L, int D
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-int dropout_f32_inplace(float* x, __nv_bfloat16* xb, long long n, float p, unsigned long long seed, cudaStream_t s) {
+int dropout_f32_inplace(float* x, __nv_bfloat16* xb, long long n, float p, unsigned long long seed, cudaStream_t s,
+                        const StepCtl* ctl) {
   SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
-  dropout_f32_kernel<<<(unsigned)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8), 256, 0, s>>>(x, xb, n, p, seed);
+  dropout_f32_kernel<<<(unsigned)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8), 256, 0, s>>>(x, xb, n, p, seed, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
 }

@@ -55,6 +55,19 @@ struct LrwEngine : EngineBase {
   size_t xs /* (2*depth+1) stream buffers */, lastb_cls, lastb_frames, logits_a, dlogits_a, logits_c, dlogits_c, acc,
       bad_token, rot;
   size_t ce_part, ce_xt, ce_lse, ce_tok;  // fused audio head: per-slot (max, sum) partials, target logits, lse, token copy
+  // Device-resident step control (common.cuh StepCtl): {uint32 skip mask | uint64 dropout seed} in the workspace. With
+  // dev_ctl on, EVERY sublayer's kernels are launched each step and return at once when their bit is set, and dropout
+  // sites read the seed from device memory: the launch sequence no longer depends on host RNG, so the shipped
+  // layer_dropout / ff_dropout config replays from one CUDA graph (svsr_lrw_step_control).
+  size_t ctl = 0;
+  bool dev_ctl = false;
+  StepCtl sctl(int sublayer) const {  // predicate + seed of one x-transformers sublayer (-1: seed only)
+    StepCtl c;
+    if (!dev_ctl) return c;
+    c.seed = ws<unsigned long long>(ctl + 8);
+    if (sublayer >= 0) c.skip = ws<unsigned>(ctl), c.bit = 1u << sublayer;
+    return c;
+  }
   size_t pack_jobs;  // device table for the single-launch weight repack
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
@@ -222,6 +235,7 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   e.ce_xt = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 4);
   e.ce_lse = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 4);
   e.ce_tok = b.take((size_t)e.N * c.audio_alignment * c.vq_groups * 8);
+  e.ctl = b.take(16);
   // ---- backward scratch ----
   e.dx = b.take((size_t)e.M * Dp * 4);
   for (int i = 0; i < 3; ++i) e.dxb[i] = b.take((size_t)e.M * Dp * 2);
@@ -319,8 +333,9 @@ static int engine_pack_deferred(LrwEngine& e, cudaStream_t s, bool may_overlap) 
 
 // Linear forward / input gradient / weight gradient on the (possibly K- or N-padded) bf16 operand copies
 static int lw_fwd(const LrwEngine& e, const bf16* x, int ldx, int M, const LinRef& l, void* out, int ldc, int out_fp32,
-                  const void* resid, cudaStream_t s) {
+                  const void* resid, cudaStream_t s, const StepCtl& ctl = StepCtl()) {
   IgemmProblem p;
+  p.ctl = ctl;
   p.a = x, p.a_N = M, p.a_C = ldx, p.cin = l.Kp, p.ntaps = 1;
   p.o_N = M;
   p.b = e.ws<bf16>(l.wb), p.b_rows = l.Np, p.b_cols = l.Kp;
@@ -330,8 +345,9 @@ static int lw_fwd(const LrwEngine& e, const bf16* x, int ldx, int M, const LinRe
   return igemm_launch(p, s);
 }
 static int lw_dgrad(const LrwEngine& e, const bf16* dy, int ldy, int M, const LinRef& l, void* out, int ldc,
-                    cudaStream_t s) {
+                    cudaStream_t s, const StepCtl& ctl = StepCtl()) {
   IgemmProblem p;
+  p.ctl = ctl;
   p.a = dy, p.a_N = M, p.a_C = ldy, p.cin = l.ldt, p.ntaps = 1;
   p.o_N = M;
   p.b = e.ws<bf16>(l.wt), p.b_rows = l.K, p.b_cols = l.ldt;
@@ -339,15 +355,16 @@ static int lw_dgrad(const LrwEngine& e, const bf16* dy, int ldy, int M, const Li
   return igemm_launch(p, s);
 }
 static int lw_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, int ldx, int M, const LinRef& l,
-                    cudaStream_t s) {
+                    cudaStream_t s, const StepCtl& ctl = StepCtl()) {
   WgradProblem p;
+  p.ctl = ctl;
   p.a = dy, p.a_N = M, p.a_C = ldy, p.a_cin = l.ldt, p.ntaps = 1;
   p.b = x, p.b_C = ldx, p.n_cols = l.Kp;
   p.k_N = M;
   if (l.Kp == l.K && !l.glu) {  // rows of the arena matrix are 16-byte aligned: accumulate in place
     p.out = e.G + l.w, p.ldo = l.K, p.m_valid = l.N;
     RC(wgrad_launch(p, s));
-    if (l.b >= 0) RC(colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s));
+    if (l.b >= 0) RC(colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s, &ctl));
     return SVSR_OK;
   }
   // word-boundary widths (K = 513 / 2052): gradient into a zero-padded scratch, then added into the arena layout
@@ -357,10 +374,10 @@ static int lw_wgrad(const LrwEngine& e, const bf16* dy, int ldy, const bf16* x, 
   RC(wgrad_launch(p, s));
   RC(unpack_linear_wgrad(tmp, e.G + l.w, l.N, l.K, l.Kp, l.glu, s));
   if (l.b >= 0) {
-    if (!l.glu) return colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s);
+    if (!l.glu) return colsum_bf16(dy, ldy, e.G + l.b, M, l.N, s, &ctl);
     float* bt = e.ws<float>(e.bias_tmp);
     SVSR_CHECK_CUDA(cudaMemsetAsync(bt, 0, (size_t)l.Np * 4, s));
-    RC(colsum_bf16(dy, ldy, bt, M, l.Np, s));
+    RC(colsum_bf16(dy, ldy, bt, M, l.Np, s, &ctl));
     RC(unpack_linear_wgrad(bt, e.G + l.b, l.N, 1, 1, 1, s));
   }
   return SVSR_OK;
@@ -515,8 +532,12 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
   }
 
   // emb_dropout_bert on cat(cls_tokens, inputs_embeds) (lightning.py:150)
-  if (train && c.emb_dropout > 0.f)
-    RC(dropout_f32_inplace(e.xs_buf(0), nullptr, (long long)e.M * Dp, c.emb_dropout, dropout_seed + 0x3000ULL, s));
+  const bool dc = e.dev_ctl && c.enc_type == 0;
+  const unsigned long long seed0 = dc ? 0ULL : dropout_seed;  // device control: the kernels add *seed to the site constant
+  if (train && c.emb_dropout > 0.f) {
+    const StepCtl cs = e.sctl(-1);
+    RC(dropout_f32_inplace(e.xs_buf(0), nullptr, (long long)e.M * Dp, c.emb_dropout, seed0 + 0x3000ULL, s, &cs));
+  }
   // ---- encoder (lightning.py:152-158) ----
   e.last_seed = dropout_seed;
   if (c.enc_type == 1) RC(bert_forward(e, train, s));
@@ -527,23 +548,26 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
     float* xo = e.xs_buf(2 * i + 2);
     const float* g_a = e.padded ? e.ws<float>(L.g_a_pad) : e.P + L.g_a;
     const float* g_f = e.padded ? e.ws<float>(L.g_f_pad) : e.P + L.g_f;
-    if (skip_mask & (1u << (2 * i))) {
+    const StepCtl ca = e.sctl(2 * i), cf = e.sctl(2 * i + 1);
+    if (!dc && (skip_mask & (1u << (2 * i)))) {
       SVSR_CHECK_CUDA(cudaMemcpyAsync(xf, xa, (size_t)e.M * Dp * 4, cudaMemcpyDeviceToDevice, s));
     } else {
-      RC(rmsnorm_fwd(xa, g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, Dp, 1e-8f, s, D));
-      RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s));
+      RC(rmsnorm_fwd(xa, g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, Dp, 1e-8f, s, D, &ca));
+      RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s, ca));
       RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
-                       s, train ? c.attn_dropout : 0.f, dropout_seed + 0x2000ULL * (unsigned long long)(i + 1)));
-      RC(lw_fwd(e, e.ws<bf16>(L.obuf), inner, e.M, L.out, xf, Dp, 1, xa, s));
+                       s, train ? c.attn_dropout : 0.f, seed0 + 0x2000ULL * (unsigned long long)(i + 1), &ca));
+      RC(lw_fwd(e, e.ws<bf16>(L.obuf), inner, e.M, L.out, xf, Dp, 1, xa, s, ca));
+      if (dc) RC(copy_if_skipped(xf, xa, (long long)e.M * Dp, ca, s));
     }
-    if (skip_mask & (1u << (2 * i + 1))) {
+    if (!dc && (skip_mask & (1u << (2 * i + 1)))) {
       SVSR_CHECK_CUDA(cudaMemcpyAsync(xo, xf, (size_t)e.M * Dp * 4, cudaMemcpyDeviceToDevice, s));
     } else {
-      RC(rmsnorm_fwd(xf, g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, Dp, 1e-8f, s, D));
-      RC(lw_fwd(e, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * Fp, 0, nullptr, s));
+      RC(rmsnorm_fwd(xf, g_f, e.ws<bf16>(L.xn_f), e.ws<float>(L.inv_f), e.M, Dp, 1e-8f, s, D, &cf));
+      RC(lw_fwd(e, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, e.ws<bf16>(L.hbuf), 2 * Fp, 0, nullptr, s, cf));
       RC(geglu_fwd(e.ws<bf16>(L.hbuf), e.ws<bf16>(L.ubuf), e.M, Fp, train ? c.ff_dropout : 0.f,
-                   dropout_seed + 0x1000ULL * (unsigned long long)i, s));
-      RC(lw_fwd(e, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, xo, Dp, 1, xf, s));
+                   seed0 + 0x1000ULL * (unsigned long long)i, s, &cf));
+      RC(lw_fwd(e, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, xo, Dp, 1, xf, s, cf));
+      if (dc) RC(copy_if_skipped(xo, xf, (long long)e.M * Dp, cf, s));
     }
   }
   const float* last = e.last_hidden();
@@ -777,39 +801,43 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     const float* g_f = e.padded ? e.ws<float>(L.g_f_pad) : e.P + L.g_f;
     float* dg_a = e.padded ? e.ws<float>(e.dg_pad) + (size_t)(2 * i) * Dp : e.G + L.g_a;
     float* dg_f = e.padded ? e.ws<float>(e.dg_pad) + (size_t)(2 * i + 1) * Dp : e.G + L.g_f;
-    if (!(e.last_skip & (1u << (2 * i + 1)))) {
+    const bool dc = e.dev_ctl;
+    const unsigned long long seed0 = dc ? 0ULL : e.last_seed;
+    const StepCtl ca = e.sctl(2 * i), cf = e.sctl(2 * i + 1);
+    if (dc || !(e.last_skip & (1u << (2 * i + 1)))) {
       bf16* dxb = e.ws<bf16>(e.dxb[xb]);
       bf16* dxb_next = e.ws<bf16>(e.dxb[(xb + 1) % 3]);  // 3-deep: unit k-1's side work may still read its copy
       bf16* du = e.ws<bf16>(e.t_du);
       bf16* dh = e.ws<bf16>(e.t_dh[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
       RC(sq.fork());  // dxb complete
-      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, w));
-      RC(lw_dgrad(e, dxb, Dp, e.M, L.ff2, du, Fp, s));
+      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.ubuf), Fp, e.M, L.ff2, w, cf));
+      RC(lw_dgrad(e, dxb, Dp, e.M, L.ff2, du, Fp, s, cf));
       RC(geglu_bwd(e.ws<bf16>(L.hbuf), du, dh, e.M, Fp, e.last_train ? c.ff_dropout : 0.f,
-                   e.last_seed + 0x1000ULL * (unsigned long long)i, s));
+                   seed0 + 0x1000ULL * (unsigned long long)i, s, &cf));
       RC(sq.fork());  // dh complete
-      RC(lw_wgrad(e, dh, 2 * Fp, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, w));
-      RC(lw_dgrad(e, dh, 2 * Fp, e.M, L.ff1, dyn, Dp, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), g_f, e.ws<float>(L.inv_f), dx, dxb_next, dg_f, e.M, Dp, 1e-8f, s, D));
+      RC(lw_wgrad(e, dh, 2 * Fp, e.ws<bf16>(L.xn_f), Dp, e.M, L.ff1, w, cf));
+      RC(lw_dgrad(e, dh, 2 * Fp, e.M, L.ff1, dyn, Dp, s, cf));
+      // (a dropped sublayer only hands the stream gradient's bf16 copy on: rmsnorm_bwd under `cf`)
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i + 1), g_f, e.ws<float>(L.inv_f), dx, dxb_next, dg_f, e.M, Dp, 1e-8f, s, D, &cf));
       xb = (xb + 1) % 3;
       RC(sq.end_unit());
     }
-    if (!(e.last_skip & (1u << (2 * i)))) {
+    if (dc || !(e.last_skip & (1u << (2 * i)))) {
       bf16* dxb = e.ws<bf16>(e.dxb[xb]);
       bf16* dxb_next = e.ws<bf16>(e.dxb[(xb + 1) % 3]);  // 3-deep: unit k-1's side work may still read its copy
       bf16* d_o = e.ws<bf16>(e.t_do);
       bf16* dqkv = e.ws<bf16>(e.t_dqkv[i & 1]);
       bf16* dyn = e.ws<bf16>(e.t_dyn);
       RC(sq.fork());
-      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.obuf), inner, e.M, L.out, w));
-      RC(lw_dgrad(e, dxb, Dp, e.M, L.out, d_o, inner, s));
+      RC(lw_wgrad(e, dxb, Dp, e.ws<bf16>(L.obuf), inner, e.M, L.out, w, ca));
+      RC(lw_dgrad(e, dxb, Dp, e.M, L.out, d_o, inner, s, ca));
       RC(attention_bwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), d_o, dqkv, c.B, c.T + 1, c.heads, c.rotary_v, s,
-                       e.last_train ? c.attn_dropout : 0.f, e.last_seed + 0x2000ULL * (unsigned long long)(i + 1)));
+                       e.last_train ? c.attn_dropout : 0.f, seed0 + 0x2000ULL * (unsigned long long)(i + 1), &ca));
       RC(sq.fork());
-      RC(lw_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, w));
-      RC(lw_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, Dp, s));
-      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), g_a, e.ws<float>(L.inv_a), dx, dxb_next, dg_a, e.M, Dp, 1e-8f, s, D));
+      RC(lw_wgrad(e, dqkv, 3 * inner, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, w, ca));
+      RC(lw_dgrad(e, dqkv, 3 * inner, e.M, L.qkv, dyn, Dp, s, ca));
+      RC(rmsnorm_bwd(dyn, e.xs_buf(2 * i), g_a, e.ws<float>(L.inv_a), dx, dxb_next, dg_a, e.M, Dp, 1e-8f, s, D, &ca));
       xb = (xb + 1) % 3;
       RC(sq.end_unit());
     }
@@ -821,8 +849,11 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
     }
 
   // ---- emb_dropout, mean pool / CLS ----
-  if (e.last_train && c.emb_dropout > 0.f)
-    RC(dropout_f32_inplace(dx, nullptr, (long long)e.M * Dp, c.emb_dropout, e.last_seed + 0x3000ULL, s));
+  if (e.last_train && c.emb_dropout > 0.f) {
+    const StepCtl cs = e.sctl(-1);
+    RC(dropout_f32_inplace(dx, nullptr, (long long)e.M * Dp, c.emb_dropout, (e.dev_ctl ? 0ULL : e.last_seed) + 0x3000ULL, s,
+                           &cs));
+  }
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_cls_bwd(dx, T0, e.G + e.cls_off, c.B, c.T, HW4, 512, s, Dp));
   if (e.padded) RC(wb_column_bwd(dx, e.G + e.cls_off, c.B, c.T, Dp, 512, s));
@@ -884,6 +915,7 @@ int svsr_lrw_bind(void* h, float* params, float* grads, float* buffers, void* wo
                "lrw_bind: workspace must be 1024-byte aligned, arenas 16-byte aligned");
   e->pack_table_ready = false;
   e->pack_deferred = false, e->pack_pending = false;
+  e->dev_ctl = false;
   return engine_base_bind(*e, params, grads, buffers, workspace);
 }
 int svsr_lrw_pack_weights(void* h, void* stream) {
@@ -948,6 +980,19 @@ int svsr_lrw_logits_audio(void* h, void* stream) {
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
   return lw_fwd(*e, e->ws<bf16>(e->lastb_frames), e->Dp, e->N, e->aud, e->ws<float>(e->logits_a), AGV, 1, nullptr,
                 static_cast<cudaStream_t>(stream));
+}
+// Device-resident step control (StepCtl): mode 1 writes {skip_mask, dropout_seed} to the engine's control words on
+// `stream` and switches the engine to predicated launches (every sublayer's kernels are enqueued each step; a dropped
+// sublayer's return at once) -- the forward's skip_mask / dropout_seed ARGUMENTS are then ignored, so a captured CUDA
+// graph replays any step of the layer_dropout / ff_dropout config. mode 0 returns to host-valued control.
+int svsr_lrw_step_control(void* h, int mode, uint32_t skip_mask, uint64_t dropout_seed, void* stream) {
+  LrwEngine* e = static_cast<LrwEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrw: bind() first");
+  SVSR_REQUIRE(mode == 0 || e->cfg.enc_type == 0, "lrw_step_control: the HuggingFace encoder variant is host controlled");
+  e->dev_ctl = mode != 0;
+  if (!e->dev_ctl) return SVSR_OK;
+  return set_step_ctl(e->ws<unsigned>(e->ctl), e->ws<unsigned long long>(e->ctl + 8), skip_mask,
+                      (unsigned long long)dropout_seed, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_early_grad_region(void* h, int64_t* begin, int64_t* end) {
   LrwEngine* e = static_cast<LrwEngine*>(h);

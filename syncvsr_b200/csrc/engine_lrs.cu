@@ -57,6 +57,7 @@ struct LrsEngine : EngineBase {
   int n_pack_jobs = 0;
   bool pack_table_ready = false;
   int last_L = 0, last_Llab = 0, last_train = 0, last_audio = 0;
+  int bwd_stage = 0;
   unsigned long long last_seed = 0;
   float pd = 0.f, pa = 0.f;  // dropout probabilities in effect for the last forward (0 in eval mode)
   // per-site seeds: every Dropout module instance of the reference draws an independent mask
@@ -578,10 +579,19 @@ static int ffn_bwd(LrsEngine& e, SideQueue& sq, const LrsScratch& t, const bf16*
   return sq.end_unit();
 }
 
-static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
-  SVSR_REQUIRE(e.fwd_done, "lrs backward called before (or twice after) forward");
-  SVSR_REQUIRE(e.last_train, "lrs backward needs a train-mode forward (batch-statistics BatchNorm backward)");
-  e.fwd_done = false;
+// stage < 0: the whole backward. Staged (data parallel: the gradient all-reduce of a finished group overlaps the next
+// stage): 0 = loss heads + attention decoder, 1 = encoder.after_norm + the Conformer blocks, 2 = embed + visual frontend.
+// Every stage joins the weight-gradient stream before it returns, so its parameters' gradients are final.
+static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaStream_t s) {
+  if (stage <= 0) {
+    SVSR_REQUIRE(e.fwd_done, "lrs backward called before (or twice after) forward");
+    SVSR_REQUIRE(e.last_train, "lrs backward needs a train-mode forward (batch-statistics BatchNorm backward)");
+    e.fwd_done = false;
+    e.bwd_stage = 0;
+  } else {
+    SVSR_REQUIRE(e.bwd_stage == stage - 1, "lrs backward stage %d called out of order (last finished: %d)", stage, e.bwd_stage);
+  }
+  if (stage >= 0) e.bwd_stage = stage;
   const svsr_lrs_config& c = e.cfg;
   const int D = c.adim, F = c.eunits, Fd = c.dunits, H = c.aheads, T = c.T, M = e.M;
   const int L = e.last_L, Md = c.B * L;
@@ -590,6 +600,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
   const float pd = e.pd, pa = e.pa;
   SideQueue sq(e, s);
   cudaStream_t w = e.wq;
+  if (stage <= 0) {
   if (e.last_audio && e.fused_head()) RC(lrs_audio_head_gemm(e, 2, grad_scale, s));
   if (grad_scale) {
     if (e.last_audio && !e.fused_head())
@@ -693,7 +704,10 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
     }
     RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s, pd, e.site(4)));
   }
+  if (stage == 0) return sq.join();
+  }  // stage <= 0
 
+  if (stage < 0 || stage == 1) {
   // ---- encoder.after_norm, then the Conformer blocks in reverse ----
   RC(ln_bwd(e, nullptr, dx, e.xs_buf(5 * c.elayers), e.after, dx, 0, M, s));
   for (int i = c.elayers - 1; i >= 0; --i) {
@@ -765,6 +779,9 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, cudaStream_t s) {
       RC(ffn_bwd(e, sq, t, t.dxb, M, Lc.mac1, Lc.mac2, e.ws<bf16>(Lc.h_mac), e.ws<bf16>(Lc.yn[0]), x0, Lc.n_mac, dx, F, s));
     }
   }
+  if (stage == 1) return sq.join();
+  }  // stage 1
+
   // ---- unit: embed (x * sqrt(D)) -> average pool; then the frontend ----
   {
     const LrsScratch t = lrs_scratch(e, sq.unit);
@@ -857,7 +874,13 @@ int svsr_lrs_encode(void* h, const float* x, const int64_t* lengths, int train, 
 int svsr_lrs_backward(void* h, const float* grad_scale, void* stream) {
   LrsEngine* e = static_cast<LrsEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrs: bind() first");
-  return lrs_backward(*e, grad_scale, static_cast<cudaStream_t>(stream));
+  return lrs_backward(*e, grad_scale, -1, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrs_backward_stage(void* h, const float* grad_scale, int stage, void* stream) {
+  LrsEngine* e = static_cast<LrsEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrs: bind() first");
+  SVSR_REQUIRE(stage >= 0 && stage <= 2, "lrs_backward_stage: stage must be 0, 1 or 2");
+  return lrs_backward(*e, grad_scale, stage, static_cast<cudaStream_t>(stream));
 }
 // The step never writes the audio logits to HBM (fused head); materialise them once, on request (svsr_lrs_tensor
 // "logits_audio"), from the last forward's encoder output.

@@ -39,6 +39,7 @@ struct IgemmKParams {
   int tma_store;  // bf16 output goes smem-staged through a TMA tensor store (full-line writes, hardware clipping)
   IgemmCe ce;     // fused cross-entropy epilogue (mode 0 = off)
   IgemmBnBwd bnb;  // fused BatchNorm-backward statistics (n = 0: off)
+  StepCtl ctl;
 };
 
 // A pipeline stage holds KPS consecutive 64-wide k-blocks (A sub-tile + B sub-tile each): one mbarrier round trip
@@ -87,6 +88,7 @@ template <int BN, int STAGES, int KPS, bool BNB>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmKParams p) {
+  if (ctl_skipped(p.ctl)) return;  // sublayer dropped this step (device-resident layer_dropout mask)
   // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
   // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
   using L = IgemmSmem<BN, STAGES, KPS>;
@@ -713,6 +715,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   CUtensorMap tmC = tmA;
   kp.tma_store = (!p.out_fp32 && p.b_rows % 64 == 0 && p.ce.mode != 1) ? 1 : 0;
   kp.ce = p.ce;
+  kp.ctl = p.ctl;
   kp.bnb = p.bnb;
   if (p.bnb.n) {
     SVSR_REQUIRE(p.bnb.n == 1 || p.bnb.n == 2, "igemm: bnb.n = %d", p.bnb.n);

@@ -94,6 +94,7 @@ struct IgemmProblem {
   double algo_flops = 0;  // algorithmic FLOPs of this launch for the profiler (0 = 2*pixels*N*taps*cin)
   IgemmCe ce;             // fused cross-entropy epilogue (dense GEMMs only)
   IgemmBnBwd bnb;         // fused BatchNorm-backward statistics (bf16 outputs with a multiple of 64 channels)
+  StepCtl ctl;            // device-resident skip predicate (common.cuh): the launch returns at once when its bit is set
 };
 
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);

@@ -20,6 +20,7 @@ struct WgradKParams {
   int ldo;
   int m_valid;
   int vec_ok;  // output rows 16-byte aligned: red.global.add.v4.f32 usable
+  StepCtl ctl;
 };
 
 template <int BN, int STAGES>
@@ -35,6 +36,7 @@ struct WgradSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradKParams p) {
+  if (ctl_skipped(p.ctl)) return;
   using L = WgradSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,6 +223,7 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
   kp.out = p.out, kp.ldo = p.ldo;
   kp.m_valid = p.m_valid > 0 ? p.m_valid : p.ntaps * p.a_cin;
   kp.vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  kp.ctl = p.ctl;
 
   const int BN = p.n_cols <= 64 ? 64 : (p.n_cols <= 128 ? 128 : 256);
   const int num_mblocks = (kp.ngroups + 1) / 2;

@@ -27,6 +27,7 @@ struct WgradProblem {
   int ldo = 0;
   int m_valid = 0;  // rows of D actually written (0 = all ntaps * a_cin)
   double algo_flops = 0;  // algorithmic FLOPs for the profiler (0 = 2*pixels*ntaps*a_cin*n_cols)
+  StepCtl ctl;            // device-resident skip predicate (generic kernel only)
 };
 
 int wgrad_launch(const WgradProblem& p, cudaStream_t stream);

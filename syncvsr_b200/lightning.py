@@ -149,6 +149,11 @@ class TransformerLightningModule(nn.Module):
         self._metrics = torch.zeros(8, device=self.device_, dtype=torch.float32)
         self._anchor = torch.zeros((), device=self.device_, requires_grad=True)
         self._last_skip = 0  # layer_dropout mask of the last forward (bit i = sublayer i dropped); read by FusedAdamW
+        # device_control: the step's layer_dropout mask / dropout seed live in device memory and every sublayer is
+        # launched predicated on them (svsr_lrw_step_control) -- what lets train.DataParallelStep replay ONE CUDA graph
+        # under the shipped layer_dropout / ff_dropout config. Off: they are kernel arguments (host-side skipping).
+        self.device_control = False
+        self._ctl_preset = None
         # Gradient synchronisation: gradients are written straight into the flat arena (no autograd graph through the
         # parameters), so torch DDP's reducer never sees them. Under torchrun (process group initialised) the native
         # backward all-reduces the arena itself (SUM / world = DDP's mean); DataParallelStep does its own staged
@@ -390,18 +395,19 @@ class TransformerLightningModule(nn.Module):
             hard = labels.long().contiguous()
         else:  # CutMix soft labels [B, num_labels] (augment.py; lightning.py:163-165,177-179)
             soft = labels.float().contiguous()
-        skip = 0
-        if self.training and self.layer_dropout > 0.0:  # host RNG per sublayer, like x-transformers' layer_dropout
-            for i in range(2 * self.depth):  # (the engine refuses depth > 16, so 32 bits hold every sublayer)
-                if random.random() < self.layer_dropout:
-                    skip |= 1 << i
+        if self._ctl_preset is not None:  # train.DataParallelStep already wrote this step's control words (graph mode)
+            skip, seed = self._ctl_preset
+        else:
+            skip, seed = self._draw_step_control()
+            if self.device_control:
+                self._apply_step_control(skip, seed)
         self._last_skip = skip
         check(lib().svsr_lrw_forward(
             self._h, C.c_void_p(videos.data_ptr()), C.c_void_p(audio_tokens.data_ptr()),
             C.c_int64(audio_tokens.stride(0)), C.c_void_p(hard.data_ptr() if hard is not None else 0),
             C.c_void_p(soft.data_ptr() if soft is not None else 0), C.c_void_p(wm.data_ptr() if wm is not None else 0),
             C.c_int(int(self.training)), C.c_uint32(skip),
-            C.c_uint64(self._step_seed()),
+            C.c_uint64(seed),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrw_forward")
         self._precise_logits = False
         if self.training:
@@ -412,6 +418,23 @@ class TransformerLightningModule(nn.Module):
             m = self._metrics.clone()
         return {"loss_total": m[0], "loss_category": m[1], "loss_audio": m[2], "accuracy_top1": m[3],
                 "accuracy_top5": m[4]}
+
+    def _draw_step_control(self):
+        """This step's layer_dropout mask (bit i = sublayer i dropped; host RNG per sublayer, like x-transformers'
+        `random() < layer_dropout`) and dropout seed. Eval mode: (0, 0)."""
+        skip = 0
+        if self.training and self.layer_dropout > 0.0:
+            for i in range(2 * self.depth):  # (the engine refuses depth > 16, so 32 bits hold every sublayer)
+                if random.random() < self.layer_dropout:
+                    skip |= 1 << i
+        return skip, self._step_seed()
+
+    def _apply_step_control(self, skip: int, seed: int) -> None:
+        """Device-resident control (svsr_lrw_step_control): the mask and the seed go to two control words in the
+        workspace on the current stream; the engine then launches every sublayer predicated on them."""
+        check(lib().svsr_lrw_step_control(self._h, C.c_int(1), C.c_uint32(skip), C.c_uint64(seed), self._stream()),
+              "svsr_lrw_step_control")
+        self._last_skip = skip
 
     def _step_seed(self) -> int:
         """Seed of this step's dropout masks (training mode only); `self.dropout_seed` pins it for reproducible tests."""

@@ -168,31 +168,43 @@ class DataParallelStep:
         return [dist.all_reduce(g[:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True),
                 dist.all_reduce(g[b:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
 
+    def _stochastic(self) -> bool:
+        m = self.module
+        return m.layer_dropout > 0.0 or m.ff_dropout > 0.0 or m.emb_dropout > 0.0 or m.attn_dropout > 0.0
+
     def _replayable(self) -> bool:
         m = self.module
-        return (self.graph and m.training and not m.hf and m.layer_dropout == 0.0 and m.ff_dropout == 0.0
-                and m.emb_dropout == 0.0 and m.attn_dropout == 0.0 and m._shape_key is not None)
+        return self.graph and m.training and not m.hf and m._shape_key is not None
 
-    def _capture(self, batch) -> dict:
+    def _capture(self, batch, ctl=None) -> dict:
         m = self.module
         cap_stream = self._hi if self._hi is not None else torch.cuda.Stream(device=m.flat_params.device)
         cap_stream.wait_stream(torch.cuda.current_stream())
         n0 = lib().svsr_launch_count()
         graphs, pool = [], None
         m._weights_dirty = True  # the repack belongs to every replay: the optimizer has always just run
-        for part in ((0, 1) if self.staged else (-1,)):
-            g = torch.cuda.CUDAGraph()
-            # thread_local: NCCL's watchdog thread polls events while we capture
-            with torch.cuda.graph(g, pool=pool, stream=cap_stream, capture_error_mode="thread_local"):
-                if part <= 0:
-                    metrics = self._forward(batch)
-                self._backward(part)
-            pool = g.pool()
-            graphs.append(g)
+        if self._stochastic():
+            # layer_dropout / dropout seeds: device-resident control words instead of kernel arguments, every sublayer
+            # launched predicated -- the captured launch sequence is the same for every step (svsr_lrw_step_control)
+            m.device_control = True
+            m._apply_step_control(*(ctl if ctl is not None else m._draw_step_control()))
+            m._ctl_preset = (m._last_skip, 0)
+        try:
+            for part in ((0, 1) if self.staged else (-1,)):
+                g = torch.cuda.CUDAGraph()
+                # thread_local: NCCL's watchdog thread polls events while we capture
+                with torch.cuda.graph(g, pool=pool, stream=cap_stream, capture_error_mode="thread_local"):
+                    if part <= 0:
+                        metrics = self._forward(batch)
+                    self._backward(part)
+                pool = g.pool()
+                graphs.append(g)
+        finally:
+            m._ctl_preset = None
         return {"graphs": graphs, "metrics": metrics, "batch": batch,
                 "launches": int(lib().svsr_launch_count() - n0)}
 
-    def _graph_entry(self, batch):
+    def _graph_entry(self, batch, ctl=None):
         gen = getattr(self.module, "_engine_gen", 0)
         if gen != self._graph_gen:  # another clip geometry = another engine: its graphs are kept while it is alive
             alive = self.module._engines.alive
@@ -216,7 +228,7 @@ class DataParallelStep:
             key = (gen, "static")
             ent = self._graphs.get(key)
         if ent is None:
-            ent = self._graphs[key] = self._capture(batch)
+            ent = self._graphs[key] = self._capture(batch, ctl)
         return ent
 
     def __call__(self, videos, audio_tokens, labels, word_mask=None) -> Dict[str, torch.Tensor]:
@@ -224,8 +236,12 @@ class DataParallelStep:
         batch = (videos, audio_tokens, labels, word_mask)
         cur = torch.cuda.current_stream()
         if self._replayable() and m._shape_key == (videos.shape[0], videos.shape[2], videos.shape[3], videos.shape[4]):
-            ent = self._graph_entry(batch)
+            # this step's layer_dropout mask + dropout seed: host RNG like the reference, handed over in device memory
+            ctl = m._draw_step_control() if self._stochastic() else None
+            ent = self._graph_entry(batch, ctl)
             graphs = ent["graphs"]
+            if ctl is not None:
+                m._apply_step_control(*ctl)
             graphs[0].replay()
             if self.staged:
                 hs = self._reduce_early() if self.world > 1 else []
@@ -266,24 +282,75 @@ class DataParallelStep:
         return metrics
 
 
+def lrs_stage_of(key: str) -> int:
+    """Backward stage (svsr_lrs_backward_stage) after which the gradient of parameter `key` is final."""
+    if key.startswith(("decoder.", "ctc.", "audio_classifier.")):
+        return 0
+    if key.startswith(("encoder.encoders.", "encoder.after_norm.")):
+        return 1
+    return 2  # encoder.frontend.*, encoder.embed.*
+
+
+def stage_ranges(offsets: Dict[str, tuple], stage_of=lrs_stage_of, n_stages: int = 3):
+    """Contiguous element ranges of the flat arena per backward stage: {name: (offset, numel, ...)} -> [[(a, b), ...]].
+    Tensors are 4-element aligned in the arena; adjacent tensors of one stage merge into one range (one all-reduce)."""
+    per = [[] for _ in range(n_stages)]
+    for key, (off, n, *_rest) in offsets.items():
+        per[stage_of(key)].append((off, off + (n + 3) // 4 * 4))
+    out = []
+    for rs in per:
+        rs.sort()
+        merged = []
+        for a, b in rs:
+            if merged and merged[-1][1] == a:
+                merged[-1] = (merged[-1][0], b)
+            else:
+                merged.append((a, b))
+        out.append(merged)
+    return out
+
+
+def allreduce_ranges(flat: torch.Tensor, ranges, group=None):
+    """Async SUM all-reduce of each (a, b) slice of the flat gradient arena; returns the work handles."""
+    return [dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True) for a, b in ranges]
+
+
 class SentenceDataParallelStep:
     """The same data-parallel step for the LRS sentence-level module (syncvsr_b200.e2e.E2E): zero_grad -> forward ->
-    backward -> ONE all-reduce(SUM) of the flat gradient arena -> fused clip + AdamW (LRS/video/lightning.py:89-96,
-    gradient_clip_val 5.0, main.py:33-49). BatchNorm statistics stay per rank, as in the reference."""
+    backward -> all-reduce(SUM) of the flat gradient arena -> fused clip + AdamW (LRS/video/lightning.py:89-96,
+    gradient_clip_val 5.0, main.py:33-49). BatchNorm statistics stay per rank, as in the reference.
 
-    def __init__(self, module, optimizer: FusedAdamW, group=None, warmup: int = 0, total: int = 1):
+    The 1.0 GB gradient arena is reduced in three pieces as the backward retires them (svsr_lrs_backward_stage): the loss
+    heads + decoder (65 M parameters) while the Conformer blocks compute, the blocks (171 M) while the frontend
+    computes, and only the frontend + embed (12 M) after the last kernel -- what DDP's bucketed reducer does for the
+    reference, with three buckets cut at the engine's stage boundaries."""
+
+    def __init__(self, module, optimizer: FusedAdamW, group=None, warmup: int = 0, total: int = 1,
+                 staged: Optional[bool] = None):
         self.module, self.opt, self.group = module, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.warmup, self.total, self.global_step = warmup, total, 0
+        self.staged = (self.world > 1) if staged is None else bool(staged)
+        self._ranges = stage_ranges(module._offsets)
 
     def __call__(self, x, lengths, audios, label):
         m = self.module
         self.opt.zero_grad()
         with torch.no_grad():
             out = m(x, lengths, audios, label)
-        check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
-        if self.world > 1:
-            dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        if not self.staged:
+            check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
+            if self.world > 1:
+                dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            hs = []
+            for stage in range(3):
+                check(lib().svsr_lrs_backward_stage(m._h, C.c_void_p(0), C.c_int(stage), m._stream()),
+                      f"svsr_lrs_backward_stage {stage}")
+                if self.world > 1:
+                    hs += allreduce_ranges(m.flat_grads, self._ranges[stage], self.group)
+            for h in hs:
+                h.wait()
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
         self.global_step += 1
         self.opt.step(lr=lr, grad_div=float(self.world))

@@ -178,3 +178,80 @@ def test_lrs_engine_rejects_unsupported_geometry():
     assert b"adim" in L.svsr_last_error()
     bad = LrsConfig(2, 12, 88, 88, 256, 4, 512, 1, 1, 512, 300, 33, 2, 2, 64, 17, 0.1, 0.1, 10.0, 1e-5, 0.1)  # kernel 33
     assert L.svsr_lrs_create(C.byref(bad), C.byref(h)) != 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# staged gradient all-reduce of the LRS step (train.SentenceDataParallelStep): ranges + a 2-rank gloo run
+# ---------------------------------------------------------------------------------------------------------------
+def _lrs_offsets():
+    L, h = _lrs_engine()
+    name, ndim, off, decay = C.c_char_p(), C.c_int(), C.c_int64(), C.c_int()
+    shape = (C.c_int64 * 5)()
+    offs = {}
+    for i in range(L.svsr_lrs_num_params(h)):
+        _lib.check(L.svsr_lrs_param_info(h, i, C.byref(name), C.byref(ndim), shape, C.byref(off), C.byref(decay)), "info")
+        shp = tuple(shape[k] for k in range(ndim.value))
+        offs[name.value.decode()] = (off.value, math.prod(shp), shp, bool(decay.value))
+    n_total = L.svsr_lrs_param_count(h)
+    L.svsr_lrs_destroy(h)
+    return offs, n_total
+
+
+def test_lrs_stage_ranges_partition_the_gradient_arena():
+    """The three backward stages' ranges (heads + decoder | Conformer blocks | frontend + embed) cover every parameter
+    exactly once with a handful of contiguous slices: one NCCL call per slice, nothing reduced twice, nothing missed."""
+    from syncvsr_b200.train import lrs_stage_of, stage_ranges
+
+    offs, n_total = _lrs_offsets()
+    ranges = stage_ranges(offs)
+    assert len(ranges) == 3 and all(ranges)
+    flat = sorted(r for rs in ranges for r in rs)
+    assert flat[0][0] == 0 and flat[-1][1] == n_total
+    for (a0, a1), (b0, b1) in zip(flat, flat[1:]):
+        assert a1 == b0, "gap or overlap between stage ranges"
+    assert sum(len(rs) for rs in ranges) <= 8  # decayed + non-decayed region per stage (+ the stage-0 heads split)
+    cover = torch.full((n_total,), -1, dtype=torch.int8)
+    for st, rs in enumerate(ranges):
+        for a, b in rs:
+            cover[a:b] = st
+    for key, (off, n, *_r) in offs.items():
+        assert (cover[off:off + n] == lrs_stage_of(key)).all(), key
+
+
+def _staged_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from syncvsr_b200.lightning import allreduce_mean_
+    from syncvsr_b200.train import allreduce_ranges, stage_ranges
+
+    offs = {f"decoder.w{i}": (i * 40, 38) for i in range(3)}
+    offs.update({f"encoder.encoders.0.w{i}": (120 + i * 40, 40) for i in range(3)})
+    offs.update({"encoder.frontend.w": (240, 17), "encoder.embed.0.weight": (260, 40)})
+    ranges = stage_ranges(offs)
+    g = torch.Generator().manual_seed(7 + rank)
+    flat = torch.randn(300, generator=g)
+    whole = flat.clone()
+    hs = []
+    for st in range(3):  # what SentenceDataParallelStep does after each svsr_lrs_backward_stage
+        hs += allreduce_ranges(flat, ranges[st])
+    for h in hs:
+        h.wait()
+    dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+    mean = allreduce_mean_(torch.full((5,), float(rank + 1)))  # the module-level DDP replacement: SUM / world
+    ok = torch.equal(flat, whole) and torch.allclose(mean, torch.full((5,), 1.5))
+    q.put((rank, bool(ok), ranges))
+    dist.destroy_process_group()
+
+
+def test_staged_allreduce_equals_one_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 77) % 500
+    procs = [ctx.Process(target=_staged_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)]
+    assert res[0][2] == [[(0, 120)], [(120, 240)], [(240, 300)]]  # (4-element padded tensors merge into one slice)

@@ -419,17 +419,58 @@ def test_graph_step_drops_its_graphs_when_the_engine_is_rebuilt(Module):
     assert l1 == pytest.approx(l0, rel=2e-4) and rel(p1, p0) < 1e-5
 
 
-def test_step_with_dropout_is_never_replayed_from_a_graph(Module):
-    """A module whose launch sequence depends on per-step host RNG (layer_dropout, dropout seeds) keeps launching kernel
-    by kernel even when graph=True."""
+def test_step_with_shipped_dropouts_replays_from_one_graph(Module):
+    """The shipped training config (layer_dropout .2, ff_dropout .3, config/bert-12l-512d_...yaml:25-28) replays from ONE
+    captured CUDA graph: the layer_dropout mask and the dropout seed are device-resident control words
+    (svsr_lrw_step_control), every sublayer is launched predicated. Same host RNG draws => the same trajectory as the
+    kernel-by-kernel step that skips on the host (losses, parameters, per-sublayer Adam step counts)."""
+    import random
+
     from syncvsr_b200.train import DataParallelStep, FusedAdamW
 
-    m = Module(make_cfg(depth=2, layer_dropout=0.2, ff_dropout=0.3)).train()
-    step = DataParallelStep(m, FusedAdamW.from_config(m), graph=True)
     b = tuple(t.cuda() for t in O.make_inputs(710, 2))
-    for _ in range(3):
-        out = step(*b)
-    assert step.graph_replays == 0 and torch.isfinite(out["loss_total"])
+    P = O.make_params(13, depth=3)
+    runs = {}
+    for graph in (True, False):
+        m = Module(make_cfg(depth=3, layer_dropout=0.3, ff_dropout=0.3)).train()
+        m.load_state_dict(P, strict=False)
+        opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+        step = DataParallelStep(m, opt, graph=graph)
+        random.seed(4242)
+        losses, skips = [], []
+        for _ in range(6):
+            out = step(*b)
+            losses.append(float(out["loss_total"]))
+            skips.append(m._last_skip)
+        runs[graph] = (losses, skips, m.flat_params.clone(), dict(opt._group_steps), step.graph_replays)
+    (l1, s1, p1, g1, r1), (l0, s0, p0, g0, r0) = runs[True], runs[False]
+    assert r1 == 5 and r0 == 0  # (the first step of a module builds its engine and launches kernel by kernel)
+    assert s1 == s0 and len(set(s1)) > 1 and any(s1)  # the same masks, and they do vary
+    assert g1 == g0
+    for a, c in zip(l1, l0):
+        assert a == pytest.approx(c, rel=2e-4)
+    assert rel(p1, p0) < 1e-5
+
+
+def test_device_resident_skip_mask_matches_oracle_skip_set(Module):
+    """Predicated launches: sublayers 1 and 2 dropped through the device control words equal the oracle's skip set; their
+    parameters get exactly zero gradient (the reference: `grad is None`), the others match the oracle's."""
+    meta = dict(B=2, S=88, A=4, G=2, V=320, depth=2, seed_p=7, seed_x=80, extra_tokens=0)
+    m, P, (videos, tokens, labels, wm) = _native(Module, meta)
+    m.device_control = True
+    m._apply_step_control(0b0110, 0)
+    m._ctl_preset = (0b0110, 0)
+    out = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    out["loss_total"].backward()
+    Pq = {k: v.clone().requires_grad_("running" not in k) for k, v in P.items()}
+    o = O.lrw_forward(Pq, videos, tokens, labels, wm, depth=2, q=O.bf16_ste, skip={1, 2})
+    o["loss_total"].backward()
+    assert float(out["loss_total"]) == pytest.approx(float(o["loss_total"]), rel=1e-3)
+    for k, p in m._param_views.items():
+        if k.startswith(("encoder.layers.1.", "encoder.layers.2.")):
+            assert float(p.grad.abs().max()) == 0.0 and Pq[k].grad is None, k
+        elif k.startswith(("encoder", "audio_projection", "category_classifier", "cls_token")):
+            assert rel(p.grad, Pq[k].grad) < 4e-2, k
 
 
 @pytest.mark.parametrize("B,T", [(1, 29), (3, 21), (5, 40)])
