@@ -248,9 +248,10 @@ int svsr_lrw_logits_audio(void* handle, void* stream);
  * dropout_seed arguments are ignored until mode 0 -- so ONE captured CUDA graph replays any step of the shipped
  * layer_dropout .2 / ff_dropout .3 config (call this before each replay). mode 0: host-valued control again. */
 int svsr_lrw_step_control(void* handle, int mode, uint32_t skip_mask, uint64_t dropout_seed, void* stream);
-/* The same backward in two stages so that the data-parallel step can overlap communication with compute:
- * stage 0 = loss heads + encoder + mean-pool (completes the gradient arena range returned by
- * svsr_lrw_early_grad_region: cls_token, encoder and head weights, ~160 MB), stage 1 = ResNet trunk + stem. */
+/* The same backward in three stages, called in order, so that the data-parallel step can overlap communication with
+ * compute: stage 0 = loss heads + encoder + mean-pool (completes cls_token, encoder and head gradients, ~160 MB; the
+ * decayed part is the range svsr_lrw_early_grad_region returns), stage 1 = resnet.layer4 + layer3 (42 MB), stage 2 =
+ * layer2 + layer1 + stem3d (3 MB: the only all-reduce that cannot hide behind compute). */
 int svsr_lrw_backward_stage(void* handle, const float* grad_scale, int stage, void* stream);
 int svsr_lrw_early_grad_region(void* handle, int64_t* begin, int64_t* end);
 /* named activation for parity tests: last_hidden_state, logits_audio, ... dtype 0=f32 1=bf16 2=u8 3=i32 */

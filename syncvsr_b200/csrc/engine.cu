@@ -80,7 +80,7 @@ struct LrwEngine : EngineBase {
   unsigned long long last_seed = 0;
   int last_train = 0;
   bool fwd_done = false;
-  bool bwd_stage0_done = false;
+  bool bwd_stage0_done = false, bwd_stage1_done = false;
 
   float* xs_buf(int i) const { return ws<float>(xs) + (size_t)i * M * Dp; }
   // audio_projection + reshape + log-softmax + NLL in the GEMM epilogue (igemm.cuh, IgemmCe): softmax width % 64 == 0
@@ -741,7 +741,8 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
 }
 
 // stage 0: loss heads + encoder + mean-pool/CLS (completes the gradients of cls_token, encoder and head weights);
-// stage 1: ResNet trunk + stem. stage < 0: both. Each stage joins the side stream before returning.
+// stage 1: resnet.layer4 + layer3; stage 2: layer2 + layer1 + stem3d. stage < 0: everything. Each stage joins the side
+// stream before returning, so a data-parallel caller can all-reduce its parameters' gradients while the next one runs.
 static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cudaStream_t s) {
   if (stage <= 0) {
     SVSR_REQUIRE(e.fwd_done, "lrw backward called before (or twice after) forward");
@@ -862,6 +863,15 @@ static int engine_backward(LrwEngine& e, const float* grad_scale, int stage, cud
   }  // stage <= 0
 
   // ---- resnet trunk + stem ----
+  if (stage == 1) {  // layer4 + layer3: 10.5 M of the trunk's 11.2 M parameters
+    e.bwd_stage1_done = true;
+    return frontend_backward(e, e.fe, sq, s, 7, 4, false);
+  }
+  if (stage == 2) {
+    SVSR_REQUIRE(e.bwd_stage1_done, "lrw backward stage 2 called before stage 1");
+    e.bwd_stage1_done = false;
+    return frontend_backward(e, e.fe, sq, s, 3, 0, true);
+  }
   return frontend_backward(e, e.fe, sq, s);
 }
 
@@ -968,7 +978,7 @@ int svsr_lrw_backward(void* h, const float* grad_scale, void* stream) {
 int svsr_lrw_backward_stage(void* h, const float* grad_scale, int stage, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
-  SVSR_REQUIRE(stage == 0 || stage == 1, "lrw_backward_stage: stage must be 0 or 1");
+  SVSR_REQUIRE(stage >= 0 && stage <= 2, "lrw_backward_stage: stage must be 0, 1 or 2");
   return engine_backward(*e, grad_scale, stage, static_cast<cudaStream_t>(stream));
 }
 // The step never writes the audio logits to HBM (fused head); this materialises them once, on request, from the last

@@ -480,7 +480,11 @@ static int frontend_forward(EngineBase& e, Frontend& f, const float* videos, int
 
 // Backward of the frontend. On entry gbuf[0] holds d loss / d (last block output) (bf16, NHWC); weight-gradient
 // GEMMs go to the side stream through `sq`. Ends with sq.join().
-static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStream_t s) {
+// Blocks bi_hi .. bi_lo (7 = layer4.1 ... 0 = layer1.0), then -- with_stem -- the stem. A caller that splits the trunk
+// (data parallel: all-reduce layer3-4's gradients while layer1-2 + the stem still compute) calls it with an EVEN number
+// of blocks per call, so the T0 / T4 ping-pong is back in place for the next call.
+static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStream_t s, int bi_hi = 7, int bi_lo = 0,
+                             bool with_stem = true) {
   cudaStream_t w = e.wq;
   bf16* T0 = e.ws<bf16>(f.gbuf[0]);  // dOut of the current block, later da1
   bf16* T2 = e.ws<bf16>(f.gbuf[1]);  // activation-masked upstream gradient (identity shortcut branch)
@@ -492,7 +496,7 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
   // dgrad + wgrad tensor kernels time-sharing the SMs anyway (3.55 of its 3.98 ms), so the reduce passes run in the
   // weight-gradient kernels' shadow. Kept as a tested option.
   const char* fuse = getenv("SVSR_BN_BWD_FUSED");
-  const bool fused = !f.swish && fuse && fuse[0] == '1';
+  const bool fused = !f.swish && fuse && fuse[0] == '1' && bi_hi == 7 && bi_lo == 0;
   if (fused) {
     // ---- ReLU trunk (LRW), reversed, BatchNorm-backward reductions fused into the producing input-gradient GEMMs ----
     // G  = relu-masked gradient w.r.t. the block's output (produced masked by the NEXT block's conv1 dgrad, which also
@@ -555,7 +559,7 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
     T0 = G;
   } else {
     // ---- trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
-    for (int bi = 7; bi >= 0; --bi) {
+    for (int bi = bi_hi; bi >= bi_lo; --bi) {
       BlockRef& blk = f.blocks[bi];
       bf16* DC2 = e.ws<bf16>(f.gbuf[3 + (bi & 1)]);
       bf16* DC1 = e.ws<bf16>(f.gbuf[5 + (bi & 1)]);
@@ -597,6 +601,7 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
       RC(sq.end_unit());
     }
   }
+  if (!with_stem) return sq.join();
   // ---- stem ----
   bf16* dz = e.ws<bf16>(f.stem_dz);
   RC(stem_bwd_fused(T0, e.ws<uint8_t>(f.argmax), e.ws<bf16>(f.y0), e.ws<float>(f.stem_bn.coef), e.G + f.stem_bn.gamma,

@@ -24,6 +24,15 @@ def cosine_with_warmup(step: int, base_lr: float, warmup: int, total: int) -> fl
     return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, progress))))
 
 
+def lrw_stage_of(key: str) -> int:
+    """Backward stage (svsr_lrw_backward_stage) after which the gradient of LRW parameter `key` is final."""
+    if key.startswith(("resnet.layer3.", "resnet.layer4.")):
+        return 1
+    if key.startswith(("stem3d.", "resnet.")):
+        return 2
+    return 0  # cls_token, encoder.*, audio_projection.*, category_classifier.*
+
+
 class FusedAdamW:
     """AdamW over the module's flat arenas (decayed region first), with global-norm clipping fused in."""
 
@@ -112,10 +121,11 @@ class DataParallelStep:
     `module(...)`/`loss.backward()` API is equivalent and is what the parity tests use.
 
     graph=True: zero_grad + weight repack + forward + backward (~470 launches on two streams) are captured ONCE per
-    set of input buffers into a CUDA graph and replayed; on N > 1 ranks they are two graphs (heads + encoder | trunk +
-    stem) so that the first all-reduce still overlaps the trunk backward. Only a step whose launch sequence is
-    the same every time can be replayed: a module with layer_dropout or any dropout probability > 0 (per-step host
-    RNG: skipped sublayers, mask seeds are kernel arguments) keeps launching kernel by kernel.
+    set of input buffers into a CUDA graph and replayed; on N > 1 ranks they are three graphs (heads + encoder | layer4-3 | layer2-1 +
+    stem) so that each group's all-reduce overlaps the next group's backward. Only a step whose launch sequence is the
+    same every time can be replayed: with layer_dropout / dropout probabilities > 0 the per-step host RNG (dropped
+    sublayers, mask seeds) is handed over in device memory and every sublayer is launched predicated
+    (svsr_lrw_step_control), so the shipped training config replays from the same graph(s) too.
     high_priority=True: the step's main stream is a high-priority stream, so that whenever an SM frees up the
     critical chain (forward, input gradients, BatchNorm backward) is scheduled before the weight-gradient kernels
     the engine runs beside it on its own (default-priority) stream."""
@@ -130,9 +140,8 @@ class DataParallelStep:
         self.warmup = int(sch.get("num_warmup_steps", 0))
         self.total = int(sch.get("num_training_steps", 1))
         self.global_step = 0
-        a, b = C.c_int64(), C.c_int64()
-        check(lib().svsr_lrw_early_grad_region(module._h, C.byref(a), C.byref(b)), "svsr_lrw_early_grad_region")
-        self._early = (int(a.value), int(b.value))
+        # the gradient arena as contiguous slices per backward stage (heads + encoder | layer4 + layer3 | layer2-1 + stem)
+        self._ranges = stage_ranges(module._offsets, lrw_stage_of)
         self.graph = bool(graph)
         self.staged = (self.world > 1) if staged is None else bool(staged)
         self._hi = torch.cuda.Stream(device=module.flat_params.device, priority=-1) if high_priority else None
@@ -159,14 +168,9 @@ class DataParallelStep:
             check(lib().svsr_lrw_backward_stage(m._h, C.c_void_p(0), C.c_int(stage), m._stream()),
                   f"backward stage {stage}")
 
-    def _reduce_early(self):
-        g, (a, b) = self.module.flat_grads, self._early
-        return [dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
-
-    def _reduce_late(self):
-        g, (a, b) = self.module.flat_grads, self._early
-        return [dist.all_reduce(g[:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True),
-                dist.all_reduce(g[b:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+    def _reduce(self, stage: int):
+        """All-reduce (async, NCCL's stream) of the slices whose gradients backward stage `stage` has just completed."""
+        return allreduce_ranges(self.module.flat_grads, self._ranges[stage], self.group) if self.world > 1 else []
 
     def _stochastic(self) -> bool:
         m = self.module
@@ -190,7 +194,7 @@ class DataParallelStep:
             m._apply_step_control(*(ctl if ctl is not None else m._draw_step_control()))
             m._ctl_preset = (m._last_skip, 0)
         try:
-            for part in ((0, 1) if self.staged else (-1,)):
+            for part in ((0, 1, 2) if self.staged else (-1,)):
                 g = torch.cuda.CUDAGraph()
                 # thread_local: NCCL's watchdog thread polls events while we capture
                 with torch.cuda.graph(g, pool=pool, stream=cap_stream, capture_error_mode="thread_local"):
@@ -244,9 +248,11 @@ class DataParallelStep:
                 m._apply_step_control(*ctl)
             graphs[0].replay()
             if self.staged:
-                hs = self._reduce_early() if self.world > 1 else []
+                hs = self._reduce(0)
                 graphs[1].replay()
-                hs += self._reduce_late() if self.world > 1 else []
+                hs += self._reduce(1)
+                graphs[2].replay()
+                hs += self._reduce(2)
                 for h in hs:
                     h.wait()
             m._weights_dirty = False  # (num_batches_tracked += 1 is a device op: it is part of the graph)
@@ -264,11 +270,12 @@ class DataParallelStep:
                     self._backward(-1)
                 else:
                     # overlap: the encoder/head gradients (~160 MB, finished first) are all-reduced on NCCL's stream
-                    # while the ResNet trunk + stem backward still runs; the remaining ~45 MB follow at the end.
-                    self._backward(0)
-                    hs = self._reduce_early() if self.world > 1 else []
-                    self._backward(1)
-                    hs += self._reduce_late() if self.world > 1 else []
+                    # while the trunk backward runs, layer4 + layer3 (42 MB) while layer2-1 + stem run; only the last
+                    # 3 MB cannot hide behind compute.
+                    hs = []
+                    for stage in range(3):
+                        self._backward(stage)
+                        hs += self._reduce(stage)
                     for h in hs:
                         h.wait()
             finally:

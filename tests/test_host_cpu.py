@@ -197,6 +197,25 @@ def _lrs_offsets():
     return offs, n_total
 
 
+def test_lrw_stage_ranges_partition_the_gradient_arena():
+    """LRW: heads + encoder | resnet.layer4-3 | layer2-1 + stem3d -- six slices (decayed + non-decayed per stage) tile the
+    arena; the last stage (the only all-reduce that cannot overlap compute) is < 2 % of the bytes."""
+    from syncvsr_b200.train import lrw_stage_of, stage_ranges
+
+    L, h = _engine()
+    rows = _table(L, h)
+    n_total = L.svsr_lrw_param_count(h)
+    L.svsr_lrw_destroy(h)
+    offs = {nm: (off, math.prod(shp), shp, dec) for nm, shp, off, dec in rows}
+    ranges = stage_ranges(offs, lrw_stage_of)
+    flat = sorted(r for rs in ranges for r in rs)
+    assert flat[0][0] == 0 and flat[-1][1] == n_total and len(flat) == 6
+    for (a0, a1), (b0, b1) in zip(flat, flat[1:]):
+        assert a1 == b0
+    size = [sum(b - a for a, b in rs) for rs in ranges]
+    assert size[2] < 0.02 * n_total and size[0] > 0.8 * n_total and size[1] > 10_000_000
+
+
 def test_lrs_stage_ranges_partition_the_gradient_arena():
     """The three backward stages' ranges (heads + decoder | Conformer blocks | frontend + embed) cover every parameter
     exactly once with a handful of contiguous slices: one NCCL call per slice, nothing reduced twice, nothing missed."""
