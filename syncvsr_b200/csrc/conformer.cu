@@ -2,6 +2,7 @@
 // lines each one follows. The dense contractions around them (every Linear / pointwise Conv1d, forward, input- and
 // weight-gradient) run on the tcgen05 implicit-GEMM kernels (igemm.cu / wgrad.cu).
 #include "conformer.cuh"
+#include "attention_rel_tc.cuh"
 
 namespace svsr {
 
@@ -471,26 +472,6 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const float*
 // =================================================================================================
 constexpr int AQT = 32;   // query rows per CTA (8 warps x 4 rows)
 constexpr int APITCH = 66;  // bf16 elements per shared-memory row (33 words)
-
-struct AttnK {
-  const __nv_bfloat16 *q, *k, *v, *p;
-  int ldq, ldk, ldv, ldp;
-  const float *bu, *bv;
-  const int* klen;
-  int causal, B, H, Tq, Tk;
-  float scale;
-  __nv_bfloat16* o;
-  int ldo;
-  float* lse;
-  // backward
-  const __nv_bfloat16* d_o;
-  __nv_bfloat16 *dq, *dk, *dv;
-  int lddq, lddk, lddv;
-  float *dp, *dbu, *dbv;
-  float *Pg, *DSg;  // scratch [B,H,Tq,Tk] each
-  float drop_p;     // dropout on the attention probabilities (attention.py:81)
-  unsigned long long drop_seed;
-};
 
 struct AttnSmem {
   __nv_bfloat16 *Ks, *Vs, *Ps;
@@ -1299,12 +1280,18 @@ int attn_smem_attr(K kernel, size_t bytes, size_t* cur) {
   }
   return SVSR_OK;
 }
+// tcgen05 kernels (attention_rel_tc.cu) unless SVSR_ATTN_TC=0
+bool attn_use_tc() {  // read per call: the parity tests run both paths in one process
+  const char* e = getenv("SVSR_ATTN_TC");
+  return !(e && e[0] == '0');
+}
 }  // namespace
 
 int attention_core_fwd(const AttnProblem& p, cudaStream_t s) {
   AttnK k;
   int rc = attn_fill(p, k);
   if (rc) return rc;
+  if (attn_use_tc()) return attention_rel_tc_fwd(k, s);
   static size_t attr = 48 * 1024;
   const size_t smem = attn_smem_bytes(p.Tk, p.p != nullptr, false);
   rc = attn_smem_attr(attention_core_fwd_kernel, smem, &attr);
@@ -1314,7 +1301,10 @@ int attention_core_fwd(const AttnProblem& p, cudaStream_t s) {
   LAUNCH_CHECK();
   return SVSR_OK;
 }
-size_t attention_scratch_bytes(int B, int H, int Tq, int Tk) { return (size_t)2 * B * H * Tq * Tk * sizeof(float); }
+size_t attention_scratch_bytes(int B, int H, int Tq, int Tk) {
+  const size_t cuda_core = (size_t)2 * B * H * Tq * Tk * sizeof(float), tc = attention_rel_tc_scratch_bytes(B, H, Tq, Tk);
+  return cuda_core > tc ? cuda_core : tc;
+}
 
 int attention_core_bwd(const AttnProblem& p, const AttnGrads& g, cudaStream_t s) {
   AttnK k;
@@ -1325,6 +1315,7 @@ int attention_core_bwd(const AttnProblem& p, const AttnGrads& g, cudaStream_t s)
   SVSR_REQUIRE(g.lddq % 8 == 0 && g.lddk % 8 == 0 && g.lddv % 8 == 0, "attention_bwd: gradient pitches must be multiples of 8");
   k.d_o = g.d_o, k.dq = g.dq, k.dk = g.dk, k.dv = g.dv, k.lddq = g.lddq, k.lddk = g.lddk, k.lddv = g.lddv;
   k.dp = g.dp, k.dbu = g.dbias_u, k.dbv = g.dbias_v;
+  if (attn_use_tc()) return attention_rel_tc_bwd(k, g.scratch, s);
   k.Pg = g.scratch, k.DSg = g.scratch + (size_t)p.B * p.H * p.Tq * p.Tk;
   static size_t attr = 48 * 1024;
   const size_t smem = attn_smem_bytes(p.Tk, p.p != nullptr, true);

@@ -7,6 +7,8 @@ to ~2e-4; integer work (sos/eos insertion, token indexing) is bit-exact."""
 import math
 from types import SimpleNamespace
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -214,11 +216,18 @@ ATTN_CASES = [
     ("dec_self", 3, 4, 9, 9, False, False, True),
     ("dec_src", 3, 4, 9, 40, False, True, False),
     ("dec_src_c4", 2, 12, 41, 250, False, True, False),
+    # several 128-row query tiles / 64-key tiles of the tcgen05 kernels (attention_rel_tc.cu)
+    ("enc_rel_c4", 1, 12, 250, 250, True, True, False),
+    ("enc_rel_long", 1, 2, 300, 300, True, True, False),
+    ("dec_self_long", 2, 2, 150, 150, False, False, True),
+    ("dec_src_long_q", 1, 2, 140, 70, False, True, False),
 ]
 
 
 @pytest.mark.parametrize("name,B,H,Tq,Tk,use_rel,use_klen,causal", ATTN_CASES)
 def test_attention_core_fwd_bwd(ops, name, B, H, Tq, Tk, use_rel, use_klen, causal):
+    if os.environ.get("SVSR_ATTN_TC") == "0" and use_rel and Tk > 256:
+        pytest.skip("the CUDA-core comparator keeps K, V and the p window of the whole clip in shared memory (Tk <= ~280)")
     D = H * 64
     fused = Tq == Tk  # self-attention: q | k | v are column blocks of one [rows, 3D] buffer (the engine's layout)
     if fused:
@@ -250,7 +259,10 @@ def test_attention_core_fwd_bwd(ops, name, B, H, Tq, Tk, use_rel, use_klen, caus
                                                       klen=klen, causal=causal)
     assert rel(dq, grads[0]) < 6e-3 and rel(dk, grads[1]) < 6e-3 and rel(dv, grads[2]) < 6e-3, name
     if use_rel:
-        assert rel(dp, grads[3]) < 2e-3 and rel(dbu, grads[4]) < 2e-3 and rel(dbv, grads[5]) < 2e-3, name
+        # tensor-core path: dS and (q + v) are bf16 MMA operands (what the reference's autocast matmul rounds too), so the
+        # p-side gradients carry bf16 operand error like dq/dk/dv; the fp32 CUDA-core comparator keeps the tighter bound
+        tol = 2e-3 if os.environ.get("SVSR_ATTN_TC") == "0" else BF16_TOL
+        assert rel(dp, grads[3]) < tol and rel(dbu, grads[4]) < tol and rel(dbv, grads[5]) < tol, name
     if use_klen:  # masked keys receive exactly zero gradient
         for b in range(B):
             n = int(klen[b])
