@@ -326,7 +326,7 @@ def lrs_args(lmax):
                            max_label_len=lmax)
 
 
-def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: int = 1):
+def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: int = 1, graph: bool = True):
     import torch
     import torch.distributed as dist
 
@@ -337,7 +337,7 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
     torch.manual_seed(1234)
     m = E2E(5049, lrs_args(Lmax)).train()
     opt = FusedAdamW(m, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.03, max_grad_norm=5.0)
-    dp = SentenceDataParallelStep(m, opt)
+    dp = SentenceDataParallelStep(m, opt, graph=graph)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     x = torch.randn(B, T_, 1, S, S, device="cuda", generator=g)
     lengths = torch.randint(T_ // 2, T_ + 1, (B,), device="cuda", generator=g)
@@ -353,7 +353,8 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
 
     def step():
         out = dp(x, lengths, tokens, label)
-        m._ensure(x, Lmax)  # the bf16 weight repack belongs to the step
+        if not dp.graph_replays:
+            m._ensure(x, Lmax)  # the bf16 weight repack belongs to the step (graph mode: it is the graph's first node)
         return out
 
     for _ in range(warmup):
@@ -361,6 +362,10 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    from syncvsr_b200._lib import lib
+
+    lib().svsr_launch_count.restype = C.c_longlong
+    n0, g0 = int(lib().svsr_launch_count()), dp.graph_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -368,6 +373,7 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    launches = int(lib().svsr_launch_count()) - n0 + dp.graph_launches - g0  # replays do not pass the library's counter
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,7 +381,8 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
     gf = LRS_FWD_GF.get(T_, LRS_FWD_GF[150] * T_ / 150) * 3 - 1.76 * T_ / 29
     res = {"ms_per_step": ms, "clips_per_s": world * B * 1e3 / ms, "frames_per_s": world * B * T_ * 1e3 / ms,
            "algorithmic_tflops_per_gpu": B * gf / ms, "loss": [float(v) for v in out[:4]], "acc": float(out[4]),
-           "workspace_gb": m._ws.numel() / 2 ** 30, "params_M": m.flat_params.numel() / 1e6}
+           "workspace_gb": m._ws.numel() / 2 ** 30, "params_M": m.flat_params.numel() / 1e6,
+           "graph_replays": dp.graph_replays, "launches": launches}
     del dp, opt, m
     torch.cuda.empty_cache()
     return res
@@ -394,7 +401,7 @@ def run_lrs_arm(args, T_: int, B: int, cid: str):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    r = lrs_step_ms(args.steps, max(args.warmup, 3), T_, B, rank, world)
+    r = lrs_step_ms(args.steps, max(args.warmup, 3), T_, B, rank, world, graph=bool(args.graph))
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         peak_tf, _, peak_src = measured_peaks()
@@ -406,7 +413,9 @@ def run_lrs_arm(args, T_: int, B: int, cid: str):
             "config": {"workload": f"LRS E2E step: Conformer-12L adim 768 + CTC + decoder-6L + audio CE, x[{B},{T_},1,88,88] "
                                    f"per GPU, fwd+bwd+allreduce+AdamW (BASELINE configs[{2 if T_ == 150 else 3}])",
                        "global_batch": world * B, "parallelism": f"dp{world}", "loss": r["loss"], "acc": r["acc"],
-                       "frames_per_s": r["frames_per_s"], "workspace_gb": r["workspace_gb"]},
+                       "frames_per_s": r["frames_per_s"], "workspace_gb": r["workspace_gb"],
+                       "launch_mode": "cuda graph replay" if r["graph_replays"] else "kernel by kernel"},
+            "gpu_launches": r["launches"],
             "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": r["algorithmic_tflops_per_gpu"],
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": r["algorithmic_tflops_per_gpu"] / peak_tf,
                          "peak_source": peak_src, "traffic": None},

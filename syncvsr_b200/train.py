@@ -332,32 +332,121 @@ class SentenceDataParallelStep:
     computes, and only the frontend + embed (12 M) after the last kernel -- what DDP's bucketed reducer does for the
     reference, with three buckets cut at the engine's stage boundaries."""
 
+    MAX_GRAPH_SETS = 4
+
     def __init__(self, module, optimizer: FusedAdamW, group=None, warmup: int = 0, total: int = 1,
-                 staged: Optional[bool] = None):
+                 staged: Optional[bool] = None, graph: bool = False):
+        """graph=True: zero_grad + weight repack + forward + backward (~1 250 launches on two streams) are captured once per
+        set of input buffers and clip geometry into a CUDA graph (three under torchrun, cut at the backward stages so that
+        each all-reduce still overlaps the next stage) and replayed. Only with dropout_rate = transformer_attn_dropout_rate
+        = 0: the LRS kernels take their dropout seeds as launch arguments, so a step with dropout launches kernel by
+        kernel."""
         self.module, self.opt, self.group = module, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.warmup, self.total, self.global_step = warmup, total, 0
         self.staged = (self.world > 1) if staged is None else bool(staged)
         self._ranges = stage_ranges(module._offsets)
+        self.graph = bool(graph)
+        self._graphs: Dict[tuple, dict] = {}
+        self._static: Dict[int, tuple] = {}
+        self.graph_replays = 0
+        self.graph_launches = 0
+
+    def _backward(self, stage: int) -> None:
+        m = self.module
+        if stage < 0:
+            check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
+        else:
+            check(lib().svsr_lrs_backward_stage(m._h, C.c_void_p(0), C.c_int(stage), m._stream()),
+                  f"svsr_lrs_backward_stage {stage}")
+
+    def _reduce(self, stage: int):
+        return allreduce_ranges(self.module.flat_grads, self._ranges[stage], self.group) if self.world > 1 else []
+
+    def _replayable(self, x, label) -> bool:
+        m = self.module
+        return (self.graph and m.training and m.dropout_rate == 0.0 and m.attn_dropout_rate == 0.0
+                and m._shape_key == (x.shape[0], x.shape[1], x.shape[3], x.shape[4]) and label.shape[1] + 1 <= m._lmax)
+
+    def _capture(self, batch) -> dict:
+        m = self.module
+        cap = torch.cuda.Stream(device=m.flat_params.device)
+        cap.wait_stream(torch.cuda.current_stream())
+        n0 = lib().svsr_launch_count()
+        graphs, pool, out = [], None, None
+        for part in ((0, 1, 2) if self.staged else (-1,)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=cap, capture_error_mode="thread_local"):
+                if part <= 0:
+                    m._weights_dirty = True  # the repack belongs to every replay: the optimizer has always just run
+                    self.opt.zero_grad()
+                    with torch.no_grad():
+                        out = m(*batch)
+                self._backward(part)
+            pool = g.pool()
+            graphs.append(g)
+        return {"graphs": graphs, "out": out, "batch": batch, "launches": int(lib().svsr_launch_count() - n0)}
+
+    def _graph_entry(self, batch) -> dict:
+        gen = getattr(self.module, "_engine_gen", 0)
+        alive = self.module._engines.alive
+        for k in [k for k in self._graphs if not alive(k[0])]:  # graphs of a destroyed engine point into freed memory
+            del self._graphs[k]
+        for g in [g for g in self._static if not alive(g)]:
+            del self._static[g]
+        key = (gen,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) if isinstance(t, torch.Tensor) else None for t in batch)
+        ent = self._graphs.get(key)
+        static = self._static.get(gen)
+        if ent is None and static is None and sum(k[0] == gen for k in self._graphs) >= self.MAX_GRAPH_SETS:
+            static = self._static[gen] = tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in batch)
+        if ent is None and static is not None:
+            if any(isinstance(d, torch.Tensor) and d.shape != t.shape for d, t in zip(static, batch)):
+                return None  # another label / token length than the static set was made for: launch kernel by kernel
+            for d, t in zip(static, batch):
+                if isinstance(d, torch.Tensor):
+                    d.copy_(t, non_blocking=True)
+            batch, key = static, (gen, "static")
+            ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(batch)
+        return ent
 
     def __call__(self, x, lengths, audios, label):
         m = self.module
-        self.opt.zero_grad()
-        with torch.no_grad():
-            out = m(x, lengths, audios, label)
-        if not self.staged:
-            check(lib().svsr_lrs_backward(m._h, C.c_void_p(0), m._stream()), "svsr_lrs_backward")
-            if self.world > 1:
-                dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        ent = None
+        if self._replayable(x, label) and (audios is None or audios.dtype == torch.long) and x.dtype == torch.float32 \
+                and lengths.dtype == torch.long and label.dtype == torch.long and x.is_contiguous():
+            ent = self._graph_entry((x, lengths, audios, label))
+        if ent is not None:
+            graphs = ent["graphs"]
+            graphs[0].replay()
+            if self.staged:
+                hs = self._reduce(0)
+                graphs[1].replay()
+                hs += self._reduce(1)
+                graphs[2].replay()
+                hs += self._reduce(2)
+                for h in hs:
+                    h.wait()
+            m._weights_dirty = False
+            self.graph_replays += 1
+            self.graph_launches += ent["launches"]
+            out = ent["out"]
         else:
-            hs = []
-            for stage in range(3):
-                check(lib().svsr_lrs_backward_stage(m._h, C.c_void_p(0), C.c_int(stage), m._stream()),
-                      f"svsr_lrs_backward_stage {stage}")
+            self.opt.zero_grad()
+            with torch.no_grad():
+                out = m(x, lengths, audios, label)
+            if not self.staged:
+                self._backward(-1)
                 if self.world > 1:
-                    hs += allreduce_ranges(m.flat_grads, self._ranges[stage], self.group)
-            for h in hs:
-                h.wait()
+                    dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                hs = []
+                for stage in range(3):
+                    self._backward(stage)
+                    hs += self._reduce(stage)
+                for h in hs:
+                    h.wait()
         lr = cosine_with_warmup(self.global_step, self.opt.lr, self.warmup, self.total) if self.total > 1 else self.opt.lr
         self.global_step += 1
         self.opt.step(lr=lr, grad_div=float(self.world))
