@@ -257,12 +257,25 @@ dwconv1d_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (k < K) {
-    for (int t = t0; t < t1; ++t) {
-      const int ts = t + k - pad;
-      if (ts < 0 || ts >= T) continue;
-      const F8 d = ld8(dy + ((long long)b * T + t) * C + c0), xv = ld8(x + ((long long)b * T + ts) * C + c0);
+    // four rows in flight (fixed trip count, predicated loads: eight independent 16-byte loads ahead of the FMAs)
+    for (int t = t0; t < t1; t += 4) {
+      uint4 dq[4], xq[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(d.v[j], xv.v[j], acc[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + u, ts = tt + k - pad;
+        const bool ok = tt < t1 && ts >= 0 && ts < T;
+        dq[u] = ok ? *reinterpret_cast<const uint4*>(dy + ((long long)b * T + tt) * C + c0) : make_uint4(0u, 0u, 0u, 0u);
+        xq[u] = ok ? *reinterpret_cast<const uint4*>(x + ((long long)b * T + ts) * C + c0) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 d0 = unpack_bf16x2(dq[u].x), d1 = unpack_bf16x2(dq[u].y), d2 = unpack_bf16x2(dq[u].z), d3 = unpack_bf16x2(dq[u].w);
+        const float2 x0 = unpack_bf16x2(xq[u].x), x1 = unpack_bf16x2(xq[u].y), x2 = unpack_bf16x2(xq[u].z), x3 = unpack_bf16x2(xq[u].w);
+        acc[0] = fmaf(d0.x, x0.x, acc[0]), acc[1] = fmaf(d0.y, x0.y, acc[1]);
+        acc[2] = fmaf(d1.x, x1.x, acc[2]), acc[3] = fmaf(d1.y, x1.y, acc[3]);
+        acc[4] = fmaf(d2.x, x2.x, acc[4]), acc[5] = fmaf(d2.y, x2.y, acc[5]);
+        acc[6] = fmaf(d3.x, x3.x, acc[6]), acc[7] = fmaf(d3.y, x3.y, acc[7]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(dw + (c0 + j) * K + k, acc[j]);

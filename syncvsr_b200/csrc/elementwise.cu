@@ -915,19 +915,48 @@ __global__ void unpack_linear_wgrad_kernel(const float* __restrict__ tmp, float*
     grad[i] += tmp[(long long)r * Kp + k];
   }
 }
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db, int M,
-                                   int N, const StepCtl ctl) {
+// db[col] += sum_r dy[r][col] (the bias gradient of a Linear). A thread owns 8 consecutive columns (one 16-byte load per
+// row, four rows in flight); a block covers 64 columns x a strided slab of rows, reduces its 32 row lanes through shared
+// memory and issues 64 atomics. ld % 8 == 0 and the row pitch covers N rounded up to 8 (bf16 GEMM operands do): the last
+// group may read pad columns, which are never accumulated into db.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ db,
+                                                          int M, int N, const StepCtl ctl) {
   if (ctl_skipped(ctl)) return;
-  // block handles 64 columns x a slab of rows; threads: 64 columns x 4 row lanes
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane_r = threadIdx.x >> 6;
-  float acc = 0.f;
-  if (col < N)
-    for (int r = blockIdx.y * 4 + lane_r; r < M; r += gridDim.y * 4) acc += __bfloat162float(dy[(long long)r * ld + col]);
-  __shared__ float s[256];
-  s[threadIdx.x] = acc;
+  const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;  // 8 column groups x 32 row lanes
+  const int col = blockIdx.x * 64 + cg * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (col < N) {
+    const int step = gridDim.y * 32;
+    int r = blockIdx.y * 32 + lane_r;
+    const __nv_bfloat16* p = dy + col;
+    for (; r + 3 * step < M; r += 4 * step) {
+      F8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld8(p + (long long)(r + u * step) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[u].v[k];
+    }
+    for (; r < M; r += step) {
+      const F8 v = ld8(p + (long long)r * ld);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+    }
+  }
+  __shared__ float s[32][65];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[lane_r][cg * 8 + k] = acc[k];
   __syncthreads();
-  if (lane_r == 0 && col < N) atomicAdd(db + col, s[threadIdx.x] + s[threadIdx.x + 64] + s[threadIdx.x + 128] + s[threadIdx.x + 192]);
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += s[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(db + c, t);
+  }
 }
 // dst = src when the sublayer's bit is set in the device-resident skip mask (residual stream passes through a dropped
 // sublayer, lightning.py:95-105 layer_dropout), nothing otherwise
@@ -1153,7 +1182,13 @@ int unpack_linear_wgrad(const float* tmp, float* grad, int N, int K, int Kp, int
   return SVSR_OK;
 }
 int colsum_bf16(const __nv_bfloat16* dy, int ld, float* db, int M, int N, cudaStream_t s, const StepCtl* ctl) {
-  dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64 < 1 ? 1 : (M + 63) / 64));
+  SVSR_REQUIRE(ld % 8 == 0 && ((N + 7) & ~7) <= ld, "colsum_bf16: pitch %d must be a multiple of 8 that covers N=%d rounded up to 8", ld, N);
+  // about four blocks per SM; every block keeps at least 128 rows (4 rows in flight per thread) when M allows
+  const int bx = (N + 63) / 64;
+  int by = (148 * 4 + bx - 1) / bx;
+  const int by_max = (M + 127) / 128;
+  by = by < 1 ? 1 : (by > by_max ? by_max : by);
+  dim3 grid((unsigned)bx, (unsigned)by);
   colsum_bf16_kernel<<<grid, 256, 0, s>>>(dy, ld, db, M, N, ctl ? *ctl : StepCtl());
   LAUNCH_CHECK();
   return SVSR_OK;
