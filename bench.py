@@ -130,9 +130,56 @@ def cpu_reference_clips_per_s(steps: int, warmup: int, batch: int = 2):
     return batch * steps / dt, dt / steps * 1e3, cores, torch.get_num_threads()
 
 
+def cpu_reference_lrs_clips_per_s(steps: int, warmup: int, T_: int, batch: int = 1):
+    """The oracle port of E2E.forward (oracle/lrs_oracle.py, pinned to the reference's own module) + backward on the host
+    cores: lrs2.yaml widths, `batch` clips of T_ frames per step."""
+    import torch
+
+    from oracle import lrs_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: v.clone().requires_grad_("running" not in k and v.dtype.is_floating_point) for k, v in O.make_params(0).items()}
+    x, lengths, tokens, label = O.make_inputs(1234, batch, T_)
+
+    def one():
+        for v in P.values():
+            v.grad = None
+        out = O.lrs_forward(P, x, lengths, tokens, label, elayers=12, dlayers=6, heads=12, odim=5049, audio_alignment=2,
+                            audio_vocab_size=640)
+        loss = out["loss"] if isinstance(out, dict) else out[0]
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores, torch.get_num_threads()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.config in ("c3", "c4"):
+        T_, B = (150, 16) if args.config == "c3" else (250, 8)
+        steps, warmup = min(args.steps, 6), min(args.warmup, 1)
+        cps, ms, cores, threads = cpu_reference_lrs_clips_per_s(steps, warmup, T_)
+        sample = (f"oracle port of e2e_asr_transformer.py:186-227 fwd+bwd, fp32, B=1 x T={T_} x {steps} steps (+{warmup} "
+                  f"warm-up), {threads} torch threads on {cores} host cores")
+        print(json.dumps({
+            "impl": "reference", "metric": f"clips/sec (fwd+bwd) LRS-shape [B,{T_},1,88,88]", "config_id": args.config,
+            "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": lrs_workload(T_, B), "global_batch": args.gpus * B, "parallelism": f"dp{args.gpus}",
+                       "sample": f"each CPU step is a bounded sample of that workload: [1,{T_},1,88,88], fwd+bwd, fp32"},
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
         return
     steps, warmup = min(args.steps, 8), min(args.warmup, 2)
     cps, ms, cores, threads = cpu_reference_clips_per_s(steps, warmup)
@@ -314,11 +361,11 @@ def run_head_arm(args):
 LRS_FWD_GF = {150: 94.8 + 54.9 + 0.59 + 6.5, 250: 158.1 + 93.4 + 0.98 + 8.0}  # SURVEY.md 8(d), per clip, forward
 
 
-def lrs_args(lmax):
+def lrs_args(lmax, dropout=0.0):
     from types import SimpleNamespace
 
     return SimpleNamespace(adim=768, aheads=12, eunits=3072, elayers=12, ddim=768, dheads=12, dunits=3072, dlayers=6,
-                           mtlalpha=0.1, lsm_weight=0.1, dropout_rate=0.0, transformer_attn_dropout_rate=0.0,
+                           mtlalpha=0.1, lsm_weight=0.1, dropout_rate=dropout, transformer_attn_dropout_rate=dropout,
                            transformer_input_layer="conv3d", transformer_encoder_attn_layer_type="rel_mha",
                            macaron_style=True, use_cnn_module=True, cnn_module_kernel=31, zero_triu=False,
                            a_upsample_ratio=1, relu_type="swish", transformer_length_normalized_loss=False,
@@ -326,7 +373,13 @@ def lrs_args(lmax):
                            max_label_len=lmax)
 
 
-def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: int = 1, graph: bool = True):
+def lrs_workload(T_: int, B: int) -> str:
+    return (f"LRS E2E step: Conformer-12L adim 768 + CTC + decoder-6L + audio CE, x[{B},{T_},1,88,88] per GPU, "
+            f"fwd+bwd+allreduce+AdamW (BASELINE configs[{2 if T_ == 150 else 3}])")
+
+
+def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: int = 1, graph: bool = True,
+                dropout: float = 0.0, e2e: bool = True):
     import torch
     import torch.distributed as dist
 
@@ -335,7 +388,7 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
 
     Lmax = 40
     torch.manual_seed(1234)
-    m = E2E(5049, lrs_args(Lmax)).train()
+    m = E2E(5049, lrs_args(Lmax, dropout)).train()
     opt = FusedAdamW(m, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.03, max_grad_norm=5.0)
     dp = SentenceDataParallelStep(m, opt, graph=graph)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
@@ -378,12 +431,43 @@ def lrs_step_ms(steps: int, warmup: int, T_: int, B: int, rank: int = 0, world: 
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    e2e_res, pipe = None, None
+    if e2e:
+        # ---- end to end through the public API: pinned HOST inputs copied every step (the copy of step i+1 overlaps step i
+        # on a second stream), the step's loss read back to pinned host memory ----
+        from syncvsr_b200.train import PrefetchedStep
+
+        host = tuple(t.cpu().pin_memory() for t in (x, lengths, tokens, label))
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        pipe = PrefetchedStep(dp, host)
+
+        def e2e_run(n):
+            for i in range(n):
+                pipe(host, host if i + 1 < n else None)
+                if not dp.graph_replays:
+                    m._ensure(x, Lmax)
+
+        e2e_run(2)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        e2e_run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e_res = {"value": world * B * 1e3 / e2e_ms, "unit": "clips/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 4}
     gf = LRS_FWD_GF.get(T_, LRS_FWD_GF[150] * T_ / 150) * 3 - 1.76 * T_ / 29
-    res = {"ms_per_step": ms, "clips_per_s": world * B * 1e3 / ms, "frames_per_s": world * B * T_ * 1e3 / ms,
+    res = {"e2e": e2e_res, "ms_per_step": ms, "clips_per_s": world * B * 1e3 / ms, "frames_per_s": world * B * T_ * 1e3 / ms,
            "algorithmic_tflops_per_gpu": B * gf / ms, "loss": [float(v) for v in out[:4]], "acc": float(out[4]),
            "workspace_gb": m._ws.numel() / 2 ** 30, "params_M": m.flat_params.numel() / 1e6,
            "graph_replays": dp.graph_replays, "launches": launches}
-    del dp, opt, m
+    del pipe, dp, opt, m
     torch.cuda.empty_cache()
     return res
 
@@ -403,6 +487,18 @@ def run_lrs_arm(args, T_: int, B: int, cid: str):
         sampler.start()
     r = lrs_step_ms(args.steps, max(args.warmup, 3), T_, B, rank, world, graph=bool(args.graph))
     clocks = sampler.stop() if sampler else None
+    # the reference's yaml (lrs2.yaml / lrs3.yaml: dropout_rate 0.1, transformer_attn_dropout_rate 0.1): the LRS kernels take
+    # their dropout seeds as launch arguments, so this step launches kernel by kernel
+    rd = lrs_step_ms(max(args.steps // 2, 3), 3, T_, B, rank, world, graph=bool(args.graph), dropout=0.1, e2e=False)
+    shipped = {"value": rd["clips_per_s"], "unit": "clips/s", "ms_per_step": rd["ms_per_step"],
+               "launch_mode": "cuda graph replay" if rd["graph_replays"] else "kernel by kernel",
+               "config": "dropout_rate 0.1, transformer_attn_dropout_rate 0.1 (the reference's yaml)"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cps, cms, cores, threads = cpu_reference_lrs_clips_per_s(6, 1, T_)
+        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port of E2E.forward + backward (oracle/lrs_oracle.py), fp32, B=1 x T={T_} x 6 steps "
+                         f"(+1 warm-up), {cms:.0f} ms/step, {threads} torch threads on {cores} host cores"}
     if rank == 0:
         peak_tf, _, peak_src = measured_peaks()
         print(json.dumps({
@@ -410,12 +506,11 @@ def run_lrs_arm(args, T_: int, B: int, cid: str):
             "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"LRS E2E step: Conformer-12L adim 768 + CTC + decoder-6L + audio CE, x[{B},{T_},1,88,88] "
-                                   f"per GPU, fwd+bwd+allreduce+AdamW (BASELINE configs[{2 if T_ == 150 else 3}])",
+            "config": {"workload": lrs_workload(T_, B),
                        "global_batch": world * B, "parallelism": f"dp{world}", "loss": r["loss"], "acc": r["acc"],
                        "frames_per_s": r["frames_per_s"], "workspace_gb": r["workspace_gb"],
                        "launch_mode": "cuda graph replay" if r["graph_replays"] else "kernel by kernel"},
-            "gpu_launches": r["launches"],
+            "gpu_launches": r["launches"], "e2e": r["e2e"], "cpu_baseline": cpu, "shipped_dropouts": shipped,
             "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": r["algorithmic_tflops_per_gpu"],
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": r["algorithmic_tflops_per_gpu"] / peak_tf,
                          "peak_source": peak_src, "traffic": None},
@@ -619,7 +714,7 @@ def run_native_arm(args):
             also["c5_audio_head_stress"] = head_stress(steps=10, warmup=3)
             peak_tf_, _, _ = measured_peaks()
             also["c5_audio_head_stress"]["frac_of_tensor_peak"] = also["c5_audio_head_stress"]["algorithmic_tflops"] / peak_tf_
-            also["c3_lrs2_T150_B16"] = lrs_step_ms(steps=5, warmup=3, T_=150, B=16)
+            also["c3_lrs2_T150_B16"] = lrs_step_ms(steps=5, warmup=3, T_=150, B=16, e2e=False)
         except Exception as ex:  # never lose the headline line to a side measurement
             also["error"] = repr(ex)
         line["also"] = also
