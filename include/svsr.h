@@ -397,6 +397,12 @@ int svsr_lrs_backward(void* handle, const float* grad_scale, void* stream);
  * Conformer blocks, 2 = embed + visual frontend. When a stage returns, the gradients of ITS parameters are final on
  * `stream`, so a data-parallel caller all-reduces them while the next stage computes (syncvsr_b200/train.py). */
 int svsr_lrs_backward_stage(void* handle, const float* grad_scale, int stage, void* stream);
+/* Device-resident step seed. mode 1: writes dropout_seed to the engine's control word on `stream`; from then on every
+ * dropout site of forward / encode / backward reads the step seed from device memory (the dropout_seed ARGUMENTS are
+ * ignored), so ONE captured CUDA graph replays every step of the shipped dropout_rate / transformer_attn_dropout_rate
+ * config (lrs2.yaml:21-22,46-47): call this before each replay. Same masks as the host-valued path for the same seed.
+ * mode 0: host-valued seeds again. */
+int svsr_lrs_step_control(void* handle, int mode, uint64_t dropout_seed, void* stream);
 /* named tensors: encoder_out, embed_out, frontend, logits_audio, ctc_logits, pred, ys_in, ys_out, layer<i>.x<k>;
  * dtype 0=f32 1=bf16 2=u8 3=i32 4=i64 */
 int svsr_lrs_tensor(void* handle, const char* name, void** ptr, int64_t* numel, int* dtype);

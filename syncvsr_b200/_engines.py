@@ -19,12 +19,13 @@ from ._lib import check, lib
 
 
 class Engine:
-    __slots__ = ("h", "ws", "ws_bytes", "id", "key", "packed_version", "packed_native")
+    __slots__ = ("h", "ws", "ws_bytes", "id", "key", "packed_version", "packed_native", "dev_seed")
 
     def __init__(self, h, ws, ws_bytes, eid, key):
         self.h, self.ws, self.ws_bytes, self.id, self.key = h, ws, ws_bytes, eid, key
         self.packed_version = -1  # autograd version of the parameter arena at the last repack of THIS engine
         self.packed_native = -1   # native-update counter (mark_weights_updated) at the last repack
+        self.dev_seed = False     # LRS: the engine reads its dropout step seed from device memory (svsr_lrs_step_control)
 
 
 class EngineCache:

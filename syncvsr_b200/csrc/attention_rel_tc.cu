@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(NT, 2) attn_rel_fwd_kernel(const AttnK a) {
   const int nk = (active_keys(a, b, i0) + KT - 1) / KT;
   const float c2 = a.scale * LOG2E;
   const float ks = DROP ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  const unsigned long long dseed = DROP ? seed_plus(a.drop_seed, a.seed_base) : 0ULL;
   const unsigned long long e0 = (((unsigned long long)b * a.H + h) * a.Tq + i) * a.Tk;
   float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's 32 keys only
   float o[32];
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(NT, 2) attn_rel_fwd_kernel(const AttnK a) {
       for (int e = 0; e < 32; ++e) {
         float pv = t[e] == -INFINITY ? 0.f : exp2f(t[e] - m_new);
         sum += pv;  // the softmax normaliser is taken before dropout
-        if (DROP) pv = dropout_keep(a.drop_seed, e0 + (unsigned long long)(j0 + hf * 32 + e), a.drop_p) ? pv * ks : 0.f;
+        if (DROP) pv = dropout_keep(dseed, e0 + (unsigned long long)(j0 + hf * 32 + e), a.drop_p) ? pv * ks : 0.f;
         t[e] = pv;
       }
     } else {
@@ -344,6 +345,7 @@ attn_rel_bwd_q_kernel(const AttnK a, __nv_bfloat16* __restrict__ Pg, __nv_bfloat
   const int jend = active_keys(a, b, i0);
   const float c2 = a.scale * LOG2E;
   const float ks = DROP ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  const unsigned long long dseed = DROP ? seed_plus(a.drop_seed, a.seed_base) : 0ULL;
   const unsigned long long e0 = ((unsigned long long)bh * a.Tq + i) * a.Tk;
   __nv_bfloat16* prow = Pg + (bh * a.Tq + i) * (long long)Tkp + hf * 32;
   __nv_bfloat16* dsrow = DSg + (bh * a.Tq + i) * (long long)Tkp + hf * 32;
@@ -402,7 +404,7 @@ attn_rel_bwd_q_kernel(const AttnK a, __nv_bfloat16* __restrict__ Pg, __nv_bfloat
           const bool masked = j >= klen || (a.causal && j > i) || !row_ok;
           const float pj = masked ? 0.f : exp2f((s[e] + add[u]) * c2 - lse2);
           // dropout on the probabilities: d p = mask o d p~ ; the key/value side uses p~ = mask o p
-          const float mj = (DROP && !dropout_keep(a.drop_seed, e0 + (unsigned long long)j, a.drop_p)) ? 0.f : ks;
+          const float mj = (DROP && !dropout_keep(dseed, e0 + (unsigned long long)j, a.drop_p)) ? 0.f : ks;
           s[e] = pj * mj;
           dp[e] = pj * (dp[e] * mj - delta) * a.scale;
         }

@@ -26,6 +26,7 @@ struct AttnK {
   float *Pg, *DSg;  // CUDA-core path: fp32 scratch [B,H,Tq,Tk] each
   float drop_p;     // dropout on the attention probabilities (attention.py:81)
   unsigned long long drop_seed;
+  const unsigned long long* seed_base;  // optional device word added to drop_seed (graph-replayed steps)
 };
 
 int attention_rel_tc_fwd(const AttnK& k, cudaStream_t s);

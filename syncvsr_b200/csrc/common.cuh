@@ -233,6 +233,10 @@ struct StepCtl {
   const unsigned long long* seed = nullptr;
 };
 #ifdef __CUDACC__
+// step seed kept in device memory (graph replay): effective seed = site constant + *base; base == nullptr: the value as is
+__device__ __forceinline__ unsigned long long seed_plus(unsigned long long v, const unsigned long long* base) {
+  return base ? v + __ldg(base) : v;
+}
 __device__ __forceinline__ bool ctl_skipped(const StepCtl& c) { return c.skip && (__ldg(c.skip) & c.bit) != 0u; }
 __device__ __forceinline__ unsigned long long ctl_seed(const StepCtl& c, unsigned long long site) {
   return c.seed ? __ldg(c.seed) + site : site;

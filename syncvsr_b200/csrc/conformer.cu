@@ -342,7 +342,8 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
   }
 }
 __global__ void cast_scale_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4, float alpha,
-                                  float p, unsigned long long seed) {
+                                  float p, unsigned long long seed, const unsigned long long* seed_base) {
+  seed = seed_plus(seed, seed_base);
   const float ks = p > 0.f ? alpha / (1.0f - p) : alpha;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[i];
@@ -359,13 +360,15 @@ __global__ void cast_scale_kernel(const float* __restrict__ x, __nv_bfloat16* __
 }
 // y = dropout(x) (bf16 -> bf16), and dst(fp32) += dropout-mask * src(bf16): forward / backward of a stand-alone Dropout
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
-                                    float p, unsigned long long seed) {
+                                    float p, unsigned long long seed, const unsigned long long* seed_base) {
+  seed = seed_plus(seed, seed_base);
   const float ks = 1.0f / (1.0f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(dropout_keep(seed, (unsigned long long)i, p) ? __bfloat162float(x[i]) * ks : 0.f);
 }
 __global__ void dropout_add_kernel(float* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long n, float p,
-                                   unsigned long long seed) {
+                                   unsigned long long seed, const unsigned long long* seed_base) {
+  seed = seed_plus(seed, seed_base);
   const float ks = 1.0f / (1.0f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (dropout_keep(seed, (unsigned long long)i, p)) dst[i] += __bfloat162float(src[i]) * ks;
@@ -436,7 +439,8 @@ __global__ void rel_pos_table_kernel(__nv_bfloat16* __restrict__ pe, int T, int 
 }
 __global__ void embed_posenc_kernel(const long long* __restrict__ tok, const float* __restrict__ emb,
                                     float* __restrict__ x, int rows, int L, int D, int V, float p,
-                                    unsigned long long seed) {
+                                    unsigned long long seed, const unsigned long long* seed_base) {
+  seed = seed_plus(seed, seed_base);
   const long long total = (long long)rows * (D / 2);
   const float sc = sqrtf((float)D);
   const float ks = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -460,7 +464,9 @@ __global__ void embed_posenc_kernel(const long long* __restrict__ tok, const flo
   }
 }
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const float* __restrict__ dx,
-                                 float* __restrict__ demb, int rows, int D, int V, float p, unsigned long long seed) {
+                                 float* __restrict__ demb, int rows, int D, int V, float p, unsigned long long seed,
+                                 const unsigned long long* seed_base) {
+  seed = seed_plus(seed, seed_base);
   const long long total = (long long)rows * D;
   const float sc = sqrtf((float)D) * (p > 0.f ? 1.0f / (1.0f - p) : 1.0f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -678,7 +684,7 @@ __global__ void __launch_bounds__(256) attention_core_fwd_kernel(const AttnK a) 
       for (int j = lane; j < a.Tk; j += 32) {
         const float e = __expf(S[j] - m);
         sum += e;  // the softmax normaliser is taken before dropout
-        S[j] = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : e * ks;
+        S[j] = (a.drop_p > 0.f && !dropout_keep(seed_plus(a.drop_seed, a.seed_base), e0 + j, a.drop_p)) ? 0.f : e * ks;
       }
       sum = warp_sum(sum);
     } else {  // every key masked: the reference's re-masked softmax row is all zero (attention.py:72-77)
@@ -743,7 +749,7 @@ __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a
       const bool masked = j >= klen || (a.causal && j > i) || !row_ok;
       const float pj = masked ? 0.f : __expf(S[j] * a.scale - lse);
       // dropout mask on the probabilities: d p = mask * d p~ ; the key/value side uses p~ = mask * p
-      const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
+      const float mj = (a.drop_p > 0.f && !dropout_keep(seed_plus(a.drop_seed, a.seed_base), e0 + j, a.drop_p)) ? 0.f : ks;
       S[j] = pj;
       S2[j] *= mj;
       delta = fmaf(pj, S2[j], delta);
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(256) attention_core_bwd_q_kernel(const AttnK a
     for (int j = lane; j < a.Tk; j += 32) {
       const float pj = S[j];
       const float ds = pj * (S2[j] - delta) * a.scale;
-      const float mj = (a.drop_p > 0.f && !dropout_keep(a.drop_seed, e0 + j, a.drop_p)) ? 0.f : ks;
+      const float mj = (a.drop_p > 0.f && !dropout_keep(seed_plus(a.drop_seed, a.seed_base), e0 + j, a.drop_p)) ? 0.f : ks;
       S2[j] = ds;
       if (row_ok) Pg[j] = pj * mj, DSg[j] = ds;
     }
@@ -1203,23 +1209,23 @@ int add_f32(float* dst, const float* src, long long n, cudaStream_t s) {
   return SVSR_OK;
 }
 int cast_scale_f32_bf16(const float* x, __nv_bfloat16* y, long long n, float alpha, cudaStream_t s, float drop_p,
-                        unsigned long long drop_seed) {
+                        unsigned long long drop_seed, const unsigned long long* seed_base) {
   SVSR_REQUIRE(n % 4 == 0, "cast_scale: n must be a multiple of 4");
-  cast_scale_kernel<<<grid_for(n / 4, 256 * 2), 256, 0, s>>>(x, y, n / 4, alpha, drop_p, drop_seed);
+  cast_scale_kernel<<<grid_for(n / 4, 256 * 2), 256, 0, s>>>(x, y, n / 4, alpha, drop_p, drop_seed, seed_base);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, float p, unsigned long long seed,
-                 cudaStream_t s) {
+                 cudaStream_t s, const unsigned long long* seed_base) {
   SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
-  dropout_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n, p, seed);
+  dropout_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n, p, seed, seed_base);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int dropout_add_bf16_to_f32(float* dst, const __nv_bfloat16* src, long long n, float p, unsigned long long seed,
-                            cudaStream_t s) {
+                            cudaStream_t s, const unsigned long long* seed_base) {
   SVSR_REQUIRE(p > 0.f && p < 1.f, "dropout: p=%f out of (0,1)", p);
-  dropout_add_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(dst, src, n, p, seed);
+  dropout_add_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(dst, src, n, p, seed, seed_base);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -1250,15 +1256,16 @@ int rel_pos_table(__nv_bfloat16* pe, int T, int D, cudaStream_t s) {
   return SVSR_OK;
 }
 int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, int V, cudaStream_t s,
-                     float drop_p, unsigned long long drop_seed) {
+                     float drop_p, unsigned long long drop_seed, const unsigned long long* seed_base) {
   embed_posenc_kernel<<<grid_for((long long)rows * (D / 2), 256), 256, 0, s>>>(tok, emb, x, rows, L, D, V, drop_p,
-                                                                              drop_seed);
+                                                                              drop_seed, seed_base);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
 int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, int V, cudaStream_t s, float drop_p,
-              unsigned long long drop_seed) {
-  embed_bwd_kernel<<<grid_for((long long)rows * D, 256), 256, 0, s>>>(tok, dx, demb, rows, D, V, drop_p, drop_seed);
+              unsigned long long drop_seed, const unsigned long long* seed_base) {
+  embed_bwd_kernel<<<grid_for((long long)rows * D, 256), 256, 0, s>>>(tok, dx, demb, rows, D, V, drop_p, drop_seed,
+                                                                      seed_base);
   LAUNCH_CHECK();
   return SVSR_OK;
 }
@@ -1281,7 +1288,7 @@ int attn_fill(const AttnProblem& p, AttnK& k) {
   k.d_o = nullptr, k.dq = k.dk = k.dv = nullptr, k.lddq = k.lddk = k.lddv = 0;
   k.dp = k.dbu = k.dbv = k.Pg = k.DSg = nullptr;
   SVSR_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "attention: dropout %f out of [0,1)", p.drop_p);
-  k.drop_p = p.drop_p, k.drop_seed = p.drop_seed;
+  k.drop_p = p.drop_p, k.drop_seed = p.drop_seed, k.seed_base = p.seed_base;
   return SVSR_OK;
 }
 template <class K>

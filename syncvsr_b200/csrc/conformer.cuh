@@ -51,6 +51,7 @@ struct AttnProblem {
   int causal = 0;
   float drop_p = 0.f;  // dropout on the attention probabilities (attention.py:81); mask index ((b*H+h)*Tq+i)*Tk+j
   unsigned long long drop_seed = 0;
+  const unsigned long long* seed_base = nullptr;  // optional device word added to drop_seed (graph-replayed steps)
   int B = 0, H = 0, Tq = 0, Tk = 0;
   float scale = 0.125f;
   __nv_bfloat16* o = nullptr;  // [B*Tq, ldo]
@@ -76,10 +77,12 @@ size_t attention_scratch_bytes(int B, int H, int Tq, int Tk);
 // rel: row r of [2T-1, D] encodes relative position T-1-r (bf16, GEMM operand of linear_pos)
 int rel_pos_table(__nv_bfloat16* pe, int T, int D, cudaStream_t s);
 // decoder input: x[b,l,:] = emb[tok[b,l]] * sqrt(D) + pe_abs[l]   (fp32 stream) and its weight gradient (+=, atomics)
+// seed_base (every dropout entry below): optional device word added to the seed, so that a captured CUDA graph replays
+// with a new step seed (engine_lrs.cu, svsr_lrs_step_control)
 int embed_posenc_fwd(const long long* tok, const float* emb, float* x, int rows, int L, int D, int V, cudaStream_t s,
-                     float drop_p = 0.f, unsigned long long drop_seed = 0);
+                     float drop_p = 0.f, unsigned long long drop_seed = 0, const unsigned long long* seed_base = nullptr);
 int embed_bwd(const long long* tok, const float* dx, float* demb, int rows, int D, int V, cudaStream_t s,
-              float drop_p = 0.f, unsigned long long drop_seed = 0);
+              float drop_p = 0.f, unsigned long long drop_seed = 0, const unsigned long long* seed_base = nullptr);
 
 // ---- CTC (ctc.py:64-73,83-151: log_softmax + CTCLoss(reduction=sum, zero_infinity) / batch) ------------------------------
 // logits fp32 [B*T, ld] (V valid columns); labels int64 [B, Lmax] padded with -1; in_len int [B].
@@ -108,11 +111,12 @@ int meanpool_bf16_bwd(const __nv_bfloat16* df, __nv_bfloat16* dout, long long N,
 int add_f32(float* dst, const float* src, long long n, cudaStream_t s);                                 // dst += src
 // y = bf16(alpha * x * dropout_mask): the branch gradient of `residual + alpha * dropout(branch)`
 int cast_scale_f32_bf16(const float* x, __nv_bfloat16* y, long long n, float alpha, cudaStream_t s, float drop_p = 0.f,
-                        unsigned long long drop_seed = 0);
+                        unsigned long long drop_seed = 0, const unsigned long long* seed_base = nullptr);
 // stand-alone Dropout forward (bf16) and its backward accumulated into an fp32 gradient (dst += mask * src)
-int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, float p, unsigned long long seed, cudaStream_t s);
+int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, float p, unsigned long long seed, cudaStream_t s,
+                 const unsigned long long* seed_base = nullptr);
 int dropout_add_bf16_to_f32(float* dst, const __nv_bfloat16* src, long long n, float p, unsigned long long seed,
-                            cudaStream_t s);
+                            cudaStream_t s, const unsigned long long* seed_base = nullptr);
 int dropout_mask_u8(unsigned char* out, long long n, float p, unsigned long long seed, cudaStream_t s);  // tests
 int lengths_i64_to_i32(const long long* in, int* out, int n, int maxv, cudaStream_t s);                 // clamp to [0, maxv]
 

@@ -61,7 +61,21 @@ struct LrsEngine : EngineBase {
   unsigned long long last_seed = 0;
   float pd = 0.f, pa = 0.f;  // dropout probabilities in effect for the last forward (0 in eval mode)
   // per-site seeds: every Dropout module instance of the reference draws an independent mask
-  unsigned long long site(int id) const { return last_seed + 0x632BE59BD9B4E019ULL * (unsigned long long)(id + 1); }
+  // Device-resident step seed (svsr_lrs_step_control): with dev_ctl on, the step seed lives in the workspace word `ctl`
+  // and every dropout kernel adds it to its site constant on the device (seed_base()), so the launch arguments no longer
+  // depend on host RNG and ONE captured CUDA graph replays every step of the shipped dropout config. Same masks as the
+  // host-valued path for the same seed.
+  size_t ctl = 0;
+  bool dev_ctl = false;
+  unsigned long long site(int id) const {
+    return (dev_ctl ? 0ULL : last_seed) + 0x632BE59BD9B4E019ULL * (unsigned long long)(id + 1);
+  }
+  const unsigned long long* seed_base() const { return dev_ctl ? ws<unsigned long long>(ctl) : nullptr; }
+  StepCtl seed_ctl() const {
+    StepCtl c;
+    c.seed = seed_base();
+    return c;
+  }
   static int enc_site(int layer, int k) { return 16 * (layer + 1) + k; }        // k: 0 mac hidden, 1 mac out, 2 attn
   static int dec_site(int layer, int k) { return 16 * (layer + 65) + k; }       // probs, 3 attn out, 4 conv out, ...
   bool fwd_done = false;
@@ -106,7 +120,7 @@ void fused_ref(LinRef& l, long long w, long long bias, int N, int K, Bump& b) {
 
 int lin_fwd(const EngineBase& e, const bf16* x, int rows, const LinRef& l, void* out, int ldc, int out_fp32,
             const void* resid, float alpha, int relu, cudaStream_t s, float drop_p = 0.f,
-            unsigned long long drop_seed = 0) {
+            unsigned long long drop_seed = 0, const unsigned long long* seed_base = nullptr) {
   IgemmProblem p;
   p.a = x, p.a_N = rows, p.a_C = l.K, p.cin = l.K, p.ntaps = 1;
   p.o_N = rows;
@@ -116,6 +130,7 @@ int lin_fwd(const EngineBase& e, const bf16* x, int rows, const LinRef& l, void*
   p.resid = resid, p.resid_fp32 = 1;
   p.alpha = alpha, p.bias_scale = alpha, p.relu = relu;
   p.drop_p = drop_p, p.drop_seed = drop_seed;
+  p.ctl.seed = seed_base;  // the epilogue's mask seed = drop_seed + *seed_base (common.cuh ctl_seed)
   return igemm_launch(p, s);
 }
 // out[rows, K] = alpha * dy[rows, N (pitch ldy)] . W (+ resid fp32) (* [relu_mask > 0])
@@ -296,6 +311,7 @@ static int lrs_build(LrsEngine& e, long long nodecay_base) {
   e.feats = b.take((size_t)M * 512 * 2);
   e.pe_rel = b.take((size_t)(2 * T - 1) * D * 2);
   e.klen = b.take((size_t)c.B * sizeof(int));
+  e.ctl = b.take(16);
   e.xs = b.take((size_t)(5 * c.elayers + 1) * M * D * 4);
   e.enc_f32 = b.take((size_t)M * D * 4);
   e.enc_b = b.take((size_t)M * D * 2);
@@ -397,10 +413,10 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   RC(meanpool_bf16(f4, e.ws<bf16>(e.feats), M, HW4, 512, s));
   // ---- embed: Linear + x * sqrt(D) (encoder.py:170-174; embedding.py:212) ----
-  RC(lin_fwd(e, e.ws<bf16>(e.feats), M, e.embed, e.xs_buf(0), D, 1, nullptr, sqrtf((float)D), 0, s, pd, e.site(1)));
+  RC(lin_fwd(e, e.ws<bf16>(e.feats), M, e.embed, e.xs_buf(0), D, 1, nullptr, sqrtf((float)D), 0, s, pd, e.site(1), e.seed_base()));
   const bf16* pe = e.ws<bf16>(e.pe_rel);
   if (pd > 0.f) {  // the dropped pos_emb tensor is shared by every block (embedding.py:217)
-    RC(dropout_bf16(pe, e.ws<bf16>(e.pe_drop), (long long)(2 * T - 1) * D, pd, e.site(2), s));
+    RC(dropout_bf16(pe, e.ws<bf16>(e.pe_drop), (long long)(2 * T - 1) * D, pd, e.site(2), s, e.seed_base()));
     pe = e.ws<bf16>(e.pe_drop);
   }
   // ---- Conformer blocks (encoder_layer.py:76-150) ----
@@ -411,8 +427,8 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
     // macaron feed-forward, scaled by 1/2
     RC(ln_fwd(e, x0, L.n_mac, e.ws<bf16>(L.yn[0]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[0]), M, L.mac1, e.ws<bf16>(L.h_mac), F, 0, nullptr, 1.f, 1, s, pd,
-               e.site(LrsEngine::enc_site(i, 0))));
-    RC(lin_fwd(e, e.ws<bf16>(L.h_mac), M, L.mac2, x1, D, 1, x0, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 1))));
+               e.site(LrsEngine::enc_site(i, 0)), e.seed_base()));
+    RC(lin_fwd(e, e.ws<bf16>(L.h_mac), M, L.mac2, x1, D, 1, x0, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 1)), e.seed_base()));
     // relative-position multi-head self-attention (attention.py:192-278)
     RC(ln_fwd(e, x1, L.n_mha, e.ws<bf16>(L.yn[1]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[1]), M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * D, 0, nullptr, 1.f, 0, s));
@@ -425,10 +441,10 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
       a.klen = e.ws<int>(e.klen);
       a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
       a.o = e.ws<bf16>(L.ctx), a.ldo = D, a.lse = e.ws<float>(L.lse);
-      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2)), a.seed_base = e.seed_base();
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(L.ctx), M, L.out, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 3))));
+    RC(lin_fwd(e, e.ws<bf16>(L.ctx), M, L.out, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 3)), e.seed_base()));
     // convolution module (convolution.py:56-75)
     RC(ln_fwd(e, x2, L.n_conv, e.ws<bf16>(L.yn[2]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[2]), M, L.pw1, e.ws<bf16>(L.hpw1), 2 * D, 0, nullptr, 1.f, 0, s));
@@ -438,12 +454,12 @@ static int lrs_encoder_forward(LrsEngine& e, const float* x, const long long* le
     if (train) RC(bn_col_reduce(e.ws<bf16>(L.dwo), nullptr, nullptr, M, D, e.ws<double>(L.bn.stats_f), 0, s));
     RC(bn_fwd(e, e.ws<bf16>(L.dwo), M, L.bn, train, s));
     RC(bn_apply(e.ws<bf16>(L.dwo), e.ws<float>(L.bn.coef), nullptr, nullptr, 2, e.ws<bf16>(L.act), M, D, s));
-    RC(lin_fwd(e, e.ws<bf16>(L.act), M, L.pw2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 4))));
+    RC(lin_fwd(e, e.ws<bf16>(L.act), M, L.pw2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::enc_site(i, 4)), e.seed_base()));
     // feed-forward, scaled by 1/2, and the block's final LayerNorm
     RC(ln_fwd(e, x3, L.n_ff, e.ws<bf16>(L.yn[3]), nullptr, M, s));
     RC(lin_fwd(e, e.ws<bf16>(L.yn[3]), M, L.ff1, e.ws<bf16>(L.h_ff), F, 0, nullptr, 1.f, 1, s, pd,
-               e.site(LrsEngine::enc_site(i, 5))));
-    RC(lin_fwd(e, e.ws<bf16>(L.h_ff), M, L.ff2, x4, D, 1, x3, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 6))));
+               e.site(LrsEngine::enc_site(i, 5)), e.seed_base()));
+    RC(lin_fwd(e, e.ws<bf16>(L.h_ff), M, L.ff2, x4, D, 1, x3, 0.5f, 0, s, pd, e.site(LrsEngine::enc_site(i, 6)), e.seed_base()));
     RC(ln_fwd(e, x4, L.n_fin, nullptr, x5, M, s));
   }
   return ln_fwd(e, e.xs_buf(5 * c.elayers), e.after, e.ws<bf16>(e.enc_b), e.ws<float>(e.enc_f32), M, s);
@@ -481,7 +497,7 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
   // ---- CTC (ctc.py:83-151) ----
   const bf16* enc_ctc = enc_b;  // ctc_lo(dropout(hs_pad)), ctc.py:97
   if (pd > 0.f) {
-    RC(dropout_bf16(enc_b, e.ws<bf16>(e.enc_ctc), (long long)M * D, pd, e.site(3), s));
+    RC(dropout_bf16(enc_b, e.ws<bf16>(e.enc_ctc), (long long)M * D, pd, e.site(3), s, e.seed_base()));
     enc_ctc = e.ws<bf16>(e.enc_ctc);
   }
   RC(lin_fwd(e, enc_ctc, M, e.ctc, e.ws<float>(e.logits_c), e.ldv, 1, nullptr, 1.f, 0, s));
@@ -494,7 +510,7 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
   add_sos_eos_kernel<<<(c.B + 63) / 64, 64, 0, s>>>(label, Llab, ys_in, ys_out, c.B, c.odim - 1, c.odim - 1);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
-  RC(embed_posenc_fwd(ys_in, e.P + e.dec_emb, e.xd_buf(0), Md, L, D, c.odim, s, pd, e.site(4)));
+  RC(embed_posenc_fwd(ys_in, e.P + e.dec_emb, e.xd_buf(0), Md, L, D, c.odim, s, pd, e.site(4), e.seed_base()));
   for (int i = 0; i < c.dlayers; ++i) {
     DecLayerRef& Ld = e.dec[i];
     float *x0 = e.xd_buf(3 * i), *x1 = e.xd_buf(3 * i + 1), *x2 = e.xd_buf(3 * i + 2), *x3 = e.xd_buf(3 * i + 3);
@@ -506,10 +522,10 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
       a.causal = 1;
       a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
       a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
-      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0)), a.seed_base = e.seed_base();
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, x1, D, 1, x0, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 1))));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, x1, D, 1, x0, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 1)), e.seed_base()));
     RC(ln_fwd(e, x1, Ld.n2, e.ws<bf16>(Ld.yn[1]), nullptr, Md, s));
     RC(lin_fwd(e, e.ws<bf16>(Ld.yn[1]), Md, Ld.q_c, e.ws<bf16>(Ld.qc), D, 0, nullptr, 1.f, 0, s));
     RC(lin_fwd(e, enc_b, M, Ld.kv_c, e.ws<bf16>(Ld.kvc), 2 * D, 0, nullptr, 1.f, 0, s));
@@ -520,14 +536,14 @@ static int lrs_forward(LrsEngine& e, const float* x, const long long* lengths, c
       a.klen = e.ws<int>(e.klen);
       a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
       a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
-      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
+      a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2)), a.seed_base = e.seed_base();
       RC(attention_core_fwd(a, s));
     }
-    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 3))));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, x2, D, 1, x1, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 3)), e.seed_base()));
     RC(ln_fwd(e, x2, Ld.n3, e.ws<bf16>(Ld.yn[2]), nullptr, Md, s));
     RC(lin_fwd(e, e.ws<bf16>(Ld.yn[2]), Md, Ld.ff1, e.ws<bf16>(Ld.h), Fd, 0, nullptr, 1.f, 1, s, pd,
-               e.site(LrsEngine::dec_site(i, 4))));
-    RC(lin_fwd(e, e.ws<bf16>(Ld.h), Md, Ld.ff2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 5))));
+               e.site(LrsEngine::dec_site(i, 4)), e.seed_base()));
+    RC(lin_fwd(e, e.ws<bf16>(Ld.h), Md, Ld.ff2, x3, D, 1, x2, 1.f, 0, s, pd, e.site(LrsEngine::dec_site(i, 5)), e.seed_base()));
   }
   RC(ln_fwd(e, e.xd_buf(3 * c.dlayers), e.dec_after, e.ws<bf16>(e.dec_yn), nullptr, Md, s));
   RC(lin_fwd(e, e.ws<bf16>(e.dec_yn), Md, e.outl, e.ws<float>(e.pred), e.ldv, 1, nullptr, 1.f, 0, s));
@@ -621,7 +637,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
     if (pd > 0.f) {  // through the Dropout in front of ctc_lo
       RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, e.ws<bf16>(e.enc_ctc), M, e.ctc, w));
       RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, t.gD[1], D, 0, nullptr, 1.f, nullptr, s));
-      RC(dropout_add_bf16_to_f32(dx, t.gD[1], (long long)M * D, pd, e.site(3), s));
+      RC(dropout_add_bf16_to_f32(dx, t.gD[1], (long long)M * D, pd, e.site(3), s, e.seed_base()));
     } else {
       RC(linear_wgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, enc_b, M, e.ctc, w));
       RC(lin_dgrad(e, e.ws<bf16>(e.dlogits_c), e.ldv, M, e.ctc, dx, D, 1, dx, 1.f, nullptr, s));
@@ -645,13 +661,13 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
       float *x0 = e.xd_buf(3 * i), *x1 = e.xd_buf(3 * i + 1), *x2 = e.xd_buf(3 * i + 2);
       {  // unit: feed-forward
         const LrsScratch t = lrs_scratch(e, sq.unit);
-        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 5))));
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 5)), e.seed_base()));
         RC(ffn_bwd(e, sq, t, t.ddxb, Md, Ld.ff1, Ld.ff2, e.ws<bf16>(Ld.h), e.ws<bf16>(Ld.yn[2]), x2, Ld.n3, ddx, Fd, s));
       }
       {  // unit: source attention over the encoder output
         const LrsScratch t = lrs_scratch(e, sq.unit);
         bf16 *dyn = t.gD[0], *dctx = t.gD[1], *dq = t.gD[2], *dkv = t.dkv;
-        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 3))));
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 3)), e.seed_base()));
         RC(sq.fork());
         RC(linear_wgrad(e, t.ddxb, D, e.ws<bf16>(Ld.ctx_c), Md, Ld.out_c, w));
         RC(lin_dgrad(e, t.ddxb, D, Md, Ld.out_c, dctx, D, 0, nullptr, 1.f, nullptr, s));
@@ -662,7 +678,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
           a.klen = e.ws<int>(e.klen);
           a.B = c.B, a.H = H, a.Tq = L, a.Tk = T, a.scale = 0.125f;
           a.o = e.ws<bf16>(Ld.ctx_c), a.ldo = D, a.lse = e.ws<float>(Ld.lse_c);
-          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2));
+          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 2)), a.seed_base = e.seed_base();
           AttnGrads g;
           g.d_o = dctx, g.dq = dq, g.lddq = D, g.dk = dkv, g.dv = dkv + D, g.lddk = g.lddv = 2 * D;
           g.scratch = e.ws<float>(e.attn_scratch);
@@ -679,7 +695,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
       {  // unit: causal self-attention
         const LrsScratch t = lrs_scratch(e, sq.unit);
         bf16 *dyn = t.gD[0], *dctx = t.gD[1], *dqkv = t.g3D;
-        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 1))));
+        RC(cast_scale_f32_bf16(ddx, t.ddxb, (long long)Md * D, 1.f, s, pd, e.site(LrsEngine::dec_site(i, 1)), e.seed_base()));
         RC(sq.fork());
         RC(linear_wgrad(e, t.ddxb, D, e.ws<bf16>(Ld.ctx_s), Md, Ld.out_s, w));
         RC(lin_dgrad(e, t.ddxb, D, Md, Ld.out_s, dctx, D, 0, nullptr, 1.f, nullptr, s));
@@ -689,7 +705,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
           a.causal = 1;
           a.B = c.B, a.H = H, a.Tq = L, a.Tk = L, a.scale = 0.125f;
           a.o = e.ws<bf16>(Ld.ctx_s), a.ldo = D, a.lse = e.ws<float>(Ld.lse_s);
-          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0));
+          a.drop_p = pa, a.drop_seed = e.site(LrsEngine::dec_site(i, 0)), a.seed_base = e.seed_base();
           AttnGrads g;
           g.d_o = dctx, g.dq = dqkv, g.dk = dqkv + D, g.dv = dqkv + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
           g.scratch = e.ws<float>(e.attn_scratch);
@@ -702,7 +718,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
         RC(sq.end_unit());
       }
     }
-    RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s, pd, e.site(4)));
+    RC(embed_bwd(e.ws<long long>(e.ys_in), ddx, e.G + e.dec_emb, Md, D, c.odim, s, pd, e.site(4), e.seed_base()));
   }
   if (stage == 0) return sq.join();
   }  // stage <= 0
@@ -717,13 +733,13 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
     RC(ln_bwd(e, nullptr, dx, x4, Lc.n_fin, dx, 0, M, s));
     {  // unit: feed-forward (x 1/2)
       const LrsScratch t = lrs_scratch(e, sq.unit);
-      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 6))));
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 6)), e.seed_base()));
       RC(ffn_bwd(e, sq, t, t.dxb, M, Lc.ff1, Lc.ff2, e.ws<bf16>(Lc.h_ff), e.ws<bf16>(Lc.yn[3]), x3, Lc.n_ff, dx, F, s));
     }
     {  // unit: convolution module
       const LrsScratch t = lrs_scratch(e, sq.unit);
       bf16 *dyn = t.gD[0], *t1 = t.gD[1], *t2 = t.gD[2], *g3 = t.g3D;
-      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 4))));
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 4)), e.seed_base()));
       RC(sq.fork());
       RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(Lc.act), M, Lc.pw2, w));
       RC(lin_dgrad(e, t.dxb, D, M, Lc.pw2, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d act
@@ -745,7 +761,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
     {  // unit: relative-position self-attention
       const LrsScratch t = lrs_scratch(e, sq.unit);
       bf16 *dyn = t.gD[0], *t1 = t.gD[1], *g3 = t.g3D;
-      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 3))));
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 1.f, s, pd, e.site(LrsEngine::enc_site(i, 3)), e.seed_base()));
       RC(sq.fork());
       RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(Lc.ctx), M, Lc.out, w));
       RC(lin_dgrad(e, t.dxb, D, M, Lc.out, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d ctx
@@ -757,7 +773,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
         a.klen = e.ws<int>(e.klen);
         a.B = c.B, a.H = H, a.Tq = T, a.Tk = T, a.scale = 0.125f;
         a.o = e.ws<bf16>(Lc.ctx), a.ldo = D, a.lse = e.ws<float>(Lc.lse);
-        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2));
+        a.drop_p = pa, a.drop_seed = e.site(LrsEngine::enc_site(i, 2)), a.seed_base = e.seed_base();
         AttnGrads g;
         g.d_o = t1, g.dq = g3, g.dk = g3 + D, g.dv = g3 + 2 * D, g.lddq = g.lddk = g.lddv = 3 * D;
         g.dp = e.ws<float>(e.dp), g.dbias_u = e.G + Lc.bias_u, g.dbias_v = e.G + Lc.bias_v;
@@ -775,7 +791,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
     }
     {  // unit: macaron feed-forward (x 1/2)
       const LrsScratch t = lrs_scratch(e, sq.unit);
-      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 1))));
+      RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, 0.5f, s, pd, e.site(LrsEngine::enc_site(i, 1)), e.seed_base()));
       RC(ffn_bwd(e, sq, t, t.dxb, M, Lc.mac1, Lc.mac2, e.ws<bf16>(Lc.h_mac), e.ws<bf16>(Lc.yn[0]), x0, Lc.n_mac, dx, F, s));
     }
   }
@@ -785,7 +801,7 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
   // ---- unit: embed (x * sqrt(D)) -> average pool; then the frontend ----
   {
     const LrsScratch t = lrs_scratch(e, sq.unit);
-    RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, sqrtf((float)D), s, pd, e.site(1)));
+    RC(cast_scale_f32_bf16(dx, t.dxb, (long long)M * D, sqrtf((float)D), s, pd, e.site(1), e.seed_base()));
     RC(sq.fork());
     RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(e.feats), M, e.embed, w));
     RC(lin_dgrad(e, t.dxb, D, M, e.embed, e.ws<bf16>(e.dfeat), 512, 0, nullptr, 1.f, nullptr, s));
@@ -881,6 +897,14 @@ int svsr_lrs_backward_stage(void* h, const float* grad_scale, int stage, void* s
   SVSR_REQUIRE(e->WS, "lrs: bind() first");
   SVSR_REQUIRE(stage >= 0 && stage <= 2, "lrs_backward_stage: stage must be 0, 1 or 2");
   return lrs_backward(*e, grad_scale, stage, static_cast<cudaStream_t>(stream));
+}
+int svsr_lrs_step_control(void* h, int mode, uint64_t dropout_seed, void* stream) {
+  LrsEngine* e = static_cast<LrsEngine*>(h);
+  SVSR_REQUIRE(e->WS, "lrs: bind() first");
+  e->dev_ctl = mode != 0;
+  if (!e->dev_ctl) return SVSR_OK;
+  return set_step_ctl(e->ws<unsigned>(e->ctl + 8), e->ws<unsigned long long>(e->ctl), 0u, (unsigned long long)dropout_seed,
+                      static_cast<cudaStream_t>(stream));
 }
 // The step never writes the audio logits to HBM (fused head); materialise them once, on request (svsr_lrs_tensor
 // "logits_audio"), from the last forward's encoder output.

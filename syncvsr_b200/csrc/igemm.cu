@@ -328,7 +328,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float ks = 1.0f / (1.0f - p.drop_p);
           const unsigned long long e0 = (unsigned long long)(row_off + col0);
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) f[jj] = dropout_keep(p.drop_seed, e0 + jj, p.drop_p) ? f[jj] * ks : 0.f;
+          for (int jj = 0; jj < 32; ++jj) f[jj] = dropout_keep(ctl_seed(p.ctl, p.drop_seed), e0 + jj, p.drop_p) ? f[jj] * ks : 0.f;
         }
         if (p.resid && row_valid) {
           if (p.resid_fp32) {

@@ -314,6 +314,27 @@ class E2E(nn.Module):
             return 0
         return self.dropout_seed if self.dropout_seed is not None else random.getrandbits(63)
 
+    def _apply_step_seed(self, seed: Optional[int]) -> None:
+        """Device-resident step seed (svsr_lrs_step_control): seed = this step's dropout seed written to the engine's
+        control word on the current stream -- every dropout site then reads it from device memory, which is what lets
+        train.SentenceDataParallelStep replay ONE CUDA graph under the shipped dropout config. None: host-valued again."""
+        check(lib().svsr_lrs_step_control(self._h, C.c_int(0 if seed is None else 1), C.c_uint64(seed or 0), self._stream()),
+              "svsr_lrs_step_control")
+        if self._ent is not None:
+            self._ent.dev_seed = seed is not None
+
+    def _seed_arg(self) -> int:
+        """The step's dropout seed. An engine switched to the device-resident seed ignores the argument: a step launched
+        kernel by kernel on such an engine refreshes the device word first (never inside a graph capture, where the
+        caller sets it per replay)."""
+        dev = self._ent is not None and self._ent.dev_seed
+        if dev and torch.cuda.is_current_stream_capturing():
+            return 0  # ignored by the engine; nothing is drawn, so the host RNG stream stays one draw per step
+        seed = self._step_seed()
+        if dev:
+            self._apply_step_seed(seed)
+        return seed
+
     def attach_codec(self, fn) -> None:
         """`fn(audios [B, samples]) -> int64 tokens [B, Ta, G]`: the frozen neural audio quantiser of
         e2e_asr_transformer.py:167-180 (wav2vec 2.0 / vq-wav2vec). It is off the gradient path and needs pretrained
@@ -336,7 +357,7 @@ class E2E(nn.Module):
             lengths = masks.to(self.device_).reshape(B, -1).sum(-1).long().contiguous()
         check(lib().svsr_lrs_encode(self._h, C.c_void_p(xs.data_ptr()),
                                     C.c_void_p(lengths.data_ptr() if lengths is not None else 0),
-                                    C.c_int(int(self.training)), C.c_uint64(self._step_seed()), self._stream()),
+                                    C.c_int(int(self.training)), C.c_uint64(self._seed_arg()), self._stream()),
               "svsr_lrs_encode")
         if self.training:
             self._nbt += 1
@@ -366,7 +387,7 @@ class E2E(nn.Module):
             self._h, C.c_void_p(x.data_ptr()), C.c_void_p(lengths.data_ptr()),
             C.c_void_p(tokens.data_ptr() if tokens is not None else 0),
             C.c_int64(tokens.stride(0) if tokens is not None else 0), C.c_void_p(label.data_ptr()),
-            C.c_int(int(label.shape[1])), C.c_int(int(self.training)), C.c_uint64(self._step_seed()),
+            C.c_int(int(label.shape[1])), C.c_int(int(self.training)), C.c_uint64(self._seed_arg()),
             C.c_void_p(self._metrics.data_ptr()), self._stream()), "svsr_lrs_forward")
         self._last_BL = (B, int(label.shape[1]) + 1)
         if self.training:

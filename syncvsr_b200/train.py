@@ -338,9 +338,9 @@ class SentenceDataParallelStep:
                  staged: Optional[bool] = None, graph: bool = False):
         """graph=True: zero_grad + weight repack + forward + backward (~1 250 launches on two streams) are captured once per
         set of input buffers and clip geometry into a CUDA graph (three under torchrun, cut at the backward stages so that
-        each all-reduce still overlaps the next stage) and replayed. Only with dropout_rate = transformer_attn_dropout_rate
-        = 0: the LRS kernels take their dropout seeds as launch arguments, so a step with dropout launches kernel by
-        kernel."""
+        each all-reduce still overlaps the next stage) and replayed. With dropout (the shipped lrs2/lrs3.yaml: 0.1 / 0.1)
+        the step seed is drawn on the host as before but handed over in device memory (svsr_lrs_step_control): every
+        dropout site adds it to its own constant on the device, so the same graph serves every step."""
         self.module, self.opt, self.group = module, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.warmup, self.total, self.global_step = warmup, total, 0
@@ -365,8 +365,12 @@ class SentenceDataParallelStep:
 
     def _replayable(self, x, label) -> bool:
         m = self.module
-        return (self.graph and m.training and m.dropout_rate == 0.0 and m.attn_dropout_rate == 0.0
+        return (self.graph and m.training
                 and m._shape_key == (x.shape[0], x.shape[1], x.shape[3], x.shape[4]) and label.shape[1] + 1 <= m._lmax)
+
+    def _stochastic(self) -> bool:
+        m = self.module
+        return m.dropout_rate > 0.0 or m.attn_dropout_rate > 0.0
 
     def _capture(self, batch) -> dict:
         m = self.module
@@ -374,6 +378,8 @@ class SentenceDataParallelStep:
         cap.wait_stream(torch.cuda.current_stream())
         n0 = lib().svsr_launch_count()
         graphs, pool, out = [], None, None
+        if self._stochastic():  # the engine switches to the device-resident step seed (kept for this engine's lifetime)
+            m._apply_step_seed(0)  # (the value is set per replay; nothing is drawn from the host RNG here)
         for part in ((0, 1, 2) if self.staged else (-1,)):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=cap, capture_error_mode="thread_local"):
@@ -419,6 +425,8 @@ class SentenceDataParallelStep:
             ent = self._graph_entry((x, lengths, audios, label))
         if ent is not None:
             graphs = ent["graphs"]
+            if self._stochastic():
+                m._apply_step_seed(m._step_seed())  # this step's masks: host RNG like the reference, read on the device
             graphs[0].replay()
             if self.staged:
                 hs = self._reduce(0)
