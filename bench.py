@@ -649,11 +649,11 @@ def run_native_arm(args):
     achieved_tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
     share = {k: round(v["ms"] / ms_prof_total, 4) for k, v in prof.items()}
     traffic, traffic_src = None, None
-    tp = ROOT / "profiles" / "r1_traffic.json"  # dram__bytes_read+write per launch from one ncu pass (tools/ncu_traffic.py)
+    tp = ROOT / "profiles" / "r2_traffic.json"  # dram__bytes_read+write per launch from one ncu pass (tools/ncu_traffic.py)
     if tp.exists():
         fam = json.loads(tp.read_text()).get("families", {}).get(dom)
         if fam:
-            traffic, traffic_src = fam["dram_bytes_per_launch"], "profiles/r1_traffic.json (ncu dram__bytes, avg per launch)"
+            traffic, traffic_src = fam["dram_bytes_per_launch"], "profiles/r2_traffic.json (ncu dram__bytes, avg per launch)"
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
