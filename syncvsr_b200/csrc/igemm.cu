@@ -699,6 +699,10 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   int BN = p.b_rows <= 64 ? 64 : (p.b_rows <= 128 ? 128 : 256);
   if (BN == 256 && m_tiles * ((p.b_rows + 255) / 256) < 100) BN = 128;
   if (BN == 128 && m_tiles * ((p.b_rows + 127) / 128) < 100 && !p.ce.mode) BN = 64;
+  if (const char* force = getenv("SVSR_IGEMM_BN")) {  // measurement only (tools/gemm_bench.py): override the N tile
+    const int f = atoi(force);
+    if ((f == 64 || f == 128 || f == 256) && !(p.ce.mode && f == 64)) BN = f;
+  }
   {
     uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
     uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
