@@ -44,10 +44,11 @@ struct IgemmKParams {
 
 // A pipeline stage holds KPS consecutive 64-wide k-blocks (A sub-tile + B sub-tile each): one mbarrier round trip
 // (~200 cycles of issue-side latency) is then amortised over 4*KPS MMAs, which matters when N is small.
-template <int BN, int STAGES, int KPS>
+// CG = 2 (CTA pair, cta_group::2): a CTA stages its own 128 rows of A and HALF of the B tile.
+template <int BN, int STAGES, int KPS, int CG = 1>
 struct IgemmSmem {
   static constexpr int A_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16 (one 128B swizzle row each)
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = BN / CG * 128;
   static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = KPS * SUB_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
@@ -84,14 +85,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 constexpr int IGEMM_THREADS = 320;
 
-template <int BN, int STAGES, int KPS, bool BNB>
+template <int BN, int STAGES, int KPS, bool BNB, int CG = 1>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmKParams p) {
   if (ctl_skipped(p.ctl)) return;  // sublayer dropped this step (device-resident layer_dropout mask)
+  // CG = 2: the two CTAs of a (2,1,1) cluster work on M-tiles (2 t, 2 t + 1) of the same column tile as ONE M = 256 MMA:
+  // each stages its own A box and half of the B tile, the leader (rank 0) issues the MMAs and multicasts the commits,
+  // both drain their own 128 accumulator rows with the unchanged epilogue.
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int cta = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ncta = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // Persistent: CTA c processes tiles c, c + gridDim.x, ... The TMA warp runs ahead across tile boundaries, the MMA
   // warp alternates between two TMEM accumulators, and the epilogue of tile j overlaps the MMAs of tile j+1.
-  using L = IgemmSmem<BN, STAGES, KPS>;
+  using L = IgemmSmem<BN, STAGES, KPS, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET2);
@@ -106,7 +113,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = p.ntaps * p.cblocks;
-  const int m_tiles = p.m_tiles;
+  const int m_tiles = (p.m_tiles + CG - 1) / CG;  // (pairs of) M-tiles per column tile
   const int total_tiles = m_tiles * p.n_tiles;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
@@ -120,15 +127,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader's)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   if (p.bn_stats || BNB)
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_stats[i] = 0.f;
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -136,8 +147,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+      for (int tile = cta; tile < total_tiles; tile += ncta) {
+        const int nt = tile / m_tiles, mt = CG * (tile - nt * m_tiles) + rank;  // (an odd tail tile: boxes out of range = zeros)
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -145,16 +156,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb0 = 0; kb0 < num_kb; kb0 += KPS) {
           const int nk = min(KPS, num_kb - kb0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)(nk * (p.a_box_bytes + L::B_BYTES)));
+          // pair: the leader's barrier counts the bytes of BOTH CTAs' loads
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(nk * CG * (p.a_box_bytes + L::B_BYTES)));
           for (int u = 0; u < nk; ++u) {
             const int kb = kb0 + u;
             const int tap = kb / p.cblocks;
             const int cc = kb - tap * p.cblocks;
             uint8_t* sA = smem + stage * L::STAGE_BYTES + u * L::SUB_BYTES;
             uint8_t* sB = sA + L::A_BYTES;
-            tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
-                        oh0 * p.stride + p.tap_dh[tap], n0);
-            tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+            if (CG == 2) {
+              tma_load_4d_2sm(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
+                              oh0 * p.stride + p.tap_dh[tap], n0);
+              tma_load_2d_2sm(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN + rank * (BN / 2));
+            } else {
+              tma_load_4d(sA, &tmA, &full_bar[stage], p.a_coff + cc * 64, ow0 * p.stride + p.tap_dw[tap],
+                          oh0 * p.stride + p.tap_dh[tap], n0);
+              tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_kbase[tap] + cc * 64, nt * BN);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -165,12 +183,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    if (lane == 0 && rank == 0) {  // pair: only the leader issues MMAs (for both CTAs' accumulators)
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;  // local tile counter
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      for (int tile = cta; tile < total_tiles; tile += ncta, ++j) {
         const int acc = j & 1;
         const uint32_t use = (uint32_t)(j >> 1);
         mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator
@@ -188,16 +206,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb0 | u | k) != 0);
+              if (CG == 2) umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb0 | u | k) != 0);
+              else umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb0 | u | k) != 0);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+          if (CG == 2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
     __syncwarp();
@@ -227,8 +249,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool do_staged_stats = p.bn_stats && p.tma_store && (!SHARED_TILE || grp == 0);
     float ce_scale = 1.f;
     if (p.ce.mode == 2) ce_scale = p.ce.dscale * (p.ce.grad_scale ? __ldg(p.ce.grad_scale) : 1.f);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-      const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+    for (int tile = cta; tile < total_tiles; tile += ncta, ++j) {
+      const int nt = tile / m_tiles, mt = CG * (tile - nt * m_tiles) + rank;
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -544,7 +566,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
     if (p.tma_store && leader) tma_store_wait_all();  // smem must outlive the last bulk store
     if (do_staged_stats && stat_nt >= 0) {
@@ -585,8 +610,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) {
+    cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the peer's MMAs / remote arrives can still touch it
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,6 +653,27 @@ static int launch_tb(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   igemm_kernel<BN, STAGES, KPS, BNB><<<grid, IGEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, kp);
   note_launch();
   SVSR_CHECK_CUDA(cudaGetLastError());
+  return SVSR_OK;
+}
+// CTA pairs (cta_group::2): a (2,1,1) cluster per pair of M-tiles, `pairs` clusters
+template <int BN, int STAGES, int KPS>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmKParams& kp,
+                       int pairs, cudaStream_t stream) {
+  using L = IgemmSmem<BN, STAGES, KPS, 2>;
+  auto kernel = igemm_kernel<BN, STAGES, KPS, false, 2>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs)), cfg.blockDim = dim3(IGEMM_THREADS), cfg.dynamicSmemBytes = L::TOTAL, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  SVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, kp));
+  note_launch();
   return SVSR_OK;
 }
 // (the fused BatchNorm-backward statistics are a separate instantiation: the common launches carry none of their registers)
@@ -703,10 +754,16 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     const int f = atoi(force);
     if ((f == 64 || f == 128 || f == 256) && !(p.ce.mode && f == 64)) BN = f;
   }
+  // CTA pairs (cta_group::2, M = 256 MMAs; SVSR_IGEMM_2CTA=0 turns them off): each CTA of a pair stages half of the B tile
+  static const bool pair_env = [] {
+    const char* e = getenv("SVSR_IGEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = pair_env && BN >= 128 && !p.ce.mode && !p.bnb.n && m_tiles >= 2;
   {
     uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
     uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
-    uint32_t box[2] = {64, (uint32_t)BN};
+    uint32_t box[2] = {64, (uint32_t)(pair ? BN / 2 : BN)};
     int rc = make_tmap_bf16(&tmB, p.b, 2, dims, strides, box, nullptr, true);
     if (rc) return rc;
   }
@@ -741,6 +798,14 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
                                         : 2.0 * p.o_N * p.OH * p.OW * (double)p.b_rows * p.ntaps * p.cin;
   prof_begin(PROF_IGEMM, flops, stream);
   int rc;
+  if (pair) {
+    const long long pair_tiles = (m_tiles + 1) / 2 * kp.n_tiles;
+    const int pairs = (int)(pair_tiles < 74 ? pair_tiles : 74);
+    rc = BN == 128 ? launch_pair<128, 3, 2>(tmA, tmB, tmC, kp, pairs, stream)   // 3 x 2 x (16 + 8) KB
+                   : launch_pair<256, 4, 1>(tmA, tmB, tmC, kp, pairs, stream);  // 4 x (16 + 16) KB
+    prof_end(stream);
+    return rc;
+  }
   switch (BN) {
     case 64: rc = launch_t<64, 3, 2>(tmA, tmB, tmC, kp, grid, stream); break;    // 3 x 48 KB
     case 128: rc = launch_t<128, 2, 2>(tmA, tmB, tmC, kp, grid, stream); break;  // 2 x 64 KB

@@ -23,21 +23,24 @@ struct WgradKParams {
   StepCtl ctl;
 };
 
-template <int BN, int STAGES>
+// CG = 2 (CTA pair, cta_group::2): the pair's MMA covers two 128-row blocks of D (one per CTA) against ONE gradient tile whose
+// 64-channel blocks are split between the two CTAs.
+template <int BN, int STAGES, int CG = 1>
 struct WgradSmem {
   static constexpr int BLK = 128 * 128;  // one 64-channel block: 128 pixel rows x 128 B
   static constexpr int A_BYTES = 2 * BLK;
-  static constexpr int B_BYTES = (BN / 64) * BLK;
+  static constexpr int B_BYTES = (BN / 64 / CG) * BLK;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradKParams p) {
   if (ctl_skipped(p.ctl)) return;
-  using L = WgradSmem<BN, STAGES>;
+  using L = WgradSmem<BN, STAGES, CG>;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -47,11 +50,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mb0 = blockIdx.x * p.mb_per_cta;  // first 128-row block of D handled here
+  // CG = 1: this CTA owns blocks mb0 .. mb0 + mb_cnt - 1. CG = 2: the pair owns block PAIRS, MMA i of the pair covers blocks
+  // mb0 + 2 i (leader's accumulator rows) and mb0 + 2 i + 1 (peer's); block_of(i) is this CTA's block
+  const int mb0 = (int)(blockIdx.x / CG) * p.mb_per_cta * CG;
   const int nb = blockIdx.y;
   const int split = blockIdx.z, nsplit = gridDim.z;
   const int num_mblocks = (p.ngroups + 1) / 2;
-  const int mb_cnt = min(p.mb_per_cta, num_mblocks - mb0);
+  const int mb_cnt = min(p.mb_per_cta, (num_mblocks - mb0 + CG - 1) / CG);
+  auto block_of = [&](int i) { return mb0 + CG * i + rank; };
+  auto nsub_of = [&](int mb) { return max(0, min(2, p.ngroups - 2 * mb)); };
   const int my_ktiles = (p.ktiles - split + nsplit - 1) / nsplit;  // kt = split, split+nsplit, ...
   constexpr uint32_t TMEM_COLS = 512;
 
@@ -73,9 +80,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;
@@ -94,19 +105,32 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * L::STAGE_BYTES;
           uint8_t* sB = sA + L::A_BYTES;
-          const int g0 = 2 * (mb0 + mbi);
-          const int nsub = (g0 + 1 < p.ngroups) ? 2 : 1;
-          mbar_expect_tx(&full_bar[stage], box_bytes * (uint32_t)(nsub + BN / 64));
+          const int mb = block_of(mbi);
+          const int g0 = 2 * mb;
+          const int nsub = nsub_of(mb);
+          // pair: the leader's barrier counts the bytes of BOTH CTAs' loads (an odd tail block of the peer loads no A)
+          if (rank == 0)
+            mbar_expect_tx(&full_bar[stage],
+                           box_bytes * (uint32_t)(nsub + (CG == 2 ? nsub_of(mb + 1) : 0) + BN / 64));
           for (int sub = 0; sub < nsub; ++sub) {
             const int g = g0 + sub;
             const int tap = g / p.a_cblocks;
             const int cb = g - tap * p.a_cblocks;
-            tma_load_4d(sA + sub * L::BLK, &tmA, &full_bar[stage], p.a_coff + cb * 64,
-                        w0 * p.a_stride + p.tap_dw[tap], h0 * p.a_stride + p.tap_dh[tap], n0);
+            if (CG == 2)
+              tma_load_4d_2sm(sA + sub * L::BLK, &tmA, &full_bar[stage], p.a_coff + cb * 64,
+                              w0 * p.a_stride + p.tap_dw[tap], h0 * p.a_stride + p.tap_dh[tap], n0);
+            else
+              tma_load_4d(sA + sub * L::BLK, &tmA, &full_bar[stage], p.a_coff + cb * 64,
+                          w0 * p.a_stride + p.tap_dw[tap], h0 * p.a_stride + p.tap_dh[tap], n0);
           }
 #pragma unroll
-          for (int blk = 0; blk < BN / 64; ++blk)
-            tma_load_4d(sB + blk * L::BLK, &tmB, &full_bar[stage], p.b_coff + nb * BN + blk * 64, w0, h0, n0);
+          for (int blk = 0; blk < BN / 64 / CG; ++blk) {
+            if (CG == 2)
+              tma_load_4d_2sm(sB + blk * L::BLK, &tmB, &full_bar[stage],
+                              p.b_coff + nb * BN + (rank * (BN / 128) + blk) * 64, w0, h0, n0);
+            else
+              tma_load_4d(sB + blk * L::BLK, &tmB, &full_bar[stage], p.b_coff + nb * BN + blk * 64, w0, h0, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -116,8 +140,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+    if (lane == 0 && rank == 0) {  // pair: the leader issues the MMAs for both CTAs' accumulator rows
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 1, 1);  // both operands MN-major
       const int ksteps = (p.box_rows + 15) / 16;
       int stage = 0;
       uint32_t phase = 0;
@@ -132,16 +156,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // 64-channel blocks are LBO = 16 KB apart.
             const uint64_t a_desc = umma_smem_desc_sw128(a_addr + ks * 2048, L::BLK, 1024);
             const uint64_t b_desc = umma_smem_desc_sw128(b_addr + ks * 2048, L::BLK, 1024);
-            umma_bf16(tmem_base + (uint32_t)(mbi * BN), a_desc, b_desc, idesc, (i | ks) != 0);
+            if (CG == 2) umma_bf16_2sm(tmem_base + (uint32_t)(mbi * BN), a_desc, b_desc, idesc, (i | ks) != 0);
+            else umma_bf16(tmem_base + (uint32_t)(mbi * BN), a_desc, b_desc, idesc, (i | ks) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CG == 2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
-      umma_commit(tmem_full_bar);
+      if (CG == 2) umma_commit_2sm(tmem_full_bar);
+      else umma_commit(tmem_full_bar);
     }
     __syncwarp();
   } else {
@@ -150,7 +177,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     for (int mbi = 0; mbi < mb_cnt; ++mbi) {
-      const int g = 2 * (mb0 + mbi) + (r >> 6);
+      const int g = 2 * block_of(mbi) + (r >> 6);
       const bool row_valid = (g < p.ngroups) && (my_ktiles > 0) && (g * 64 + (r & 63) < p.m_valid);
       float* orow = p.out + (long long)(g * 64 + (r & 63)) * p.ldo;
 #pragma unroll 1
@@ -178,8 +205,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) {
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradKParams& kp, dim3 grid,
+                       cudaStream_t stream) {
+  using L = WgradSmem<BN, STAGES, 2>;
+  auto kernel = wgrad_kernel<BN, STAGES, 2>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SVSR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(192), cfg.dynamicSmemBytes = L::TOTAL, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  SVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, kp));
+  note_launch();
+  return SVSR_OK;
 }
 
 template <int BN, int STAGES>
@@ -227,9 +280,18 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
 
   const int BN = p.n_cols <= 64 ? 64 : (p.n_cols <= 128 ? 128 : 256);
   const int num_mblocks = (kp.ngroups + 1) / 2;
-  kp.mb_per_cta = 512 / BN;
-  if (kp.mb_per_cta > num_mblocks) kp.mb_per_cta = num_mblocks;
-  const int gx = (num_mblocks + kp.mb_per_cta - 1) / kp.mb_per_cta;
+  // CTA pairs (cta_group::2; SVSR_IGEMM_2CTA=0 turns them off): M = 256 MMAs over two 128-row blocks of D, the gradient tile's
+  // 64-channel blocks split between the two CTAs
+  static const bool pair_env = [] {
+    const char* e = getenv("SVSR_IGEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = pair_env && BN >= 128 && num_mblocks >= 2;
+  const int cg = pair ? 2 : 1;
+  kp.mb_per_cta = 512 / BN;  // accumulators [128 x BN] per CTA
+  const int units = (num_mblocks + cg - 1) / cg;  // blocks (or block pairs) to distribute
+  if (kp.mb_per_cta > units) kp.mb_per_cta = units;
+  const int gx = cg * ((units + kp.mb_per_cta - 1) / kp.mb_per_cta);
   const int gy = (p.n_cols + BN - 1) / BN;
   // split-K factor from a small cost model (microseconds): one CTA per SM is resident (192 KB of smem), so the launch
   // runs in ceil(ctas / 148) waves of  t_fixed + mb_per_cta * (ktiles_per_cta * t_stage + t_epilogue);  the fp32 red.add
@@ -281,6 +343,12 @@ int wgrad_launch(const WgradProblem& p, cudaStream_t stream) {
                            : 2.0 * p.k_N * p.k_H * p.k_W * (double)p.ntaps * p.a_cin * (double)p.n_cols;
   prof_begin(PROF_WGRAD, flops, stream);
   int rc;
+  if (pair) {
+    rc = BN == 128 ? launch_pair<128, 4>(tmA, tmB, kp, grid, stream)   // 4 x (32 + 16) KB
+                   : launch_pair<256, 3>(tmA, tmB, kp, grid, stream);  // 3 x (32 + 32) KB
+    prof_end(stream);
+    return rc;
+  }
   switch (BN) {
     case 64: rc = launch_t<64, 3>(tmA, tmB, kp, grid, stream); break;
     case 128: rc = launch_t<128, 3>(tmA, tmB, kp, grid, stream); break;
