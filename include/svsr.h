@@ -146,6 +146,12 @@ int svsr_rotary_table(float* tab, int n, void* stream);
 int svsr_attention_fwd(const void* qkv, const float* rot, void* o, int B, int n, int heads, int rotary_v, void* stream);
 int svsr_attention_bwd(const void* qkv, const float* rot, const void* d_o, void* dqkv, int B, int n, int heads,
                        int rotary_v, void* stream);
+/* The forward of the x-transformers attention sublayer core in ONE kernel (lightning.py:95-105,158):
+ * to_q | to_k | to_v projection of the normalised activations (TMA-fed tcgen05 GEMM, one head x four clips per CTA), rotary,
+ * softmax, PV. xn bf16 [B*n, ldx]; w bf16 [3*heads*64, Kp] (q | k | v weight rows, Kp % 64 == 0 contracted columns, Kp <= ldx);
+ * qkv bf16 [B*n, 3*heads*64] receives the projections (what svsr_attention_bwd reads); o bf16 [B*n, heads*64]. n <= 32. */
+int svsr_attention_qkv_fwd(const void* xn, int ldx, const void* w, int Kp, const float* rot, void* qkv, void* o, int B,
+                           int n, int heads, int rotary_v, void* stream);
 /* GEGLU + Dropout(ff_dropout): u = dropout(h[:, :F] * gelu(h[:, F:])). The keep-mask is a counter-based function of
  * (seed, element index), regenerated identically by the backward; p_drop = 0 disables it. */
 int svsr_geglu_fwd(const void* h, void* u, int M, int F, float p_drop, uint64_t seed, void* stream);

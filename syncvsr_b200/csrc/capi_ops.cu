@@ -93,6 +93,11 @@ int svsr_attention_bwd(const void* qkv, const float* rot, const void* d_o, void*
   return attention_bwd(static_cast<const bf16*>(qkv), rot, static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), B,
                        n, heads, rotary_v, ST(stream));
 }
+int svsr_attention_qkv_fwd(const void* xn, int ldx, const void* w, int Kp, const float* rot, void* qkv, void* o, int B,
+                           int n, int heads, int rotary_v, void* stream) {
+  return attention_qkv_tc_fwd(static_cast<const bf16*>(xn), ldx, static_cast<const bf16*>(w), Kp, rot,
+                              static_cast<bf16*>(qkv), static_cast<bf16*>(o), B, n, heads, rotary_v, ST(stream));
+}
 int svsr_geglu_fwd(const void* h, void* u, int M, int F, float p_drop, uint64_t seed, void* stream) {
   SVSR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "geglu: dropout p=%f out of [0,1)", p_drop);
   return geglu_fwd(static_cast<const bf16*>(h), static_cast<bf16*>(u), M, F, p_drop, seed, ST(stream));

@@ -37,6 +37,13 @@ int attention_tc_bwd(const __nv_bfloat16* qkv, const float* rot, const __nv_bflo
                      int heads, int rotary_v, cudaStream_t s, float drop_p, unsigned long long drop_seed,
                      const StepCtl* ctl = nullptr);
 
+// attention_tc.cu: the FORWARD of the whole sublayer core in one kernel -- q | k | v projection of the normalised activations
+// (TMA-fed tcgen05 GEMM, one head x four clips per CTA), rotary, softmax, PV. xn [B*n, ldx] bf16; w [3*heads*64, Kp] bf16
+// K-major (Kp % 64 == 0 contracted columns); qkv [B*n, 3*heads*64] receives the projections (the backward kernel reads them).
+int attention_qkv_tc_fwd(const __nv_bfloat16* xn, int ldx, const __nv_bfloat16* w, int Kp, const float* rot,
+                         __nv_bfloat16* qkv, __nv_bfloat16* o, int B, int n, int heads, int rotary_v, cudaStream_t s,
+                         float drop_p = 0.f, unsigned long long drop_seed = 0, const StepCtl* ctl = nullptr);
+
 // u[M,F] = dropout_p(h[:, :F] * gelu(h[:, F:])) ; dh from du. The dropout mask is a counter-based function of
 // (seed, element index): forward and backward regenerate the same mask, nothing is stored. p = 0 disables it.
 int geglu_fwd(const __nv_bfloat16* h, __nv_bfloat16* u, int M, int F, float p, unsigned long long seed, cudaStream_t s,

@@ -553,9 +553,22 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
       SVSR_CHECK_CUDA(cudaMemcpyAsync(xf, xa, (size_t)e.M * Dp * 4, cudaMemcpyDeviceToDevice, s));
     } else {
       RC(rmsnorm_fwd(xa, g_a, e.ws<bf16>(L.xn_a), e.ws<float>(L.inv_a), e.M, Dp, 1e-8f, s, D, &ca));
-      RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s, ca));
-      RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
-                       s, train ? c.attn_dropout : 0.f, seed0 + 0x2000ULL * (unsigned long long)(i + 1), &ca));
+      // q | k | v projection + rotary + softmax + PV in ONE kernel (attention_tc.cu) when the sequence fits 32 token slots;
+      // SVSR_ATTN_QKV_FUSED=0 (or SVSR_ATTN_TC=0) keeps the projection GEMM and the attention core as two launches
+      static const bool fuse_qkv = [] {
+        const char* a = getenv("SVSR_ATTN_QKV_FUSED");
+        const char* t = getenv("SVSR_ATTN_TC");
+        return !(a && a[0] == '0') && !(t && t[0] == '0');
+      }();
+      if (fuse_qkv && c.T + 1 <= 32 && L.qkv.b < 0 && L.qkv.Kp % 64 == 0 && L.qkv.Kp <= Dp && L.qkv.Np >= 3 * inner) {
+        RC(attention_qkv_tc_fwd(e.ws<bf16>(L.xn_a), Dp, e.ws<bf16>(L.qkv.wb), L.qkv.Kp, e.ws<float>(e.rot),
+                                e.ws<bf16>(L.qkvbuf), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v, s,
+                                train ? c.attn_dropout : 0.f, seed0 + 0x2000ULL * (unsigned long long)(i + 1), &ca));
+      } else {
+        RC(lw_fwd(e, e.ws<bf16>(L.xn_a), Dp, e.M, L.qkv, e.ws<bf16>(L.qkvbuf), 3 * inner, 0, nullptr, s, ca));
+        RC(attention_fwd(e.ws<bf16>(L.qkvbuf), e.ws<float>(e.rot), e.ws<bf16>(L.obuf), c.B, c.T + 1, c.heads, c.rotary_v,
+                         s, train ? c.attn_dropout : 0.f, seed0 + 0x2000ULL * (unsigned long long)(i + 1), &ca));
+      }
       RC(lw_fwd(e, e.ws<bf16>(L.obuf), inner, e.M, L.out, xf, Dp, 1, xa, s, ca));
       if (dc) RC(copy_if_skipped(xf, xa, (long long)e.M * Dp, ca, s));
     }

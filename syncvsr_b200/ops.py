@@ -268,6 +268,15 @@ def attention_fwd(qkv, rot, B, n, heads, rotary_v=True):
     return o
 
 
+def attention_qkv_fwd(xn, w, rot, B, n, heads, rotary_v=True):
+    """Fused to_q|to_k|to_v projection + rotary + softmax + PV. xn bf16 [B*n, K], w bf16 [3*heads*64, K]; returns (qkv, o)."""
+    qkv = torch.empty(B * n, 3 * heads * 64, device=xn.device, dtype=torch.bfloat16)
+    o = torch.empty(B * n, heads * 64, device=xn.device, dtype=torch.bfloat16)
+    check(lib().svsr_attention_qkv_fwd(ptr(xn), _i(xn.stride(0)), ptr(w), _i(w.shape[1]), ptr(rot), ptr(qkv), ptr(o), _i(B),
+                                       _i(n), _i(heads), _i(rotary_v), stream_ptr()), "svsr_attention_qkv_fwd")
+    return qkv, o
+
+
 def attention_bwd(qkv, rot, d_o, B, n, heads, rotary_v=True):
     dqkv = torch.empty_like(qkv)
     check(lib().svsr_attention_bwd(ptr(qkv), ptr(rot), ptr(d_o), ptr(dqkv), _i(B), _i(n), _i(heads), _i(rotary_v),

@@ -420,6 +420,22 @@ def test_attention_fwd_bwd(ops, monkeypatch, B, n, rotary_v, tc):
         assert rel(dqkv[:, i * 512:(i + 1) * 512], gq[:, i * 512:(i + 1) * 512]) < (1.5e-2 if tc else 2 * BF16_TOL), name
 
 
+@pytest.mark.parametrize("B,n,K", [(64, 30, 512), (5, 30, 576), (3, 17, 128)])
+def test_fused_qkv_projection_attention_forward(ops, B, n, K):
+    """attention_qkv_tc_fwd (projection + rotary + softmax + PV in one kernel) against the two-launch path: the GEMM's qkv
+    buffer and the tcgen05 attention core on it; clip counts that are not a multiple of the 4-clip tile, the 576-column
+    pitch of the word-boundary variant, short sequences."""
+    heads = 8
+    xn = randn(B * n, K, seed=61, scale=1.0)
+    w = randn(3 * heads * 64, K, seed=62, scale=K ** -0.5)
+    rot = ops.rotary_table(n)
+    qkv_ref = ops.gemm(xn, w)
+    o_ref = ops.attention_fwd(qkv_ref, rot, B, n, heads)
+    qkv, o = ops.attention_qkv_fwd(xn, w, rot, B, n, heads)
+    assert rel(qkv, qkv_ref) < 1e-3  # same tcgen05 accumulation, one bf16 rounding on both sides
+    assert rel(o, o_ref) < BF16_TOL
+
+
 def test_geglu(ops):
     h = randn(500, 4096, seed=70)
     hr = h.float().requires_grad_(True)
