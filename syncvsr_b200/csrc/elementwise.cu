@@ -307,14 +307,28 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
                     const __nv_bfloat16* __restrict__ c, const float* __restrict__ coef,
                     const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc,
                     __nv_bfloat16* __restrict__ gmask_out, long long rows, int C,
-                    const __nv_bfloat16* __restrict__ sw_res, const float* __restrict__ sw_rcoef) {
+                    const __nv_bfloat16* __restrict__ sw_res, const float* __restrict__ sw_rcoef,
+                    const double* __restrict__ fstats, float* dgamma, float* dbeta) {
   const int cg = C >> 3, rpb = 256 / cg;
   if (threadIdx.x >= rpb * cg) return;
   const int g = threadIdx.x % cg;
   F8 sc = ldf8(coef + 2 * C + g * 8), cB, cD, shf;
   {
     const F8 mean = ldf8(coef + g * 8), invstd = ldf8(coef + C + g * 8);
-    const F8 k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
+    F8 k1, k2;
+    if (fstats) {
+      // bn_bwd_finalize folded in: k1 = sum g / rows, k2 = sum g*xhat / rows straight from the fp64 reduction; the first
+      // row lane of block 0 accumulates d gamma / d beta (one writer per channel)
+      const double inv_rows = 1.0 / (double)rows;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double sg = fstats[g * 8 + k], sgx = fstats[C + g * 8 + k];
+        k1.v[k] = (float)(sg * inv_rows), k2.v[k] = (float)(sgx * inv_rows);
+        if (blockIdx.x == 0 && threadIdx.x < cg) dbeta[g * 8 + k] += (float)sg, dgamma[g * 8 + k] += (float)sgx;
+      }
+    } else {
+      k1 = ldf8(kcoef + g * 8), k2 = ldf8(kcoef + C + g * 8);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float t = sc.v[k] * invstd.v[k] * k2.v[k];
@@ -1049,15 +1063,20 @@ int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, f
 }
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
                  const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
-                 cudaStream_t s, const __nv_bfloat16* sw_res, const float* sw_rcoef) {
+                 cudaStream_t s, const __nv_bfloat16* sw_res, const float* sw_rcoef, const double* fused_stats,
+                 float* dgamma, float* dbeta) {
   SVSR_REQUIRE(C % 8 == 0 && C <= 2048, "bn_bwd_apply: unsupported channel count %d", C);
+  SVSR_REQUIRE(fused_stats ? (dgamma && dbeta) : kcoef != nullptr, "bn_bwd_apply: kcoef, or the reduction sums with dgamma / dbeta");
   const unsigned grid = grid_for(rows, (256 / (C / 8)) * 4, 148 * 3);
   if (self_mask == 1)
-    bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
+    bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef,
+                                                 fused_stats, dgamma, dbeta);
   else if (self_mask == 2)
-    bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
+    bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef,
+                                                 fused_stats, dgamma, dbeta);
   else
-    bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef);
+    bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(dout, relu_ref, c, coef, kcoef, dc, gmask_out, rows, C, sw_res, sw_rcoef,
+                                                 fused_stats, dgamma, dbeta);
   LAUNCH_CHECK();
   return SVSR_OK;
 }

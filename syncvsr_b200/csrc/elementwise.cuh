@@ -32,7 +32,10 @@ int bn_bwd_finalize(const double* stats, long long rows, int C, float* dgamma, f
 // dc = scale * (g - k1 - xhat*k2); optionally also writes g (the relu-masked upstream gradient) to gmask_out
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* relu_ref, const __nv_bfloat16* c, const float* coef,
                  const float* kcoef, __nv_bfloat16* dc, __nv_bfloat16* gmask_out, long long rows, int C, int self_mask,
-                 cudaStream_t s, const __nv_bfloat16* sw_res = nullptr, const float* sw_rcoef = nullptr);
+                 cudaStream_t s, const __nv_bfloat16* sw_res = nullptr, const float* sw_rcoef = nullptr,
+                 // bn_bwd_finalize folded into this launch: the fp64 sums of bn_bwd_reduce ([2][C]) instead of kcoef; d gamma /
+                 // d beta (+=) are then written here
+                 const double* fused_stats = nullptr, float* dgamma = nullptr, float* dbeta = nullptr);
 
 // stem epilogue: y0 [N,IH,IW,64] -> max_pool3x3s2p1(gelu(bn(y0))) [N,OH,OW,64] + argmax slot (uint8)
 // swish = 1: Swish instead of GELU (LRS frontend3D, conv3d_extractor.py:31-38)

@@ -287,9 +287,9 @@ static int bn_bwd(const EngineBase& e, const bf16* dout, const bf16* relu_ref, c
                   const bf16* sw_res = nullptr, const float* sw_rcoef = nullptr) {
   RC(bn_bwd_reduce(dout, relu_ref, c, e.ws<float>(bn.coef), rows, bn.C, e.ws<double>(bn.stats_b), self_mask, s, sw_res,
                    sw_rcoef));
-  RC(bn_bwd_finalize(e.ws<double>(bn.stats_b), rows, bn.C, e.G + bn.gamma, e.G + bn.beta, e.ws<float>(bn.kcoef), s));
-  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), e.ws<float>(bn.kcoef), dc, gmask_out, rows, bn.C,
-                      self_mask, s, sw_res, sw_rcoef);
+  // (bn_bwd_finalize is folded into the apply launch: one kernel less per BatchNorm on the backward chain)
+  return bn_bwd_apply(dout, relu_ref, c, e.ws<float>(bn.coef), nullptr, dc, gmask_out, rows, bn.C, self_mask, s, sw_res,
+                      sw_rcoef, e.ws<double>(bn.stats_b), e.G + bn.gamma, e.G + bn.beta);
 }
 
 // Backward runs on two streams: `s` carries the critical chain (dgrad GEMMs, BatchNorm / attention / norm backward),

@@ -744,10 +744,8 @@ static int lrs_backward(LrsEngine& e, const float* grad_scale, int stage, cudaSt
       RC(linear_wgrad(e, t.dxb, D, e.ws<bf16>(Lc.act), M, Lc.pw2, w));
       RC(lin_dgrad(e, t.dxb, D, M, Lc.pw2, t1, D, 0, nullptr, 1.f, nullptr, s));  // t1 = d act
       RC(bn_col_reduce(e.ws<bf16>(Lc.dwo), t1, e.ws<float>(Lc.bn.coef), M, D, e.ws<double>(Lc.bn.stats_b), 1, s));
-      RC(bn_bwd_finalize(e.ws<double>(Lc.bn.stats_b), M, D, e.G + Lc.bn.gamma, e.G + Lc.bn.beta,
-                         e.ws<float>(Lc.bn.kcoef), s));
-      RC(bn_bwd_apply(t1, nullptr, e.ws<bf16>(Lc.dwo), e.ws<float>(Lc.bn.coef), e.ws<float>(Lc.bn.kcoef), t2, nullptr, M,
-                      D, 2, s));  // t2 = d dwo
+      RC(bn_bwd_apply(t1, nullptr, e.ws<bf16>(Lc.dwo), e.ws<float>(Lc.bn.coef), nullptr, t2, nullptr, M, D, 2, s, nullptr,
+                      nullptr, e.ws<double>(Lc.bn.stats_b), e.G + Lc.bn.gamma, e.G + Lc.bn.beta));  // t2 = d dwo
       RC(sq.fork());
       RC(dwconv1d_wgrad(e.ws<bf16>(Lc.u), t2, e.G + Lc.dw_w, e.G + Lc.dw_b, c.B, T, D, c.cnn_kernel, w));
       RC(dwconv1d_fwd(t2, e.ws<float>(Lc.dw_wT), nullptr, t1, c.B, T, D, c.cnn_kernel, 1, s, 1));  // t1 = d u
