@@ -759,7 +759,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     const char* e = getenv("SVSR_IGEMM_2CTA");
     return !(e && e[0] == '0');
   }();
-  const bool pair = pair_env && BN >= 128 && !p.ce.mode && !p.bnb.n && m_tiles >= 2;
+  const bool pair = pair_env && BN >= 128 && !p.bnb.n && m_tiles >= 2;  // (the fused BN-backward variant keeps single CTAs)
   {
     uint64_t dims[2] = {(uint64_t)p.b_cols, (uint64_t)p.b_rows};
     uint64_t strides[1] = {(uint64_t)p.b_cols * 2};
