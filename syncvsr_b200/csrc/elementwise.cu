@@ -400,27 +400,68 @@ stem_bn_gelu_pool_kernel(const __nv_bfloat16* __restrict__ y0, const float* __re
     // all-negative window has two candidates (its largest or its smallest z).
     // Both extrema are tracked in the ONE pass over the window: nearly every warp holds at least one all-negative
     // (channel, window) pair, so a second pass over the nine pixels used to run warp-wide.
+    // The window extrema are found on the RAW bf16 conv outputs with packed bf16x2 max / min (z = y*scale + shift is
+    // monotone in y, so the extreme z sit at the extreme y: which one depends on the sign of the scale) -- two channels per
+    // instruction and no fp32 transform of the 72 window elements; the first position attaining each extreme (torch's
+    // max_pool tie rule) comes from a second sweep in descending position order with packed equality masks.
     float zmax[8], zmin[8];
     int imax[8], imin[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) zmax[k] = -INFINITY, imax[k] = 0, zmin[k] = INFINITY, imin[k] = 0;
     const __nv_bfloat16* img = y0 + (size_t)n * IH * IW * C + g * 8;
+    uint4 win[9];
+    unsigned vmask = 0;  // bit p set: window position p lies inside the image
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = 2 * (int)oh + kh - 1;
-      if (ih < 0 || ih >= IH) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int iw = 2 * (int)ow + kw - 1;
-        if (iw < 0 || iw >= IW) continue;
-        const F8 v = ld8(img + (size_t)(ih * IW + iw) * C);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float z = v.v[k] * sc.v[k] + sh.v[k];
-          if (z > zmax[k]) zmax[k] = z, imax[k] = kh * 3 + kw;
-          if (z < zmin[k]) zmin[k] = z, imin[k] = kh * 3 + kw;
-        }
+        const bool ok = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
+        win[kh * 3 + kw] = ok ? *reinterpret_cast<const uint4*>(img + (size_t)(ih * IW + iw) * C) : make_uint4(0u, 0u, 0u, 0u);
+        vmask |= ok ? (1u << (kh * 3 + kw)) : 0u;
       }
+    }
+    const int first_valid = __ffs(vmask) - 1;  // >= 0: the window centre always exists
+    uint32_t mx[4], mn[4], ix[4], in_[4];
+    mx[0] = mn[0] = win[4].x, mx[1] = mn[1] = win[4].y, mx[2] = mn[2] = win[4].z, mx[3] = mn[3] = win[4].w;  // the centre
+#pragma unroll
+    for (int pos = 0; pos < 9; ++pos) {
+      if (!(vmask & (1u << pos))) continue;
+      const uint32_t w[4] = {win[pos].x, win[pos].y, win[pos].z, win[pos].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&mx[q]), v);
+        const __nv_bfloat162 b = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&mn[q]), v);
+        mx[q] = *reinterpret_cast<const uint32_t*>(&a), mn[q] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ix[q] = in_[q] = 0u;
+#pragma unroll
+    for (int pos = 8; pos >= 0; --pos) {  // descending: the LAST assignment = the FIRST position with equality
+      if (!(vmask & (1u << pos))) continue;
+      const uint32_t w[4] = {win[pos].x, win[pos].y, win[pos].z, win[pos].w};
+      const uint32_t pp = (uint32_t)pos * 0x00010001u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+        const uint32_t ex = __heq2_mask(v, *reinterpret_cast<const __nv_bfloat162*>(&mx[q]));
+        const uint32_t en = __heq2_mask(v, *reinterpret_cast<const __nv_bfloat162*>(&mn[q]));
+        ix[q] = (pp & ex) | (ix[q] & ~ex);
+        in_[q] = (pp & en) | (in_[q] & ~en);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = k >> 1, hi = k & 1;
+      const float ymx = __uint_as_float(hi ? (mx[q] & 0xffff0000u) : (mx[q] << 16));
+      const float ymn = __uint_as_float(hi ? (mn[q] & 0xffff0000u) : (mn[q] << 16));
+      const int pmx = (int)((ix[q] >> (16 * hi)) & 0xffu), pmn = (int)((in_[q] >> (16 * hi)) & 0xffu);
+      const float za = fmaf(ymx, sc.v[k], sh.v[k]), zb = fmaf(ymn, sc.v[k], sh.v[k]);
+      const bool up = sc.v[k] > 0.f;
+      zmax[k] = up ? za : zb, imax[k] = up ? pmx : pmn;
+      zmin[k] = up ? zb : za, imin[k] = up ? pmn : pmx;
+      if (sc.v[k] == 0.f) imax[k] = imin[k] = first_valid;  // constant channel: every position ties, the first one wins
     }
     float best[8];
 #pragma unroll
