@@ -596,11 +596,16 @@ stem_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, const uint8_t* __restri
 __device__ __forceinline__ uint32_t pair_mask(uint32_t m, int j) { return __byte_perm(m, 0, j ? 0x3322 : 0x1100); }
 
 // APPLY: dc = scale * (dz - k1 - xhat * k2) with dz = sum of the dzp of the <= 4 windows that selected this input.
+// One thread = 8 channels of a 2 x 2 QUAD of input pixels (2a, 2a+1) x (2b, 2b+1): the quad touches exactly the four
+// pooling windows (a, b), (a, b+1), (a+1, b), (a+1, b+1), and which window position each (pixel, window) pair means is a
+// compile-time constant -- pixel (2a, 2b) is the centre (4) of window (a, b); (2a, 2b+1) is position 5 of (a, b) and 3 of
+// (a, b+1); (2a+1, 2b) is 7 of (a, b) and 1 of (a+1, b); (2a+1, 2b+1) is 8 / 6 / 2 / 0 of the four. Four window loads serve
+// four pixels (the pixel-per-thread version issued sixteen), nine mask tests instead of sixteen.
 __global__ void __launch_bounds__(256)
 stem_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dzp, const uint8_t* __restrict__ argmax,
                       const __nv_bfloat16* __restrict__ y0, const float* __restrict__ coef,
-                      const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc, unsigned npix, unsigned IH,
-                      unsigned IW, unsigned OH, unsigned OW, unsigned mIH, unsigned mIW) {
+                      const float* __restrict__ kcoef, __nv_bfloat16* __restrict__ dc, unsigned nquad, unsigned IH,
+                      unsigned IW, unsigned OH, unsigned OW, unsigned QH, unsigned QW, unsigned mQH, unsigned mQW) {
   constexpr unsigned C = 64;
   const unsigned g = threadIdx.x & 7, slot = threadIdx.x >> 3;
   F8 sc, ca, cb;  // dc = dz*sc + (v*cb + ca): cb = -sc*k2*invstd, ca = -sc*k1 + sc*k2*mean*invstd
@@ -614,44 +619,53 @@ stem_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dzp, const uint8_t* __re
       ca.v[k] = -sc.v[k] * k1.v[k] - cb.v[k] * mean.v[k];
     }
   }
-  for (unsigned pix = blockIdx.x * 32u + slot; pix < npix; pix += gridDim.x * 32u) {
-    const unsigned t1 = fastdiv(pix, mIW), iw = pix - t1 * IW, n = fastdiv(t1, mIH), ih = t1 - n * IH;
-    const unsigned oh0 = ih >> 1, oh1 = (ih + 1) >> 1, ow0 = iw >> 1, ow1 = (iw + 1) >> 1;
-    const bool vh1 = (oh1 != oh0) && (oh1 < OH), vw1 = (ow1 != ow0) && (ow1 < OW);
-    const unsigned oh1c = vh1 ? oh1 : oh0, ow1c = vw1 ? ow1 : ow0;
-    const unsigned r0 = (n * OH + oh0) * OW, r1 = (n * OH + oh1c) * OW;
-    const unsigned o[4] = {(r0 + ow0) * C + g * 8, (r0 + ow1c) * C + g * 8, (r1 + ow0) * C + g * 8,
-                           (r1 + ow1c) * C + g * 8};
-    // window position of (ih,iw) inside window (oh,ow): (ih - 2*oh + 1) * 3 + (iw - 2*ow + 1), replicated to 4 bytes;
-    // windows that do not exist get the impossible position 0xff
-    const unsigned ph0 = (ih - 2 * oh0 + 1) * 3, ph1 = (ih - 2 * oh1c + 1) * 3;
-    const unsigned pw0 = iw - 2 * ow0 + 1, pw1 = iw - 2 * ow1c + 1;
-    const uint32_t pp[4] = {(ph0 + pw0) * 0x01010101u, vw1 ? (ph0 + pw1) * 0x01010101u : 0xffffffffu,
-                            vh1 ? (ph1 + pw0) * 0x01010101u : 0xffffffffu,
-                            (vh1 && vw1) ? (ph1 + pw1) * 0x01010101u : 0xffffffffu};
+  for (unsigned quad = blockIdx.x * 32u + slot; quad < nquad; quad += gridDim.x * 32u) {
+    const unsigned t1 = fastdiv(quad, mQW), b = quad - t1 * QW, n = fastdiv(t1, mQH), a = t1 - n * QH;
+    const unsigned ih0 = 2 * a, iw0 = 2 * b;
+    const bool row1 = ih0 + 1 < IH, col1 = iw0 + 1 < IW;      // the quad's second pixel row / column exists
+    const bool wr1 = a + 1 < OH, wc1 = b + 1 < OW;            // the windows below / to the right exist
+    // windows: w[0] = (a, b), w[1] = (a, b+1), w[2] = (a+1, b), w[3] = (a+1, b+1); a missing one loads (a, b) again and is masked
+    const unsigned o00 = ((n * OH + a) * OW + b) * C + g * 8;
+    const unsigned ow_[4] = {o00, wc1 ? o00 + C : o00, wr1 ? o00 + OW * C : o00, (wr1 && wc1) ? o00 + (OW + 1) * C : o00};
     uint2 am[4];
     uint4 dd[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {  // all loads first
-      am[w] = *reinterpret_cast<const uint2*>(argmax + o[w]);
-      dd[w] = *reinterpret_cast<const uint4*>(dzp + o[w]);
+      am[w] = *reinterpret_cast<const uint2*>(argmax + ow_[w]);
+      dd[w] = *reinterpret_cast<const uint4*>(dzp + ow_[w]);
     }
-    const F8 v = ld8(y0 + pix * C + g * 8);
-    float acc[8];
+    const unsigned p00 = ((n * IH + ih0) * IW + iw0) * C + g * 8;
+    const unsigned pix_[4] = {p00, p00 + C, p00 + IW * C, p00 + (IW + 1) * C};
+    const bool pv[4] = {true, col1, row1, row1 && col1};
+    F8 v[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int q = 0; q < 4; ++q) v[q] = pv[q] ? ld8(y0 + pix_[q]) : F8{};
+    float acc[4][8];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const uint32_t mlo = __vcmpeq4(am[w].x, pp[w]), mhi = __vcmpeq4(am[w].y, pp[w]);
-      const float2 a = unpack_bf16x2(dd[w].x & pair_mask(mlo, 0)), b = unpack_bf16x2(dd[w].y & pair_mask(mlo, 1));
-      const float2 c2 = unpack_bf16x2(dd[w].z & pair_mask(mhi, 0)), d2 = unpack_bf16x2(dd[w].w & pair_mask(mhi, 1));
-      acc[0] += a.x, acc[1] += a.y, acc[2] += b.x, acc[3] += b.y;
-      acc[4] += c2.x, acc[5] += c2.y, acc[6] += d2.x, acc[7] += d2.y;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+    // (pixel q, window w, position): the nine pairs of a quad
+    auto add = [&](int q, int w, uint32_t pos, bool on) {
+      const uint32_t pp = on ? pos * 0x01010101u : 0xffffffffu;  // a window that does not exist matches nothing
+      const uint32_t mlo = __vcmpeq4(am[w].x, pp), mhi = __vcmpeq4(am[w].y, pp);
+      const float2 x0 = unpack_bf16x2(dd[w].x & pair_mask(mlo, 0)), x1 = unpack_bf16x2(dd[w].y & pair_mask(mlo, 1));
+      const float2 x2 = unpack_bf16x2(dd[w].z & pair_mask(mhi, 0)), x3 = unpack_bf16x2(dd[w].w & pair_mask(mhi, 1));
+      acc[q][0] += x0.x, acc[q][1] += x0.y, acc[q][2] += x1.x, acc[q][3] += x1.y;
+      acc[q][4] += x2.x, acc[q][5] += x2.y, acc[q][6] += x3.x, acc[q][7] += x3.y;
+    };
+    add(0, 0, 4u, true);
+    add(1, 0, 5u, true), add(1, 1, 3u, wc1);
+    add(2, 0, 7u, true), add(2, 2, 1u, wr1);
+    add(3, 0, 8u, true), add(3, 1, 6u, wc1), add(3, 2, 2u, wr1), add(3, 3, 0u, wr1 && wc1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!pv[q]) continue;
+      F8 out;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out.v[k] = fmaf(acc[q][k], sc.v[k], fmaf(v[q].v[k], cb.v[k], ca.v[k]));
+      st8(dc + pix_[q], out);
     }
-    F8 out;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out.v[k] = fmaf(acc[k], sc.v[k], fmaf(v.v[k], cb.v[k], ca.v[k]));
-    st8(dc + pix * C + g * 8, out);
   }
 }
 
@@ -1153,10 +1167,12 @@ int stem_bwd_fused(__nv_bfloat16* dout, const uint8_t* argmax, const __nv_bfloat
   LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<1, 128, 0, s>>>(stats_scratch, npix, 64, dgamma, dbeta, kcoef_scratch);
   LAUNCH_CHECK();
-  stem_bwd_apply_kernel<<<grid_for(npix, 32 * 8, 148 * 16), 256, 0, s>>>(dout, argmax, y0, coef, kcoef_scratch, dc,
-                                                                         (unsigned)npix, (unsigned)IH, (unsigned)IW,
-                                                                         (unsigned)OH, (unsigned)OW, magic(IH),
-                                                                         magic(IW));
+  const int QH = (IH + 1) / 2, QW = (IW + 1) / 2;  // 2 x 2 quads of input pixels
+  const long long nquad = (long long)N * QH * QW;
+  stem_bwd_apply_kernel<<<grid_for(nquad, 32 * 4, 148 * 16), 256, 0, s>>>(dout, argmax, y0, coef, kcoef_scratch, dc,
+                                                                          (unsigned)nquad, (unsigned)IH, (unsigned)IW,
+                                                                          (unsigned)OH, (unsigned)OW, (unsigned)QH,
+                                                                          (unsigned)QW, magic(QH), magic(QW));
   LAUNCH_CHECK();
   return SVSR_OK;
 }
