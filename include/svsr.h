@@ -79,6 +79,11 @@ int svsr_conv_taps_fprop_bnstats(const void* x, const void* w, void* y, double* 
  * Replaces autograd's conv backward-data for resnet.layer1-4 (lightning.py:114-117). */
 int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int stride, int pad, int out_fp32, void* stream);
+/* The same input-gradient GEMM with the ReLU mask of the tensor the gradient flows into applied in the epilogue (timm
+ * BasicBlock `out = relu(bn2(c2) + shortcut)` via lightning.py:114-117): dx = (W^T dy + resid) * [relu_mask > 0], relu_mask a
+ * bf16 tensor of dx's geometry (the block's output). The BatchNorm-backward passes downstream then read one tensor less. */
+int svsr_conv2d_dgrad_masked(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, int stride, int pad, const void* relu_mask, void* stream);
 /* The same input-gradient GEMM with the BatchNorm-backward reduction of its CONSUMER fused into the epilogue (timm
  * BasicBlock via lightning.py:114-117): dx = (W^T dy + resid) * mask, mask = [relu_mask > 0] (bf16 tensor of dx's geometry,
  * the ReLU after `out = relu(bn2(c2) + shortcut)`) or -- self_mask -- [c0*scale0 + shift0 > 0] (the ReLU directly after

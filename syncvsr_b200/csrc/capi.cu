@@ -155,6 +155,13 @@ int svsr_conv2d_dgrad(const void* dy, const void* wd, void* dx, const void* resi
                            static_cast<cudaStream_t>(stream));
 }
 
+// the same with the ReLU mask of the tensor the gradient flows INTO applied in the epilogue: dx = (W^T dy + resid) * [mask > 0]
+int svsr_conv2d_dgrad_masked(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, int stride, int pad, const void* relu_mask, void* stream) {
+  return conv2d_dgrad_impl(dy, wd, dx, resid, N, H, W, Cin, Cout, R, S, stride, pad, 0, relu_mask, nullptr,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int svsr_conv2d_dgrad_bnbwd(const void* dy, const void* wd, void* dx, const void* resid, int N, int H, int W, int Cin,
                             int Cout, int R, int S, int stride, int pad, const void* relu_mask, int self_mask,
                             const void* c0, const float* coef0, double* stats0, const void* c1, const float* coef1,

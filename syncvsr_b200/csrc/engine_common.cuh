@@ -236,8 +236,12 @@ static int conv_fwd(const EngineBase& e, const bf16* x, int Hin, const ConvRef& 
   p.bn_stats = bn_stats;
   return igemm_launch(p, s);
 }
+// relu_mask (optional): the ReLU output the gradient flows into (bf16, dx's geometry) -- applied in the GEMM epilogue
 static int conv_dgrad(const EngineBase& e, const bf16* dy, int Hin, const ConvRef& c, bf16* dx, const bf16* resid,
-                      cudaStream_t s) {
+                      cudaStream_t s, const bf16* relu_mask = nullptr) {
+  if (relu_mask)
+    return svsr_conv2d_dgrad_masked(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride,
+                                    c.pad, relu_mask, s);
   return svsr_conv2d_dgrad(dy, e.ws<bf16>(c.wd), dx, resid, e.N, Hin, Hin, c.cin, c.cout, c.R, c.R, c.stride, c.pad, 0,
                            s);
 }
@@ -559,6 +563,14 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
     T0 = G;
   } else {
     // ---- trunk, reversed: one unit per block; dc2 / dc1 / dcds double buffered by block parity ----
+    // ReLU trunk: the gradient flowing into a block's output is masked by that output's ReLU where it is PRODUCED -- in the
+    // epilogue of the next block's conv1 input-gradient GEMM (conv_dgrad's relu_mask) -- so the two or four BatchNorm-backward
+    // passes that consume it read no mask tensor and write no masked copy (SVSR_RELU_MASK_IN_DGRAD=0: the passes mask).
+    static const bool mask_in_dgrad = [] {
+      const char* v = getenv("SVSR_RELU_MASK_IN_DGRAD");
+      return !(v && v[0] == '0');
+    }();
+    bool g_masked = !f.swish && mask_in_dgrad && bi_hi < 7;  // (a later stage starts on a gradient the earlier one masked)
     for (int bi = bi_hi; bi >= bi_lo; --bi) {
       BlockRef& blk = f.blocks[bi];
       bf16* DC2 = e.ws<bf16>(f.gbuf[3 + (bi & 1)]);
@@ -568,8 +580,9 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
       const long long rows = (long long)e.N * blk.Hout * blk.Hout;
       const bf16* out = e.ws<bf16>(blk.out);
       if (!f.swish) {
-        RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, blk.ds ? nullptr : T2, s));
-        if (blk.ds) RC(bn_bwd(e, T0, out, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
+        const bf16* ref = g_masked ? nullptr : out;
+        RC(bn_bwd(e, T0, ref, e.ws<bf16>(blk.c2), rows, blk.bn2, DC2, (blk.ds || g_masked) ? nullptr : T2, s));
+        if (blk.ds) RC(bn_bwd(e, T0, ref, e.ws<bf16>(blk.cds), rows, blk.bnds, DCD, nullptr, s));
       } else {
         // Swish(bn2(c2) + shortcut): the pre-activation is rebuilt from c2 and the shortcut operand (resnet.py:104-105)
         if (blk.ds) {
@@ -584,18 +597,24 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
       RC(sq.fork());  // dc2 (and dcds) complete
       RC(conv_wgrad(e, e.ws<bf16>(blk.a1), blk.Hout, DC2, blk.conv2, w));
       if (blk.ds) RC(conv_wgrad(e, xin, blk.Hin, DCD, blk.convds, w));
-      RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, T0, nullptr, s));  // T0 := da1
+      // da1: a pre-masked upstream gradient is itself the identity-path residual below, so it must survive -> da1 goes to T2
+      bf16* DA1 = g_masked ? T2 : T0;
+      const bf16* ident = g_masked ? T0 : T2;
+      RC(conv_dgrad(e, DC2, blk.Hout, blk.conv2, DA1, nullptr, s));
       // bn1 is followed directly by its activation: mask / derivative recomputed from c1 (a1 is not read)
-      RC(bn_bwd(e, T0, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, f.swish ? 2 : 1));
+      RC(bn_bwd(e, DA1, nullptr, e.ws<bf16>(blk.c1), rows, blk.bn1, DC1, nullptr, s, f.swish ? 2 : 1));
       RC(sq.fork());  // dc1 complete
       RC(conv_wgrad(e, xin, blk.Hin, DC1, blk.conv1, w));
+      // the gradient w.r.t. this block's input = the previous block's ReLU output (block 0: the stem's GELU output, no mask)
+      const bf16* next_mask = (!f.swish && mask_in_dgrad && bi > 0) ? xin : nullptr;
       if (blk.ds) {
         SVSR_CHECK_CUDA(cudaMemsetAsync(T4, 0, (size_t)e.N * blk.Hin * blk.Hin * blk.cin * 2, s));
         RC(conv_dgrad(e, DCD, blk.Hin, blk.convds, T4, nullptr, s));
-        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s));
+        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T4, s, next_mask));
       } else {
-        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, T2, s));
+        RC(conv_dgrad(e, DC1, blk.Hin, blk.conv1, T4, ident, s, next_mask));
       }
+      g_masked = next_mask != nullptr;
       bf16* t = T0;
       T0 = T4, T4 = t;
       RC(sq.end_unit());
