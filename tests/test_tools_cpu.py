@@ -18,9 +18,9 @@ def test_traffic_summary_uses_the_last_complete_step(tmp_path):
     out = tmp_path / "traffic.json"
     run("ncu_traffic.py", ROOT / "profiles" / "r2_traffic_final.csv", out)
     fam = json.loads(out.read_text())["families"]
-    # one step = 149 launches of the implicit-GEMM family (generic + both halo kernels; round 2 added the backward launch of
-    # the fused audio head) and 70 of the weight-gradient one
-    assert fam["igemm_kernel"]["launches"] == 149 and fam["wgrad_kernel"]["launches"] == 70
+    # one step = 137 launches of the implicit-GEMM family (generic + both halo kernels; round 2 added the backward launch of
+    # the fused audio head and moved the 12 q|k|v projections into the fused attention kernel) and 70 of the weight-gradient one
+    assert fam["igemm_kernel"]["launches"] == 137 and fam["wgrad_kernel"]["launches"] == 70
     committed = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())["families"]["igemm_kernel"]
     assert abs(fam["igemm_kernel"]["dram_bytes_per_launch"] - committed["dram_bytes_per_launch"]) < 1.0
     # AdamW streams 28 bytes per parameter: the pass sits at the HBM roofline
@@ -29,10 +29,10 @@ def test_traffic_summary_uses_the_last_complete_step(tmp_path):
 
 def test_launch_summary_and_layer_roofline_agree_on_the_step():
     text = run("launch_summary.py", ROOT / "profiles" / "r2_traffic_final.csv")
-    assert "472 launches" in text.splitlines()[0]
+    assert "441 launches" in text.splitlines()[0]
     table = run("layer_roofline.py", ROOT / "profiles" / "r2_traffic_final.csv")
     rows = [l for l in table.splitlines() if l.startswith("| ") and "launch |" not in l]
-    assert len(rows) == 1 + 19 + 8 + 1  # stem, 19 trunk convs, first and last encoder layer, total
+    assert len(rows) == 1 + 19 + 6 + 1  # stem, 19 trunk convs, first and last encoder layer (to_out, ff1, ff2), total
     stem = next(l for l in rows if l.startswith("| stem"))
     assert "conv_t5_c64_halo_kernel" in stem
     total = [c.strip() for c in rows[-1].split("|")]
