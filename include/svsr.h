@@ -238,11 +238,14 @@ int svsr_lrw_forward(void* handle, const float* videos, const int64_t* tokens, i
 /* Parity-mode forward: same model, fp32 activations and split-bf16 ([hi|lo|hi].[hi|hi|lo]) tensor-core operands through
  * the same tcgen05 kernels (csrc/precise.cuh) -- fp32-class accuracy for north_star's 1e-3 output tolerance.
  * Forward only (no backward, running BatchNorm buffers untouched); results are read with svsr_lrw_tensor
- * ("last_hidden_state", "logits_audio", "logits_category"). precise_ws: caller-allocated scratch. */
+ * ("last_hidden_state", "logits_audio", "logits_category"). precise_ws: caller-allocated scratch. word_mask: device
+ * fp32 [B, T], required by the dim-513 word-boundary variant (it becomes hidden channel 512), NULL otherwise. Covers the
+ * x-transformers and the HuggingFace-BERT encoder variants; dropouts are never applied (the deterministic function). */
 int64_t svsr_lrw_precise_workspace_bytes(void* handle);
 int svsr_lrw_forward_precise(void* handle, void* precise_ws, int64_t precise_ws_bytes, const float* videos,
                              const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
-                             const float* soft_labels, int train, uint32_t skip_mask, float* metrics, void* stream);
+                             const float* soft_labels, const float* word_mask, int train, uint32_t skip_mask,
+                             float* metrics, void* stream);
 /* forward_videos (lightning.py:112-119) only: fills the "inputs_embeds" tensor ([B,T+1,dim] fp32, row 0 = CLS) */
 int svsr_lrw_forward_videos(void* handle, const float* videos, int train, void* stream);
 /* (*grad_scale) * d loss_total / d params accumulated (+=) into the gradient arena; grad_scale is a DEVICE fp32

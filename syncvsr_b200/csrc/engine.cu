@@ -246,26 +246,32 @@ static int engine_build(LrwEngine& e, long long nodecay_base) {
   for (int i = 0; i < 2; ++i) e.t_dqkv[i] = b.take((size_t)e.M * 3 * inner * 2);
   e.pack_jobs = b.take(192 * sizeof(PackJob));
   e.ws_bytes = b.off;
-  {  // parity-mode scratch (only allocated by the caller when forward_precise is used; dim 512 only)
+  {  // parity-mode scratch (only allocated by the caller when forward_precise is used). D-wide fp32 rows have pitch
+     // Dq = ceil8(D); split operands are zero-padded to Kd = ceil64(D) / Kf = ceil64(4D) columns per third
     Bump pb;
     const size_t AGVp = (size_t)AGV;
+    const size_t Dq = (size_t)(D + 7) / 8 * 8, Kd = (size_t)Dp, Kf = (size_t)Fp;
     e.p_patches = pb.take(n0 * 4);
     e.p_y0 = pb.take(n0 * 4);
     for (int i = 0; i < 6; ++i) e.p_act[i] = pb.take(n1 * 4);
+    const size_t I = c.enc_type == 1 ? (size_t)c.bert_intermediate : 0;  // HuggingFace BERT: intermediate_size
     size_t s3 = n0 * 3 * 2;                                   // stem patches, 192 channels
-    if ((size_t)e.M * 3 * F * 2 > s3) s3 = (size_t)e.M * 3 * F * 2;
-    if ((size_t)e.N * 3 * D * 2 > s3) s3 = (size_t)e.N * 3 * D * 2;
+    if ((size_t)e.M * 3 * Kf * 2 > s3) s3 = (size_t)e.M * 3 * Kf * 2;
+    if ((size_t)e.M * 3 * I * 2 > s3) s3 = (size_t)e.M * 3 * I * 2;
+    if ((size_t)e.N * 3 * Kd * 2 > s3) s3 = (size_t)e.N * 3 * Kd * 2;
     e.p_s3 = pb.take(s3);
     size_t w3 = (size_t)512 * 9 * 1536 * 2;
-    if ((size_t)2 * F * 3 * D * 2 > w3) w3 = (size_t)2 * F * 3 * D * 2;
-    if (AGVp * 3 * D * 2 > w3) w3 = AGVp * 3 * D * 2;
+    if ((size_t)2 * F * 3 * Kd * 2 > w3) w3 = (size_t)2 * F * 3 * Kd * 2;
+    if ((size_t)D * 3 * Kf * 2 > w3) w3 = (size_t)D * 3 * Kf * 2;
+    if (I * 3 * Kd * 2 > w3) w3 = I * 3 * Kd * 2;
+    if (AGVp * 3 * Kd * 2 > w3) w3 = AGVp * 3 * Kd * 2;
     e.p_w3 = pb.take(w3);
-    for (int i = 0; i < 2; ++i) e.p_xs[i] = pb.take((size_t)e.M * D * 4);
-    e.p_xn = pb.take((size_t)e.M * D * 4);
+    for (int i = 0; i < 2; ++i) e.p_xs[i] = pb.take((size_t)e.M * Dq * 4);
+    e.p_xn = pb.take((size_t)e.M * Dq * 4);
     e.p_qkv = pb.take((size_t)e.M * 3 * inner * 4);
     e.p_o = pb.take((size_t)e.M * inner * 4);
-    e.p_h = pb.take((size_t)e.M * 2 * F * 4);
-    e.p_u = pb.take((size_t)e.M * F * 4);
+    e.p_h = pb.take((size_t)e.M * (2 * (size_t)F > I ? 2 * (size_t)F : I) * 4);
+    e.p_u = pb.take((size_t)e.M * ((size_t)F > I ? (size_t)F : I) * 4);
     e.p_lc = pb.take((size_t)c.B * D * 4);
     e.p_lf = pb.take((size_t)e.N * D * 4);
     e.p_bytes = pb.off;
@@ -619,16 +625,19 @@ static int engine_forward(LrwEngine& e, const float* videos, const long long* to
 // ------------------------------------------------------------------------------------------------
 // Parity-mode forward (see precise.cuh): fp32 activations, split-bf16 tensor-core operands, forward only.
 // ------------------------------------------------------------------------------------------------
-static int precise_gemm(const LrwEngine& e, uint8_t* PW, const float* x, long long rows, int K, const float* w, int N,
-                        const float* bias, const float* resid, float* out, int ldc, cudaStream_t s) {
+// out[rows, N] (pitch ldc) = x[rows, K] (pitch ldx) . w[N, K]^T (+ bias) (+ resid, pitch ldc). K is zero-padded to a
+// multiple of 64 per split third (K = 513 / 2052 of the word-boundary variant), which adds exact zeros to the sums.
+static int precise_gemm(const LrwEngine& e, uint8_t* PW, const float* x, int ldx, long long rows, int K, const float* w,
+                        int N, const float* bias, const float* resid, float* out, int ldc, cudaStream_t s) {
   bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
   bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
-  RC(split3_f32(x, S3, rows, K, s));
-  RC(pack_linear_weight_split(w, W3, N, K, s));
+  const int Kp = (K + 63) / 64 * 64;
+  RC(split3_f32(x, ldx, S3, rows, K, Kp, s));
+  RC(pack_linear_weight_split(w, W3, N, K, Kp, s));
   IgemmProblem p;
-  p.a = S3, p.a_N = (int)rows, p.a_C = 3 * K, p.cin = 3 * K, p.ntaps = 1;
+  p.a = S3, p.a_N = (int)rows, p.a_C = 3 * Kp, p.cin = 3 * Kp, p.ntaps = 1;
   p.o_N = (int)rows;
-  p.b = W3, p.b_rows = N, p.b_cols = 3 * K;
+  p.b = W3, p.b_rows = N, p.b_cols = 3 * Kp;
   p.out = out, p.out_fp32 = 1, p.ldc = ldc;
   p.bias = bias, p.resid = resid, p.resid_fp32 = 1;
   return igemm_launch(p, s);
@@ -637,7 +646,7 @@ static int precise_conv(const LrwEngine& e, uint8_t* PW, const float* x, int Hin
                         double* bn_stats, cudaStream_t s) {
   bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
   bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
-  RC(split3_f32(x, S3, (long long)e.N * Hin * Hin, c.cin, s));
+  RC(split3_f32(x, c.cin, S3, (long long)e.N * Hin * Hin, c.cin, c.cin, s));
   RC(pack_conv_weight_split(e.P + c.w, W3, c.cout, c.cin, c.R * c.R, s));
   IgemmProblem p;
   p.a = S3, p.a_N = e.N, p.a_H = Hin, p.a_W = Hin, p.a_C = 3 * c.cin, p.cin = 3 * c.cin, p.stride = c.stride;
@@ -661,12 +670,14 @@ static int precise_bn_coef(const LrwEngine& e, long long rows, const BnRef& bn, 
 }
 
 static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos, const long long* tokens,
-                                  long long tok_stride_b, const long long* labels, const float* soft_labels, int train,
-                                  uint32_t skip_mask, float* metrics, cudaStream_t s) {
+                                  long long tok_stride_b, const long long* labels, const float* soft_labels,
+                                  const float* word_mask, int train, uint32_t skip_mask, float* metrics,
+                                  cudaStream_t s) {
   const svsr_lrw_config& c = e.cfg;
-  SVSR_REQUIRE(!e.padded && c.enc_type == 0, "lrw: the parity-mode forward supports the dim-512 x-transformers config only");
+  SVSR_REQUIRE(!e.padded || word_mask, "lrw: dim 513 (data.use_word_boundary) needs the word_mask input");
   RC(engine_pack_deferred(e, s, false));
   const int D = c.dim, inner = c.heads * 64, F = 4 * D;
+  const int Dq = (D + 7) / 8 * 8;  // pitch of the D-wide fp32 rows (== D for dim 512)
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(PW + off); };
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.fe.stats_arena), 0, e.fe.stats_arena_bytes, s));
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(e.acc), 0, 8 * sizeof(double) + 256, s));
@@ -676,7 +687,7 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
   {
     bf16* S3 = reinterpret_cast<bf16*>(PW + e.p_s3);
     bf16* W3 = reinterpret_cast<bf16*>(PW + e.p_w3);
-    RC(split3_f32(PF(e.p_patches), S3, (long long)e.N * e.fe.H0 * e.fe.H0, 64, s));
+    RC(split3_f32(PF(e.p_patches), 64, S3, (long long)e.N * e.fe.H0 * e.fe.H0, 64, 64, s));
     RC(pack_stem_weight_split(e.P + e.fe.stem_conv.w, W3, s));
     IgemmProblem p;
     p.a = S3, p.a_N = c.B, p.a_H = c.T, p.a_W = e.fe.H0 * e.fe.H0, p.a_C = 192, p.cin = 192;
@@ -714,35 +725,60 @@ static int engine_forward_precise(LrwEngine& e, uint8_t* PW, const float* videos
   const int HW4 = e.fe.blocks[7].Hout * e.fe.blocks[7].Hout;
   float* xa = PF(e.p_xs[0]);
   float* xb = PF(e.p_xs[1]);
-  RC(meanpool_cls_f32(x, e.P + e.cls_off, xa, c.B, c.T, HW4, D, s));
-  SVSR_CHECK_CUDA(cudaMemcpyAsync(e.xs_buf(0), xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+  RC(meanpool_cls_f32(x, e.P + e.cls_off, xa, c.B, c.T, HW4, 512, Dq, s));
+  if (e.padded) RC(wb_column(xa, e.P + e.cls_off, word_mask, c.B, c.T, Dq, 512, s));  // channel 512 = word_mask / cls[512]
+  // the product path's tensors ("inputs_embeds", "last_hidden_state") have pitch Dp; their padding columns stay zero
+  auto publish = [&](float* dst, const float* src) {
+    return cudaMemcpy2DAsync(dst, (size_t)e.Dp * 4, src, (size_t)Dq * 4, (size_t)D * 4, (size_t)e.M,
+                             cudaMemcpyDeviceToDevice, s);
+  };
+  SVSR_CHECK_CUDA(publish(e.xs_buf(0), xa));
   // ---- encoder (sublayer outputs ping-pong between xa and xb) ----
-  for (int i = 0; i < c.depth; ++i) {
+  for (int i = 0; i < (int)e.enc.size(); ++i) {
     EncLayerRef& L = e.enc[i];
     if (!(skip_mask & (1u << (2 * i)))) {
-      RC(rmsnorm_fwd_f32(xa, e.P + L.g_a, PF(e.p_xn), e.M, D, 1e-8f, s));
-      RC(precise_gemm(e, PW, PF(e.p_xn), e.M, D, e.P + L.qkv.w, 3 * inner, nullptr, nullptr, PF(e.p_qkv), 3 * inner, s));
+      RC(rmsnorm_fwd_f32(xa, e.P + L.g_a, PF(e.p_xn), e.M, D, Dq, 1e-8f, s));
+      RC(precise_gemm(e, PW, PF(e.p_xn), Dq, e.M, D, e.P + L.qkv.w, 3 * inner, nullptr, nullptr, PF(e.p_qkv), 3 * inner, s));
       RC(attention_fwd_f32(PF(e.p_qkv), e.ws<float>(e.rot), PF(e.p_o), c.B, c.T + 1, c.heads, c.rotary_v, s));
-      RC(precise_gemm(e, PW, PF(e.p_o), e.M, inner, e.P + L.out.w, D, nullptr, xa, xb, D, s));
+      RC(precise_gemm(e, PW, PF(e.p_o), inner, e.M, inner, e.P + L.out.w, D, nullptr, xa, xb, Dq, s));
       float* t = xa;
       xa = xb, xb = t;
     }
     if (!(skip_mask & (1u << (2 * i + 1)))) {
-      RC(rmsnorm_fwd_f32(xa, e.P + L.g_f, PF(e.p_xn), e.M, D, 1e-8f, s));
-      RC(precise_gemm(e, PW, PF(e.p_xn), e.M, D, e.P + L.ff1.w, 2 * F, e.P + L.ff1.b, nullptr, PF(e.p_h), 2 * F, s));
+      RC(rmsnorm_fwd_f32(xa, e.P + L.g_f, PF(e.p_xn), e.M, D, Dq, 1e-8f, s));
+      RC(precise_gemm(e, PW, PF(e.p_xn), Dq, e.M, D, e.P + L.ff1.w, 2 * F, e.P + L.ff1.b, nullptr, PF(e.p_h), 2 * F, s));
       RC(geglu_fwd_f32(PF(e.p_h), PF(e.p_u), e.M, F, s));
-      RC(precise_gemm(e, PW, PF(e.p_u), e.M, F, e.P + L.ff2.w, D, e.P + L.ff2.b, xa, xb, D, s));
+      RC(precise_gemm(e, PW, PF(e.p_u), F, e.M, F, e.P + L.ff2.w, D, e.P + L.ff2.b, xa, xb, Dq, s));
       float* t = xa;
       xa = xb, xb = t;
     }
   }
-  SVSR_CHECK_CUDA(cudaMemcpyAsync(e.xs_buf(2 * c.depth), xa, (size_t)e.M * D * 4, cudaMemcpyDeviceToDevice, s));
+  if (c.enc_type == 1) {
+    // transformers.BertModel(inputs_embeds=...) (lightning.py:90-92,152-156): embeddings (+ position, + token type 0,
+    // LayerNorm), then post-LayerNorm layers; dropouts are not applied in parity mode (it is the deterministic function)
+    const int I = c.bert_intermediate, L1 = c.T + 1;
+    float* x1 = PF(e.p_xn);
+    RC(bert_embed_fwd(xa, e.P + e.b_pos, e.P + e.b_tt, x1, e.M, L1, D, s));
+    RC(layernorm_fwd_f32(x1, e.P + e.b_eln_g, e.P + e.b_eln_b, xa, e.M, D, c.bert_ln_eps, s));
+    for (int i = 0; i < c.depth; ++i) {
+      BertLayerRef& Lb = e.bert[i];
+      RC(precise_gemm(e, PW, xa, D, e.M, D, e.P + Lb.qkv.w, 3 * D, e.P + Lb.qkv.b, nullptr, PF(e.p_qkv), 3 * D, s));
+      RC(attention_fwd_f32(PF(e.p_qkv), nullptr, PF(e.p_o), c.B, L1, c.heads, 0, s));
+      RC(precise_gemm(e, PW, PF(e.p_o), D, e.M, D, e.P + Lb.out.w, D, e.P + Lb.out.b, xa, xb, D, s));
+      RC(layernorm_fwd_f32(xb, e.P + Lb.ln1_g, e.P + Lb.ln1_b, x1, e.M, D, c.bert_ln_eps, s));
+      RC(precise_gemm(e, PW, x1, D, e.M, D, e.P + Lb.inter.w, I, e.P + Lb.inter.b, nullptr, PF(e.p_h), I, s));
+      RC(gelu_fwd_f32(PF(e.p_h), PF(e.p_u), (long long)e.M * I, s));
+      RC(precise_gemm(e, PW, PF(e.p_u), I, e.M, I, e.P + Lb.outd.w, D, e.P + Lb.outd.b, x1, xb, D, s));
+      RC(layernorm_fwd_f32(xb, e.P + Lb.ln2_g, e.P + Lb.ln2_b, xa, e.M, D, c.bert_ln_eps, s));
+    }
+  }
+  SVSR_CHECK_CUDA(publish(e.last_hidden(), xa));
   // ---- heads ----
   const int AGV = c.audio_alignment * c.vq_groups * c.audio_vocab;
-  RC(split_last_f32(xa, PF(e.p_lc), PF(e.p_lf), c.B, c.T, D, s));
-  RC(precise_gemm(e, PW, PF(e.p_lc), c.B, D, e.P + e.cat.w, c.num_labels, e.P + e.cat.b, nullptr, e.ws<float>(e.logits_c),
-                  e.cat_ld, s));
-  RC(precise_gemm(e, PW, PF(e.p_lf), e.N, D, e.P + e.aud.w, AGV, e.P + e.aud.b, nullptr, e.ws<float>(e.logits_a), AGV, s));
+  RC(split_last_f32(xa, Dq, PF(e.p_lc), PF(e.p_lf), c.B, c.T, D, s));
+  RC(precise_gemm(e, PW, PF(e.p_lc), D, c.B, D, e.P + e.cat.w, c.num_labels, e.P + e.cat.b, nullptr,
+                  e.ws<float>(e.logits_c), e.cat_ld, s));
+  RC(precise_gemm(e, PW, PF(e.p_lf), D, e.N, D, e.P + e.aud.w, AGV, e.P + e.aud.b, nullptr, e.ws<float>(e.logits_a), AGV, s));
   const long long audio_rows = (long long)e.N * c.audio_alignment * c.vq_groups;
   RC(category_ce(e.ws<float>(e.logits_c), e.cat_ld, labels, soft_labels, c.B, c.num_labels, c.label_smoothing, nullptr,
                  e.cat_ld, e.ws<double>(e.acc), 0.f, s));
@@ -964,7 +1000,8 @@ int svsr_lrw_forward(void* h, const float* videos, const int64_t* tokens, int64_
 int64_t svsr_lrw_precise_workspace_bytes(void* h) { return (int64_t)static_cast<LrwEngine*>(h)->p_bytes; }
 int svsr_lrw_forward_precise(void* h, void* precise_ws, int64_t precise_ws_bytes, const float* videos,
                              const int64_t* tokens, int64_t tok_stride_b, const int64_t* labels,
-                             const float* soft_labels, int train, uint32_t skip_mask, float* metrics, void* stream) {
+                             const float* soft_labels, const float* word_mask, int train, uint32_t skip_mask,
+                             float* metrics, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);
   SVSR_REQUIRE(e->WS, "lrw: bind() first");
   SVSR_REQUIRE(precise_ws && (size_t)precise_ws_bytes >= e->p_bytes && ((uintptr_t)precise_ws & 1023) == 0,
@@ -973,8 +1010,8 @@ int svsr_lrw_forward_precise(void* h, void* precise_ws, int64_t precise_ws_bytes
   SVSR_REQUIRE(tok_stride_b >= (int64_t)e->cfg.T * e->cfg.audio_alignment * e->cfg.vq_groups,
                "lrw_forward_precise: audio_tokens has fewer than T*alignment rows per clip");
   return engine_forward_precise(*e, static_cast<uint8_t*>(precise_ws), videos, reinterpret_cast<const long long*>(tokens),
-                                tok_stride_b, reinterpret_cast<const long long*>(labels), soft_labels, train, skip_mask,
-                                metrics, static_cast<cudaStream_t>(stream));
+                                tok_stride_b, reinterpret_cast<const long long*>(labels), soft_labels, word_mask, train,
+                                skip_mask, metrics, static_cast<cudaStream_t>(stream));
 }
 int svsr_lrw_forward_videos(void* h, const float* videos, int train, void* stream) {
   LrwEngine* e = static_cast<LrwEngine*>(h);

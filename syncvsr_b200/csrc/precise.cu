@@ -11,14 +11,16 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 #define GRID_STRIDE(i, total) \
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
 
-__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int C) {
-  GRID_STRIDE(i, rows * C) {
-    const long long r = i / C;
-    const int c = (int)(i % C);
+// x fp32 [rows, C] at pitch ldx -> [rows, 3 Cp] = hi | lo | hi, columns C..Cp of every third are zero
+__global__ void split3_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ out, long long rows, int C,
+                              int Cp) {
+  GRID_STRIDE(i, rows * Cp) {
+    const long long r = i / Cp;
+    const int c = (int)(i % Cp);
     __nv_bfloat16 hi, lo;
-    split2(x[i], hi, lo);
-    __nv_bfloat16* o = out + r * 3 * C;
-    o[c] = hi, o[C + c] = lo, o[2 * C + c] = hi;
+    split2(c < C ? x[r * ldx + c] : 0.f, hi, lo);
+    __nv_bfloat16* o = out + r * 3 * Cp;
+    o[c] = hi, o[Cp + c] = lo, o[2 * Cp + c] = hi;
   }
 }
 __global__ void pack_conv_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
@@ -33,14 +35,15 @@ __global__ void pack_conv_split_kernel(const float* __restrict__ w, __nv_bfloat1
     o[ci] = hi, o[Cin + ci] = hi, o[2 * Cin + ci] = lo;
   }
 }
-__global__ void pack_linear_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K) {
-  GRID_STRIDE(i, (long long)N * K) {
-    const long long n = i / K;
-    const int k = (int)(i % K);
+__global__ void pack_linear_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K,
+                                         int Kp) {
+  GRID_STRIDE(i, (long long)N * Kp) {
+    const long long n = i / Kp;
+    const int k = (int)(i % Kp);
     __nv_bfloat16 hi, lo;
-    split2(w[i], hi, lo);
-    __nv_bfloat16* o = out + n * 3 * K;
-    o[k] = hi, o[K + k] = hi, o[2 * K + k] = lo;
+    split2(k < K ? w[n * K + k] : 0.f, hi, lo);
+    __nv_bfloat16* o = out + n * 3 * Kp;
+    o[k] = hi, o[Kp + k] = hi, o[2 * Kp + k] = lo;
   }
 }
 __global__ void pack_stem_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
@@ -103,33 +106,33 @@ __global__ void stem_pool_f32_kernel(const float* __restrict__ y0, const float* 
   }
 }
 __global__ void meanpool_cls_f32_kernel(const float* __restrict__ a, const float* __restrict__ cls,
-                                        float* __restrict__ xs, int B, int T, int HW, int C) {
+                                        float* __restrict__ xs, int B, int T, int HW, int C, int ld) {
   GRID_STRIDE(i, (long long)B * (T + 1) * C) {
     const int c = (int)(i % C);
     const long long row = i / C;
     const int tt = (int)(row % (T + 1));
     const long long b = row / (T + 1);
     if (tt == 0) {
-      xs[i] = cls[c];
+      xs[row * ld + c] = cls[c];
       continue;
     }
     const float* src = a + ((b * T + (tt - 1)) * HW) * (long long)C + c;
     float acc = 0.f;
     for (int p = 0; p < HW; ++p) acc += src[(long long)p * C];
-    xs[i] = acc / (float)HW;
+    xs[row * ld + c] = acc / (float)HW;
   }
 }
 __global__ void rmsnorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y,
-                                   int M, int D, float eps) {
+                                   int M, int D, int ld, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int row = warp; row < M; row += nwarps) {
-    const float* xr = x + (long long)row * D;
+    const float* xr = x + (long long)row * ld;
     float ss = 0.f;
     for (int j = lane; j < D; j += 32) ss += xr[j] * xr[j];
     ss = warp_sum(ss);
     const float inv = 1.0f / fmaxf(sqrtf(ss) * rsqrtf((float)D), eps);
-    for (int j = lane; j < D; j += 32) y[(long long)row * D + j] = xr[j] * inv * g[j];
+    for (int j = lane; j < D; j += 32) y[(long long)row * ld + j] = xr[j] * inv * g[j];
   }
 }
 // one CTA per (batch, head); plain fp32, n <= 64, head dim 64
@@ -148,7 +151,7 @@ attention_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ ro
     const float* src = qkv + (long long)b * n * ld + which * inner + h * 64;
     for (int i = threadIdx.x; i < n * 64; i += blockDim.x) dst[(i >> 6) * 65 + (i & 63)] = src[(long long)(i >> 6) * ld + (i & 63)];
     __syncthreads();
-    if (which < 2 || rotary_v) {
+    if (rot && (which < 2 || rotary_v)) {
       for (int i = threadIdx.x; i < n * 16; i += blockDim.x) {
         const int pos = i >> 4, f = i & 15;
         const float c = rot[pos * 32 + f], s_ = rot[pos * 32 + 16 + f];
@@ -183,6 +186,25 @@ attention_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ ro
     o[((long long)b * n + r) * inner + h * 64 + d] = acc;
   }
 }
+// torch.nn.LayerNorm over the last dimension (biased variance), one warp per row
+__global__ void layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                     float* __restrict__ y, int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < M; row += nwarps) {
+    const float* xr = x + (long long)row * D;
+    float sum = 0.f;
+    for (int j = lane; j < D; j += 32) sum += xr[j];
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+    for (int j = lane; j < D; j += 32) sq += (xr[j] - mean) * (xr[j] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+    for (int j = lane; j < D; j += 32) y[(long long)row * D + j] = (xr[j] - mean) * rstd * g[j] + b[j];
+  }
+}
+__global__ void gelu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  GRID_STRIDE(i, n) y[i] = gelu_f(x[i]);
+}
 __global__ void geglu_f32_kernel(const float* __restrict__ h, float* __restrict__ u, long long M, int F) {
   GRID_STRIDE(i, M * F) {
     const long long r = i / F;
@@ -190,17 +212,18 @@ __global__ void geglu_f32_kernel(const float* __restrict__ h, float* __restrict_
     u[i] = h[r * 2 * F + c] * gelu_f(h[r * 2 * F + F + c]);
   }
 }
-__global__ void split_last_f32_kernel(const float* __restrict__ last, float* __restrict__ cls,
+__global__ void split_last_f32_kernel(const float* __restrict__ last, int ld, float* __restrict__ cls,
                                       float* __restrict__ frames, int B, int T, int D) {
   GRID_STRIDE(i, (long long)B * (T + 1) * D) {
     const int d = (int)(i % D);
     const long long row = i / D;
     const int tt = (int)(row % (T + 1));
     const long long b = row / (T + 1);
+    const float v = last[row * ld + d];
     if (tt == 0)
-      cls[b * D + d] = last[i];
+      cls[b * D + d] = v;
     else
-      frames[(b * T + tt - 1) * D + d] = last[i];
+      frames[(b * T + tt - 1) * D + d] = v;
   }
 }
 
@@ -215,16 +238,18 @@ inline unsigned nblk(long long total) {
 
 }  // namespace
 
-int split3_f32(const float* x, __nv_bfloat16* out, long long rows, int C, cudaStream_t s) {
-  split3_kernel<<<nblk(rows * C), 256, 0, s>>>(x, out, rows, C);
+int split3_f32(const float* x, int ldx, __nv_bfloat16* out, long long rows, int C, int Cp, cudaStream_t s) {
+  SVSR_REQUIRE(ldx >= C && Cp >= C && Cp % 8 == 0, "split3_f32: pitch %d / padded width %d do not cover C=%d", ldx, Cp, C);
+  split3_kernel<<<nblk(rows * Cp), 256, 0, s>>>(x, ldx, out, rows, C, Cp);
   LAUNCHED();
 }
 int pack_conv_weight_split(const float* w, __nv_bfloat16* out, int Cout, int Cin, int RS, cudaStream_t s) {
   pack_conv_split_kernel<<<nblk((long long)Cout * Cin * RS), 256, 0, s>>>(w, out, Cout, Cin, RS);
   LAUNCHED();
 }
-int pack_linear_weight_split(const float* w, __nv_bfloat16* out, int N, int K, cudaStream_t s) {
-  pack_linear_split_kernel<<<nblk((long long)N * K), 256, 0, s>>>(w, out, N, K);
+int pack_linear_weight_split(const float* w, __nv_bfloat16* out, int N, int K, int Kp, cudaStream_t s) {
+  SVSR_REQUIRE(Kp >= K && Kp % 8 == 0, "pack_linear_weight_split: padded width %d does not cover K=%d", Kp, K);
+  pack_linear_split_kernel<<<nblk((long long)N * Kp), 256, 0, s>>>(w, out, N, K, Kp);
   LAUNCHED();
 }
 int pack_stem_weight_split(const float* w, __nv_bfloat16* out, cudaStream_t s) {
@@ -246,12 +271,13 @@ int stem_bn_gelu_pool_f32(const float* y0, const float* coef, float* out, int N,
   stem_pool_f32_kernel<<<nblk((long long)N * OH * OW * 64), 256, 0, s>>>(y0, coef, out, N, IH, IW, OH, OW);
   LAUNCHED();
 }
-int meanpool_cls_f32(const float* a, const float* cls, float* x_stream, int B, int T, int HW, int C, cudaStream_t s) {
-  meanpool_cls_f32_kernel<<<nblk((long long)B * (T + 1) * C), 256, 0, s>>>(a, cls, x_stream, B, T, HW, C);
+int meanpool_cls_f32(const float* a, const float* cls, float* x_stream, int B, int T, int HW, int C, int ld,
+                     cudaStream_t s) {
+  meanpool_cls_f32_kernel<<<nblk((long long)B * (T + 1) * C), 256, 0, s>>>(a, cls, x_stream, B, T, HW, C, ld);
   LAUNCHED();
 }
-int rmsnorm_fwd_f32(const float* x, const float* g, float* y, int M, int D, float eps, cudaStream_t s) {
-  rmsnorm_f32_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, y, M, D, eps);
+int rmsnorm_fwd_f32(const float* x, const float* g, float* y, int M, int D, int ld, float eps, cudaStream_t s) {
+  rmsnorm_f32_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, y, M, D, ld, eps);
   LAUNCHED();
 }
 int attention_fwd_f32(const float* qkv, const float* rot, float* o, int B, int n, int heads, int rotary_v,
@@ -267,12 +293,20 @@ int attention_fwd_f32(const float* qkv, const float* rot, float* o, int B, int n
   attention_f32_kernel<<<B * heads, 128, smem, s>>>(qkv, rot, o, n, heads, rotary_v);
   LAUNCHED();
 }
+int layernorm_fwd_f32(const float* x, const float* g, const float* b, float* y, int M, int D, float eps, cudaStream_t s) {
+  layernorm_f32_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, y, M, D, eps);
+  LAUNCHED();
+}
+int gelu_fwd_f32(const float* x, float* y, long long n, cudaStream_t s) {
+  gelu_f32_kernel<<<nblk(n), 256, 0, s>>>(x, y, n);
+  LAUNCHED();
+}
 int geglu_fwd_f32(const float* h, float* u, int M, int F, cudaStream_t s) {
   geglu_f32_kernel<<<nblk((long long)M * F), 256, 0, s>>>(h, u, M, F);
   LAUNCHED();
 }
-int split_last_f32(const float* last, float* cls, float* frames, int B, int T, int D, cudaStream_t s) {
-  split_last_f32_kernel<<<nblk((long long)B * (T + 1) * D), 256, 0, s>>>(last, cls, frames, B, T, D);
+int split_last_f32(const float* last, int ld, float* cls, float* frames, int B, int T, int D, cudaStream_t s) {
+  split_last_f32_kernel<<<nblk((long long)B * (T + 1) * D), 256, 0, s>>>(last, ld, cls, frames, B, T, D);
   LAUNCHED();
 }
 

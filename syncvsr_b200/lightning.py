@@ -447,10 +447,16 @@ class TransformerLightningModule(nn.Module):
     def forward_precise(self, videos: torch.Tensor, audio_tokens: torch.Tensor, labels: torch.Tensor,
                         word_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Parity-mode forward (fp32 activations, split-bf16 tensor-core operands; csrc/precise.cuh): same outputs as
-        forward() at fp32-class accuracy. Forward only; `last_hidden_state()` / `logits_audio()` read its results."""
-        if self.use_wb or self.hf:
-            raise SvsrError("forward_precise (parity mode) supports the dim-512 x-transformers configuration only")
+        forward() at fp32-class accuracy, for every encoder configuration (x-transformers dim 512, the dim-513 word-boundary
+        variant, HuggingFace BERT). Forward only and dropout-free; `last_hidden_state()` / `logits_audio()` read its
+        results."""
         videos = videos.to(self.device_, torch.float32).contiguous()
+        wm = None
+        if self.use_wb:  # word_mask is hidden channel 512 (lightning.py:145-150)
+            B, T = videos.shape[0], videos.shape[2]
+            wm = word_mask.to(self.device_, torch.float32).contiguous()
+            if tuple(wm.shape) != (B, T):
+                raise ValueError(f"word_mask must be [B, T] = {(B, T)} with data.use_word_boundary, got {tuple(wm.shape)}")
         audio_tokens = audio_tokens.to(self.device_, torch.long).contiguous()
         labels = labels.to(self.device_)
         self._ensure(videos)
@@ -467,7 +473,8 @@ class TransformerLightningModule(nn.Module):
             self._h, C.c_void_p(pptr), C.c_int64(need), C.c_void_p(videos.data_ptr()),
             C.c_void_p(audio_tokens.data_ptr()), C.c_int64(audio_tokens.stride(0)),
             C.c_void_p(hard.data_ptr() if hard is not None else 0), C.c_void_p(soft.data_ptr() if soft is not None else 0),
-            C.c_int(int(self.training)), C.c_uint32(0), C.c_void_p(metrics.data_ptr()), self._stream()),
+            C.c_void_p(wm.data_ptr() if wm is not None else 0), C.c_int(int(self.training)), C.c_uint32(0),
+            C.c_void_p(metrics.data_ptr()), self._stream()),
             "svsr_lrw_forward_precise")
         self._precise_logits = True
         return {"loss_total": metrics[0], "loss_category": metrics[1], "loss_audio": metrics[2],

@@ -124,6 +124,68 @@ def test_parity_mode_forward_matches_reference_within_1e3(Module, name, golden_d
     assert float(m.state_dict()["stem3d.1.running_var"].mean()) == 1.0
 
 
+def test_parity_mode_word_boundary_variant_within_1e3(Module, golden_dir):
+    """Parity mode of the dim-513 word-boundary configuration (lightning.py:46-47,145-150) against the reference's own
+    forward: K = 513 / 2052 contractions are zero-padded per split third, the 513-wide fp32 rows live at pitch 520."""
+    fx = torch.load(golden_dir / "lrw_wb_d2.pt")
+    meta = fx["meta"]
+    m = Module(make_cfg(depth=meta["depth"], use_wb=True)).train()
+    P = O.make_params(meta["seed_p"], depth=meta["depth"], dim=513)
+    m.load_state_dict(P, strict=False)
+    videos, tokens, labels, _ = O.make_inputs(meta["seed_x"], meta["B"])
+    wm = fx["word_mask"]
+    with pytest.raises(Exception):
+        m.forward_precise(videos.cuda(), tokens.cuda(), labels.cuda(), wm[:, :5].cuda())  # wrong word_mask shape
+    out = m.forward_precise(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    g = fx["metrics"]
+    for k in ("loss_total", "loss_category", "loss_audio"):
+        assert float(out[k]) == pytest.approx(g[k], rel=1e-4), k
+    assert float(out["accuracy_top1"]) == g["accuracy_top1"] and float(out["accuracy_top5"]) == g["accuracy_top5"]
+    last = m.last_hidden_state().cpu()
+    assert last.shape == (meta["B"], 30, 513)
+    assert rel(last[:, 0, :], fx["last_hidden_state_cls"]) < 1e-3
+    assert rel(last[:, 7, :], fx["last_hidden_state_t7"]) < 1e-3
+    assert last.double().abs().sum().item() == pytest.approx(fx["last_hidden_state_abs"], rel=1e-4)
+    la = m.logits_audio().cpu().reshape(meta["B"], 29, -1)
+    assert rel(la[:, 3, :], fx["logits_audio_t3"]) < 1e-3
+    assert la.double().abs().sum().item() == pytest.approx(fx["logits_audio_abs"], rel=1e-3)
+    assert rel(m.logits_category().cpu(), fx["logits_category"]) < 1e-3
+    emb = m._named_tensor("inputs_embeds", (meta["B"], 30, 576)).cpu()
+    assert torch.equal(emb[:, 1:, 512], wm) and float(emb[:, :, 513:].abs().sum()) == 0.0
+    assert rel(emb[:, 1:, :512].flatten(0, 1)[:2], fx["inputs_embeds_t0"]) < 1e-3
+    # the throughput-mode step still runs on the same engine afterwards
+    out2 = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    assert float(out2["loss_total"]) == pytest.approx(g["loss_total"], rel=1e-3)
+
+
+def test_parity_mode_huggingface_bert_variant_within_1e3(Module, golden_dir):
+    """Parity mode of `model.bert.type: huggingface` (lightning.py:90-92,152-156) against the reference module's own
+    forward through transformers.BertModel: embeddings + LayerNorm, post-LayerNorm layers, erf GELU, all fp32."""
+    fx = torch.load(golden_dir / "lrw_hf_d2.pt")
+    meta, hf = fx["meta"], fx["meta"]["hf"]
+    cfg = make_cfg(depth=meta["depth"])
+    cfg["model"]["bert"]["type"] = "huggingface"
+    for k, v in hf.items():
+        cfg["model"]["bert"][k] = v
+    m = Module(cfg).train()
+    P = O.make_hf_params(O.make_params(meta["seed_p"], depth=meta["depth"]), hf, seed=meta["seed_p"] + 100)
+    m.load_state_dict(P, strict=False)
+    videos, tokens, labels, wm = O.make_inputs(meta["seed_x"], meta["B"])
+    out = m.forward_precise(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+    g = fx["metrics"]
+    for k in ("loss_total", "loss_category", "loss_audio"):
+        assert float(out[k]) == pytest.approx(g[k], rel=1e-4), k
+    assert float(out["accuracy_top1"]) == g["accuracy_top1"] and float(out["accuracy_top5"]) == g["accuracy_top5"]
+    last = m.last_hidden_state().cpu()
+    assert rel(last[:, 0, :], fx["last_hidden_state_cls"]) < 1e-3
+    assert rel(last[:, 7, :], fx["last_hidden_state_t7"]) < 1e-3
+    assert last.double().abs().sum().item() == pytest.approx(fx["last_hidden_state_abs"], rel=1e-4)
+    la = m.logits_audio().cpu().reshape(meta["B"], 29, -1)
+    assert rel(la[:, 3, :], fx["logits_audio_t3"]) < 1e-3
+    assert la.double().abs().sum().item() == pytest.approx(fx["logits_audio_abs"], rel=1e-3)
+    assert rel(m.logits_category().cpu(), fx["logits_category"]) < 1e-3
+
+
 def test_forward_backward_vs_oracle_same_storage_points(Module):
     """Oracle run with bf16 rounding at the CUDA path's storage points: tight on scalars, bf16-chaos-limited on deep
     tensors; gradients of the heads/encoder agree to bf16 precision, trunk gradients in direction and norm."""
