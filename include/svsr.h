@@ -118,6 +118,14 @@ int svsr_gemm_wgrad(const void* dy, int ldy, const void* x, int ldx, float* dw, 
 /* videos fp32 [B,1,T,H,W] -> 7x7/stride-2/pad-3 patches bf16 [B,T,OH*OW,64] (slot kh*8+kw); the 5-tap temporal
  * part of Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (lightning.py:50) then runs as an implicit GEMM over these. */
 int svsr_stem_patch(const float* videos, void* patches, int B, int T, int H, int W, void* stream);
+/* The same Conv3d WITHOUT the patch tensor (csrc/stem_direct.cu): the 7x7/s2 window rows are built in shared memory
+ * from a bf16 copy of the video (video_bf16: [B,T,H,W] bf16, even W, (H/2)*(W/2) a multiple of 16). Forward: y0 bf16
+ * [B,T,OH*OW,64], w_packed bf16 [64,320] (column kt*64 + kh*8 + kw), bn_stats fp64 [2][64] (+=) or NULL; bit-identical to
+ * svsr_stem_patch + the 5-tap implicit GEMM. Weight gradient: out fp32 [320, ldo] (row kt*64 + kh*8 + kw) += . */
+int svsr_stem_conv_direct(const void* video_bf16, const void* w_packed, void* y0, double* bn_stats, int B, int T, int H,
+                          int W, void* stream);
+int svsr_stem_wgrad_direct(const void* video_bf16, const void* dz, float* out, int ldo, int B, int T, int H, int W,
+                           void* stream);
 /* nn.BatchNorm{2,3}d forward (+ optional residual with its own BN coefficients, + ReLU): lightning.py:51 and the
  * bn1/bn2/downsample.1 of every BasicBlock. coef (fp32 [4][C]) receives mean, invstd, scale, shift for backward.
  * train=1: batch statistics + running-stat update; train=0: running statistics. stats_scratch: fp64 [2*C]. */

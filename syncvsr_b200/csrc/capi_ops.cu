@@ -7,6 +7,7 @@
 #include "heads.cuh"
 #include "igemm.cuh"
 #include "conformer.cuh"
+#include "stem_direct.cuh"
 
 using namespace svsr;
 typedef __nv_bfloat16 bf16;
@@ -21,6 +22,18 @@ extern "C" {
 
 int svsr_stem_patch(const float* videos, void* patches, int B, int T, int H, int W, void* stream) {
   return stem_patch(videos, static_cast<bf16*>(patches), B, T, H, W, ST(stream));
+}
+
+int svsr_stem_conv_direct(const void* video_bf16, const void* w_packed, void* y0, double* bn_stats, int B, int T, int H,
+                          int W, void* stream) {
+  SVSR_REQUIRE(video_bf16 && w_packed && y0, "stem_conv_direct: null pointer");
+  return stem_direct_fwd(video_bf16, static_cast<const bf16*>(w_packed), static_cast<bf16*>(y0), bn_stats, B, T, H, W, 0.0,
+                         ST(stream));
+}
+int svsr_stem_wgrad_direct(const void* video_bf16, const void* dz, float* out, int ldo, int B, int T, int H, int W,
+                           void* stream) {
+  SVSR_REQUIRE(video_bf16 && dz && out, "stem_wgrad_direct: null pointer");
+  return stem_direct_wgrad(video_bf16, static_cast<const bf16*>(dz), out, ldo, B, T, H, W, 0.0, ST(stream));
 }
 
 int svsr_batchnorm_fwd(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float* running_mean,

@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "igemm.cuh"
 #include "wgrad.cuh"
+#include "stem_direct.cuh"
 
 namespace svsr {
 
@@ -117,6 +118,10 @@ struct Frontend {
   BnRef stem_bn;
   BlockRef blocks[8];
   size_t patches = 0, y0 = 0, x1 = 0, argmax = 0, gbuf[9] = {0}, stem_dz = 0;
+  // SVSR_STEM_DIRECT=1: no patch tensor -- the stem's forward and weight-gradient kernels build the 7x7/s2 window rows
+  // in shared memory from `vid`, a bf16 copy of the clip batch kept for backward (stem_direct.cu)
+  bool direct = false;
+  size_t vid = 0;
   size_t stats_arena = 0, stats_arena_bytes = 0;  // fp64 BN statistic accumulators (forward + backward slot per BN)
 };
 
@@ -390,7 +395,14 @@ static int frontend_build(EngineBase& e, Frontend& f, const std::string& stem_w,
 // activations, BN statistic slots and backward scratch of the frontend
 static void frontend_alloc(EngineBase& e, Frontend& f, Bump& b) {
   const size_t n0 = (size_t)e.N * f.H0 * f.H0 * 64;
-  f.patches = b.take(n0 * 2);
+  {
+    const char* d = getenv("SVSR_STEM_DIRECT");
+    f.direct = d && d[0] == '1' && stem_direct_supported(f.H, f.H);
+  }
+  if (f.direct)
+    f.vid = b.take((size_t)e.N * f.H * f.H * 2);
+  else
+    f.patches = b.take(n0 * 2);
   f.y0 = b.take(n0 * 2);
   const size_t n1 = (size_t)e.N * f.H1 * f.H1 * 64;
   f.x1 = b.take(n1 * 2);
@@ -438,8 +450,13 @@ static int frontend_forward(EngineBase& e, Frontend& f, const float* videos, int
   const int act = f.swish ? 2 : 1;
   SVSR_CHECK_CUDA(cudaMemsetAsync(e.ws<uint8_t>(f.stats_arena), 0, f.stats_arena_bytes, s));
   // ---- stem: 7x7/s2 patch gather, 5-tap temporal implicit GEMM, BN3d + GELU|Swish + max-pool ----
-  RC(stem_patch(videos, e.ws<bf16>(f.patches), f.B, f.T, f.H, f.H, s));
-  {
+  if (f.direct) {
+    RC(cast_f32_to_bf16(videos, e.ws<bf16>(f.vid), (long long)e.N * f.H * f.H, s));
+    RC(stem_direct_fwd(e.ws<bf16>(f.vid), e.ws<bf16>(f.stem_conv.wf), e.ws<bf16>(f.y0),
+                       train ? e.ws<double>(f.stem_bn.stats_f) : nullptr, f.B, f.T, f.H, f.H,
+                       2.0 * e.N * f.H0 * f.H0 * 64.0 * 245.0, s));
+  } else {
+    RC(stem_patch(videos, e.ws<bf16>(f.patches), f.B, f.T, f.H, f.H, s));
     IgemmProblem p;
     p.a = e.ws<bf16>(f.patches), p.a_N = f.B, p.a_H = f.T, p.a_W = f.H0 * f.H0, p.a_C = 64, p.cin = 64;
     p.ntaps = 5;
@@ -630,15 +647,19 @@ static int frontend_backward(EngineBase& e, Frontend& f, SideQueue& sq, cudaStre
   {
     float* tmp = e.ws<float>(e.wgrad_tmp);
     SVSR_CHECK_CUDA(cudaMemsetAsync(tmp, 0, 320 * 64 * 4, w));
-    WgradProblem p;
-    p.a = e.ws<bf16>(f.patches), p.a_N = f.B, p.a_H = f.T, p.a_W = f.H0 * f.H0, p.a_C = 64, p.a_cin = 64;
-    p.ntaps = 5;
-    for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0;
-    p.b = dz, p.b_C = 64, p.n_cols = 64;
-    p.k_N = f.B, p.k_H = f.T, p.k_W = f.H0 * f.H0;
-    p.out = tmp, p.ldo = 64;
-    p.algo_flops = 2.0 * e.N * f.H0 * f.H0 * 64.0 * 245.0;
-    RC(wgrad_launch(p, w));
+    if (f.direct) {
+      RC(stem_direct_wgrad(e.ws<bf16>(f.vid), dz, tmp, 64, f.B, f.T, f.H, f.H, 2.0 * e.N * f.H0 * f.H0 * 64.0 * 245.0, w));
+    } else {
+      WgradProblem p;
+      p.a = e.ws<bf16>(f.patches), p.a_N = f.B, p.a_H = f.T, p.a_W = f.H0 * f.H0, p.a_C = 64, p.a_cin = 64;
+      p.ntaps = 5;
+      for (int kt = 0; kt < 5; ++kt) p.tap_dh[kt] = kt - 2, p.tap_dw[kt] = 0;
+      p.b = dz, p.b_C = 64, p.n_cols = 64;
+      p.k_N = f.B, p.k_H = f.T, p.k_W = f.H0 * f.H0;
+      p.out = tmp, p.ldo = 64;
+      p.algo_flops = 2.0 * e.N * f.H0 * f.H0 * 64.0 * 245.0;
+      RC(wgrad_launch(p, w));
+    }
     RC(unpack_stem_wgrad(tmp, e.G + f.stem_conv.w, w));
   }
   return sq.join();

@@ -152,6 +152,30 @@ def stem_patch(videos: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def stem_conv_direct(videos: torch.Tensor, w_packed: torch.Tensor):
+    """Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) without the patch tensor: returns (y0 bf16 [B,T,OH*OW,64], stats fp64 [2,64])."""
+    _req(videos, torch.float32, "videos"), _req(w_packed, torch.bfloat16, "w_packed")
+    B, _, T, H, W = videos.shape
+    vb = videos.to(torch.bfloat16).contiguous()
+    y = torch.empty(B, T, (H // 2) * (W // 2), 64, device=videos.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2, 64, device=videos.device, dtype=torch.float64)
+    check(lib().svsr_stem_conv_direct(ptr(vb), ptr(w_packed), ptr(y), ptr(stats), _i(B), _i(T), _i(H), _i(W),
+                                      stream_ptr()), "svsr_stem_conv_direct")
+    return y, stats
+
+
+def stem_wgrad_direct(videos: torch.Tensor, dz: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Weight gradient of stem_conv_direct: fp32 [320, 64] (row kt*64 + kh*8 + kw); accumulates into `out`."""
+    _req(videos, torch.float32, "videos"), _req(dz, torch.bfloat16, "dz")
+    B, _, T, H, W = videos.shape
+    vb = videos.to(torch.bfloat16).contiguous()
+    if out is None:
+        out = torch.zeros(320, 64, device=videos.device, dtype=torch.float32)
+    check(lib().svsr_stem_wgrad_direct(ptr(vb), ptr(dz), ptr(out), _i(out.stride(0)), _i(B), _i(T), _i(H), _i(W),
+                                       stream_ptr()), "svsr_stem_wgrad_direct")
+    return out
+
+
 def batchnorm_fwd(x, gamma, beta, running_mean, running_var, train=True, res=None, res_coef=None, relu=False,
                   eps=1e-5, momentum=0.1):
     """x: bf16 [..., C] channels-last. Returns (out bf16, coef fp32 [4, C])."""

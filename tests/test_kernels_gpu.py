@@ -274,6 +274,48 @@ def test_stem_conv_matches_conv3d(ops):
     assert rel(y.view(B, T, 44, 44, 64), ref.permute(0, 2, 3, 4, 1)) < BF16_TOL
 
 
+@pytest.mark.parametrize("B,T,S", [(2, 29, 88), (1, 8, 96), (3, 5, 88), (1, 1, 88), (1, 150, 88), (5, 21, 96)])
+def test_stem_without_patch_tensor_matches_patch_path(ops, B, T, S):
+    """stem_direct.cu (7x7/s2 window rows built in shared memory from the bf16 video) against the patch tensor + 5-tap
+    temporal implicit GEMM it replaces: forward bit-identical (same operand bytes, same MMA sequence), fused BatchNorm
+    statistics, weight gradient up to the fp32 order of the cross-CTA reduction; and against Conv3d itself."""
+    v = randn(B, 1, T, S, S, seed=61, dtype=torch.float32)
+    w = randn(64, 1, 5, 7, 7, seed=62, scale=0.05, dtype=torch.float32)
+    wp = torch.zeros(64, 5, 8, 8, device="cuda")
+    wp[:, :, :7, :7] = w[:, 0]
+    wp = wp.reshape(64, 320).bfloat16().contiguous()
+    taps = [(kt - 2, 0) for kt in range(5)]
+    P = ops.stem_patch(v)
+    y_ref, st_ref = ops.conv_taps_fprop_bnstats(P, wp, taps)
+    y, st = ops.stem_conv_direct(v, wp)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    assert rel(st, st_ref) < 1e-6
+    ref = F.conv3d(v.bfloat16().float(), w.bfloat16().float(), None, (1, 2, 2), (2, 3, 3))
+    assert rel(y.view(B, T, S // 2, S // 2, 64), ref.permute(0, 2, 3, 4, 1)) < BF16_TOL
+    dz = randn(B, T, (S // 2) ** 2, 64, seed=63, scale=0.1)
+    base = torch.randn(320, 64, device="cuda")
+    g_ref = ops.conv_taps_wgrad(P, dz, taps, out=base.clone())
+    g = ops.stem_wgrad_direct(v, dz, out=base.clone())
+    torch.cuda.synchronize()
+    assert rel(g - base, g_ref - base) < 2e-5
+    wt = torch.zeros(64, 1, 5, 7, 7, device="cuda", dtype=torch.float64, requires_grad=True)  # fp64: no TF32 in the reference
+    F.conv3d(v.bfloat16().double(), wt, None, (1, 2, 2), (2, 3, 3)).backward(
+        dz.double().view(B, T, S // 2, S // 2, 64).permute(0, 4, 1, 2, 3))
+    gw = (g - base).view(5, 8, 8, 64)[:, :7, :7].permute(3, 0, 1, 2)  # [co, kt, kh, kw]
+    assert rel(gw, wt.grad[:, 0]) < F32_TOL
+    pad = (g - base).view(5, 8, 8, 64)  # the padding slots (kh = 7, kw = 7) see zero operands
+    assert float(pad[:, 7].abs().max()) == 0.0 and float(pad[:, :, 7].abs().max()) == 0.0
+
+
+def test_stem_without_patch_tensor_refuses_uncovered_frames(ops):
+    from syncvsr_b200._lib import SvsrError
+
+    v = randn(1, 1, 4, 90, 90, seed=64, dtype=torch.float32)  # 45 x 45 output pixels: not a multiple of the 16-pixel tile
+    with pytest.raises(SvsrError):
+        ops.stem_conv_direct(v, torch.zeros(64, 320, device="cuda", dtype=torch.bfloat16))
+
+
 # ---------------------------------------------------------------- BatchNorm --------------------------------------
 @pytest.mark.parametrize("C,rows", [(64, 5000), (128, 1111), (256, 700), (512, 90)])
 def test_batchnorm_fwd_bwd(ops, C, rows):

@@ -571,6 +571,30 @@ def test_two_stream_backward_equals_single_stream_full_batch(Module, monkeypatch
     assert rel(grads[0], grads[1]) < 1e-4 and rel(grads[2], grads[1]) < 1e-4
 
 
+@pytest.mark.parametrize("S", [88, 96])
+def test_patch_free_stem_step_equals_patch_tensor_step(Module, monkeypatch, S):
+    """SVSR_STEM_DIRECT=1 (stem_direct.cu: no [clips, frames, pixels, 64] patch tensor, window rows built in shared
+    memory by the conv and weight-gradient kernels) against the patch-tensor path on a whole forward + backward: the
+    forward is bit-identical, gradients differ by the order of fp32 atomics only."""
+    meta = dict(B=3, S=S, A=4, G=2, V=320, depth=1, seed_p=21, seed_x=97, extra_tokens=0)
+    res = {}
+    for mode in ("0", "1", "0"):
+        monkeypatch.setenv("SVSR_STEM_DIRECT", mode)
+        m, P, (videos, tokens, labels, wm) = _native(Module, meta)
+        out = m(videos.cuda(), tokens.cuda(), labels.cuda(), wm.cuda())
+        out["loss_total"].backward()
+        torch.cuda.synchronize()
+        res.setdefault(mode, []).append((float(out["loss_total"]), m.last_hidden_state().clone(), m.flat_grads.clone(),
+                                         m._param_views["stem3d.0.weight"].grad.clone()))
+    (l0, h0, g0, s0), (l0b, _, g0b, s0b) = res["0"]
+    (l1, h1, g1, s1), = res["1"]
+    assert l1 == l0 and torch.equal(h1, h0)
+    noise = max(rel(g0b, g0), 1e-6)  # run-to-run difference of the patch path itself (atomics)
+    assert rel(g1, g0) < max(10 * noise, 1e-4), (rel(g1, g0), noise)
+    assert rel(s1, s0) < max(10 * rel(s0b, s0), 1e-4)
+    assert float(s1.norm()) > 0
+
+
 def test_huggingface_bert_encoder_variant(Module, golden_dir):
     """`model.bert.type: huggingface` (lightning.py:90-92,152-156): the encoder is transformers.BertModel. Forward is
     checked against the reference module's own outputs (golden), gradients against the oracle, which runs the
