@@ -33,7 +33,8 @@ constexpr int SD_SLOTS = SD_FT + 4;
 constexpr int SD_A_BYTES = SD_SLOTS * SD_PW * 128;  // 24 KB halo tile
 constexpr int SD_B_BYTES = 5 * 8192;                // resident weights (forward)
 constexpr int SD_DZ_BYTES = SD_FT * SD_PW * 128;    // 16 KB gradient tile (weight gradient)
-constexpr int SD_PRODUCERS = 128;
+constexpr int SD_FWD_PRODUCERS = 256;  // forward: eight producer warps
+constexpr int SD_WG_PRODUCERS = 128;   // weight gradient: the four drain warps produce during the main loop
 
 struct StemDirectParams {
   const uint32_t* vid;  // bf16 video as pixel pairs [N * T * H][W / 2]
@@ -44,31 +45,41 @@ struct StemDirectParams {
   int ldo;
 };
 
-// one producer thread's share (pixel ptid & 15, every eighth (slot, kh) pair) of the halo tile at sA
+// one producer thread's share (pixel ptid & 15, every (NPROD/16)-th (slot, kh) pair) of the halo tile at sA. All of the
+// thread's loads are issued before the first store: the producers run at the latency of ONE round trip to L2 per tile.
+template <int NPROD>
 __device__ __forceinline__ void build_patch_tile(uint8_t* sA, const StemDirectParams& p, int n, int t0, int w0, int ptid) {
+  constexpr int STEP = NPROD / 16, ITERS = (SD_SLOTS * 7 + STEP - 1) / STEP;
   const int px = ptid & 15;
   const int pix = w0 + px;
   const int oh = pix / p.OW, ow = pix - oh * p.OW;
   const int sw = px & 7;
   uint8_t* rowbase = sA + px * 128;
   const bool in_m2 = ow >= 2, in_m1 = ow >= 1, in_p1 = ow + 1 < p.W2;
-#pragma unroll 1
-  for (int rest = ptid >> 4; rest < SD_SLOTS * 7; rest += SD_PRODUCERS / 16) {
+  const uint32_t* clip = p.vid + (long long)n * p.T * p.H * p.W2 + ow;
+  uint32_t a[ITERS], b[ITERS], d[ITERS], e[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int rest = (ptid >> 4) + it * STEP;
     const int slot = rest / 7, kh = rest - slot * 7;
     const int t = t0 - 2 + slot, ih = 2 * oh + kh - 3;
-    uint4 c = make_uint4(0u, 0u, 0u, 0u);
-    if (t >= 0 && t < p.T && ih >= 0 && ih < p.H) {
-      const uint32_t* src = p.vid + ((long long)(n * p.T + t) * p.H + ih) * p.W2 + ow;
-      const uint32_t a = in_m2 ? __ldg(src - 2) : 0u;
-      const uint32_t b = in_m1 ? __ldg(src - 1) : 0u;
-      const uint32_t d = __ldg(src);
-      const uint32_t e = in_p1 ? __ldg(src + 1) : 0u;
-      c.x = __byte_perm(a, b, 0x5432);  // x[2ow-3], x[2ow-2]
-      c.y = __byte_perm(b, d, 0x5432);  // x[2ow-1], x[2ow]
-      c.z = __byte_perm(d, e, 0x5432);  // x[2ow+1], x[2ow+2]
-      c.w = e >> 16;                    // x[2ow+3], 0
-    }
-    *reinterpret_cast<uint4*>(rowbase + slot * (SD_PW * 128) + ((kh ^ sw) << 4)) = c;
+    const bool ok = rest < SD_SLOTS * 7 && t >= 0 && t < p.T && ih >= 0 && ih < p.H;
+    const uint32_t* src = clip + (long long)(t * p.H + ih) * p.W2;  // dereferenced only when ok
+    a[it] = (ok && in_m2) ? __ldg(src - 2) : 0u;
+    b[it] = (ok && in_m1) ? __ldg(src - 1) : 0u;
+    d[it] = ok ? __ldg(src) : 0u;
+    e[it] = (ok && in_p1) ? __ldg(src + 1) : 0u;
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int rest = (ptid >> 4) + it * STEP;
+    const int slot = rest / 7, kh = rest - slot * 7;
+    uint4 c;
+    c.x = __byte_perm(a[it], b[it], 0x5432);  // x[2ow-3], x[2ow-2]
+    c.y = __byte_perm(b[it], d[it], 0x5432);  // x[2ow-1], x[2ow]
+    c.z = __byte_perm(d[it], e[it], 0x5432);  // x[2ow+1], x[2ow+2]
+    c.w = e[it] >> 16;                        // x[2ow+3], 0
+    if (rest < SD_SLOTS * 7) *reinterpret_cast<uint4*>(rowbase + slot * (SD_PW * 128) + ((kh ^ sw) << 4)) = c;
   }
 }
 
@@ -82,7 +93,7 @@ __device__ __forceinline__ void clear_stages(uint8_t* base, int stage_stride, in
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward: y0[n, t, pixel, :] = sum_kt window(n, t + kt - 2, pixel) . Wm[:, kt*64 .. kt*64+64)^T  (+ BN statistics)
-// warps: 0 = weight load, 1 = MMA issue, 2..9 = epilogue (two warpgroups alternating tiles), 10..13 = producers
+// warps: 0 = weight load, 1 = MMA issue, 2..9 = epilogue (two warpgroups alternating tiles), 10..17 = producers
 // ---------------------------------------------------------------------------------------------------------------
 struct FwdSmem {
   static constexpr int B_OFFSET = 0;
@@ -95,7 +106,7 @@ struct FwdSmem {
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
 };
 
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(320 + SD_FWD_PRODUCERS, 1)
 conv_stem_direct_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                         const StemDirectParams p) {
   using L = FwdSmem;
@@ -119,7 +130,7 @@ conv_stem_direct_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < SD_STAGES; ++s) mbar_init(&full_bar[s], SD_PRODUCERS), mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < SD_STAGES; ++s) mbar_init(&full_bar[s], SD_FWD_PRODUCERS), mbar_init(&empty_bar[s], 1);
     for (int a = 0; a < 2; ++a) mbar_init(&tmem_full_bar[a], 1), mbar_init(&tmem_empty_bar[a], 4);
     mbar_init(b_bar, 1);
     fence_barrier_init();
@@ -177,7 +188,7 @@ conv_stem_direct_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_co
       const int n = tile / tiles_per_clip, rem = tile - n * tiles_per_clip;
       const int tt = rem / p.wtiles, wt = rem - tt * p.wtiles;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      build_patch_tile(sA + stage * SD_A_BYTES, p, n, tt * SD_FT, wt * SD_PW, ptid);
+      build_patch_tile<SD_FWD_PRODUCERS>(sA + stage * SD_A_BYTES, p, n, tt * SD_FT, wt * SD_PW, ptid);
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(&full_bar[stage]);
       if (++stage == SD_STAGES) stage = 0, phase ^= 1;
@@ -293,7 +304,7 @@ wgrad_stem_direct_kernel(const __grid_constant__ CUtensorMap tmDZ, const StemDir
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDZ);
     // a stage is full when the 128 producers have arrived and the gradient box's bytes have landed
-    for (int s = 0; s < SD_STAGES; ++s) mbar_init(&full_bar[s], SD_PRODUCERS + 1), mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < SD_STAGES; ++s) mbar_init(&full_bar[s], SD_WG_PRODUCERS + 1), mbar_init(&empty_bar[s], 1);
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -360,7 +371,7 @@ wgrad_stem_direct_kernel(const __grid_constant__ CUtensorMap tmDZ, const StemDir
         const int n = tile / tiles_per_clip, rem = tile - n * tiles_per_clip;
         const int tt = rem / p.wtiles, wt = rem - tt * p.wtiles;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        build_patch_tile(smem + stage * WD_STAGE_BYTES, p, n, tt * SD_FT, wt * SD_PW, ptid);
+        build_patch_tile<SD_WG_PRODUCERS>(smem + stage * WD_STAGE_BYTES, p, n, tt * SD_FT, wt * SD_PW, ptid);
         fence_proxy_async_smem();
         mbar_arrive(&full_bar[stage]);
         if (++stage == SD_STAGES) stage = 0, phase ^= 1;
@@ -443,7 +454,7 @@ int stem_direct_fwd(const void* video_bf16, const __nv_bfloat16* w_packed, __nv_
   }
   const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
   prof_begin(PROF_IGEMM, algo_flops > 0 ? algo_flops : 2.0 * B * T * (double)npix * 64.0 * 320.0, stream);
-  conv_stem_direct_kernel<<<grid, 448, FwdSmem::TOTAL, stream>>>(tmB, tmC, p);
+  conv_stem_direct_kernel<<<grid, 320 + SD_FWD_PRODUCERS, FwdSmem::TOTAL, stream>>>(tmB, tmC, p);
   note_launch();
   prof_end(stream);
   SVSR_CHECK_CUDA(cudaGetLastError());

@@ -44,5 +44,44 @@ def main():
                   f"{nbytes / us * 1e-3:7.1f} GB/s (distinct bytes)")
 
 
+def direct():
+    """The stem without the patch tensor (csrc/stem_direct.cu) against the patch tensor + halo kernels, launch by launch,
+    from the fp32 video: patch gather | bf16 cast, forward contraction, weight gradient. Buffers preallocated."""
+    import ctypes as C
+
+    from syncvsr_b200._lib import check, lib, ptr, stream_ptr
+
+    B, T, S = 64, 29, 88
+    npix = (S // 2) ** 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    v = torch.randn(B, 1, T, S, S, device="cuda", generator=g)
+    wp = (torch.randn(64, 320, device="cuda", generator=g) * 0.05).bfloat16()
+    dz = (torch.randn(B, T, npix, 64, device="cuda", generator=g) * 0.1).bfloat16()
+    P = torch.empty(B, T, npix, 64, device="cuda", dtype=torch.bfloat16)
+    vb = torch.empty(B, T, S, S, device="cuda", dtype=torch.bfloat16)
+    y = torch.empty(B, T, npix, 64, device="cuda", dtype=torch.bfloat16)
+    st = torch.zeros(2, 64, device="cuda", dtype=torch.float64)
+    out = torch.zeros(320, 64, device="cuda")
+    L, i = lib(), C.c_int
+    taps = [(kt - 2, 0) for kt in range(5)]
+    os.environ["SVSR_STEM_HALO"] = "1"
+    rows = [
+        ("patch gather (fp32 video -> 460 MB patch tensor)",
+         lambda: check(L.svsr_stem_patch(ptr(v), ptr(P), i(B), i(T), i(S), i(S), stream_ptr()), "patch")),
+        ("forward, patch tensor by TMA", lambda: ops.conv_taps_fprop_bnstats(P, wp, taps)),
+        ("weight gradient, patch tensor by TMA", lambda: ops.conv_taps_wgrad(P, dz, taps, out=out)),
+        ("bf16 copy of the video", lambda: vb.copy_(v.view(B, T, S, S))),
+        ("forward, window rows built in shared memory",
+         lambda: check(L.svsr_stem_conv_direct(ptr(vb), ptr(wp), ptr(y), ptr(st), i(B), i(T), i(S), i(S), stream_ptr()), "fwd")),
+        ("weight gradient, window rows built in shared memory",
+         lambda: check(L.svsr_stem_wgrad_direct(ptr(vb), ptr(dz), ptr(out), i(64), i(B), i(T), i(S), i(S), stream_ptr()), "wg")),
+    ]
+    for name, fn in rows:
+        print(f"{name:52s} {timeit(fn):8.1f} us")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "direct":
+        direct()
+    else:
+        main()
