@@ -118,8 +118,8 @@ struct Frontend {
   BnRef stem_bn;
   BlockRef blocks[8];
   size_t patches = 0, y0 = 0, x1 = 0, argmax = 0, gbuf[9] = {0}, stem_dz = 0;
-  // SVSR_STEM_DIRECT=1: no patch tensor -- the stem's forward and weight-gradient kernels build the 7x7/s2 window rows
-  // in shared memory from `vid`, a bf16 copy of the clip batch kept for backward (stem_direct.cu)
+  // No patch tensor (default; SVSR_STEM_DIRECT=0 restores it): the stem's forward and weight-gradient kernels build the
+  // 7x7/s2 window rows in shared memory from `vid`, a bf16 copy of the clip batch kept for backward (stem_direct.cu)
   bool direct = false;
   size_t vid = 0;
   size_t stats_arena = 0, stats_arena_bytes = 0;  // fp64 BN statistic accumulators (forward + backward slot per BN)
@@ -397,7 +397,7 @@ static void frontend_alloc(EngineBase& e, Frontend& f, Bump& b) {
   const size_t n0 = (size_t)e.N * f.H0 * f.H0 * 64;
   {
     const char* d = getenv("SVSR_STEM_DIRECT");
-    f.direct = d && d[0] == '1' && stem_direct_supported(f.H, f.H);
+    f.direct = !(d && d[0] == '0') && stem_direct_supported(f.H, f.H);
   }
   if (f.direct)
     f.vid = b.take((size_t)e.N * f.H * f.H * 2);

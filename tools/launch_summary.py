@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals for the LAST training
-step in the file (from the last stem_patch launch on) and, with --grids, per-grid-size detail."""
+step in the file (from the last stem launch -- stem_patch, or conv_stem_direct on the patch-free path -- on) and, with --grids, per-grid-size detail."""
 import collections
 import csv
 import re
@@ -23,7 +23,7 @@ def load(path):
 
 def main():
     recs = load(sys.argv[1])
-    idx = [i for i, r in enumerate(recs) if "stem_patch" in r[0]]
+    idx = [i for i, r in enumerate(recs) if "stem_patch" in r[0] or "conv_stem_direct" in r[0]]  # first stem launch of a step
     # the last COMPLETE step: a capture cut by `ncu -c N` ends inside a step, which shows as a shorter last segment
     segs = [recs[a:b] for a, b in zip(idx, idx[1:] + [len(recs)])]
     full = max(len(sg) for sg in segs)

@@ -18,7 +18,7 @@ def load(path):
             continue
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("svsr::", "").replace("<unnamed>::", "")
         recs.append((name, float(r["Metric Value"].replace(",", "")) / 1e3, r["Grid Size"]))
-    idx = [i for i, r in enumerate(recs) if "stem_patch" in r[0]]
+    idx = [i for i, r in enumerate(recs) if "stem_patch" in r[0] or "conv_stem_direct" in r[0]]  # first stem launch of a step
     segs = [recs[a:b] for a, b in zip(idx, idx[1:] + [len(recs)])]
     full = max(len(s) for s in segs)
     return [s for s in segs if len(s) == full][-1]
@@ -26,7 +26,7 @@ def load(path):
 
 def main():
     step = load(sys.argv[1])
-    fam = ("igemm_kernel", "conv3x3_c64_halo_kernel", "conv_t5_c64_halo_kernel")
+    fam = ("igemm_kernel", "conv3x3_c64_halo_kernel", "conv_t5_c64_halo_kernel", "conv_stem_direct_kernel")
     gemms = [r for r in step if r[0].startswith(fam)]
     N = 64 * 29
     layers = [("stem temporal conv 5 taps 64->64 (K 245 of 320)", 2.0 * N * 44 * 44 * 64 * 245)]

@@ -26,7 +26,7 @@ def main():
         elif r["Metric Name"] == "gpu__time_duration.sum":
             d["us"] = v / 1e3 if unit == "ns" else v * 1e3 if unit == "ms" else v
     ks = list(per_id.values())
-    idx = [i for i, k in enumerate(ks) if "stem_patch" in k["name"]]
+    idx = [i for i, k in enumerate(ks) if "stem_patch" in k["name"] or "conv_stem_direct" in k["name"]]  # first stem launch of a step
     # the last COMPLETE step: a capture cut by `ncu -c N` ends inside a step, which shows as a shorter last segment
     segs = [ks[a:b] for a, b in zip(idx, idx[1:] + [len(ks)])] if idx else [ks]
     full = max(len(sg) for sg in segs)
@@ -34,9 +34,9 @@ def main():
     fam = collections.defaultdict(lambda: {"launches": 0, "bytes": 0.0, "us": 0.0})
     for k in step:
         f = re.sub(r"<.*", "", k["name"]).strip()
-        if f in ("conv3x3_c64_halo_kernel", "conv_t5_c64_halo_kernel"):  # bench.py's PROF_IGEMM family
+        if f in ("conv3x3_c64_halo_kernel", "conv_t5_c64_halo_kernel", "conv_stem_direct_kernel"):  # bench.py's PROF_IGEMM family
             f = "igemm_kernel"
-        if f in ("wgrad3x3_c64_halo_kernel", "wgrad_t5_c64_halo_kernel"):  # bench.py's PROF_WGRAD family
+        if f in ("wgrad3x3_c64_halo_kernel", "wgrad_t5_c64_halo_kernel", "wgrad_stem_direct_kernel"):  # bench.py's PROF_WGRAD family
             f = "wgrad_kernel"
         fam[f]["launches"] += 1
         fam[f]["bytes"] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
