@@ -34,6 +34,6 @@ def test_launch_summary_and_layer_roofline_agree_on_the_step():
     rows = [l for l in table.splitlines() if l.startswith("| ") and "launch |" not in l]
     assert len(rows) == 1 + 19 + 6 + 1  # stem, 19 trunk convs, first and last encoder layer (to_out, ff1, ff2), total
     stem = next(l for l in rows if l.startswith("| stem"))
-    assert "conv_t5_c64_halo_kernel" in stem
+    assert "conv_stem_direct_kernel" in stem  # the patch-free stem forward (csrc/stem_direct.cu)
     total = [c.strip() for c in rows[-1].split("|")]
     assert 400 < float(total[6]) < 700  # forward GEMM launches: ~500 TFLOP/s under ncu
